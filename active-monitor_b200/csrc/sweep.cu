@@ -1,0 +1,520 @@
+// sweep.cu — the am_sweep handle and the C-ABI entry points of libamsweep.
+//
+// Owns one shard of the HealthCheck record array in HBM (16 SoA columns,
+// SURVEY.md Appendix B.1) on one CUDA device, the staging area for
+// upsert / remove / post_result calls coming from the controller's goroutines
+// (hcc.go:170-188 Reconcile workers, hcc.go:635/:662/:821/:836 watch loops),
+// and the launch of the sweep kernel (sweep_kernels.cuh) that replaces the
+// per-CR schedule ladder and remedy state machine for every record at once.
+//
+// There is deliberately no CPU path in this file: without a CUDA device
+// am_sweep_create fails with AM_E_DEVICE.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "sweep_kernels.cuh"
+
+using namespace amsweep;
+
+namespace {
+thread_local std::string g_create_error;
+
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 2 + 4096;
+    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 2 + 4096;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+}  // namespace
+
+struct am_sweep {
+  int device = 0;
+  uint64_t capacity = 0, cap_padded = 0, shard_base = 0;
+  uint64_t n_records = 0;  // high-water mark
+  DevCols cols{};
+  void* col_ptr[16] = {};
+  size_t col_elem[16] = {};
+  unsigned long long* tile_desc = nullptr;
+  unsigned long long* acc = nullptr;
+  uint32_t* done = nullptr;
+  uint32_t epoch = 0;
+  uint32_t* due_idx[2] = {nullptr, nullptr};
+  uint8_t* due_action[2] = {nullptr, nullptr};
+  am_tick_stats_t* h_stats = nullptr;  // pinned + mapped
+  am_tick_stats_t* d_stats_mapped = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::mutex mu;  // guards the staged vectors
+  std::atomic_flag ticking = ATOMIC_FLAG_INIT;
+  std::vector<uint32_t> up_idx;
+  std::vector<am_record_t> up_rec;
+  std::vector<uint32_t> rm_idx;
+  std::vector<uint32_t> res_idx, res_bits;
+  PinnedBuf pin_in, pin_out;
+  DevBuf dev_in;
+  std::string last_error;
+  uint64_t launches = 0;
+  double last_ms = -1.0;
+  uint64_t seed = 0;
+};
+
+namespace {
+
+#define AM_CUDA(h, expr)                                                              \
+  do {                                                                                \
+    cudaError_t _e = (expr);                                                          \
+    if (_e != cudaSuccess) {                                                          \
+      char _b[512];                                                                   \
+      snprintf(_b, sizeof _b, "%s -> %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      if (h) (h)->last_error = _b; else g_create_error = _b;                          \
+      return _e == cudaErrorMemoryAllocation ? AM_E_NOMEM : AM_E_DEVICE;              \
+    }                                                                                 \
+  } while (0)
+
+constexpr size_t kColElem[16] = {8, 8, 8, 8, 8, 4, 4, 8, 4, 4, 4, 4, 4, 4, 4, 8};
+
+void** col_slot(DevCols& c, int k) {
+  void** slots[16] = {(void**)&c.minute,         (void**)&c.hour,          (void**)&c.dom,
+                      (void**)&c.month,          (void**)&c.dow,           (void**)&c.ras,
+                      (void**)&c.flags,          (void**)&c.finished_at,   (void**)&c.runs_limit,
+                      (void**)&c.reset_interval, (void**)&c.success,       (void**)&c.failed,
+                      (void**)&c.remedy_success, (void**)&c.remedy_failed, (void**)&c.remedy_total,
+                      (void**)&c.remedy_finished_at};
+  return slots[k];
+}
+void* const* cols_member(const am_record_cols_t* c, int k) {
+  void* const* slots[16] = {(void* const*)&c->minute,         (void* const*)&c->hour,
+                            (void* const*)&c->dom,            (void* const*)&c->month,
+                            (void* const*)&c->dow,            (void* const*)&c->ras,
+                            (void* const*)&c->flags,          (void* const*)&c->finished_at,
+                            (void* const*)&c->runs_limit,     (void* const*)&c->reset_interval,
+                            (void* const*)&c->success,        (void* const*)&c->failed,
+                            (void* const*)&c->remedy_success, (void* const*)&c->remedy_failed,
+                            (void* const*)&c->remedy_total,   (void* const*)&c->remedy_finished_at};
+  return slots[k];
+}
+
+struct TickGuard {
+  am_sweep* h;
+  bool ok;
+  explicit TickGuard(am_sweep* hh) : h(hh), ok(!hh->ticking.test_and_set(std::memory_order_acquire)) {}
+  ~TickGuard() { if (ok) h->ticking.clear(std::memory_order_release); }
+};
+
+// Apply staged upserts / removes / results (called with the tick guard held).
+int drain_staged(am_sweep* h) {
+  std::vector<uint32_t> up_idx, rm_idx, res_idx, res_bits;
+  std::vector<am_record_t> up_rec;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    up_idx.swap(h->up_idx); up_rec.swap(h->up_rec); rm_idx.swap(h->rm_idx);
+    res_idx.swap(h->res_idx); res_bits.swap(h->res_bits);
+  }
+  const size_t nu = up_idx.size(), nr = rm_idx.size(), np = res_idx.size();
+  if (nu + nr + np == 0) return AM_OK;
+  for (uint32_t i : up_idx)  // upserts extend the swept range (high-water mark)
+    if ((uint64_t)i + 1 > h->n_records) h->n_records = (uint64_t)i + 1;
+  // layout of the staging block: [up_rec][up_idx][rm_idx][res_idx][res_bits]
+  size_t o_rec = 0, o_ui = o_rec + nu * sizeof(am_record_t), o_rm = o_ui + nu * 4,
+         o_ri = o_rm + nr * 4, o_rb = o_ri + np * 4, total = o_rb + np * 4;
+  AM_CUDA(h, h->pin_in.reserve(total));
+  AM_CUDA(h, h->dev_in.reserve(total));
+  char* hp = (char*)h->pin_in.p;
+  if (nu) { memcpy(hp + o_rec, up_rec.data(), nu * sizeof(am_record_t)); memcpy(hp + o_ui, up_idx.data(), nu * 4); }
+  if (nr) memcpy(hp + o_rm, rm_idx.data(), nr * 4);
+  if (np) { memcpy(hp + o_ri, res_idx.data(), np * 4); memcpy(hp + o_rb, res_bits.data(), np * 4); }
+  AM_CUDA(h, cudaMemcpyAsync(h->dev_in.p, hp, total, cudaMemcpyHostToDevice, h->stream));
+  char* dp = (char*)h->dev_in.p;
+  const int B = 256;
+  // order: removes, then upserts (a delete + re-create in one tick keeps the new CR), then results
+  if (nr) {
+    tombstone_kernel<<<(unsigned)((nr + B - 1) / B), B, 0, h->stream>>>(h->cols.flags, (const uint32_t*)(dp + o_rm), (uint32_t)nr);
+    h->launches++;
+  }
+  if (nu) {
+    scatter_records_kernel<<<(unsigned)((nu + B - 1) / B), B, 0, h->stream>>>(
+        h->cols, (const uint32_t*)(dp + o_ui), (const am_record_t*)(dp + o_rec), (uint32_t)nu);
+    h->launches++;
+  }
+  if (np) {
+    post_result_kernel<<<(unsigned)((np + B - 1) / B), B, 0, h->stream>>>(
+        h->cols.flags, (const uint32_t*)(dp + o_ri), (const uint32_t*)(dp + o_rb), (uint32_t)np);
+    h->launches++;
+  }
+  AM_CUDA(h, cudaGetLastError());
+  // the staging block is reused by the next drain: wait until the copy was consumed
+  AM_CUDA(h, cudaStreamSynchronize(h->stream));
+  return AM_OK;
+}
+
+int launch_sweep(am_sweep* h, int64_t T, uint32_t mode, uint32_t* d_idx, uint8_t* d_act, uint64_t cap,
+                 am_tick_stats_t* out_stats, uint32_t* out_count, cudaStream_t s) {
+  if (h->n_records == 0) {
+    // nothing to sweep: publish zeros without a launch
+    if (out_stats) AM_CUDA(h, cudaMemsetAsync(out_stats, 0, sizeof(am_tick_stats_t), s));
+    if (out_count) AM_CUDA(h, cudaMemsetAsync(out_count, 0, 4, s));
+    return AM_OK;
+  }
+  SweepParams p{};
+  p.c = h->cols;
+  p.n_records = h->n_records;
+  p.shard_base = h->shard_base;
+  p.seed = h->seed;
+  p.T = T;
+  p.n_tiles = (uint32_t)((h->n_records + kTile - 1) / kTile);
+  p.mode = mode;
+  p.cap = (uint32_t)(cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : cap);
+  h->epoch = (h->epoch + 1) & 0x3FFFFFFFu;
+  if (h->epoch == 0) {  // 30-bit stamp wrapped: clear descriptors once
+    AM_CUDA(h, cudaMemsetAsync(h->tile_desc, 0, (h->cap_padded / kTile) * 8, s));
+    h->epoch = 1;
+  }
+  p.epoch = h->epoch;
+  p.due_idx = d_idx;
+  p.due_action = d_act;
+  p.tile_desc = h->tile_desc;
+  p.acc = h->acc;
+  p.done = h->done;
+  p.out_stats = out_stats;
+  p.out_count = out_count;
+  if (mode & AM_SWEEP_CLOSED_LOOP) sweep_tick_kernel<true><<<p.n_tiles, kBlock, 0, s>>>(p);
+  else sweep_tick_kernel<false><<<p.n_tiles, kBlock, 0, s>>>(p);
+  h->launches++;
+  AM_CUDA(h, cudaGetLastError());
+  return AM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* am_last_error_detail(const am_sweep_t* h) {
+  return h ? h->last_error.c_str() : g_create_error.c_str();
+}
+
+int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t shard_base) {
+  if (!out || capacity == 0 || capacity > 0xFFFFF000ull) return AM_E_INVAL;
+  *out = nullptr;
+  am_sweep* none = nullptr;
+  int ndev = 0;
+  AM_CUDA(none, cudaGetDeviceCount(&ndev));
+  if (device_id < 0 || device_id >= ndev) {
+    g_create_error = "no such CUDA device";
+    return AM_E_DEVICE;
+  }
+  AM_CUDA(none, cudaSetDevice(device_id));
+  am_sweep* h = new (std::nothrow) am_sweep();
+  if (!h) return AM_E_NOMEM;
+  h->device = device_id;
+  h->capacity = capacity;
+  h->cap_padded = (capacity + kTile - 1) / kTile * kTile;
+  h->shard_base = shard_base;
+  int rc = [&]() -> int {
+    AM_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    AM_CUDA(h, cudaEventCreate(&h->ev0));
+    AM_CUDA(h, cudaEventCreate(&h->ev1));
+    for (int k = 0; k < 16; ++k) {
+      void* p = nullptr;
+      AM_CUDA(h, cudaMalloc(&p, h->cap_padded * kColElem[k]));
+      AM_CUDA(h, cudaMemsetAsync(p, 0, h->cap_padded * kColElem[k], h->stream));
+      *col_slot(h->cols, k) = p;
+      h->col_ptr[k] = p;
+      h->col_elem[k] = kColElem[k];
+    }
+    fill_u32_kernel<<<1184, 256, 0, h->stream>>>(h->cols.flags, AM_F_TOMBSTONE, h->cap_padded);
+    h->launches++;
+    const size_t ntiles = h->cap_padded / kTile;
+    AM_CUDA(h, cudaMalloc((void**)&h->tile_desc, ntiles * 8));
+    AM_CUDA(h, cudaMemsetAsync(h->tile_desc, 0, ntiles * 8, h->stream));
+    AM_CUDA(h, cudaMalloc((void**)&h->acc, kNumAcc * 8));
+    AM_CUDA(h, cudaMemsetAsync(h->acc, 0, kNumAcc * 8, h->stream));
+    AM_CUDA(h, cudaMalloc((void**)&h->done, 4));
+    AM_CUDA(h, cudaMemsetAsync(h->done, 0, 4, h->stream));
+    for (int b = 0; b < 2; ++b) {
+      AM_CUDA(h, cudaMalloc((void**)&h->due_idx[b], h->cap_padded * 4));
+      AM_CUDA(h, cudaMalloc((void**)&h->due_action[b], h->cap_padded));
+    }
+    AM_CUDA(h, cudaHostAlloc((void**)&h->h_stats, sizeof(am_tick_stats_t), cudaHostAllocMapped));
+    memset(h->h_stats, 0, sizeof(am_tick_stats_t));
+    AM_CUDA(h, cudaHostGetDevicePointer((void**)&h->d_stats_mapped, h->h_stats, 0));
+    AM_CUDA(h, cudaGetLastError());
+    AM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return AM_OK;
+  }();
+  if (rc != AM_OK) {
+    g_create_error = h->last_error;
+    am_sweep_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return AM_OK;
+}
+
+void am_sweep_destroy(am_sweep_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (int k = 0; k < 16; ++k) if (h->col_ptr[k]) cudaFree(h->col_ptr[k]);
+  if (h->tile_desc) cudaFree(h->tile_desc);
+  if (h->acc) cudaFree(h->acc);
+  if (h->done) cudaFree(h->done);
+  for (int b = 0; b < 2; ++b) {
+    if (h->due_idx[b]) cudaFree(h->due_idx[b]);
+    if (h->due_action[b]) cudaFree(h->due_action[b]);
+  }
+  if (h->h_stats) cudaFreeHost(h->h_stats);
+  h->pin_in.release(); h->pin_out.release(); h->dev_in.release();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+uint64_t am_sweep_size(const am_sweep_t* h) { return h ? h->n_records : 0; }
+uint64_t am_sweep_capacity(const am_sweep_t* h) { return h ? h->capacity : 0; }
+int am_sweep_device(const am_sweep_t* h) { return h ? h->device : -1; }
+double am_sweep_last_kernel_ms(const am_sweep_t* h) { return h ? h->last_ms : -1.0; }
+uint64_t am_sweep_launch_count(const am_sweep_t* h) { return h ? h->launches : 0; }
+void* am_sweep_column_ptr(am_sweep_t* h, int column) {
+  return (h && column >= 0 && column < 16) ? h->col_ptr[column] : nullptr;
+}
+int am_sweep_set_seed(am_sweep_t* h, uint64_t seed) {
+  if (!h) return AM_E_INVAL;
+  h->seed = seed;
+  return AM_OK;
+}
+
+int am_sweep_load_range(am_sweep_t* h, uint64_t first, uint64_t n, const am_record_cols_t* cols) {
+  if (!h || !cols || first + n > h->capacity || first + n < first) return AM_E_INVAL;
+  if (n == 0) return AM_OK;
+  TickGuard g(h);
+  if (!g.ok) return AM_E_BUSY;
+  AM_CUDA(h, cudaSetDevice(h->device));
+  for (int k = 0; k < 16; ++k) {
+    char* dst = (char*)h->col_ptr[k] + first * kColElem[k];
+    const void* src = *cols_member(cols, k);
+    if (src) AM_CUDA(h, cudaMemcpyAsync(dst, src, n * kColElem[k], cudaMemcpyHostToDevice, h->stream));
+    else AM_CUDA(h, cudaMemsetAsync(dst, 0, n * kColElem[k], h->stream));
+  }
+  AM_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (first + n > h->n_records) h->n_records = first + n;
+  return AM_OK;
+}
+
+int am_sweep_upsert(am_sweep_t* h, uint64_t n, const uint64_t* idx, const am_record_t* recs) {
+  if (!h || (n && (!idx || !recs))) return AM_E_INVAL;
+  for (uint64_t k = 0; k < n; ++k)
+    if (idx[k] >= h->capacity) return AM_E_RANGE;
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (uint64_t k = 0; k < n; ++k) {
+    h->up_idx.push_back((uint32_t)idx[k]);
+    am_record_t r = recs[k];
+    r.flags &= ~AM_F_TOMBSTONE;
+    r.reserved = 0;
+    h->up_rec.push_back(r);
+  }
+  return AM_OK;
+}
+
+int am_sweep_remove(am_sweep_t* h, uint64_t n, const uint64_t* idx) {
+  if (!h || (n && !idx)) return AM_E_INVAL;
+  for (uint64_t k = 0; k < n; ++k)
+    if (idx[k] >= h->capacity) return AM_E_RANGE;
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (uint64_t k = 0; k < n; ++k) h->rm_idx.push_back((uint32_t)idx[k]);
+  return AM_OK;
+}
+
+int am_sweep_post_result(am_sweep_t* h, uint64_t n, const uint64_t* idx, const uint8_t* phase,
+                         const uint8_t* remedy_phase) {
+  if (!h || (n && (!idx || !phase))) return AM_E_INVAL;
+  for (uint64_t k = 0; k < n; ++k) {
+    if (idx[k] >= h->capacity) return AM_E_RANGE;
+    if (phase[k] > AM_PHASE_FAILED || (remedy_phase && remedy_phase[k] > AM_PHASE_FAILED)) return AM_E_INVAL;
+  }
+  std::lock_guard<std::mutex> lk(h->mu);
+  for (uint64_t k = 0; k < n; ++k) {
+    uint32_t bits = 0;
+    if (phase[k] == AM_PHASE_SUCCEEDED) bits |= AM_F_PENDING_OK;
+    else if (phase[k] == AM_PHASE_FAILED) bits |= AM_F_PENDING_FAIL;
+    const uint8_t rp = remedy_phase ? remedy_phase[k] : AM_PHASE_NONE;
+    if (rp != AM_PHASE_NONE) bits |= AM_F_REMEDY_PENDING | (rp == AM_PHASE_SUCCEEDED ? AM_F_REMEDY_OUTCOME_OK : 0u);
+    h->res_idx.push_back((uint32_t)idx[k]);
+    h->res_bits.push_back(bits);
+  }
+  return AM_OK;
+}
+
+int am_sweep_tick(am_sweep_t* h, int64_t unix_sec, uint32_t mode, uint64_t* due_idx,
+                  uint32_t* due_action, uint64_t cap, uint64_t* n_out, am_tick_stats_t* stats) {
+  if (!h || (cap && (!due_idx || !due_action))) return AM_E_INVAL;
+  if (unix_sec >= (1ll << 55) || unix_sec <= -(1ll << 55)) return AM_E_RANGE;
+  TickGuard g(h);
+  if (!g.ok) return AM_E_BUSY;
+  AM_CUDA(h, cudaSetDevice(h->device));
+  int rc = drain_staged(h);
+  if (rc != AM_OK) return rc;
+  AM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  rc = launch_sweep(h, unix_sec, mode, h->due_idx[0], h->due_action[0], h->cap_padded,
+                    h->d_stats_mapped, nullptr, h->stream);
+  if (rc != AM_OK) return rc;
+  AM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  AM_CUDA(h, cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  AM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_ms = ms;
+  am_tick_stats_t st = *h->h_stats;
+  st.n_records = h->n_records;
+  if (stats) *stats = st;
+  const uint64_t n = st.n_emitted;
+  if (n_out) *n_out = n;
+  const uint64_t ncopy = n < cap ? n : cap;
+  if (ncopy) {
+    AM_CUDA(h, h->pin_out.reserve(ncopy * 5));
+    uint32_t* hi = (uint32_t*)h->pin_out.p;
+    uint8_t* ha = (uint8_t*)h->pin_out.p + ncopy * 4;
+    AM_CUDA(h, cudaMemcpyAsync(hi, h->due_idx[0], ncopy * 4, cudaMemcpyDeviceToHost, h->stream));
+    AM_CUDA(h, cudaMemcpyAsync(ha, h->due_action[0], ncopy, cudaMemcpyDeviceToHost, h->stream));
+    AM_CUDA(h, cudaStreamSynchronize(h->stream));
+    const uint64_t base = h->shard_base;
+    for (uint64_t k = 0; k < ncopy; ++k) {  // widen into the caller's (Go) memory
+      due_idx[k] = base + hi[k];
+      due_action[k] = ha[k];
+    }
+  }
+  return n > cap ? AM_E_NOSPACE : AM_OK;
+}
+
+int am_sweep_tick_device(am_sweep_t* h, int64_t unix_sec, uint32_t mode, void* d_due_idx,
+                         void* d_due_action, uint64_t cap, void* d_count, void* d_stats,
+                         void* cuda_stream) {
+  if (!h || (cap && (!d_due_idx || !d_due_action))) return AM_E_INVAL;
+  if (unix_sec >= (1ll << 55) || unix_sec <= -(1ll << 55)) return AM_E_RANGE;
+  TickGuard g(h);
+  if (!g.ok) return AM_E_BUSY;
+  AM_CUDA(h, cudaSetDevice(h->device));
+  int rc = drain_staged(h);
+  if (rc != AM_OK) return rc;
+  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  return launch_sweep(h, unix_sec, mode, (uint32_t*)d_due_idx, (uint8_t*)d_due_action, cap,
+                      (am_tick_stats_t*)d_stats, (uint32_t*)d_count, s);
+}
+
+int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint32_t mode,
+                       uint64_t seed, am_tick_stats_t* stats_out) {
+  if (!h || !stats_out) return AM_E_INVAL;
+  if (n_ticks == 0) return AM_OK;
+  if (n_ticks > (1ull << 24)) return AM_E_INVAL;
+  if (unix_sec0 >= (1ll << 55) - (int64_t)n_ticks || unix_sec0 <= -(1ll << 55)) return AM_E_RANGE;
+  TickGuard g(h);
+  if (!g.ok) return AM_E_BUSY;
+  AM_CUDA(h, cudaSetDevice(h->device));
+  int rc = drain_staged(h);
+  if (rc != AM_OK) return rc;
+  h->seed = seed;
+  am_tick_stats_t* d_stats = nullptr;
+  AM_CUDA(h, cudaMalloc((void**)&d_stats, n_ticks * sizeof(am_tick_stats_t)));
+  AM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  for (uint64_t k = 0; k < n_ticks && rc == AM_OK; ++k) {
+    rc = launch_sweep(h, unix_sec0 + (int64_t)k, mode, h->due_idx[k & 1], h->due_action[k & 1],
+                      h->cap_padded, d_stats + k, nullptr, h->stream);
+  }
+  if (rc == AM_OK) {
+    cudaError_t e = cudaEventRecord(h->ev1, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(stats_out, d_stats, n_ticks * sizeof(am_tick_stats_t), cudaMemcpyDeviceToHost);
+    float ms = 0;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    if (e != cudaSuccess) { h->last_error = cudaGetErrorString(e); rc = AM_E_DEVICE; }
+    else h->last_ms = ms;
+  }
+  cudaFree(d_stats);
+  return rc;
+}
+
+int am_sweep_read(am_sweep_t* h, uint64_t first, uint64_t n, const uint64_t* idx,
+                  am_record_cols_t* out) {
+  if (!h || !out) return AM_E_INVAL;
+  if (n == 0) return AM_OK;
+  TickGuard g(h);
+  if (!g.ok) return AM_E_BUSY;
+  AM_CUDA(h, cudaSetDevice(h->device));
+  if (!idx) {
+    if (first + n > h->capacity || first + n < first) return AM_E_INVAL;
+    for (int k = 0; k < 16; ++k) {
+      void* dst = *cols_member(out, k);
+      if (!dst) continue;
+      AM_CUDA(h, cudaMemcpyAsync(dst, (char*)h->col_ptr[k] + first * kColElem[k], n * kColElem[k],
+                                 cudaMemcpyDeviceToHost, h->stream));
+    }
+    AM_CUDA(h, cudaStreamSynchronize(h->stream));
+    return AM_OK;
+  }
+  if (n > 0xFFFFFFFFull) return AM_E_INVAL;
+  for (uint64_t k = 0; k < n; ++k)
+    if (idx[k] >= h->capacity) return AM_E_RANGE;
+  const size_t o_idx = n * sizeof(am_record_t), total = o_idx + n * 4;
+  AM_CUDA(h, h->pin_in.reserve(total));
+  AM_CUDA(h, h->dev_in.reserve(total));
+  uint32_t* hidx = (uint32_t*)((char*)h->pin_in.p + o_idx);
+  for (uint64_t k = 0; k < n; ++k) hidx[k] = (uint32_t)idx[k];
+  char* dp = (char*)h->dev_in.p;
+  AM_CUDA(h, cudaMemcpyAsync(dp + o_idx, hidx, n * 4, cudaMemcpyHostToDevice, h->stream));
+  gather_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
+      h->cols, (const uint32_t*)(dp + o_idx), (am_record_t*)dp, (uint32_t)n);
+  h->launches++;
+  AM_CUDA(h, cudaGetLastError());
+  AM_CUDA(h, cudaMemcpyAsync(h->pin_in.p, dp, n * sizeof(am_record_t), cudaMemcpyDeviceToHost, h->stream));
+  AM_CUDA(h, cudaStreamSynchronize(h->stream));
+  const am_record_t* r = (const am_record_t*)h->pin_in.p;
+  for (uint64_t k = 0; k < n; ++k) {
+    if (out->minute) out->minute[k] = r[k].minute;
+    if (out->hour) out->hour[k] = r[k].hour;
+    if (out->dom) out->dom[k] = r[k].dom;
+    if (out->month) out->month[k] = r[k].month;
+    if (out->dow) out->dow[k] = r[k].dow;
+    if (out->ras) out->ras[k] = r[k].ras;
+    if (out->flags) out->flags[k] = r[k].flags;
+    if (out->finished_at) out->finished_at[k] = r[k].finished_at;
+    if (out->runs_limit) out->runs_limit[k] = r[k].runs_limit;
+    if (out->reset_interval) out->reset_interval[k] = r[k].reset_interval;
+    if (out->success) out->success[k] = r[k].success;
+    if (out->failed) out->failed[k] = r[k].failed;
+    if (out->remedy_success) out->remedy_success[k] = r[k].remedy_success;
+    if (out->remedy_failed) out->remedy_failed[k] = r[k].remedy_failed;
+    if (out->remedy_total) out->remedy_total[k] = r[k].remedy_total;
+    if (out->remedy_finished_at) out->remedy_finished_at[k] = r[k].remedy_finished_at;
+  }
+  return AM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,546 @@
+// sweep_kernels.cuh — the per-tick schedule-evaluation sweep for sm_100a.
+//
+// One launch evaluates every HealthCheck record of a shard at one wall-clock
+// second T.  It replaces, for N records at once, the
+// per-CR decisions of the reference controller (hcc.go = internal/controllers/
+// healthcheck_controller.go):
+//     hcc.go:227        Workflow.Resource == nil      -> record skipped
+//     hcc.go:238-250    pause rule                    -> AM_ACT_STOPPED
+//     hcc.go:251-263    cron arm (robfig bitmasks)    -> matches(T), A.7
+//     hcc.go:264, :751  interval / timer              -> T - finishedAt >= ras
+//     hcc.go:635-661    Succeeded transition          -> apply_result()
+//     hcc.go:662-722    Failed transition + remedy gate
+//     hcc.go:821-851    remedy result counters
+//
+// Shape of the kernel (pure integer work, HBM-bandwidth bound, no tensor cores):
+//   * records live as SoA columns in HBM; a CTA of 256 threads owns one tile of
+//     1024 consecutive records, a warp owns 128 of them;
+//   * every warp-level load instruction is fully coalesced: lane L reads the
+//     16 B (two u64 records) or 8 B (two i32 records) at column + (w + 2L),
+//     twice per tile ("halves"), so 16 independent loads are in flight per
+//     lane before the first use;
+//   * the tick's broken-down time is computed once per CTA and staged in
+//     shared memory as one-hot words; a 5-field schedule fires iff
+//     minute&M && hour&H && month&Mo && dayMatches (five ANDs, no loop);
+//   * remedy/counter columns are touched only by lanes whose record has a
+//     posted result (or is due, in closed-loop mode): 56 B/record otherwise;
+//   * emitted (index, action) pairs are compacted IN ORDER: warp ballots +
+//     popc give the in-warp rank, a CTA scan the in-tile rank, and a
+//     decoupled look-back over per-tile descriptors the global rank, all in
+//     one pass over the data;
+//   * per-tick statistics are reduced warp -> CTA -> global; the last CTA to
+//     finish publishes them and re-arms the accumulators, so a tick is exactly
+//     one kernel launch with no memsets.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/amsweep.h"
+#include "civil.h"
+
+namespace amsweep {
+
+constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
+constexpr int kRecPerWarp = 128;             // 2 halves x 32 lanes x 2 records
+constexpr int kTile = kWarps * kRecPerWarp;  // 1024 records per CTA
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kNumAcc = 16;  // == number of u64 fields of am_tick_stats_t
+
+struct DevCols {
+  uint64_t *minute, *hour, *dom, *month, *dow;
+  int32_t* ras;
+  uint32_t* flags;
+  int64_t* finished_at;
+  int32_t *runs_limit, *reset_interval;
+  int32_t *success, *failed, *remedy_success, *remedy_failed, *remedy_total;
+  int64_t* remedy_finished_at;
+};
+
+struct SweepParams {
+  DevCols c;
+  uint64_t n_records;
+  uint64_t shard_base;
+  uint64_t seed;
+  int64_t T;
+  uint32_t n_tiles;
+  uint32_t mode;
+  uint32_t cap;    // entries in due_idx / due_action
+  uint32_t epoch;  // 30-bit launch stamp of the tile descriptors
+  uint32_t* due_idx;
+  uint8_t* due_action;
+  unsigned long long* tile_desc;  // [n_tiles] {epoch:30, status:2, count:32}
+  unsigned long long* acc;        // [kNumAcc] cross-CTA accumulators (self re-arming)
+  uint32_t* done;                 // CTA completion ticket
+  am_tick_stats_t* out_stats;     // device or mapped-host; may be null
+  uint32_t* out_count;            // may be null
+};
+
+// ---- streaming loads / stores: every byte is touched once per tick --------
+template <typename T>
+__device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
+template <typename T>
+__device__ __forceinline__ void st_stream(T* p, T v) { __stcs(p, v); }
+
+__device__ __forceinline__ uint64_t sm64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ uint64_t outcome_key(uint64_t seed, uint64_t gidx, uint64_t t) {
+  return sm64(sm64(seed ^ sm64(gidx)) + t);
+}
+
+// bit i of a 4-bit value -> byte i of a word (0/1 each)
+__device__ __forceinline__ uint32_t spread4(uint32_t v) { return ((v & 0xFu) * 0x00204081u) & 0x01010101u; }
+
+// Mutable per-record state carried through the result state machine.
+struct RecState {
+  uint32_t flags;
+  int64_t fa;       // finishedAt
+  int32_t s, f;     // SuccessCount, FailedCount
+  int32_t rs, rf, rt;  // RemedySuccessCount, RemedyFailedCount, RemedyTotalRuns
+  int64_t rfa;      // RemedyFinishedAt, 0 == nil
+  int32_t limit, reset;
+};
+
+// watchRemedyWorkflow result, hcc.go:821-851
+__device__ __forceinline__ void remedy_result(RecState& r, int64_t T, bool ok, uint32_t& res) {
+  if (ok) { r.rs = (int32_t)((uint32_t)r.rs + 1u); res += 1u << 16; }
+  else    { r.rf = (int32_t)((uint32_t)r.rf + 1u); res += 1u << 24; }
+  r.rt = (int32_t)((uint32_t)r.rs + (uint32_t)r.rf);
+  r.rfa = T;
+}
+
+// Step 1 of B.3: apply a posted workflow result.  Returns action bits; `res`
+// counts {ok, fail, remedy_ok, remedy_fail} in its four bytes (a record can
+// take two results in one closed-loop tick) for the metrics counters.
+__device__ __forceinline__ uint32_t apply_result(RecState& r, int64_t T, uint32_t& res) {
+  uint32_t act = 0;
+  const uint32_t f = r.flags;
+  if (f & AM_F_PENDING_OK) {  // hcc.go:635-661
+    r.s = (int32_t)((uint32_t)r.s + 1u);
+    r.fa = T;
+    res += 1u;
+    if ((f & AM_F_HAS_REMEDY) && r.rt >= 1) {  // :649
+      r.rt = r.rs = r.rf = 0;
+      r.rfa = 0;
+      act |= AM_ACT_RESET_ON_PASS;
+    }
+  } else if (f & AM_F_PENDING_FAIL) {  // hcc.go:662-722
+    r.f = (int32_t)((uint32_t)r.f + 1u);
+    r.fa = T;
+    res += 1u << 8;
+    if (f & AM_F_HAS_REMEDY) {  // :677
+      bool run = false;
+      if (r.limit != 0 && r.reset != 0) {  // :679
+        if (r.limit > r.rt) {               // :681
+          run = true;
+        } else if (r.rfa == 0) {
+          act |= AM_ACT_ANOMALY;  // nil RemedyFinishedAt at :690 (N3)
+        } else {
+          // int(now.Sub(RemedyFinishedAt).Seconds()): Sub saturates at
+          // +-9223372036 s, far outside the i32 resetInterval domain
+          int64_t d = (int64_t)((uint64_t)T - (uint64_t)r.rfa);
+          d = d > 9223372036ll ? 9223372036ll : (d < -9223372036ll ? -9223372036ll : d);
+          if ((int64_t)r.reset >= d) {  // :692
+            act |= AM_ACT_REMEDY_SKIP;
+          } else {  // :695-704
+            r.rt = r.rs = r.rf = 0;
+            r.rfa = 0;
+            act |= AM_ACT_RESET_ON_INTERVAL;
+            run = true;
+          }
+        }
+      } else {  // :712-719
+        run = true;
+      }
+      if (run) {
+        act |= AM_ACT_RUN_REMEDY;
+        if (f & AM_F_REMEDY_PENDING) remedy_result(r, T, (f & AM_F_REMEDY_OUTCOME_OK) != 0, res);
+      }
+    }
+  } else if (f & AM_F_REMEDY_PENDING) {  // remedy finished on its own
+    remedy_result(r, T, (f & AM_F_REMEDY_OUTCOME_OK) != 0, res);
+  }
+  r.flags = f & ~(AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK);
+  return act;
+}
+
+// Decoupled look-back over tile descriptors; executed by warp 0 of the CTA.
+// Descriptor = {epoch:30 | status:2}{count:32}; status 1 = tile aggregate,
+// 2 = inclusive prefix.  A stale epoch reads as "not written yet", so the
+// array never needs clearing between launches.
+__device__ __forceinline__ uint32_t tile_lookback(unsigned long long* desc, uint32_t tile,
+                                                  uint32_t epoch, uint32_t agg, int lane) {
+  const unsigned long long tagA = ((unsigned long long)((epoch << 2) | 1u)) << 32;
+  const unsigned long long tagP = ((unsigned long long)((epoch << 2) | 2u)) << 32;
+  volatile unsigned long long* vd = desc;
+  if (tile == 0) {
+    if (lane == 0) vd[0] = tagP | agg;
+    return 0;
+  }
+  if (lane == 0) vd[tile] = tagA | agg;
+  uint32_t excl = 0;
+  int64_t idx = (int64_t)tile - 1;
+  while (true) {
+    int64_t my = idx - lane;
+    unsigned long long d = (my >= 0) ? vd[my] : tagP;  // before tile 0: prefix 0
+    uint32_t hi = (uint32_t)(d >> 32);
+    uint32_t st = ((hi >> 2) == epoch) ? (hi & 3u) : 0u;
+    unsigned pmask = __ballot_sync(kFull, st == 2u);
+    unsigned invalid = __ballot_sync(kFull, st == 0u);
+    if (pmask) {
+      int first = __ffs(pmask) - 1;
+      if (invalid & ((1u << first) - 1u)) continue;  // a nearer tile is not ready
+      uint32_t v = (lane <= first) ? (uint32_t)d : 0u;
+      excl += __reduce_add_sync(kFull, v);
+      break;
+    }
+    if (invalid) continue;
+    excl += __reduce_add_sync(kFull, (uint32_t)d);
+    idx -= 32;
+  }
+  if (lane == 0) vd[tile] = tagP | (unsigned long long)(excl + agg);
+  return excl;
+}
+
+// ---------------------------------------------------------------------------
+// The sweep.  CLOSED = closed-loop harness: a due record
+// completes in the same tick with its preset outcome.
+// ---------------------------------------------------------------------------
+template <bool CLOSED>
+__global__ void __launch_bounds__(kBlock, 2) sweep_tick_kernel(const SweepParams p) {
+  __shared__ TickWords s_words;
+  __shared__ uint32_t s_warp_tot[kWarps];
+  __shared__ uint32_t s_stat[12];
+  __shared__ uint32_t s_xor[2];
+  __shared__ uint32_t s_sumrel;
+  __shared__ uint32_t s_base;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const uint32_t tile = blockIdx.x;
+  const uint32_t tile_base = tile * (uint32_t)kTile;
+  const int64_t T = p.T;
+
+  // A 5-field schedule has Second == 1<<0 (ParseStandard prepends "0"): off
+  // the minute no mask can match, so the 40 B/record of masks are not read
+  // unless the caller asks for a full scan.
+  int64_t sec_of_min = T % 60;
+  if (sec_of_min < 0) sec_of_min += 60;
+  const bool load_masks = (sec_of_min == 0) || (p.mode & AM_SWEEP_FULL_SCAN);
+
+  // ---- phase A: issue every schedule-column load of this lane up front ----
+  // half h covers records r0(h) .. r0(h)+1, r0 = tile_base + warp*128 + h*64 + lane*2
+  uint32_t r0[2];
+  ulonglong2 mi[2], hr[2], dm[2], mo[2], dw[2];
+  longlong2 fa[2];
+  int2 ras[2];
+  uint2 fl[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    r0[h] = tile_base + (uint32_t)(warp * kRecPerWarp + h * 64 + lane * 2);
+    fl[h] = ld_stream(reinterpret_cast<const uint2*>(p.c.flags + r0[h]));
+    ras[h] = ld_stream(reinterpret_cast<const int2*>(p.c.ras + r0[h]));
+    fa[h] = ld_stream(reinterpret_cast<const longlong2*>(p.c.finished_at + r0[h]));
+  }
+  if (load_masks) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mi[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.minute + r0[h]));
+      hr[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.hour + r0[h]));
+      dm[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.dom + r0[h]));
+      mo[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.month + r0[h]));
+      dw[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.dow + r0[h]));
+    }
+  } else {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mi[h] = hr[h] = dm[h] = mo[h] = dw[h] = make_ulonglong2(0, 0);
+    }
+  }
+
+  // ---- stage the tick's broken-down time in shared memory ----------------
+  if (tid == 0) s_words = tick_words_from_unix(T);
+  if (tid < 12) s_stat[tid] = 0;
+  if (tid == 12) { s_xor[0] = 0; s_xor[1] = 0; s_sumrel = 0; }
+  __syncthreads();
+  const TickWords w = s_words;
+
+  uint32_t act[2][2];
+  uint32_t st0 = 0, st1 = 0, st2 = 0, st3 = 0;  // packed per-lane statistics
+
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t flg[2] = {fl[h].x, fl[h].y};
+    const int32_t rasv[2] = {ras[h].x, ras[h].y};
+    const int64_t fav[2] = {fa[h].x, fa[h].y};
+    const uint64_t miv[2] = {mi[h].x, mi[h].y}, hrv[2] = {hr[h].x, hr[h].y};
+    const uint64_t dmv[2] = {dm[h].x, dm[h].y}, mov[2] = {mo[h].x, mo[h].y};
+    const uint64_t dwv[2] = {dw[h].x, dw[h].y};
+
+    bool live[2], due[2], stopped_now[2], need_b[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t f = flg[j];
+      const uint32_t kind = f & AM_KIND_MASK;
+      live[j] = !(f & AM_F_TOMBSTONE) && (kind - 1u) < 5u;  // kinds 1..5 are evaluated
+      const bool has_result = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL)) != 0;
+      const bool pending = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING)) != 0;
+      // step 1 sets finishedAt = T before the due decision is taken
+      const int64_t fa_eff = has_result ? T : fav[j];
+      const int64_t elapsed = (int64_t)((uint64_t)T - (uint64_t)fa_eff);
+      const bool due_iv = !(elapsed < (int64_t)rasv[j]);  // not(hcc.go:264) == timer :751 fired
+      const bool fld = (miv[j] & w.minute) && (hrv[j] & w.hour) && (mov[j] & w.month);
+      const bool dmm = (dmv[j] & w.dom) != 0, dwm = (dwv[j] & w.dow) != 0;
+      const bool star = ((dmv[j] | dwv[j]) >> 63) != 0;  // robfig dayMatches
+      const bool due_cron = w.sec0 && fld && (star ? (dmm && dwm) : (dmm || dwm));
+      const bool is_iv = (kind == AM_KIND_INTERVAL) || (kind == AM_KIND_CRON_EVERY);
+      due[j] = live[j] && (is_iv ? due_iv : (kind == AM_KIND_CRON_SPEC && due_cron));
+      stopped_now[j] = live[j] && kind == AM_KIND_STOPPED && !(f & AM_F_STOPPED_REPORTED);
+      need_b[j] = live[j] && (pending || (CLOSED && due[j]));
+      act[h][j] = (due[j] ? AM_ACT_SUBMIT_HC : 0u) | (stopped_now[j] ? AM_ACT_STOPPED : 0u) |
+                  ((live[j] && kind == AM_KIND_PARSE_ERROR) ? AM_ACT_PARSE_ERROR : 0u);
+    }
+
+    uint32_t nfl[2] = {flg[0], flg[1]};
+    int64_t nfa[2] = {fav[0], fav[1]};
+    const bool lane_b = need_b[0] || need_b[1];
+
+    if (__any_sync(kFull, lane_b)) {
+      // ---- phase B: remedy/counter columns, only for lanes that need them --
+      int2 lim = make_int2(0, 0), rst = make_int2(0, 0), sc = make_int2(0, 0), fc = make_int2(0, 0);
+      int2 rsc = make_int2(0, 0), rfc = make_int2(0, 0), rtc = make_int2(0, 0);
+      longlong2 rfa = make_longlong2(0, 0);
+      if (lane_b) {
+        const uint32_t r = r0[h];
+        lim = ld_stream(reinterpret_cast<const int2*>(p.c.runs_limit + r));
+        rst = ld_stream(reinterpret_cast<const int2*>(p.c.reset_interval + r));
+        sc = ld_stream(reinterpret_cast<const int2*>(p.c.success + r));
+        fc = ld_stream(reinterpret_cast<const int2*>(p.c.failed + r));
+        rsc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_success + r));
+        rfc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_failed + r));
+        rtc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_total + r));
+        rfa = ld_stream(reinterpret_cast<const longlong2*>(p.c.remedy_finished_at + r));
+      }
+      int32_t ns[2] = {sc.x, sc.y}, nf[2] = {fc.x, fc.y};
+      int32_t nrs[2] = {rsc.x, rsc.y}, nrf[2] = {rfc.x, rfc.y}, nrt[2] = {rtc.x, rtc.y};
+      int64_t nrfa[2] = {rfa.x, rfa.y};
+      const int32_t limv[2] = {lim.x, lim.y}, rstv[2] = {rst.x, rst.y};
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        if (need_b[j]) {
+          RecState s{flg[j], fav[j], ns[j], nf[j], nrs[j], nrf[j], nrt[j], nrfa[j], limv[j], rstv[j]};
+          uint32_t res = 0;
+          uint32_t a = apply_result(s, T, res);
+          if (CLOSED && due[j]) {
+            const uint64_t gidx = p.shard_base + (uint64_t)(r0[h] + (uint32_t)j);
+            const uint64_t k = outcome_key(p.seed, gidx, (uint64_t)T);
+            const uint32_t failp = (s.flags >> AM_F_FAILP_SHIFT) & 0xFFu;
+            const bool fail = (uint32_t)(k & 0xFF) < failp;
+            const bool rem_ok = (uint32_t)((k >> 8) & 0xFF) < 179u;
+            s.flags |= (fail ? AM_F_PENDING_FAIL : AM_F_PENDING_OK) | AM_F_REMEDY_PENDING |
+                       (rem_ok ? AM_F_REMEDY_OUTCOME_OK : 0u);
+            a |= apply_result(s, T, res);
+          }
+          act[h][j] |= a;
+          st2 += (res & 0xFFu) | ((res & 0xFF00u) << 8);          // ok | fail<<16
+          st3 += ((res >> 16) & 0xFFu) | ((res >> 8) & 0xFF0000u);  // remedy ok | fail<<16
+          nfl[j] = s.flags; nfa[j] = s.fa;
+          ns[j] = s.s; nf[j] = s.f; nrs[j] = s.rs; nrf[j] = s.rf; nrt[j] = s.rt; nrfa[j] = s.rfa;
+        }
+      }
+      if (lane_b) {
+        const uint32_t r = r0[h];
+        if (ns[0] != sc.x || ns[1] != sc.y)
+          st_stream(reinterpret_cast<int2*>(p.c.success + r), make_int2(ns[0], ns[1]));
+        if (nf[0] != fc.x || nf[1] != fc.y)
+          st_stream(reinterpret_cast<int2*>(p.c.failed + r), make_int2(nf[0], nf[1]));
+        if (nrs[0] != rsc.x || nrs[1] != rsc.y)
+          st_stream(reinterpret_cast<int2*>(p.c.remedy_success + r), make_int2(nrs[0], nrs[1]));
+        if (nrf[0] != rfc.x || nrf[1] != rfc.y)
+          st_stream(reinterpret_cast<int2*>(p.c.remedy_failed + r), make_int2(nrf[0], nrf[1]));
+        if (nrt[0] != rtc.x || nrt[1] != rtc.y)
+          st_stream(reinterpret_cast<int2*>(p.c.remedy_total + r), make_int2(nrt[0], nrt[1]));
+        if (nrfa[0] != rfa.x || nrfa[1] != rfa.y)
+          st_stream(reinterpret_cast<longlong2*>(p.c.remedy_finished_at + r),
+                    make_longlong2(nrfa[0], nrfa[1]));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (stopped_now[j]) {  // hcc.go:238-250: Status "Stopped", FinishedAt = now
+        nfa[j] = T;
+        nfl[j] |= AM_F_STOPPED_REPORTED;
+      }
+      st0 += spread4(act[h][j]);
+      st1 += spread4(act[h][j] >> 4);
+    }
+    if (nfl[0] != flg[0] || nfl[1] != flg[1])
+      st_stream(reinterpret_cast<uint2*>(p.c.flags + r0[h]), make_uint2(nfl[0], nfl[1]));
+    if (nfa[0] != fav[0] || nfa[1] != fav[1])
+      st_stream(reinterpret_cast<longlong2*>(p.c.finished_at + r0[h]), make_longlong2(nfa[0], nfa[1]));
+  }
+
+  // ---- ordered compaction: in-warp ranks from ballots ---------------------
+  const unsigned lt = (1u << lane) - 1u;
+  const unsigned b00 = __ballot_sync(kFull, act[0][0] != 0), b01 = __ballot_sync(kFull, act[0][1] != 0);
+  const unsigned b10 = __ballot_sync(kFull, act[1][0] != 0), b11 = __ballot_sync(kFull, act[1][1] != 0);
+  const uint32_t tot0 = __popc(b00) + __popc(b01);
+  const uint32_t warp_total = tot0 + __popc(b10) + __popc(b11);
+  uint32_t rank[2][2];
+  rank[0][0] = __popc(b00 & lt) + __popc(b01 & lt);
+  rank[0][1] = rank[0][0] + (act[0][0] != 0);
+  rank[1][0] = tot0 + __popc(b10 & lt) + __popc(b11 & lt);
+  rank[1][1] = rank[1][0] + (act[1][0] != 0);
+  if (lane == 0) s_warp_tot[warp] = warp_total;
+
+  // ---- statistics: lane -> warp (redux) -> CTA (shared atomics) ------------
+  if (__any_sync(kFull, (st0 | st1 | st2 | st3) != 0)) {
+    const uint32_t q0 = __reduce_add_sync(kFull, st0);  // 4 x 8-bit action counts
+    const uint32_t q1 = __reduce_add_sync(kFull, st1);
+    const uint32_t q2 = __reduce_add_sync(kFull, st2);  // 2 x 16-bit result counts
+    const uint32_t q3 = __reduce_add_sync(kFull, st3);
+    if (lane < 12) {
+      uint32_t v;
+      if (lane < 8) v = ((lane < 4 ? q0 : q1) >> ((lane & 3) * 8)) & 0xFFu;
+      else v = ((lane < 10 ? q2 : q3) >> ((lane & 1) * 16)) & 0xFFFFu;
+      if (v) atomicAdd(&s_stat[lane], v);
+    }
+  }
+  if (warp_total) {
+    uint32_t xl = 0, xh = 0, rel = 0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (act[h][j]) {
+          const uint32_t local = r0[h] + (uint32_t)j;
+          const uint64_t g = p.shard_base + local;
+          xl ^= (uint32_t)g;
+          xh ^= (uint32_t)(g >> 32);
+          rel += local - tile_base;
+        }
+    xl = __reduce_xor_sync(kFull, xl);
+    xh = __reduce_xor_sync(kFull, xh);
+    rel = __reduce_add_sync(kFull, rel);
+    if (lane == 0) {
+      atomicXor(&s_xor[0], xl);
+      atomicXor(&s_xor[1], xh);
+      atomicAdd(&s_sumrel, rel);
+    }
+  }
+  __syncthreads();
+
+  // ---- CTA total and global base (decoupled look-back, warp 0) -------------
+  if (warp == 0) {
+    uint32_t v = lane < kWarps ? s_warp_tot[lane] : 0u;
+    const uint32_t tile_total = __reduce_add_sync(kFull, v);
+    const uint32_t excl = tile_lookback(p.tile_desc, tile, p.epoch, tile_total, lane);
+    if (lane == 0) s_base = excl;
+    // flush CTA statistics while the other warps wait
+    if (lane < 12) {
+      const uint32_t sv = s_stat[lane];
+      if (sv) atomicAdd(&p.acc[2 + lane], (unsigned long long)sv);
+    }
+    if (lane == 12 && tile_total) {
+      atomicAdd(&p.acc[1], (unsigned long long)tile_total);
+      atomicXor(&p.acc[14], ((unsigned long long)s_xor[1] << 32) | s_xor[0]);
+      atomicAdd(&p.acc[15], (p.shard_base + tile_base) * (unsigned long long)tile_total + s_sumrel);
+    }
+  }
+  __syncthreads();
+
+  uint32_t base = s_base;
+#pragma unroll
+  for (int k = 0; k < kWarps; ++k) base += (k < warp) ? s_warp_tot[k] : 0u;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (act[h][j]) {
+        const uint32_t pos = base + rank[h][j];
+        if (pos < p.cap) {
+          p.due_idx[pos] = r0[h] + (uint32_t)j;
+          p.due_action[pos] = (uint8_t)act[h][j];
+        }
+      }
+
+  // ---- last CTA out publishes the tick's statistics and re-arms ------------
+  if (tid == 0) {
+    __threadfence();
+    const uint32_t ticket = atomicAdd(p.done, 1u);
+    if (ticket == gridDim.x - 1) {
+      __threadfence();
+      unsigned long long v[kNumAcc];
+#pragma unroll
+      for (int k = 0; k < kNumAcc; ++k) v[k] = atomicExch(&p.acc[k], 0ull);
+      v[0] = p.n_records;
+      if (p.out_stats) {
+        unsigned long long* o = reinterpret_cast<unsigned long long*>(p.out_stats);
+#pragma unroll
+        for (int k = 0; k < kNumAcc; ++k) o[k] = v[k];
+      }
+      if (p.out_count) *p.out_count = (uint32_t)v[1];
+      *p.done = 0;
+      __threadfence_system();
+    }
+  }
+}
+
+// ---- small maintenance kernels (upsert / remove / post_result / read) -------
+__global__ void fill_u32_kernel(uint32_t* p, uint32_t v, uint64_t n) {
+  uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+__global__ void scatter_records_kernel(DevCols c, const uint32_t* __restrict__ idx,
+                                       const am_record_t* __restrict__ recs, uint32_t n) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t i = idx[k];
+  const am_record_t r = recs[k];
+  c.minute[i] = r.minute; c.hour[i] = r.hour; c.dom[i] = r.dom; c.month[i] = r.month; c.dow[i] = r.dow;
+  c.ras[i] = r.ras; c.flags[i] = r.flags; c.finished_at[i] = r.finished_at;
+  c.runs_limit[i] = r.runs_limit; c.reset_interval[i] = r.reset_interval;
+  c.success[i] = r.success; c.failed[i] = r.failed; c.remedy_success[i] = r.remedy_success;
+  c.remedy_failed[i] = r.remedy_failed; c.remedy_total[i] = r.remedy_total;
+  c.remedy_finished_at[i] = r.remedy_finished_at;
+}
+
+__global__ void tombstone_kernel(uint32_t* flags, const uint32_t* __restrict__ idx, uint32_t n) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) flags[idx[k]] = AM_F_TOMBSTONE;
+}
+
+// bits: the AM_F_PENDING_* / AM_F_REMEDY_* flags to install (hcc.go:635/:662/:821/:836)
+__global__ void post_result_kernel(uint32_t* flags, const uint32_t* __restrict__ idx,
+                                   const uint32_t* __restrict__ bits, uint32_t n) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t m = AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK;
+  const uint32_t i = idx[k];
+  flags[i] = (flags[i] & ~m) | (bits[k] & m);
+}
+
+__global__ void gather_records_kernel(DevCols c, const uint32_t* __restrict__ idx, am_record_t* out,
+                                      uint32_t n) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t i = idx[k];
+  am_record_t r;
+  r.minute = c.minute[i]; r.hour = c.hour[i]; r.dom = c.dom[i]; r.month = c.month[i]; r.dow = c.dow[i];
+  r.finished_at = c.finished_at[i]; r.remedy_finished_at = c.remedy_finished_at[i];
+  r.ras = c.ras[i]; r.flags = c.flags[i];
+  r.runs_limit = c.runs_limit[i]; r.reset_interval = c.reset_interval[i];
+  r.success = c.success[i]; r.failed = c.failed[i]; r.remedy_success = c.remedy_success[i];
+  r.remedy_failed = c.remedy_failed[i]; r.remedy_total = c.remedy_total[i];
+  r.reserved = 0;
+  out[k] = r;
+}
+
+}  // namespace amsweep

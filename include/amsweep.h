@@ -1,0 +1,266 @@
+/*
+ * amsweep.h — C-ABI of libamsweep: the B200-native per-tick HealthCheck
+ * schedule-evaluation sweep for keikoproj/active-monitor.
+ *
+ * This header is the drop-in boundary.  Every entry point
+ * names the reference decision it replaces; `hcc.go` abbreviates
+ * internal/controllers/healthcheck_controller.go of the reference.
+ *
+ * Conventions (cgo-friendly):
+ *   - plain C, fixed-width integers, flat arrays; no callbacks, no torch types;
+ *   - every input is COPIED during the call, the library never retains caller
+ *     memory; outputs go to caller-provided buffers (capacity passed in);
+ *   - return value: 0 on success, negative AM_E_* on failure; never aborts,
+ *     never throws across the boundary;
+ *   - per-record anomalies are DATA (action bit AM_ACT_ANOMALY), not failures;
+ *   - there is NO CPU fallback: without a CUDA device am_sweep_create fails
+ *     with AM_E_DEVICE.
+ */
+#ifndef AMSWEEP_H_
+#define AMSWEEP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMSWEEP_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------- */
+#define AM_OK 0
+#define AM_E_INVAL (-1)       /* NULL pointer, bad argument                   */
+#define AM_E_RANGE (-2)       /* value outside the HBM column's domain (N1)   */
+#define AM_E_NOSPACE (-3)     /* caller buffer too small; needed size returned */
+#define AM_E_DEVICE (-4)      /* CUDA failure; see am_last_error_detail       */
+#define AM_E_NOMEM (-5)       /* host or device allocation failed             */
+#define AM_E_PARSE (-6)       /* cron spec rejected (robfig error text in err) */
+#define AM_E_UNSUPPORTED (-7) /* valid spec the device path does not evaluate
+                                 (non-UTC CRON_TZ); keep it on the Go path    */
+#define AM_E_BUSY (-8)        /* second concurrent am_sweep_tick on a handle  */
+
+/* ---- cron (replaces cron.ParseStandard, hcc.go:253; robfig/cron v3.0.1) - */
+#define AM_CRON_ERROR 0
+#define AM_CRON_SPEC 1  /* SpecSchedule: five uint64 masks, bit 63 = starBit  */
+#define AM_CRON_EVERY 2 /* ConstantDelaySchedule: delay_sec > 0               */
+
+#define AM_STAR_BIT (1ull << 63)
+
+typedef struct am_cron {
+  uint64_t minute, hour, dom, month, dow; /* robfig SpecSchedule fields      */
+  int64_t delay_sec;                      /* ConstantDelaySchedule.Delay / s  */
+  int32_t kind;                           /* AM_CRON_*                        */
+  int32_t tz_id;                          /* 0 = time.Local == UTC (distroless
+                                             image, Dockerfile:25)            */
+} am_cron_t;
+
+/* Parse `spec[0..len)` exactly as cron.ParseStandard does.  On a rejected
+ * spec returns AM_E_PARSE, sets out->kind = AM_CRON_ERROR and writes the
+ * robfig-style message (NUL-terminated, truncated to errcap) into err. */
+int am_cron_parse(const char* spec, size_t len, am_cron_t* out, char* err, size_t errcap);
+
+/* matches(T) of SURVEY Appendix A.7 for one schedule and one UTC second:
+ * 1 if a SpecSchedule fires exactly at unix_sec, else 0 (host helper; the
+ * device evaluates the same predicate inside the sweep kernel). */
+int am_cron_matches(const am_cron_t* c, int64_t unix_sec);
+
+/* Schedule.Next(t) for whole-second t (hcc.go:262): first activation strictly
+ * after unix_sec, or INT64_MIN when none within five years (robfig returns the
+ * zero time).  UTC only. */
+int64_t am_cron_next(const am_cron_t* c, int64_t unix_sec);
+
+/* RepeatAfterSec as hcc.go:262 derives it for a clock reading with a non-zero
+ * nanosecond part: whole seconds from floor(now) to Next(now).
+ * Returns 0 when Next() finds nothing. */
+int64_t am_cron_repeat_after_sec(const am_cron_t* c, int64_t unix_sec);
+
+/* ---- record schema -------------------------------- */
+/* flags word */
+#define AM_KIND_MASK 0x7u
+#define AM_KIND_NO_RESOURCE 0u   /* Workflow.Resource == nil, hcc.go:227       */
+#define AM_KIND_STOPPED 1u       /* ras<=0 && cron=="", hcc.go:238             */
+#define AM_KIND_INTERVAL 2u      /* ras>0 (cron ignored), hcc.go:264           */
+#define AM_KIND_CRON_SPEC 3u     /* ras<=0 && 5-field/descriptor, hcc.go:251   */
+#define AM_KIND_CRON_EVERY 4u    /* ras<=0 && "@every d", hcc.go:251           */
+#define AM_KIND_PARSE_ERROR 5u   /* ParseStandard error, hcc.go:254-257        */
+#define AM_KIND_HOST_FALLBACK 6u /* AM_E_UNSUPPORTED specs: never evaluated    */
+#define AM_F_HAS_REMEDY (1u << 3)        /* !RemedyWorkflow.IsEmpty()          */
+#define AM_F_PENDING_OK (1u << 4)        /* workflow phase Succeeded posted    */
+#define AM_F_PENDING_FAIL (1u << 5)      /* workflow phase Failed posted       */
+#define AM_F_REMEDY_PENDING (1u << 6)    /* a remedy outcome is attached       */
+#define AM_F_REMEDY_OUTCOME_OK (1u << 7) /* ... and it is Succeeded            */
+#define AM_F_TOMBSTONE (1u << 8)         /* removed / never upserted           */
+#define AM_F_STOPPED_REPORTED (1u << 9)  /* "Stopped" status already written   */
+#define AM_F_FAILP_SHIFT 16              /* closed-loop harness: P(fail)*256   */
+#define AM_F_FAILP_MASK (0xFFu << AM_F_FAILP_SHIFT)
+
+/* action byte emitted per record per tick (0 = nothing to do) */
+#define AM_ACT_SUBMIT_HC 0x01u         /* hcc.go:269-288 submit the workflow   */
+#define AM_ACT_RUN_REMEDY 0x02u        /* hcc.go:683/705/714 processRemedy     */
+#define AM_ACT_STOPPED 0x04u           /* hcc.go:238-250 write status Stopped  */
+#define AM_ACT_PARSE_ERROR 0x08u       /* hcc.go:254-257 warning event+requeue */
+#define AM_ACT_REMEDY_SKIP 0x10u       /* hcc.go:692-693                       */
+#define AM_ACT_RESET_ON_PASS 0x20u     /* hcc.go:649-660                       */
+#define AM_ACT_RESET_ON_INTERVAL 0x40u /* hcc.go:695-704                       */
+#define AM_ACT_ANOMALY 0x80u           /* nil RemedyFinishedAt at hcc.go:690   */
+
+/* One HealthCheck as the controller sees it (api/v1alpha1/healthcheck_types.go
+ * :32-44 spec, :47-66 status); Go `int` is int64. */
+typedef struct am_healthcheck {
+  int64_t repeat_after_sec;      /* Spec.RepeatAfterSec                        */
+  const char* cron;              /* Spec.Schedule.Cron (not NUL-terminated)    */
+  size_t cron_len;               /* 0 == ""                                    */
+  int32_t has_resource;          /* Spec.Workflow.Resource != nil              */
+  int32_t has_remedy;            /* !Spec.RemedyWorkflow.IsEmpty()             */
+  int64_t remedy_runs_limit;     /* Spec.RemedyRunsLimit                       */
+  int64_t remedy_reset_interval; /* Spec.RemedyResetInterval                   */
+  int64_t finished_at;           /* Status.FinishedAt.Unix()                   */
+  int64_t remedy_finished_at;    /* Status.RemedyFinishedAt.Unix()             */
+  int32_t finished_at_set;       /* Status.FinishedAt != nil                   */
+  int32_t remedy_finished_at_set;
+  int64_t success_count, failed_count;
+  int64_t remedy_success_count, remedy_failed_count, remedy_total_runs;
+  uint32_t fail_p8;              /* closed-loop harness only, 0..255           */
+  uint32_t reserved;
+} am_healthcheck_t;
+
+/* One packed record = one element of each SoA column. */
+typedef struct am_record {
+  uint64_t minute, hour, dom, month, dow;
+  int64_t finished_at;        /* nil => 0 (hcc.go:231-235)                     */
+  int64_t remedy_finished_at; /* nil => 0 (nil-ness matters: N3)               */
+  int32_t ras;                /* RepeatAfterSec | @every delay                 */
+  uint32_t flags;
+  int32_t runs_limit, reset_interval;
+  int32_t success, failed, remedy_success, remedy_failed, remedy_total;
+  int32_t reserved;
+} am_record_t;
+
+/* Ladder classification at upsert, in the order hcc.go:227 -> 238 -> 251 ->
+ * 264.  Returns AM_OK, AM_E_RANGE (value does not fit the column,
+ * N1) or AM_E_UNSUPPORTED (record gets AM_KIND_HOST_FALLBACK).  A cron parse
+ * error is NOT a call failure: kind = AM_KIND_PARSE_ERROR, like the reference's
+ * per-reconcile error. */
+int am_healthcheck_classify(const am_healthcheck_t* hc, am_record_t* out);
+
+/* RemedyWorkflow.IsEmpty (api/v1alpha1/healthcheck_types.go:104-106):
+ * reflect.DeepEqual against the zero value — note a non-nil empty rbacRules
+ * slice is NOT empty. */
+int am_remedy_is_empty(size_t generate_name_len, int resource_is_nil, int64_t timeout,
+                       int rbac_rules_is_nil);
+
+/* SoA view used by bulk load / upsert / read.  Any pointer may be NULL:
+ * on input a NULL column means "all zero", on output "do not read". */
+typedef struct am_record_cols {
+  uint64_t *minute, *hour, *dom, *month, *dow;
+  int32_t* ras;
+  uint32_t* flags;
+  int64_t* finished_at;
+  int32_t *runs_limit, *reset_interval;
+  int32_t *success, *failed, *remedy_success, *remedy_failed, *remedy_total;
+  int64_t* remedy_finished_at;
+} am_record_cols_t;
+
+/* ---- the sweep ---------------------------------------------------------- */
+typedef struct am_sweep am_sweep_t;
+
+typedef struct am_tick_stats {
+  uint64_t n_records;  /* slots swept (high-water mark of this shard)        */
+  uint64_t n_emitted;  /* records with a non-zero action                      */
+  uint64_t n_submit_hc, n_run_remedy, n_stopped, n_parse_error;
+  uint64_t n_remedy_skip, n_reset_on_pass, n_reset_on_interval, n_anomaly;
+  uint64_t n_result_ok, n_result_fail; /* feed metrics.MonitorSuccess/Error,
+                                          collector.go:19-31 (workflow=healthCheck) */
+  uint64_t n_remedy_ok, n_remedy_fail; /* same vectors, workflow=remedy        */
+  uint64_t idx_xor, idx_sum;           /* checksum of emitted global indices   */
+} am_tick_stats_t;
+
+#define AM_SWEEP_CLOSED_LOOP 0x1u /* harness: a due record completes instantly
+                                     with its preset outcome     */
+#define AM_SWEEP_FULL_SCAN 0x2u   /* read every schedule column even on ticks
+                                     where no 5-field cron can fire (sec!=0)  */
+
+/* One shard of the record array on one CUDA device.  `capacity` slots are
+ * allocated up front; `shard_base` is added to local indices wherever a
+ * global index is reported (multi-GPU index-range sharding). */
+int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t shard_base);
+void am_sweep_destroy(am_sweep_t*);
+
+/* Bulk load of a contiguous index range [first, first+n) — informer re-list
+ * after (re)start (SURVEY §5 "failure detection / recovery"). */
+int am_sweep_load_range(am_sweep_t*, uint64_t first, uint64_t n, const am_record_cols_t* cols);
+
+/* Reconcile of created/updated CRs (hcc.go:170-188): scatter n records to
+ * local slots idx[i].  Thread-safe; staged and applied by the next tick. */
+int am_sweep_upsert(am_sweep_t*, uint64_t n, const uint64_t* idx, const am_record_t* recs);
+
+/* CR deleted (hcc.go:175-186: Stop() its timer): tombstone the slots. */
+int am_sweep_remove(am_sweep_t*, uint64_t n, const uint64_t* idx);
+
+/* Terminal workflow phases observed by the watch loops (hcc.go:635, :662,
+ * :821, :836).  phase / remedy_phase: 0 none, 1 Succeeded, 2 Failed.
+ * Thread-safe; staged and applied at the start of the next tick. */
+#define AM_PHASE_NONE 0
+#define AM_PHASE_SUCCEEDED 1
+#define AM_PHASE_FAILED 2
+int am_sweep_post_result(am_sweep_t*, uint64_t n, const uint64_t* idx, const uint8_t* phase,
+                         const uint8_t* remedy_phase);
+
+/* One tick at wall-clock second unix_sec: drain staged ops, run the sweep
+ * kernel, return the ascending list of (global index, action) for every record
+ * whose action is non-zero.  Replaces, for every record at once, the decisions
+ * at hcc.go:238-267, :649-660, :677-721, :821-851 and the timer at :751.
+ * If n_emitted > cap: AM_E_NOSPACE, *n_out = needed, first cap entries valid.
+ * Single caller at a time per handle (AM_E_BUSY otherwise). */
+int am_sweep_tick(am_sweep_t*, int64_t unix_sec, uint32_t mode, uint64_t* due_idx,
+                  uint32_t* due_action, uint64_t cap, uint64_t* n_out, am_tick_stats_t* stats);
+
+/* Same tick, results left in HBM: launches on `cuda_stream` (a cudaStream_t /
+ * CUstream as void*, NULL = the handle's own stream) and does not synchronise.
+ * d_due_idx (u32 LOCAL indices), d_due_action (u8) hold `cap` entries;
+ * d_count receives n_emitted (u32); d_stats (may be NULL) receives an
+ * am_tick_stats_t.  Used for device-resident pipelines and the multi-GPU
+ * gather. */
+int am_sweep_tick_device(am_sweep_t*, int64_t unix_sec, uint32_t mode, void* d_due_idx,
+                         void* d_due_action, uint64_t cap, void* d_count, void* d_stats,
+                         void* cuda_stream);
+
+/* Streaming: n_ticks consecutive one-second ticks starting at unix_sec0,
+ * back-to-back on the device (BASELINE config 5).  Per-tick stats are written
+ * to stats_out[0..n_ticks) (host).  Emitted lists go to an HBM ring and are
+ * not copied to the host.  `seed` keys the closed-loop outcome sequence. */
+int am_sweep_run_ticks(am_sweep_t*, int64_t unix_sec0, uint64_t n_ticks, uint32_t mode,
+                       uint64_t seed, am_tick_stats_t* stats_out);
+
+/* Device -> host read-back of record state (status write-back, hcc.go:1445;
+ * checkpoint). idx == NULL reads the range [first, first+n). */
+int am_sweep_read(am_sweep_t*, uint64_t first, uint64_t n, const uint64_t* idx,
+                  am_record_cols_t* out);
+
+/* Introspection */
+uint64_t am_sweep_size(const am_sweep_t*);     /* high-water mark (slots swept) */
+uint64_t am_sweep_capacity(const am_sweep_t*);
+int am_sweep_device(const am_sweep_t*);
+/* Device time of the last am_sweep_tick / am_sweep_run_ticks sweep kernels
+ * (CUDA events on the launching stream), milliseconds; <0 if none. */
+double am_sweep_last_kernel_ms(const am_sweep_t*);
+/* Number of kernels this library has launched on the handle so far. */
+uint64_t am_sweep_launch_count(const am_sweep_t*);
+/* Raw device pointer of a column (for zero-copy wrapping by torch / NCCL
+ * plumbing); column ids follow am_record_cols_t member order, 0..15. */
+void* am_sweep_column_ptr(am_sweep_t*, int column);
+int am_sweep_set_seed(am_sweep_t*, uint64_t seed);
+
+/* UTC broken-down time exactly as the kernel computes it (test hook):
+ * out[0..6) = sec, min, hour, dom(1-31), month(1-12), dow(0=Sunday). */
+void am_civil_from_unix(int64_t unix_sec, int32_t out[6]);
+
+const char* am_strerror(int code);
+const char* am_last_error_detail(const am_sweep_t*); /* NULL handle: create-time error */
+int am_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMSWEEP_H_ */

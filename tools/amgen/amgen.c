@@ -1,0 +1,290 @@
+/*
+ * amgen.c — deterministic synthetic HealthCheck populations.
+ *
+ * Neutral test/bench tooling: it knows nothing about cron semantics.  It draws
+ * HealthCheck specs (repeatAfterSec / schedule.cron STRINGS / remedy knobs /
+ * status) shaped like the reference's examples (examples/inlineHello.yaml:7-16,
+ * examples/bdd/inlineMemoryRemedyUnitTest.yaml:8-11) from a keyed splitmix64
+ * stream, and hands each one to a caller-supplied classify function — the
+ * product's am_healthcheck_classify or the oracle's orc_classify, which share
+ * the am_healthcheck_t / am_record_t layouts — to obtain the packed record.
+ *
+ * Populations (config id):
+ *    1  N x {repeatAfterSec: 60}                         BASELINE configs[0]
+ *   11  N x {cron: "@every 1m"} (inlineHello.yaml as shipped) — same due-set
+ *    2  mixed 5-field cron + repeatAfterSec               BASELINE configs[1]
+ *    3  config 2 + remedy state, 50 % pending Failed      BASELINE configs[2]
+ *    4  = 2 (sharded by the caller)                       BASELINE configs[3]
+ *    5  = 2 with per-record failure probability (closed loop), 55 = 3-mix
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/amsweep.h"
+
+typedef int (*amgen_classify_fn)(const am_healthcheck_t*, am_record_t*);
+
+static inline uint64_t sm64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+uint64_t amgen_key(uint64_t seed, uint64_t i, uint64_t f) { return sm64(sm64(seed ^ sm64(i)) + f); }
+
+/* field ids of the keyed stream */
+enum { K_KIND = 1, K_RAS, K_FIN, K_FINSET, K_FAILP, K_CRON = 16, K_REMEDY = 64, K_LIMIT, K_RESET,
+       K_PEND, K_RT, K_RS, K_RFA, K_ROUT, K_S, K_F, K_VIOL };
+
+typedef struct { uint64_t seed, i, ctr; } rng_t;
+static uint64_t rnd(rng_t* r) { return amgen_key(r->seed, r->i, K_CRON + (r->ctr++)); }
+static uint32_t below(rng_t* r, uint32_t n) { return (uint32_t)(rnd(r) % n); }
+
+static const char* const MON[] = {"jan", "feb", "mar", "apr", "may", "jun",
+                                  "jul", "aug", "sep", "oct", "nov", "dec"};
+static const char* const DOW[] = {"sun", "mon", "tue", "wed", "thu", "fri", "sat"};
+
+typedef struct { int lo, hi; const int* steps; int nsteps; const char* const* names; int name_base; int qmark; } fdesc_t;
+static const int ST_MIN[] = {2, 3, 5, 10, 15, 20, 30};
+static const int ST_HR[] = {2, 3, 4, 6, 8, 12};
+static const int ST_DOM[] = {2, 5, 7, 10, 15};
+static const int ST_MON[] = {2, 3, 4, 6};
+static const int ST_DOW[] = {2, 3};
+static const fdesc_t FD[5] = {
+    {0, 59, ST_MIN, 7, NULL, 0, 0}, {0, 23, ST_HR, 6, NULL, 0, 0}, {1, 31, ST_DOM, 5, NULL, 0, 1},
+    {1, 12, ST_MON, 4, MON, 1, 0},  {0, 6, ST_DOW, 2, DOW, 0, 1},
+};
+
+static char* put_val(char* p, const fdesc_t* d, int v, rng_t* r) {
+  if (d->names && below(r, 10) == 0) {
+    const char* nm = d->names[v - d->name_base];
+    /* names are case-insensitive in robfig: vary the case */
+    int up = (int)below(r, 3);
+    for (int k = 0; k < 3; k++) *p++ = (up == 2 || (up == 1 && k == 0)) ? (char)(nm[k] - 32) : nm[k];
+    return p;
+  }
+  return p + sprintf(p, "%d", v);
+}
+
+/* one cron field from the fixed grammar: '*' 40 %, '* /k' 20 %, single 15 %,
+ * range 10 %, list 10 %, range/k 5 %; '?' replaces '*' for 5 % of dom/dow */
+static char* put_field(char* p, const fdesc_t* d, rng_t* r) {
+  uint32_t u = below(r, 100);
+  int span = d->hi - d->lo + 1;
+  if (u < 40) {
+    *p++ = (d->qmark && below(r, 20) == 0) ? '?' : '*';
+  } else if (u < 60) {
+    p += sprintf(p, "*/%d", d->steps[below(r, (uint32_t)d->nsteps)]);
+  } else if (u < 75) {
+    p = put_val(p, d, d->lo + (int)below(r, (uint32_t)span), r);
+  } else if (u < 85) {
+    int a = d->lo + (int)below(r, (uint32_t)span);
+    int b = a + (int)below(r, (uint32_t)(d->hi - a + 1));
+    p = put_val(p, d, a, r);
+    *p++ = '-';
+    p = put_val(p, d, b, r);
+  } else if (u < 95) {
+    int cnt = 2 + (int)below(r, 3);
+    for (int k = 0; k < cnt; k++) {
+      if (k) *p++ = ',';
+      p = put_val(p, d, d->lo + (int)below(r, (uint32_t)span), r);
+    }
+  } else {
+    int a = d->lo + (int)below(r, (uint32_t)span);
+    int b = a + (int)below(r, (uint32_t)(d->hi - a + 1));
+    p += sprintf(p, "%d-%d/%d", a, b, d->steps[below(r, (uint32_t)d->nsteps)]);
+  }
+  return p;
+}
+
+static const char* const EVERY[] = {"@every 3s", "@every 5s", "@every 1m", "@every 90s",
+                                    "@every 1h", "@every 1h30m", "@every 500ms"};
+static const int64_t EVERY_SEC[] = {3, 5, 60, 90, 3600, 5400, 1};
+static const char* const BAD[] = {"NOT_A_VALID_CRON", "0 * * * * *", "60 * * * *", "* * * * 7",
+                                  "* * * *", "*/0 * * * *", "5-1 * * * *", "@every",
+                                  "@fortnightly", "* 24 * * *", "* * 0 * *", "* * * 13 *",
+                                  "1-2-3 * * * *", "1/2/3 * * * *", "a * * * *", "@every 5 s"};
+static const char* const DESC[] = {"@hourly", "@daily", "@midnight", "@weekly", "@monthly",
+                                   "@yearly", "@annually"};
+static const int RAS_CHOICES[] = {5, 10, 30, 60, 300, 900, 3600};
+
+#define AMGEN_STR 128 /* bytes reserved per cron string */
+
+/* Draw HealthCheck #i of population `config`; cron text goes to buf[AMGEN_STR].
+ * *post_flags receives pending-result bits to OR into the classified record
+ * (config 3: the result this tick; not part of the CR). */
+void amgen_healthcheck(int config, uint64_t seed, uint64_t i, int64_t T0, am_healthcheck_t* hc,
+                       char* buf, uint32_t* post_flags) {
+  memset(hc, 0, sizeof *hc);
+  *post_flags = 0;
+  buf[0] = 0;
+  hc->has_resource = 1;
+  hc->cron = buf;
+  int64_t period = 60;
+  int mix = (config == 3 || config == 55) ? 3 : 2;
+  if (config == 1) {
+    hc->repeat_after_sec = 60;
+    hc->finished_at_set = 1;
+    hc->finished_at = T0 - (int64_t)(amgen_key(seed, i, K_FIN) % 120);
+    return;
+  }
+  if (config == 11) {
+    strcpy(buf, "@every 1m");
+    hc->cron_len = strlen(buf);
+    hc->finished_at_set = 1;
+    hc->finished_at = T0 - (int64_t)(amgen_key(seed, i, K_FIN) % 120);
+    return;
+  }
+  uint32_t u = (uint32_t)(amgen_key(seed, i, K_KIND) % 1000);
+  rng_t r = {seed, i, 0};
+  if (u < 500) { /* INTERVAL */
+    hc->repeat_after_sec = RAS_CHOICES[amgen_key(seed, i, K_RAS) % 7];
+    period = hc->repeat_after_sec;
+    if (below(&r, 8) == 0) { /* cron present but ignored (hcc.go:251 vs :264) */
+      strcpy(buf, "*/5 * * * *");
+      hc->cron_len = strlen(buf);
+    }
+  } else if (u < 900) { /* 5-field cron / descriptor */
+    period = 3600;
+    if (below(&r, 25) == 0) {
+      strcpy(buf, DESC[below(&r, 7)]);
+    } else {
+      char* p = buf;
+      if (below(&r, 50) == 0) p += sprintf(p, "%s", below(&r, 2) ? "CRON_TZ=UTC " : "TZ=UTC ");
+      for (int f = 0; f < 5; f++) {
+        if (f) { *p++ = ' '; if (below(&r, 40) == 0) *p++ = (below(&r, 2) ? '\t' : ' '); }
+        p = put_field(p, &FD[f], &r);
+      }
+      *p = 0;
+    }
+    hc->cron_len = strlen(buf);
+    hc->repeat_after_sec = -(int64_t)below(&r, 2); /* 0 or -1: both take the cron arm */
+  } else if (u < 980) { /* @every */
+    uint32_t k = below(&r, 7);
+    strcpy(buf, EVERY[k]);
+    hc->cron_len = strlen(buf);
+    period = EVERY_SEC[k];
+  } else if (u < 990) { /* paused */
+    hc->repeat_after_sec = -(int64_t)below(&r, 2);
+  } else if (u < 995) { /* parse error */
+    strcpy(buf, BAD[below(&r, 16)]);
+    hc->cron_len = strlen(buf);
+  } else { /* Workflow.Resource == nil */
+    hc->has_resource = 0;
+    hc->repeat_after_sec = 60;
+  }
+  if (amgen_key(seed, i, K_FINSET) % 50 != 0) { /* 2 % never ran */
+    hc->finished_at_set = 1;
+    hc->finished_at = T0 - (int64_t)(amgen_key(seed, i, K_FIN) % (uint64_t)(2 * period + 1));
+  }
+  hc->fail_p8 = (uint32_t)(amgen_key(seed, i, K_FAILP) % 64);
+  hc->success_count = (int64_t)(amgen_key(seed, i, K_S) % 1001);
+  hc->failed_count = (int64_t)(amgen_key(seed, i, K_F) % 1001);
+
+  if (mix == 3) {
+    static const int LIM[] = {0, 1, 2, 5};
+    static const int RST[] = {0, 60, 300};
+    hc->has_remedy = (amgen_key(seed, i, K_REMEDY) % 100) < 60;
+    hc->remedy_runs_limit = LIM[amgen_key(seed, i, K_LIMIT) % 4];
+    hc->remedy_reset_interval = RST[amgen_key(seed, i, K_RESET) % 3];
+    int64_t rt = (int64_t)(amgen_key(seed, i, K_RT) % 7);
+    int64_t rs = (int64_t)(amgen_key(seed, i, K_RS) % (uint64_t)(rt + 1));
+    hc->remedy_total_runs = rt;
+    hc->remedy_success_count = rs;
+    hc->remedy_failed_count = rt - rs;
+    if (rt > 0) {
+      hc->remedy_finished_at_set = 1;
+      hc->remedy_finished_at = T0 - (int64_t)(amgen_key(seed, i, K_RFA) % 601);
+    }
+    if (amgen_key(seed, i, K_VIOL) % 1000 == 0) { /* N3: limit reached, nil time */
+      hc->has_remedy = 1;
+      hc->remedy_runs_limit = 2;
+      hc->remedy_reset_interval = 300;
+      hc->remedy_total_runs = 3;
+      hc->remedy_success_count = 1;
+      hc->remedy_failed_count = 2;
+      hc->remedy_finished_at_set = 0;
+      hc->remedy_finished_at = 0;
+    }
+    if (config == 3) {
+      uint32_t pz = (uint32_t)(amgen_key(seed, i, K_PEND) % 4);
+      if (pz < 2) {
+        *post_flags |= AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING;
+        if ((amgen_key(seed, i, K_ROUT) % 10) < 7) *post_flags |= AM_F_REMEDY_OUTCOME_OK;
+      } else if (pz == 2) {
+        *post_flags |= AM_F_PENDING_OK;
+      }
+    }
+  }
+}
+
+typedef struct {
+  int config;
+  uint64_t seed, first, lo, hi;
+  int64_t T0;
+  amgen_classify_fn fn;
+  const am_record_cols_t* cols;
+  int64_t bad; /* classify failures other than AM_E_UNSUPPORTED */
+} job_t;
+
+static void* fill_worker(void* p) {
+  job_t* j = (job_t*)p;
+  const am_record_cols_t* c = j->cols;
+  char buf[AMGEN_STR];
+  for (uint64_t i = j->lo; i < j->hi; i++) {
+    am_healthcheck_t hc;
+    am_record_t r;
+    uint32_t post;
+    amgen_healthcheck(j->config, j->seed, i, j->T0, &hc, buf, &post);
+    int rc = j->fn(&hc, &r);
+    if (rc != 0 && rc != AM_E_UNSUPPORTED) j->bad++;
+    uint32_t kind = r.flags & AM_KIND_MASK;
+    if (kind != AM_KIND_NO_RESOURCE && kind != AM_KIND_HOST_FALLBACK) r.flags |= post;
+    uint64_t o = i - j->first;
+    c->minute[o] = r.minute; c->hour[o] = r.hour; c->dom[o] = r.dom; c->month[o] = r.month;
+    c->dow[o] = r.dow; c->ras[o] = r.ras; c->flags[o] = r.flags; c->finished_at[o] = r.finished_at;
+    c->runs_limit[o] = r.runs_limit; c->reset_interval[o] = r.reset_interval;
+    c->success[o] = r.success; c->failed[o] = r.failed; c->remedy_success[o] = r.remedy_success;
+    c->remedy_failed[o] = r.remedy_failed; c->remedy_total[o] = r.remedy_total;
+    c->remedy_finished_at[o] = r.remedy_finished_at;
+  }
+  return NULL;
+}
+
+/* Fill SoA columns for records [first, first+n) of a population through the
+ * given classify function.  Returns the number of unexpected classify
+ * failures (0 expected). */
+int64_t amgen_fill(int config, uint64_t seed, uint64_t first, uint64_t n, int64_t T0,
+                   amgen_classify_fn fn, const am_record_cols_t* cols, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  if (nthreads > 256) nthreads = 256;
+  job_t jobs[256];
+  pthread_t th[256];
+  uint64_t chunk = (n + (uint64_t)nthreads - 1) / (uint64_t)nthreads;
+  for (int t = 0; t < nthreads; t++) {
+    uint64_t lo = (uint64_t)t * chunk < n ? (uint64_t)t * chunk : n;
+    uint64_t hi = lo + chunk < n ? lo + chunk : n;
+    jobs[t] = (job_t){config, seed, first, first + lo, first + hi, T0, fn, cols, 0};
+  }
+  for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, fill_worker, &jobs[t]);
+  fill_worker(&jobs[0]);
+  int64_t bad = jobs[0].bad;
+  for (int t = 1; t < nthreads; t++) { pthread_join(th[t], NULL); bad += jobs[t].bad; }
+  return bad;
+}
+
+/* Materialise the HealthChecks themselves (for the Python oracle and for the
+ * "faithful shape" CPU baseline): hcs[k].cron points into strpool + k*96. */
+void amgen_healthchecks(int config, uint64_t seed, uint64_t first, uint64_t n, int64_t T0,
+                        am_healthcheck_t* hcs, char* strpool, uint32_t* post_flags) {
+  for (uint64_t k = 0; k < n; k++) {
+    amgen_healthcheck(config, seed, first + k, T0, &hcs[k], strpool + k * AMGEN_STR,
+                      &post_flags[k]);
+  }
+}
+
+int amgen_str_stride(void) { return AMGEN_STR; }
