@@ -20,6 +20,13 @@
 #include "../../include/amsweep.h"
 #include "civil.h"
 
+// the ABI's struct layouts are part of the contract (tests/test_abi.py)
+static_assert(sizeof(am_cron_t) == 56, "am_cron_t layout");
+static_assert(sizeof(am_healthcheck_t) == 120, "am_healthcheck_t layout");
+static_assert(sizeof(am_record_t) == 96, "am_record_t layout");
+static_assert(sizeof(am_tick_stats_t) == 128, "am_tick_stats_t layout");
+static_assert(sizeof(am_record_cols_t) == 128, "am_record_cols_t layout");
+
 namespace {
 
 using std::string_view;

@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — HealthCheck schedule evaluations/sec of the B200 sweep.
+
+One "step" = one tick of the hot path (schedule ladder + remedy state machine,
+SURVEY.md Appendix B.3) over the whole resident record array.  Workload at N=1:
+BASELINE.json configs[1] — 10 M HealthChecks, mixed 5-field cron + repeatAfterSec,
+seed 2 (tools/amgen).  At N>1 every rank owns an index-range shard of the same
+size (weak scaling) and the step ends with the all-gather of the due lists.
+
+  value     device-resident: state and outputs stay in HBM, CUDA events on the
+            launching stream, max over ranks.
+  e2e       through the host C-ABI call a cgo shim makes (am_sweep_post_result +
+            am_sweep_tick): results posted from host memory, due list copied
+            back to host memory, every step.
+  roofline  algorithmic bytes of the sweep kernel / its measured duration,
+            against MEASURED_PEAKS.json's HBM copy bandwidth.
+  cpu_baseline / --impl reference
+            the CPU oracle (our restatement of hcc.go + robfig/cron v3.0.1; the
+            Go reference cannot be executed here) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tools", "amgen")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "healthcheck_schedule_evals_per_sec"
+UNIT = "evals/s"
+N_PER_GPU = 10_000_000
+CONFIG, SEED = 2, 2
+B_READ = 56          # algorithmic bytes read per evaluation, schedule-only
+B_EMIT = 5           # u32 index + u8 action per emitted record (this layout)
+B_STOP = 12          # flags + finishedAt written when "Stopped" is first reported
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons while the GPU is under the bench load."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def n_since(self, t0):
+        return sum(1 for t, _ in self.rows if t >= t0)
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            if t < t0 or t > t1:
+                continue
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_sweep_rate(cols, T0, seconds, threads, oracle_c):
+    """Oracle ticks over the whole population, T advancing by one minute per
+    tick, for about `seconds`; returns (evals/s, ticks run)."""
+    n = len(cols["flags"])
+    work = {k: v.copy() for k, v in cols.items()}
+    oracle_c.sweep(work, T0, threads=threads)  # warm caches / page in
+    t0 = time.perf_counter()
+    k = 0
+    while True:
+        k += 1
+        oracle_c.sweep(work, T0 + 60 * k, threads=threads)
+        if time.perf_counter() - t0 >= seconds or k >= 400:
+            break
+    dt = time.perf_counter() - t0
+    return n * k / dt, k
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU path on this box's host cores.  The reference is
+    Go (robfig/cron un-vendored, no Go toolchain): this times oracle/ — our C
+    restatement of the same decisions — with every host thread."""
+    if rank != 0:
+        return
+    import amgen
+    import oracle_c
+    threads = os.cpu_count() or 1
+    n = min(N_PER_GPU, args.n)
+    cols = amgen.fill(CONFIG, SEED, 0, n, amgen.T0_MON_0915, oracle_c.load().orc_classify)
+    work = {k: v.copy() for k, v in cols.items()}
+    for w in range(args.warmup):
+        oracle_c.sweep(work, amgen.T0_MON_0915 - 60 * (w + 1), threads=threads)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        oracle_c.sweep(work, amgen.T0_MON_0915 + 60 * k, threads=threads)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"{n} records x {args.steps} ticks (whole config-2 population each step)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[1]: {n} HealthChecks, mixed 5-field cron + "
+                               "repeatAfterSec, seed 2, one tick per step", "records": n,
+                   "note": "CPU oracle port of hcc.go + robfig/cron v3.0.1; Go reference not runnable here"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_PER_GPU, help="records per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import amgen
+    am = importlib.import_module("active-monitor_b200")
+    gather = importlib.import_module("active-monitor_b200.gather")
+    lib = am.load()  # no fallback: raises if the CUDA library is missing
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sweep has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    T0 = amgen.T0_MON_0915
+    n = args.n
+    base = rank * n
+    cols = amgen.fill(CONFIG, SEED, base, n, T0, lib.am_healthcheck_classify)
+    sweep = am.Sweep(capacity=n, device=local_rank, shard_base=base)
+    sweep.load_range(0, cols)
+
+    d_idx = torch.empty(n, dtype=torch.int32, device=dev)
+    d_act = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    d_st = torch.zeros(16, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step(k):
+        # every step is an on-the-minute tick: all 56 B/record are needed
+        sweep.tick_device(T0 + 60 * k, 0, d_idx.data_ptr(), d_act.data_ptr(), n, d_cnt.data_ptr(),
+                          d_st.data_ptr(), stream.cuda_stream)
+        if world > 1:
+            return gather.allgather_due(d_idx, d_act, d_cnt, base)
+        return None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # warm-up: at least W steps and ~0.4 s of load so clocks settle
+    t_w = time.perf_counter()
+    w = 0
+    while w < args.warmup or time.perf_counter() - t_w < 0.4:
+        step(-1 - w)
+        w += 1
+        if w % 64 == 0:
+            torch.cuda.synchronize()
+    barrier()
+    launches0 = sweep.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_load0 = time.perf_counter()
+    ev0.record(stream)
+    for k in range(args.steps):
+        step(k)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = sweep.launch_count - launches0
+    stats = dict(zip(am.abi.STAT_FIELDS, [int(v) for v in d_st.cpu().tolist()]))
+    # keep the identical load running until the clock sampler has seen it
+    if sampler:
+        k = args.steps
+        while sampler.n_since(t_load0) < 6 and time.perf_counter() - t_load0 < 3.0:
+            for _ in range(32):
+                step(k); k += 1
+            torch.cuda.synchronize()
+    t_load1 = time.perf_counter()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop(t_load0, t_load1) if sampler else None
+
+    # ---- kernel-only duration for the roofline (N=1 timed region == kernels only) ----
+    kev0, kev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev0.record(stream)
+    kreps = max(20, min(args.steps, 200))
+    for k in range(kreps):
+        sweep.tick_device(T0 + 60 * k, 0, d_idx.data_ptr(), d_act.data_ptr(), n, d_cnt.data_ptr(),
+                          d_st.data_ptr(), stream.cuda_stream)
+    kev1.record(stream)
+    torch.cuda.synchronize()
+    k_ms = kev0.elapsed_time(kev1) / kreps
+    alg_bytes = n * B_READ + stats["n_emitted"] * B_EMIT + stats["n_stopped"] * B_STOP
+    peak, peak_src = measured_peaks()
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+
+    # ---- e2e: host buffers through am_sweep_post_result + am_sweep_tick ----
+    e2e = None
+    if True:
+        sweep2 = sweep  # same resident state; results now come from / go to host memory
+        idx_h = np.empty(n, dtype=np.uint64)
+        act_h = np.empty(n, dtype=np.uint32)
+        prev = None
+        h2d = d2h = 0
+        reps = max(5, min(args.steps, 50))
+        for phase_name in ("warm", "timed"):
+            if phase_name == "timed":
+                barrier()
+                t0 = time.perf_counter()
+                h2d = d2h = 0
+            for k in range(3 if phase_name == "warm" else reps):
+                if prev is not None and len(prev):
+                    ph = np.full(len(prev), am.PHASE_SUCCEEDED, dtype=np.uint8)
+                    sweep2.post_result(prev - base, ph)
+                    h2d += len(prev) * 8
+                gi, ga, st = sweep2.tick(T0 + 3600 + 60 * k + (0 if phase_name == "warm" else 600),
+                                         buffers=(idx_h, act_h))
+                prev = gi[(ga & am.ACT_SUBMIT_HC) != 0].copy()
+                d2h += len(gi) * 5 + 128
+            if phase_name == "timed":
+                barrier()
+                dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": n * world * reps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d // reps,
+               "d2h_bytes_per_step": d2h // reps, "ms_per_step": dt / reps * 1e3, "steps": reps,
+               "api": "am_sweep_post_result + am_sweep_tick (host buffers)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle_c
+        threads = os.cpu_count() or 1
+        host_cols = amgen.fill(CONFIG, SEED, 0, n, T0, oracle_c.load().orc_classify)
+        v_mt, k_mt = cpu_sweep_rate(host_cols, T0, args.cpu_seconds, threads, oracle_c)
+        v_1t, k_1t = cpu_sweep_rate(host_cols, T0, min(4.0, args.cpu_seconds), 1, oracle_c)
+        # B1 "faithful shape": re-parse + Next() per evaluation, 100k-record subsample
+        hcs, _, _ = amgen.healthchecks(CONFIG, SEED, 0, 100_000, T0)
+        import ctypes as C
+        t0 = time.perf_counter()
+        reps_b1 = 0
+        while time.perf_counter() - t0 < 2.0:
+            oracle_c.load().orc_faithful_eval(C.byref(hcs), 100_000, T0)
+            reps_b1 += 1
+        v_b1 = 100_000 * reps_b1 / (time.perf_counter() - t0)
+        cpu = {"value": v_mt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{k_mt} ticks x {n} records (whole config-2 population), oracle sweep on {threads} threads",
+               "single_thread_value": v_1t,
+               "faithful_shape_value": v_b1,
+               "faithful_shape_note": "1 thread, re-parse cron + Next() per evaluation as hcc.go:253-262 does, 100k-record subsample"}
+
+    if rank == 0:
+        value = n * world * args.steps / (ms * 1e-3)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": w, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[1]: {n} HealthChecks per GPU, mixed 5-field cron + "
+                                   "repeatAfterSec (tools/amgen config 2, seed 2), one on-the-minute tick per step",
+                       "records_per_gpu": n, "records_total": n * world,
+                       "l2": "inputs (560 MB/GPU) larger than L2 (126 MB); no flush needed",
+                       "parallelism": f"index-range shards x{world}" + (", NCCL all-gather of due lists" if world > 1 else ""),
+                       "due_per_tick": stats["n_submit_hc"], "emitted_per_tick": stats["n_emitted"]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "sweep_tick_kernel<false>", "kernel_ms": k_ms,
+                         "algorithmic_bytes": alg_bytes,
+                         "bytes_model": f"N*{B_READ} + emitted*{B_EMIT} + stopped*{B_STOP}"},
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

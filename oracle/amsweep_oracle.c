@@ -18,6 +18,11 @@
 #include <string.h>
 #include <time.h>
 
+_Static_assert(sizeof(orc_cron_t) == 56, "layout");
+_Static_assert(sizeof(orc_healthcheck_t) == 120, "layout");
+_Static_assert(sizeof(orc_record_t) == 96, "layout");
+_Static_assert(sizeof(orc_tick_stats_t) == 128, "layout");
+
 /* ------------------------------------------------------------------------ */
 /* constants mirrored from include/amsweep.h (values are the contract)       */
 #define KIND_MASK 0x7u

@@ -1,0 +1,318 @@
+"""GPU parity tests: the CUDA sweep, called through the C-ABI, against the CPU
+oracle on the same seeded inputs — bit-exact due lists, action bytes, statistics
+and every mutated status column.
+
+Bit-exact here means: against our restatement of hcc.go + robfig/cron v3.0.1;
+the Go binary could not be executed in this environment (oracle/amsweep_oracle.h).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+T0 = 1789982100      # 2026-09-21 09:15:00 UTC Monday
+T_OCT1 = 1790812800  # 2026-10-01 00:00:00 UTC Thursday
+
+
+def _gen_pair(gen, am, orc, config, seed, n, T, first=0):
+    """Columns through the PRODUCT classifier and through the ORACLE classifier."""
+    prod = gen.fill(config, seed, first, n, T, am.load().am_healthcheck_classify)
+    orac = gen.fill(config, seed, first, n, T, orc.load().orc_classify)
+    for name in am.COLUMN_NAMES:  # upsert-time parity (parser + ladder)
+        np.testing.assert_array_equal(prod[name], orac[name], err_msg=f"classify column {name}")
+    return prod, orac
+
+
+def _assert_tick_equal(am, got, want, sweep, ocols, n, what=""):
+    gi, ga, gs = got
+    wi, wa, ws = want
+    assert gs == ws, f"{what}: stats differ\n gpu={gs}\n cpu={ws}"
+    np.testing.assert_array_equal(gi, wi, err_msg=f"{what}: due indices")
+    np.testing.assert_array_equal(ga, wa, err_msg=f"{what}: action bytes")
+    dev = sweep.read_range(0, n)
+    for name in am.COLUMN_NAMES:
+        np.testing.assert_array_equal(dev[name], ocols[name], err_msg=f"{what}: column {name}")
+
+
+@pytest.mark.parametrize("config,n", [(1, 1000), (11, 1000)])
+def test_config1_interval_1000(am, orc, gen, config, n):
+    """BASELINE configs[0]: 1 000 checks, repeatAfterSec=60 / "@every 1m" — same due-set."""
+    prod, orac = _gen_pair(gen, am, orc, config, 1, n, T0)
+    with am.Sweep(capacity=n) as s:
+        s.load_range(0, prod)
+        got = s.tick(T0)
+        want = orc.sweep(orac, T0)
+        _assert_tick_equal(am, got, want, s, orac, n, f"config {config}")
+        assert 0.35 * n < got[2]["n_submit_hc"] < 0.65 * n  # ~50 % due by construction
+    # both variants of inlineHello.yaml yield the identical due-set
+    a = gen.fill(1, 1, 0, n, T0, am.load().am_healthcheck_classify)
+    b = gen.fill(11, 1, 0, n, T0, am.load().am_healthcheck_classify)
+    with am.Sweep(capacity=n) as sa, am.Sweep(capacity=n) as sb:
+        sa.load_range(0, a)
+        sb.load_range(0, b)
+        ia, _, _ = sa.tick(T0)
+        ib, _, _ = sb.tick(T0)
+        np.testing.assert_array_equal(ia, ib)
+
+
+@pytest.mark.parametrize("T", [T0, T_OCT1, T0 + 1, T0 + 45, 1767225600, 1709164800])
+@pytest.mark.parametrize("n", [1, 63, 1024, 1025, 200_003])
+def test_config2_mixed(am, orc, gen, T, n):
+    """BASELINE configs[1] population at oracle-friendly sizes, several ticks, ragged sizes."""
+    prod, orac = _gen_pair(gen, am, orc, 2, 2, n, T0)
+    with am.Sweep(capacity=n) as s:
+        s.load_range(0, prod)
+        got = s.tick(T)
+        want = orc.sweep(orac, T)
+        _assert_tick_equal(am, got, want, s, orac, n, f"config2 n={n} T={T}")
+        # second tick one second later: STOPPED is reported once only
+        got2 = s.tick(T + 1)
+        want2 = orc.sweep(orac, T + 1)
+        _assert_tick_equal(am, got2, want2, s, orac, n, "config2 second tick")
+
+
+@pytest.mark.parametrize("T", [T0, T_OCT1])
+@pytest.mark.parametrize("n", [1000, 300_007])
+def test_config3_remedy_state_machine(am, orc, gen, T, n):
+    """BASELINE configs[2]: 50 % pending Failed, 25 % Succeeded; remedy gate and counters."""
+    prod, orac = _gen_pair(gen, am, orc, 3, 3, n, T0)
+    with am.Sweep(capacity=n) as s:
+        s.load_range(0, prod)
+        got = s.tick(T)
+        want = orc.sweep(orac, T)
+        _assert_tick_equal(am, got, want, s, orac, n, f"config3 n={n}")
+        st = got[2]
+        if n > 100_000:
+            for k in ("n_run_remedy", "n_remedy_skip", "n_reset_on_pass", "n_reset_on_interval",
+                      "n_anomaly", "n_result_ok", "n_result_fail", "n_remedy_ok", "n_remedy_fail"):
+                assert st[k] > 0, f"population does not exercise {k}"
+
+
+def test_full_scan_mode_equals_default(am, orc, gen):
+    n = 50_000
+    prod, orac = _gen_pair(gen, am, orc, 2, 7, n, T0)
+    with am.Sweep(capacity=n) as s:
+        s.load_range(0, prod)
+        for T in (T0 + 7, T0 + 60):
+            got = s.tick(T, mode=am.SWEEP_FULL_SCAN)
+            want = orc.sweep(orac, T)
+            _assert_tick_equal(am, got, want, s, orac, n, f"full-scan T={T}")
+
+
+def test_remedy_gate_known_answers(am, orc):
+    """SURVEY Appendix C remedy vectors, through upsert + post_result + tick."""
+    T = T0
+    A = am
+    rows = [  # runsLimit, resetInterval, RT, d (None = nil), expected action bits
+        (2, 300, 1, 10, A.ACT_RUN_REMEDY),
+        (2, 300, 2, 300, A.ACT_REMEDY_SKIP),
+        (2, 300, 2, 301, A.ACT_RESET_ON_INTERVAL | A.ACT_RUN_REMEDY),
+        (0, 300, 9, 10, A.ACT_RUN_REMEDY),
+        (2, 0, 9, 10, A.ACT_RUN_REMEDY),
+        (2, 300, 2, None, A.ACT_ANOMALY),
+    ]
+    recs = np.zeros(len(rows) + 2, dtype=am.RECORD_DTYPE)
+    for k, (lim, rst, rt, d, _) in enumerate(rows):
+        rc, r = am.classify(repeat_after_sec=3600, has_remedy=True, remedy_runs_limit=lim,
+                            remedy_reset_interval=rst, remedy_total_runs=rt,
+                            remedy_failed_count=rt, finished_at=T - 5,
+                            remedy_finished_at=None if d is None else T - d)
+        assert rc == 0
+        recs[k] = r[0]
+    # pending Succeeded with RT>=1 resets; with RT==0 leaves everything alone
+    for k, rt in ((len(rows), 3), (len(rows) + 1, 0)):
+        rc, r = am.classify(repeat_after_sec=3600, has_remedy=True, remedy_total_runs=rt,
+                            remedy_success_count=rt, finished_at=T - 5,
+                            remedy_finished_at=(T - 50) if rt else None)
+        recs[k] = r[0]
+    n = len(recs)
+    with am.Sweep(capacity=n) as s:
+        s.upsert(np.arange(n), recs)
+        phase = np.array([am.PHASE_FAILED] * len(rows) + [am.PHASE_SUCCEEDED] * 2, dtype=np.uint8)
+        rphase = np.array([am.PHASE_SUCCEEDED] * n, dtype=np.uint8)
+        s.post_result(np.arange(n), phase, rphase)
+        idx, act, st = s.tick(T)
+        got = dict(zip(idx.tolist(), act.tolist()))
+        for k, row in enumerate(rows):
+            assert got.get(k, 0) == row[4], f"row {k}: {row} -> {got.get(k, 0):#x}"
+        assert got.get(len(rows)) == A.ACT_RESET_ON_PASS
+        assert len(rows) + 1 not in got
+        after = s.read(np.arange(n))
+        assert after["remedy_total"][0] == 2 and after["remedy_success"][0] == 1
+        assert after["remedy_total"][2] == 1          # reset then one run
+        assert after["remedy_total"][1] == 2          # skipped: untouched
+        assert after["remedy_total"][len(rows)] == 0 and after["remedy_finished_at"][len(rows)] == 0
+        assert (after["finished_at"] == T).all()      # every record took a result
+        assert (after["flags"] & (A.F_PENDING_OK | A.F_PENDING_FAIL | A.F_REMEDY_PENDING)).max() == 0
+        # oracle agrees record by record
+        oc = am.records_to_columns(recs)
+        bits = np.where(phase == am.PHASE_FAILED, A.F_PENDING_FAIL, A.F_PENDING_OK).astype(np.uint32)
+        oc["flags"] = oc["flags"] | bits | np.uint32(A.F_REMEDY_PENDING | A.F_REMEDY_OUTCOME_OK)
+        wi, wa, ws = orc.sweep(oc, T)
+        np.testing.assert_array_equal(idx, wi)
+        np.testing.assert_array_equal(act, wa)
+        assert st == ws
+        for name in am.COLUMN_NAMES:
+            np.testing.assert_array_equal(after[name], oc[name], err_msg=name)
+
+
+def test_upsert_remove_and_deferred_remedy_result(am, orc, gen):
+    n = 5000
+    prod, orac = _gen_pair(gen, am, orc, 3, 11, n, T0)
+    recs = am.columns_to_records(prod)
+    with am.Sweep(capacity=n + 100) as s:
+        # scatter in a shuffled order, in two batches, as Reconcile workers would
+        perm = np.random.default_rng(0).permutation(n)
+        s.upsert(perm[: n // 2], recs[perm[: n // 2]])
+        s.upsert(perm[n // 2:], recs[perm[n // 2:]])
+        gone = np.array([3, 77, 1024, n - 1], dtype=np.uint64)
+        s.remove(gone)
+        orac["flags"][gone.astype(np.int64)] = am.F_TOMBSTONE
+        got = s.tick(T0)
+        assert s.size == n
+        want = orc.sweep(orac, T0)
+        dev = s.read_range(0, n)
+        assert got[2] == want[2]
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+        for name in am.COLUMN_NAMES:
+            keep = np.ones(n, bool)
+            keep[gone.astype(np.int64)] = False  # tombstoned slots keep only the flag
+            np.testing.assert_array_equal(dev[name][keep], orac[name][keep], err_msg=name)
+        assert (dev["flags"][gone.astype(np.int64)] == am.F_TOMBSTONE).all()
+        # a remedy that finishes on its own (hcc.go:821-851), posted later
+        live = np.flatnonzero((orac["flags"] & 7 == am.KIND_INTERVAL) & (orac["flags"] & am.F_TOMBSTONE == 0))[:50]
+        s.post_result(live, np.zeros(len(live), np.uint8), np.full(len(live), am.PHASE_FAILED, np.uint8))
+        orac["flags"][live] |= am.F_REMEDY_PENDING
+        got = s.tick(T0 + 3)
+        want = orc.sweep(orac, T0 + 3)
+        assert got[2] == want[2] and got[2]["n_remedy_fail"] == len(live)
+        dev = s.read(live)
+        np.testing.assert_array_equal(dev["remedy_failed"], orac["remedy_failed"][live])
+        np.testing.assert_array_equal(dev["remedy_finished_at"], np.full(len(live), T0 + 3))
+
+
+def test_nospace_reports_needed_size(am, gen):
+    n = 4096
+    prod = gen.fill(1, 1, 0, n, T0, am.load().am_healthcheck_classify)
+    with am.Sweep(capacity=n) as s:
+        s.load_range(0, prod)
+        with pytest.raises(am.AmError) as ei:
+            s.tick(T0, cap=10)
+        assert ei.value.code == am.AM_E_NOSPACE
+        full_idx, _, st = s.tick(T0)
+        assert ei.value.needed == st["n_emitted"] == len(full_idx)
+        np.testing.assert_array_equal(ei.value.partial[0], full_idx[:10])
+
+
+def test_shard_base_gives_global_indices(am, orc, gen):
+    n, base = 3000, 12_500_000
+    prod = gen.fill(2, 4, base, n, T0, am.load().am_healthcheck_classify)
+    orac = gen.fill(2, 4, base, n, T0, orc.load().orc_classify)
+    with am.Sweep(capacity=n, shard_base=base) as s:
+        s.load_range(0, prod)
+        got = s.tick(T0)
+        want = orc.sweep(orac, T0, shard_base=base)
+        assert got[2] == want[2]
+        np.testing.assert_array_equal(got[0], want[0])
+        assert got[0].min() >= base
+
+
+def test_closed_loop_many_ticks(am, orc, gen):
+    """BASELINE configs[4] in miniature: consecutive ticks, due records complete at once."""
+    n, seed = 20_000, 5
+    for config in (5, 55):
+        prod, orac = _gen_pair(gen, am, orc, config, seed, n, T0)
+        with am.Sweep(capacity=n) as s:
+            s.load_range(0, prod)
+            s.set_seed(seed)
+            for k in range(0, 130):
+                T = T0 - 60 + k  # crosses two minute boundaries
+                got = s.tick(T, mode=am.SWEEP_CLOSED_LOOP)
+                want = orc.sweep(orac, T, mode=1, seed=seed)
+                assert got[2] == want[2], f"config {config} tick {k}"
+                np.testing.assert_array_equal(got[0], want[0])
+                np.testing.assert_array_equal(got[1], want[1])
+            dev = s.read_range(0, n)
+            for name in am.COLUMN_NAMES:
+                np.testing.assert_array_equal(dev[name], orac[name], err_msg=f"config {config} {name}")
+
+
+def test_run_ticks_streaming_matches_single_ticks(am, orc, gen):
+    n, seed, nt = 30_000, 9, 200
+    prod, orac = _gen_pair(gen, am, orc, 5, seed, n, T0)
+    with am.Sweep(capacity=n) as s:
+        s.load_range(0, prod)
+        stats = s.run_ticks(T0 - 30, nt, mode=am.SWEEP_CLOSED_LOOP, seed=seed)
+        assert s.last_kernel_ms > 0
+        for k in range(nt):
+            _, _, ws = orc.sweep(orac, T0 - 30 + k, mode=1, seed=seed)
+            gs = {f: int(stats[f][k]) for f in am.abi.STAT_FIELDS}
+            assert gs == ws, f"tick {k}"
+        dev = s.read_range(0, n)
+        for name in am.COLUMN_NAMES:
+            np.testing.assert_array_equal(dev[name], orac[name], err_msg=name)
+
+
+def test_tick_device_resident_outputs(am, orc, gen):
+    import torch
+    n = 100_000
+    prod, orac = _gen_pair(gen, am, orc, 2, 21, n, T0)
+    dev = torch.device("cuda:0")
+    with am.Sweep(capacity=n) as s:
+        s.load_range(0, prod)
+        d_idx = torch.empty(n, dtype=torch.int32, device=dev)
+        d_act = torch.empty(n, dtype=torch.uint8, device=dev)
+        d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        d_st = torch.zeros(16, dtype=torch.int64, device=dev)
+        stream = torch.cuda.current_stream()
+        s.tick_device(T0, 0, d_idx.data_ptr(), d_act.data_ptr(), n, d_cnt.data_ptr(),
+                      d_st.data_ptr(), stream.cuda_stream)
+        stream.synchronize()
+        wi, wa, ws = orc.sweep(orac, T0)
+        cnt = int(d_cnt.item())
+        assert cnt == len(wi)
+        np.testing.assert_array_equal(d_idx[:cnt].cpu().numpy().astype(np.uint64), wi)
+        np.testing.assert_array_equal(d_act[:cnt].cpu().numpy().astype(np.uint32), wa)
+        got_stats = dict(zip(am.abi.STAT_FIELDS, [int(v) & ((1 << 64) - 1) for v in d_st.cpu().tolist()]))
+        assert got_stats == ws
+
+
+def test_full_size_10m_properties(am, gen):
+    """BASELINE configs[1] at full size (10 M): size-independent properties — the
+    list is strictly ascending, its length/checksums equal the statistics, the
+    sum of per-shard ticks equals the whole, and re-ticking is idempotent."""
+    n = 10_000_000
+    lib = am.load()
+    prod = gen.fill(2, 2, 0, n, T0, lib.am_healthcheck_classify)
+    with am.Sweep(capacity=n) as s:
+        s.load_range(0, prod)
+        idx, act, st = s.tick(T0)
+        assert st["n_records"] == n and st["n_emitted"] == len(idx)
+        assert (np.diff(idx.astype(np.int64)) > 0).all()
+        assert int(np.bitwise_xor.reduce(idx)) == st["idx_xor"]
+        assert int(idx.sum(dtype=np.uint64)) == st["idx_sum"]
+        assert int((act & am.ACT_SUBMIT_HC != 0).sum()) == st["n_submit_hc"]
+        assert int((act & am.ACT_PARSE_ERROR != 0).sum()) == st["n_parse_error"]
+        assert int((act & am.ACT_STOPPED != 0).sum()) == st["n_stopped"] > 0
+        # numpy restatement of the interval rule on the same columns (not the oracle)
+        kind = prod["flags"] & 7
+        iv = (kind == am.KIND_INTERVAL) | (kind == am.KIND_CRON_EVERY)
+        due_iv = iv & ((T0 - prod["finished_at"]) >= prod["ras"])
+        got_due = np.zeros(n, bool)
+        got_due[idx[(act & am.ACT_SUBMIT_HC) != 0].astype(np.int64)] = True
+        np.testing.assert_array_equal(got_due[iv], due_iv[iv])
+        # idempotence: open loop, same T -> same due-set (STOPPED already reported)
+        idx2, act2, st2 = s.tick(T0)
+        keep = (act & ~np.uint32(am.ACT_STOPPED)) != 0
+        np.testing.assert_array_equal(idx2, idx[keep])
+        assert st2["n_stopped"] == 0
+    # shard additivity: 4 shards concatenated == the whole
+    parts = []
+    q = n // 4
+    for r in range(4):
+        cols = {k: np.ascontiguousarray(v[r * q:(r + 1) * q]) for k, v in prod.items()}
+        with am.Sweep(capacity=q, shard_base=r * q) as s:
+            s.load_range(0, cols)
+            parts.append(s.tick(T0)[0])
+    np.testing.assert_array_equal(np.concatenate(parts), idx)
