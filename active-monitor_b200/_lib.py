@@ -126,6 +126,7 @@ SYMBOLS = {
     "am_sweep_launch_count": (u64, [C.c_void_p]),
     "am_sweep_column_ptr": (C.c_void_p, [C.c_void_p, C.c_int]),
     "am_sweep_set_seed": (C.c_int, [C.c_void_p, u64]),
+    "am_sweep_stream": (C.c_void_p, [C.c_void_p]),
     "am_civil_from_unix": (None, [i64, P(i32 * 6)]),
     "am_strerror": (C.c_char_p, [C.c_int]),
     "am_last_error_detail": (C.c_char_p, [C.c_void_p]),

@@ -307,6 +307,7 @@ uint64_t am_sweep_launch_count(const am_sweep_t* h) { return h ? h->launches : 0
 void* am_sweep_column_ptr(am_sweep_t* h, int column) {
   return (h && column >= 0 && column < 16) ? h->col_ptr[column] : nullptr;
 }
+void* am_sweep_stream(am_sweep_t* h) { return h ? (void*)h->stream : nullptr; }
 int am_sweep_set_seed(am_sweep_t* h, uint64_t seed) {
   if (!h) return AM_E_INVAL;
   h->seed = seed;
@@ -424,7 +425,7 @@ int am_sweep_tick_device(am_sweep_t* h, int64_t unix_sec, uint32_t mode, void* d
   AM_CUDA(h, cudaSetDevice(h->device));
   int rc = drain_staged(h);
   if (rc != AM_OK) return rc;
-  cudaStream_t s = cuda_stream ? (cudaStream_t)cuda_stream : h->stream;
+  cudaStream_t s = (cudaStream_t)cuda_stream;  // NULL == CUDA default stream
   return launch_sweep(h, unix_sec, mode, (uint32_t*)d_due_idx, (uint8_t*)d_due_action, cap,
                       (am_tick_stats_t*)d_stats, (uint32_t*)d_count, s);
 }

@@ -230,7 +230,8 @@ class Sweep:
 
     def tick_device(self, unix_sec: int, mode: int, d_idx: int, d_act: int, cap: int,
                     d_count: int, d_stats: int = 0, stream: int = 0):
-        """Device-resident tick on a caller stream; raw device pointers (ints)."""
+        """Device-resident tick on a caller stream (0 = CUDA default stream); raw
+        device pointers (ints).  Does not synchronise."""
         self._check(self._lib.am_sweep_tick_device(self._h, unix_sec, mode, d_idx, d_act, cap,
                                                    d_count, d_stats or None, stream or None),
                     "am_sweep_tick_device")
@@ -260,6 +261,11 @@ class Sweep:
     # -- introspection
     def set_seed(self, seed: int):
         self._check(self._lib.am_sweep_set_seed(self._h, seed), "am_sweep_set_seed")
+
+    @property
+    def stream(self) -> int:
+        """the handle's own cudaStream_t"""
+        return self._lib.am_sweep_stream(self._h) or 0
 
     @property
     def size(self) -> int:

@@ -101,17 +101,17 @@ class ClockSampler:
 
 
 def cpu_sweep_rate(cols, T0, seconds, threads, oracle_c):
-    """Oracle ticks over the whole population, T advancing by one minute per
-    tick, for about `seconds`; returns (evals/s, ticks run)."""
+    """The same step as the GPU arm — the single tick T0 over the whole
+    population — repeated for about `seconds`; returns (evals/s, ticks run)."""
     n = len(cols["flags"])
     work = {k: v.copy() for k, v in cols.items()}
-    oracle_c.sweep(work, T0, threads=threads)  # warm caches / page in
+    oracle_c.sweep(work, T0, threads=threads)  # warm caches / page in / first "Stopped" reports
     t0 = time.perf_counter()
     k = 0
     while True:
         k += 1
-        oracle_c.sweep(work, T0 + 60 * k, threads=threads)
-        if time.perf_counter() - t0 >= seconds or k >= 400:
+        oracle_c.sweep(work, T0, threads=threads)
+        if time.perf_counter() - t0 >= seconds or k >= 2000:
             break
     dt = time.perf_counter() - t0
     return n * k / dt, k
@@ -130,10 +130,10 @@ def run_reference(args, rank):
     cols = amgen.fill(CONFIG, SEED, 0, n, amgen.T0_MON_0915, oracle_c.load().orc_classify)
     work = {k: v.copy() for k, v in cols.items()}
     for w in range(args.warmup):
-        oracle_c.sweep(work, amgen.T0_MON_0915 - 60 * (w + 1), threads=threads)
+        oracle_c.sweep(work, amgen.T0_MON_0915, threads=threads)
     t0 = time.perf_counter()
     for k in range(args.steps):
-        oracle_c.sweep(work, amgen.T0_MON_0915 + 60 * k, threads=threads)
+        oracle_c.sweep(work, amgen.T0_MON_0915, threads=threads)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
     sample = f"{n} records x {args.steps} ticks (whole config-2 population each step)"
@@ -195,11 +195,13 @@ def main():
     d_act = torch.empty(n, dtype=torch.uint8, device=dev)
     d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
     d_st = torch.zeros(16, dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # explicit stream: kernels, events and NCCL all on it
+    torch.cuda.set_stream(stream)
 
     def step(k):
-        # every step is an on-the-minute tick: all 56 B/record are needed
-        sweep.tick_device(T0 + 60 * k, 0, d_idx.data_ptr(), d_act.data_ptr(), n, d_cnt.data_ptr(),
+        # BASELINE configs[1] is ONE tick: every step is that tick (T0, on the minute,
+        # open loop => idempotent), over inputs 4.4x larger than L2
+        sweep.tick_device(T0, 0, d_idx.data_ptr(), d_act.data_ptr(), n, d_cnt.data_ptr(),
                           d_st.data_ptr(), stream.cuda_stream)
         if world > 1:
             return gather.allgather_due(d_idx, d_act, d_cnt, base)
@@ -250,7 +252,7 @@ def main():
     kev0.record(stream)
     kreps = max(20, min(args.steps, 200))
     for k in range(kreps):
-        sweep.tick_device(T0 + 60 * k, 0, d_idx.data_ptr(), d_act.data_ptr(), n, d_cnt.data_ptr(),
+        sweep.tick_device(T0, 0, d_idx.data_ptr(), d_act.data_ptr(), n, d_cnt.data_ptr(),
                           d_st.data_ptr(), stream.cuda_stream)
     kev1.record(stream)
     torch.cuda.synchronize()
@@ -259,27 +261,31 @@ def main():
     peak, peak_src = measured_peaks()
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
 
-    # ---- e2e: host buffers through am_sweep_post_result + am_sweep_tick ----
+    # ---- e2e: the call a cgo shim makes, host buffers both ways, real cadence ----
+    # consecutive one-second ticks; the host closes the loop: every check the previous
+    # tick submitted is posted back as Succeeded (H2D), then the tick runs and its due
+    # list is copied to host memory (D2H).  AM_SWEEP_FULL_SCAN keeps the device work per
+    # step identical to the `value` step (all 56 B/record read on every tick).
     e2e = None
     if True:
-        sweep2 = sweep  # same resident state; results now come from / go to host memory
         idx_h = np.empty(n, dtype=np.uint64)
         act_h = np.empty(n, dtype=np.uint32)
         prev = None
         h2d = d2h = 0
-        reps = max(5, min(args.steps, 50))
+        reps = max(10, min(args.steps, 120))
+        tick_no = 0
         for phase_name in ("warm", "timed"):
             if phase_name == "timed":
                 barrier()
                 t0 = time.perf_counter()
                 h2d = d2h = 0
-            for k in range(3 if phase_name == "warm" else reps):
+            for k in range(5 if phase_name == "warm" else reps):
                 if prev is not None and len(prev):
                     ph = np.full(len(prev), am.PHASE_SUCCEEDED, dtype=np.uint8)
-                    sweep2.post_result(prev - base, ph)
+                    sweep.post_result(prev - base, ph)
                     h2d += len(prev) * 8
-                gi, ga, st = sweep2.tick(T0 + 3600 + 60 * k + (0 if phase_name == "warm" else 600),
-                                         buffers=(idx_h, act_h))
+                gi, ga, st = sweep.tick(T0 + tick_no, mode=am.SWEEP_FULL_SCAN, buffers=(idx_h, act_h))
+                tick_no += 1
                 prev = gi[(ga & am.ACT_SUBMIT_HC) != 0].copy()
                 d2h += len(gi) * 5 + 128
             if phase_name == "timed":
@@ -291,7 +297,8 @@ def main():
             dt = float(t.item())
         e2e = {"value": n * world * reps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d // reps,
                "d2h_bytes_per_step": d2h // reps, "ms_per_step": dt / reps * 1e3, "steps": reps,
-               "api": "am_sweep_post_result + am_sweep_tick (host buffers)"}
+               "api": "am_sweep_post_result + am_sweep_tick (host buffers), consecutive 1 s ticks, "
+                      "host-closed loop, AM_SWEEP_FULL_SCAN"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -322,7 +329,7 @@ def main():
             "warmup": w, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": f"BASELINE configs[1]: {n} HealthChecks per GPU, mixed 5-field cron + "
-                                   "repeatAfterSec (tools/amgen config 2, seed 2), one on-the-minute tick per step",
+                                   "repeatAfterSec (tools/amgen config 2, seed 2); step = the single tick T0=2026-09-21T09:15:00Z",
                        "records_per_gpu": n, "records_total": n * world,
                        "l2": "inputs (560 MB/GPU) larger than L2 (126 MB); no flush needed",
                        "parallelism": f"index-range shards x{world}" + (", NCCL all-gather of due lists" if world > 1 else ""),

@@ -72,7 +72,8 @@ int64_t am_cron_next(const am_cron_t* c, int64_t unix_sec);
 
 /* RepeatAfterSec as hcc.go:262 derives it for a clock reading with a non-zero
  * nanosecond part: whole seconds from floor(now) to Next(now).
- * Returns 0 when Next() finds nothing. */
+ * When Next() finds nothing (Go zero time) Sub saturates and the Go value is
+ * int(minDuration/Second)+1 = -9223372035, returned as is. */
 int64_t am_cron_repeat_after_sec(const am_cron_t* c, int64_t unix_sec);
 
 /* ---- record schema -------------------------------- */
@@ -217,7 +218,8 @@ int am_sweep_tick(am_sweep_t*, int64_t unix_sec, uint32_t mode, uint64_t* due_id
                   uint32_t* due_action, uint64_t cap, uint64_t* n_out, am_tick_stats_t* stats);
 
 /* Same tick, results left in HBM: launches on `cuda_stream` (a cudaStream_t /
- * CUstream as void*, NULL = the handle's own stream) and does not synchronise.
+ * CUstream as void*; NULL = CUDA's default stream, as in every CUDA API; use
+ * am_sweep_stream() for the handle's own stream) and does not synchronise.
  * d_due_idx (u32 LOCAL indices), d_due_action (u8) hold `cap` entries;
  * d_count receives n_emitted (u32); d_stats (may be NULL) receives an
  * am_tick_stats_t.  Used for device-resident pipelines and the multi-GPU
@@ -251,6 +253,8 @@ uint64_t am_sweep_launch_count(const am_sweep_t*);
  * plumbing); column ids follow am_record_cols_t member order, 0..15. */
 void* am_sweep_column_ptr(am_sweep_t*, int column);
 int am_sweep_set_seed(am_sweep_t*, uint64_t seed);
+/* The handle's own non-blocking stream (cudaStream_t as void*). */
+void* am_sweep_stream(am_sweep_t*);
 
 /* UTC broken-down time exactly as the kernel computes it (test hook):
  * out[0..6) = sec, min, hour, dom(1-31), month(1-12), dow(0=Sunday). */

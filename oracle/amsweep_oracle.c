@@ -613,16 +613,19 @@ static int day_matches(const orc_cron_t* s, const struct tm* t) {
   return dom_match || dow_match;
 }
 
-/* the whole-second activation predicate */
-int orc_cron_matches(const orc_cron_t* c, int64_t T) {
+/* the whole-second activation predicate, given T's UTC fields */
+static int matches_tm(const orc_cron_t* c, const struct tm* t) {
   if (c->kind != CRON_SPEC) return 0;
+  if (t->tm_sec != 0) return 0; /* Second mask is 1<<0 */
+  if (((1ull << (unsigned)t->tm_min) & c->minute) == 0) return 0;
+  if (((1ull << (unsigned)t->tm_hour) & c->hour) == 0) return 0;
+  if (((1ull << (unsigned)(t->tm_mon + 1)) & c->month) == 0) return 0;
+  return day_matches(c, t);
+}
+int orc_cron_matches(const orc_cron_t* c, int64_t T) {
   struct tm t;
   utc_tm(T, &t);
-  if (t.tm_sec != 0) return 0; /* Second mask is 1<<0 */
-  if (((1ull << (unsigned)t.tm_min) & c->minute) == 0) return 0;
-  if (((1ull << (unsigned)t.tm_hour) & c->hour) == 0) return 0;
-  if (((1ull << (unsigned)(t.tm_mon + 1)) & c->month) == 0) return 0;
-  return day_matches(c, &t);
+  return matches_tm(c, &t);
 }
 
 static int64_t tm_date(int year, int mon1, int mday, int hh, int mm, int ss) {
@@ -871,8 +874,10 @@ static uint32_t apply_result(orc_record_t* r, int64_t T, orc_tick_stats_t* st) {
   return act;
 }
 
-uint32_t orc_tick_record(orc_record_t* r, int64_t T, uint32_t mode, uint64_t seed,
-                         uint64_t gidx, orc_tick_stats_t* st) {
+/* `tmT` = gmtime(T), computed once per tick by the sweeps (glibc's gmtime_r
+ * takes a process-wide lock, which would serialise the threaded baseline) */
+static uint32_t tick_record_tm(orc_record_t* r, int64_t T, const struct tm* tmT, uint32_t mode,
+                               uint64_t seed, uint64_t gidx, orc_tick_stats_t* st) {
   uint32_t kind = r->flags & KIND_MASK;
   if (r->flags & F_TOMBSTONE) return 0;
   if (kind == KIND_NO_RESOURCE || kind == KIND_HOST_FALLBACK || kind > KIND_HOST_FALLBACK)
@@ -900,7 +905,7 @@ uint32_t orc_tick_record(orc_record_t* r, int64_t T, uint32_t mode, uint64_t see
     }
     case KIND_CRON_SPEC: {
       orc_cron_t c = {r->minute, r->hour, r->dom, r->month, r->dow, 0, CRON_SPEC, 0};
-      due = orc_cron_matches(&c, T);
+      due = matches_tm(&c, tmT);
       break;
     }
   }
@@ -920,6 +925,13 @@ uint32_t orc_tick_record(orc_record_t* r, int64_t T, uint32_t mode, uint64_t see
   return act;
 }
 
+uint32_t orc_tick_record(orc_record_t* r, int64_t T, uint32_t mode, uint64_t seed,
+                         uint64_t gidx, orc_tick_stats_t* st) {
+  struct tm tmT;
+  utc_tm(T, &tmT);
+  return tick_record_tm(r, T, &tmT, mode, seed, gidx, st);
+}
+
 /* ---- whole-array sweeps -------------------------------------------------- */
 static void gather(const orc_record_cols_t* c, uint64_t i, orc_record_t* r) {
   r->minute = c->minute ? c->minute[i] : 0; r->hour = c->hour ? c->hour[i] : 0;
@@ -936,16 +948,19 @@ static void gather(const orc_record_cols_t* c, uint64_t i, orc_record_t* r) {
   r->remedy_finished_at = c->remedy_finished_at ? c->remedy_finished_at[i] : 0;
   r->reserved = 0;
 }
+/* write back only what the tick changed (keeps untouched cache lines clean) */
+#define PUT(col, val) do { if (c->col && c->col[i] != (val)) c->col[i] = (val); } while (0)
 static void scatter(orc_record_cols_t* c, uint64_t i, const orc_record_t* r) {
-  c->flags[i] = r->flags;
-  if (c->finished_at) c->finished_at[i] = r->finished_at;
-  if (c->success) c->success[i] = r->success;
-  if (c->failed) c->failed[i] = r->failed;
-  if (c->remedy_success) c->remedy_success[i] = r->remedy_success;
-  if (c->remedy_failed) c->remedy_failed[i] = r->remedy_failed;
-  if (c->remedy_total) c->remedy_total[i] = r->remedy_total;
-  if (c->remedy_finished_at) c->remedy_finished_at[i] = r->remedy_finished_at;
+  PUT(flags, r->flags);
+  PUT(finished_at, r->finished_at);
+  PUT(success, r->success);
+  PUT(failed, r->failed);
+  PUT(remedy_success, r->remedy_success);
+  PUT(remedy_failed, r->remedy_failed);
+  PUT(remedy_total, r->remedy_total);
+  PUT(remedy_finished_at, r->remedy_finished_at);
 }
+#undef PUT
 static void count_action(orc_tick_stats_t* st, uint32_t act, uint64_t gidx) {
   st->n_emitted++;
   st->n_submit_hc += (act & ACT_SUBMIT_HC) != 0;
@@ -966,10 +981,12 @@ int orc_sweep(orc_record_cols_t* cols, uint64_t n, uint64_t shard_base, int64_t 
   orc_tick_stats_t st;
   memset(&st, 0, sizeof st);
   st.n_records = n;
+  struct tm tmT;
+  utc_tm(T, &tmT);
   for (uint64_t i = 0; i < n; i++) {
     orc_record_t r;
     gather(cols, i, &r);
-    uint32_t act = orc_tick_record(&r, T, mode, seed, shard_base + i, &st);
+    uint32_t act = tick_record_tm(&r, T, &tmT, mode, seed, shard_base + i, &st);
     scatter(cols, i, &r);
     if (act) {
       if (st.n_emitted < cap) {
@@ -999,28 +1016,40 @@ typedef struct {
 
 static void* mt_worker(void* p) {
   mt_job_t* j = (mt_job_t*)p;
-  memset(&j->st, 0, sizeof j->st);
+  /* thread-private state lives on this thread's stack: the job structs of
+   * neighbouring threads share cache lines */
+  orc_tick_stats_t st;
+  memset(&st, 0, sizeof st);
+  orc_record_cols_t cols = *j->cols;
+  uint64_t n = 0, cap = 0, *idx = NULL;
+  uint32_t* act = NULL;
+  const uint64_t base = j->shard_base, seed = j->seed;
+  const int64_t T = j->T;
+  const uint32_t mode = j->mode;
+  struct tm tmT;
+  utc_tm(T, &tmT);
   for (uint64_t i = j->lo; i < j->hi; i++) {
     orc_record_t r;
-    gather(j->cols, i, &r);
-    uint32_t a = orc_tick_record(&r, j->T, j->mode, j->seed, j->shard_base + i, &j->st);
-    scatter(j->cols, i, &r);
+    gather(&cols, i, &r);
+    uint32_t a = tick_record_tm(&r, T, &tmT, mode, seed, base + i, &st);
+    scatter(&cols, i, &r);
     if (a) {
-      if (j->n == j->cap) {
-        uint64_t nc = j->cap ? j->cap * 2 : 1024;
-        uint64_t* ni = (uint64_t*)realloc(j->idx, nc * sizeof *ni);
-        uint32_t* na = (uint32_t*)realloc(j->act, nc * sizeof *na);
-        if (ni) j->idx = ni;
-        if (na) j->act = na;
-        if (!ni || !na) { j->oom = 1; return NULL; }
-        j->cap = nc;
+      if (n == cap) {
+        uint64_t nc = cap ? cap * 2 : 4096;
+        uint64_t* ni = (uint64_t*)realloc(idx, nc * sizeof *ni);
+        if (ni) idx = ni;
+        uint32_t* na = (uint32_t*)realloc(act, nc * sizeof *na);
+        if (na) act = na;
+        if (!ni || !na) { j->oom = 1; break; }
+        cap = nc;
       }
-      j->idx[j->n] = j->shard_base + i;
-      j->act[j->n] = a;
-      j->n++;
-      count_action(&j->st, a, j->shard_base + i);
+      idx[n] = base + i;
+      act[n] = a;
+      n++;
+      count_action(&st, a, base + i);
     }
   }
+  j->idx = idx; j->act = act; j->n = n; j->cap = cap; j->st = st;
   return NULL;
 }
 

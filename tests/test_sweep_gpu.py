@@ -82,7 +82,7 @@ def test_config3_remedy_state_machine(am, orc, gen, T, n):
         want = orc.sweep(orac, T)
         _assert_tick_equal(am, got, want, s, orac, n, f"config3 n={n}")
         st = got[2]
-        if n > 100_000:
+        if n > 100_000 and T == T0:  # remedyFinishedAt is within 600 s of T0: skips only there
             for k in ("n_run_remedy", "n_remedy_skip", "n_reset_on_pass", "n_reset_on_interval",
                       "n_anomaly", "n_result_ok", "n_result_fail", "n_remedy_ok", "n_remedy_fail"):
                 assert st[k] > 0, f"population does not exercise {k}"
