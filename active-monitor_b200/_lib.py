@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "lib", "libamsweep.so")
+# AMSWEEP_LIB: developer override to load an experimental build of the same ABI
+LIB_PATH = os.environ.get("AMSWEEP_LIB") or os.path.join(PKG, "lib", "libamsweep.so")
 
 u64, i64, u32, i32, u8 = C.c_uint64, C.c_int64, C.c_uint32, C.c_int32, C.c_uint8
 
@@ -34,6 +35,7 @@ ACT_REMEDY_SKIP, ACT_RESET_ON_PASS, ACT_RESET_ON_INTERVAL, ACT_ANOMALY = 0x10, 0
 
 SWEEP_CLOSED_LOOP, SWEEP_FULL_SCAN = 0x1, 0x2
 PHASE_NONE, PHASE_SUCCEEDED, PHASE_FAILED = 0, 1, 2
+IPC_HANDLE_BYTES = 64
 
 
 class AmCron(C.Structure):
@@ -123,10 +125,21 @@ SYMBOLS = {
     "am_sweep_capacity": (u64, [C.c_void_p]),
     "am_sweep_device": (C.c_int, [C.c_void_p]),
     "am_sweep_last_kernel_ms": (C.c_double, [C.c_void_p]),
+    "am_sweep_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "am_sweep_last_profile": (C.c_int, [C.c_void_p, P(C.c_double), P(C.c_double)]),
     "am_sweep_launch_count": (u64, [C.c_void_p]),
     "am_sweep_column_ptr": (C.c_void_p, [C.c_void_p, C.c_int]),
     "am_sweep_set_seed": (C.c_int, [C.c_void_p, u64]),
     "am_sweep_stream": (C.c_void_p, [C.c_void_p]),
+    "am_gather_create": (C.c_int, [P(C.c_void_p), C.c_int, C.c_int, C.c_int, u64]),
+    "am_gather_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "am_gather_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "am_gather_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, u64, C.c_void_p]),
+    "am_gather_out_idx": (C.c_void_p, [C.c_void_p]),
+    "am_gather_out_act": (C.c_void_p, [C.c_void_p]),
+    "am_gather_out_counts": (C.c_void_p, [C.c_void_p]),
+    "am_gather_last_error": (C.c_char_p, [C.c_void_p]),
+    "am_gather_destroy": (None, [C.c_void_p]),
     "am_civil_from_unix": (None, [i64, P(i32 * 6)]),
     "am_strerror": (C.c_char_p, [C.c_int]),
     "am_last_error_detail": (C.c_char_p, [C.c_void_p]),

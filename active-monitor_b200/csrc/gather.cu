@@ -1,0 +1,248 @@
+// gather.cu — concatenation of the per-GPU due lists over NVLink peer memory.
+//
+// The record array shards by contiguous global index range, so
+// the global ascending due list is the rank-ordered concatenation of the local
+// lists.  NCCL has no allgatherv; the portable path (gather.py) pads to the
+// largest count and needs a host round-trip to size the exchange.  Here ONE
+// kernel per tick does the whole exchange through CUDA-IPC-mapped peer memory:
+//
+//   1. every rank stores {epoch, my count} into slot[rank] of every peer's
+//      exchange block (system-scope release);
+//   2. every CTA waits until all `world` counts of this epoch have arrived in
+//      its own block, giving offset = sum(count[r], r < rank) and the total;
+//   3. the CTAs stream the local (u32 local index, u8 action) list and write
+//      (u64 global index, u8 action) at `offset` into EVERY peer's output
+//      buffer — NVSwitch gives each peer full bandwidth, the payload is
+//      ~1 MB/GPU/tick, so this is latency-, not bandwidth-bound;
+//   4. the last CTA fences (system scope), raises done[rank] on every peer and
+//      waits for all peers' done flags: when the kernel retires, this rank's
+//      output buffer holds the complete global list.
+//
+// Output buffers are double-buffered by epoch parity: a rank can be at most one
+// epoch ahead of a peer (step 4), and each rank's consumers are stream-ordered
+// before its next push, so epoch e+2 never overwrites data still being read.
+//
+// The reference has no counterpart (single Go process, no collectives); the
+// consumer of the list is createSubmitWorkflow, hcc.go:502.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/amsweep.h"
+
+namespace {
+
+constexpr int kMaxWorld = 16;
+
+struct ExchangeHeader {
+  unsigned long long count_slot[kMaxWorld];  // {epoch:32 | count:32}, slot r written by rank r
+  unsigned long long done_slot[kMaxWorld];   // epoch, slot r written by rank r
+  unsigned int cta_done;                     // local CTA ticket
+  unsigned int pad[31];
+};
+
+struct PushParams {
+  unsigned char* peer[kMaxWorld];  // base of every rank's exchange block (own included)
+  const uint32_t* idx_local;
+  const uint8_t* act_local;
+  const uint32_t* count_local;
+  uint32_t* out_counts;  // [world+1] on this rank: per-rank counts, then the total
+  uint64_t shard_base;
+  uint64_t cap_total;
+  size_t off_idx[2], off_act[2];  // byte offsets of the two output buffers in a block
+  uint32_t epoch;
+  int rank, world;
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256) gather_push_kernel(const PushParams p) {
+  __shared__ uint32_t s_count[kMaxWorld];
+  const int tid = threadIdx.x;
+  ExchangeHeader* mine = reinterpret_cast<ExchangeHeader*>(p.peer[p.rank]);
+  const uint32_t my_count = *p.count_local;
+
+  // 1. publish my count to every peer
+  if (blockIdx.x == 0 && tid < p.world) {
+    ExchangeHeader* peer = reinterpret_cast<ExchangeHeader*>(p.peer[tid]);
+    st_release_sys(&peer->count_slot[p.rank], ((unsigned long long)p.epoch << 32) | my_count);
+  }
+  // 2. wait for every rank's count of this epoch
+  if (tid < p.world) {
+    unsigned long long v;
+    do { v = ld_acquire_sys(&mine->count_slot[tid]); } while ((uint32_t)(v >> 32) != p.epoch);
+    s_count[tid] = (uint32_t)v;
+  }
+  __syncthreads();
+  uint64_t offset = 0, total = 0;
+  for (int r = 0; r < p.world; ++r) {
+    if (r < p.rank) offset += s_count[r];
+    total += s_count[r];
+  }
+  // 3. write my list into every peer's output buffer at `offset`
+  const int buf = p.epoch & 1;
+  const uint64_t room = offset < p.cap_total ? p.cap_total - offset : 0;
+  const uint64_t n = my_count < room ? my_count : room;
+  for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + tid; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t g = p.shard_base + p.idx_local[e];
+    const uint8_t a = p.act_local[e];
+    for (int r = 0; r < p.world; ++r) {
+      reinterpret_cast<uint64_t*>(p.peer[r] + p.off_idx[buf])[offset + e] = g;
+      (p.peer[r] + p.off_act[buf])[offset + e] = a;
+    }
+  }
+  // 4. completion: last CTA raises my done flag everywhere, then waits for all peers
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int ticket = atomicAdd(&mine->cta_done, 1u);
+    if (ticket == gridDim.x - 1) {
+      __threadfence_system();
+      for (int r = 0; r < p.world; ++r) {
+        ExchangeHeader* peer = reinterpret_cast<ExchangeHeader*>(p.peer[r]);
+        st_release_sys(&peer->done_slot[p.rank], (unsigned long long)p.epoch);
+      }
+      for (int r = 0; r < p.world; ++r) {
+        while (ld_acquire_sys(&mine->done_slot[r]) != (unsigned long long)p.epoch) {}
+      }
+      for (int r = 0; r < p.world; ++r) p.out_counts[r] = s_count[r];
+      p.out_counts[p.world] = (uint32_t)(total < p.cap_total ? total : p.cap_total);
+      mine->cta_done = 0;
+      __threadfence();
+    }
+  }
+}
+
+}  // namespace
+
+struct am_gather {
+  int device = 0, rank = 0, world = 1;
+  uint64_t cap_total = 0;
+  size_t block_bytes = 0;
+  size_t off_idx[2] = {0, 0}, off_act[2] = {0, 0};
+  unsigned char* block = nullptr;                 // my exchange block (cudaMalloc, IPC-exported)
+  unsigned char* peer[kMaxWorld] = {};            // mapped peers (own = block)
+  bool opened[kMaxWorld] = {};
+  uint32_t* out_counts = nullptr;
+  uint32_t epoch = 0;
+  bool connected = false;
+  std::string last_error;
+};
+
+#define AMG_CUDA(g, expr)                                                                       \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      char _b[384];                                                                             \
+      snprintf(_b, sizeof _b, "%s -> %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      (g)->last_error = _b;                                                                     \
+      return AM_E_DEVICE;                                                                       \
+    }                                                                                           \
+  } while (0)
+
+extern "C" {
+
+int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_t cap_total) {
+  if (!out || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || cap_total == 0) return AM_E_INVAL;
+  *out = nullptr;
+  am_gather* g = new (std::nothrow) am_gather();
+  if (!g) return AM_E_NOMEM;
+  g->device = device; g->rank = rank; g->world = world; g->cap_total = cap_total;
+  auto align = [](size_t v) { return (v + 255) / 256 * 256; };
+  size_t off = align(sizeof(ExchangeHeader));
+  for (int b = 0; b < 2; ++b) { g->off_idx[b] = off; off = align(off + cap_total * 8); }
+  for (int b = 0; b < 2; ++b) { g->off_act[b] = off; off = align(off + cap_total); }
+  g->block_bytes = off;
+  int rc = [&]() -> int {
+    AMG_CUDA(g, cudaSetDevice(device));
+    AMG_CUDA(g, cudaMalloc((void**)&g->block, g->block_bytes));
+    AMG_CUDA(g, cudaMemset(g->block, 0, g->block_bytes));
+    AMG_CUDA(g, cudaMalloc((void**)&g->out_counts, (kMaxWorld + 1) * 4));
+    AMG_CUDA(g, cudaMemset(g->out_counts, 0, (kMaxWorld + 1) * 4));
+    AMG_CUDA(g, cudaDeviceSynchronize());
+    return AM_OK;
+  }();
+  g->peer[rank] = g->block;
+  if (rc != AM_OK) { am_gather_destroy(g); return rc; }
+  *out = g;
+  return AM_OK;
+}
+
+int am_gather_export(am_gather_t* g, void* handle_out) {
+  if (!g || !handle_out) return AM_E_INVAL;
+  static_assert(sizeof(cudaIpcMemHandle_t) == AM_IPC_HANDLE_BYTES, "IPC handle size");
+  AMG_CUDA(g, cudaSetDevice(g->device));
+  cudaIpcMemHandle_t h;
+  AMG_CUDA(g, cudaIpcGetMemHandle(&h, g->block));
+  memcpy(handle_out, &h, sizeof h);
+  return AM_OK;
+}
+
+int am_gather_connect(am_gather_t* g, const void* handles) {
+  if (!g || !handles) return AM_E_INVAL;
+  AMG_CUDA(g, cudaSetDevice(g->device));
+  for (int r = 0; r < g->world; ++r) {
+    if (r == g->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)handles + (size_t)r * AM_IPC_HANDLE_BYTES, sizeof h);
+    void* p = nullptr;
+    AMG_CUDA(g, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    g->peer[r] = (unsigned char*)p;
+    g->opened[r] = true;
+  }
+  g->connected = true;
+  return AM_OK;
+}
+
+int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_local,
+                   const void* d_count_local, uint64_t shard_base, void* cuda_stream) {
+  if (!g || !d_idx_local || !d_act_local || !d_count_local) return AM_E_INVAL;
+  if (!g->connected && g->world > 1) return AM_E_INVAL;
+  AMG_CUDA(g, cudaSetDevice(g->device));
+  PushParams p{};
+  for (int r = 0; r < g->world; ++r) p.peer[r] = g->peer[r];
+  p.idx_local = (const uint32_t*)d_idx_local;
+  p.act_local = (const uint8_t*)d_act_local;
+  p.count_local = (const uint32_t*)d_count_local;
+  p.out_counts = g->out_counts;
+  p.shard_base = shard_base;
+  p.cap_total = g->cap_total;
+  for (int b = 0; b < 2; ++b) { p.off_idx[b] = g->off_idx[b]; p.off_act[b] = g->off_act[b]; }
+  g->epoch += 1;
+  if (g->epoch == 0) g->epoch = 2;  // keep parity continuity irrelevant: 0 is the "never written" value
+  p.epoch = g->epoch;
+  p.rank = g->rank;
+  p.world = g->world;
+  gather_push_kernel<<<32, 256, 0, (cudaStream_t)cuda_stream>>>(p);
+  AMG_CUDA(g, cudaGetLastError());
+  return AM_OK;
+}
+
+void* am_gather_out_idx(am_gather_t* g) { return g ? g->block + g->off_idx[g->epoch & 1] : nullptr; }
+void* am_gather_out_act(am_gather_t* g) { return g ? g->block + g->off_act[g->epoch & 1] : nullptr; }
+void* am_gather_out_counts(am_gather_t* g) { return g ? g->out_counts : nullptr; }
+const char* am_gather_last_error(const am_gather_t* g) { return g ? g->last_error.c_str() : ""; }
+
+void am_gather_destroy(am_gather_t* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < g->world; ++r)
+    if (g->opened[r] && g->peer[r]) cudaIpcCloseMemHandle(g->peer[r]);
+  if (g->block) cudaFree(g->block);
+  if (g->out_counts) cudaFree(g->out_counts);
+  delete g;
+}
+
+}  // extern "C"

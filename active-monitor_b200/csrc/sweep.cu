@@ -15,6 +15,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "sweep_kernels.cuh"
@@ -63,22 +64,31 @@ struct am_sweep {
   DevCols cols{};
   void* col_ptr[16] = {};
   size_t col_elem[16] = {};
-  unsigned long long* tile_desc = nullptr;
+  uint32_t* seg_idx = nullptr;       // per-tile segments written by the sweep kernel
+  uint8_t* seg_act = nullptr;
+  uint32_t* tile_count = nullptr;    // [tiles]
+  uint32_t* group_count[2] = {nullptr, nullptr};  // [groups], parity = tick number & 1
   unsigned long long* acc = nullptr;
-  uint32_t* done = nullptr;
-  uint32_t epoch = 0;
+  uint32_t parity = 0;
   uint32_t* due_idx[2] = {nullptr, nullptr};
   uint8_t* due_action[2] = {nullptr, nullptr};
   am_tick_stats_t* h_stats = nullptr;  // pinned + mapped
   am_tick_stats_t* d_stats_mapped = nullptr;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evp[3] = {nullptr, nullptr, nullptr};  // profiling: before sweep, between, after compact
+  bool profiling = false, profiled = false;
   std::mutex mu;  // guards the staged vectors
   std::atomic_flag ticking = ATOMIC_FLAG_INIT;
+  // staged ops, each stamped with its arrival number (call order is preserved per slot)
+  uint64_t op_seq = 0;
   std::vector<uint32_t> up_idx;
   std::vector<am_record_t> up_rec;
+  std::vector<uint64_t> up_seq;
   std::vector<uint32_t> rm_idx;
+  std::vector<uint64_t> rm_seq;
   std::vector<uint32_t> res_idx, res_bits;
+  std::vector<uint64_t> res_seq;
   PinnedBuf pin_in, pin_out;
   DevBuf dev_in;
   std::string last_error;
@@ -134,15 +144,45 @@ struct TickGuard {
 int drain_staged(am_sweep* h) {
   std::vector<uint32_t> up_idx, rm_idx, res_idx, res_bits;
   std::vector<am_record_t> up_rec;
+  std::vector<uint64_t> up_seq, rm_seq, res_seq;
   {
     std::lock_guard<std::mutex> lk(h->mu);
-    up_idx.swap(h->up_idx); up_rec.swap(h->up_rec); rm_idx.swap(h->rm_idx);
-    res_idx.swap(h->res_idx); res_bits.swap(h->res_bits);
+    up_idx.swap(h->up_idx); up_rec.swap(h->up_rec); up_seq.swap(h->up_seq);
+    rm_idx.swap(h->rm_idx); rm_seq.swap(h->rm_seq);
+    res_idx.swap(h->res_idx); res_bits.swap(h->res_bits); res_seq.swap(h->res_seq);
+  }
+  if (up_idx.size() + rm_idx.size() + res_idx.size() == 0) return AM_OK;
+  for (uint32_t i : up_idx)  // every upserted slot extends the swept range (high-water mark),
+    if ((uint64_t)i + 1 > h->n_records) h->n_records = (uint64_t)i + 1;  // even if removed again
+  {
+    // Resolve per slot in call order: the latest upsert/remove wins; a result
+    // survives only if it was posted after that slot's latest upsert/remove
+    // (an older one belongs to the replaced CR); of several results the latest.
+    // After this the three scatter kernels touch disjoint / ordered slots.
+    std::unordered_map<uint32_t, uint64_t> state, res_last;
+    state.reserve(up_idx.size() + rm_idx.size());
+    for (size_t k = 0; k < up_idx.size(); ++k) { uint64_t& v = state[up_idx[k]]; if (up_seq[k] > v) v = up_seq[k]; }
+    for (size_t k = 0; k < rm_idx.size(); ++k) { uint64_t& v = state[rm_idx[k]]; if (rm_seq[k] > v) v = rm_seq[k]; }
+    size_t w = 0;
+    for (size_t k = 0; k < up_idx.size(); ++k)
+      if (state[up_idx[k]] == up_seq[k]) { up_idx[w] = up_idx[k]; up_rec[w] = up_rec[k]; ++w; }
+    up_idx.resize(w); up_rec.resize(w);
+    w = 0;
+    for (size_t k = 0; k < rm_idx.size(); ++k)
+      if (state[rm_idx[k]] == rm_seq[k]) rm_idx[w++] = rm_idx[k];
+    rm_idx.resize(w);
+    res_last.reserve(res_idx.size());
+    for (size_t k = 0; k < res_idx.size(); ++k) { uint64_t& v = res_last[res_idx[k]]; if (res_seq[k] > v) v = res_seq[k]; }
+    w = 0;
+    for (size_t k = 0; k < res_idx.size(); ++k) {
+      auto it = state.find(res_idx[k]);
+      const bool newer = it == state.end() || res_seq[k] > it->second;
+      if (newer && res_last[res_idx[k]] == res_seq[k]) { res_idx[w] = res_idx[k]; res_bits[w] = res_bits[k]; ++w; }
+    }
+    res_idx.resize(w); res_bits.resize(w);
   }
   const size_t nu = up_idx.size(), nr = rm_idx.size(), np = res_idx.size();
   if (nu + nr + np == 0) return AM_OK;
-  for (uint32_t i : up_idx)  // upserts extend the swept range (high-water mark)
-    if ((uint64_t)i + 1 > h->n_records) h->n_records = (uint64_t)i + 1;
   // layout of the staging block: [up_rec][up_idx][rm_idx][res_idx][res_bits]
   size_t o_rec = 0, o_ui = o_rec + nu * sizeof(am_record_t), o_rm = o_ui + nu * 4,
          o_ri = o_rm + nr * 4, o_rb = o_ri + np * 4, total = o_rb + np * 4;
@@ -155,7 +195,7 @@ int drain_staged(am_sweep* h) {
   AM_CUDA(h, cudaMemcpyAsync(h->dev_in.p, hp, total, cudaMemcpyHostToDevice, h->stream));
   char* dp = (char*)h->dev_in.p;
   const int B = 256;
-  // order: removes, then upserts (a delete + re-create in one tick keeps the new CR), then results
+  // slots of the three kernels are disjoint (removes vs upserts) or ordered (results last)
   if (nr) {
     tombstone_kernel<<<(unsigned)((nr + B - 1) / B), B, 0, h->stream>>>(h->cols.flags, (const uint32_t*)(dp + o_rm), (uint32_t)nr);
     h->launches++;
@@ -192,22 +232,34 @@ int launch_sweep(am_sweep* h, int64_t T, uint32_t mode, uint32_t* d_idx, uint8_t
   p.T = T;
   p.n_tiles = (uint32_t)((h->n_records + kTile - 1) / kTile);
   p.mode = mode;
-  p.cap = (uint32_t)(cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : cap);
-  h->epoch = (h->epoch + 1) & 0x3FFFFFFFu;
-  if (h->epoch == 0) {  // 30-bit stamp wrapped: clear descriptors once
-    AM_CUDA(h, cudaMemsetAsync(h->tile_desc, 0, (h->cap_padded / kTile) * 8, s));
-    h->epoch = 1;
-  }
-  p.epoch = h->epoch;
-  p.due_idx = d_idx;
-  p.due_action = d_act;
-  p.tile_desc = h->tile_desc;
+  p.seg_idx = h->seg_idx;
+  p.seg_act = h->seg_act;
+  p.tile_count = h->tile_count;
+  p.group_count = h->group_count[h->parity];
   p.acc = h->acc;
-  p.done = h->done;
-  p.out_stats = out_stats;
-  p.out_count = out_count;
+  if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[0], s));
   if (mode & AM_SWEEP_CLOSED_LOOP) sweep_tick_kernel<true><<<p.n_tiles, kBlock, 0, s>>>(p);
   else sweep_tick_kernel<false><<<p.n_tiles, kBlock, 0, s>>>(p);
+  if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[1], s));
+  CompactParams c{};
+  c.seg_idx = h->seg_idx;
+  c.seg_act = h->seg_act;
+  c.tile_count = h->tile_count;
+  c.group_count = h->group_count[h->parity];
+  c.group_count_next = h->group_count[h->parity ^ 1];
+  c.acc = h->acc;
+  c.out_idx = d_idx;
+  c.out_act = d_act;
+  c.out_stats = out_stats;
+  c.out_count = out_count;
+  c.n_records = h->n_records;
+  c.n_tiles = p.n_tiles;
+  c.n_groups = (p.n_tiles + kGroupTiles - 1) / kGroupTiles;
+  c.cap = (uint32_t)(cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : cap);
+  compact_kernel<<<c.n_groups, 256, 0, s>>>(c);
+  if (h->profiling) { AM_CUDA(h, cudaEventRecord(h->evp[2], s)); h->profiled = true; }
+  h->parity ^= 1;
+  h->launches++;
   h->launches++;
   AM_CUDA(h, cudaGetLastError());
   return AM_OK;
@@ -242,6 +294,7 @@ int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t
     AM_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     AM_CUDA(h, cudaEventCreate(&h->ev0));
     AM_CUDA(h, cudaEventCreate(&h->ev1));
+    for (int k = 0; k < 3; ++k) AM_CUDA(h, cudaEventCreate(&h->evp[k]));
     for (int k = 0; k < 16; ++k) {
       void* p = nullptr;
       AM_CUDA(h, cudaMalloc(&p, h->cap_padded * kColElem[k]));
@@ -253,12 +306,17 @@ int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t
     fill_u32_kernel<<<1184, 256, 0, h->stream>>>(h->cols.flags, AM_F_TOMBSTONE, h->cap_padded);
     h->launches++;
     const size_t ntiles = h->cap_padded / kTile;
-    AM_CUDA(h, cudaMalloc((void**)&h->tile_desc, ntiles * 8));
-    AM_CUDA(h, cudaMemsetAsync(h->tile_desc, 0, ntiles * 8, h->stream));
+    const size_t ngroups = (ntiles + kGroupTiles - 1) / kGroupTiles;
+    AM_CUDA(h, cudaMalloc((void**)&h->seg_idx, h->cap_padded * 4));
+    AM_CUDA(h, cudaMalloc((void**)&h->seg_act, h->cap_padded));
+    AM_CUDA(h, cudaMalloc((void**)&h->tile_count, ntiles * 4));
+    AM_CUDA(h, cudaMemsetAsync(h->tile_count, 0, ntiles * 4, h->stream));
+    for (int b = 0; b < 2; ++b) {
+      AM_CUDA(h, cudaMalloc((void**)&h->group_count[b], ngroups * 4));
+      AM_CUDA(h, cudaMemsetAsync(h->group_count[b], 0, ngroups * 4, h->stream));
+    }
     AM_CUDA(h, cudaMalloc((void**)&h->acc, kNumAcc * 8));
     AM_CUDA(h, cudaMemsetAsync(h->acc, 0, kNumAcc * 8, h->stream));
-    AM_CUDA(h, cudaMalloc((void**)&h->done, 4));
-    AM_CUDA(h, cudaMemsetAsync(h->done, 0, 4, h->stream));
     for (int b = 0; b < 2; ++b) {
       AM_CUDA(h, cudaMalloc((void**)&h->due_idx[b], h->cap_padded * 4));
       AM_CUDA(h, cudaMalloc((void**)&h->due_action[b], h->cap_padded));
@@ -284,9 +342,11 @@ void am_sweep_destroy(am_sweep_t* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (int k = 0; k < 16; ++k) if (h->col_ptr[k]) cudaFree(h->col_ptr[k]);
-  if (h->tile_desc) cudaFree(h->tile_desc);
+  if (h->seg_idx) cudaFree(h->seg_idx);
+  if (h->seg_act) cudaFree(h->seg_act);
+  if (h->tile_count) cudaFree(h->tile_count);
+  for (int b = 0; b < 2; ++b) if (h->group_count[b]) cudaFree(h->group_count[b]);
   if (h->acc) cudaFree(h->acc);
-  if (h->done) cudaFree(h->done);
   for (int b = 0; b < 2; ++b) {
     if (h->due_idx[b]) cudaFree(h->due_idx[b]);
     if (h->due_action[b]) cudaFree(h->due_action[b]);
@@ -295,6 +355,7 @@ void am_sweep_destroy(am_sweep_t* h) {
   h->pin_in.release(); h->pin_out.release(); h->dev_in.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int k = 0; k < 3; ++k) if (h->evp[k]) cudaEventDestroy(h->evp[k]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -306,6 +367,23 @@ double am_sweep_last_kernel_ms(const am_sweep_t* h) { return h ? h->last_ms : -1
 uint64_t am_sweep_launch_count(const am_sweep_t* h) { return h ? h->launches : 0; }
 void* am_sweep_column_ptr(am_sweep_t* h, int column) {
   return (h && column >= 0 && column < 16) ? h->col_ptr[column] : nullptr;
+}
+int am_sweep_set_profiling(am_sweep_t* h, int on) {
+  if (!h) return AM_E_INVAL;
+  h->profiling = on != 0;
+  h->profiled = false;
+  return AM_OK;
+}
+int am_sweep_last_profile(am_sweep_t* h, double* sweep_ms, double* compact_ms) {
+  if (!h || !h->profiled) return AM_E_INVAL;
+  AM_CUDA(h, cudaSetDevice(h->device));
+  AM_CUDA(h, cudaEventSynchronize(h->evp[2]));
+  float a = 0, b = 0;
+  AM_CUDA(h, cudaEventElapsedTime(&a, h->evp[0], h->evp[1]));
+  AM_CUDA(h, cudaEventElapsedTime(&b, h->evp[1], h->evp[2]));
+  if (sweep_ms) *sweep_ms = a;
+  if (compact_ms) *compact_ms = b;
+  return AM_OK;
 }
 void* am_sweep_stream(am_sweep_t* h) { return h ? (void*)h->stream : nullptr; }
 int am_sweep_set_seed(am_sweep_t* h, uint64_t seed) {
@@ -338,6 +416,7 @@ int am_sweep_upsert(am_sweep_t* h, uint64_t n, const uint64_t* idx, const am_rec
   std::lock_guard<std::mutex> lk(h->mu);
   for (uint64_t k = 0; k < n; ++k) {
     h->up_idx.push_back((uint32_t)idx[k]);
+    h->up_seq.push_back(++h->op_seq);
     am_record_t r = recs[k];
     r.flags &= ~AM_F_TOMBSTONE;
     r.reserved = 0;
@@ -351,7 +430,7 @@ int am_sweep_remove(am_sweep_t* h, uint64_t n, const uint64_t* idx) {
   for (uint64_t k = 0; k < n; ++k)
     if (idx[k] >= h->capacity) return AM_E_RANGE;
   std::lock_guard<std::mutex> lk(h->mu);
-  for (uint64_t k = 0; k < n; ++k) h->rm_idx.push_back((uint32_t)idx[k]);
+  for (uint64_t k = 0; k < n; ++k) { h->rm_idx.push_back((uint32_t)idx[k]); h->rm_seq.push_back(++h->op_seq); }
   return AM_OK;
 }
 
@@ -371,6 +450,7 @@ int am_sweep_post_result(am_sweep_t* h, uint64_t n, const uint64_t* idx, const u
     if (rp != AM_PHASE_NONE) bits |= AM_F_REMEDY_PENDING | (rp == AM_PHASE_SUCCEEDED ? AM_F_REMEDY_OUTCOME_OK : 0u);
     h->res_idx.push_back((uint32_t)idx[k]);
     h->res_bits.push_back(bits);
+    h->res_seq.push_back(++h->op_seq);
   }
   return AM_OK;
 }

@@ -24,13 +24,17 @@
 //     minute&M && hour&H && month&Mo && dayMatches (five ANDs, no loop);
 //   * remedy/counter columns are touched only by lanes whose record has a
 //     posted result (or is due, in closed-loop mode): 56 B/record otherwise;
-//   * emitted (index, action) pairs are compacted IN ORDER: warp ballots +
-//     popc give the in-warp rank, a CTA scan the in-tile rank, and a
-//     decoupled look-back over per-tile descriptors the global rank, all in
-//     one pass over the data;
-//   * per-tick statistics are reduced warp -> CTA -> global; the last CTA to
-//     finish publishes them and re-arms the accumulators, so a tick is exactly
-//     one kernel launch with no memsets.
+//   * emitted (index, action) pairs are compacted IN ORDER without any
+//     dependency between CTAs: warp ballots + popc give the in-warp rank, a CTA
+//     scan the in-tile rank, and the tile writes its entries to its own
+//     segment (offset = first record of the tile) plus one count; a second,
+//     tiny kernel (compact_kernel) turns segments into the contiguous ascending
+//     list.  A single-pass decoupled look-back was measured first and rejected:
+//     in-order completion left SM slots idle (profiles/r01a_lookback_sweep_ncu.csv);
+//   * per-tick statistics are reduced lane -> warp (redux) -> CTA (shared
+//     atomics) -> global (fire-and-forget RED); the kernel boundary before
+//     compact_kernel is the only global synchronisation, so the sweep kernel
+//     has one __syncthreads, no fences and no completion tickets.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -40,7 +44,10 @@
 
 namespace amsweep {
 
-constexpr int kBlock = 256;
+#ifndef AM_BLOCK
+#define AM_BLOCK 256
+#endif
+constexpr int kBlock = AM_BLOCK;
 constexpr int kWarps = kBlock / 32;
 constexpr int kRecPerWarp = 128;             // 2 halves x 32 lanes x 2 records
 constexpr int kTile = kWarps * kRecPerWarp;  // 1024 records per CTA
@@ -65,15 +72,28 @@ struct SweepParams {
   int64_t T;
   uint32_t n_tiles;
   uint32_t mode;
-  uint32_t cap;    // entries in due_idx / due_action
-  uint32_t epoch;  // 30-bit launch stamp of the tile descriptors
-  uint32_t* due_idx;
-  uint8_t* due_action;
-  unsigned long long* tile_desc;  // [n_tiles] {epoch:30, status:2, count:32}
-  unsigned long long* acc;        // [kNumAcc] cross-CTA accumulators (self re-arming)
-  uint32_t* done;                 // CTA completion ticket
-  am_tick_stats_t* out_stats;     // device or mapped-host; may be null
-  uint32_t* out_count;            // may be null
+  uint32_t* seg_idx;         // [n_tiles * kTile] per-tile segments of local indices
+  uint8_t* seg_act;          // [n_tiles * kTile] ... and action bytes
+  uint32_t* tile_count;      // [n_tiles] entries emitted by each tile
+  uint32_t* group_count;     // [n_groups] sum of tile_count over kGroupTiles tiles (zero on entry)
+  unsigned long long* acc;   // [kNumAcc] statistics accumulators (zero on entry)
+};
+
+constexpr int kGroupTiles = 8;  // tiles per compaction group
+
+struct CompactParams {
+  const uint32_t* seg_idx;
+  const uint8_t* seg_act;
+  const uint32_t* tile_count;
+  const uint32_t* group_count;  // this tick's group sums
+  uint32_t* group_count_next;   // the other parity: zeroed here for the next tick
+  unsigned long long* acc;      // read, published, re-armed by the last group
+  uint32_t* out_idx;            // [cap] ascending local indices
+  uint8_t* out_act;             // [cap]
+  am_tick_stats_t* out_stats;   // device or mapped-host; may be null
+  uint32_t* out_count;          // may be null
+  uint64_t n_records;
+  uint32_t n_tiles, n_groups, cap;
 };
 
 // ---- streaming loads / stores: every byte is touched once per tick --------
@@ -81,6 +101,21 @@ template <typename T>
 __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
 template <typename T>
 __device__ __forceinline__ void st_stream(T* p, T v) { __stcs(p, v); }
+
+// Segment entries are written once by the sweep and read once, a few tens of
+// microseconds later, by compact_kernel: keep them L2-resident (evict_last)
+// while 560 MB of evict_first column data streams past them.
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_keep_u32(uint32_t* p, uint32_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keep_u8(uint8_t* p, uint32_t v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
 
 __device__ __forceinline__ uint64_t sm64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;
@@ -168,56 +203,20 @@ __device__ __forceinline__ uint32_t apply_result(RecState& r, int64_t T, uint32_
   return act;
 }
 
-// Decoupled look-back over tile descriptors; executed by warp 0 of the CTA.
-// Descriptor = {epoch:30 | status:2}{count:32}; status 1 = tile aggregate,
-// 2 = inclusive prefix.  A stale epoch reads as "not written yet", so the
-// array never needs clearing between launches.
-__device__ __forceinline__ uint32_t tile_lookback(unsigned long long* desc, uint32_t tile,
-                                                  uint32_t epoch, uint32_t agg, int lane) {
-  const unsigned long long tagA = ((unsigned long long)((epoch << 2) | 1u)) << 32;
-  const unsigned long long tagP = ((unsigned long long)((epoch << 2) | 2u)) << 32;
-  volatile unsigned long long* vd = desc;
-  if (tile == 0) {
-    if (lane == 0) vd[0] = tagP | agg;
-    return 0;
-  }
-  if (lane == 0) vd[tile] = tagA | agg;
-  uint32_t excl = 0;
-  int64_t idx = (int64_t)tile - 1;
-  while (true) {
-    int64_t my = idx - lane;
-    unsigned long long d = (my >= 0) ? vd[my] : tagP;  // before tile 0: prefix 0
-    uint32_t hi = (uint32_t)(d >> 32);
-    uint32_t st = ((hi >> 2) == epoch) ? (hi & 3u) : 0u;
-    unsigned pmask = __ballot_sync(kFull, st == 2u);
-    unsigned invalid = __ballot_sync(kFull, st == 0u);
-    if (pmask) {
-      int first = __ffs(pmask) - 1;
-      if (invalid & ((1u << first) - 1u)) continue;  // a nearer tile is not ready
-      uint32_t v = (lane <= first) ? (uint32_t)d : 0u;
-      excl += __reduce_add_sync(kFull, v);
-      break;
-    }
-    if (invalid) continue;
-    excl += __reduce_add_sync(kFull, (uint32_t)d);
-    idx -= 32;
-  }
-  if (lane == 0) vd[tile] = tagP | (unsigned long long)(excl + agg);
-  return excl;
-}
-
 // ---------------------------------------------------------------------------
 // The sweep.  CLOSED = closed-loop harness: a due record
 // completes in the same tick with its preset outcome.
 // ---------------------------------------------------------------------------
+#ifndef AM_MIN_BLOCKS
+#define AM_MIN_BLOCKS 3
+#endif
 template <bool CLOSED>
-__global__ void __launch_bounds__(kBlock, 2) sweep_tick_kernel(const SweepParams p) {
+__global__ void __launch_bounds__(kBlock, AM_MIN_BLOCKS) sweep_tick_kernel(const SweepParams p) {
   __shared__ TickWords s_words;
   __shared__ uint32_t s_warp_tot[kWarps];
   __shared__ uint32_t s_stat[12];
   __shared__ uint32_t s_xor[2];
   __shared__ uint32_t s_sumrel;
-  __shared__ uint32_t s_base;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -435,59 +434,117 @@ __global__ void __launch_bounds__(kBlock, 2) sweep_tick_kernel(const SweepParams
   }
   __syncthreads();
 
-  // ---- CTA total and global base (decoupled look-back, warp 0) -------------
-  if (warp == 0) {
-    uint32_t v = lane < kWarps ? s_warp_tot[lane] : 0u;
-    const uint32_t tile_total = __reduce_add_sync(kFull, v);
-    const uint32_t excl = tile_lookback(p.tile_desc, tile, p.epoch, tile_total, lane);
-    if (lane == 0) s_base = excl;
-    // flush CTA statistics while the other warps wait
-    if (lane < 12) {
-      const uint32_t sv = s_stat[lane];
-      if (sv) atomicAdd(&p.acc[2 + lane], (unsigned long long)sv);
-    }
-    if (lane == 12 && tile_total) {
-      atomicAdd(&p.acc[1], (unsigned long long)tile_total);
-      atomicXor(&p.acc[14], ((unsigned long long)s_xor[1] << 32) | s_xor[0]);
-      atomicAdd(&p.acc[15], (p.shard_base + tile_base) * (unsigned long long)tile_total + s_sumrel);
-    }
-  }
-  __syncthreads();
-
-  uint32_t base = s_base;
+  // ---- in-tile base, segment write-out, per-tile count ----------------------
+  const uint64_t keep = l2_evict_last_policy();
+  uint32_t base = tile_base, tile_total = 0;
 #pragma unroll
-  for (int k = 0; k < kWarps; ++k) base += (k < warp) ? s_warp_tot[k] : 0u;
+  for (int k = 0; k < kWarps; ++k) {
+    const uint32_t v = s_warp_tot[k];
+    base += (k < warp) ? v : 0u;
+    tile_total += v;
+  }
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
     for (int j = 0; j < 2; ++j)
       if (act[h][j]) {
         const uint32_t pos = base + rank[h][j];
-        if (pos < p.cap) {
-          p.due_idx[pos] = r0[h] + (uint32_t)j;
-          p.due_action[pos] = (uint8_t)act[h][j];
-        }
+        st_keep_u32(p.seg_idx + pos, r0[h] + (uint32_t)j, keep);
+        st_keep_u8(p.seg_act + pos, act[h][j], keep);
       }
-
-  // ---- last CTA out publishes the tick's statistics and re-arms ------------
-  if (tid == 0) {
-    __threadfence();
-    const uint32_t ticket = atomicAdd(p.done, 1u);
-    if (ticket == gridDim.x - 1) {
-      __threadfence();
-      unsigned long long v[kNumAcc];
-#pragma unroll
-      for (int k = 0; k < kNumAcc; ++k) v[k] = atomicExch(&p.acc[k], 0ull);
-      v[0] = p.n_records;
-      if (p.out_stats) {
-        unsigned long long* o = reinterpret_cast<unsigned long long*>(p.out_stats);
-#pragma unroll
-        for (int k = 0; k < kNumAcc; ++k) o[k] = v[k];
-      }
-      if (p.out_count) *p.out_count = (uint32_t)v[1];
-      *p.done = 0;
-      __threadfence_system();
+  if (warp == 0) {  // CTA statistics -> global accumulators (RED, no return value)
+    if (lane < 12) {
+      const uint32_t sv = s_stat[lane];
+      if (sv) atomicAdd(&p.acc[2 + lane], (unsigned long long)sv);
     }
+    if (lane == 12) {
+      p.tile_count[tile] = tile_total;
+      if (tile_total) {
+        atomicAdd(&p.group_count[tile / kGroupTiles], tile_total);
+        atomicXor(&p.acc[14], ((unsigned long long)s_xor[1] << 32) | s_xor[0]);
+        atomicAdd(&p.acc[15], (p.shard_base + tile_base) * (unsigned long long)tile_total + s_sumrel);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Segments -> contiguous ascending list.  One CTA per group of kGroupTiles
+// tiles: its global base is the sum of the earlier groups' counts (a few KB of
+// L2-resident reads), the in-group offsets a kGroupTiles-wide scan; entries just written
+// by the sweep are still in L2.  The last group publishes the tick's
+// statistics and re-arms the accumulators; every group zeroes its slot of the
+// other-parity group counters for the next tick.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) compact_kernel(const CompactParams p) {
+  __shared__ uint32_t s_part[8];
+  __shared__ uint32_t s_off[kGroupTiles + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t g = blockIdx.x;
+
+  uint32_t part = 0;
+  for (uint32_t j = tid; j < g; j += blockDim.x) part += p.group_count[j];
+  part = __reduce_add_sync(kFull, part);
+  if (lane == 0) s_part[warp] = part;
+  if (warp == 0) {  // exclusive scan of this group's tile counts (first kGroupTiles lanes)
+    const uint32_t t = g * kGroupTiles + (uint32_t)lane;
+    const uint32_t c = (lane < kGroupTiles && t < p.n_tiles) ? p.tile_count[t] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int d = 1; d < kGroupTiles; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(kFull, incl, d);
+      if (lane >= d) incl += up;
+    }
+    if (lane < kGroupTiles) s_off[lane] = incl - c;
+    if (lane == kGroupTiles - 1) s_off[kGroupTiles] = incl;
+  }
+  __syncthreads();
+  uint32_t base = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) base += s_part[k];
+  const uint32_t group_total = s_off[kGroupTiles];
+
+  // four independent (index, action) loads in flight per thread
+  for (uint32_t e0 = tid; e0 < group_total; e0 += 4u * blockDim.x) {
+    uint32_t src[4], vi[4], va[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t e = e0 + (uint32_t)u * blockDim.x;
+      int tt = 0;  // which tile of the group holds entry e
+#pragma unroll
+      for (int k = 1; k < kGroupTiles; ++k) tt += (e >= s_off[k]) ? 1 : 0;
+      src[u] = (g * kGroupTiles + (uint32_t)tt) * (uint32_t)kTile + (e - s_off[tt]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool ok = e0 + (uint32_t)u * blockDim.x < group_total;
+      vi[u] = ok ? __ldcs(p.seg_idx + src[u]) : 0u;
+      va[u] = ok ? (uint32_t)__ldcs(p.seg_act + src[u]) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t e = e0 + (uint32_t)u * blockDim.x;
+      const uint32_t pos = base + e;
+      if (e < group_total && pos < p.cap) {
+        p.out_idx[pos] = vi[u];
+        p.out_act[pos] = (uint8_t)va[u];
+      }
+    }
+  }
+  if (tid == 0) p.group_count_next[g] = 0;
+
+  if (g == p.n_groups - 1 && tid == 0) {
+    unsigned long long v[kNumAcc];
+#pragma unroll
+    for (int k = 0; k < kNumAcc; ++k) { v[k] = p.acc[k]; p.acc[k] = 0; }
+    v[0] = p.n_records;
+    v[1] = (unsigned long long)base + group_total;  // n_emitted
+    if (p.out_stats) {
+      unsigned long long* o = reinterpret_cast<unsigned long long*>(p.out_stats);
+#pragma unroll
+      for (int k = 0; k < kNumAcc; ++k) o[k] = v[k];
+    }
+    if (p.out_count) *p.out_count = (uint32_t)v[1];
   }
 }
 

@@ -54,3 +54,75 @@ def allgather_due(idx_local: torch.Tensor, act_local: torch.Tensor, count, shard
     idx = torch.cat([all_idx[r * maxc: r * maxc + counts[r]] for r in range(world)])
     act = torch.cat([all_act[r * maxc: r * maxc + counts[r]] for r in range(world)])
     return idx, act, counts
+
+
+class PeerGather:
+    """B200-native due-list concatenation: one kernel per tick writes every
+    rank's list straight into every peer's output buffer over NVLink
+    (csrc/gather.cu), replacing the counts all-gather + host sync + padded
+    all-gather above.  torch.distributed is used once, at set-up, to swap the
+    CUDA-IPC handles."""
+
+    def __init__(self, device_index: int, cap_total: int, group=None):
+        import ctypes as C
+
+        from . import _lib as L
+        self._L, self._C = L, C
+        self._lib = L.load()
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.cap_total = cap_total
+        self.device = torch.device("cuda", device_index)
+        h = C.c_void_p()
+        rc = self._lib.am_gather_create(C.byref(h), device_index, self.rank, self.world, cap_total)
+        if rc != 0:
+            raise RuntimeError(f"am_gather_create failed: {rc}")
+        self._h = h
+        mine = C.create_string_buffer(L.IPC_HANDLE_BYTES)
+        self._check(self._lib.am_gather_export(self._h, mine), "am_gather_export")
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(mine.raw), group=group)
+            blob = b"".join(handles)
+            self._check(self._lib.am_gather_connect(self._h, blob), "am_gather_connect")
+            dist.barrier(group)
+
+    def _check(self, rc, where):
+        if rc != 0:
+            raise RuntimeError(f"{where}: {rc}: {self._lib.am_gather_last_error(self._h).decode()}")
+
+    def push(self, d_idx_ptr: int, d_act_ptr: int, d_count_ptr: int, shard_base: int, stream: int):
+        self._check(self._lib.am_gather_push(self._h, d_idx_ptr, d_act_ptr, d_count_ptr, shard_base,
+                                             stream or None), "am_gather_push")
+
+    def _wrap(self, ptr: int, n: int, dtype):
+        """zero-copy torch view of library-owned device memory"""
+        class _Arr:
+            pass
+        itemsize = torch.empty(0, dtype=dtype).element_size()
+        typestr = {torch.int64: "<i8", torch.uint8: "|u1", torch.int32: "<i4"}[dtype]
+        a = _Arr()
+        a.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False),
+                                      "version": 3, "strides": (itemsize,)}
+        return torch.as_tensor(a, device=self.device)
+
+    def result(self):
+        """(global idx int64[total], action uint8[total], counts list) — call after
+        the push has retired on its stream (synchronises to read the counts)."""
+        counts_t = self._wrap(self._lib.am_gather_out_counts(self._h), self.world + 1, torch.int32)
+        counts = counts_t.tolist()
+        total = counts[self.world]
+        idx = self._wrap(self._lib.am_gather_out_idx(self._h), max(total, 1), torch.int64)[:total]
+        act = self._wrap(self._lib.am_gather_out_act(self._h), max(total, 1), torch.uint8)[:total]
+        return idx, act, counts[: self.world]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.am_gather_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

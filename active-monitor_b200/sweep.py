@@ -262,6 +262,15 @@ class Sweep:
     def set_seed(self, seed: int):
         self._check(self._lib.am_sweep_set_seed(self._h, seed), "am_sweep_set_seed")
 
+    def set_profiling(self, on: bool):
+        self._check(self._lib.am_sweep_set_profiling(self._h, int(on)), "am_sweep_set_profiling")
+
+    def last_profile(self):
+        """(sweep_tick_kernel ms, compact_kernel ms) of the last tick; waits for it."""
+        a, b = C.c_double(), C.c_double()
+        self._check(self._lib.am_sweep_last_profile(self._h, C.byref(a), C.byref(b)), "am_sweep_last_profile")
+        return a.value, b.value
+
     @property
     def stream(self) -> int:
         """the handle's own cudaStream_t"""

@@ -247,6 +247,12 @@ int am_sweep_device(const am_sweep_t*);
 /* Device time of the last am_sweep_tick / am_sweep_run_ticks sweep kernels
  * (CUDA events on the launching stream), milliseconds; <0 if none. */
 double am_sweep_last_kernel_ms(const am_sweep_t*);
+/* Per-kernel device timing: when on, every tick records CUDA events on the
+ * launching stream around each of its two kernels (sweep_tick_kernel,
+ * compact_kernel).  am_sweep_last_profile waits for the last tick and returns
+ * their durations in milliseconds.  Off by default. */
+int am_sweep_set_profiling(am_sweep_t*, int on);
+int am_sweep_last_profile(am_sweep_t*, double* sweep_ms, double* compact_ms);
 /* Number of kernels this library has launched on the handle so far. */
 uint64_t am_sweep_launch_count(const am_sweep_t*);
 /* Raw device pointer of a column (for zero-copy wrapping by torch / NCCL
@@ -255,6 +261,28 @@ void* am_sweep_column_ptr(am_sweep_t*, int column);
 int am_sweep_set_seed(am_sweep_t*, uint64_t seed);
 /* The handle's own non-blocking stream (cudaStream_t as void*). */
 void* am_sweep_stream(am_sweep_t*);
+
+/* ---- multi-GPU: due-list concatenation over NVLink peer memory --
+ * One am_gather per rank (one process per GPU).  Every rank creates its
+ * exchange block, exports a CUDA-IPC handle, the handles are exchanged by the
+ * caller's plumbing (torch.distributed / any side channel) and connected; then
+ * each tick every rank calls am_gather_push once, after its sweep on the same
+ * stream.  When the push kernel retires, out_idx/out_act on EVERY rank hold the
+ * global ascending (u64 index, u8 action) list and out_counts[0..world) the
+ * per-rank counts, out_counts[world] the total.  No NCCL, no host round-trip.
+ * The reference has no counterpart (single process; consumer is hcc.go:502). */
+#define AM_IPC_HANDLE_BYTES 64
+typedef struct am_gather am_gather_t;
+int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_t cap_total);
+int am_gather_export(am_gather_t*, void* handle_out /* AM_IPC_HANDLE_BYTES */);
+int am_gather_connect(am_gather_t*, const void* handles /* world x AM_IPC_HANDLE_BYTES, rank order */);
+int am_gather_push(am_gather_t*, const void* d_idx_local /* u32 */, const void* d_act_local /* u8 */,
+                   const void* d_count_local /* u32 */, uint64_t shard_base, void* cuda_stream);
+void* am_gather_out_idx(am_gather_t*);    /* u64[cap_total], valid after the last push retires */
+void* am_gather_out_act(am_gather_t*);    /* u8[cap_total]                                    */
+void* am_gather_out_counts(am_gather_t*); /* u32[world+1]                                     */
+const char* am_gather_last_error(const am_gather_t*);
+void am_gather_destroy(am_gather_t*);
 
 /* UTC broken-down time exactly as the kernel computes it (test hook):
  * out[0..6) = sec, min, hour, dom(1-31), month(1-12), dow(0=Sunday). */

@@ -22,8 +22,10 @@ T0 = amgen.T0_MON_0915
 cols = amgen.fill(a.config, a.config, 0, a.n, T0, am.load().am_healthcheck_classify)
 with am.Sweep(capacity=a.n) as s:
     s.load_range(0, cols)
+    s.set_profiling(True)
     for k in range(a.ticks):
         if a.config == 3 and k:  # re-arm the pending results so every tick does the same work
             s.load_range(0, cols)
         idx, act, st = s.tick(T0 + k * a.dt, mode=a.mode)
-        print(k, st["n_emitted"], st["n_submit_hc"], f"{s.last_kernel_ms * 1e3:.1f} us")
+        ka, kb = s.last_profile()
+        print(k, st["n_emitted"], st["n_submit_hc"], f"pair {s.last_kernel_ms * 1e3:.1f} us  sweep {ka * 1e3:.1f} us  compact {kb * 1e3:.1f} us")
