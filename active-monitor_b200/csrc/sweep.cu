@@ -15,7 +15,6 @@
 #include <mutex>
 #include <new>
 #include <string>
-#include <unordered_map>
 #include <vector>
 
 #include "sweep_kernels.cuh"
@@ -80,15 +79,11 @@ struct am_sweep {
   bool profiling = false, profiled = false;
   std::mutex mu;  // guards the staged vectors
   std::atomic_flag ticking = ATOMIC_FLAG_INIT;
-  // staged ops, each stamped with its arrival number (call order is preserved per slot)
-  uint64_t op_seq = 0;
-  std::vector<uint32_t> up_idx;
-  std::vector<am_record_t> up_rec;
-  std::vector<uint64_t> up_seq;
-  std::vector<uint32_t> rm_idx;
-  std::vector<uint64_t> rm_seq;
-  std::vector<uint32_t> res_idx, res_bits;
-  std::vector<uint64_t> res_seq;
+  // staged controller events in arrival order (tick-local sequence numbers)
+  std::vector<StagedOp> ops;
+  std::vector<am_record_t> op_recs;
+  uint32_t n_state_ops = 0, n_result_ops = 0;
+  uint32_t* marks = nullptr;  // [2 * cap_padded] per-slot {latest state op, latest result} of this tick
   PinnedBuf pin_in, pin_out;
   DevBuf dev_in;
   std::string last_error;
@@ -142,74 +137,43 @@ struct TickGuard {
 
 // Apply staged upserts / removes / results (called with the tick guard held).
 int drain_staged(am_sweep* h) {
-  std::vector<uint32_t> up_idx, rm_idx, res_idx, res_bits;
-  std::vector<am_record_t> up_rec;
-  std::vector<uint64_t> up_seq, rm_seq, res_seq;
+  std::vector<StagedOp> ops;
+  std::vector<am_record_t> recs;
+  uint32_t n_state = 0, n_result = 0;
   {
     std::lock_guard<std::mutex> lk(h->mu);
-    up_idx.swap(h->up_idx); up_rec.swap(h->up_rec); up_seq.swap(h->up_seq);
-    rm_idx.swap(h->rm_idx); rm_seq.swap(h->rm_seq);
-    res_idx.swap(h->res_idx); res_bits.swap(h->res_bits); res_seq.swap(h->res_seq);
+    ops.swap(h->ops);
+    recs.swap(h->op_recs);
+    n_state = h->n_state_ops; n_result = h->n_result_ops;
+    h->n_state_ops = h->n_result_ops = 0;
   }
-  if (up_idx.size() + rm_idx.size() + res_idx.size() == 0) return AM_OK;
-  for (uint32_t i : up_idx)  // every upserted slot extends the swept range (high-water mark),
-    if ((uint64_t)i + 1 > h->n_records) h->n_records = (uint64_t)i + 1;  // even if removed again
-  {
-    // Resolve per slot in call order: the latest upsert/remove wins; a result
-    // survives only if it was posted after that slot's latest upsert/remove
-    // (an older one belongs to the replaced CR); of several results the latest.
-    // After this the three scatter kernels touch disjoint / ordered slots.
-    std::unordered_map<uint32_t, uint64_t> state, res_last;
-    state.reserve(up_idx.size() + rm_idx.size());
-    for (size_t k = 0; k < up_idx.size(); ++k) { uint64_t& v = state[up_idx[k]]; if (up_seq[k] > v) v = up_seq[k]; }
-    for (size_t k = 0; k < rm_idx.size(); ++k) { uint64_t& v = state[rm_idx[k]]; if (rm_seq[k] > v) v = rm_seq[k]; }
-    size_t w = 0;
-    for (size_t k = 0; k < up_idx.size(); ++k)
-      if (state[up_idx[k]] == up_seq[k]) { up_idx[w] = up_idx[k]; up_rec[w] = up_rec[k]; ++w; }
-    up_idx.resize(w); up_rec.resize(w);
-    w = 0;
-    for (size_t k = 0; k < rm_idx.size(); ++k)
-      if (state[rm_idx[k]] == rm_seq[k]) rm_idx[w++] = rm_idx[k];
-    rm_idx.resize(w);
-    res_last.reserve(res_idx.size());
-    for (size_t k = 0; k < res_idx.size(); ++k) { uint64_t& v = res_last[res_idx[k]]; if (res_seq[k] > v) v = res_seq[k]; }
-    w = 0;
-    for (size_t k = 0; k < res_idx.size(); ++k) {
-      auto it = state.find(res_idx[k]);
-      const bool newer = it == state.end() || res_seq[k] > it->second;
-      if (newer && res_last[res_idx[k]] == res_seq[k]) { res_idx[w] = res_idx[k]; res_bits[w] = res_bits[k]; ++w; }
-    }
-    res_idx.resize(w); res_bits.resize(w);
-  }
-  const size_t nu = up_idx.size(), nr = rm_idx.size(), np = res_idx.size();
-  if (nu + nr + np == 0) return AM_OK;
-  // layout of the staging block: [up_rec][up_idx][rm_idx][res_idx][res_bits]
-  size_t o_rec = 0, o_ui = o_rec + nu * sizeof(am_record_t), o_rm = o_ui + nu * 4,
-         o_ri = o_rm + nr * 4, o_rb = o_ri + np * 4, total = o_rb + np * 4;
+  const size_t n = ops.size();
+  if (n == 0) return AM_OK;
+  for (const StagedOp& op : ops)  // every upserted slot extends the swept range (high-water mark)
+    if (op.kind == kOpUpsert && (uint64_t)op.idx + 1 > h->n_records) h->n_records = (uint64_t)op.idx + 1;
+  const size_t o_ops = 0, o_rec = (n * sizeof(StagedOp) + 255) / 256 * 256,
+               total = o_rec + recs.size() * sizeof(am_record_t);
   AM_CUDA(h, h->pin_in.reserve(total));
   AM_CUDA(h, h->dev_in.reserve(total));
   char* hp = (char*)h->pin_in.p;
-  if (nu) { memcpy(hp + o_rec, up_rec.data(), nu * sizeof(am_record_t)); memcpy(hp + o_ui, up_idx.data(), nu * 4); }
-  if (nr) memcpy(hp + o_rm, rm_idx.data(), nr * 4);
-  if (np) { memcpy(hp + o_ri, res_idx.data(), np * 4); memcpy(hp + o_rb, res_bits.data(), np * 4); }
+  memcpy(hp + o_ops, ops.data(), n * sizeof(StagedOp));
+  if (!recs.empty()) memcpy(hp + o_rec, recs.data(), recs.size() * sizeof(am_record_t));
   AM_CUDA(h, cudaMemcpyAsync(h->dev_in.p, hp, total, cudaMemcpyHostToDevice, h->stream));
-  char* dp = (char*)h->dev_in.p;
-  const int B = 256;
-  // slots of the three kernels are disjoint (removes vs upserts) or ordered (results last)
-  if (nr) {
-    tombstone_kernel<<<(unsigned)((nr + B - 1) / B), B, 0, h->stream>>>(h->cols.flags, (const uint32_t*)(dp + o_rm), (uint32_t)nr);
+  const StagedOp* d_ops = (const StagedOp*)((char*)h->dev_in.p + o_ops);
+  const am_record_t* d_recs = (const am_record_t*)((char*)h->dev_in.p + o_rec);
+  const unsigned B = 256, G = (unsigned)((n + B - 1) / B);
+  mark_ops_kernel<<<G, B, 0, h->stream>>>(h->marks, d_ops, (uint32_t)n);
+  h->launches++;
+  if (n_state) {
+    apply_state_ops_kernel<<<G, B, 0, h->stream>>>(h->cols, h->marks, d_ops, d_recs, (uint32_t)n);
     h->launches++;
   }
-  if (nu) {
-    scatter_records_kernel<<<(unsigned)((nu + B - 1) / B), B, 0, h->stream>>>(
-        h->cols, (const uint32_t*)(dp + o_ui), (const am_record_t*)(dp + o_rec), (uint32_t)nu);
+  if (n_result) {
+    apply_result_ops_kernel<<<G, B, 0, h->stream>>>(h->cols.flags, h->marks, d_ops, (uint32_t)n);
     h->launches++;
   }
-  if (np) {
-    post_result_kernel<<<(unsigned)((np + B - 1) / B), B, 0, h->stream>>>(
-        h->cols.flags, (const uint32_t*)(dp + o_ri), (const uint32_t*)(dp + o_rb), (uint32_t)np);
-    h->launches++;
-  }
+  clear_marks_kernel<<<G, B, 0, h->stream>>>(h->marks, d_ops, (uint32_t)n);
+  h->launches++;
   AM_CUDA(h, cudaGetLastError());
   // the staging block is reused by the next drain: wait until the copy was consumed
   AM_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -317,6 +281,8 @@ int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t
     }
     AM_CUDA(h, cudaMalloc((void**)&h->acc, kNumAcc * 8));
     AM_CUDA(h, cudaMemsetAsync(h->acc, 0, kNumAcc * 8, h->stream));
+    AM_CUDA(h, cudaMalloc((void**)&h->marks, h->cap_padded * 8));
+    AM_CUDA(h, cudaMemsetAsync(h->marks, 0, h->cap_padded * 8, h->stream));
     for (int b = 0; b < 2; ++b) {
       AM_CUDA(h, cudaMalloc((void**)&h->due_idx[b], h->cap_padded * 4));
       AM_CUDA(h, cudaMalloc((void**)&h->due_action[b], h->cap_padded));
@@ -347,6 +313,7 @@ void am_sweep_destroy(am_sweep_t* h) {
   if (h->tile_count) cudaFree(h->tile_count);
   for (int b = 0; b < 2; ++b) if (h->group_count[b]) cudaFree(h->group_count[b]);
   if (h->acc) cudaFree(h->acc);
+  if (h->marks) cudaFree(h->marks);
   for (int b = 0; b < 2; ++b) {
     if (h->due_idx[b]) cudaFree(h->due_idx[b]);
     if (h->due_action[b]) cudaFree(h->due_action[b]);
@@ -414,14 +381,18 @@ int am_sweep_upsert(am_sweep_t* h, uint64_t n, const uint64_t* idx, const am_rec
   for (uint64_t k = 0; k < n; ++k)
     if (idx[k] >= h->capacity) return AM_E_RANGE;
   std::lock_guard<std::mutex> lk(h->mu);
+  if (h->ops.size() + n > 0xFFFFFFF0ull) return AM_E_NOSPACE;
+  const size_t o = h->ops.size(), r = h->op_recs.size();
+  h->ops.resize(o + n);
+  h->op_recs.resize(r + n);
   for (uint64_t k = 0; k < n; ++k) {
-    h->up_idx.push_back((uint32_t)idx[k]);
-    h->up_seq.push_back(++h->op_seq);
-    am_record_t r = recs[k];
-    r.flags &= ~AM_F_TOMBSTONE;
-    r.reserved = 0;
-    h->up_rec.push_back(r);
+    h->ops[o + k] = StagedOp{(uint32_t)idx[k], (uint32_t)(o + k + 1), kOpUpsert, (uint32_t)(r + k)};
+    am_record_t rec = recs[k];
+    rec.flags &= ~AM_F_TOMBSTONE;
+    rec.reserved = 0;
+    h->op_recs[r + k] = rec;
   }
+  h->n_state_ops += (uint32_t)n;
   return AM_OK;
 }
 
@@ -430,7 +401,11 @@ int am_sweep_remove(am_sweep_t* h, uint64_t n, const uint64_t* idx) {
   for (uint64_t k = 0; k < n; ++k)
     if (idx[k] >= h->capacity) return AM_E_RANGE;
   std::lock_guard<std::mutex> lk(h->mu);
-  for (uint64_t k = 0; k < n; ++k) { h->rm_idx.push_back((uint32_t)idx[k]); h->rm_seq.push_back(++h->op_seq); }
+  if (h->ops.size() + n > 0xFFFFFFF0ull) return AM_E_NOSPACE;
+  const size_t o = h->ops.size();
+  h->ops.resize(o + n);
+  for (uint64_t k = 0; k < n; ++k) h->ops[o + k] = StagedOp{(uint32_t)idx[k], (uint32_t)(o + k + 1), kOpRemove, 0};
+  h->n_state_ops += (uint32_t)n;
   return AM_OK;
 }
 
@@ -442,16 +417,18 @@ int am_sweep_post_result(am_sweep_t* h, uint64_t n, const uint64_t* idx, const u
     if (phase[k] > AM_PHASE_FAILED || (remedy_phase && remedy_phase[k] > AM_PHASE_FAILED)) return AM_E_INVAL;
   }
   std::lock_guard<std::mutex> lk(h->mu);
+  if (h->ops.size() + n > 0xFFFFFFF0ull) return AM_E_NOSPACE;
+  const size_t o = h->ops.size();
+  h->ops.resize(o + n);
   for (uint64_t k = 0; k < n; ++k) {
     uint32_t bits = 0;
     if (phase[k] == AM_PHASE_SUCCEEDED) bits |= AM_F_PENDING_OK;
     else if (phase[k] == AM_PHASE_FAILED) bits |= AM_F_PENDING_FAIL;
     const uint8_t rp = remedy_phase ? remedy_phase[k] : AM_PHASE_NONE;
     if (rp != AM_PHASE_NONE) bits |= AM_F_REMEDY_PENDING | (rp == AM_PHASE_SUCCEEDED ? AM_F_REMEDY_OUTCOME_OK : 0u);
-    h->res_idx.push_back((uint32_t)idx[k]);
-    h->res_bits.push_back(bits);
-    h->res_seq.push_back(++h->op_seq);
+    h->ops[o + k] = StagedOp{(uint32_t)idx[k], (uint32_t)(o + k + 1), kOpResult, bits};
   }
+  h->n_result_ops += (uint32_t)n;
   return AM_OK;
 }
 

@@ -548,19 +548,47 @@ __global__ void __launch_bounds__(256) compact_kernel(const CompactParams p) {
   }
 }
 
-// ---- small maintenance kernels (upsert / remove / post_result / read) -------
+// ---- small maintenance kernels (create / read) -----------------------------
 __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, uint64_t n) {
   uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) p[i] = v;
 }
 
-__global__ void scatter_records_kernel(DevCols c, const uint32_t* __restrict__ idx,
-                                       const am_record_t* __restrict__ recs, uint32_t n) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+// ---- staged controller events (upsert / remove / post_result) ---------------
+// Events reach the library from many goroutines between two ticks; per slot
+// they must take effect in call order.  Each event carries a tick-local
+// sequence number (1-based).  mark: atomicMax of the sequence into the slot's
+// mark pair {latest upsert/remove, latest result}; apply: only the marked
+// winners write — the latest upsert/remove, then the latest result if it was
+// posted after it (an older result belongs to the replaced CR); clear: marks
+// back to zero.  No host-side hashing or sorting.
+struct StagedOp {
+  uint32_t idx;   // local slot
+  uint32_t seq;   // 1-based arrival number within the tick
+  uint32_t kind;  // 0 upsert (arg = index into the record array), 1 remove, 2 result (arg = flag bits)
+  uint32_t arg;
+};
+constexpr uint32_t kOpUpsert = 0, kOpRemove = 1, kOpResult = 2;
+
+__global__ void mark_ops_kernel(uint32_t* marks, const StagedOp* __restrict__ ops, uint32_t n) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const uint32_t i = idx[k];
-  const am_record_t r = recs[k];
+  const StagedOp op = ops[k];
+  atomicMax(&marks[2u * op.idx + (op.kind == kOpResult ? 1u : 0u)], op.seq);
+}
+
+// upserts (hcc.go:170-188 Reconcile) and removes (hcc.go:175-186)
+__global__ void apply_state_ops_kernel(DevCols c, const uint32_t* __restrict__ marks,
+                                       const StagedOp* __restrict__ ops,
+                                       const am_record_t* __restrict__ recs, uint32_t n) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const StagedOp op = ops[k];
+  if (op.kind == kOpResult || marks[2u * op.idx] != op.seq) return;
+  const uint32_t i = op.idx;
+  if (op.kind == kOpRemove) { c.flags[i] = AM_F_TOMBSTONE; return; }
+  const am_record_t r = recs[op.arg];
   c.minute[i] = r.minute; c.hour[i] = r.hour; c.dom[i] = r.dom; c.month[i] = r.month; c.dow[i] = r.dow;
   c.ras[i] = r.ras; c.flags[i] = r.flags; c.finished_at[i] = r.finished_at;
   c.runs_limit[i] = r.runs_limit; c.reset_interval[i] = r.reset_interval;
@@ -569,19 +597,25 @@ __global__ void scatter_records_kernel(DevCols c, const uint32_t* __restrict__ i
   c.remedy_finished_at[i] = r.remedy_finished_at;
 }
 
-__global__ void tombstone_kernel(uint32_t* flags, const uint32_t* __restrict__ idx, uint32_t n) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n) flags[idx[k]] = AM_F_TOMBSTONE;
+// terminal phases observed by the watch loops (hcc.go:635/:662/:821/:836)
+__global__ void apply_result_ops_kernel(uint32_t* flags, const uint32_t* __restrict__ marks,
+                                        const StagedOp* __restrict__ ops, uint32_t n) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const StagedOp op = ops[k];
+  if (op.kind != kOpResult) return;
+  const uint32_t s = marks[2u * op.idx], r = marks[2u * op.idx + 1u];
+  if (r != op.seq || op.seq < s) return;
+  const uint32_t m = AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK;
+  flags[op.idx] = (flags[op.idx] & ~m) | (op.arg & m);
 }
 
-// bits: the AM_F_PENDING_* / AM_F_REMEDY_* flags to install (hcc.go:635/:662/:821/:836)
-__global__ void post_result_kernel(uint32_t* flags, const uint32_t* __restrict__ idx,
-                                   const uint32_t* __restrict__ bits, uint32_t n) {
-  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void clear_marks_kernel(uint32_t* marks, const StagedOp* __restrict__ ops, uint32_t n) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const uint32_t m = AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK;
-  const uint32_t i = idx[k];
-  flags[i] = (flags[i] & ~m) | (bits[k] & m);
+  const uint32_t i = ops[k].idx;
+  marks[2u * i] = 0;
+  marks[2u * i + 1u] = 0;
 }
 
 __global__ void gather_records_kernel(DevCols c, const uint32_t* __restrict__ idx, am_record_t* out,

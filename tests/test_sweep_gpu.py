@@ -316,3 +316,39 @@ def test_full_size_10m_properties(am, gen):
             s.load_range(0, cols)
             parts.append(s.tick(T0)[0])
     np.testing.assert_array_equal(np.concatenate(parts), idx)
+
+
+def test_staged_events_take_effect_in_call_order(am):
+    """Reconcile workers and watch loops call in between two ticks; per slot the
+    calls must take effect in order (resolved on the device, csrc/sweep_kernels.cuh)."""
+    T = T0
+    def rec(ras, fin):
+        rc, r = am.classify(repeat_after_sec=ras, finished_at=fin)
+        assert rc == 0
+        return r
+    A, B = rec(60, T - 1000), rec(7, T - 1)          # A is due at T, B is not
+    with am.Sweep(capacity=64) as s:
+        s.upsert([0], A); s.remove([0])              # created then deleted      -> gone
+        s.remove([1]); s.upsert([1], A)              # deleted then re-created   -> present, due
+        s.upsert([2], A); s.upsert([2], B)           # two reconciles            -> the later spec
+        s.upsert([3], B); s.upsert([3], A)
+        s.upsert([4], A)
+        s.post_result([4], [am.PHASE_FAILED]); s.upsert([4], B)   # result of the replaced CR is dropped
+        s.upsert([5], B); s.post_result([5], [am.PHASE_SUCCEEDED])  # result after the upsert applies
+        s.upsert([6], B)
+        s.post_result([6], [am.PHASE_SUCCEEDED]); s.post_result([6], [am.PHASE_FAILED])  # last result wins
+        s.upsert(np.array([7, 7, 7]), np.concatenate([A, B, A]))  # duplicates inside one call: last wins
+        idx, act, st = s.tick(T)
+        got = dict(zip(idx.tolist(), act.tolist()))
+        assert got == {1: am.ACT_SUBMIT_HC, 3: am.ACT_SUBMIT_HC, 7: am.ACT_SUBMIT_HC}, got
+        cols = s.read_range(0, 8)
+        assert cols["flags"][0] == am.F_TOMBSTONE
+        assert cols["ras"].tolist()[1:8] == [60, 7, 60, 7, 7, 7, 60]
+        assert cols["failed"][4] == 0 and cols["finished_at"][4] == T - 1     # dropped result
+        assert cols["success"][5] == 1 and cols["finished_at"][5] == T        # applied result
+        assert cols["failed"][6] == 1 and cols["success"][6] == 0             # FAILED posted last
+        assert st["n_result_ok"] == 1 and st["n_result_fail"] == 1 and s.size == 8
+        # marks are cleared: the next tick sees no stale ordering state
+        s.post_result([5], [am.PHASE_FAILED])
+        _, _, st2 = s.tick(T + 1)
+        assert st2["n_result_fail"] == 1 and s.read([5])["failed"][0] == 1
