@@ -159,6 +159,8 @@ def main():
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="records per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="N>1: NVLink peer-write kernel (csrc/gather.cu) or the padded NCCL all-gather")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -197,13 +199,18 @@ def main():
     d_st = torch.zeros(16, dtype=torch.int64, device=dev)
     stream = torch.cuda.Stream(device=dev)  # explicit stream: kernels, events and NCCL all on it
     torch.cuda.set_stream(stream)
+    peer = None
+    if world > 1 and args.gather == "peer":
+        peer = gather.PeerGather(local_rank, cap_total=n * world)
 
     def step(k):
         # BASELINE configs[1] is ONE tick: every step is that tick (T0, on the minute,
         # open loop => idempotent), over inputs 4.4x larger than L2
         sweep.tick_device(T0, 0, d_idx.data_ptr(), d_act.data_ptr(), n, d_cnt.data_ptr(),
                           d_st.data_ptr(), stream.cuda_stream)
-        if world > 1:
+        if peer is not None:  # one kernel: counts + lists written into every peer over NVLink
+            peer.push(d_idx.data_ptr(), d_act.data_ptr(), d_cnt.data_ptr(), base, stream.cuda_stream)
+        elif world > 1:
             return gather.allgather_due(d_idx, d_act, d_cnt, base)
         return None
 
@@ -337,7 +344,9 @@ def main():
                                    "repeatAfterSec (tools/amgen config 2, seed 2); step = the single tick T0=2026-09-21T09:15:00Z",
                        "records_per_gpu": n, "records_total": n * world,
                        "l2": "inputs (560 MB/GPU) larger than L2 (126 MB); no flush needed",
-                       "parallelism": f"index-range shards x{world}" + (", NCCL all-gather of due lists" if world > 1 else ""),
+                       "parallelism": f"index-range shards x{world}" + (
+                           "" if world == 1 else (", due lists concatenated by the NVLink peer-write kernel"
+                                                  if peer is not None else ", padded NCCL all-gather of due lists")),
                        "due_per_tick": stats["n_submit_hc"], "emitted_per_tick": stats["n_emitted"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
@@ -355,6 +364,8 @@ def main():
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
+        if peer is not None:
+            peer.close()
         dist.destroy_process_group()
 
 
