@@ -220,13 +220,13 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    # warm-up: at least W steps and ~0.4 s of load so clocks settle
-    t_w = time.perf_counter()
-    w = 0
-    while w < args.warmup or time.perf_counter() - t_w < 0.4:
-        step(-1 - w)
-        w += 1
-        if w % 64 == 0:
+    # Every rank must run the SAME number of steps (each step ends in a cross-GPU
+    # exchange at N>1), so warm-up and the trailing clock-sampling load are counted,
+    # never timed: at least W steps and ~0.4 s of load so clocks settle.
+    w = max(args.warmup, 3000)
+    for i in range(w):
+        step(-1 - i)
+        if i % 256 == 255:
             torch.cuda.synchronize()
     barrier()
     launches0 = sweep.launch_count
@@ -238,20 +238,21 @@ def main():
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = sweep.launch_count - launches0
+    launches = sweep.launch_count - launches0 + (args.steps if peer is not None else 0)
     stats = dict(zip(am.abi.STAT_FIELDS, [int(v) for v in d_st.cpu().tolist()]))
-    # keep the identical load running until the clock sampler has seen it
-    if sampler:
-        k = args.steps
-        while sampler.n_since(t_load0) < 6 and time.perf_counter() - t_load0 < 3.0:
-            for _ in range(32):
-                step(k); k += 1
-            torch.cuda.synchronize()
-    t_load1 = time.perf_counter()
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # keep the identical load running ~0.8 s more (same count on every rank) so the
+    # 100 ms nvidia-smi sampler sees the GPU under exactly this load
+    extra = min(20000, max(64, int(0.8 / max(ms / args.steps * 1e-3, 1e-6))))
+    for k in range(extra):
+        step(k)
+        if k % 256 == 255:
+            torch.cuda.synchronize()
+    barrier()
+    t_load1 = time.perf_counter()
     clocks = sampler.stop(t_load0, t_load1) if sampler else None
 
     # ---- per-kernel durations for the roofline (CUDA events on the launching stream
