@@ -131,7 +131,7 @@ SYMBOLS = {
     "am_sweep_column_ptr": (C.c_void_p, [C.c_void_p, C.c_int]),
     "am_sweep_set_seed": (C.c_int, [C.c_void_p, u64]),
     "am_sweep_stream": (C.c_void_p, [C.c_void_p]),
-    "am_gather_create": (C.c_int, [P(C.c_void_p), C.c_int, C.c_int, C.c_int, u64]),
+    "am_gather_create": (C.c_int, [P(C.c_void_p), C.c_int, C.c_int, C.c_int, u64, C.c_int]),
     "am_gather_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "am_gather_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "am_gather_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, u64, C.c_void_p]),

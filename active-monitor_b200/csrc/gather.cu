@@ -56,6 +56,7 @@ struct PushParams {
   size_t off_idx[2], off_act[2];  // byte offsets of the two output buffers in a block
   uint32_t epoch;
   int rank, world;
+  int idx_bytes;  // 4: u32 global indices on the wire and in the output, 8: u64
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -90,16 +91,32 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const PushParams p) {
     if (r < p.rank) offset += s_count[r];
     total += s_count[r];
   }
-  // 3. write my list into every peer's output buffer at `offset`
+  // 3. write my list into every peer's output buffer at `offset`: 4 entries in
+  //    flight per thread, each stored to all peers (NVSwitch: every peer at full
+  //    bandwidth; warp-level stores coalesce into 128 B / 32 B NVLink writes)
   const int buf = p.epoch & 1;
   const uint64_t room = offset < p.cap_total ? p.cap_total - offset : 0;
   const uint64_t n = my_count < room ? my_count : room;
-  for (uint64_t e = blockIdx.x * (uint64_t)blockDim.x + tid; e < n; e += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t g = p.shard_base + p.idx_local[e];
-    const uint8_t a = p.act_local[e];
-    for (int r = 0; r < p.world; ++r) {
-      reinterpret_cast<uint64_t*>(p.peer[r] + p.off_idx[buf])[offset + e] = g;
-      (p.peer[r] + p.off_act[buf])[offset + e] = a;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t e0 = blockIdx.x * (uint64_t)blockDim.x + tid; e0 < n; e0 += 4 * stride) {
+    uint32_t li[4];
+    uint8_t la[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t e = e0 + (uint64_t)u * stride;
+      li[u] = e < n ? __ldcs(p.idx_local + e) : 0u;
+      la[u] = e < n ? __ldcs(p.act_local + e) : (uint8_t)0;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t e = e0 + (uint64_t)u * stride;
+      if (e >= n) continue;
+      const uint64_t g = p.shard_base + li[u];
+      for (int r = 0; r < p.world; ++r) {
+        if (p.idx_bytes == 4) reinterpret_cast<uint32_t*>(p.peer[r] + p.off_idx[buf])[offset + e] = (uint32_t)g;
+        else reinterpret_cast<uint64_t*>(p.peer[r] + p.off_idx[buf])[offset + e] = g;
+        (p.peer[r] + p.off_act[buf])[offset + e] = la[u];
+      }
     }
   }
   // 4. completion: last CTA raises my done flag everywhere, then waits for all peers
@@ -129,6 +146,8 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const PushParams p) {
 struct am_gather {
   int device = 0, rank = 0, world = 1;
   uint64_t cap_total = 0;
+  int idx_bytes = 8;
+  int n_ctas = 296;
   size_t block_bytes = 0;
   size_t off_idx[2] = {0, 0}, off_act[2] = {0, 0};
   unsigned char* block = nullptr;                 // my exchange block (cudaMalloc, IPC-exported)
@@ -153,12 +172,15 @@ struct am_gather {
 
 extern "C" {
 
-int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_t cap_total) {
+int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_t cap_total,
+                     int idx_bytes) {
   if (!out || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || cap_total == 0) return AM_E_INVAL;
+  if (idx_bytes != 4 && idx_bytes != 8) return AM_E_INVAL;
   *out = nullptr;
   am_gather* g = new (std::nothrow) am_gather();
   if (!g) return AM_E_NOMEM;
   g->device = device; g->rank = rank; g->world = world; g->cap_total = cap_total;
+  g->idx_bytes = idx_bytes;
   auto align = [](size_t v) { return (v + 255) / 256 * 256; };
   size_t off = align(sizeof(ExchangeHeader));
   for (int b = 0; b < 2; ++b) { g->off_idx[b] = off; off = align(off + cap_total * 8); }
@@ -166,6 +188,9 @@ int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_
   g->block_bytes = off;
   int rc = [&]() -> int {
     AMG_CUDA(g, cudaSetDevice(device));
+    int sms = 148;
+    AMG_CUDA(g, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    g->n_ctas = 2 * sms;
     AMG_CUDA(g, cudaMalloc((void**)&g->block, g->block_bytes));
     AMG_CUDA(g, cudaMemset(g->block, 0, g->block_bytes));
     AMG_CUDA(g, cudaMalloc((void**)&g->out_counts, (kMaxWorld + 1) * 4));
@@ -224,7 +249,9 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
   p.epoch = g->epoch;
   p.rank = g->rank;
   p.world = g->world;
-  gather_push_kernel<<<32, 256, 0, (cudaStream_t)cuda_stream>>>(p);
+  p.idx_bytes = g->idx_bytes;
+  if (p.idx_bytes == 4 && shard_base > 0xFFFFFFFFull) return AM_E_RANGE;
+  gather_push_kernel<<<g->n_ctas, 256, 0, (cudaStream_t)cuda_stream>>>(p);
   AMG_CUDA(g, cudaGetLastError());
   return AM_OK;
 }

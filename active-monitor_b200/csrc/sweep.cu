@@ -194,6 +194,7 @@ int launch_sweep(am_sweep* h, int64_t T, uint32_t mode, uint32_t* d_idx, uint8_t
   p.shard_base = h->shard_base;
   p.seed = h->seed;
   p.T = T;
+  p.words = tick_words_from_unix(T);
   p.n_tiles = (uint32_t)((h->n_records + kTile - 1) / kTile);
   p.mode = mode;
   p.seg_idx = h->seg_idx;

@@ -19,9 +19,10 @@
 //     16 B (two u64 records) or 8 B (two i32 records) at column + (w + 2L),
 //     twice per tile ("halves"), so 16 independent loads are in flight per
 //     lane before the first use;
-//   * the tick's broken-down time is computed once per CTA and staged in
-//     shared memory as one-hot words; a 5-field schedule fires iff
-//     minute&M && hour&H && month&Mo && dayMatches (five ANDs, no loop);
+//   * the tick's broken-down time is computed once per tick as one-hot words
+//     and reaches every CTA through the kernel parameters (constant bank); a
+//     5-field schedule fires iff minute&M && hour&H && month&Mo && dayMatches
+//     (five ANDs, no loop);
 //   * remedy/counter columns are touched only by lanes whose record has a
 //     posted result (or is due, in closed-loop mode): 56 B/record otherwise;
 //   * emitted (index, action) pairs are compacted IN ORDER without any
@@ -70,6 +71,7 @@ struct SweepParams {
   uint64_t shard_base;
   uint64_t seed;
   int64_t T;
+  TickWords words;  // T's UTC fields as one-hot words, computed once per tick by the launcher
   uint32_t n_tiles;
   uint32_t mode;
   uint32_t* seg_idx;         // [n_tiles * kTile] per-tile segments of local indices
@@ -212,11 +214,12 @@ __device__ __forceinline__ uint32_t apply_result(RecState& r, int64_t T, uint32_
 #endif
 template <bool CLOSED>
 __global__ void __launch_bounds__(kBlock, AM_MIN_BLOCKS) sweep_tick_kernel(const SweepParams p) {
-  __shared__ TickWords s_words;
+  // one row per warp, written unconditionally: no zero-initialisation, no shared
+  // atomics, and therefore a single __syncthreads in the whole kernel
   __shared__ uint32_t s_warp_tot[kWarps];
-  __shared__ uint32_t s_stat[12];
-  __shared__ uint32_t s_xor[2];
-  __shared__ uint32_t s_sumrel;
+  __shared__ uint32_t s_wstat[kWarps][12];
+  __shared__ uint32_t s_wxor[kWarps][2];
+  __shared__ uint32_t s_wsum[kWarps];
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -262,12 +265,11 @@ __global__ void __launch_bounds__(kBlock, AM_MIN_BLOCKS) sweep_tick_kernel(const
     }
   }
 
-  // ---- stage the tick's broken-down time in shared memory ----------------
-  if (tid == 0) s_words = tick_words_from_unix(T);
-  if (tid < 12) s_stat[tid] = 0;
-  if (tid == 12) { s_xor[0] = 0; s_xor[1] = 0; s_sumrel = 0; }
-  __syncthreads();
-  const TickWords w = s_words;
+  // The tick's broken-down time: one-hot words computed once per tick (civil.h) and
+  // delivered through the kernel parameters, i.e. the constant bank / uniform
+  // registers — cheaper than staging them in shared memory, which cost every CTA a
+  // serial thread-0 section and a barrier (profiles/r01_summary.md).
+  const TickWords w = p.words;
 
   uint32_t act[2][2];
   uint32_t st0 = 0, st1 = 0, st2 = 0, st3 = 0;  // packed per-lane statistics
@@ -397,40 +399,39 @@ __global__ void __launch_bounds__(kBlock, AM_MIN_BLOCKS) sweep_tick_kernel(const
   rank[1][1] = rank[1][0] + (act[1][0] != 0);
   if (lane == 0) s_warp_tot[warp] = warp_total;
 
-  // ---- statistics: lane -> warp (redux) -> CTA (shared atomics) ------------
-  if (__any_sync(kFull, (st0 | st1 | st2 | st3) != 0)) {
-    const uint32_t q0 = __reduce_add_sync(kFull, st0);  // 4 x 8-bit action counts
-    const uint32_t q1 = __reduce_add_sync(kFull, st1);
-    const uint32_t q2 = __reduce_add_sync(kFull, st2);  // 2 x 16-bit result counts
-    const uint32_t q3 = __reduce_add_sync(kFull, st3);
+  // ---- statistics: lane -> warp (redux) -> per-warp shared row ---------------
+  {
+    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+    if (__any_sync(kFull, (st0 | st1 | st2 | st3) != 0)) {
+      q0 = __reduce_add_sync(kFull, st0);  // 4 x 8-bit action counts
+      q1 = __reduce_add_sync(kFull, st1);
+      q2 = __reduce_add_sync(kFull, st2);  // 2 x 16-bit result counts
+      q3 = __reduce_add_sync(kFull, st3);
+    }
     if (lane < 12) {
       uint32_t v;
       if (lane < 8) v = ((lane < 4 ? q0 : q1) >> ((lane & 3) * 8)) & 0xFFu;
       else v = ((lane < 10 ? q2 : q3) >> ((lane & 1) * 16)) & 0xFFFFu;
-      if (v) atomicAdd(&s_stat[lane], v);
+      s_wstat[warp][lane] = v;
     }
-  }
-  if (warp_total) {
     uint32_t xl = 0, xh = 0, rel = 0;
+    if (warp_total) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < 2; ++h)
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
-        if (act[h][j]) {
-          const uint32_t local = r0[h] + (uint32_t)j;
-          const uint64_t g = p.shard_base + local;
-          xl ^= (uint32_t)g;
-          xh ^= (uint32_t)(g >> 32);
-          rel += local - tile_base;
-        }
-    xl = __reduce_xor_sync(kFull, xl);
-    xh = __reduce_xor_sync(kFull, xh);
-    rel = __reduce_add_sync(kFull, rel);
-    if (lane == 0) {
-      atomicXor(&s_xor[0], xl);
-      atomicXor(&s_xor[1], xh);
-      atomicAdd(&s_sumrel, rel);
+        for (int j = 0; j < 2; ++j)
+          if (act[h][j]) {
+            const uint32_t local = r0[h] + (uint32_t)j;
+            const uint64_t g = p.shard_base + local;
+            xl ^= (uint32_t)g;
+            xh ^= (uint32_t)(g >> 32);
+            rel += local - tile_base;
+          }
+      xl = __reduce_xor_sync(kFull, xl);
+      xh = __reduce_xor_sync(kFull, xh);
+      rel = __reduce_add_sync(kFull, rel);
     }
+    if (lane == 0) { s_wxor[warp][0] = xl; s_wxor[warp][1] = xh; s_wsum[warp] = rel; }
   }
   __syncthreads();
 
@@ -454,15 +455,20 @@ __global__ void __launch_bounds__(kBlock, AM_MIN_BLOCKS) sweep_tick_kernel(const
       }
   if (warp == 0) {  // CTA statistics -> global accumulators (RED, no return value)
     if (lane < 12) {
-      const uint32_t sv = s_stat[lane];
+      uint32_t sv = 0;
+#pragma unroll
+      for (int k = 0; k < kWarps; ++k) sv += s_wstat[k][lane];
       if (sv) atomicAdd(&p.acc[2 + lane], (unsigned long long)sv);
     }
     if (lane == 12) {
       p.tile_count[tile] = tile_total;
       if (tile_total) {
+        uint32_t xl = 0, xh = 0, rel = 0;
+#pragma unroll
+        for (int k = 0; k < kWarps; ++k) { xl ^= s_wxor[k][0]; xh ^= s_wxor[k][1]; rel += s_wsum[k]; }
         atomicAdd(&p.group_count[tile / kGroupTiles], tile_total);
-        atomicXor(&p.acc[14], ((unsigned long long)s_xor[1] << 32) | s_xor[0]);
-        atomicAdd(&p.acc[15], (p.shard_base + tile_base) * (unsigned long long)tile_total + s_sumrel);
+        atomicXor(&p.acc[14], ((unsigned long long)xh << 32) | xl);
+        atomicAdd(&p.acc[15], (p.shard_base + tile_base) * (unsigned long long)tile_total + rel);
       }
     }
   }

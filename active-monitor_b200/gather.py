@@ -63,7 +63,7 @@ class PeerGather:
     all-gather above.  torch.distributed is used once, at set-up, to swap the
     CUDA-IPC handles."""
 
-    def __init__(self, device_index: int, cap_total: int, group=None):
+    def __init__(self, device_index: int, cap_total: int, group=None, idx_bytes: int = 8):
         import ctypes as C
 
         from . import _lib as L
@@ -74,7 +74,9 @@ class PeerGather:
         self.cap_total = cap_total
         self.device = torch.device("cuda", device_index)
         h = C.c_void_p()
-        rc = self._lib.am_gather_create(C.byref(h), device_index, self.rank, self.world, cap_total)
+        self.idx_bytes = idx_bytes
+        rc = self._lib.am_gather_create(C.byref(h), device_index, self.rank, self.world, cap_total,
+                                        idx_bytes)
         if rc != 0:
             raise RuntimeError(f"am_gather_create failed: {rc}")
         self._h = h
@@ -100,7 +102,7 @@ class PeerGather:
         class _Arr:
             pass
         itemsize = torch.empty(0, dtype=dtype).element_size()
-        typestr = {torch.int64: "<i8", torch.uint8: "|u1", torch.int32: "<i4"}[dtype]
+        typestr = {torch.int64: "<i8", torch.uint8: "|u1", torch.int32: "<i4"}[dtype]  # u32 viewed as i32
         a = _Arr()
         a.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False),
                                       "version": 3, "strides": (itemsize,)}
@@ -112,7 +114,8 @@ class PeerGather:
         counts_t = self._wrap(self._lib.am_gather_out_counts(self._h), self.world + 1, torch.int32)
         counts = counts_t.tolist()
         total = counts[self.world]
-        idx = self._wrap(self._lib.am_gather_out_idx(self._h), max(total, 1), torch.int64)[:total]
+        idt = torch.int64 if self.idx_bytes == 8 else torch.int32
+        idx = self._wrap(self._lib.am_gather_out_idx(self._h), max(total, 1), idt)[:total]
         act = self._wrap(self._lib.am_gather_out_act(self._h), max(total, 1), torch.uint8)[:total]
         return idx, act, counts[: self.world]
 

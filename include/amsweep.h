@@ -273,12 +273,15 @@ void* am_sweep_stream(am_sweep_t*);
  * The reference has no counterpart (single process; consumer is hcc.go:502). */
 #define AM_IPC_HANDLE_BYTES 64
 typedef struct am_gather am_gather_t;
-int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_t cap_total);
+/* idx_bytes: 8 = u64 global indices; 4 = u32 (halves the NVLink payload; the
+ * caller guarantees every global index < 2^32). */
+int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_t cap_total,
+                     int idx_bytes);
 int am_gather_export(am_gather_t*, void* handle_out /* AM_IPC_HANDLE_BYTES */);
 int am_gather_connect(am_gather_t*, const void* handles /* world x AM_IPC_HANDLE_BYTES, rank order */);
 int am_gather_push(am_gather_t*, const void* d_idx_local /* u32 */, const void* d_act_local /* u8 */,
                    const void* d_count_local /* u32 */, uint64_t shard_base, void* cuda_stream);
-void* am_gather_out_idx(am_gather_t*);    /* u64[cap_total], valid after the last push retires */
+void* am_gather_out_idx(am_gather_t*);    /* u64|u32[cap_total], valid after the last push retires */
 void* am_gather_out_act(am_gather_t*);    /* u8[cap_total]                                    */
 void* am_gather_out_counts(am_gather_t*); /* u32[world+1]                                     */
 const char* am_gather_last_error(const am_gather_t*);
