@@ -11,9 +11,9 @@
 //   2. every CTA waits until all `world` counts of this epoch have arrived in
 //      its own block, giving offset = sum(count[r], r < rank) and the total;
 //   3. the CTAs stream the local (u32 local index, u8 action) list and write
-//      (u64 global index, u8 action) at `offset` into EVERY peer's output
-//      buffer — NVSwitch gives each peer full bandwidth, the payload is
-//      ~1 MB/GPU/tick, so this is latency-, not bandwidth-bound;
+//      (u32|u64 global index, u8 action) at `offset` into EVERY peer's output
+//      buffer, as destination-aligned 16 B + 4 B vector stores — NVSwitch gives
+//      each peer full bandwidth;
 //   4. the last CTA fences (system scope), raises done[rank] on every peer and
 //      waits for all peers' done flags: when the kernel retires, this rank's
 //      output buffer holds the complete global list.
@@ -28,6 +28,7 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -91,31 +92,58 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const PushParams p) {
     if (r < p.rank) offset += s_count[r];
     total += s_count[r];
   }
-  // 3. write my list into every peer's output buffer at `offset`: 4 entries in
-  //    flight per thread, each stored to all peers (NVSwitch: every peer at full
-  //    bandwidth; warp-level stores coalesce into 128 B / 32 B NVLink writes)
+  // 3. write my list into every peer's output buffer at `offset`.  Work items are
+  //    DESTINATION-aligned quads (4 consecutive output slots): an interior quad is
+  //    one 16 B index store + one 4 B action store per peer (NVLink packets of
+  //    512 B / 128 B per warp) instead of eight scalar stores; the ragged first and
+  //    last quads fall back to scalar stores.  Source reads are local and unaligned
+  //    (scalar, L2-resident: the list was just written by compact_kernel).
+  //    Four quads are in flight per thread so a small grid saturates the link
+  //    while leaving the SMs to the next tick's sweep.
   const int buf = p.epoch & 1;
   const uint64_t room = offset < p.cap_total ? p.cap_total - offset : 0;
   const uint64_t n = my_count < room ? my_count : room;
+  const uint64_t q_lo = offset / 4, q_hi = (offset + n + 3) / 4;  // quads [q_lo, q_hi)
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t e0 = blockIdx.x * (uint64_t)blockDim.x + tid; e0 < n; e0 += 4 * stride) {
-    uint32_t li[4];
-    uint8_t la[4];
+  for (uint64_t q0 = q_lo + blockIdx.x * (uint64_t)blockDim.x + tid; q0 < q_hi; q0 += 4 * stride) {
+    uint32_t gi[4][4], ga[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const uint64_t e = e0 + (uint64_t)u * stride;
-      li[u] = e < n ? __ldcs(p.idx_local + e) : 0u;
-      la[u] = e < n ? __ldcs(p.act_local + e) : (uint8_t)0;
+      const uint64_t q = q0 + (uint64_t)u * stride;
+      ga[u] = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t pos = 4 * q + k;  // output slot
+        const bool ok = q < q_hi && pos >= offset && pos < offset + n;
+        const uint64_t e = pos - offset;
+        gi[u][k] = ok ? (uint32_t)(p.shard_base + __ldcs(p.idx_local + e)) : 0u;
+        ga[u] |= (ok ? (uint32_t)__ldcs(p.act_local + e) : 0u) << (8 * k);
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const uint64_t e = e0 + (uint64_t)u * stride;
-      if (e >= n) continue;
-      const uint64_t g = p.shard_base + li[u];
-      for (int r = 0; r < p.world; ++r) {
-        if (p.idx_bytes == 4) reinterpret_cast<uint32_t*>(p.peer[r] + p.off_idx[buf])[offset + e] = (uint32_t)g;
-        else reinterpret_cast<uint64_t*>(p.peer[r] + p.off_idx[buf])[offset + e] = g;
-        (p.peer[r] + p.off_act[buf])[offset + e] = la[u];
+      const uint64_t q = q0 + (uint64_t)u * stride;
+      if (q >= q_hi) continue;
+      const bool full = 4 * q >= offset && 4 * q + 4 <= offset + n;
+      if (full && p.idx_bytes == 4) {
+        const uint4 v = make_uint4(gi[u][0], gi[u][1], gi[u][2], gi[u][3]);
+        for (int r = 0; r < p.world; ++r) {
+          reinterpret_cast<uint4*>(p.peer[r] + p.off_idx[buf])[q] = v;
+          reinterpret_cast<uint32_t*>(p.peer[r] + p.off_act[buf])[q] = ga[u];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t pos = 4 * q + k;
+          if (pos < offset || pos >= offset + n) continue;
+          // u64 indices: the global index may exceed 32 bits, recompute it in full
+          const uint64_t g64 = p.shard_base + __ldcs(p.idx_local + (pos - offset));
+          for (int r = 0; r < p.world; ++r) {
+            if (p.idx_bytes == 4) reinterpret_cast<uint32_t*>(p.peer[r] + p.off_idx[buf])[pos] = gi[u][k];
+            else reinterpret_cast<uint64_t*>(p.peer[r] + p.off_idx[buf])[pos] = g64;
+            (p.peer[r] + p.off_act[buf])[pos] = (uint8_t)(ga[u] >> (8 * k));
+          }
+        }
       }
     }
   }
@@ -190,7 +218,8 @@ int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_
     AMG_CUDA(g, cudaSetDevice(device));
     int sms = 148;
     AMG_CUDA(g, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    g->n_ctas = 2 * sms;
+    g->n_ctas = sms / 2;  // a small grid: the exchange shares the GPU with the next sweep
+    if (const char* e = getenv("AMSWEEP_PUSH_CTAS")) { int v = atoi(e); if (v > 0 && v <= 4096) g->n_ctas = v; }
     AMG_CUDA(g, cudaMalloc((void**)&g->block, g->block_bytes));
     AMG_CUDA(g, cudaMemset(g->block, 0, g->block_bytes));
     AMG_CUDA(g, cudaMalloc((void**)&g->out_counts, (kMaxWorld + 1) * 4));

@@ -205,7 +205,7 @@ def main():
         # global indices fit u32 here (records_total < 2^32): 5 B per entry on the wire
         peer = gather.PeerGather(local_rank, cap_total=n * world,
                                  idx_bytes=4 if n * world < (1 << 32) else 8)
-        gstream = torch.cuda.Stream(device=dev)
+        gstream = torch.cuda.Stream(device=dev, priority=-1)  # exchange CTAs are placed ahead of pending sweep CTAs
         ev_sweep = [torch.cuda.Event() for _ in range(2)]
         ev_gather = [torch.cuda.Event() for _ in range(2)]
     step_no = [0]
