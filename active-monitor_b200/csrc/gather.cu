@@ -218,7 +218,7 @@ int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_
     AMG_CUDA(g, cudaSetDevice(device));
     int sms = 148;
     AMG_CUDA(g, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    g->n_ctas = sms / 2;  // a small grid: the exchange shares the GPU with the next sweep
+    g->n_ctas = sms;  // one CTA per SM: the exchange shares the GPU with the next sweep
     if (const char* e = getenv("AMSWEEP_PUSH_CTAS")) { int v = atoi(e); if (v > 0 && v <= 4096) g->n_ctas = v; }
     AMG_CUDA(g, cudaMalloc((void**)&g->block, g->block_bytes));
     AMG_CUDA(g, cudaMemset(g->block, 0, g->block_bytes));

@@ -203,8 +203,15 @@ int launch_sweep(am_sweep* h, int64_t T, uint32_t mode, uint32_t* d_idx, uint8_t
   p.group_count = h->group_count[h->parity];
   p.acc = h->acc;
   if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[0], s));
-  if (mode & AM_SWEEP_CLOSED_LOOP) sweep_tick_kernel<true><<<p.n_tiles, kBlock, 0, s>>>(p);
-  else sweep_tick_kernel<false><<<p.n_tiles, kBlock, 0, s>>>(p);
+  // off the minute no 5-field schedule can fire: the mask columns are not read
+  int64_t sec_of_min = T % 60;
+  if (sec_of_min < 0) sec_of_min += 60;
+  const bool masks = sec_of_min == 0 || (mode & AM_SWEEP_FULL_SCAN);
+  const bool closed = (mode & AM_SWEEP_CLOSED_LOOP) != 0;
+  if (closed && masks) sweep_tick_kernel<true, true><<<p.n_tiles, kBlock, 0, s>>>(p);
+  else if (closed) sweep_tick_kernel<true, false><<<p.n_tiles, kBlock, 0, s>>>(p);
+  else if (masks) sweep_tick_kernel<false, true><<<p.n_tiles, kBlock, 0, s>>>(p);
+  else sweep_tick_kernel<false, false><<<p.n_tiles, kBlock, 0, s>>>(p);
   if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[1], s));
   CompactParams c{};
   c.seg_idx = h->seg_idx;
@@ -215,17 +222,15 @@ int launch_sweep(am_sweep* h, int64_t T, uint32_t mode, uint32_t* d_idx, uint8_t
   c.acc = h->acc;
   c.out_idx = d_idx;
   c.out_act = d_act;
-  c.out_stats = out_stats;
-  c.out_count = out_count;
-  c.n_records = h->n_records;
+  c.shard_base = h->shard_base;
   c.n_tiles = p.n_tiles;
   c.n_groups = (p.n_tiles + kGroupTiles - 1) / kGroupTiles;
   c.cap = (uint32_t)(cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : cap);
   compact_kernel<<<c.n_groups, 256, 0, s>>>(c);
+  publish_kernel<<<1, 32, 0, s>>>(h->acc, out_stats, out_count, h->n_records);
   if (h->profiling) { AM_CUDA(h, cudaEventRecord(h->evp[2], s)); h->profiled = true; }
   h->parity ^= 1;
-  h->launches++;
-  h->launches++;
+  h->launches += 3;
   AM_CUDA(h, cudaGetLastError());
   return AM_OK;
 }

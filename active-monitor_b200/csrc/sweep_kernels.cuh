@@ -89,12 +89,10 @@ struct CompactParams {
   const uint32_t* tile_count;
   const uint32_t* group_count;  // this tick's group sums
   uint32_t* group_count_next;   // the other parity: zeroed here for the next tick
-  unsigned long long* acc;      // read, published, re-armed by the last group
+  unsigned long long* acc;      // action-bit counts and index checksums are added here
   uint32_t* out_idx;            // [cap] ascending local indices
   uint8_t* out_act;             // [cap]
-  am_tick_stats_t* out_stats;   // device or mapped-host; may be null
-  uint32_t* out_count;          // may be null
-  uint64_t n_records;
+  uint64_t shard_base;  // for the global-index checksums
   uint32_t n_tiles, n_groups, cap;
 };
 
@@ -212,14 +210,16 @@ __device__ __forceinline__ uint32_t apply_result(RecState& r, int64_t T, uint32_
 #ifndef AM_MIN_BLOCKS
 #define AM_MIN_BLOCKS 3
 #endif
-template <bool CLOSED>
-__global__ void __launch_bounds__(kBlock, AM_MIN_BLOCKS) sweep_tick_kernel(const SweepParams p) {
+// MASKS = the five cron-field columns are read and matched.  Off the minute a
+// 5-field schedule cannot fire (ParseStandard pins Second to 1<<0), so the
+// launcher picks MASKS=false unless AM_SWEEP_FULL_SCAN is set: 40 of the 56
+// bytes per record and all of the mask arithmetic disappear at compile time.
+template <bool CLOSED, bool MASKS>
+__global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS + 1) sweep_tick_kernel(const SweepParams p) {
   // one row per warp, written unconditionally: no zero-initialisation, no shared
   // atomics, and therefore a single __syncthreads in the whole kernel
   __shared__ uint32_t s_warp_tot[kWarps];
-  __shared__ uint32_t s_wstat[kWarps][12];
-  __shared__ uint32_t s_wxor[kWarps][2];
-  __shared__ uint32_t s_wsum[kWarps];
+  __shared__ uint32_t s_wres[kWarps][4];  // posted results applied: ok, fail, remedy ok, remedy fail
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -227,13 +227,6 @@ __global__ void __launch_bounds__(kBlock, AM_MIN_BLOCKS) sweep_tick_kernel(const
   const uint32_t tile = blockIdx.x;
   const uint32_t tile_base = tile * (uint32_t)kTile;
   const int64_t T = p.T;
-
-  // A 5-field schedule has Second == 1<<0 (ParseStandard prepends "0"): off
-  // the minute no mask can match, so the 40 B/record of masks are not read
-  // unless the caller asks for a full scan.
-  int64_t sec_of_min = T % 60;
-  if (sec_of_min < 0) sec_of_min += 60;
-  const bool load_masks = (sec_of_min == 0) || (p.mode & AM_SWEEP_FULL_SCAN);
 
   // ---- phase A: issue every schedule-column load of this lane up front ----
   // half h covers records r0(h) .. r0(h)+1, r0 = tile_base + warp*128 + h*64 + lane*2
@@ -249,7 +242,7 @@ __global__ void __launch_bounds__(kBlock, AM_MIN_BLOCKS) sweep_tick_kernel(const
     ras[h] = ld_stream(reinterpret_cast<const int2*>(p.c.ras + r0[h]));
     fa[h] = ld_stream(reinterpret_cast<const longlong2*>(p.c.finished_at + r0[h]));
   }
-  if (load_masks) {
+  if (MASKS) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       mi[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.minute + r0[h]));
@@ -257,11 +250,6 @@ __global__ void __launch_bounds__(kBlock, AM_MIN_BLOCKS) sweep_tick_kernel(const
       dm[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.dom + r0[h]));
       mo[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.month + r0[h]));
       dw[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.dow + r0[h]));
-    }
-  } else {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      mi[h] = hr[h] = dm[h] = mo[h] = dw[h] = make_ulonglong2(0, 0);
     }
   }
 
@@ -272,90 +260,89 @@ __global__ void __launch_bounds__(kBlock, AM_MIN_BLOCKS) sweep_tick_kernel(const
   const TickWords w = p.words;
 
   uint32_t act[2][2];
-  uint32_t st0 = 0, st1 = 0, st2 = 0, st3 = 0;  // packed per-lane statistics
+  uint32_t res_lane = 0;  // 4 x 8-bit counts of results applied by this lane
 
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const uint32_t flg[2] = {fl[h].x, fl[h].y};
     const int32_t rasv[2] = {ras[h].x, ras[h].y};
     const int64_t fav[2] = {fa[h].x, fa[h].y};
-    const uint64_t miv[2] = {mi[h].x, mi[h].y}, hrv[2] = {hr[h].x, hr[h].y};
-    const uint64_t dmv[2] = {dm[h].x, dm[h].y}, mov[2] = {mo[h].x, mo[h].y};
-    const uint64_t dwv[2] = {dw[h].x, dw[h].y};
 
-    bool live[2], due[2], stopped_now[2], need_b[2];
+    bool due[2], stopped_now[2], need_b[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const uint32_t f = flg[j];
       const uint32_t kind = f & AM_KIND_MASK;
-      live[j] = !(f & AM_F_TOMBSTONE) && (kind - 1u) < 5u;  // kinds 1..5 are evaluated
+      // kinds 1..5 are evaluated; tombstones, NO_RESOURCE (hcc.go:227) and host-fallback are not
+      const bool live = ((0x3Eu >> kind) & 1u) && !(f & AM_F_TOMBSTONE);
       const bool has_result = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL)) != 0;
       const bool pending = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING)) != 0;
       // step 1 sets finishedAt = T before the due decision is taken
       const int64_t fa_eff = has_result ? T : fav[j];
       const int64_t elapsed = (int64_t)((uint64_t)T - (uint64_t)fa_eff);
       const bool due_iv = !(elapsed < (int64_t)rasv[j]);  // not(hcc.go:264) == timer :751 fired
-      const bool fld = (miv[j] & w.minute) && (hrv[j] & w.hour) && (mov[j] & w.month);
-      const bool dmm = (dmv[j] & w.dom) != 0, dwm = (dwv[j] & w.dow) != 0;
-      const bool star = ((dmv[j] | dwv[j]) >> 63) != 0;  // robfig dayMatches
-      const bool due_cron = w.sec0 && fld && (star ? (dmm && dwm) : (dmm || dwm));
-      const bool is_iv = (kind == AM_KIND_INTERVAL) || (kind == AM_KIND_CRON_EVERY);
-      due[j] = live[j] && (is_iv ? due_iv : (kind == AM_KIND_CRON_SPEC && due_cron));
-      stopped_now[j] = live[j] && kind == AM_KIND_STOPPED && !(f & AM_F_STOPPED_REPORTED);
-      need_b[j] = live[j] && (pending || (CLOSED && due[j]));
+      bool due_cron = false;
+      if (MASKS) {
+        const uint64_t miv = j ? mi[h].y : mi[h].x, hrv = j ? hr[h].y : hr[h].x;
+        const uint64_t dmv = j ? dm[h].y : dm[h].x, mov = j ? mo[h].y : mo[h].x;
+        const uint64_t dwv = j ? dw[h].y : dw[h].x;
+        const bool fld = (miv & w.minute) && (hrv & w.hour) && (mov & w.month);
+        const bool dmm = (dmv & w.dom) != 0, dwm = (dwv & w.dow) != 0;
+        const bool star = ((dmv | dwv) >> 63) != 0;  // robfig dayMatches
+        due_cron = w.sec0 && fld && (star ? (dmm && dwm) : (dmm || dwm));
+      }
+      const bool is_iv = ((0x14u >> kind) & 1u) != 0;  // INTERVAL or CRON_EVERY
+      due[j] = live && (is_iv ? due_iv : (kind == AM_KIND_CRON_SPEC && due_cron));
+      stopped_now[j] = live && kind == AM_KIND_STOPPED && !(f & AM_F_STOPPED_REPORTED);
+      need_b[j] = live && (pending || (CLOSED && due[j]));
       act[h][j] = (due[j] ? AM_ACT_SUBMIT_HC : 0u) | (stopped_now[j] ? AM_ACT_STOPPED : 0u) |
-                  ((live[j] && kind == AM_KIND_PARSE_ERROR) ? AM_ACT_PARSE_ERROR : 0u);
+                  ((live && kind == AM_KIND_PARSE_ERROR) ? AM_ACT_PARSE_ERROR : 0u);
     }
 
     uint32_t nfl[2] = {flg[0], flg[1]};
     int64_t nfa[2] = {fav[0], fav[1]};
+    bool dirty = false;  // flags / finishedAt of this lane's pair changed
     const bool lane_b = need_b[0] || need_b[1];
 
     if (__any_sync(kFull, lane_b)) {
       // ---- phase B: remedy/counter columns, only for lanes that need them --
-      int2 lim = make_int2(0, 0), rst = make_int2(0, 0), sc = make_int2(0, 0), fc = make_int2(0, 0);
-      int2 rsc = make_int2(0, 0), rfc = make_int2(0, 0), rtc = make_int2(0, 0);
-      longlong2 rfa = make_longlong2(0, 0);
       if (lane_b) {
         const uint32_t r = r0[h];
-        lim = ld_stream(reinterpret_cast<const int2*>(p.c.runs_limit + r));
-        rst = ld_stream(reinterpret_cast<const int2*>(p.c.reset_interval + r));
-        sc = ld_stream(reinterpret_cast<const int2*>(p.c.success + r));
-        fc = ld_stream(reinterpret_cast<const int2*>(p.c.failed + r));
-        rsc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_success + r));
-        rfc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_failed + r));
-        rtc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_total + r));
-        rfa = ld_stream(reinterpret_cast<const longlong2*>(p.c.remedy_finished_at + r));
-      }
-      int32_t ns[2] = {sc.x, sc.y}, nf[2] = {fc.x, fc.y};
-      int32_t nrs[2] = {rsc.x, rsc.y}, nrf[2] = {rfc.x, rfc.y}, nrt[2] = {rtc.x, rtc.y};
-      int64_t nrfa[2] = {rfa.x, rfa.y};
-      const int32_t limv[2] = {lim.x, lim.y}, rstv[2] = {rst.x, rst.y};
+        const int2 lim = ld_stream(reinterpret_cast<const int2*>(p.c.runs_limit + r));
+        const int2 rst = ld_stream(reinterpret_cast<const int2*>(p.c.reset_interval + r));
+        const int2 sc = ld_stream(reinterpret_cast<const int2*>(p.c.success + r));
+        const int2 fc = ld_stream(reinterpret_cast<const int2*>(p.c.failed + r));
+        const int2 rsc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_success + r));
+        const int2 rfc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_failed + r));
+        const int2 rtc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_total + r));
+        const longlong2 rfa = ld_stream(reinterpret_cast<const longlong2*>(p.c.remedy_finished_at + r));
+        int32_t ns[2] = {sc.x, sc.y}, nf[2] = {fc.x, fc.y};
+        int32_t nrs[2] = {rsc.x, rsc.y}, nrf[2] = {rfc.x, rfc.y}, nrt[2] = {rtc.x, rtc.y};
+        int64_t nrfa[2] = {rfa.x, rfa.y};
+        const int32_t limv[2] = {lim.x, lim.y}, rstv[2] = {rst.x, rst.y};
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        if (need_b[j]) {
-          RecState s{flg[j], fav[j], ns[j], nf[j], nrs[j], nrf[j], nrt[j], nrfa[j], limv[j], rstv[j]};
-          uint32_t res = 0;
-          uint32_t a = apply_result(s, T, res);
-          if (CLOSED && due[j]) {
-            const uint64_t gidx = p.shard_base + (uint64_t)(r0[h] + (uint32_t)j);
-            const uint64_t k = outcome_key(p.seed, gidx, (uint64_t)T);
-            const uint32_t failp = (s.flags >> AM_F_FAILP_SHIFT) & 0xFFu;
-            const bool fail = (uint32_t)(k & 0xFF) < failp;
-            const bool rem_ok = (uint32_t)((k >> 8) & 0xFF) < 179u;
-            s.flags |= (fail ? AM_F_PENDING_FAIL : AM_F_PENDING_OK) | AM_F_REMEDY_PENDING |
-                       (rem_ok ? AM_F_REMEDY_OUTCOME_OK : 0u);
-            a |= apply_result(s, T, res);
+        for (int j = 0; j < 2; ++j) {
+          if (need_b[j]) {
+            RecState s{flg[j], fav[j], ns[j], nf[j], nrs[j], nrf[j], nrt[j], nrfa[j], limv[j], rstv[j]};
+            uint32_t res = 0;
+            uint32_t a = apply_result(s, T, res);
+            if (CLOSED && due[j]) {
+              const uint64_t gidx = p.shard_base + (uint64_t)(r0[h] + (uint32_t)j);
+              const uint64_t k = outcome_key(p.seed, gidx, (uint64_t)T);
+              const uint32_t failp = (s.flags >> AM_F_FAILP_SHIFT) & 0xFFu;
+              const bool fail = (uint32_t)(k & 0xFF) < failp;
+              const bool rem_ok = (uint32_t)((k >> 8) & 0xFF) < 179u;
+              s.flags |= (fail ? AM_F_PENDING_FAIL : AM_F_PENDING_OK) | AM_F_REMEDY_PENDING |
+                         (rem_ok ? AM_F_REMEDY_OUTCOME_OK : 0u);
+              a |= apply_result(s, T, res);
+            }
+            act[h][j] |= a;
+            res_lane += res;  // per lane at most 4 records x 2 results per byte
+            nfl[j] = s.flags; nfa[j] = s.fa;
+            ns[j] = s.s; nf[j] = s.f; nrs[j] = s.rs; nrf[j] = s.rf; nrt[j] = s.rt; nrfa[j] = s.rfa;
+            dirty = true;  // a result always clears its PENDING flags
           }
-          act[h][j] |= a;
-          st2 += (res & 0xFFu) | ((res & 0xFF00u) << 8);          // ok | fail<<16
-          st3 += ((res >> 16) & 0xFFu) | ((res >> 8) & 0xFF0000u);  // remedy ok | fail<<16
-          nfl[j] = s.flags; nfa[j] = s.fa;
-          ns[j] = s.s; nf[j] = s.f; nrs[j] = s.rs; nrf[j] = s.rf; nrt[j] = s.rt; nrfa[j] = s.rfa;
         }
-      }
-      if (lane_b) {
-        const uint32_t r = r0[h];
         if (ns[0] != sc.x || ns[1] != sc.y)
           st_stream(reinterpret_cast<int2*>(p.c.success + r), make_int2(ns[0], ns[1]));
         if (nf[0] != fc.x || nf[1] != fc.y)
@@ -376,14 +363,13 @@ __global__ void __launch_bounds__(kBlock, AM_MIN_BLOCKS) sweep_tick_kernel(const
       if (stopped_now[j]) {  // hcc.go:238-250: Status "Stopped", FinishedAt = now
         nfa[j] = T;
         nfl[j] |= AM_F_STOPPED_REPORTED;
+        dirty = true;
       }
-      st0 += spread4(act[h][j]);
-      st1 += spread4(act[h][j] >> 4);
     }
-    if (nfl[0] != flg[0] || nfl[1] != flg[1])
+    if (dirty) {
       st_stream(reinterpret_cast<uint2*>(p.c.flags + r0[h]), make_uint2(nfl[0], nfl[1]));
-    if (nfa[0] != fav[0] || nfa[1] != fav[1])
       st_stream(reinterpret_cast<longlong2*>(p.c.finished_at + r0[h]), make_longlong2(nfa[0], nfa[1]));
+    }
   }
 
   // ---- ordered compaction: in-warp ranks from ballots ---------------------
@@ -399,39 +385,17 @@ __global__ void __launch_bounds__(kBlock, AM_MIN_BLOCKS) sweep_tick_kernel(const
   rank[1][1] = rank[1][0] + (act[1][0] != 0);
   if (lane == 0) s_warp_tot[warp] = warp_total;
 
-  // ---- statistics: lane -> warp (redux) -> per-warp shared row ---------------
+  // ---- results applied this tick (feeds metrics.MonitorSuccess/Error): lane ->
+  //      warp (two redux over 16-bit halves) -> per-warp shared row.  The action
+  //      statistics and index checksums are derived from the emitted entries
+  //      by compact_kernel, so records that emit nothing cost nothing here.
   {
-    uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-    if (__any_sync(kFull, (st0 | st1 | st2 | st3) != 0)) {
-      q0 = __reduce_add_sync(kFull, st0);  // 4 x 8-bit action counts
-      q1 = __reduce_add_sync(kFull, st1);
-      q2 = __reduce_add_sync(kFull, st2);  // 2 x 16-bit result counts
-      q3 = __reduce_add_sync(kFull, st3);
+    uint32_t lo = 0, hi = 0;
+    if (__any_sync(kFull, res_lane != 0)) {
+      lo = __reduce_add_sync(kFull, (res_lane & 0xFFu) | ((res_lane & 0xFF00u) << 8));           // ok | fail<<16
+      hi = __reduce_add_sync(kFull, ((res_lane >> 16) & 0xFFu) | ((res_lane >> 8) & 0xFF0000u));  // remedy ok | fail<<16
     }
-    if (lane < 12) {
-      uint32_t v;
-      if (lane < 8) v = ((lane < 4 ? q0 : q1) >> ((lane & 3) * 8)) & 0xFFu;
-      else v = ((lane < 10 ? q2 : q3) >> ((lane & 1) * 16)) & 0xFFFFu;
-      s_wstat[warp][lane] = v;
-    }
-    uint32_t xl = 0, xh = 0, rel = 0;
-    if (warp_total) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-          if (act[h][j]) {
-            const uint32_t local = r0[h] + (uint32_t)j;
-            const uint64_t g = p.shard_base + local;
-            xl ^= (uint32_t)g;
-            xh ^= (uint32_t)(g >> 32);
-            rel += local - tile_base;
-          }
-      xl = __reduce_xor_sync(kFull, xl);
-      xh = __reduce_xor_sync(kFull, xh);
-      rel = __reduce_add_sync(kFull, rel);
-    }
-    if (lane == 0) { s_wxor[warp][0] = xl; s_wxor[warp][1] = xh; s_wsum[warp] = rel; }
+    if (lane < 4) s_wres[warp][lane] = ((lane < 2 ? lo : hi) >> ((lane & 1) * 16)) & 0xFFFFu;
   }
   __syncthreads();
 
@@ -453,23 +417,16 @@ __global__ void __launch_bounds__(kBlock, AM_MIN_BLOCKS) sweep_tick_kernel(const
         st_keep_u32(p.seg_idx + pos, r0[h] + (uint32_t)j, keep);
         st_keep_u8(p.seg_act + pos, act[h][j], keep);
       }
-  if (warp == 0) {  // CTA statistics -> global accumulators (RED, no return value)
-    if (lane < 12) {
+  if (warp == 0) {  // per-tile count, group counter, result counters (RED, no return value)
+    if (lane < 4) {
       uint32_t sv = 0;
 #pragma unroll
-      for (int k = 0; k < kWarps; ++k) sv += s_wstat[k][lane];
-      if (sv) atomicAdd(&p.acc[2 + lane], (unsigned long long)sv);
+      for (int k = 0; k < kWarps; ++k) sv += s_wres[k][lane];
+      if (sv) atomicAdd(&p.acc[10 + lane], (unsigned long long)sv);
     }
-    if (lane == 12) {
+    if (lane == 4) {
       p.tile_count[tile] = tile_total;
-      if (tile_total) {
-        uint32_t xl = 0, xh = 0, rel = 0;
-#pragma unroll
-        for (int k = 0; k < kWarps; ++k) { xl ^= s_wxor[k][0]; xh ^= s_wxor[k][1]; rel += s_wsum[k]; }
-        atomicAdd(&p.group_count[tile / kGroupTiles], tile_total);
-        atomicXor(&p.acc[14], ((unsigned long long)xh << 32) | xl);
-        atomicAdd(&p.acc[15], (p.shard_base + tile_base) * (unsigned long long)tile_total + rel);
-      }
+      if (tile_total) atomicAdd(&p.group_count[tile / kGroupTiles], tile_total);
     }
   }
 }
@@ -478,13 +435,16 @@ __global__ void __launch_bounds__(kBlock, AM_MIN_BLOCKS) sweep_tick_kernel(const
 // Segments -> contiguous ascending list.  One CTA per group of kGroupTiles
 // tiles: its global base is the sum of the earlier groups' counts (a few KB of
 // L2-resident reads), the in-group offsets a kGroupTiles-wide scan; entries just written
-// by the sweep are still in L2.  The last group publishes the tick's
-// statistics and re-arms the accumulators; every group zeroes its slot of the
-// other-parity group counters for the next tick.
+// by the sweep are still in L2.  While moving its entries every thread also counts their
+// action bits and checksums their indices (statistics cost is proportional to what
+// was emitted, not to N); every group zeroes its slot of the other-parity group
+// counters for the next tick.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) compact_kernel(const CompactParams p) {
   __shared__ uint32_t s_part[8];
   __shared__ uint32_t s_off[kGroupTiles + 1];
+  __shared__ uint32_t s_cnt[8][8];               // per-warp counts of the 8 action bits
+  __shared__ unsigned long long s_chk[8][2];     // per-warp xor / sum of emitted global indices
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t g = blockIdx.x;
 
@@ -510,6 +470,10 @@ __global__ void __launch_bounds__(256) compact_kernel(const CompactParams p) {
   for (int k = 0; k < 8; ++k) base += s_part[k];
   const uint32_t group_total = s_off[kGroupTiles];
 
+  // per-thread statistics of the entries it moves: 8 action-bit counts (two words of
+  // four bytes; a thread moves < 64 entries) and the checksums of the global indices
+  uint32_t c0 = 0, c1 = 0;
+  unsigned long long cx = 0, cs = 0;
   // four independent (index, action) loads in flight per thread
   for (uint32_t e0 = tid; e0 < group_total; e0 += 4u * blockDim.x) {
     uint32_t src[4], vi[4], va[4];
@@ -531,27 +495,65 @@ __global__ void __launch_bounds__(256) compact_kernel(const CompactParams p) {
     for (int u = 0; u < 4; ++u) {
       const uint32_t e = e0 + (uint32_t)u * blockDim.x;
       const uint32_t pos = base + e;
-      if (e < group_total && pos < p.cap) {
-        p.out_idx[pos] = vi[u];
-        p.out_act[pos] = (uint8_t)va[u];
+      if (e < group_total) {
+        c0 += spread4(va[u]);
+        c1 += spread4(va[u] >> 4);
+        const unsigned long long gi = p.shard_base + vi[u];
+        cx ^= gi;
+        cs += gi;
+        if (pos < p.cap) {
+          p.out_idx[pos] = vi[u];
+          p.out_act[pos] = (uint8_t)va[u];
+        }
       }
+    }
+  }
+  // statistics: thread -> warp (redux; 16-bit fields so 32 lanes x 63 fit) -> CTA -> global RED
+  if (group_total) {
+    const uint32_t a0 = __reduce_add_sync(kFull, (c0 & 0xFFu) | ((c0 & 0xFF00u) << 8));
+    const uint32_t a1 = __reduce_add_sync(kFull, ((c0 >> 16) & 0xFFu) | ((c0 >> 8) & 0xFF0000u));
+    const uint32_t a2 = __reduce_add_sync(kFull, (c1 & 0xFFu) | ((c1 & 0xFF00u) << 8));
+    const uint32_t a3 = __reduce_add_sync(kFull, ((c1 >> 16) & 0xFFu) | ((c1 >> 8) & 0xFF0000u));
+    const uint32_t xl = __reduce_xor_sync(kFull, (uint32_t)cx), xh = __reduce_xor_sync(kFull, (uint32_t)(cx >> 32));
+    unsigned long long sum = cs;
+#pragma unroll
+    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(kFull, sum, d);
+    if (lane < 8) {
+      const uint32_t q = lane < 2 ? a0 : (lane < 4 ? a1 : (lane < 6 ? a2 : a3));
+      s_cnt[warp][lane] = (q >> ((lane & 1) * 16)) & 0xFFFFu;
+    }
+    if (lane == 0) { s_chk[warp][0] = ((unsigned long long)xh << 32) | xl; s_chk[warp][1] = sum; }
+    __syncthreads();
+    if (tid < 8) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v += s_cnt[k][tid];
+      if (v) atomicAdd(&p.acc[2 + tid], (unsigned long long)v);
+    }
+    if (tid == 8) {
+      unsigned long long x = 0, t = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { x ^= s_chk[k][0]; t += s_chk[k][1]; }
+      atomicXor(&p.acc[14], x);
+      atomicAdd(&p.acc[15], t);
     }
   }
   if (tid == 0) p.group_count_next[g] = 0;
 
-  if (g == p.n_groups - 1 && tid == 0) {
-    unsigned long long v[kNumAcc];
-#pragma unroll
-    for (int k = 0; k < kNumAcc; ++k) { v[k] = p.acc[k]; p.acc[k] = 0; }
-    v[0] = p.n_records;
-    v[1] = (unsigned long long)base + group_total;  // n_emitted
-    if (p.out_stats) {
-      unsigned long long* o = reinterpret_cast<unsigned long long*>(p.out_stats);
-#pragma unroll
-      for (int k = 0; k < kNumAcc; ++k) o[k] = v[k];
-    }
-    if (p.out_count) *p.out_count = (uint32_t)v[1];
-  }
+  if (g == p.n_groups - 1 && tid == 0) p.acc[1] = (unsigned long long)base + group_total;  // n_emitted
+}
+
+// One warp, after the kernel boundary that completes every group's REDs: publish the
+// tick's am_tick_stats_t (device or mapped-host memory) and re-arm the accumulators.
+__global__ void publish_kernel(unsigned long long* acc, am_tick_stats_t* out_stats, uint32_t* out_count,
+                               uint64_t n_records) {
+  const int k = threadIdx.x;
+  if (k >= kNumAcc) return;
+  unsigned long long v = acc[k];
+  acc[k] = 0;
+  if (k == 0) v = n_records;
+  if (out_stats) reinterpret_cast<unsigned long long*>(out_stats)[k] = v;
+  if (k == 1 && out_count) *out_count = (uint32_t)v;
 }
 
 // ---- small maintenance kernels (create / read) -----------------------------
