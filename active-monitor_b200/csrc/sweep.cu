@@ -79,9 +79,10 @@ struct am_sweep {
   bool profiling = false, profiled = false;
   std::mutex mu;  // guards the staged vectors
   std::atomic_flag ticking = ATOMIC_FLAG_INIT;
-  // staged controller events in arrival order (tick-local sequence numbers)
-  std::vector<StagedOp> ops;
-  std::vector<am_record_t> op_recs;
+  // staged controller events in arrival order, written straight into pinned host
+  // memory (the H2D copy at the next tick reads them in place)
+  PinnedBuf st_ops, st_recs;
+  size_t n_ops = 0, n_recs = 0;
   uint32_t n_state_ops = 0, n_result_ops = 0;
   uint32_t* marks = nullptr;  // [2 * cap_padded] per-slot {latest state op, latest result} of this tick
   PinnedBuf pin_in, pin_out;
@@ -135,32 +136,40 @@ struct TickGuard {
   ~TickGuard() { if (ok) h->ticking.clear(std::memory_order_release); }
 };
 
+// Grow a pinned staging array (called under h->mu); keeps the contents.
+cudaError_t grow_pinned(PinnedBuf& b, size_t used_bytes, size_t want_bytes) {
+  if (want_bytes <= b.cap) return cudaSuccess;
+  void* np = nullptr;
+  size_t ncap = want_bytes * 2 + 65536;
+  cudaError_t e = cudaHostAlloc(&np, ncap, cudaHostAllocDefault);
+  if (e != cudaSuccess) return e;
+  if (used_bytes) memcpy(np, b.p, used_bytes);
+  if (b.p) cudaFreeHost(b.p);
+  b.p = np;
+  b.cap = ncap;
+  return cudaSuccess;
+}
+
 // Apply staged upserts / removes / results (called with the tick guard held).
 int drain_staged(am_sweep* h) {
-  std::vector<StagedOp> ops;
-  std::vector<am_record_t> recs;
-  uint32_t n_state = 0, n_result = 0;
-  {
-    std::lock_guard<std::mutex> lk(h->mu);
-    ops.swap(h->ops);
-    recs.swap(h->op_recs);
-    n_state = h->n_state_ops; n_result = h->n_result_ops;
-    h->n_state_ops = h->n_result_ops = 0;
-  }
-  const size_t n = ops.size();
+  // Hold the staging lock for the H2D enqueue only: the copies read the pinned arrays in
+  // place, and callers may not append until the copy has been consumed.
+  std::unique_lock<std::mutex> lk(h->mu);
+  const size_t n = h->n_ops, nrec = h->n_recs;
   if (n == 0) return AM_OK;
-  for (const StagedOp& op : ops)  // every upserted slot extends the swept range (high-water mark)
-    if (op.kind == kOpUpsert && (uint64_t)op.idx + 1 > h->n_records) h->n_records = (uint64_t)op.idx + 1;
-  const size_t o_ops = 0, o_rec = (n * sizeof(StagedOp) + 255) / 256 * 256,
-               total = o_rec + recs.size() * sizeof(am_record_t);
-  AM_CUDA(h, h->pin_in.reserve(total));
+  const uint32_t n_state = h->n_state_ops, n_result = h->n_result_ops;
+  const StagedOp* ops = (const StagedOp*)h->st_ops.p;
+  if (n_state)
+    for (size_t k = 0; k < n; ++k)  // every upserted slot extends the swept range (high-water mark)
+      if ((ops[k].arg & kOpKindMask) == kOpUpsert && (uint64_t)ops[k].idx + 1 > h->n_records)
+        h->n_records = (uint64_t)ops[k].idx + 1;
+  const size_t o_rec = (n * sizeof(StagedOp) + 255) / 256 * 256, total = o_rec + nrec * sizeof(am_record_t);
   AM_CUDA(h, h->dev_in.reserve(total));
-  char* hp = (char*)h->pin_in.p;
-  memcpy(hp + o_ops, ops.data(), n * sizeof(StagedOp));
-  if (!recs.empty()) memcpy(hp + o_rec, recs.data(), recs.size() * sizeof(am_record_t));
-  AM_CUDA(h, cudaMemcpyAsync(h->dev_in.p, hp, total, cudaMemcpyHostToDevice, h->stream));
-  const StagedOp* d_ops = (const StagedOp*)((char*)h->dev_in.p + o_ops);
-  const am_record_t* d_recs = (const am_record_t*)((char*)h->dev_in.p + o_rec);
+  char* dp = (char*)h->dev_in.p;
+  AM_CUDA(h, cudaMemcpyAsync(dp, h->st_ops.p, n * sizeof(StagedOp), cudaMemcpyHostToDevice, h->stream));
+  if (nrec) AM_CUDA(h, cudaMemcpyAsync(dp + o_rec, h->st_recs.p, nrec * sizeof(am_record_t), cudaMemcpyHostToDevice, h->stream));
+  const StagedOp* d_ops = (const StagedOp*)dp;
+  const am_record_t* d_recs = (const am_record_t*)(dp + o_rec);
   const unsigned B = 256, G = (unsigned)((n + B - 1) / B);
   mark_ops_kernel<<<G, B, 0, h->stream>>>(h->marks, d_ops, (uint32_t)n);
   h->launches++;
@@ -175,8 +184,10 @@ int drain_staged(am_sweep* h) {
   clear_marks_kernel<<<G, B, 0, h->stream>>>(h->marks, d_ops, (uint32_t)n);
   h->launches++;
   AM_CUDA(h, cudaGetLastError());
-  // the staging block is reused by the next drain: wait until the copy was consumed
+  // the pinned arrays are refilled by the next calls: wait until the copies were consumed
   AM_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->n_ops = h->n_recs = 0;
+  h->n_state_ops = h->n_result_ops = 0;
   return AM_OK;
 }
 
@@ -326,6 +337,7 @@ void am_sweep_destroy(am_sweep_t* h) {
   }
   if (h->h_stats) cudaFreeHost(h->h_stats);
   h->pin_in.release(); h->pin_out.release(); h->dev_in.release();
+  h->st_ops.release(); h->st_recs.release();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int k = 0; k < 3; ++k) if (h->evp[k]) cudaEventDestroy(h->evp[k]);
@@ -387,17 +399,19 @@ int am_sweep_upsert(am_sweep_t* h, uint64_t n, const uint64_t* idx, const am_rec
   for (uint64_t k = 0; k < n; ++k)
     if (idx[k] >= h->capacity) return AM_E_RANGE;
   std::lock_guard<std::mutex> lk(h->mu);
-  if (h->ops.size() + n > 0xFFFFFFF0ull) return AM_E_NOSPACE;
-  const size_t o = h->ops.size(), r = h->op_recs.size();
-  h->ops.resize(o + n);
-  h->op_recs.resize(r + n);
+  if (h->n_ops + n > 0x3FFFFFF0ull || h->n_recs + n > 0x3FFFFFF0ull) return AM_E_NOSPACE;
+  AM_CUDA(h, cudaSetDevice(h->device));
+  AM_CUDA(h, grow_pinned(h->st_ops, h->n_ops * sizeof(StagedOp), (h->n_ops + n) * sizeof(StagedOp)));
+  AM_CUDA(h, grow_pinned(h->st_recs, h->n_recs * sizeof(am_record_t), (h->n_recs + n) * sizeof(am_record_t)));
+  StagedOp* ops = (StagedOp*)h->st_ops.p + h->n_ops;
+  am_record_t* dst = (am_record_t*)h->st_recs.p + h->n_recs;
   for (uint64_t k = 0; k < n; ++k) {
-    h->ops[o + k] = StagedOp{(uint32_t)idx[k], (uint32_t)(o + k + 1), kOpUpsert, (uint32_t)(r + k)};
-    am_record_t rec = recs[k];
-    rec.flags &= ~AM_F_TOMBSTONE;
-    rec.reserved = 0;
-    h->op_recs[r + k] = rec;
+    ops[k] = StagedOp{(uint32_t)idx[k], kOpUpsert | (uint32_t)(h->n_recs + k)};
+    dst[k] = recs[k];
+    dst[k].flags &= ~AM_F_TOMBSTONE;
+    dst[k].reserved = 0;
   }
+  h->n_ops += n; h->n_recs += n;
   h->n_state_ops += (uint32_t)n;
   return AM_OK;
 }
@@ -407,10 +421,12 @@ int am_sweep_remove(am_sweep_t* h, uint64_t n, const uint64_t* idx) {
   for (uint64_t k = 0; k < n; ++k)
     if (idx[k] >= h->capacity) return AM_E_RANGE;
   std::lock_guard<std::mutex> lk(h->mu);
-  if (h->ops.size() + n > 0xFFFFFFF0ull) return AM_E_NOSPACE;
-  const size_t o = h->ops.size();
-  h->ops.resize(o + n);
-  for (uint64_t k = 0; k < n; ++k) h->ops[o + k] = StagedOp{(uint32_t)idx[k], (uint32_t)(o + k + 1), kOpRemove, 0};
+  if (h->n_ops + n > 0x3FFFFFF0ull) return AM_E_NOSPACE;
+  AM_CUDA(h, cudaSetDevice(h->device));
+  AM_CUDA(h, grow_pinned(h->st_ops, h->n_ops * sizeof(StagedOp), (h->n_ops + n) * sizeof(StagedOp)));
+  StagedOp* ops = (StagedOp*)h->st_ops.p + h->n_ops;
+  for (uint64_t k = 0; k < n; ++k) ops[k] = StagedOp{(uint32_t)idx[k], kOpRemove};
+  h->n_ops += n;
   h->n_state_ops += (uint32_t)n;
   return AM_OK;
 }
@@ -418,22 +434,29 @@ int am_sweep_remove(am_sweep_t* h, uint64_t n, const uint64_t* idx) {
 int am_sweep_post_result(am_sweep_t* h, uint64_t n, const uint64_t* idx, const uint8_t* phase,
                          const uint8_t* remedy_phase) {
   if (!h || (n && (!idx || !phase))) return AM_E_INVAL;
-  for (uint64_t k = 0; k < n; ++k) {
-    if (idx[k] >= h->capacity) return AM_E_RANGE;
-    if (phase[k] > AM_PHASE_FAILED || (remedy_phase && remedy_phase[k] > AM_PHASE_FAILED)) return AM_E_INVAL;
+  const uint64_t cap = h->capacity;
+  uint64_t bad = 0;
+  for (uint64_t k = 0; k < n; ++k) {  // branch-free validation pass
+    bad |= (uint64_t)(idx[k] >= cap) | (uint64_t)(phase[k] > AM_PHASE_FAILED) << 1;
+    if (remedy_phase) bad |= (uint64_t)(remedy_phase[k] > AM_PHASE_FAILED) << 1;
   }
+  if (bad & 1) return AM_E_RANGE;
+  if (bad & 2) return AM_E_INVAL;
   std::lock_guard<std::mutex> lk(h->mu);
-  if (h->ops.size() + n > 0xFFFFFFF0ull) return AM_E_NOSPACE;
-  const size_t o = h->ops.size();
-  h->ops.resize(o + n);
-  for (uint64_t k = 0; k < n; ++k) {
-    uint32_t bits = 0;
-    if (phase[k] == AM_PHASE_SUCCEEDED) bits |= AM_F_PENDING_OK;
-    else if (phase[k] == AM_PHASE_FAILED) bits |= AM_F_PENDING_FAIL;
-    const uint8_t rp = remedy_phase ? remedy_phase[k] : AM_PHASE_NONE;
-    if (rp != AM_PHASE_NONE) bits |= AM_F_REMEDY_PENDING | (rp == AM_PHASE_SUCCEEDED ? AM_F_REMEDY_OUTCOME_OK : 0u);
-    h->ops[o + k] = StagedOp{(uint32_t)idx[k], (uint32_t)(o + k + 1), kOpResult, bits};
+  if (h->n_ops + n > 0x3FFFFFF0ull) return AM_E_NOSPACE;
+  AM_CUDA(h, cudaSetDevice(h->device));
+  AM_CUDA(h, grow_pinned(h->st_ops, h->n_ops * sizeof(StagedOp), (h->n_ops + n) * sizeof(StagedOp)));
+  StagedOp* ops = (StagedOp*)h->st_ops.p + h->n_ops;
+  // phase -> flag bits: {none, Succeeded, Failed} -> {0, PENDING_OK, PENDING_FAIL}
+  static const uint32_t kPhaseBits[3] = {0u, AM_F_PENDING_OK, AM_F_PENDING_FAIL};
+  static const uint32_t kRemedyBits[3] = {0u, AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK, AM_F_REMEDY_PENDING};
+  if (remedy_phase) {
+    for (uint64_t k = 0; k < n; ++k)
+      ops[k] = StagedOp{(uint32_t)idx[k], kOpResult | kPhaseBits[phase[k]] | kRemedyBits[remedy_phase[k]]};
+  } else {
+    for (uint64_t k = 0; k < n; ++k) ops[k] = StagedOp{(uint32_t)idx[k], kOpResult | kPhaseBits[phase[k]]};
   }
+  h->n_ops += n;
   h->n_result_ops += (uint32_t)n;
   return AM_OK;
 }

@@ -565,25 +565,23 @@ __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, uint64_t n) {
 
 // ---- staged controller events (upsert / remove / post_result) ---------------
 // Events reach the library from many goroutines between two ticks; per slot
-// they must take effect in call order.  Each event carries a tick-local
-// sequence number (1-based).  mark: atomicMax of the sequence into the slot's
+// they must take effect in call order.  An event's tick-local sequence number
+// is its position in the staged array (1-based).  mark: atomicMax of the sequence into the slot's
 // mark pair {latest upsert/remove, latest result}; apply: only the marked
 // winners write — the latest upsert/remove, then the latest result if it was
 // posted after it (an older result belongs to the replaced CR); clear: marks
 // back to zero.  No host-side hashing or sorting.
 struct StagedOp {
-  uint32_t idx;   // local slot
-  uint32_t seq;   // 1-based arrival number within the tick
-  uint32_t kind;  // 0 upsert (arg = index into the record array), 1 remove, 2 result (arg = flag bits)
-  uint32_t arg;
-};
-constexpr uint32_t kOpUpsert = 0, kOpRemove = 1, kOpResult = 2;
+  uint32_t idx;  // local slot
+  uint32_t arg;  // kind in the top 2 bits; low 30 bits: record index (upsert) or flag bits (result)
+};               // the sequence number of an op is its position in the array + 1
+constexpr uint32_t kOpUpsert = 0u << 30, kOpRemove = 1u << 30, kOpResult = 2u << 30, kOpKindMask = 3u << 30;
 
 __global__ void mark_ops_kernel(uint32_t* marks, const StagedOp* __restrict__ ops, uint32_t n) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const StagedOp op = ops[k];
-  atomicMax(&marks[2u * op.idx + (op.kind == kOpResult ? 1u : 0u)], op.seq);
+  atomicMax(&marks[2u * op.idx + ((op.arg & kOpKindMask) == kOpResult ? 1u : 0u)], k + 1u);
 }
 
 // upserts (hcc.go:170-188 Reconcile) and removes (hcc.go:175-186)
@@ -593,10 +591,11 @@ __global__ void apply_state_ops_kernel(DevCols c, const uint32_t* __restrict__ m
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const StagedOp op = ops[k];
-  if (op.kind == kOpResult || marks[2u * op.idx] != op.seq) return;
+  const uint32_t kind = op.arg & kOpKindMask;
+  if (kind == kOpResult || marks[2u * op.idx] != k + 1u) return;
   const uint32_t i = op.idx;
-  if (op.kind == kOpRemove) { c.flags[i] = AM_F_TOMBSTONE; return; }
-  const am_record_t r = recs[op.arg];
+  if (kind == kOpRemove) { c.flags[i] = AM_F_TOMBSTONE; return; }
+  const am_record_t r = recs[op.arg & ~kOpKindMask];
   c.minute[i] = r.minute; c.hour[i] = r.hour; c.dom[i] = r.dom; c.month[i] = r.month; c.dow[i] = r.dow;
   c.ras[i] = r.ras; c.flags[i] = r.flags; c.finished_at[i] = r.finished_at;
   c.runs_limit[i] = r.runs_limit; c.reset_interval[i] = r.reset_interval;
@@ -611,9 +610,9 @@ __global__ void apply_result_ops_kernel(uint32_t* flags, const uint32_t* __restr
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const StagedOp op = ops[k];
-  if (op.kind != kOpResult) return;
+  if ((op.arg & kOpKindMask) != kOpResult) return;
   const uint32_t s = marks[2u * op.idx], r = marks[2u * op.idx + 1u];
-  if (r != op.seq || op.seq < s) return;
+  if (r != k + 1u || k + 1u < s) return;
   const uint32_t m = AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK;
   flags[op.idx] = (flags[op.idx] & ~m) | (op.arg & m);
 }

@@ -312,6 +312,7 @@ def main():
     if True:
         idx_h = np.empty(n, dtype=np.uint64)
         act_h = np.empty(n, dtype=np.uint32)
+        ok_phase = np.full(n, am.PHASE_SUCCEEDED, dtype=np.uint8)
         prev = None
         h2d = d2h = 0
         reps = max(10, min(args.steps, 120))
@@ -323,12 +324,13 @@ def main():
                 h2d = d2h = 0
             for k in range(5 if phase_name == "warm" else reps):
                 if prev is not None and len(prev):
-                    ph = np.full(len(prev), am.PHASE_SUCCEEDED, dtype=np.uint8)
-                    sweep.post_result(prev - base, ph)
+                    sweep.post_result(prev, ok_phase[: len(prev)])
                     h2d += len(prev) * 8
                 gi, ga, st = sweep.tick(T0 + tick_no, mode=am.SWEEP_FULL_SCAN, buffers=(idx_h, act_h))
                 tick_no += 1
-                prev = gi[(ga & am.ACT_SUBMIT_HC) != 0].copy()
+                prev = gi[(ga & am.ACT_SUBMIT_HC) != 0]  # the checks just submitted ...
+                if base:
+                    prev -= base                                 # ... as local slots of this shard
                 d2h += len(gi) * 5 + 128
             if phase_name == "timed":
                 barrier()
