@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const PushParams p) {
   const uint64_t q_lo = offset / 4, q_hi = (offset + n + 3) / 4;  // quads [q_lo, q_hi)
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t q0 = q_lo + blockIdx.x * (uint64_t)blockDim.x + tid; q0 < q_hi; q0 += 4 * stride) {
-    uint32_t gi[4][4], ga[4];
+    uint32_t li[4][4], ga[4];  // local indices and packed action bytes of four quads
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const uint64_t q = q0 + (uint64_t)u * stride;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const PushParams p) {
         const uint64_t pos = 4 * q + k;  // output slot
         const bool ok = q < q_hi && pos >= offset && pos < offset + n;
         const uint64_t e = pos - offset;
-        gi[u][k] = ok ? (uint32_t)(p.shard_base + __ldcs(p.idx_local + e)) : 0u;
+        li[u][k] = ok ? __ldcs(p.idx_local + e) : 0u;
         ga[u] |= (ok ? (uint32_t)__ldcs(p.act_local + e) : 0u) << (8 * k);
       }
     }
@@ -126,21 +126,30 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const PushParams p) {
       if (q >= q_hi) continue;
       const bool full = 4 * q >= offset && 4 * q + 4 <= offset + n;
       if (full && p.idx_bytes == 4) {
-        const uint4 v = make_uint4(gi[u][0], gi[u][1], gi[u][2], gi[u][3]);
+        const uint32_t b32 = (uint32_t)p.shard_base;
+        const uint4 v = make_uint4(b32 + li[u][0], b32 + li[u][1], b32 + li[u][2], b32 + li[u][3]);
         for (int r = 0; r < p.world; ++r) {
           reinterpret_cast<uint4*>(p.peer[r] + p.off_idx[buf])[q] = v;
           reinterpret_cast<uint32_t*>(p.peer[r] + p.off_act[buf])[q] = ga[u];
         }
-      } else {
+      } else if (full) {
+        const ulonglong2 v0 = make_ulonglong2(p.shard_base + li[u][0], p.shard_base + li[u][1]);
+        const ulonglong2 v1 = make_ulonglong2(p.shard_base + li[u][2], p.shard_base + li[u][3]);
+        for (int r = 0; r < p.world; ++r) {
+          ulonglong2* d = reinterpret_cast<ulonglong2*>(p.peer[r] + p.off_idx[buf]) + 2 * q;
+          d[0] = v0;
+          d[1] = v1;
+          reinterpret_cast<uint32_t*>(p.peer[r] + p.off_act[buf])[q] = ga[u];
+        }
+      } else {  // ragged first / last quad of my segment: scalar stores
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const uint64_t pos = 4 * q + k;
           if (pos < offset || pos >= offset + n) continue;
-          // u64 indices: the global index may exceed 32 bits, recompute it in full
-          const uint64_t g64 = p.shard_base + __ldcs(p.idx_local + (pos - offset));
+          const uint64_t g = p.shard_base + li[u][k];
           for (int r = 0; r < p.world; ++r) {
-            if (p.idx_bytes == 4) reinterpret_cast<uint32_t*>(p.peer[r] + p.off_idx[buf])[pos] = gi[u][k];
-            else reinterpret_cast<uint64_t*>(p.peer[r] + p.off_idx[buf])[pos] = g64;
+            if (p.idx_bytes == 4) reinterpret_cast<uint32_t*>(p.peer[r] + p.off_idx[buf])[pos] = (uint32_t)g;
+            else reinterpret_cast<uint64_t*>(p.peer[r] + p.off_idx[buf])[pos] = g;
             (p.peer[r] + p.off_act[buf])[pos] = (uint8_t)(ga[u] >> (8 * k));
           }
         }

@@ -42,7 +42,8 @@ def _worker(rank, world, port, n_total, ticks, q):
         out = []
         with am.Sweep(capacity=cnt, device=rank, shard_base=first) as s:
             s.load_range(0, cols)
-            pg = gather.PeerGather(rank, cap_total=n_total)
+            # alternate the wire format: u32 global indices on even worlds' first rank pair, u64 otherwise
+            pg = gather.PeerGather(rank, cap_total=n_total, idx_bytes=4 if world % 4 == 0 else 8)
             d_idx = torch.empty(cnt, dtype=torch.int32, device=dev)
             d_act = torch.empty(cnt, dtype=torch.uint8, device=dev)
             d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -65,9 +66,10 @@ def _worker(rank, world, port, n_total, ticks, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_sweep_and_both_gathers_equal_unsharded_oracle(world):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     import amgen
     import oracle_c
@@ -88,6 +90,7 @@ def test_sharded_sweep_and_both_gathers_equal_unsharded_oracle(world):
         for rank in range(world):
             pi, pa, pc, ni, na, nc = results[rank][k]
             assert sum(pc) == len(wi) and pc == nc
+            pi = pi.astype(np.int64) & (0xFFFFFFFF if pi.dtype == np.int32 else -1)  # u32 viewed as i32
             np.testing.assert_array_equal(pi.astype(np.uint64), wi, err_msg=f"peer gather rank {rank} tick {k}")
             np.testing.assert_array_equal(pa.astype(np.uint32), wa)
             np.testing.assert_array_equal(ni.astype(np.uint64), wi, err_msg=f"nccl gather rank {rank} tick {k}")
