@@ -7,6 +7,10 @@
 #pragma once
 #include <stdint.h>
 
+#ifndef INT64_MIN
+#define INT64_MIN (-9223372036854775807ll - 1)
+#endif
+
 #if defined(__CUDACC__)
 #define AM_HD __host__ __device__ __forceinline__
 #else
@@ -88,6 +92,67 @@ AM_HD TickWords tick_words_from_unix(int64_t t) {
   w.sec0 = (c.sec == 0) ? 1u : 0u;
   w.pad = 0;
   return w;
+}
+
+#if defined(__CUDA_ARCH__)
+#define AM_CTZ64(x) (__ffsll((long long)(x)) - 1)
+#else
+#define AM_CTZ64(x) __builtin_ctzll(x)
+#endif
+
+constexpr int64_t kNoNextFire = INT64_MIN;  // robfig's zero time: nothing within five years
+
+// SpecSchedule.Next(t) of robfig/cron v3.0.1 (call site hcc.go:262) for a whole
+// UTC second t: the first activation strictly after t, or kNoNextFire when the
+// year would pass year(t+1s)+5.  Not the Go field-increment loop: a forward scan
+// over days with bit tricks (jump over months whose bit is clear; first set
+// hour/minute bit by count-trailing-zeros), shared by the host helper
+// am_cron_next and the device kernel next_fire_kernel.
+AM_HD int64_t cron_next_utc(uint64_t minute, uint64_t hour, uint64_t dom, uint64_t month,
+                            uint64_t dow, int64_t t) {
+  const uint64_t mins = minute & ((1ull << 60) - 1);
+  const uint64_t hrs = hour & ((1ull << 24) - 1);
+  if (!mins || !hrs) return kNoNextFire;
+  const bool star = ((dom | dow) >> 63) != 0;
+  const int64_t start = t + 1;
+  int64_t day0;
+  int32_t sod;
+  split_days(start, day0, sod);
+  int64_t y;
+  int32_t m, d;
+  civil_from_days(day0, y, m, d);
+  const int64_t year_limit = y + 5;
+  const int32_t mod0 = (sod + 59) / 60;  // first candidate minute-of-day on the starting day
+  for (int64_t day = day0;; ++day) {
+    civil_from_days(day, y, m, d);
+    if (y > year_limit) return kNoNextFire;
+    if (!((month >> m) & 1)) {  // jump to the 1st of the next month
+      int64_t ny = y;
+      int32_t nm = m + 1;
+      if (nm == 13) { nm = 1; ++ny; }
+      day = days_from_civil(ny, nm, 1) - 1;
+      continue;
+    }
+    const bool a = (dom >> d) & 1, b = (dow >> weekday_from_days(day)) & 1;
+    if (!(star ? (a && b) : (a || b))) continue;  // robfig dayMatches
+    if (day != day0)
+      return day * 86400 + (int64_t)AM_CTZ64(hrs) * 3600 + (int64_t)AM_CTZ64(mins) * 60;
+    if (mod0 >= 1440) continue;  // start was in the last minute of the day
+    const int32_t h0 = mod0 / 60, m0 = mod0 % 60;
+    if ((hrs >> h0) & 1) {
+      const uint64_t later = mins >> m0;
+      if (later) return day * 86400 + h0 * 3600 + (int64_t)(m0 + AM_CTZ64(later)) * 60;
+    }
+    const uint64_t hl = (h0 + 1 < 24) ? (hrs >> (h0 + 1)) : 0;
+    if (hl) return day * 86400 + (int64_t)(h0 + 1 + AM_CTZ64(hl)) * 3600 + (int64_t)AM_CTZ64(mins) * 60;
+  }
+}
+
+// hcc.go:262  RepeatAfterSec = int(Next(now).Sub(now')/time.Second) + 1 for a real
+// clock (0 < ns): whole seconds from floor(now) to the next activation; when Next is
+// the zero time Sub saturates: int(minDuration/Second) + 1.
+AM_HD int64_t repeat_after_from_next(int64_t next, int64_t t) {
+  return next == kNoNextFire ? -9223372036ll + 1 : next - t;
 }
 
 }  // namespace amsweep

@@ -367,11 +367,6 @@ const Named kNamed[] = {
     {"@hourly", 1, every_value(kHour), every_value(kDom), every_value(kMonth), every_value(kDow)},
 };
 
-bool day_ok(const am_cron_t& c, int dom, int dow) {
-  bool a = (c.dom >> dom) & 1, b = (c.dow >> dow) & 1;
-  return ((c.dom | c.dow) & AM_STAR_BIT) ? (a && b) : (a || b);
-}
-
 bool fits32(int64_t v) { return v >= INT32_MIN && v <= INT32_MAX; }
 constexpr int64_t kTimeLimit = 1ll << 55;
 
@@ -481,52 +476,11 @@ int64_t am_cron_next(const am_cron_t* c, int64_t t) {
   if (!c) return INT64_MIN;
   if (c->kind == AM_CRON_EVERY) return t + c->delay_sec;
   if (c->kind != AM_CRON_SPEC) return INT64_MIN;
-  const uint64_t mins = c->minute & ((1ull << 60) - 1);
-  const uint64_t hrs = c->hour & ((1ull << 24) - 1);
-  if (!mins || !hrs) return INT64_MIN;
-  const int64_t start = t + 1;
-  int64_t day0;
-  int32_t sod;
-  amsweep::split_days(start, day0, sod);
-  int64_t y;
-  int32_t m, d;
-  amsweep::civil_from_days(day0, y, m, d);
-  const int64_t year_limit = y + 5;  // robfig: give up after yearLimit
-  // first candidate minute-of-day on the starting day: ceil(sod / 60)
-  int32_t mod0 = (sod + 59) / 60;
-  for (int64_t day = day0;; ++day) {
-    amsweep::civil_from_days(day, y, m, d);
-    if (y > year_limit) return INT64_MIN;
-    if (!((c->month >> m) & 1)) {  // jump to the 1st of the next month
-      int64_t ny = y;
-      int32_t nm = m + 1;
-      if (nm == 13) { nm = 1; ++ny; }
-      day = amsweep::days_from_civil(ny, nm, 1) - 1;
-      continue;
-    }
-    if (!day_ok(*c, d, amsweep::weekday_from_days(day))) continue;
-    if (day != day0) {
-      return day * 86400 + (int64_t)__builtin_ctzll(hrs) * 3600 + (int64_t)__builtin_ctzll(mins) * 60;
-    }
-    if (mod0 >= 1440) continue;  // start was in the last minute of the day
-    int32_t h0 = mod0 / 60, m0 = mod0 % 60;
-    if ((hrs >> h0) & 1) {
-      uint64_t later = mins >> m0;
-      if (later) return day * 86400 + h0 * 3600 + (int64_t)(m0 + __builtin_ctzll(later)) * 60;
-    }
-    uint64_t hl = (h0 + 1 < 24) ? (hrs >> (h0 + 1)) : 0;
-    if (hl) {
-      int32_t h = h0 + 1 + __builtin_ctzll(hl);
-      return day * 86400 + (int64_t)h * 3600 + (int64_t)__builtin_ctzll(mins) * 60;
-    }
-  }
+  return amsweep::cron_next_utc(c->minute, c->hour, c->dom, c->month, c->dow, t);
 }
 
 int64_t am_cron_repeat_after_sec(const am_cron_t* c, int64_t unix_sec) {
-  int64_t nx = am_cron_next(c, unix_sec);
-  // zero time: Sub saturates at minDuration, int(minDuration/Second)+1
-  if (nx == INT64_MIN) return -9223372036ll + 1;
-  return nx - unix_sec;
+  return amsweep::repeat_after_from_next(am_cron_next(c, unix_sec), unix_sec);
 }
 
 int am_remedy_is_empty(size_t generate_name_len, int resource_is_nil, int64_t timeout,

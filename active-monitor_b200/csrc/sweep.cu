@@ -548,6 +548,28 @@ int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint3
   return rc;
 }
 
+int am_sweep_repeat_after_sec(am_sweep_t* h, int64_t unix_sec, uint64_t first, uint64_t n, int64_t* out) {
+  if (!h || (n && !out)) return AM_E_INVAL;
+  if (first + n > h->capacity || first + n < first || n > 0xFFFFFFFFull) return AM_E_INVAL;
+  if (unix_sec >= (1ll << 55) || unix_sec <= -(1ll << 55)) return AM_E_RANGE;
+  if (n == 0) return AM_OK;
+  TickGuard g(h);
+  if (!g.ok) return AM_E_BUSY;
+  AM_CUDA(h, cudaSetDevice(h->device));
+  int rc = drain_staged(h);
+  if (rc != AM_OK) return rc;
+  AM_CUDA(h, h->dev_in.reserve(n * 8));
+  AM_CUDA(h, h->pin_out.reserve(n * 8));
+  next_fire_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->cols, (uint32_t)first, (uint32_t)n,
+                                                                     unix_sec, (int64_t*)h->dev_in.p);
+  h->launches++;
+  AM_CUDA(h, cudaGetLastError());
+  AM_CUDA(h, cudaMemcpyAsync(h->pin_out.p, h->dev_in.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+  AM_CUDA(h, cudaStreamSynchronize(h->stream));
+  memcpy(out, h->pin_out.p, n * 8);
+  return AM_OK;
+}
+
 int am_sweep_read(am_sweep_t* h, uint64_t first, uint64_t n, const uint64_t* idx,
                   am_record_cols_t* out) {
   if (!h || !out) return AM_E_INVAL;

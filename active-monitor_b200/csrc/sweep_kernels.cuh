@@ -563,6 +563,27 @@ __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, uint64_t n) {
   for (; i < n; i += stride) p[i] = v;
 }
 
+// RepeatAfterSec as the reference derives it at reconcile time (hcc.go:259-262):
+// for a 5-field schedule Next(T) - T (robfig SpecSchedule.Next, cron_next_utc), for
+// "@every d" and interval checks the stored interval, 0 for everything else.  One
+// thread per record; the day scan diverges, which is fine for an on-demand query
+// (status display, timer-wheel bucketing) that is not part of the per-tick path.
+__global__ void next_fire_kernel(DevCols c, uint32_t first, uint32_t n, int64_t T, int64_t* out) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t i = first + k;
+  const uint32_t f = c.flags[i];
+  const uint32_t kind = f & AM_KIND_MASK;
+  int64_t v = 0;
+  if (!(f & AM_F_TOMBSTONE)) {
+    if (kind == AM_KIND_CRON_SPEC)
+      v = repeat_after_from_next(cron_next_utc(c.minute[i], c.hour[i], c.dom[i], c.month[i], c.dow[i], T), T);
+    else if (kind == AM_KIND_INTERVAL || kind == AM_KIND_CRON_EVERY)
+      v = c.ras[i];
+  }
+  out[k] = v;
+}
+
 // ---- staged controller events (upsert / remove / post_result) ---------------
 // Events reach the library from many goroutines between two ticks; per slot
 // they must take effect in call order.  An event's tick-local sequence number

@@ -242,6 +242,13 @@ class Sweep:
                                                  out.ctypes.data), "am_sweep_run_ticks")
         return out
 
+    def repeat_after_sec(self, unix_sec: int, first: int, n: int) -> np.ndarray:
+        """hcc.go:262 for every record of [first, first+n): Next() evaluated on the device."""
+        out = np.zeros(n, dtype=np.int64)
+        self._check(self._lib.am_sweep_repeat_after_sec(self._h, unix_sec, first, n, out.ctypes.data),
+                    "am_sweep_repeat_after_sec")
+        return out
+
     # -- state out
     def read_range(self, first: int, n: int, names=None) -> dict:
         cols = {name: np.zeros(n, dtype=dt) for name, dt in L.COLUMNS

@@ -235,6 +235,13 @@ int am_sweep_tick_device(am_sweep_t*, int64_t unix_sec, uint32_t mode, void* d_d
 int am_sweep_run_ticks(am_sweep_t*, int64_t unix_sec0, uint64_t n_ticks, uint32_t mode,
                        uint64_t seed, am_tick_stats_t* stats_out);
 
+/* RepeatAfterSec of records [first, first+n) as the reference derives it at
+ * reconcile time (hcc.go:259-262): Next(unix_sec) - unix_sec for a 5-field
+ * schedule (robfig SpecSchedule.Next evaluated on the device; -9223372035 when
+ * nothing fires within five years), the stored interval for "@every"/interval
+ * checks, 0 otherwise.  On-demand query, not part of the per-tick path. */
+int am_sweep_repeat_after_sec(am_sweep_t*, int64_t unix_sec, uint64_t first, uint64_t n, int64_t* out);
+
 /* Device -> host read-back of record state (status write-back, hcc.go:1445;
  * checkpoint). idx == NULL reads the range [first, first+n). */
 int am_sweep_read(am_sweep_t*, uint64_t first, uint64_t n, const uint64_t* idx,

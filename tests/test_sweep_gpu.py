@@ -352,3 +352,30 @@ def test_staged_events_take_effect_in_call_order(am):
         s.post_result([5], [am.PHASE_FAILED])
         _, _, st2 = s.tick(T + 1)
         assert st2["n_result_fail"] == 1 and s.read([5])["failed"][0] == 1
+
+
+def test_repeat_after_sec_on_device_equals_oracle(am, orc, gen):
+    """hcc.go:262's RepeatAfterSec = Next(now) - now, evaluated for
+    every record on the device, against the oracle's Go-shaped Next()."""
+    import ctypes as C
+    n = 60_000
+    prod, _ = _gen_pair(gen, am, orc, 2, 2, n, T0)
+    lib = orc.load()
+    with am.Sweep(capacity=n) as s:
+        s.load_range(0, prod)
+        for T in (T0, T0 + 17, T_OCT1 - 1, 1709164799, 4102444799):
+            got = s.repeat_after_sec(T, 0, n)
+            kind = prod["flags"] & 7
+            want = np.zeros(n, dtype=np.int64)
+            iv = (kind == am.KIND_INTERVAL) | (kind == am.KIND_CRON_EVERY)
+            want[iv] = prod["ras"][iv]
+            for i in np.flatnonzero(kind == am.KIND_CRON_SPEC):
+                c = orc.OrcCron(int(prod["minute"][i]), int(prod["hour"][i]), int(prod["dom"][i]),
+                                int(prod["month"][i]), int(prod["dow"][i]), 0, 1, 0)
+                want[i] = lib.orc_cron_repeat_after_sec(C.byref(c), T)
+            np.testing.assert_array_equal(got, want, err_msg=f"T={T}")
+            assert (got[kind == am.KIND_CRON_SPEC] != 0).all()
+        # a sub-range, and the unsatisfiable schedule (Feb 30): Go's saturated value
+        rc, r = am.classify(cron="0 0 30 2 *")
+        s.upsert([5], r)
+        assert s.repeat_after_sec(T0, 5, 1)[0] == -9223372035
