@@ -434,28 +434,32 @@ int am_sweep_remove(am_sweep_t* h, uint64_t n, const uint64_t* idx) {
 int am_sweep_post_result(am_sweep_t* h, uint64_t n, const uint64_t* idx, const uint8_t* phase,
                          const uint8_t* remedy_phase) {
   if (!h || (n && (!idx || !phase))) return AM_E_INVAL;
-  const uint64_t cap = h->capacity;
-  uint64_t bad = 0;
-  for (uint64_t k = 0; k < n; ++k) {  // branch-free validation pass
-    bad |= (uint64_t)(idx[k] >= cap) | (uint64_t)(phase[k] > AM_PHASE_FAILED) << 1;
-    if (remedy_phase) bad |= (uint64_t)(remedy_phase[k] > AM_PHASE_FAILED) << 1;
-  }
-  if (bad & 1) return AM_E_RANGE;
-  if (bad & 2) return AM_E_INVAL;
   std::lock_guard<std::mutex> lk(h->mu);
   if (h->n_ops + n > 0x3FFFFFF0ull) return AM_E_NOSPACE;
   AM_CUDA(h, cudaSetDevice(h->device));
   AM_CUDA(h, grow_pinned(h->st_ops, h->n_ops * sizeof(StagedOp), (h->n_ops + n) * sizeof(StagedOp)));
   StagedOp* ops = (StagedOp*)h->st_ops.p + h->n_ops;
+  // one pass: validate and stage; nothing is committed (n_ops unchanged) on a bad entry.
   // phase -> flag bits: {none, Succeeded, Failed} -> {0, PENDING_OK, PENDING_FAIL}
-  static const uint32_t kPhaseBits[3] = {0u, AM_F_PENDING_OK, AM_F_PENDING_FAIL};
-  static const uint32_t kRemedyBits[3] = {0u, AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK, AM_F_REMEDY_PENDING};
+  static const uint32_t kPhaseBits[4] = {0u, AM_F_PENDING_OK, AM_F_PENDING_FAIL, 0u};
+  static const uint32_t kRemedyBits[4] = {0u, AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK, AM_F_REMEDY_PENDING, 0u};
+  const uint64_t cap = h->capacity;
+  uint64_t bad_range = 0, bad_phase = 0;
   if (remedy_phase) {
-    for (uint64_t k = 0; k < n; ++k)
-      ops[k] = StagedOp{(uint32_t)idx[k], kOpResult | kPhaseBits[phase[k]] | kRemedyBits[remedy_phase[k]]};
+    for (uint64_t k = 0; k < n; ++k) {
+      bad_range |= (uint64_t)(idx[k] >= cap);
+      bad_phase |= (uint64_t)(phase[k] > AM_PHASE_FAILED) | (uint64_t)(remedy_phase[k] > AM_PHASE_FAILED);
+      ops[k] = StagedOp{(uint32_t)idx[k], kOpResult | kPhaseBits[phase[k] & 3] | kRemedyBits[remedy_phase[k] & 3]};
+    }
   } else {
-    for (uint64_t k = 0; k < n; ++k) ops[k] = StagedOp{(uint32_t)idx[k], kOpResult | kPhaseBits[phase[k]]};
+    for (uint64_t k = 0; k < n; ++k) {
+      bad_range |= (uint64_t)(idx[k] >= cap);
+      bad_phase |= (uint64_t)(phase[k] > AM_PHASE_FAILED);
+      ops[k] = StagedOp{(uint32_t)idx[k], kOpResult | kPhaseBits[phase[k] & 3]};
+    }
   }
+  if (bad_range) return AM_E_RANGE;
+  if (bad_phase) return AM_E_INVAL;
   h->n_ops += n;
   h->n_result_ops += (uint32_t)n;
   return AM_OK;

@@ -313,6 +313,7 @@ def main():
         idx_h = np.empty(n, dtype=np.uint64)
         act_h = np.empty(n, dtype=np.uint32)
         ok_phase = np.full(n, am.PHASE_SUCCEEDED, dtype=np.uint8)
+        sel = np.empty(n, dtype=np.uint64)
         prev = None
         h2d = d2h = 0
         reps = max(10, min(args.steps, 120))
@@ -328,9 +329,9 @@ def main():
                     h2d += len(prev) * 8
                 gi, ga, st = sweep.tick(T0 + tick_no, mode=am.SWEEP_FULL_SCAN, buffers=(idx_h, act_h))
                 tick_no += 1
-                prev = gi[(ga & am.ACT_SUBMIT_HC) != 0]  # the checks just submitted ...
-                if base:
-                    prev -= base                                 # ... as local slots of this shard
+                # the checks just submitted, as local slots (compiled loop standing in for the
+                # Go shim's walk over the tick's result, hcc.go:269-288)
+                prev = amgen.select_submitted(gi, ga, base, sel)
                 d2h += len(gi) * 5 + 128
             if phase_name == "timed":
                 barrier()

@@ -288,3 +288,17 @@ void amgen_healthchecks(int config, uint64_t seed, uint64_t first, uint64_t n, i
 }
 
 int amgen_str_stride(void) { return AMGEN_STR; }
+
+/* Harness stand-in for the controller's loop over a tick's result (the Go shim
+ * walks the (index, action) list to submit workflows, hcc.go:269-288): collect
+ * the LOCAL slots of the checks whose action carries AM_ACT_SUBMIT_HC, i.e. the
+ * workflows whose completion the closed-loop harness posts back next tick. */
+uint64_t amgen_select_submitted(const uint64_t* idx, const uint32_t* act, uint64_t n, uint64_t base,
+                                uint64_t* out_local) {
+  uint64_t m = 0;
+  for (uint64_t k = 0; k < n; k++) {
+    out_local[m] = idx[k] - base;
+    m += (act[k] & AM_ACT_SUBMIT_HC) ? 1u : 0u;
+  }
+  return m;
+}

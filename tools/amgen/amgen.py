@@ -53,6 +53,8 @@ def load() -> C.CDLL:
         lib.amgen_healthchecks.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int64,
                                            C.c_void_p, C.c_void_p, C.c_void_p]
         lib.amgen_str_stride.restype = C.c_int
+        lib.amgen_select_submitted.restype = C.c_uint64
+        lib.amgen_select_submitted.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         lib.amgen_key.restype = C.c_uint64
         lib.amgen_key.argtypes = [C.c_uint64] * 3
         _lib = lib
@@ -91,3 +93,10 @@ def healthchecks(config: int, seed: int, first: int, n: int, T0: int):
         ln = hcs[k].cron_len
         crons.append(raw[k * stride:k * stride + ln].decode("utf-8"))
     return hcs, crons, post
+
+
+def select_submitted(idx: np.ndarray, act: np.ndarray, base: int, out: np.ndarray) -> np.ndarray:
+    """local slots of the entries whose action has AM_ACT_SUBMIT_HC (compiled loop: stands
+    in for the Go shim walking the tick's result); `out` must hold len(idx) u64."""
+    m = load().amgen_select_submitted(idx.ctypes.data, act.ctypes.data, len(idx), base, out.ctypes.data)
+    return out[:m]

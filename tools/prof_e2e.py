@@ -12,6 +12,7 @@ s = am.Sweep(capacity=n)
 s.load_range(0, cols)
 idx_h, act_h = np.empty(n, np.uint64), np.empty(n, np.uint32)
 ok = np.full(n, am.PHASE_SUCCEEDED, np.uint8)
+sel = np.empty(n, np.uint64)
 prev = None
 acc = {"post": 0.0, "tick": 0.0, "glue": 0.0, "kernel_ms": 0.0}
 for k in range(60):
@@ -21,7 +22,7 @@ for k in range(60):
     t1 = time.perf_counter()
     gi, ga, st = s.tick(T0 + k, mode=am.SWEEP_FULL_SCAN, buffers=(idx_h, act_h))
     t2 = time.perf_counter()
-    prev = gi[(ga & am.ACT_SUBMIT_HC) != 0]
+    prev = amgen.select_submitted(gi, ga, 0, sel)
     t3 = time.perf_counter()
     if k >= 10:
         acc["post"] += t1 - t0; acc["tick"] += t2 - t1; acc["glue"] += t3 - t2; acc["kernel_ms"] += s.last_kernel_ms
