@@ -261,26 +261,28 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
 
   uint32_t act[2][2];
   uint32_t res_lane = 0;  // 4 x 8-bit counts of results applied by this lane
+  uint32_t nfl[2][2];     // flags / finishedAt after this tick
+  int64_t nfa[2][2];
+  bool dirty[2] = {false, false};
+  uint32_t needy = 0, due_bits = 0;  // bit (2h+j): record needs the remedy/counter columns / is due
 
+  // ---- schedule decision for the lane's four records ------------------------
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const uint32_t flg[2] = {fl[h].x, fl[h].y};
-    const int32_t rasv[2] = {ras[h].x, ras[h].y};
-    const int64_t fav[2] = {fa[h].x, fa[h].y};
-
-    bool due[2], stopped_now[2], need_b[2];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-      const uint32_t f = flg[j];
+      const uint32_t f = j ? fl[h].y : fl[h].x;
+      const int32_t rasv = j ? ras[h].y : ras[h].x;
+      const int64_t fav = j ? fa[h].y : fa[h].x;
       const uint32_t kind = f & AM_KIND_MASK;
       // kinds 1..5 are evaluated; tombstones, NO_RESOURCE (hcc.go:227) and host-fallback are not
       const bool live = ((0x3Eu >> kind) & 1u) && !(f & AM_F_TOMBSTONE);
       const bool has_result = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL)) != 0;
       const bool pending = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING)) != 0;
       // step 1 sets finishedAt = T before the due decision is taken
-      const int64_t fa_eff = has_result ? T : fav[j];
+      const int64_t fa_eff = has_result ? T : fav;
       const int64_t elapsed = (int64_t)((uint64_t)T - (uint64_t)fa_eff);
-      const bool due_iv = !(elapsed < (int64_t)rasv[j]);  // not(hcc.go:264) == timer :751 fired
+      const bool due_iv = !(elapsed < (int64_t)rasv);  // not(hcc.go:264) == timer :751 fired
       bool due_cron = false;
       if (MASKS) {
         const uint64_t miv = j ? mi[h].y : mi[h].x, hrv = j ? hr[h].y : hr[h].x;
@@ -292,83 +294,77 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
         due_cron = w.sec0 && fld && (star ? (dmm && dwm) : (dmm || dwm));
       }
       const bool is_iv = ((0x14u >> kind) & 1u) != 0;  // INTERVAL or CRON_EVERY
-      due[j] = live && (is_iv ? due_iv : (kind == AM_KIND_CRON_SPEC && due_cron));
-      stopped_now[j] = live && kind == AM_KIND_STOPPED && !(f & AM_F_STOPPED_REPORTED);
-      need_b[j] = live && (pending || (CLOSED && due[j]));
-      act[h][j] = (due[j] ? AM_ACT_SUBMIT_HC : 0u) | (stopped_now[j] ? AM_ACT_STOPPED : 0u) |
+      const bool due = live && (is_iv ? due_iv : (kind == AM_KIND_CRON_SPEC && due_cron));
+      const bool stopped_now = live && kind == AM_KIND_STOPPED && !(f & AM_F_STOPPED_REPORTED);
+      act[h][j] = (due ? AM_ACT_SUBMIT_HC : 0u) | (stopped_now ? AM_ACT_STOPPED : 0u) |
                   ((live && kind == AM_KIND_PARSE_ERROR) ? AM_ACT_PARSE_ERROR : 0u);
+      nfl[h][j] = f;
+      nfa[h][j] = fav;
+      if (stopped_now) {  // hcc.go:238-250: Status "Stopped", FinishedAt = now
+        nfl[h][j] = f | AM_F_STOPPED_REPORTED;
+        nfa[h][j] = T;
+        dirty[h] = true;
+      }
+      if (live && (pending || (CLOSED && due))) needy |= 1u << (2 * h + j);
+      if (due) due_bits |= 1u << (2 * h + j);
     }
+  }
 
-    uint32_t nfl[2] = {flg[0], flg[1]};
-    int64_t nfa[2] = {fav[0], fav[1]};
-    bool dirty = false;  // flags / finishedAt of this lane's pair changed
-    const bool lane_b = need_b[0] || need_b[1];
-
-    if (__any_sync(kFull, lane_b)) {
-      // ---- phase B: remedy/counter columns, only for lanes that need them --
-      if (lane_b) {
-        const uint32_t r = r0[h];
-        const int2 lim = ld_stream(reinterpret_cast<const int2*>(p.c.runs_limit + r));
-        const int2 rst = ld_stream(reinterpret_cast<const int2*>(p.c.reset_interval + r));
-        const int2 sc = ld_stream(reinterpret_cast<const int2*>(p.c.success + r));
-        const int2 fc = ld_stream(reinterpret_cast<const int2*>(p.c.failed + r));
-        const int2 rsc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_success + r));
-        const int2 rfc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_failed + r));
-        const int2 rtc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_total + r));
-        const longlong2 rfa = ld_stream(reinterpret_cast<const longlong2*>(p.c.remedy_finished_at + r));
-        int32_t ns[2] = {sc.x, sc.y}, nf[2] = {fc.x, fc.y};
-        int32_t nrs[2] = {rsc.x, rsc.y}, nrf[2] = {rfc.x, rfc.y}, nrt[2] = {rtc.x, rtc.y};
-        int64_t nrfa[2] = {rfa.x, rfa.y};
-        const int32_t limv[2] = {lim.x, lim.y}, rstv[2] = {rst.x, rst.y};
+  // ---- results + remedy state machine: a warp loop in which every lane takes its
+  //      next needy record.  With few posted results / due records per warp the loop
+  //      runs once or twice instead of four predicated copies of the state machine;
+  //      the remedy/counter columns are read and written per record (the 36 B/record
+  //      are only touched for records that need them).
+  while (__any_sync(kFull, needy != 0)) {
+    if (needy) {
+      const int b = __ffs(needy) - 1;
+      needy &= needy - 1;
+      const uint32_t i = r0[0] + (uint32_t)(64 * (b >> 1) + (b & 1));
+      const int32_t lim = ld_stream(p.c.runs_limit + i), rst = ld_stream(p.c.reset_interval + i);
+      const int32_t sc = ld_stream(p.c.success + i), fc = ld_stream(p.c.failed + i);
+      const int32_t rsc = ld_stream(p.c.remedy_success + i), rfc = ld_stream(p.c.remedy_failed + i);
+      const int32_t rtc = ld_stream(p.c.remedy_total + i);
+      const int64_t rfa = ld_stream(p.c.remedy_finished_at + i);
+      const uint32_t f0 = b == 0 ? nfl[0][0] : b == 1 ? nfl[0][1] : b == 2 ? nfl[1][0] : nfl[1][1];
+      const int64_t fa0 = b == 0 ? nfa[0][0] : b == 1 ? nfa[0][1] : b == 2 ? nfa[1][0] : nfa[1][1];
+      RecState s{f0, fa0, sc, fc, rsc, rfc, rtc, rfa, lim, rst};
+      uint32_t res = 0;
+      uint32_t a = apply_result(s, T, res);
+      if (CLOSED && ((due_bits >> b) & 1u)) {
+        const uint64_t k = outcome_key(p.seed, p.shard_base + i, (uint64_t)T);
+        const uint32_t failp = (s.flags >> AM_F_FAILP_SHIFT) & 0xFFu;
+        const bool fail = (uint32_t)(k & 0xFF) < failp;
+        const bool rem_ok = (uint32_t)((k >> 8) & 0xFF) < 179u;
+        s.flags |= (fail ? AM_F_PENDING_FAIL : AM_F_PENDING_OK) | AM_F_REMEDY_PENDING |
+                   (rem_ok ? AM_F_REMEDY_OUTCOME_OK : 0u);
+        a |= apply_result(s, T, res);
+      }
+      res_lane += res;  // per lane at most 4 records x 2 results per byte
+      if (s.s != sc) st_stream(p.c.success + i, s.s);
+      if (s.f != fc) st_stream(p.c.failed + i, s.f);
+      if (s.rs != rsc) st_stream(p.c.remedy_success + i, s.rs);
+      if (s.rf != rfc) st_stream(p.c.remedy_failed + i, s.rf);
+      if (s.rt != rtc) st_stream(p.c.remedy_total + i, s.rt);
+      if (s.rfa != rfa) st_stream(p.c.remedy_finished_at + i, s.rfa);
+      // (a record "Stopped" in this very tick already carries STOPPED_REPORTED and
+      // finishedAt = T in nfl/nfa, and apply_result preserves both: the pause rule of
+      // hcc.go:238-250 and a posted result commute)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          if (need_b[j]) {
-            RecState s{flg[j], fav[j], ns[j], nf[j], nrs[j], nrf[j], nrt[j], nrfa[j], limv[j], rstv[j]};
-            uint32_t res = 0;
-            uint32_t a = apply_result(s, T, res);
-            if (CLOSED && due[j]) {
-              const uint64_t gidx = p.shard_base + (uint64_t)(r0[h] + (uint32_t)j);
-              const uint64_t k = outcome_key(p.seed, gidx, (uint64_t)T);
-              const uint32_t failp = (s.flags >> AM_F_FAILP_SHIFT) & 0xFFu;
-              const bool fail = (uint32_t)(k & 0xFF) < failp;
-              const bool rem_ok = (uint32_t)((k >> 8) & 0xFF) < 179u;
-              s.flags |= (fail ? AM_F_PENDING_FAIL : AM_F_PENDING_OK) | AM_F_REMEDY_PENDING |
-                         (rem_ok ? AM_F_REMEDY_OUTCOME_OK : 0u);
-              a |= apply_result(s, T, res);
-            }
-            act[h][j] |= a;
-            res_lane += res;  // per lane at most 4 records x 2 results per byte
-            nfl[j] = s.flags; nfa[j] = s.fa;
-            ns[j] = s.s; nf[j] = s.f; nrs[j] = s.rs; nrf[j] = s.rf; nrt[j] = s.rt; nrfa[j] = s.rfa;
-            dirty = true;  // a result always clears its PENDING flags
-          }
+      for (int q = 0; q < 4; ++q) {
+        if (q == b) {
+          act[q >> 1][q & 1] |= a;
+          nfl[q >> 1][q & 1] = s.flags;
+          nfa[q >> 1][q & 1] = s.fa;
         }
-        if (ns[0] != sc.x || ns[1] != sc.y)
-          st_stream(reinterpret_cast<int2*>(p.c.success + r), make_int2(ns[0], ns[1]));
-        if (nf[0] != fc.x || nf[1] != fc.y)
-          st_stream(reinterpret_cast<int2*>(p.c.failed + r), make_int2(nf[0], nf[1]));
-        if (nrs[0] != rsc.x || nrs[1] != rsc.y)
-          st_stream(reinterpret_cast<int2*>(p.c.remedy_success + r), make_int2(nrs[0], nrs[1]));
-        if (nrf[0] != rfc.x || nrf[1] != rfc.y)
-          st_stream(reinterpret_cast<int2*>(p.c.remedy_failed + r), make_int2(nrf[0], nrf[1]));
-        if (nrt[0] != rtc.x || nrt[1] != rtc.y)
-          st_stream(reinterpret_cast<int2*>(p.c.remedy_total + r), make_int2(nrt[0], nrt[1]));
-        if (nrfa[0] != rfa.x || nrfa[1] != rfa.y)
-          st_stream(reinterpret_cast<longlong2*>(p.c.remedy_finished_at + r),
-                    make_longlong2(nrfa[0], nrfa[1]));
       }
+      if (b < 2) dirty[0] = true; else dirty[1] = true;  // a result always clears its PENDING flags
     }
+  }
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      if (stopped_now[j]) {  // hcc.go:238-250: Status "Stopped", FinishedAt = now
-        nfa[j] = T;
-        nfl[j] |= AM_F_STOPPED_REPORTED;
-        dirty = true;
-      }
-    }
-    if (dirty) {
-      st_stream(reinterpret_cast<uint2*>(p.c.flags + r0[h]), make_uint2(nfl[0], nfl[1]));
-      st_stream(reinterpret_cast<longlong2*>(p.c.finished_at + r0[h]), make_longlong2(nfa[0], nfa[1]));
+  for (int h = 0; h < 2; ++h) {
+    if (dirty[h]) {
+      st_stream(reinterpret_cast<uint2*>(p.c.flags + r0[h]), make_uint2(nfl[h][0], nfl[h][1]));
+      st_stream(reinterpret_cast<longlong2*>(p.c.finished_at + r0[h]), make_longlong2(nfa[h][0], nfa[h][1]));
     }
   }
 
