@@ -219,10 +219,12 @@ int launch_sweep(am_sweep* h, int64_t T, uint32_t mode, uint32_t* d_idx, uint8_t
   if (sec_of_min < 0) sec_of_min += 60;
   const bool masks = sec_of_min == 0 || (mode & AM_SWEEP_FULL_SCAN);
   const bool closed = (mode & AM_SWEEP_CLOSED_LOOP) != 0;
-  if (closed && masks) sweep_tick_kernel<true, true><<<p.n_tiles, kBlock, 0, s>>>(p);
-  else if (closed) sweep_tick_kernel<true, false><<<p.n_tiles, kBlock, 0, s>>>(p);
-  else if (masks) sweep_tick_kernel<false, true><<<p.n_tiles, kBlock, 0, s>>>(p);
-  else sweep_tick_kernel<false, false><<<p.n_tiles, kBlock, 0, s>>>(p);
+  // dynamic shared memory = the per-lane staging slots of phase A
+  const size_t smem = masks ? kStageBytesMasks : kStageBytesNoMasks;
+  if (closed && masks) sweep_tick_kernel<true, true><<<p.n_tiles, kBlock, smem, s>>>(p);
+  else if (closed) sweep_tick_kernel<true, false><<<p.n_tiles, kBlock, smem, s>>>(p);
+  else if (masks) sweep_tick_kernel<false, true><<<p.n_tiles, kBlock, smem, s>>>(p);
+  else sweep_tick_kernel<false, false><<<p.n_tiles, kBlock, smem, s>>>(p);
   if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[1], s));
   CompactParams c{};
   c.seg_idx = h->seg_idx;
@@ -272,6 +274,11 @@ int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t
   h->cap_padded = (capacity + kTile - 1) / kTile * kTile;
   h->shard_base = shard_base;
   int rc = [&]() -> int {
+    // 56 KB of dynamic shared memory per CTA needs the opt-in attribute
+    AM_CUDA(h, cudaFuncSetAttribute(sweep_tick_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageBytesMasks));
+    AM_CUDA(h, cudaFuncSetAttribute(sweep_tick_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageBytesMasks));
+    AM_CUDA(h, cudaFuncSetAttribute(sweep_tick_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageBytesNoMasks));
+    AM_CUDA(h, cudaFuncSetAttribute(sweep_tick_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStageBytesNoMasks));
     AM_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     AM_CUDA(h, cudaEventCreate(&h->ev0));
     AM_CUDA(h, cudaEventCreate(&h->ev1));

@@ -15,10 +15,10 @@
 // Shape of the kernel (pure integer work, HBM-bandwidth bound, no tensor cores):
 //   * records live as SoA columns in HBM; a CTA of 256 threads owns one tile of
 //     1024 consecutive records, a warp owns 128 of them;
-//   * every warp-level load instruction is fully coalesced: lane L reads the
-//     16 B (two u64 records) or 8 B (two i32 records) at column + (w + 2L),
-//     twice per tile ("halves"), so 16 independent loads are in flight per
-//     lane before the first use;
+//   * every warp-level copy is fully coalesced: lane L copies the 16 B (two u64
+//     records) or 8 B (two i32 records) at column + (w + 2L), twice per tile
+//     ("halves"), with cp.async into its own shared-memory slots — 16 copies in
+//     flight per lane, 56 KB per CTA, independent of register allocation;
 //   * the tick's broken-down time is computed once per tick as one-hot words
 //     and reaches every CTA through the kernel parameters (constant bank); a
 //     5-field schedule fires iff minute&M && hour&H && month&Mo && dayMatches
@@ -54,6 +54,9 @@ constexpr int kRecPerWarp = 128;             // 2 halves x 32 lanes x 2 records
 constexpr int kTile = kWarps * kRecPerWarp;  // 1024 records per CTA
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kNumAcc = 16;  // == number of u64 fields of am_tick_stats_t
+// phase-A staging per CTA: 12 (6 u64 columns x 2 halves) or 2 slots of 16 B + 4 slots of 8 B per thread
+constexpr size_t kStageBytesMasks = (size_t)kBlock * (12 * 16 + 4 * 8);    // 56 KB
+constexpr size_t kStageBytesNoMasks = (size_t)kBlock * (2 * 16 + 4 * 8);   // 16 KB
 
 struct DevCols {
   uint64_t *minute, *hour, *dom, *month, *dow;
@@ -99,6 +102,29 @@ struct CompactParams {
 // ---- streaming loads / stores: every byte is touched once per tick --------
 template <typename T>
 __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
+
+// Phase-A column copies: global -> this lane's own shared-memory slots with
+// cp.async (LDGSTS), streaming (evict-first) L2 policy.  All 16 copies of a lane
+// are in flight at once no matter how the register allocator schedules the rest
+// of the kernel: as plain register loads the compiler split them into two
+// batches (and once even sank half of them into the match branches), costing up
+// to 45 % of the bandwidth.  A lane only reads back what it copied itself, so a
+// per-thread cp.async.wait_all is the only synchronisation needed.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* g, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(g), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t smem_addr, const void* g, uint64_t pol) {
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(smem_addr), "l"(g), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 template <typename T>
 __device__ __forceinline__ void st_stream(T* p, T v) { __stcs(p, v); }
 
@@ -228,28 +254,48 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   const uint32_t tile_base = tile * (uint32_t)kTile;
   const int64_t T = p.T;
 
-  // ---- phase A: issue every schedule-column load of this lane up front ----
-  // half h covers records r0(h) .. r0(h)+1, r0 = tile_base + warp*128 + h*64 + lane*2
+  // ---- phase A: every schedule-column copy of this lane, issued up front ----
+  // half h covers records r0(h) .. r0(h)+1, r0 = tile_base + warp*128 + h*64 + lane*2.
+  // Shared-memory slots: kS16 slots of 16 B per thread ([slot][tid], conflict-free),
+  // then 4 slots of 8 B per thread.
+  extern __shared__ __align__(16) unsigned char stage[];
+  constexpr int kS16 = MASKS ? 12 : 2;
+  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+  const uint64_t stream_pol = l2_evict_first_policy();
   uint32_t r0[2];
-  ulonglong2 mi[2], hr[2], dm[2], mo[2], dw[2];
-  longlong2 fa[2];
-  int2 ras[2];
-  uint2 fl[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     r0[h] = tile_base + (uint32_t)(warp * kRecPerWarp + h * 64 + lane * 2);
-    fl[h] = ld_stream(reinterpret_cast<const uint2*>(p.c.flags + r0[h]));
-    ras[h] = ld_stream(reinterpret_cast<const int2*>(p.c.ras + r0[h]));
-    fa[h] = ld_stream(reinterpret_cast<const longlong2*>(p.c.finished_at + r0[h]));
+    cp_async8(stage_s + (uint32_t)(kS16 * kBlock * 16 + ((2 * h + 0) * kBlock + tid) * 8), p.c.flags + r0[h], stream_pol);
+    cp_async8(stage_s + (uint32_t)(kS16 * kBlock * 16 + ((2 * h + 1) * kBlock + tid) * 8), p.c.ras + r0[h], stream_pol);
+    cp_async16(stage_s + (uint32_t)((h * kBlock + tid) * 16), p.c.finished_at + r0[h], stream_pol);
   }
   if (MASKS) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      mi[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.minute + r0[h]));
-      hr[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.hour + r0[h]));
-      dm[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.dom + r0[h]));
-      mo[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.month + r0[h]));
-      dw[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.dow + r0[h]));
+      cp_async16(stage_s + (uint32_t)(((2 + 5 * h + 0) * kBlock + tid) * 16), p.c.minute + r0[h], stream_pol);
+      cp_async16(stage_s + (uint32_t)(((2 + 5 * h + 1) * kBlock + tid) * 16), p.c.hour + r0[h], stream_pol);
+      cp_async16(stage_s + (uint32_t)(((2 + 5 * h + 2) * kBlock + tid) * 16), p.c.dom + r0[h], stream_pol);
+      cp_async16(stage_s + (uint32_t)(((2 + 5 * h + 3) * kBlock + tid) * 16), p.c.month + r0[h], stream_pol);
+      cp_async16(stage_s + (uint32_t)(((2 + 5 * h + 4) * kBlock + tid) * 16), p.c.dow + r0[h], stream_pol);
+    }
+  }
+  cp_async_wait_all();
+  const ulonglong2* s16 = reinterpret_cast<const ulonglong2*>(stage);
+  const uint2* s8 = reinterpret_cast<const uint2*>(stage + kS16 * kBlock * 16);
+  ulonglong2 mi[2], hr[2], dm[2], mo[2], dw[2], fa[2];
+  uint2 ras[2], fl[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    fl[h] = s8[(2 * h + 0) * kBlock + tid];
+    ras[h] = s8[(2 * h + 1) * kBlock + tid];
+    fa[h] = s16[h * kBlock + tid];
+    if (MASKS) {
+      mi[h] = s16[(2 + 5 * h + 0) * kBlock + tid];
+      hr[h] = s16[(2 + 5 * h + 1) * kBlock + tid];
+      dm[h] = s16[(2 + 5 * h + 2) * kBlock + tid];
+      mo[h] = s16[(2 + 5 * h + 3) * kBlock + tid];
+      dw[h] = s16[(2 + 5 * h + 4) * kBlock + tid];
     }
   }
 
@@ -272,8 +318,8 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const uint32_t f = j ? fl[h].y : fl[h].x;
-      const int32_t rasv = j ? ras[h].y : ras[h].x;
-      const int64_t fav = j ? fa[h].y : fa[h].x;
+      const int32_t rasv = (int32_t)(j ? ras[h].y : ras[h].x);
+      const int64_t fav = (int64_t)(j ? fa[h].y : fa[h].x);
       const uint32_t kind = f & AM_KIND_MASK;
       // kinds 1..5 are evaluated; tombstones, NO_RESOURCE (hcc.go:227) and host-fallback are not
       const bool live = ((0x3Eu >> kind) & 1u) && !(f & AM_F_TOMBSTONE);
@@ -288,10 +334,11 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
         const uint64_t miv = j ? mi[h].y : mi[h].x, hrv = j ? hr[h].y : hr[h].x;
         const uint64_t dmv = j ? dm[h].y : dm[h].x, mov = j ? mo[h].y : mo[h].x;
         const uint64_t dwv = j ? dw[h].y : dw[h].x;
-        const bool fld = (miv & w.minute) && (hrv & w.hour) && (mov & w.month);
+        // branch-free: every term is evaluated (no short-circuit control flow)
+        const bool fld = ((miv & w.minute) != 0) & ((hrv & w.hour) != 0) & ((mov & w.month) != 0);
         const bool dmm = (dmv & w.dom) != 0, dwm = (dwv & w.dow) != 0;
         const bool star = ((dmv | dwv) >> 63) != 0;  // robfig dayMatches
-        due_cron = w.sec0 && fld && (star ? (dmm && dwm) : (dmm || dwm));
+        due_cron = (w.sec0 != 0) & fld & (star ? (dmm & dwm) : (dmm | dwm));
       }
       const bool is_iv = ((0x14u >> kind) & 1u) != 0;  // INTERVAL or CRON_EVERY
       const bool due = live && (is_iv ? due_iv : (kind == AM_KIND_CRON_SPEC && due_cron));
