@@ -104,7 +104,8 @@ template <typename T>
 __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
 
 // Phase-A column copies: global -> this lane's own shared-memory slots with
-// cp.async (LDGSTS), streaming (evict-first) L2 policy.  All 16 copies of a lane
+// cp.async (LDGSTS; the L2::cache_hint form raised "illegal instruction" on sm_100a
+// with the 8-byte size, so the copies carry no eviction hint).  All 16 copies of a lane
 // are in flight at once no matter how the register allocator schedules the rest
 // of the kernel: as plain register loads the compiler split them into two
 // batches (and once even sank half of them into the match branches), costing up
@@ -115,13 +116,11 @@ __device__ __forceinline__ uint64_t l2_evict_first_policy() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* g, uint64_t pol) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(g), "l"(pol)
-               : "memory");
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* g, uint64_t /*pol*/) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
 }
-__device__ __forceinline__ void cp_async8(uint32_t smem_addr, const void* g, uint64_t pol) {
-  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(smem_addr), "l"(g), "l"(pol)
-               : "memory");
+__device__ __forceinline__ void cp_async8(uint32_t smem_addr, const void* g, uint64_t /*pol*/) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(g) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
