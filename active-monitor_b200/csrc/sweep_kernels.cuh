@@ -14,11 +14,11 @@
 //
 // Shape of the kernel (pure integer work, HBM-bandwidth bound, no tensor cores):
 //   * records live as SoA columns in HBM; a CTA of 256 threads owns one tile of
-//     1024 consecutive records, a warp owns 128 of them;
-//   * every warp-level copy is fully coalesced: lane L copies the 16 B (two u64
-//     records) or 8 B (two i32 records) at column + (w + 2L), twice per tile
-//     ("halves"), with cp.async into its own shared-memory slots — 16 copies in
-//     flight per lane, 56 KB per CTA, independent of register allocation;
+//     1024 consecutive records, a warp owns 128 consecutive ones;
+//   * the tile's schedule columns are staged in shared memory by TMA bulk copies
+//     (cp.async.bulk + mbarrier): one elected thread issues one 4-8 KB copy per
+//     column, 56 KB in flight per CTA independent of register allocation, no
+//     per-lane load instructions; thread t then owns records 4t..4t+3;
 //   * the tick's broken-down time is computed once per tick as one-hot words
 //     and reaches every CTA through the kernel parameters (constant bank); a
 //     5-field schedule fires iff minute&M && hour&H && month&Mo && dayMatches
@@ -50,13 +50,13 @@ namespace amsweep {
 #endif
 constexpr int kBlock = AM_BLOCK;
 constexpr int kWarps = kBlock / 32;
-constexpr int kRecPerWarp = 128;             // 2 halves x 32 lanes x 2 records
+constexpr int kRecPerWarp = 128;             // 32 lanes x 4 consecutive records
 constexpr int kTile = kWarps * kRecPerWarp;  // 1024 records per CTA
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kNumAcc = 16;  // == number of u64 fields of am_tick_stats_t
-// phase-A staging per CTA: 12 (6 u64 columns x 2 halves) or 2 slots of 16 B + 4 slots of 8 B per thread
-constexpr size_t kStageBytesMasks = (size_t)kBlock * (12 * 16 + 4 * 8);    // 56 KB
-constexpr size_t kStageBytesNoMasks = (size_t)kBlock * (2 * 16 + 4 * 8);   // 16 KB
+// phase-A staging per CTA (one tile in record order): finishedAt + ras + flags [+ 5 masks]
+constexpr size_t kStageBytesNoMasks = (size_t)kTile * (8 + 4 + 4);           // 16 KB
+constexpr size_t kStageBytesMasks = kStageBytesNoMasks + (size_t)kTile * 40;  // 56 KB
 
 struct DevCols {
   uint64_t *minute, *hour, *dom, *month, *dow;
@@ -103,26 +103,44 @@ struct CompactParams {
 template <typename T>
 __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
 
-// Phase-A column copies: global -> this lane's own shared-memory slots with
-// cp.async (LDGSTS; the L2::cache_hint form raised "illegal instruction" on sm_100a
-// with the 8-byte size, so the copies carry no eviction hint).  All 16 copies of a lane
-// are in flight at once no matter how the register allocator schedules the rest
-// of the kernel: as plain register loads the compiler split them into two
-// batches (and once even sank half of them into the match branches), costing up
-// to 45 % of the bandwidth.  A lane only reads back what it copied itself, so a
-// per-thread cp.async.wait_all is the only synchronisation needed.
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-  uint64_t pol;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-  return pol;
+// Phase-A staging: TMA bulk copies (cp.async.bulk, SASS UBLKCP) global -> shared,
+// completion counted in bytes on an mbarrier.  One elected thread issues one copy per
+// column (4-8 KB each) for the whole tile; no lane executes a load for phase A, the
+// memory-level parallelism (56 KB per CTA) does not depend on register allocation, and
+// the data sits in shared memory in record order.  Measured alternatives: register
+// loads were split into two batches by ptxas and once even sunk into the match
+// branches (-45 % bandwidth); per-lane cp.async (LDGSTS) cost 16 copy + 16 read
+// instructions per lane (profiles/r01_summary.md).
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
 }
-__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* g, uint64_t /*pol*/) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(g) : "memory");
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void cp_async8(uint32_t smem_addr, const void* g, uint64_t /*pol*/) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr), "l"(g) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+               "r"(bytes)
+               : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+      "r"(phase)
+      : "memory");
+}
 
 template <typename T>
 __device__ __forceinline__ void st_stream(T* p, T v) { __stcs(p, v); }
@@ -241,8 +259,7 @@ __device__ __forceinline__ uint32_t apply_result(RecState& r, int64_t T, uint32_
 // bytes per record and all of the mask arithmetic disappear at compile time.
 template <bool CLOSED, bool MASKS>
 __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS + 1) sweep_tick_kernel(const SweepParams p) {
-  // one row per warp, written unconditionally: no zero-initialisation, no shared
-  // atomics, and therefore a single __syncthreads in the whole kernel
+  // one row per warp, written unconditionally: no zero-initialisation, no shared atomics
   __shared__ uint32_t s_warp_tot[kWarps];
   __shared__ uint32_t s_wres[kWarps][4];  // posted results applied: ok, fail, remedy ok, remedy fail
 
@@ -253,107 +270,92 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   const uint32_t tile_base = tile * (uint32_t)kTile;
   const int64_t T = p.T;
 
-  // ---- phase A: every schedule-column copy of this lane, issued up front ----
-  // half h covers records r0(h) .. r0(h)+1, r0 = tile_base + warp*128 + h*64 + lane*2.
-  // Shared-memory slots: kS16 slots of 16 B per thread ([slot][tid], conflict-free),
-  // then 4 slots of 8 B per thread.
-  extern __shared__ __align__(16) unsigned char stage[];
-  constexpr int kS16 = MASKS ? 12 : 2;
-  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
-  const uint64_t stream_pol = l2_evict_first_policy();
-  uint32_t r0[2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    r0[h] = tile_base + (uint32_t)(warp * kRecPerWarp + h * 64 + lane * 2);
-    cp_async8(stage_s + (uint32_t)(kS16 * kBlock * 16 + ((2 * h + 0) * kBlock + tid) * 8), p.c.flags + r0[h], stream_pol);
-    cp_async8(stage_s + (uint32_t)(kS16 * kBlock * 16 + ((2 * h + 1) * kBlock + tid) * 8), p.c.ras + r0[h], stream_pol);
-    cp_async16(stage_s + (uint32_t)((h * kBlock + tid) * 16), p.c.finished_at + r0[h], stream_pol);
-  }
-  if (MASKS) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      cp_async16(stage_s + (uint32_t)(((2 + 5 * h + 0) * kBlock + tid) * 16), p.c.minute + r0[h], stream_pol);
-      cp_async16(stage_s + (uint32_t)(((2 + 5 * h + 1) * kBlock + tid) * 16), p.c.hour + r0[h], stream_pol);
-      cp_async16(stage_s + (uint32_t)(((2 + 5 * h + 2) * kBlock + tid) * 16), p.c.dom + r0[h], stream_pol);
-      cp_async16(stage_s + (uint32_t)(((2 + 5 * h + 3) * kBlock + tid) * 16), p.c.month + r0[h], stream_pol);
-      cp_async16(stage_s + (uint32_t)(((2 + 5 * h + 4) * kBlock + tid) * 16), p.c.dow + r0[h], stream_pol);
-    }
-  }
-  cp_async_wait_all();
-  const ulonglong2* s16 = reinterpret_cast<const ulonglong2*>(stage);
-  const uint2* s8 = reinterpret_cast<const uint2*>(stage + kS16 * kBlock * 16);
-  ulonglong2 mi[2], hr[2], dm[2], mo[2], dw[2], fa[2];
-  uint2 ras[2], fl[2];
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    fl[h] = s8[(2 * h + 0) * kBlock + tid];
-    ras[h] = s8[(2 * h + 1) * kBlock + tid];
-    fa[h] = s16[h * kBlock + tid];
+  // ---- phase A: stage the tile's schedule columns in shared memory (TMA bulk) ----
+  // layout (record order): [fa 8K][ras 4K][flags 4K] then, with MASKS,
+  // [minute 8K][hour 8K][dom 8K][month 8K][dow 8K]; thread t owns records 4t..4t+3.
+  extern __shared__ __align__(128) unsigned char stage[];
+  __shared__ __align__(8) uint64_t s_bar;
+  int64_t* s_fa = reinterpret_cast<int64_t*>(stage);
+  int32_t* s_ras = reinterpret_cast<int32_t*>(stage + kTile * 8);
+  uint32_t* s_flags = reinterpret_cast<uint32_t*>(stage + kTile * 12);
+  uint64_t* s_mask = reinterpret_cast<uint64_t*>(stage + kTile * 16);  // 5 x kTile
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(&s_bar, (uint32_t)(MASKS ? kStageBytesMasks : kStageBytesNoMasks));
+    tma_bulk_g2s(s_fa, p.c.finished_at + tile_base, kTile * 8, &s_bar);
+    tma_bulk_g2s(s_ras, p.c.ras + tile_base, kTile * 4, &s_bar);
+    tma_bulk_g2s(s_flags, p.c.flags + tile_base, kTile * 4, &s_bar);
     if (MASKS) {
-      mi[h] = s16[(2 + 5 * h + 0) * kBlock + tid];
-      hr[h] = s16[(2 + 5 * h + 1) * kBlock + tid];
-      dm[h] = s16[(2 + 5 * h + 2) * kBlock + tid];
-      mo[h] = s16[(2 + 5 * h + 3) * kBlock + tid];
-      dw[h] = s16[(2 + 5 * h + 4) * kBlock + tid];
+      tma_bulk_g2s(s_mask + 0 * kTile, p.c.minute + tile_base, kTile * 8, &s_bar);
+      tma_bulk_g2s(s_mask + 1 * kTile, p.c.hour + tile_base, kTile * 8, &s_bar);
+      tma_bulk_g2s(s_mask + 2 * kTile, p.c.dom + tile_base, kTile * 8, &s_bar);
+      tma_bulk_g2s(s_mask + 3 * kTile, p.c.month + tile_base, kTile * 8, &s_bar);
+      tma_bulk_g2s(s_mask + 4 * kTile, p.c.dow + tile_base, kTile * 8, &s_bar);
     }
   }
+  __syncthreads();  // the initialised barrier is visible to every waiter
+  mbar_wait(&s_bar, 0);
+
+  const uint32_t r0 = tile_base + 4u * (uint32_t)tid;  // this thread's first record
+  const uint4 fl4 = *reinterpret_cast<const uint4*>(s_flags + 4 * tid);
+  const int4 ras4 = *reinterpret_cast<const int4*>(s_ras + 4 * tid);
+  const longlong2 fa01 = *reinterpret_cast<const longlong2*>(s_fa + 4 * tid);
+  const longlong2 fa23 = *reinterpret_cast<const longlong2*>(s_fa + 4 * tid + 2);
+  const uint32_t flv[4] = {fl4.x, fl4.y, fl4.z, fl4.w};
+  const int32_t rasv[4] = {ras4.x, ras4.y, ras4.z, ras4.w};
+  const int64_t fav[4] = {fa01.x, fa01.y, fa23.x, fa23.y};
 
   // The tick's broken-down time: one-hot words computed once per tick (civil.h) and
-  // delivered through the kernel parameters, i.e. the constant bank / uniform
-  // registers — cheaper than staging them in shared memory, which cost every CTA a
-  // serial thread-0 section and a barrier (profiles/r01_summary.md).
+  // delivered through the kernel parameters, i.e. the constant bank / uniform registers.
   const TickWords w = p.words;
 
-  uint32_t act[2][2];
+  uint32_t act[4];
   uint32_t res_lane = 0;  // 4 x 8-bit counts of results applied by this lane
-  uint32_t nfl[2][2];     // flags / finishedAt after this tick
-  int64_t nfa[2][2];
-  bool dirty[2] = {false, false};
-  uint32_t needy = 0, due_bits = 0;  // bit (2h+j): record needs the remedy/counter columns / is due
+  uint32_t nfl[4];        // flags / finishedAt after this tick
+  int64_t nfa[4];
+  bool dirty = false;
+  uint32_t needy = 0, due_bits = 0;  // bit j: record needs the remedy/counter columns / is due
 
-  // ---- schedule decision for the lane's four records ------------------------
+  // ---- schedule decision for the thread's four records ------------------------
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const uint32_t f = j ? fl[h].y : fl[h].x;
-      const int32_t rasv = (int32_t)(j ? ras[h].y : ras[h].x);
-      const int64_t fav = (int64_t)(j ? fa[h].y : fa[h].x);
-      const uint32_t kind = f & AM_KIND_MASK;
-      // kinds 1..5 are evaluated; tombstones, NO_RESOURCE (hcc.go:227) and host-fallback are not
-      const bool live = ((0x3Eu >> kind) & 1u) && !(f & AM_F_TOMBSTONE);
-      const bool has_result = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL)) != 0;
-      const bool pending = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING)) != 0;
-      // step 1 sets finishedAt = T before the due decision is taken
-      const int64_t fa_eff = has_result ? T : fav;
-      const int64_t elapsed = (int64_t)((uint64_t)T - (uint64_t)fa_eff);
-      const bool due_iv = !(elapsed < (int64_t)rasv);  // not(hcc.go:264) == timer :751 fired
-      bool due_cron = false;
-      if (MASKS) {
-        const uint64_t miv = j ? mi[h].y : mi[h].x, hrv = j ? hr[h].y : hr[h].x;
-        const uint64_t dmv = j ? dm[h].y : dm[h].x, mov = j ? mo[h].y : mo[h].x;
-        const uint64_t dwv = j ? dw[h].y : dw[h].x;
-        // branch-free: every term is evaluated (no short-circuit control flow)
-        const bool fld = ((miv & w.minute) != 0) & ((hrv & w.hour) != 0) & ((mov & w.month) != 0);
-        const bool dmm = (dmv & w.dom) != 0, dwm = (dwv & w.dow) != 0;
-        const bool star = ((dmv | dwv) >> 63) != 0;  // robfig dayMatches
-        due_cron = (w.sec0 != 0) & fld & (star ? (dmm & dwm) : (dmm | dwm));
-      }
-      const bool is_iv = ((0x14u >> kind) & 1u) != 0;  // INTERVAL or CRON_EVERY
-      const bool due = live && (is_iv ? due_iv : (kind == AM_KIND_CRON_SPEC && due_cron));
-      const bool stopped_now = live && kind == AM_KIND_STOPPED && !(f & AM_F_STOPPED_REPORTED);
-      act[h][j] = (due ? AM_ACT_SUBMIT_HC : 0u) | (stopped_now ? AM_ACT_STOPPED : 0u) |
-                  ((live && kind == AM_KIND_PARSE_ERROR) ? AM_ACT_PARSE_ERROR : 0u);
-      nfl[h][j] = f;
-      nfa[h][j] = fav;
-      if (stopped_now) {  // hcc.go:238-250: Status "Stopped", FinishedAt = now
-        nfl[h][j] = f | AM_F_STOPPED_REPORTED;
-        nfa[h][j] = T;
-        dirty[h] = true;
-      }
-      if (live && (pending || (CLOSED && due))) needy |= 1u << (2 * h + j);
-      if (due) due_bits |= 1u << (2 * h + j);
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t f = flv[j];
+    const uint32_t kind = f & AM_KIND_MASK;
+    // kinds 1..5 are evaluated; tombstones, NO_RESOURCE (hcc.go:227) and host-fallback are not
+    const bool live = ((0x3Eu >> kind) & 1u) && !(f & AM_F_TOMBSTONE);
+    const bool has_result = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL)) != 0;
+    const bool pending = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING)) != 0;
+    // step 1 sets finishedAt = T before the due decision is taken
+    const int64_t fa_eff = has_result ? T : fav[j];
+    const int64_t elapsed = (int64_t)((uint64_t)T - (uint64_t)fa_eff);
+    const bool due_iv = !(elapsed < (int64_t)rasv[j]);  // not(hcc.go:264) == timer :751 fired
+    bool due_cron = false;
+    if (MASKS) {
+      const uint32_t k = 4u * (uint32_t)tid + (uint32_t)j;
+      const uint64_t miv = s_mask[0 * kTile + k], hrv = s_mask[1 * kTile + k];
+      const uint64_t dmv = s_mask[2 * kTile + k], mov = s_mask[3 * kTile + k];
+      const uint64_t dwv = s_mask[4 * kTile + k];
+      // branch-free: every term is evaluated (no short-circuit control flow)
+      const bool fld = ((miv & w.minute) != 0) & ((hrv & w.hour) != 0) & ((mov & w.month) != 0);
+      const bool dmm = (dmv & w.dom) != 0, dwm = (dwv & w.dow) != 0;
+      const bool star = ((dmv | dwv) >> 63) != 0;  // robfig dayMatches
+      due_cron = (w.sec0 != 0) & fld & (star ? (dmm & dwm) : (dmm | dwm));
     }
+    const bool is_iv = ((0x14u >> kind) & 1u) != 0;  // INTERVAL or CRON_EVERY
+    const bool due = live && (is_iv ? due_iv : (kind == AM_KIND_CRON_SPEC && due_cron));
+    const bool stopped_now = live && kind == AM_KIND_STOPPED && !(f & AM_F_STOPPED_REPORTED);
+    act[j] = (due ? AM_ACT_SUBMIT_HC : 0u) | (stopped_now ? AM_ACT_STOPPED : 0u) |
+             ((live && kind == AM_KIND_PARSE_ERROR) ? AM_ACT_PARSE_ERROR : 0u);
+    nfl[j] = f;
+    nfa[j] = fav[j];
+    if (stopped_now) {  // hcc.go:238-250: Status "Stopped", FinishedAt = now
+      nfl[j] = f | AM_F_STOPPED_REPORTED;
+      nfa[j] = T;
+      dirty = true;
+    }
+    if (live && (pending || (CLOSED && due))) needy |= 1u << j;
+    if (due) due_bits |= 1u << j;
   }
 
   // ---- results + remedy state machine: a warp loop in which every lane takes its
@@ -365,14 +367,17 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
     if (needy) {
       const int b = __ffs(needy) - 1;
       needy &= needy - 1;
-      const uint32_t i = r0[0] + (uint32_t)(64 * (b >> 1) + (b & 1));
+      const uint32_t i = r0 + (uint32_t)b;
       const int32_t lim = ld_stream(p.c.runs_limit + i), rst = ld_stream(p.c.reset_interval + i);
       const int32_t sc = ld_stream(p.c.success + i), fc = ld_stream(p.c.failed + i);
       const int32_t rsc = ld_stream(p.c.remedy_success + i), rfc = ld_stream(p.c.remedy_failed + i);
       const int32_t rtc = ld_stream(p.c.remedy_total + i);
       const int64_t rfa = ld_stream(p.c.remedy_finished_at + i);
-      const uint32_t f0 = b == 0 ? nfl[0][0] : b == 1 ? nfl[0][1] : b == 2 ? nfl[1][0] : nfl[1][1];
-      const int64_t fa0 = b == 0 ? nfa[0][0] : b == 1 ? nfa[0][1] : b == 2 ? nfa[1][0] : nfa[1][1];
+      // (a record "Stopped" in this very tick already carries STOPPED_REPORTED and
+      // finishedAt = T in nfl/nfa, and apply_result preserves both: the pause rule of
+      // hcc.go:238-250 and a posted result commute)
+      const uint32_t f0 = b == 0 ? nfl[0] : b == 1 ? nfl[1] : b == 2 ? nfl[2] : nfl[3];
+      const int64_t fa0 = b == 0 ? nfa[0] : b == 1 ? nfa[1] : b == 2 ? nfa[2] : nfa[3];
       RecState s{f0, fa0, sc, fc, rsc, rfc, rtc, rfa, lim, rst};
       uint32_t res = 0;
       uint32_t a = apply_result(s, T, res);
@@ -392,39 +397,37 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
       if (s.rf != rfc) st_stream(p.c.remedy_failed + i, s.rf);
       if (s.rt != rtc) st_stream(p.c.remedy_total + i, s.rt);
       if (s.rfa != rfa) st_stream(p.c.remedy_finished_at + i, s.rfa);
-      // (a record "Stopped" in this very tick already carries STOPPED_REPORTED and
-      // finishedAt = T in nfl/nfa, and apply_result preserves both: the pause rule of
-      // hcc.go:238-250 and a posted result commute)
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (q == b) {
-          act[q >> 1][q & 1] |= a;
-          nfl[q >> 1][q & 1] = s.flags;
-          nfa[q >> 1][q & 1] = s.fa;
+          act[q] |= a;
+          nfl[q] = s.flags;
+          nfa[q] = s.fa;
         }
       }
-      if (b < 2) dirty[0] = true; else dirty[1] = true;  // a result always clears its PENDING flags
+      dirty = true;  // a result always clears its PENDING flags
     }
   }
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    if (dirty[h]) {
-      st_stream(reinterpret_cast<uint2*>(p.c.flags + r0[h]), make_uint2(nfl[h][0], nfl[h][1]));
-      st_stream(reinterpret_cast<longlong2*>(p.c.finished_at + r0[h]), make_longlong2(nfa[h][0], nfa[h][1]));
-    }
+  if (dirty) {
+    st_stream(reinterpret_cast<uint4*>(p.c.flags + r0), make_uint4(nfl[0], nfl[1], nfl[2], nfl[3]));
+    st_stream(reinterpret_cast<longlong2*>(p.c.finished_at + r0), make_longlong2(nfa[0], nfa[1]));
+    st_stream(reinterpret_cast<longlong2*>(p.c.finished_at + r0 + 2), make_longlong2(nfa[2], nfa[3]));
   }
 
-  // ---- ordered compaction: in-warp ranks from ballots ---------------------
+  // ---- ordered compaction: in-warp ranks from ballots (record order = lane, then j) ----
   const unsigned lt = (1u << lane) - 1u;
-  const unsigned b00 = __ballot_sync(kFull, act[0][0] != 0), b01 = __ballot_sync(kFull, act[0][1] != 0);
-  const unsigned b10 = __ballot_sync(kFull, act[1][0] != 0), b11 = __ballot_sync(kFull, act[1][1] != 0);
-  const uint32_t tot0 = __popc(b00) + __popc(b01);
-  const uint32_t warp_total = tot0 + __popc(b10) + __popc(b11);
-  uint32_t rank[2][2];
-  rank[0][0] = __popc(b00 & lt) + __popc(b01 & lt);
-  rank[0][1] = rank[0][0] + (act[0][0] != 0);
-  rank[1][0] = tot0 + __popc(b10 & lt) + __popc(b11 & lt);
-  rank[1][1] = rank[1][0] + (act[1][0] != 0);
+  uint32_t below = 0, warp_total = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const unsigned bj = __ballot_sync(kFull, act[j] != 0);
+    below += __popc(bj & lt);
+    warp_total += __popc(bj);
+  }
+  uint32_t rank[4];
+  rank[0] = below;
+  rank[1] = rank[0] + (act[0] != 0);
+  rank[2] = rank[1] + (act[1] != 0);
+  rank[3] = rank[2] + (act[2] != 0);
   if (lane == 0) s_warp_tot[warp] = warp_total;
 
   // ---- results applied this tick (feeds metrics.MonitorSuccess/Error): lane ->
@@ -451,14 +454,12 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
     tile_total += v;
   }
 #pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-      if (act[h][j]) {
-        const uint32_t pos = base + rank[h][j];
-        st_keep_u32(p.seg_idx + pos, r0[h] + (uint32_t)j, keep);
-        st_keep_u8(p.seg_act + pos, act[h][j], keep);
-      }
+  for (int j = 0; j < 4; ++j)
+    if (act[j]) {
+      const uint32_t pos = base + rank[j];
+      st_keep_u32(p.seg_idx + pos, r0 + (uint32_t)j, keep);
+      st_keep_u8(p.seg_act + pos, act[j], keep);
+    }
   if (warp == 0) {  // per-tile count, group counter, result counters (RED, no return value)
     if (lane < 4) {
       uint32_t sv = 0;
