@@ -266,36 +266,59 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const uint32_t tile = blockIdx.x;
-  const uint32_t tile_base = tile * (uint32_t)kTile;
   const int64_t T = p.T;
+  // The tick's broken-down time: one-hot words computed once per tick (civil.h) and
+  // delivered through the kernel parameters, i.e. the constant bank / uniform registers.
+  const TickWords w = p.words;
+  const uint64_t keep = l2_evict_last_policy();
 
-  // ---- phase A: stage the tile's schedule columns in shared memory (TMA bulk) ----
-  // layout (record order): [fa 8K][ras 4K][flags 4K] then, with MASKS,
-  // [minute 8K][hour 8K][dom 8K][month 8K][dow 8K]; thread t owns records 4t..4t+3.
-  extern __shared__ __align__(128) unsigned char stage[];
-  __shared__ __align__(8) uint64_t s_bar;
-  int64_t* s_fa = reinterpret_cast<int64_t*>(stage);
-  int32_t* s_ras = reinterpret_cast<int32_t*>(stage + kTile * 8);
-  uint32_t* s_flags = reinterpret_cast<uint32_t*>(stage + kTile * 12);
-  uint64_t* s_mask = reinterpret_cast<uint64_t*>(stage + kTile * 16);  // 5 x kTile
-  if (tid == 0) {
-    mbar_init(&s_bar, 1);
-    fence_mbar_init();
-    mbar_expect_tx(&s_bar, (uint32_t)(MASKS ? kStageBytesMasks : kStageBytesNoMasks));
-    tma_bulk_g2s(s_fa, p.c.finished_at + tile_base, kTile * 8, &s_bar);
-    tma_bulk_g2s(s_ras, p.c.ras + tile_base, kTile * 4, &s_bar);
-    tma_bulk_g2s(s_flags, p.c.flags + tile_base, kTile * 4, &s_bar);
+  // ---- phase A: a two-stage TMA pipeline over this CTA's tiles -------------------
+  // The CTA is persistent: it owns tiles blockIdx.x, blockIdx.x + gridDim.x, ...  While
+  // tile i is evaluated out of one shared-memory stage, the bulk copies of tile i+1 are
+  // already in flight into the other, so HBM stays busy through the compute, the
+  // write-out and the barriers.  Stage layout (record order): [fa 8K][ras 4K][flags 4K]
+  // then, with MASKS, [minute][hour][dom][month][dow] 8K each; thread t owns records
+  // 4t..4t+3 of the tile.
+  extern __shared__ __align__(128) unsigned char stage_mem[];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  constexpr uint32_t kStageBytes = (uint32_t)(MASKS ? kStageBytesMasks : kStageBytesNoMasks);
+  auto issue_tile = [&](uint32_t t, int st) {  // called by thread 0 only
+    unsigned char* base = stage_mem + (size_t)st * kStageBytes;
+    const uint32_t tb = t * (uint32_t)kTile;
+    mbar_expect_tx(&s_bar[st], kStageBytes);
+    tma_bulk_g2s(base, p.c.finished_at + tb, kTile * 8, &s_bar[st]);
+    tma_bulk_g2s(base + kTile * 8, p.c.ras + tb, kTile * 4, &s_bar[st]);
+    tma_bulk_g2s(base + kTile * 12, p.c.flags + tb, kTile * 4, &s_bar[st]);
     if (MASKS) {
-      tma_bulk_g2s(s_mask + 0 * kTile, p.c.minute + tile_base, kTile * 8, &s_bar);
-      tma_bulk_g2s(s_mask + 1 * kTile, p.c.hour + tile_base, kTile * 8, &s_bar);
-      tma_bulk_g2s(s_mask + 2 * kTile, p.c.dom + tile_base, kTile * 8, &s_bar);
-      tma_bulk_g2s(s_mask + 3 * kTile, p.c.month + tile_base, kTile * 8, &s_bar);
-      tma_bulk_g2s(s_mask + 4 * kTile, p.c.dow + tile_base, kTile * 8, &s_bar);
+      uint64_t* m = reinterpret_cast<uint64_t*>(base + kTile * 16);
+      tma_bulk_g2s(m + 0 * kTile, p.c.minute + tb, kTile * 8, &s_bar[st]);
+      tma_bulk_g2s(m + 1 * kTile, p.c.hour + tb, kTile * 8, &s_bar[st]);
+      tma_bulk_g2s(m + 2 * kTile, p.c.dom + tb, kTile * 8, &s_bar[st]);
+      tma_bulk_g2s(m + 3 * kTile, p.c.month + tb, kTile * 8, &s_bar[st]);
+      tma_bulk_g2s(m + 4 * kTile, p.c.dow + tb, kTile * 8, &s_bar[st]);
     }
+  };
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    fence_mbar_init();
+    if (blockIdx.x < p.n_tiles) issue_tile(blockIdx.x, 0);
   }
-  __syncthreads();  // the initialised barrier is visible to every waiter
-  mbar_wait(&s_bar, 0);
+  __syncthreads();  // the initialised barriers are visible to every waiter
+
+  uint32_t it = 0;
+  for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+  const int st = (int)(it & 1u);
+  const uint32_t tile_base = tile * (uint32_t)kTile;
+  // prefetch the next tile into the other stage (its previous readers passed the barrier
+  // that ends the previous iteration)
+  if (tid == 0 && tile + gridDim.x < p.n_tiles) issue_tile(tile + gridDim.x, st ^ 1);
+  mbar_wait(&s_bar[st], (it >> 1) & 1u);
+  const unsigned char* stage = stage_mem + (size_t)st * kStageBytes;
+  const int64_t* s_fa = reinterpret_cast<const int64_t*>(stage);
+  const int32_t* s_ras = reinterpret_cast<const int32_t*>(stage + kTile * 8);
+  const uint32_t* s_flags = reinterpret_cast<const uint32_t*>(stage + kTile * 12);
+  const uint64_t* s_mask = reinterpret_cast<const uint64_t*>(stage + kTile * 16);  // 5 x kTile
 
   const uint32_t r0 = tile_base + 4u * (uint32_t)tid;  // this thread's first record
   const uint4 fl4 = *reinterpret_cast<const uint4*>(s_flags + 4 * tid);
@@ -305,10 +328,6 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   const uint32_t flv[4] = {fl4.x, fl4.y, fl4.z, fl4.w};
   const int32_t rasv[4] = {ras4.x, ras4.y, ras4.z, ras4.w};
   const int64_t fav[4] = {fa01.x, fa01.y, fa23.x, fa23.y};
-
-  // The tick's broken-down time: one-hot words computed once per tick (civil.h) and
-  // delivered through the kernel parameters, i.e. the constant bank / uniform registers.
-  const TickWords w = p.words;
 
   uint32_t act[4];
   uint32_t res_lane = 0;  // 4 x 8-bit counts of results applied by this lane
@@ -445,7 +464,6 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   __syncthreads();
 
   // ---- in-tile base, segment write-out, per-tile count ----------------------
-  const uint64_t keep = l2_evict_last_policy();
   uint32_t base = tile_base, tile_total = 0;
 #pragma unroll
   for (int k = 0; k < kWarps; ++k) {
@@ -472,6 +490,9 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
       if (tile_total) atomicAdd(&p.group_count[tile / kGroupTiles], tile_total);
     }
   }
+  // everyone is done with this stage and with the per-warp rows before they are reused
+  __syncthreads();
+  }  // tile loop
 }
 
 // ---------------------------------------------------------------------------
