@@ -69,7 +69,6 @@ struct am_sweep {
   uint32_t* group_count[2] = {nullptr, nullptr};  // [groups], parity = tick number & 1
   unsigned long long* acc = nullptr;
   uint32_t parity = 0;
-  uint32_t sweep_grid[4] = {148, 148, 148, 148};  // persistent grid per kernel variant {closed, masks}
   uint32_t* due_idx[2] = {nullptr, nullptr};
   uint8_t* due_action[2] = {nullptr, nullptr};
   am_tick_stats_t* h_stats = nullptr;  // pinned + mapped
@@ -220,14 +219,10 @@ int launch_sweep(am_sweep* h, int64_t T, uint32_t mode, uint32_t* d_idx, uint8_t
   if (sec_of_min < 0) sec_of_min += 60;
   const bool masks = sec_of_min == 0 || (mode & AM_SWEEP_FULL_SCAN);
   const bool closed = (mode & AM_SWEEP_CLOSED_LOOP) != 0;
-  // persistent grid: every resident CTA loops over its tiles with two shared-memory stages
-  const size_t smem = 2 * (masks ? kStageBytesMasks : kStageBytesNoMasks);
-  const int v = (closed ? 2 : 0) + (masks ? 1 : 0);
-  const uint32_t grid = p.n_tiles < h->sweep_grid[v] ? p.n_tiles : h->sweep_grid[v];
-  if (closed && masks) sweep_tick_kernel<true, true><<<grid, kBlock, smem, s>>>(p);
-  else if (closed) sweep_tick_kernel<true, false><<<grid, kBlock, smem, s>>>(p);
-  else if (masks) sweep_tick_kernel<false, true><<<grid, kBlock, smem, s>>>(p);
-  else sweep_tick_kernel<false, false><<<grid, kBlock, smem, s>>>(p);
+  if (closed && masks) sweep_tick_kernel<true, true><<<p.n_tiles, kBlock, 0, s>>>(p);
+  else if (closed) sweep_tick_kernel<true, false><<<p.n_tiles, kBlock, 0, s>>>(p);
+  else if (masks) sweep_tick_kernel<false, true><<<p.n_tiles, kBlock, 0, s>>>(p);
+  else sweep_tick_kernel<false, false><<<p.n_tiles, kBlock, 0, s>>>(p);
   if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[1], s));
   CompactParams c{};
   c.seg_idx = h->seg_idx;
@@ -277,22 +272,6 @@ int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t
   h->cap_padded = (capacity + kTile - 1) / kTile * kTile;
   h->shard_base = shard_base;
   int rc = [&]() -> int {
-    // two staging buffers (2 x 56 KB with masks) need the opt-in attribute; the persistent
-    // grid is sized to the CTAs that fit on the device at once
-    {
-      int sms = 0;
-      AM_CUDA(h, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device_id));
-      const void* fn[4] = {(const void*)sweep_tick_kernel<false, false>, (const void*)sweep_tick_kernel<false, true>,
-                           (const void*)sweep_tick_kernel<true, false>, (const void*)sweep_tick_kernel<true, true>};
-      for (int v = 0; v < 4; ++v) {
-        const size_t smem = 2 * ((v & 1) ? kStageBytesMasks : kStageBytesNoMasks);
-        AM_CUDA(h, cudaFuncSetAttribute(fn[v], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        AM_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn[v], kBlock, smem));
-        if (per_sm < 1) per_sm = 1;
-        h->sweep_grid[v] = (uint32_t)(per_sm * sms);
-      }
-    }
     AM_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     AM_CUDA(h, cudaEventCreate(&h->ev0));
     AM_CUDA(h, cudaEventCreate(&h->ev1));

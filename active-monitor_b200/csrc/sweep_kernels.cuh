@@ -14,11 +14,11 @@
 //
 // Shape of the kernel (pure integer work, HBM-bandwidth bound, no tensor cores):
 //   * records live as SoA columns in HBM; a CTA of 256 threads owns one tile of
-//     1024 consecutive records, a warp owns 128 consecutive ones;
-//   * the tile's schedule columns are staged in shared memory by TMA bulk copies
-//     (cp.async.bulk + mbarrier): one elected thread issues one 4-8 KB copy per
-//     column, 56 KB in flight per CTA independent of register allocation, no
-//     per-lane load instructions; thread t then owns records 4t..4t+3;
+//     1024 consecutive records, a warp owns 128 of them;
+//   * every warp-level load instruction is fully coalesced: lane L reads the
+//     16 B (two u64 records) or 8 B (two i32 records) at column + (w + 2L),
+//     twice per tile ("halves"), so 16 independent loads are in flight per
+//     lane before the first use;
 //   * the tick's broken-down time is computed once per tick as one-hot words
 //     and reaches every CTA through the kernel parameters (constant bank); a
 //     5-field schedule fires iff minute&M && hour&H && month&Mo && dayMatches
@@ -50,13 +50,10 @@ namespace amsweep {
 #endif
 constexpr int kBlock = AM_BLOCK;
 constexpr int kWarps = kBlock / 32;
-constexpr int kRecPerWarp = 128;             // 32 lanes x 4 consecutive records
+constexpr int kRecPerWarp = 128;             // 2 halves x 32 lanes x 2 records
 constexpr int kTile = kWarps * kRecPerWarp;  // 1024 records per CTA
 constexpr unsigned kFull = 0xFFFFFFFFu;
 constexpr int kNumAcc = 16;  // == number of u64 fields of am_tick_stats_t
-// phase-A staging per CTA (one tile in record order): finishedAt + ras + flags [+ 5 masks]
-constexpr size_t kStageBytesNoMasks = (size_t)kTile * (8 + 4 + 4);           // 16 KB
-constexpr size_t kStageBytesMasks = kStageBytesNoMasks + (size_t)kTile * 40;  // 56 KB
 
 struct DevCols {
   uint64_t *minute, *hour, *dom, *month, *dow;
@@ -102,46 +99,6 @@ struct CompactParams {
 // ---- streaming loads / stores: every byte is touched once per tick --------
 template <typename T>
 __device__ __forceinline__ T ld_stream(const T* p) { return __ldcs(p); }
-
-// Phase-A staging: TMA bulk copies (cp.async.bulk, SASS UBLKCP) global -> shared,
-// completion counted in bytes on an mbarrier.  One elected thread issues one copy per
-// column (4-8 KB each) for the whole tile; no lane executes a load for phase A, the
-// memory-level parallelism (56 KB per CTA) does not depend on register allocation, and
-// the data sits in shared memory in record order.  Measured alternatives: register
-// loads were split into two batches by ptxas and once even sunk into the match
-// branches (-45 % bandwidth); per-lane cp.async (LDGSTS) cost 16 copy + 16 read
-// instructions per lane (profiles/r01_summary.md).
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_mbar_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
-      "r"(phase)
-      : "memory");
-}
-
 template <typename T>
 __device__ __forceinline__ void st_stream(T* p, T v) { __stcs(p, v); }
 
@@ -259,144 +216,181 @@ __device__ __forceinline__ uint32_t apply_result(RecState& r, int64_t T, uint32_
 // bytes per record and all of the mask arithmetic disappear at compile time.
 template <bool CLOSED, bool MASKS>
 __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS + 1) sweep_tick_kernel(const SweepParams p) {
-  // one row per warp, written unconditionally: no zero-initialisation, no shared atomics
+  // one row per warp, written unconditionally: no zero-initialisation, no shared
+  // atomics, and therefore a single __syncthreads in the whole kernel
   __shared__ uint32_t s_warp_tot[kWarps];
   __shared__ uint32_t s_wres[kWarps][4];  // posted results applied: ok, fail, remedy ok, remedy fail
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int warp = tid >> 5;
-  const int64_t T = p.T;
-  // The tick's broken-down time: one-hot words computed once per tick (civil.h) and
-  // delivered through the kernel parameters, i.e. the constant bank / uniform registers.
-  const TickWords w = p.words;
-  const uint64_t keep = l2_evict_last_policy();
-
-  // ---- phase A: a two-stage TMA pipeline over this CTA's tiles -------------------
-  // The CTA is persistent: it owns tiles blockIdx.x, blockIdx.x + gridDim.x, ...  While
-  // tile i is evaluated out of one shared-memory stage, the bulk copies of tile i+1 are
-  // already in flight into the other, so HBM stays busy through the compute, the
-  // write-out and the barriers.  Stage layout (record order): [fa 8K][ras 4K][flags 4K]
-  // then, with MASKS, [minute][hour][dom][month][dow] 8K each; thread t owns records
-  // 4t..4t+3 of the tile.
-  extern __shared__ __align__(128) unsigned char stage_mem[];
-  __shared__ __align__(8) uint64_t s_bar[2];
-  constexpr uint32_t kStageBytes = (uint32_t)(MASKS ? kStageBytesMasks : kStageBytesNoMasks);
-  auto issue_tile = [&](uint32_t t, int st) {  // called by thread 0 only
-    unsigned char* base = stage_mem + (size_t)st * kStageBytes;
-    const uint32_t tb = t * (uint32_t)kTile;
-    mbar_expect_tx(&s_bar[st], kStageBytes);
-    tma_bulk_g2s(base, p.c.finished_at + tb, kTile * 8, &s_bar[st]);
-    tma_bulk_g2s(base + kTile * 8, p.c.ras + tb, kTile * 4, &s_bar[st]);
-    tma_bulk_g2s(base + kTile * 12, p.c.flags + tb, kTile * 4, &s_bar[st]);
-    if (MASKS) {
-      uint64_t* m = reinterpret_cast<uint64_t*>(base + kTile * 16);
-      tma_bulk_g2s(m + 0 * kTile, p.c.minute + tb, kTile * 8, &s_bar[st]);
-      tma_bulk_g2s(m + 1 * kTile, p.c.hour + tb, kTile * 8, &s_bar[st]);
-      tma_bulk_g2s(m + 2 * kTile, p.c.dom + tb, kTile * 8, &s_bar[st]);
-      tma_bulk_g2s(m + 3 * kTile, p.c.month + tb, kTile * 8, &s_bar[st]);
-      tma_bulk_g2s(m + 4 * kTile, p.c.dow + tb, kTile * 8, &s_bar[st]);
-    }
-  };
-  if (tid == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
-    fence_mbar_init();
-    if (blockIdx.x < p.n_tiles) issue_tile(blockIdx.x, 0);
-  }
-  __syncthreads();  // the initialised barriers are visible to every waiter
-
-  uint32_t it = 0;
-  for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
-  const int st = (int)(it & 1u);
+  const uint32_t tile = blockIdx.x;
   const uint32_t tile_base = tile * (uint32_t)kTile;
-  // prefetch the next tile into the other stage (its previous readers passed the barrier
-  // that ends the previous iteration)
-  if (tid == 0 && tile + gridDim.x < p.n_tiles) issue_tile(tile + gridDim.x, st ^ 1);
-  mbar_wait(&s_bar[st], (it >> 1) & 1u);
-  const unsigned char* stage = stage_mem + (size_t)st * kStageBytes;
-  const int64_t* s_fa = reinterpret_cast<const int64_t*>(stage);
-  const int32_t* s_ras = reinterpret_cast<const int32_t*>(stage + kTile * 8);
-  const uint32_t* s_flags = reinterpret_cast<const uint32_t*>(stage + kTile * 12);
-  const uint64_t* s_mask = reinterpret_cast<const uint64_t*>(stage + kTile * 16);  // 5 x kTile
+  const int64_t T = p.T;
 
-  const uint32_t r0 = tile_base + 4u * (uint32_t)tid;  // this thread's first record
-  const uint4 fl4 = *reinterpret_cast<const uint4*>(s_flags + 4 * tid);
-  const int4 ras4 = *reinterpret_cast<const int4*>(s_ras + 4 * tid);
-  const longlong2 fa01 = *reinterpret_cast<const longlong2*>(s_fa + 4 * tid);
-  const longlong2 fa23 = *reinterpret_cast<const longlong2*>(s_fa + 4 * tid + 2);
-  const uint32_t flv[4] = {fl4.x, fl4.y, fl4.z, fl4.w};
-  const int32_t rasv[4] = {ras4.x, ras4.y, ras4.z, ras4.w};
-  const int64_t fav[4] = {fa01.x, fa01.y, fa23.x, fa23.y};
-
-  uint32_t act[4];
-  uint32_t res_lane = 0;  // 4 x 8-bit counts of results applied by this lane
-  uint32_t nfl[4];        // flags / finishedAt after this tick
-  int64_t nfa[4];
-  bool dirty = false;
-  uint32_t needy = 0, due_bits = 0;  // bit j: record needs the remedy/counter columns / is due
-
-  // ---- schedule decision for the thread's four records ------------------------
+  // ---- phase A: issue every schedule-column load of this lane up front ----
+  // half h covers records r0(h) .. r0(h)+1, r0 = tile_base + warp*128 + h*64 + lane*2
+  uint32_t r0[2];
+  ulonglong2 mi[2], hr[2], dm[2], mo[2], dw[2];
+  longlong2 fa[2];
+  int2 ras[2];
+  uint2 fl[2];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const uint32_t f = flv[j];
-    const uint32_t kind = f & AM_KIND_MASK;
-    // kinds 1..5 are evaluated; tombstones, NO_RESOURCE (hcc.go:227) and host-fallback are not
-    const bool live = ((0x3Eu >> kind) & 1u) && !(f & AM_F_TOMBSTONE);
-    const bool has_result = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL)) != 0;
-    const bool pending = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING)) != 0;
-    // step 1 sets finishedAt = T before the due decision is taken
-    const int64_t fa_eff = has_result ? T : fav[j];
-    const int64_t elapsed = (int64_t)((uint64_t)T - (uint64_t)fa_eff);
-    const bool due_iv = !(elapsed < (int64_t)rasv[j]);  // not(hcc.go:264) == timer :751 fired
-    bool due_cron = false;
-    if (MASKS) {
-      const uint32_t k = 4u * (uint32_t)tid + (uint32_t)j;
-      const uint64_t miv = s_mask[0 * kTile + k], hrv = s_mask[1 * kTile + k];
-      const uint64_t dmv = s_mask[2 * kTile + k], mov = s_mask[3 * kTile + k];
-      const uint64_t dwv = s_mask[4 * kTile + k];
-      // branch-free: every term is evaluated (no short-circuit control flow)
-      const bool fld = ((miv & w.minute) != 0) & ((hrv & w.hour) != 0) & ((mov & w.month) != 0);
-      const bool dmm = (dmv & w.dom) != 0, dwm = (dwv & w.dow) != 0;
-      const bool star = ((dmv | dwv) >> 63) != 0;  // robfig dayMatches
-      due_cron = (w.sec0 != 0) & fld & (star ? (dmm & dwm) : (dmm | dwm));
+  for (int h = 0; h < 2; ++h) {
+    r0[h] = tile_base + (uint32_t)(warp * kRecPerWarp + h * 64 + lane * 2);
+    fl[h] = ld_stream(reinterpret_cast<const uint2*>(p.c.flags + r0[h]));
+    ras[h] = ld_stream(reinterpret_cast<const int2*>(p.c.ras + r0[h]));
+    fa[h] = ld_stream(reinterpret_cast<const longlong2*>(p.c.finished_at + r0[h]));
+  }
+  if (MASKS) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      mi[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.minute + r0[h]));
+      hr[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.hour + r0[h]));
+      dm[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.dom + r0[h]));
+      mo[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.month + r0[h]));
+      dw[h] = ld_stream(reinterpret_cast<const ulonglong2*>(p.c.dow + r0[h]));
     }
-    const bool is_iv = ((0x14u >> kind) & 1u) != 0;  // INTERVAL or CRON_EVERY
-    const bool due = live && (is_iv ? due_iv : (kind == AM_KIND_CRON_SPEC && due_cron));
-    const bool stopped_now = live && kind == AM_KIND_STOPPED && !(f & AM_F_STOPPED_REPORTED);
-    act[j] = (due ? AM_ACT_SUBMIT_HC : 0u) | (stopped_now ? AM_ACT_STOPPED : 0u) |
-             ((live && kind == AM_KIND_PARSE_ERROR) ? AM_ACT_PARSE_ERROR : 0u);
-    nfl[j] = f;
-    nfa[j] = fav[j];
-    if (stopped_now) {  // hcc.go:238-250: Status "Stopped", FinishedAt = now
-      nfl[j] = f | AM_F_STOPPED_REPORTED;
-      nfa[j] = T;
-      dirty = true;
-    }
-    if (live && (pending || (CLOSED && due))) needy |= 1u << j;
-    if (due) due_bits |= 1u << j;
   }
 
-  // ---- results + remedy state machine: a warp loop in which every lane takes its
-  //      next needy record.  With few posted results / due records per warp the loop
-  //      runs once or twice instead of four predicated copies of the state machine;
-  //      the remedy/counter columns are read and written per record (the 36 B/record
-  //      are only touched for records that need them).
+  // Scheduling fence: a warp-level memory-ordering point.  ptxas may not sink the loads
+  // above across it, so all 16 are issued before any of the arithmetic below (without it
+  // the second half's loads were delayed behind the first half's compute: -30 % bandwidth).
+  __syncwarp();
+
+  // The tick's broken-down time: one-hot words computed once per tick (civil.h) and
+  // delivered through the kernel parameters, i.e. the constant bank / uniform
+  // registers — cheaper than staging them in shared memory, which cost every CTA a
+  // serial thread-0 section and a barrier (profiles/r01_summary.md).
+  const TickWords w = p.words;
+
+  uint32_t act[2][2];
+  uint32_t res_lane = 0;  // 4 x 8-bit counts of results applied by this lane
+  uint32_t nfl[2][2];     // flags / finishedAt after this tick
+  int64_t nfa[2][2];
+  bool dirty[2] = {false, false};
+  uint32_t needy = 0, due_bits = 0;  // bit (2h+j): record needs the remedy/counter columns / is due
+
+  // ---- schedule decision for the lane's four records ------------------------
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t f = j ? fl[h].y : fl[h].x;
+      const int32_t rasv = j ? ras[h].y : ras[h].x;
+      const int64_t fav = j ? fa[h].y : fa[h].x;
+      const uint32_t kind = f & AM_KIND_MASK;
+      // kinds 1..5 are evaluated; tombstones, NO_RESOURCE (hcc.go:227) and host-fallback are not
+      const bool live = ((0x3Eu >> kind) & 1u) && !(f & AM_F_TOMBSTONE);
+      const bool has_result = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL)) != 0;
+      const bool pending = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING)) != 0;
+      // step 1 sets finishedAt = T before the due decision is taken
+      const int64_t fa_eff = has_result ? T : fav;
+      const int64_t elapsed = (int64_t)((uint64_t)T - (uint64_t)fa_eff);
+      const bool due_iv = !(elapsed < (int64_t)rasv);  // not(hcc.go:264) == timer :751 fired
+      bool due_cron = false;
+      if (MASKS) {
+        const uint64_t miv = j ? mi[h].y : mi[h].x, hrv = j ? hr[h].y : hr[h].x;
+        const uint64_t dmv = j ? dm[h].y : dm[h].x, mov = j ? mo[h].y : mo[h].x;
+        const uint64_t dwv = j ? dw[h].y : dw[h].x;
+        // branch-free: every term is evaluated (no short-circuit control flow)
+        const bool fld = ((miv & w.minute) != 0) & ((hrv & w.hour) != 0) & ((mov & w.month) != 0);
+        const bool dmm = (dmv & w.dom) != 0, dwm = (dwv & w.dow) != 0;
+        const bool star = ((dmv | dwv) >> 63) != 0;  // robfig dayMatches
+        due_cron = (w.sec0 != 0) & fld & (star ? (dmm & dwm) : (dmm | dwm));
+      }
+      const bool is_iv = ((0x14u >> kind) & 1u) != 0;  // INTERVAL or CRON_EVERY
+      const bool due = live && (is_iv ? due_iv : (kind == AM_KIND_CRON_SPEC && due_cron));
+      const bool stopped_now = live && kind == AM_KIND_STOPPED && !(f & AM_F_STOPPED_REPORTED);
+      act[h][j] = (due ? AM_ACT_SUBMIT_HC : 0u) | (stopped_now ? AM_ACT_STOPPED : 0u) |
+                  ((live && kind == AM_KIND_PARSE_ERROR) ? AM_ACT_PARSE_ERROR : 0u);
+      nfl[h][j] = f;
+      nfa[h][j] = fav;
+      if (stopped_now) {  // hcc.go:238-250: Status "Stopped", FinishedAt = now
+        nfl[h][j] = f | AM_F_STOPPED_REPORTED;
+        nfa[h][j] = T;
+        dirty[h] = true;
+      }
+      if (live && (pending || (CLOSED && due))) needy |= 1u << (2 * h + j);
+      if (due) due_bits |= 1u << (2 * h + j);
+    }
+  }
+
+  // ---- results + remedy state machine (hcc.go:633-724, 819-852) -------------------
+  // Two shapes, chosen per warp by how many lanes have work:
+  //  dense  (>= 16 lanes, e.g. half of all checks reporting a result this tick): per
+  //         pair of records, vector loads of the eight remedy/counter columns and the
+  //         state machine predicated per record — the bytes are needed anyway and 16-B
+  //         transactions keep the LSU count low;
+  //  sparse (a few due/posted records per warp): a warp loop in which every lane takes
+  //         its next needy record with scalar accesses — the loop runs once or twice
+  //         instead of four predicated copies of the state machine.
+  if (__popc(__ballot_sync(kFull, needy != 0)) >= 16) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t nb = (needy >> (2 * h)) & 3u;
+      if (nb) {
+        const uint32_t r = r0[h];
+        const int2 lim = ld_stream(reinterpret_cast<const int2*>(p.c.runs_limit + r));
+        const int2 rst = ld_stream(reinterpret_cast<const int2*>(p.c.reset_interval + r));
+        const int2 sc = ld_stream(reinterpret_cast<const int2*>(p.c.success + r));
+        const int2 fc = ld_stream(reinterpret_cast<const int2*>(p.c.failed + r));
+        const int2 rsc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_success + r));
+        const int2 rfc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_failed + r));
+        const int2 rtc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_total + r));
+        const longlong2 rfa = ld_stream(reinterpret_cast<const longlong2*>(p.c.remedy_finished_at + r));
+        int32_t ns[2] = {sc.x, sc.y}, nf[2] = {fc.x, fc.y};
+        int32_t nrs[2] = {rsc.x, rsc.y}, nrf[2] = {rfc.x, rfc.y}, nrt[2] = {rtc.x, rtc.y};
+        int64_t nrfa[2] = {rfa.x, rfa.y};
+        const int32_t limv[2] = {lim.x, lim.y}, rstv[2] = {rst.x, rst.y};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          if ((nb >> j) & 1u) {
+            RecState s{nfl[h][j], nfa[h][j], ns[j], nf[j], nrs[j], nrf[j], nrt[j], nrfa[j], limv[j], rstv[j]};
+            uint32_t res = 0;
+            uint32_t a = apply_result(s, T, res);
+            if (CLOSED && ((due_bits >> (2 * h + j)) & 1u)) {
+              const uint64_t k = outcome_key(p.seed, p.shard_base + r + (uint32_t)j, (uint64_t)T);
+              const uint32_t failp = (s.flags >> AM_F_FAILP_SHIFT) & 0xFFu;
+              const bool fail = (uint32_t)(k & 0xFF) < failp;
+              const bool rem_ok = (uint32_t)((k >> 8) & 0xFF) < 179u;
+              s.flags |= (fail ? AM_F_PENDING_FAIL : AM_F_PENDING_OK) | AM_F_REMEDY_PENDING |
+                         (rem_ok ? AM_F_REMEDY_OUTCOME_OK : 0u);
+              a |= apply_result(s, T, res);
+            }
+            act[h][j] |= a;
+            res_lane += res;
+            nfl[h][j] = s.flags; nfa[h][j] = s.fa;
+            ns[j] = s.s; nf[j] = s.f; nrs[j] = s.rs; nrf[j] = s.rf; nrt[j] = s.rt; nrfa[j] = s.rfa;
+          }
+        }
+        dirty[h] = true;  // a result always clears its PENDING flags
+        if (ns[0] != sc.x || ns[1] != sc.y) st_stream(reinterpret_cast<int2*>(p.c.success + r), make_int2(ns[0], ns[1]));
+        if (nf[0] != fc.x || nf[1] != fc.y) st_stream(reinterpret_cast<int2*>(p.c.failed + r), make_int2(nf[0], nf[1]));
+        if (nrs[0] != rsc.x || nrs[1] != rsc.y)
+          st_stream(reinterpret_cast<int2*>(p.c.remedy_success + r), make_int2(nrs[0], nrs[1]));
+        if (nrf[0] != rfc.x || nrf[1] != rfc.y)
+          st_stream(reinterpret_cast<int2*>(p.c.remedy_failed + r), make_int2(nrf[0], nrf[1]));
+        if (nrt[0] != rtc.x || nrt[1] != rtc.y)
+          st_stream(reinterpret_cast<int2*>(p.c.remedy_total + r), make_int2(nrt[0], nrt[1]));
+        if (nrfa[0] != rfa.x || nrfa[1] != rfa.y)
+          st_stream(reinterpret_cast<longlong2*>(p.c.remedy_finished_at + r), make_longlong2(nrfa[0], nrfa[1]));
+      }
+    }
+    needy = 0;
+  }
   while (__any_sync(kFull, needy != 0)) {
     if (needy) {
       const int b = __ffs(needy) - 1;
       needy &= needy - 1;
-      const uint32_t i = r0 + (uint32_t)b;
+      const uint32_t i = r0[0] + (uint32_t)(64 * (b >> 1) + (b & 1));
       const int32_t lim = ld_stream(p.c.runs_limit + i), rst = ld_stream(p.c.reset_interval + i);
       const int32_t sc = ld_stream(p.c.success + i), fc = ld_stream(p.c.failed + i);
       const int32_t rsc = ld_stream(p.c.remedy_success + i), rfc = ld_stream(p.c.remedy_failed + i);
       const int32_t rtc = ld_stream(p.c.remedy_total + i);
       const int64_t rfa = ld_stream(p.c.remedy_finished_at + i);
-      // (a record "Stopped" in this very tick already carries STOPPED_REPORTED and
-      // finishedAt = T in nfl/nfa, and apply_result preserves both: the pause rule of
-      // hcc.go:238-250 and a posted result commute)
-      const uint32_t f0 = b == 0 ? nfl[0] : b == 1 ? nfl[1] : b == 2 ? nfl[2] : nfl[3];
-      const int64_t fa0 = b == 0 ? nfa[0] : b == 1 ? nfa[1] : b == 2 ? nfa[2] : nfa[3];
+      const uint32_t f0 = b == 0 ? nfl[0][0] : b == 1 ? nfl[0][1] : b == 2 ? nfl[1][0] : nfl[1][1];
+      const int64_t fa0 = b == 0 ? nfa[0][0] : b == 1 ? nfa[0][1] : b == 2 ? nfa[1][0] : nfa[1][1];
       RecState s{f0, fa0, sc, fc, rsc, rfc, rtc, rfa, lim, rst};
       uint32_t res = 0;
       uint32_t a = apply_result(s, T, res);
@@ -416,37 +410,39 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
       if (s.rf != rfc) st_stream(p.c.remedy_failed + i, s.rf);
       if (s.rt != rtc) st_stream(p.c.remedy_total + i, s.rt);
       if (s.rfa != rfa) st_stream(p.c.remedy_finished_at + i, s.rfa);
+      // (a record "Stopped" in this very tick already carries STOPPED_REPORTED and
+      // finishedAt = T in nfl/nfa, and apply_result preserves both: the pause rule of
+      // hcc.go:238-250 and a posted result commute)
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         if (q == b) {
-          act[q] |= a;
-          nfl[q] = s.flags;
-          nfa[q] = s.fa;
+          act[q >> 1][q & 1] |= a;
+          nfl[q >> 1][q & 1] = s.flags;
+          nfa[q >> 1][q & 1] = s.fa;
         }
       }
-      dirty = true;  // a result always clears its PENDING flags
+      if (b < 2) dirty[0] = true; else dirty[1] = true;  // a result always clears its PENDING flags
     }
   }
-  if (dirty) {
-    st_stream(reinterpret_cast<uint4*>(p.c.flags + r0), make_uint4(nfl[0], nfl[1], nfl[2], nfl[3]));
-    st_stream(reinterpret_cast<longlong2*>(p.c.finished_at + r0), make_longlong2(nfa[0], nfa[1]));
-    st_stream(reinterpret_cast<longlong2*>(p.c.finished_at + r0 + 2), make_longlong2(nfa[2], nfa[3]));
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (dirty[h]) {
+      st_stream(reinterpret_cast<uint2*>(p.c.flags + r0[h]), make_uint2(nfl[h][0], nfl[h][1]));
+      st_stream(reinterpret_cast<longlong2*>(p.c.finished_at + r0[h]), make_longlong2(nfa[h][0], nfa[h][1]));
+    }
   }
 
-  // ---- ordered compaction: in-warp ranks from ballots (record order = lane, then j) ----
+  // ---- ordered compaction: in-warp ranks from ballots ---------------------
   const unsigned lt = (1u << lane) - 1u;
-  uint32_t below = 0, warp_total = 0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const unsigned bj = __ballot_sync(kFull, act[j] != 0);
-    below += __popc(bj & lt);
-    warp_total += __popc(bj);
-  }
-  uint32_t rank[4];
-  rank[0] = below;
-  rank[1] = rank[0] + (act[0] != 0);
-  rank[2] = rank[1] + (act[1] != 0);
-  rank[3] = rank[2] + (act[2] != 0);
+  const unsigned b00 = __ballot_sync(kFull, act[0][0] != 0), b01 = __ballot_sync(kFull, act[0][1] != 0);
+  const unsigned b10 = __ballot_sync(kFull, act[1][0] != 0), b11 = __ballot_sync(kFull, act[1][1] != 0);
+  const uint32_t tot0 = __popc(b00) + __popc(b01);
+  const uint32_t warp_total = tot0 + __popc(b10) + __popc(b11);
+  uint32_t rank[2][2];
+  rank[0][0] = __popc(b00 & lt) + __popc(b01 & lt);
+  rank[0][1] = rank[0][0] + (act[0][0] != 0);
+  rank[1][0] = tot0 + __popc(b10 & lt) + __popc(b11 & lt);
+  rank[1][1] = rank[1][0] + (act[1][0] != 0);
   if (lane == 0) s_warp_tot[warp] = warp_total;
 
   // ---- results applied this tick (feeds metrics.MonitorSuccess/Error): lane ->
@@ -464,6 +460,7 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   __syncthreads();
 
   // ---- in-tile base, segment write-out, per-tile count ----------------------
+  const uint64_t keep = l2_evict_last_policy();
   uint32_t base = tile_base, tile_total = 0;
 #pragma unroll
   for (int k = 0; k < kWarps; ++k) {
@@ -472,12 +469,14 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
     tile_total += v;
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (act[j]) {
-      const uint32_t pos = base + rank[j];
-      st_keep_u32(p.seg_idx + pos, r0 + (uint32_t)j, keep);
-      st_keep_u8(p.seg_act + pos, act[j], keep);
-    }
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (act[h][j]) {
+        const uint32_t pos = base + rank[h][j];
+        st_keep_u32(p.seg_idx + pos, r0[h] + (uint32_t)j, keep);
+        st_keep_u8(p.seg_act + pos, act[h][j], keep);
+      }
   if (warp == 0) {  // per-tile count, group counter, result counters (RED, no return value)
     if (lane < 4) {
       uint32_t sv = 0;
@@ -490,9 +489,6 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
       if (tile_total) atomicAdd(&p.group_count[tile / kGroupTiles], tile_total);
     }
   }
-  // everyone is done with this stage and with the per-warp rows before they are reused
-  __syncthreads();
-  }  // tile loop
 }
 
 // ---------------------------------------------------------------------------
