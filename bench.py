@@ -42,6 +42,11 @@ CONFIG, SEED = 2, 2
 B_READ = 56          # algorithmic bytes read per evaluation, schedule-only
 B_EMIT = 5           # u32 index + u8 action per emitted record (this layout)
 B_STOP = 12          # flags + finishedAt written when "Stopped" is first reported
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE sweep_tick_kernel launch on this exact
+# workload (10 M records, config 2, tick T0), from the `ncu --set full` capture summarised in
+# profiles/r01_sweep_config2_ncu_full.csv (560.36 MB read + 3.86 MB written; part of the
+# 16.7 MB of segment writes is still dirty in L2 when the kernel ends)
+NCU_TRAFFIC_BYTES_10M_CONFIG2 = 564_213_760
 
 
 def measured_peaks():
@@ -382,7 +387,10 @@ def main():
                                                   if peer is not None else ", padded NCCL all-gather of due lists")),
                        "due_per_tick": stats["n_submit_hc"], "emitted_per_tick": stats["n_emitted"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         "traffic": NCU_TRAFFIC_BYTES_10M_CONFIG2 if n == N_PER_GPU else None,
+                         "traffic_source": "profiles/r01_sweep_config2_ncu_full.csv (ncu --set full, one launch)",
+                         "peak_source": peak_src,
                          "kernel": "sweep_tick_kernel<false>", "kernel_ms": k_ms,
                          "algorithmic_bytes": alg_bytes,
                          "bytes_model": f"N*{B_READ} + emitted*{B_EMIT} + stopped*{B_STOP}",
