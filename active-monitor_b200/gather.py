@@ -75,19 +75,30 @@ class PeerGather:
         self.device = torch.device("cuda", device_index)
         h = C.c_void_p()
         self.idx_bytes = idx_bytes
-        rc = self._lib.am_gather_create(C.byref(h), device_index, self.rank, self.world, cap_total,
-                                        idx_bytes)
-        if rc != 0:
-            raise RuntimeError(f"am_gather_create failed: {rc}")
-        self._h = h
+        self._h = None
+
+        def agree(ok: bool, what: str):
+            """every rank learns whether the step worked everywhere (no rank is left
+            waiting in a collective when another one failed)"""
+            if self.world > 1:
+                flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+                ok = bool(flag.item())
+            if not ok:
+                self.close()
+                raise RuntimeError(f"PeerGather: {what} failed on at least one rank")
+
+        rc = self._lib.am_gather_create(C.byref(h), device_index, self.rank, self.world, cap_total, idx_bytes)
         mine = C.create_string_buffer(L.IPC_HANDLE_BYTES)
-        self._check(self._lib.am_gather_export(self._h, mine), "am_gather_export")
+        if rc == 0:
+            self._h = h
+            rc = self._lib.am_gather_export(self._h, mine)
+        agree(rc == 0, "am_gather_create/export")
         if self.world > 1:
             handles = [None] * self.world
             dist.all_gather_object(handles, bytes(mine.raw), group=group)
-            blob = b"".join(handles)
-            self._check(self._lib.am_gather_connect(self._h, blob), "am_gather_connect")
-            dist.barrier(group)
+            rc = self._lib.am_gather_connect(self._h, b"".join(handles))
+            agree(rc == 0, "am_gather_connect (CUDA IPC peer mapping)")
 
     def _check(self, rc, where):
         if rc != 0:

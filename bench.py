@@ -207,9 +207,22 @@ def main():
     torch.cuda.set_stream(stream)
     peer = gstream = None
     if world > 1 and args.gather == "peer":
-        # global indices fit u32 here (records_total < 2^32): 5 B per entry on the wire
-        peer = gather.PeerGather(local_rank, cap_total=n * world,
-                                 idx_bytes=4 if n * world < (1 << 32) else 8)
+        # global indices fit u32 here (records_total < 2^32): 5 B per entry on the wire.
+        # All ranks must take the same path: agree on whether CUDA-IPC peer mapping worked.
+        ok = 1
+        try:
+            peer = gather.PeerGather(local_rank, cap_total=n * world,
+                                     idx_bytes=4 if n * world < (1 << 32) else 8)
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] rank {rank}: peer-write gather unavailable ({e}); using NCCL", file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if peer is not None:
+                peer.close()
+            peer = None
+    if peer is not None:
         gstream = torch.cuda.Stream(device=dev, priority=-1)  # exchange CTAs are placed ahead of pending sweep CTAs
         ev_sweep = [torch.cuda.Event() for _ in range(2)]
         ev_gather = [torch.cuda.Event() for _ in range(2)]

@@ -379,3 +379,31 @@ def test_repeat_after_sec_on_device_equals_oracle(am, orc, gen):
         rc, r = am.classify(cron="0 0 30 2 *")
         s.upsert([5], r)
         assert s.repeat_after_sec(T0, 5, 1)[0] == -9223372035
+
+
+def test_snapshot_restore_resumes_bit_exactly(am, orc, gen):
+    """Checkpoint/resume (SURVEY section 5: the CR status in etcd is the reference's checkpoint;
+    here: am_sweep_read of every column -> am_sweep_load_range into a fresh handle).  A day
+    fragment run in two halves with a destroy/create in between equals the uninterrupted run."""
+    n, seed = 40_000, 5
+    prod, orac = _gen_pair(gen, am, orc, 55, seed, n, T0)
+    with am.Sweep(capacity=n) as s:
+        s.load_range(0, prod)
+        s.set_seed(seed)
+        for k in range(70):
+            s.tick(T0 - 10 + k, mode=am.SWEEP_CLOSED_LOOP)
+        snap = s.read_range(0, n)                      # checkpoint
+    with am.Sweep(capacity=n) as s2:                   # "restart"
+        s2.load_range(0, snap)
+        s2.set_seed(seed)
+        tail = [s2.tick(T0 + 60 + k, mode=am.SWEEP_CLOSED_LOOP) for k in range(70)]
+        final = s2.read_range(0, n)
+    for k in range(140):
+        want = orc.sweep(orac, T0 - 10 + k, mode=1, seed=seed)
+        if k >= 70:
+            gi, ga, gs = tail[k - 70]
+            assert gs == want[2], f"tick {k}"
+            np.testing.assert_array_equal(gi, want[0])
+            np.testing.assert_array_equal(ga, want[1])
+    for name in am.COLUMN_NAMES:
+        np.testing.assert_array_equal(final[name], orac[name], err_msg=name)
