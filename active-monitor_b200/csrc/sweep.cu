@@ -581,6 +581,10 @@ int am_sweep_read(am_sweep_t* h, uint64_t first, uint64_t n, const uint64_t* idx
   TickGuard g(h);
   if (!g.ok) return AM_E_BUSY;
   AM_CUDA(h, cudaSetDevice(h->device));
+  {  // a read observes every upsert / remove / result staged before it
+    int rc = drain_staged(h);
+    if (rc != AM_OK) return rc;
+  }
   if (!idx) {
     if (first + n > h->capacity || first + n < first) return AM_E_INVAL;
     for (int k = 0; k < 16; ++k) {
