@@ -223,7 +223,9 @@ int am_sweep_tick(am_sweep_t*, int64_t unix_sec, uint32_t mode, uint64_t* due_id
  * d_due_idx (u32 LOCAL indices), d_due_action (u8) hold `cap` entries;
  * d_count receives n_emitted (u32); d_stats (may be NULL) receives an
  * am_tick_stats_t.  Used for device-resident pipelines and the multi-GPU
- * gather. */
+ * gather.  All ticks of one handle must be issued in stream order (they share
+ * the handle's segment and counter buffers); the OUTPUT buffers may alternate
+ * so that a consumer of tick k overlaps tick k+1. */
 int am_sweep_tick_device(am_sweep_t*, int64_t unix_sec, uint32_t mode, void* d_due_idx,
                          void* d_due_action, uint64_t cap, void* d_count, void* d_stats,
                          void* cuda_stream);
