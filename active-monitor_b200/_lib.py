@@ -135,6 +135,7 @@ SYMBOLS = {
     "am_gather_create": (C.c_int, [P(C.c_void_p), C.c_int, C.c_int, C.c_int, u64, C.c_int]),
     "am_gather_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "am_gather_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "am_gather_set_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "am_gather_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, u64, C.c_void_p]),
     "am_gather_out_idx": (C.c_void_p, [C.c_void_p]),
     "am_gather_out_act": (C.c_void_p, [C.c_void_p]),

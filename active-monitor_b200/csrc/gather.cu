@@ -178,6 +178,222 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const PushParams p) {
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Compressed wire format ("c3"): 3 bytes per entry over NVLink instead of 5.
+// A rank's list holds ascending LOCAL indices, so within a group of kGroupRecords
+// = 8192 consecutive records an entry is a 13-bit offset: the sender ships u16
+// offsets + u8 actions (destination-aligned 8 B + 4 B stores per quad) and one
+// count per group; every receiver scans the counts and expands
+//   global index = base[rank] + 8192 * group + offset
+// locally into its final index list (the action bytes already sit in their final
+// place).  The expansion costs 6 B of local HBM traffic per entry, the exchange
+// saves 2 B of NVLink traffic per entry per peer — NVLink is the scarce resource.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kGroupRecords = 8192;
+
+struct PushC3Params {
+  unsigned char* peer[kMaxWorld];
+  const uint32_t* idx_local;
+  const uint8_t* act_local;
+  const uint32_t* count_local;
+  uint32_t* out_counts;
+  uint64_t cap_total;
+  size_t off_act[2], off_gc[2], off_o16[2];
+  uint32_t epoch;
+  uint32_t ngroups_mine;  // groups of this rank's shard
+  uint32_t ngroups_max;   // row length of the group-count table
+  int rank, world;
+};
+
+// first position in the ascending list whose index is >= key
+__device__ __forceinline__ uint32_t lower_bound_idx(const uint32_t* a, uint32_t n, uint32_t key) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) gather_push_c3_kernel(const PushC3Params p) {
+  __shared__ uint32_t s_count[kMaxWorld];
+  const int tid = threadIdx.x;
+  ExchangeHeader* mine = reinterpret_cast<ExchangeHeader*>(p.peer[p.rank]);
+  const uint32_t my_count = *p.count_local;
+  const int buf = p.epoch & 1;
+
+  if (blockIdx.x == 0 && tid < p.world) {  // 1. publish my count
+    ExchangeHeader* peer = reinterpret_cast<ExchangeHeader*>(p.peer[tid]);
+    st_release_sys(&peer->count_slot[p.rank], ((unsigned long long)p.epoch << 32) | my_count);
+  }
+  if (tid < p.world) {  // 2. everyone's counts
+    unsigned long long v;
+    do { v = ld_acquire_sys(&mine->count_slot[tid]); } while ((uint32_t)(v >> 32) != p.epoch);
+    s_count[tid] = (uint32_t)v;
+  }
+  __syncthreads();
+  uint64_t offset = 0, total = 0;
+  for (int r = 0; r < p.world; ++r) {
+    if (r < p.rank) offset += s_count[r];
+    total += s_count[r];
+  }
+  const uint64_t room = offset < p.cap_total ? p.cap_total - offset : 0;
+  const uint32_t n = (uint32_t)(my_count < room ? my_count : room);
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+
+  // 2b. my per-group counts (binary searches on the ascending list) -> row `rank` of every peer's table
+  for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + tid; g < p.ngroups_mine; g += stride) {
+    const uint32_t lo = lower_bound_idx(p.idx_local, n, (uint32_t)g * kGroupRecords);
+    const uint32_t hi = lower_bound_idx(p.idx_local, n, ((uint32_t)g + 1u) * kGroupRecords);
+    for (int r = 0; r < p.world; ++r)
+      reinterpret_cast<uint32_t*>(p.peer[r] + p.off_gc[buf])[(size_t)p.rank * p.ngroups_max + g] = hi - lo;
+  }
+
+  // 3. offsets + actions, destination-aligned quads: one 8 B and one 4 B store per peer
+  const uint64_t q_lo = offset / 4, q_hi = (offset + n + 3) / 4;
+  for (uint64_t q0 = q_lo + blockIdx.x * (uint64_t)blockDim.x + tid; q0 < q_hi; q0 += 4 * stride) {
+    uint32_t lo16[4][2], ga[4];  // two u16 offsets per word, four action bytes per word
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t q = q0 + (uint64_t)u * stride;
+      ga[u] = 0; lo16[u][0] = 0; lo16[u][1] = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t pos = 4 * q + k;
+        const bool ok = q < q_hi && pos >= offset && pos < offset + n;
+        const uint64_t e = pos - offset;
+        const uint32_t o = ok ? (__ldcs(p.idx_local + e) & (kGroupRecords - 1u)) : 0u;
+        lo16[u][k >> 1] |= o << (16 * (k & 1));
+        ga[u] |= (ok ? (uint32_t)__ldcs(p.act_local + e) : 0u) << (8 * k);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t q = q0 + (uint64_t)u * stride;
+      if (q >= q_hi) continue;
+      const bool full = 4 * q >= offset && 4 * q + 4 <= offset + n;
+      if (full) {
+        const uint2 v = make_uint2(lo16[u][0], lo16[u][1]);
+        for (int r = 0; r < p.world; ++r) {
+          reinterpret_cast<uint2*>(p.peer[r] + p.off_o16[buf])[q] = v;
+          reinterpret_cast<uint32_t*>(p.peer[r] + p.off_act[buf])[q] = ga[u];
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t pos = 4 * q + k;
+          if (pos < offset || pos >= offset + n) continue;
+          const uint16_t o = (uint16_t)(lo16[u][k >> 1] >> (16 * (k & 1)));
+          for (int r = 0; r < p.world; ++r) {
+            reinterpret_cast<uint16_t*>(p.peer[r] + p.off_o16[buf])[pos] = o;
+            (p.peer[r] + p.off_act[buf])[pos] = (uint8_t)(ga[u] >> (8 * k));
+          }
+        }
+      }
+    }
+  }
+  // 4. completion, as in the plain format
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int ticket = atomicAdd(&mine->cta_done, 1u);
+    if (ticket == gridDim.x - 1) {
+      __threadfence_system();
+      for (int r = 0; r < p.world; ++r) {
+        ExchangeHeader* peer = reinterpret_cast<ExchangeHeader*>(p.peer[r]);
+        st_release_sys(&peer->done_slot[p.rank], (unsigned long long)p.epoch);
+      }
+      for (int r = 0; r < p.world; ++r) {
+        while (ld_acquire_sys(&mine->done_slot[r]) != (unsigned long long)p.epoch) {}
+      }
+      for (int r = 0; r < p.world; ++r) p.out_counts[r] = s_count[r];
+      p.out_counts[p.world] = (uint32_t)(total < p.cap_total ? total : p.cap_total);
+      mine->cta_done = 0;
+      __threadfence();
+    }
+  }
+}
+
+// Receiver, step 1: exclusive scan of every rank's group counts (one CTA per rank).
+// prefix[r][g] = entries of rank r in groups < g; prefix[r][ngroups[r]] = its total.
+struct ScanParams {
+  const uint32_t* gc;   // [world][ngroups_max] in my exchange block
+  uint32_t* prefix;     // [world][ngroups_max + 1], local
+  uint32_t ngroups[kMaxWorld];
+  uint32_t ngroups_max;
+};
+__global__ void __launch_bounds__(1024) gather_scan_kernel(const ScanParams p) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t ng = p.ngroups[r];
+  const uint32_t* in = p.gc + (size_t)r * p.ngroups_max;
+  uint32_t* out = p.prefix + (size_t)r * (p.ngroups_max + 1);
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < ng; base += blockDim.x) {
+    const uint32_t g = base + tid;
+    const uint32_t v = g < ng ? in[g] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+      if (lane >= d) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+      const uint32_t wv = s_warp[lane];
+      uint32_t wi = wv;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+        if (lane >= d) wi += up;
+      }
+      s_warp[lane] = wi - wv;  // exclusive prefix of the warp totals
+    }
+    __syncthreads();
+    const uint32_t carry = s_carry;
+    if (g < ng) out[g] = carry + s_warp[warp] + incl - v;
+    __syncthreads();
+    if (tid == blockDim.x - 1) s_carry = carry + s_warp[warp] + incl;
+    __syncthreads();
+  }
+  if (tid == 0) out[ng] = s_carry;
+}
+
+// Receiver, step 2: expand one (rank, group) per CTA into the final index list.
+struct DecodeParams {
+  const uint16_t* o16;       // [cap_total] in my exchange block
+  const uint32_t* prefix;    // [world][ngroups_max + 1]
+  const uint32_t* counts;    // out_counts: per-rank counts
+  void* final_idx;           // [cap_total] u32 or u64
+  uint64_t bases[kMaxWorld];
+  uint32_t ngroups[kMaxWorld];
+  uint64_t cap_total;
+  uint32_t ngroups_max;
+  int world, idx_bytes;
+};
+__global__ void __launch_bounds__(256) gather_decode_kernel(const DecodeParams p) {
+  const int r = blockIdx.y;
+  const uint32_t g = blockIdx.x;
+  if (g >= p.ngroups[r]) return;
+  uint64_t rank_off = 0;
+  for (int q = 0; q < r; ++q) rank_off += p.counts[q];
+  const uint32_t* pre = p.prefix + (size_t)r * (p.ngroups_max + 1);
+  const uint32_t lo = pre[g], cnt = pre[g + 1] - lo;
+  const uint64_t start = rank_off + lo;
+  const uint64_t gbase = p.bases[r] + (uint64_t)g * kGroupRecords;
+  for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) {
+    const uint64_t pos = start + e;
+    if (pos >= p.cap_total) break;
+    const uint64_t v = gbase + p.o16[pos];
+    if (p.idx_bytes == 4) reinterpret_cast<uint32_t*>(p.final_idx)[pos] = (uint32_t)v;
+    else reinterpret_cast<uint64_t*>(p.final_idx)[pos] = v;
+  }
+}
+
 }  // namespace
 
 struct am_gather {
@@ -193,6 +409,14 @@ struct am_gather {
   uint32_t* out_counts = nullptr;
   uint32_t epoch = 0;
   bool connected = false;
+  // compressed wire format (enabled by am_gather_set_layout)
+  bool compressed = false;
+  size_t off_gc[2] = {0, 0}, off_o16[2] = {0, 0};
+  uint32_t ngroups_max = 0;
+  uint64_t bases[kMaxWorld] = {}, sizes[kMaxWorld] = {};
+  uint32_t ngroups[kMaxWorld] = {};
+  uint32_t* prefix = nullptr;               // [world][ngroups_max + 1]
+  void* final_idx[2] = {nullptr, nullptr};  // expanded global indices, by epoch parity
   std::string last_error;
 };
 
@@ -222,6 +446,10 @@ int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_
   size_t off = align(sizeof(ExchangeHeader));
   for (int b = 0; b < 2; ++b) { g->off_idx[b] = off; off = align(off + cap_total * 8); }
   for (int b = 0; b < 2; ++b) { g->off_act[b] = off; off = align(off + cap_total); }
+  // compressed wire format: per-group counts [world][ngroups_max] and u16 offsets [cap_total]
+  g->ngroups_max = (uint32_t)((cap_total + kGroupRecords - 1) / kGroupRecords);
+  for (int b = 0; b < 2; ++b) { g->off_gc[b] = off; off = align(off + (size_t)world * g->ngroups_max * 4); }
+  for (int b = 0; b < 2; ++b) { g->off_o16[b] = off; off = align(off + cap_total * 2); }
   g->block_bytes = off;
   int rc = [&]() -> int {
     AMG_CUDA(g, cudaSetDevice(device));
@@ -268,6 +496,24 @@ int am_gather_connect(am_gather_t* g, const void* handles) {
   return AM_OK;
 }
 
+int am_gather_set_layout(am_gather_t* g, const uint64_t* bases, const uint64_t* sizes) {
+  if (!g || !bases || !sizes) return AM_E_INVAL;
+  AMG_CUDA(g, cudaSetDevice(g->device));
+  for (int r = 0; r < g->world; ++r) {
+    const uint64_t ng = (sizes[r] + kGroupRecords - 1) / kGroupRecords;
+    if (ng > g->ngroups_max) return AM_E_RANGE;
+    if (g->idx_bytes == 4 && bases[r] + sizes[r] > (1ull << 32)) return AM_E_RANGE;
+    g->bases[r] = bases[r];
+    g->sizes[r] = sizes[r];
+    g->ngroups[r] = (uint32_t)ng;
+  }
+  if (!g->prefix) AMG_CUDA(g, cudaMalloc((void**)&g->prefix, (size_t)g->world * (g->ngroups_max + 1) * 4));
+  for (int b = 0; b < 2; ++b)
+    if (!g->final_idx[b]) AMG_CUDA(g, cudaMalloc(&g->final_idx[b], g->cap_total * (size_t)g->idx_bytes));
+  g->compressed = true;
+  return AM_OK;
+}
+
 int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_local,
                    const void* d_count_local, uint64_t shard_base, void* cuda_stream) {
   if (!g || !d_idx_local || !d_act_local || !d_count_local) return AM_E_INVAL;
@@ -284,6 +530,49 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
   for (int b = 0; b < 2; ++b) { p.off_idx[b] = g->off_idx[b]; p.off_act[b] = g->off_act[b]; }
   g->epoch += 1;
   if (g->epoch == 0) g->epoch = 2;  // keep parity continuity irrelevant: 0 is the "never written" value
+  if (g->compressed) {
+    if (shard_base != g->bases[g->rank]) return AM_E_INVAL;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int buf = g->epoch & 1;
+    PushC3Params c{};
+    for (int r = 0; r < g->world; ++r) c.peer[r] = g->peer[r];
+    c.idx_local = (const uint32_t*)d_idx_local;
+    c.act_local = (const uint8_t*)d_act_local;
+    c.count_local = (const uint32_t*)d_count_local;
+    c.out_counts = g->out_counts;
+    c.cap_total = g->cap_total;
+    for (int b = 0; b < 2; ++b) { c.off_act[b] = g->off_act[b]; c.off_gc[b] = g->off_gc[b]; c.off_o16[b] = g->off_o16[b]; }
+    c.epoch = g->epoch;
+    c.ngroups_mine = g->ngroups[g->rank];
+    c.ngroups_max = g->ngroups_max;
+    c.rank = g->rank;
+    c.world = g->world;
+    gather_push_c3_kernel<<<g->n_ctas, 256, 0, st>>>(c);
+    ScanParams sp{};
+    sp.gc = reinterpret_cast<const uint32_t*>(g->block + g->off_gc[buf]);
+    sp.prefix = g->prefix;
+    sp.ngroups_max = g->ngroups_max;
+    DecodeParams dp{};
+    dp.o16 = reinterpret_cast<const uint16_t*>(g->block + g->off_o16[buf]);
+    dp.prefix = g->prefix;
+    dp.counts = g->out_counts;
+    dp.final_idx = g->final_idx[buf];
+    dp.cap_total = g->cap_total;
+    dp.ngroups_max = g->ngroups_max;
+    dp.world = g->world;
+    dp.idx_bytes = g->idx_bytes;
+    uint32_t ng_used = 1;
+    for (int r = 0; r < g->world; ++r) {
+      sp.ngroups[r] = g->ngroups[r];
+      dp.ngroups[r] = g->ngroups[r];
+      dp.bases[r] = g->bases[r];
+      if (g->ngroups[r] > ng_used) ng_used = g->ngroups[r];
+    }
+    gather_scan_kernel<<<g->world, 1024, 0, st>>>(sp);
+    gather_decode_kernel<<<dim3(ng_used, g->world), 256, 0, st>>>(dp);
+    AMG_CUDA(g, cudaGetLastError());
+    return AM_OK;
+  }
   p.epoch = g->epoch;
   p.rank = g->rank;
   p.world = g->world;
@@ -294,7 +583,10 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
   return AM_OK;
 }
 
-void* am_gather_out_idx(am_gather_t* g) { return g ? g->block + g->off_idx[g->epoch & 1] : nullptr; }
+void* am_gather_out_idx(am_gather_t* g) {
+  if (!g) return nullptr;
+  return g->compressed ? g->final_idx[g->epoch & 1] : (void*)(g->block + g->off_idx[g->epoch & 1]);
+}
 void* am_gather_out_act(am_gather_t* g) { return g ? g->block + g->off_act[g->epoch & 1] : nullptr; }
 void* am_gather_out_counts(am_gather_t* g) { return g ? g->out_counts : nullptr; }
 const char* am_gather_last_error(const am_gather_t* g) { return g ? g->last_error.c_str() : ""; }
@@ -307,6 +599,8 @@ void am_gather_destroy(am_gather_t* g) {
     if (g->opened[r] && g->peer[r]) cudaIpcCloseMemHandle(g->peer[r]);
   if (g->block) cudaFree(g->block);
   if (g->out_counts) cudaFree(g->out_counts);
+  if (g->prefix) cudaFree(g->prefix);
+  for (int b = 0; b < 2; ++b) if (g->final_idx[b]) cudaFree(g->final_idx[b]);
   delete g;
 }
 

@@ -63,7 +63,11 @@ class PeerGather:
     all-gather above.  torch.distributed is used once, at set-up, to swap the
     CUDA-IPC handles."""
 
-    def __init__(self, device_index: int, cap_total: int, group=None, idx_bytes: int = 8):
+    def __init__(self, device_index: int, cap_total: int, group=None, idx_bytes: int = 8,
+                 shard=None):
+        """shard=(first global index, number of records) of this rank switches on the
+        compressed wire format (3 B per entry over NVLink: u16 offsets within
+        8192-record groups + per-group counts, expanded on every receiver)."""
         import ctypes as C
 
         from . import _lib as L
@@ -99,6 +103,20 @@ class PeerGather:
             dist.all_gather_object(handles, bytes(mine.raw), group=group)
             rc = self._lib.am_gather_connect(self._h, b"".join(handles))
             agree(rc == 0, "am_gather_connect (CUDA IPC peer mapping)")
+        self.compressed = shard is not None
+        if shard is not None:
+            import numpy as np
+            mine_t = torch.tensor([int(shard[0]), int(shard[1])], dtype=torch.int64, device=self.device)
+            all_t = torch.empty(2 * self.world, dtype=torch.int64, device=self.device)
+            if self.world > 1:
+                dist.all_gather_into_tensor(all_t, mine_t, group=group)
+            else:
+                all_t.copy_(mine_t)
+            lay = all_t.cpu().numpy().astype(np.uint64).reshape(self.world, 2)
+            bases = np.ascontiguousarray(lay[:, 0])
+            sizes = np.ascontiguousarray(lay[:, 1])
+            rc = self._lib.am_gather_set_layout(self._h, bases.ctypes.data, sizes.ctypes.data)
+            agree(rc == 0, "am_gather_set_layout")
 
     def _check(self, rc, where):
         if rc != 0:

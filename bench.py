@@ -164,6 +164,9 @@ def main():
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="records per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--wire", default="plain", choices=["plain", "c3"],
+                    help="peer gather wire format: plain = u32 index + u8 action (5 B/entry), "
+                         "c3 = u16 group offset + u8 action + per-group counts (3 B/entry), expanded on the receiver")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N>1: NVLink peer-write kernel (csrc/gather.cu) or the padded NCCL all-gather")
     args = ap.parse_args()
@@ -212,7 +215,8 @@ def main():
         ok = 1
         try:
             peer = gather.PeerGather(local_rank, cap_total=n * world,
-                                     idx_bytes=4 if n * world < (1 << 32) else 8)
+                                     idx_bytes=4 if n * world < (1 << 32) else 8,
+                                     shard=(base, n) if args.wire == "c3" else None)
         except Exception as e:  # noqa: BLE001
             print(f"[bench] rank {rank}: peer-write gather unavailable ({e}); using NCCL", file=sys.stderr)
             ok = 0
@@ -285,7 +289,8 @@ def main():
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
-    launches = sweep.launch_count - launches0 + (args.steps if peer is not None else 0)
+    launches = sweep.launch_count - launches0 + (
+        0 if peer is None else args.steps * (3 if peer.compressed else 1))
     stats = dict(zip(am.abi.STAT_FIELDS, [int(v) for v in d_st.cpu().tolist()]))
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
@@ -396,7 +401,7 @@ def main():
                        "records_per_gpu": n, "records_total": n * world,
                        "l2": "inputs (560 MB/GPU) larger than L2 (126 MB); no flush needed",
                        "parallelism": f"index-range shards x{world}" + (
-                           "" if world == 1 else (", due lists concatenated by the NVLink peer-write kernel (overlapped with the next sweep)"
+                           "" if world == 1 else (f", due lists concatenated by the NVLink peer-write kernel, wire format {args.wire} (overlapped with the next sweep)"
                                                   if peer is not None else ", padded NCCL all-gather of due lists")),
                        "due_per_tick": stats["n_submit_hc"], "emitted_per_tick": stats["n_emitted"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

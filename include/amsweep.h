@@ -288,6 +288,11 @@ int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_
                      int idx_bytes);
 int am_gather_export(am_gather_t*, void* handle_out /* AM_IPC_HANDLE_BYTES */);
 int am_gather_connect(am_gather_t*, const void* handles /* world x AM_IPC_HANDLE_BYTES, rank order */);
+/* Optional, after connect: switch to the compressed wire format (3 B per entry on
+ * NVLink instead of 5: u16 offsets within 8192-record groups + per-group counts,
+ * expanded by each receiver into the same output as the plain format).  bases[r] /
+ * sizes[r] = first global index / number of records of rank r's shard. */
+int am_gather_set_layout(am_gather_t*, const uint64_t* bases, const uint64_t* sizes);
 int am_gather_push(am_gather_t*, const void* d_idx_local /* u32 */, const void* d_act_local /* u8 */,
                    const void* d_count_local /* u32 */, uint64_t shard_base, void* cuda_stream);
 void* am_gather_out_idx(am_gather_t*);    /* u64|u32[cap_total], valid after the last push retires */

@@ -23,7 +23,7 @@ def _ngpu():
         return 0
 
 
-def _worker(rank, world, port, n_total, ticks, q):
+def _worker(rank, world, port, n_total, ticks, wire, q):
     import torch
     import torch.distributed as dist
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tools", "amgen")):
@@ -42,8 +42,9 @@ def _worker(rank, world, port, n_total, ticks, q):
         out = []
         with am.Sweep(capacity=cnt, device=rank, shard_base=first) as s:
             s.load_range(0, cols)
-            # alternate the wire format: u32 global indices on even worlds' first rank pair, u64 otherwise
-            pg = gather.PeerGather(rank, cap_total=n_total, idx_bytes=4 if world % 4 == 0 else 8)
+            # u32 global indices on worlds divisible by 4, u64 otherwise; wire = plain | c3 (compressed)
+            pg = gather.PeerGather(rank, cap_total=n_total, idx_bytes=4 if world % 4 == 0 else 8,
+                                   shard=(first, cnt) if wire == "c3" else None)
             d_idx = torch.empty(cnt, dtype=torch.int32, device=dev)
             d_act = torch.empty(cnt, dtype=torch.uint8, device=dev)
             d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -66,8 +67,9 @@ def _worker(rank, world, port, n_total, ticks, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("wire", ["plain", "c3"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_sweep_and_both_gathers_equal_unsharded_oracle(world):
+def test_sharded_sweep_and_both_gathers_equal_unsharded_oracle(world, wire):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
@@ -77,7 +79,8 @@ def test_sharded_sweep_and_both_gathers_equal_unsharded_oracle(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + os.getpid() % 1000
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, ticks, q)) for r in range(world)]
+    port += 7 if wire == "c3" else 0
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, ticks, wire, q)) for r in range(world)]
     for p in procs:
         p.start()
     results = dict(q.get(timeout=300) for _ in range(world))

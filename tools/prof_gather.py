@@ -32,8 +32,8 @@ st = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(st)
 s.tick_device(T0, 0, d_idx.data_ptr(), d_act.data_ptr(), n, d_cnt.data_ptr(), 0, st.cuda_stream)
 st.synchronize()
-for ib in (4, 8, 4):
-    pg = gather.PeerGather(lr, cap_total=n * world, idx_bytes=ib)
+for ib, wire in ((4, "plain"), (4, "c3"), (8, "plain"), (4, "c3")):
+    pg = gather.PeerGather(lr, cap_total=n * world, idx_bytes=ib, shard=(rank * n, n) if wire == "c3" else None)
     for _ in range(5):
         pg.push(d_idx.data_ptr(), d_act.data_ptr(), d_cnt.data_ptr(), rank * n, st.cuda_stream)
     st.synchronize(); dist.barrier()
@@ -45,8 +45,9 @@ for ib in (4, 8, 4):
     st.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / K
     cnt = int(d_cnt.item())
-    print(f"rank {rank} idx_bytes {ib}: {us:.1f} us/push, {cnt} entries, "
-          f"{cnt * (ib + 1) * (world - 1) / us / 1e3:.1f} GB/s out over NVLink", flush=True)
+    wire_b = 3 if wire == "c3" else ib + 1
+    print(f"rank {rank} idx_bytes {ib} wire {wire}: {us:.1f} us/exchange, {cnt} entries, "
+          f"{cnt * wire_b * (world - 1) / us / 1e3:.1f} GB/s out over NVLink", flush=True)
     dist.barrier()
     pg.close()
 dist.barrier()
