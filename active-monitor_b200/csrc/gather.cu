@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const PushParams p) {
 // count per group; every receiver scans the counts and expands
 //   global index = base[rank] + 8192 * group + offset
 // locally into its final index list (the action bytes already sit in their final
-// place).  The expansion costs 6 B of local HBM traffic per entry, the exchange
+// place; the prefix sum over the group counts is folded into the expansion kernel).  The expansion costs 6 B of local HBM traffic per entry, the exchange
 // saves 2 B of NVLink traffic per entry per peer — NVLink is the scarce resource.
 // ---------------------------------------------------------------------------
 constexpr uint32_t kGroupRecords = 8192;
@@ -240,18 +240,37 @@ __global__ void __launch_bounds__(256) gather_push_c3_kernel(const PushC3Params 
   }
   const uint64_t room = offset < p.cap_total ? p.cap_total - offset : 0;
   const uint32_t n = (uint32_t)(my_count < room ? my_count : room);
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
 
-  // 2b. my per-group counts (binary searches on the ascending list) -> row `rank` of every peer's table
-  for (uint64_t g = blockIdx.x * (uint64_t)blockDim.x + tid; g < p.ngroups_mine; g += stride) {
-    const uint32_t lo = lower_bound_idx(p.idx_local, n, (uint32_t)g * kGroupRecords);
-    const uint32_t hi = lower_bound_idx(p.idx_local, n, ((uint32_t)g + 1u) * kGroupRecords);
-    for (int r = 0; r < p.world; ++r)
-      reinterpret_cast<uint32_t*>(p.peer[r] + p.off_gc[buf])[(size_t)p.rank * p.ngroups_max + g] = hi - lo;
+  // 2b. my per-group counts -> row `rank` of every peer's table.  The last S CTAs of the
+  //     grid do nothing else: each of their threads finds ONE group boundary by binary
+  //     search on the ascending list (255 groups per CTA: 256 boundaries), counts are
+  //     differences of neighbours.  The other CTAs go straight to the payload, so the
+  //     ~22 dependent L2 reads of a search overlap the NVLink stores.
+  __shared__ uint32_t s_bound[256];
+  const uint32_t n_search = (p.ngroups_mine + 254u) / 255u;
+  const bool split = gridDim.x > n_search;            // enough CTAs to dedicate some
+  const uint32_t n_work = split ? gridDim.x - n_search : gridDim.x;
+  const bool searcher = split ? blockIdx.x >= n_work : true;
+  if (searcher) {
+    const uint32_t first_sb = split ? blockIdx.x - n_work : blockIdx.x;
+    for (uint32_t sb = first_sb; sb < n_search; sb += (split ? n_search : gridDim.x)) {
+      const uint32_t g0 = sb * 255u;
+      const uint32_t gb = g0 + (uint32_t)tid;  // boundary index
+      s_bound[tid] = gb <= p.ngroups_mine ? lower_bound_idx(p.idx_local, n, gb * kGroupRecords) : n;
+      __syncthreads();
+      if (tid < 255 && g0 + (uint32_t)tid < p.ngroups_mine) {
+        const uint32_t cnt = s_bound[tid + 1] - s_bound[tid];
+        for (int r = 0; r < p.world; ++r)
+          reinterpret_cast<uint32_t*>(p.peer[r] + p.off_gc[buf])[(size_t)p.rank * p.ngroups_max + g0 + tid] = cnt;
+      }
+      __syncthreads();
+    }
   }
+  const bool worker = split ? blockIdx.x < n_work : true;
+  const uint64_t stride = (uint64_t)n_work * blockDim.x;
 
   // 3. offsets + actions, destination-aligned quads: one 8 B and one 4 B store per peer
-  const uint64_t q_lo = offset / 4, q_hi = (offset + n + 3) / 4;
+  const uint64_t q_lo = offset / 4, q_hi = worker ? (offset + n + 3) / 4 : 0;
   for (uint64_t q0 = q_lo + blockIdx.x * (uint64_t)blockDim.x + tid; q0 < q_hi; q0 += 4 * stride) {
     uint32_t lo16[4][2], ga[4];  // two u16 offsets per word, four action bytes per word
 #pragma unroll
@@ -315,58 +334,13 @@ __global__ void __launch_bounds__(256) gather_push_c3_kernel(const PushC3Params 
   }
 }
 
-// Receiver, step 1: exclusive scan of every rank's group counts (one CTA per rank).
-// prefix[r][g] = entries of rank r in groups < g; prefix[r][ngroups[r]] = its total.
-struct ScanParams {
-  const uint32_t* gc;   // [world][ngroups_max] in my exchange block
-  uint32_t* prefix;     // [world][ngroups_max + 1], local
-  uint32_t ngroups[kMaxWorld];
-  uint32_t ngroups_max;
-};
-__global__ void __launch_bounds__(1024) gather_scan_kernel(const ScanParams p) {
-  __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry;
-  const int r = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t ng = p.ngroups[r];
-  const uint32_t* in = p.gc + (size_t)r * p.ngroups_max;
-  uint32_t* out = p.prefix + (size_t)r * (p.ngroups_max + 1);
-  if (tid == 0) s_carry = 0;
-  __syncthreads();
-  for (uint32_t base = 0; base < ng; base += blockDim.x) {
-    const uint32_t g = base + tid;
-    const uint32_t v = g < ng ? in[g] : 0u;
-    uint32_t incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-      if (lane >= d) incl += up;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-      const uint32_t wv = s_warp[lane];
-      uint32_t wi = wv;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-        if (lane >= d) wi += up;
-      }
-      s_warp[lane] = wi - wv;  // exclusive prefix of the warp totals
-    }
-    __syncthreads();
-    const uint32_t carry = s_carry;
-    if (g < ng) out[g] = carry + s_warp[warp] + incl - v;
-    __syncthreads();
-    if (tid == blockDim.x - 1) s_carry = carry + s_warp[warp] + incl;
-    __syncthreads();
-  }
-  if (tid == 0) out[ng] = s_carry;
-}
-
-// Receiver, step 2: expand one (rank, group) per CTA into the final index list.
+// Receiver: expand one (rank, group) per CTA into the final index list.  The CTA's
+// start position is the rank's offset plus the sum of that rank's earlier group counts
+// (a few KB of L2-resident reads, as in compact_kernel); four entries are in flight per
+// thread.
 struct DecodeParams {
   const uint16_t* o16;       // [cap_total] in my exchange block
-  const uint32_t* prefix;    // [world][ngroups_max + 1]
+  const uint32_t* gc;        // [world][ngroups_max] in my exchange block
   const uint32_t* counts;    // out_counts: per-rank counts
   void* final_idx;           // [cap_total] u32 or u64
   uint64_t bases[kMaxWorld];
@@ -376,21 +350,37 @@ struct DecodeParams {
   int world, idx_bytes;
 };
 __global__ void __launch_bounds__(256) gather_decode_kernel(const DecodeParams p) {
-  const int r = blockIdx.y;
+  __shared__ uint32_t s_part[8];
+  const int r = blockIdx.y, tid = threadIdx.x;
   const uint32_t g = blockIdx.x;
-  if (g >= p.ngroups[r]) return;
-  uint64_t rank_off = 0;
-  for (int q = 0; q < r; ++q) rank_off += p.counts[q];
-  const uint32_t* pre = p.prefix + (size_t)r * (p.ngroups_max + 1);
-  const uint32_t lo = pre[g], cnt = pre[g + 1] - lo;
-  const uint64_t start = rank_off + lo;
+  if (g >= p.ngroups[r]) return;  // uniform per CTA
+  const uint32_t* row = p.gc + (size_t)r * p.ngroups_max;
+  uint32_t part = 0;
+  for (uint32_t j = tid; j < g; j += blockDim.x) part += row[j];
+  part = __reduce_add_sync(0xFFFFFFFFu, part);
+  if ((tid & 31) == 0) s_part[tid >> 5] = part;
+  __syncthreads();
+  uint64_t start = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) start += s_part[k];
+  for (int q = 0; q < r; ++q) start += p.counts[q];
+  const uint32_t cnt = row[g];
   const uint64_t gbase = p.bases[r] + (uint64_t)g * kGroupRecords;
-  for (uint32_t e = threadIdx.x; e < cnt; e += blockDim.x) {
-    const uint64_t pos = start + e;
-    if (pos >= p.cap_total) break;
-    const uint64_t v = gbase + p.o16[pos];
-    if (p.idx_bytes == 4) reinterpret_cast<uint32_t*>(p.final_idx)[pos] = (uint32_t)v;
-    else reinterpret_cast<uint64_t*>(p.final_idx)[pos] = v;
+  for (uint32_t e0 = tid; e0 < cnt; e0 += 4u * blockDim.x) {
+    uint32_t o[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t e = e0 + (uint32_t)u * blockDim.x;
+      o[u] = (e < cnt && start + e < p.cap_total) ? (uint32_t)__ldcs(p.o16 + start + e) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t e = e0 + (uint32_t)u * blockDim.x;
+      if (e >= cnt || start + e >= p.cap_total) continue;
+      const uint64_t v = gbase + o[u];
+      if (p.idx_bytes == 4) reinterpret_cast<uint32_t*>(p.final_idx)[start + e] = (uint32_t)v;
+      else reinterpret_cast<uint64_t*>(p.final_idx)[start + e] = v;
+    }
   }
 }
 
@@ -415,7 +405,6 @@ struct am_gather {
   uint32_t ngroups_max = 0;
   uint64_t bases[kMaxWorld] = {}, sizes[kMaxWorld] = {};
   uint32_t ngroups[kMaxWorld] = {};
-  uint32_t* prefix = nullptr;               // [world][ngroups_max + 1]
   void* final_idx[2] = {nullptr, nullptr};  // expanded global indices, by epoch parity
   std::string last_error;
 };
@@ -507,7 +496,6 @@ int am_gather_set_layout(am_gather_t* g, const uint64_t* bases, const uint64_t* 
     g->sizes[r] = sizes[r];
     g->ngroups[r] = (uint32_t)ng;
   }
-  if (!g->prefix) AMG_CUDA(g, cudaMalloc((void**)&g->prefix, (size_t)g->world * (g->ngroups_max + 1) * 4));
   for (int b = 0; b < 2; ++b)
     if (!g->final_idx[b]) AMG_CUDA(g, cudaMalloc(&g->final_idx[b], g->cap_total * (size_t)g->idx_bytes));
   g->compressed = true;
@@ -548,13 +536,9 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
     c.rank = g->rank;
     c.world = g->world;
     gather_push_c3_kernel<<<g->n_ctas, 256, 0, st>>>(c);
-    ScanParams sp{};
-    sp.gc = reinterpret_cast<const uint32_t*>(g->block + g->off_gc[buf]);
-    sp.prefix = g->prefix;
-    sp.ngroups_max = g->ngroups_max;
     DecodeParams dp{};
     dp.o16 = reinterpret_cast<const uint16_t*>(g->block + g->off_o16[buf]);
-    dp.prefix = g->prefix;
+    dp.gc = reinterpret_cast<const uint32_t*>(g->block + g->off_gc[buf]);
     dp.counts = g->out_counts;
     dp.final_idx = g->final_idx[buf];
     dp.cap_total = g->cap_total;
@@ -563,12 +547,10 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
     dp.idx_bytes = g->idx_bytes;
     uint32_t ng_used = 1;
     for (int r = 0; r < g->world; ++r) {
-      sp.ngroups[r] = g->ngroups[r];
       dp.ngroups[r] = g->ngroups[r];
       dp.bases[r] = g->bases[r];
       if (g->ngroups[r] > ng_used) ng_used = g->ngroups[r];
     }
-    gather_scan_kernel<<<g->world, 1024, 0, st>>>(sp);
     gather_decode_kernel<<<dim3(ng_used, g->world), 256, 0, st>>>(dp);
     AMG_CUDA(g, cudaGetLastError());
     return AM_OK;
@@ -599,7 +581,6 @@ void am_gather_destroy(am_gather_t* g) {
     if (g->opened[r] && g->peer[r]) cudaIpcCloseMemHandle(g->peer[r]);
   if (g->block) cudaFree(g->block);
   if (g->out_counts) cudaFree(g->out_counts);
-  if (g->prefix) cudaFree(g->prefix);
   for (int b = 0; b < 2; ++b) if (g->final_idx[b]) cudaFree(g->final_idx[b]);
   delete g;
 }

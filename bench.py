@@ -164,9 +164,11 @@ def main():
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="records per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--wire", default="plain", choices=["plain", "c3"],
+    ap.add_argument("--wire", default="auto", choices=["auto", "plain", "c3"],
                     help="peer gather wire format: plain = u32 index + u8 action (5 B/entry), "
-                         "c3 = u16 group offset + u8 action + per-group counts (3 B/entry), expanded on the receiver")
+                         "c3 = u16 group offset + u8 action + per-group counts (3 B/entry), expanded on the "
+                         "receiver; auto = c3 from 4 GPUs up (NVLink-volume-bound), plain below "
+                         "(profiles/r01_scaling.md)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N>1: NVLink peer-write kernel (csrc/gather.cu) or the padded NCCL all-gather")
     args = ap.parse_args()
@@ -175,6 +177,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.wire == "auto":
+        args.wire = "c3" if world >= 4 else "plain"
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -290,7 +294,7 @@ def main():
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = sweep.launch_count - launches0 + (
-        0 if peer is None else args.steps * (3 if peer.compressed else 1))
+        0 if peer is None else args.steps * (2 if peer.compressed else 1))
     stats = dict(zip(am.abi.STAT_FIELDS, [int(v) for v in d_st.cpu().tolist()]))
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
