@@ -90,6 +90,14 @@ STAT_FIELDS = ["n_records", "n_emitted", "n_submit_hc", "n_run_remedy", "n_stopp
                "idx_xor", "idx_sum"]
 
 
+class AmWorkItem(C.Structure):
+    _fields_ = [("idx", u64), ("unix_sec", i64), ("action", u32), ("reserved", u32)]
+
+
+WORK_ITEM_DTYPE = np.dtype([("idx", "<u8"), ("unix_sec", "<i8"), ("action", "<u4"), ("reserved", "<u4")])
+assert WORK_ITEM_DTYPE.itemsize == C.sizeof(AmWorkItem) == 24
+
+
 class AmTickStats(C.Structure):
     _fields_ = [(n, u64) for n in STAT_FIELDS]
 
@@ -142,6 +150,11 @@ SYMBOLS = {
     "am_gather_out_counts": (C.c_void_p, [C.c_void_p]),
     "am_gather_last_error": (C.c_char_p, [C.c_void_p]),
     "am_gather_destroy": (None, [C.c_void_p]),
+    "am_handoff_create": (C.c_int, [P(C.c_void_p), u64]),
+    "am_handoff_destroy": (None, [C.c_void_p]),
+    "am_handoff_publish": (C.c_int, [C.c_void_p, i64, u64, C.c_void_p, C.c_void_p, u32, P(u64)]),
+    "am_handoff_pop": (C.c_int, [C.c_void_p, u64, C.c_void_p, P(u64)]),
+    "am_handoff_stats": (C.c_int, [C.c_void_p, P(u64), P(u64), P(u64), P(u64)]),
     "am_civil_from_unix": (None, [i64, P(i32 * 6)]),
     "am_strerror": (C.c_char_p, [C.c_int]),
     "am_last_error_detail": (C.c_char_p, [C.c_void_p]),

@@ -301,6 +301,36 @@ void* am_gather_out_counts(am_gather_t*); /* u32[world+1]                       
 const char* am_gather_last_error(const am_gather_t*);
 void am_gather_destroy(am_gather_t*);
 
+/* ---- hand-off to the workflow side (host only, no GPU) ---- */
+/* The step AFTER the path: the 1 Hz ticker goroutine publishes the list one
+ * am_sweep_tick returned; up to MaxParallel workers (hcc.go:138, the
+ * MaxConcurrentReconciles of hcc.go:298) pop chunks and run
+ * createSubmitWorkflow / processRemedy (hcc.go:502, :759) for them.  It
+ * replaces the goroutine-per-timer fan-out of hcc.go:751 by a bounded FIFO:
+ * back-pressure instead of unbounded goroutines when the cluster is slow.
+ * Thread-safe for any number of publishers and poppers; never blocks. */
+typedef struct am_handoff am_handoff_t;
+typedef struct am_work_item {
+  uint64_t idx;     /* global record index                                    */
+  int64_t unix_sec; /* the tick that emitted it                               */
+  uint32_t action;  /* AM_ACT_* bits (already filtered by the publish mask)   */
+  uint32_t reserved;
+} am_work_item_t;
+
+int am_handoff_create(am_handoff_t** out, uint64_t capacity /* work items */);
+void am_handoff_destroy(am_handoff_t*);
+/* Enqueue, in order, the entries of one tick whose action has a bit of
+ * action_mask set (e.g. AM_ACT_SUBMIT_HC | AM_ACT_RUN_REMEDY).  All or
+ * nothing: AM_E_NOSPACE when they do not fit, nothing enqueued, *n_out = the
+ * number that would have been; AM_OK: *n_out = number enqueued. */
+int am_handoff_publish(am_handoff_t*, int64_t unix_sec, uint64_t n, const uint64_t* idx,
+                       const uint32_t* action, uint32_t action_mask, uint64_t* n_out);
+/* Dequeue up to `max` items in FIFO order (0 items is not an error). */
+int am_handoff_pop(am_handoff_t*, uint64_t max, am_work_item_t* out, uint64_t* n_out);
+/* Queue depth and lifetime totals (any pointer may be NULL). */
+int am_handoff_stats(am_handoff_t*, uint64_t* pending, uint64_t* published, uint64_t* popped,
+                     uint64_t* rejected_batches);
+
 /* UTC broken-down time exactly as the kernel computes it (test hook):
  * out[0..6) = sec, min, hour, dom(1-31), month(1-12), dow(0=Sunday). */
 void am_civil_from_unix(int64_t unix_sec, int32_t out[6]);
