@@ -16,6 +16,9 @@
 #include <cstring>
 #include <string>
 #include <string_view>
+#include <atomic>
+#include <thread>
+#include <vector>
 
 #include "../../include/amsweep.h"
 #include "civil.h"
@@ -546,6 +549,45 @@ int am_healthcheck_classify(const am_healthcheck_t* hc, am_record_t* out) {
   out->remedy_failed = (int32_t)hc->remedy_failed_count;
   out->remedy_total = (int32_t)hc->remedy_total_runs;
   return rc;
+}
+
+int am_healthcheck_classify_batch(const am_healthcheck_t* hcs, uint64_t n, am_record_t* out,
+                                  int32_t* rc_out, int n_threads, uint64_t* n_not_ok) {
+  if (n && (!hcs || !out)) return AM_E_INVAL;
+  if (n_not_ok) *n_not_ok = 0;
+  if (n == 0) return AM_OK;
+  unsigned nt = n_threads > 0 ? (unsigned)n_threads : std::thread::hardware_concurrency();
+  if (nt == 0) nt = 1;
+  const uint64_t kMinPerThread = 4096;  // below this a thread costs more than it saves
+  if ((uint64_t)nt > (n + kMinPerThread - 1) / kMinPerThread) nt = (unsigned)((n + kMinPerThread - 1) / kMinPerThread);
+  std::atomic<uint64_t> bad{0};
+  auto work = [&](uint64_t lo, uint64_t hi) {
+    uint64_t b = 0;
+    for (uint64_t i = lo; i < hi; ++i) {
+      const int rc = am_healthcheck_classify(&hcs[i], &out[i]);
+      if (rc_out) rc_out[i] = rc;
+      b += rc != AM_OK;
+    }
+    bad.fetch_add(b, std::memory_order_relaxed);
+  };
+  const uint64_t per = (n + nt - 1) / nt;
+  std::vector<std::thread> th;
+  uint64_t next_lo = per < n ? per : n;  // [0, per) is the calling thread's share
+  try {
+    th.reserve(nt - 1);
+    while (next_lo < n) {
+      const uint64_t hi = next_lo + per < n ? next_lo + per : n;
+      th.emplace_back(work, next_lo, hi);
+      next_lo = hi;
+    }
+  } catch (...) {
+    // thread or memory exhaustion: the calling thread runs whatever was not started
+  }
+  work(0, per < n ? per : n);
+  if (next_lo < n) work(next_lo, n);
+  for (auto& t : th) t.join();
+  if (n_not_ok) *n_not_ok = bad.load();
+  return AM_OK;
 }
 
 }  // extern "C"

@@ -8,9 +8,13 @@ api/v1alpha1/healthcheck_types.go:32-66.
 """
 from __future__ import annotations
 
+import ctypes as C
 import datetime as _dt
 
-from .sweep import classify, remedy_is_empty
+import numpy as np
+
+from . import _lib as L
+from .sweep import AmError, _as_bytes, classify, remedy_is_empty
 
 
 def _unix(ts):
@@ -54,3 +58,54 @@ def healthcheck_kwargs(doc: dict) -> dict:
 def record_from_manifest(doc: dict):
     """(rc, packed record) for one HealthCheck document."""
     return classify(**healthcheck_kwargs(doc))
+
+
+_KW = ("repeat_after_sec", "cron", "has_resource", "has_remedy", "remedy_runs_limit",
+       "remedy_reset_interval", "finished_at", "remedy_finished_at", "success_count", "failed_count",
+       "remedy_success_count", "remedy_failed_count", "remedy_total_runs")
+
+
+def classify_batch(items, n_threads: int = 0):
+    """`am_healthcheck_classify_batch` over a list of `classify()` keyword dicts (or manifests).
+
+    Returns (rc array int32[n], records RECORD_DTYPE[n]).  The ladder runs in the C++
+    classifier on `n_threads` host threads (0 = all); this function only lays the inputs out
+    as the am_healthcheck_t array a cgo caller would pass.
+    """
+    kws = [healthcheck_kwargs(it) if ("spec" in it or "status" in it) else it for it in items]
+    n = len(kws)
+    arr = (L.AmHealthCheck * n)()
+    keep = []  # the cron bytes must outlive the call (the library copies nothing before it returns)
+    for i, kw in enumerate(kws):
+        unknown = set(kw) - set(_KW) - {"fail_p8"}
+        if unknown:
+            raise TypeError(f"item {i}: unknown fields {sorted(unknown)}")
+        cron = kw.get("cron", "") or ""
+        raw = bytes(_as_bytes(cron))
+        keep.append(raw)
+        h = arr[i]
+        h.repeat_after_sec = int(kw.get("repeat_after_sec", 0) or 0)
+        h.cron, h.cron_len = raw, len(raw)
+        h.has_resource = int(bool(kw.get("has_resource", True)))
+        h.has_remedy = int(bool(kw.get("has_remedy", False)))
+        h.remedy_runs_limit = int(kw.get("remedy_runs_limit", 0) or 0)
+        h.remedy_reset_interval = int(kw.get("remedy_reset_interval", 0) or 0)
+        fa, rfa = kw.get("finished_at"), kw.get("remedy_finished_at")
+        h.finished_at, h.finished_at_set = (int(fa), 1) if fa is not None else (0, 0)
+        h.remedy_finished_at, h.remedy_finished_at_set = (int(rfa), 1) if rfa is not None else (0, 0)
+        h.success_count = int(kw.get("success_count", 0) or 0)
+        h.failed_count = int(kw.get("failed_count", 0) or 0)
+        h.remedy_success_count = int(kw.get("remedy_success_count", 0) or 0)
+        h.remedy_failed_count = int(kw.get("remedy_failed_count", 0) or 0)
+        h.remedy_total_runs = int(kw.get("remedy_total_runs", 0) or 0)
+        h.fail_p8 = int(kw.get("fail_p8", 0) or 0)
+    recs = np.zeros(n, dtype=L.RECORD_DTYPE)
+    rcs = np.zeros(n, dtype=np.int32)
+    bad = L.u64(0)
+    rc = L.load().am_healthcheck_classify_batch(C.cast(arr, C.c_void_p), n, recs.ctypes.data,
+                                                rcs.ctypes.data, n_threads, C.byref(bad))
+    if rc != L.AM_OK:
+        raise AmError(rc, "am_healthcheck_classify_batch")
+    assert int(bad.value) == int(np.count_nonzero(rcs))
+    del keep
+    return rcs, recs

@@ -145,6 +145,16 @@ typedef struct am_record {
  * per-reconcile error. */
 int am_healthcheck_classify(const am_healthcheck_t* hc, am_record_t* out);
 
+/* The same ladder for n HealthChecks at once (bulk ingest at
+ * controller start: the informer's initial list replays every CR through
+ * Reconcile, hcc.go:170).  Records are independent, so the batch is split
+ * over n_threads host threads (<= 0: one per hardware thread).  rc_out[i]
+ * (may be NULL) receives what am_healthcheck_classify returns for record i;
+ * the call itself returns AM_OK, or AM_E_INVAL / AM_E_NOMEM.  *n_not_ok (may
+ * be NULL) counts records whose rc is not AM_OK. */
+int am_healthcheck_classify_batch(const am_healthcheck_t* hcs, uint64_t n, am_record_t* out,
+                                  int32_t* rc_out, int n_threads, uint64_t* n_not_ok);
+
 /* RemedyWorkflow.IsEmpty (api/v1alpha1/healthcheck_types.go:104-106):
  * reflect.DeepEqual against the zero value — note a non-nil empty rbacRules
  * slice is NOT empty. */

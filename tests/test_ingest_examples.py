@@ -48,3 +48,14 @@ def test_every_example_classifies(am):
     # every manifest with a remedyworkflow block is non-empty, the others are empty
     for name, doc in docs.items():
         assert kinds[name][2] == bool((doc.get("spec") or {}).get("remedyworkflow")), name
+
+
+def test_batch_classifier_equals_per_record_calls_on_the_examples(am):
+    ingest = importlib.import_module("active-monitor_b200.ingest")
+    docs = list(_docs().values())
+    rcs, recs = ingest.classify_batch(docs, n_threads=3)
+    assert len(recs) == len(docs)
+    for i, doc in enumerate(docs):
+        rc, rec = ingest.record_from_manifest(doc)
+        assert rc == int(rcs[i])
+        assert rec.tobytes() == recs[i:i + 1].tobytes()
