@@ -22,7 +22,14 @@
 using namespace amsweep;
 
 namespace {
-thread_local std::string g_create_error;
+// Reason of the last failed am_sweep_create, process-wide: a cgo caller may be moved to
+// another OS thread between the failing call and am_last_error_detail(NULL).
+std::mutex g_create_mu;
+std::string g_create_error;
+void set_create_error(const std::string& s) {
+  std::lock_guard<std::mutex> lk(g_create_mu);
+  g_create_error = s;
+}
 
 struct PinnedBuf {
   void* p = nullptr;
@@ -101,7 +108,7 @@ namespace {
     if (_e != cudaSuccess) {                                                          \
       char _b[512];                                                                   \
       snprintf(_b, sizeof _b, "%s -> %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
-      if (h) (h)->last_error = _b; else g_create_error = _b;                          \
+      if (h) (h)->last_error = _b; else set_create_error(_b);                         \
       return _e == cudaErrorMemoryAllocation ? AM_E_NOMEM : AM_E_DEVICE;              \
     }                                                                                 \
   } while (0)
@@ -251,7 +258,11 @@ int launch_sweep(am_sweep* h, int64_t T, uint32_t mode, uint32_t* d_idx, uint8_t
 extern "C" {
 
 const char* am_last_error_detail(const am_sweep_t* h) {
-  return h ? h->last_error.c_str() : g_create_error.c_str();
+  if (h) return h->last_error.c_str();
+  static thread_local std::string copy;  // stable storage for the returned pointer
+  std::lock_guard<std::mutex> lk(g_create_mu);
+  copy = g_create_error;
+  return copy.c_str();
 }
 
 int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t shard_base) {
@@ -261,7 +272,7 @@ int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t
   int ndev = 0;
   AM_CUDA(none, cudaGetDeviceCount(&ndev));
   if (device_id < 0 || device_id >= ndev) {
-    g_create_error = "no such CUDA device";
+    set_create_error("no such CUDA device");
     return AM_E_DEVICE;
   }
   AM_CUDA(none, cudaSetDevice(device_id));
@@ -312,7 +323,7 @@ int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t
     return AM_OK;
   }();
   if (rc != AM_OK) {
-    g_create_error = h->last_error;
+    set_create_error(h->last_error);
     am_sweep_destroy(h);
     return rc;
   }
@@ -534,7 +545,10 @@ int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint3
   h->seed = seed;
   am_tick_stats_t* d_stats = nullptr;
   AM_CUDA(h, cudaMalloc((void**)&d_stats, n_ticks * sizeof(am_tick_stats_t)));
-  AM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  if (cudaError_t e = cudaEventRecord(h->ev0, h->stream); e != cudaSuccess) {
+    h->last_error = cudaGetErrorString(e);
+    rc = AM_E_DEVICE;
+  }
   for (uint64_t k = 0; k < n_ticks && rc == AM_OK; ++k) {
     rc = launch_sweep(h, unix_sec0 + (int64_t)k, mode, h->due_idx[k & 1], h->due_action[k & 1],
                       h->cap_padded, d_stats + k, nullptr, h->stream);

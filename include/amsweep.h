@@ -14,7 +14,9 @@
  *     never throws across the boundary;
  *   - per-record anomalies are DATA (action bit AM_ACT_ANOMALY), not failures;
  *   - there is NO CPU fallback: without a CUDA device am_sweep_create fails
- *     with AM_E_DEVICE.
+ *     with AM_E_DEVICE;
+ *   - every am_sweep_* / am_gather_* call makes the handle's device the
+ *     calling thread's current CUDA device (cudaSetDevice) and leaves it so.
  */
 #ifndef AMSWEEP_H_
 #define AMSWEEP_H_

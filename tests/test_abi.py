@@ -55,6 +55,14 @@ def test_create_fails_loudly_without_gpu(am):
     with pytest.raises(am.AmError) as ei:
         am.Sweep(capacity=1024)
     assert ei.value.code == am.AM_E_DEVICE
+    # the reason is readable from ANY thread afterwards (a cgo caller may have been moved
+    # to another OS thread between the two calls)
+    import threading
+    seen = []
+    t = threading.Thread(target=lambda: seen.append(am.load().am_last_error_detail(None)))
+    t.start()
+    t.join()
+    assert seen and seen[0] and b"cuda" in seen[0].lower()
 
 
 def test_product_never_links_or_imports_the_oracle(am):
