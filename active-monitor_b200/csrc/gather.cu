@@ -506,6 +506,10 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
                    const void* d_count_local, uint64_t shard_base, void* cuda_stream) {
   if (!g || !d_idx_local || !d_act_local || !d_count_local) return AM_E_INVAL;
   if (!g->connected && g->world > 1) return AM_E_INVAL;
+  // validate BEFORE the epoch advances: a rank that bumps its epoch without launching
+  // would leave its peers spinning on counts that never arrive
+  if (g->compressed && shard_base != g->bases[g->rank]) return AM_E_INVAL;
+  if (!g->compressed && g->idx_bytes == 4 && shard_base > 0xFFFFFFFFull) return AM_E_RANGE;
   AMG_CUDA(g, cudaSetDevice(g->device));
   PushParams p{};
   for (int r = 0; r < g->world; ++r) p.peer[r] = g->peer[r];
@@ -519,7 +523,6 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
   g->epoch += 1;
   if (g->epoch == 0) g->epoch = 2;  // keep parity continuity irrelevant: 0 is the "never written" value
   if (g->compressed) {
-    if (shard_base != g->bases[g->rank]) return AM_E_INVAL;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int buf = g->epoch & 1;
     PushC3Params c{};
@@ -559,7 +562,6 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
   p.rank = g->rank;
   p.world = g->world;
   p.idx_bytes = g->idx_bytes;
-  if (p.idx_bytes == 4 && shard_base > 0xFFFFFFFFull) return AM_E_RANGE;
   gather_push_kernel<<<g->n_ctas, 256, 0, (cudaStream_t)cuda_stream>>>(p);
   AMG_CUDA(g, cudaGetLastError());
   return AM_OK;

@@ -291,6 +291,11 @@ void* am_sweep_stream(am_sweep_t*);
  * stream.  When the push kernel retires, out_idx/out_act on EVERY rank hold the
  * global ascending (u64 index, u8 action) list and out_counts[0..world) the
  * per-rank counts, out_counts[world] the total.  No NCCL, no host round-trip.
+ * Like any collective, the push is a rendezvous: every rank must call it the
+ * same number of times; the kernel waits on device for its peers' counts and
+ * done flags (no timeout: a missing peer blocks the stream, as a missing rank
+ * blocks an NCCL collective).  Argument errors are reported before anything
+ * that the peers could observe happens.
  * The reference has no counterpart (single process; consumer is hcc.go:502). */
 #define AM_IPC_HANDLE_BYTES 64
 typedef struct am_gather am_gather_t;
