@@ -29,6 +29,9 @@ ap.add_argument("--sub", type=int, default=10_000)
 ap.add_argument("--full-ticks", type=int, default=60)
 ap.add_argument("--config", type=int, default=5)
 ap.add_argument("--full-scan", action="store_true")
+ap.add_argument("--per-tick", type=int, default=0,
+                help="also time this many ticks one by one (CUDA events around the three kernels of "
+                     "each tick) and report p50 / p99 / max per-tick device time")
 a = ap.parse_args()
 
 am = importlib.import_module("active-monitor_b200")
@@ -45,6 +48,26 @@ with am.Sweep(capacity=a.n) as s:
     wall = time.perf_counter() - t0
     dev_ms = s.last_kernel_ms
     launches = s.launch_count
+
+# per-tick latency distribution: the streaming run above only has a total
+per_tick = None
+if a.per_tick:
+    with am.Sweep(capacity=a.n) as s3:
+        s3.load_range(0, cols)
+        s3.set_seed(seed)
+        bufs = (np.empty(a.n, dtype=np.uint64), np.empty(a.n, dtype=np.uint32))
+        ms = np.empty(a.per_tick)
+        same = True
+        for k in range(a.per_tick):
+            _, _, st = s3.tick(T0 + k, mode=mode, buffers=bufs)
+            ms[k] = s3.last_kernel_ms
+            if k < a.ticks:  # same ticks as the streaming run: statistics must agree
+                same &= all(int(stats[f][k]) == st[f] for f in fields)
+        on = np.arange(a.per_tick) % 60 == 0
+        per_tick = {"ticks": a.per_tick, "equals_streaming_run": bool(same),
+                    "us_p50": float(np.percentile(ms, 50) * 1e3), "us_p99": float(np.percentile(ms, 99) * 1e3),
+                    "us_max": float(ms.max() * 1e3), "us_on_minute_p50": float(np.percentile(ms[on], 50) * 1e3),
+                    "us_off_minute_p50": float(np.percentile(ms[~on], 50) * 1e3) if (~on).any() else None}
 
 # full population, first ticks, against the oracle
 ocols = amgen.fill(a.config, seed, 0, a.n, T0, oracle_c.load().orc_classify)
@@ -90,5 +113,6 @@ print(json.dumps({
     "checksum_xor_of_idx_xor": int(np.bitwise_xor.reduce(stats["idx_xor"])),
     "verified_full_population_ticks": min(a.full_ticks, a.ticks), "full_ok": full_ok,
     "verified_subsample": f"{a.sub} records x {a.ticks} ticks", "sub_ok": sub_ok,
+    "per_tick": per_tick,
     "algorithmic_bytes": int(a.n * (16 * a.ticks + 40 * (a.ticks if a.full_scan else int(on_min.sum())))),
 }))
