@@ -1001,56 +1001,129 @@ int orc_sweep(orc_record_cols_t* cols, uint64_t n, uint64_t shard_base, int64_t 
   return st.n_emitted > cap ? E_NOSPACE : 0;
 }
 
+/* ---- multi-threaded sweep (CPU baseline B2) -------------------
+ * Records are independent, so the array is cut into one contiguous chunk per
+ * thread.  Two passes per chunk, separated by a barrier: (1) evaluate every
+ * record, keep its action byte in a scratch array, count; (2) with the
+ * exclusive prefix of the chunk counts known, write the chunk's entries at
+ * their final positions of the global ascending list.  No serial tail.  The
+ * worker threads are created once and parked between calls. */
+typedef struct {
+  uint64_t n;          /* entries emitted by this chunk */
+  orc_tick_stats_t st;
+  char pad[128];       /* neighbouring slots are written by different threads */
+} mt_slot_t;
+
 typedef struct {
   orc_record_cols_t* cols;
-  uint64_t lo, hi, shard_base;
+  uint64_t n, shard_base;
   int64_t T;
   uint32_t mode;
   uint64_t seed;
-  uint64_t* idx;
-  uint32_t* act;
-  uint64_t n, cap;
-  orc_tick_stats_t st;
-  int oom;
-} mt_job_t;
+  uint64_t* due_idx;
+  uint32_t* due_action;
+  uint64_t cap;
+  uint8_t* act8; /* scratch: the action byte of every record of this tick */
+  mt_slot_t* slot;
+  int nthreads;
+  pthread_barrier_t bar;
+} mt_ctx_t;
 
-static void* mt_worker(void* p) {
-  mt_job_t* j = (mt_job_t*)p;
-  /* thread-private state lives on this thread's stack: the job structs of
-   * neighbouring threads share cache lines */
+static void mt_run_chunk(mt_ctx_t* x, int t) {
+  const uint64_t chunk = (x->n + (uint64_t)x->nthreads - 1) / (uint64_t)x->nthreads;
+  const uint64_t lo = (uint64_t)t * chunk < x->n ? (uint64_t)t * chunk : x->n;
+  const uint64_t hi = lo + chunk < x->n ? lo + chunk : x->n;
+  /* thread-private state on this thread's stack */
   orc_tick_stats_t st;
   memset(&st, 0, sizeof st);
-  orc_record_cols_t cols = *j->cols;
-  uint64_t n = 0, cap = 0, *idx = NULL;
-  uint32_t* act = NULL;
-  const uint64_t base = j->shard_base, seed = j->seed;
-  const int64_t T = j->T;
-  const uint32_t mode = j->mode;
+  orc_record_cols_t cols = *x->cols;
+  const uint64_t base = x->shard_base, seed = x->seed;
+  const int64_t T = x->T;
+  const uint32_t mode = x->mode;
+  uint8_t* act8 = x->act8;
   struct tm tmT;
   utc_tm(T, &tmT);
-  for (uint64_t i = j->lo; i < j->hi; i++) {
+  uint64_t n = 0;
+  for (uint64_t i = lo; i < hi; i++) {
     orc_record_t r;
     gather(&cols, i, &r);
     uint32_t a = tick_record_tm(&r, T, &tmT, mode, seed, base + i, &st);
     scatter(&cols, i, &r);
+    act8[i] = (uint8_t)a; /* every action bit is below 0x100 */
     if (a) {
-      if (n == cap) {
-        uint64_t nc = cap ? cap * 2 : 4096;
-        uint64_t* ni = (uint64_t*)realloc(idx, nc * sizeof *ni);
-        if (ni) idx = ni;
-        uint32_t* na = (uint32_t*)realloc(act, nc * sizeof *na);
-        if (na) act = na;
-        if (!ni || !na) { j->oom = 1; break; }
-        cap = nc;
-      }
-      idx[n] = base + i;
-      act[n] = a;
       n++;
       count_action(&st, a, base + i);
     }
   }
-  j->idx = idx; j->act = act; j->n = n; j->cap = cap; j->st = st;
+  x->slot[t].n = n;
+  x->slot[t].st = st;
+  pthread_barrier_wait(&x->bar);
+  uint64_t pos = 0;
+  for (int u = 0; u < t; u++) pos += x->slot[u].n;
+  uint64_t* di = x->due_idx;
+  uint32_t* da = x->due_action;
+  const uint64_t cap = x->cap;
+  if ((!di && !da) || pos >= cap) return;
+  for (uint64_t i = lo; i < hi; i++) {
+    const uint8_t a = act8[i];
+    if (!a) continue;
+    if (pos >= cap) break;
+    if (di) di[pos] = base + i;
+    if (da) da[pos] = a;
+    pos++;
+  }
+}
+
+/* parked workers: index k runs chunk k+1 of every job that uses more than k+1 threads */
+static struct {
+  pthread_mutex_t call;  /* one MT sweep at a time */
+  pthread_mutex_t mu;
+  pthread_cond_t start, done;
+  pthread_t* th;
+  int n_workers;
+  uint64_t gen;
+  int remaining;
+  mt_ctx_t* ctx;
+} g_pool = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER,
+            PTHREAD_COND_INITIALIZER, NULL, 0, 0, 0, NULL};
+
+typedef struct { int k; uint64_t seen; } mt_worker_arg_t;
+
+static void* mt_pool_worker(void* p) {
+  mt_worker_arg_t arg = *(mt_worker_arg_t*)p;
+  free(p);
+  uint64_t seen = arg.seen;
+  for (;;) {
+    pthread_mutex_lock(&g_pool.mu);
+    while (g_pool.gen == seen) pthread_cond_wait(&g_pool.start, &g_pool.mu);
+    seen = g_pool.gen;
+    mt_ctx_t* x = g_pool.ctx;
+    pthread_mutex_unlock(&g_pool.mu);
+    const int mine = arg.k + 1 < x->nthreads;
+    if (mine) mt_run_chunk(x, arg.k + 1);
+    pthread_mutex_lock(&g_pool.mu);
+    if (--g_pool.remaining == 0) pthread_cond_signal(&g_pool.done);
+    pthread_mutex_unlock(&g_pool.mu);
+  }
   return NULL;
+}
+
+/* make sure `want` workers exist; returns how many do (called with g_pool.call held, no job posted) */
+static int mt_pool_grow(int want) {
+  if (want <= g_pool.n_workers) return g_pool.n_workers;
+  pthread_t* nt = (pthread_t*)realloc(g_pool.th, (size_t)want * sizeof *nt);
+  if (!nt) return g_pool.n_workers;
+  g_pool.th = nt;
+  while (g_pool.n_workers < want) {
+    mt_worker_arg_t* a = (mt_worker_arg_t*)malloc(sizeof *a);
+    if (!a) break;
+    a->k = g_pool.n_workers;
+    a->seen = g_pool.gen;
+    if (pthread_create(&g_pool.th[g_pool.n_workers], NULL, mt_pool_worker, a) != 0) { free(a); break; }
+    pthread_detach(g_pool.th[g_pool.n_workers]);
+    g_pool.n_workers++;
+  }
+  return g_pool.n_workers;
 }
 
 int orc_sweep_mt(orc_record_cols_t* cols, uint64_t n, uint64_t shard_base, int64_t T,
@@ -1058,48 +1131,53 @@ int orc_sweep_mt(orc_record_cols_t* cols, uint64_t n, uint64_t shard_base, int64
                  uint64_t cap, uint64_t* n_out, orc_tick_stats_t* stats, int nthreads) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 1024) nthreads = 1024;
-  mt_job_t* jobs = (mt_job_t*)calloc((size_t)nthreads, sizeof *jobs);
-  pthread_t* th = (pthread_t*)calloc((size_t)nthreads, sizeof *th);
-  if (!jobs || !th) { free(jobs); free(th); return -5; }
-  uint64_t chunk = (n + (uint64_t)nthreads - 1) / (uint64_t)nthreads;
-  for (int t = 0; t < nthreads; t++) {
-    mt_job_t* j = &jobs[t];
-    j->cols = cols; j->shard_base = shard_base; j->T = T; j->mode = mode; j->seed = seed;
-    j->lo = (uint64_t)t * chunk < n ? (uint64_t)t * chunk : n;
-    j->hi = j->lo + chunk < n ? j->lo + chunk : n;
+  if (n < (uint64_t)nthreads) nthreads = n ? (int)n : 1;
+  pthread_mutex_lock(&g_pool.call);
+  const int have = 1 + mt_pool_grow(nthreads - 1); /* the caller's thread + parked workers */
+  if (have < nthreads) nthreads = have;
+  mt_ctx_t x;
+  memset(&x, 0, sizeof x);
+  x.cols = cols; x.n = n; x.shard_base = shard_base; x.T = T; x.mode = mode; x.seed = seed;
+  x.due_idx = due_idx; x.due_action = due_action; x.cap = cap; x.nthreads = nthreads;
+  x.act8 = (uint8_t*)malloc(n ? n : 1);
+  x.slot = (mt_slot_t*)calloc((size_t)nthreads, sizeof *x.slot);
+  if (!x.act8 || !x.slot || pthread_barrier_init(&x.bar, NULL, (unsigned)nthreads) != 0) {
+    free(x.act8); free(x.slot);
+    pthread_mutex_unlock(&g_pool.call);
+    return -5;
   }
-  /* chunks 1.. on their own threads, chunk 0 on the caller's */
-  for (int t = 1; t < nthreads; t++) pthread_create(&th[t], NULL, mt_worker, &jobs[t]);
-  mt_worker(&jobs[0]);
-  for (int t = 1; t < nthreads; t++) pthread_join(th[t], NULL);
+  /* post the job: every parked worker wakes up, those beyond nthreads only acknowledge */
+  pthread_mutex_lock(&g_pool.mu);
+  g_pool.ctx = &x;
+  g_pool.remaining = g_pool.n_workers;
+  g_pool.gen++;
+  pthread_cond_broadcast(&g_pool.start);
+  pthread_mutex_unlock(&g_pool.mu);
+  mt_run_chunk(&x, 0); /* chunk 0 on the caller's thread */
+  pthread_mutex_lock(&g_pool.mu);
+  while (g_pool.remaining != 0) pthread_cond_wait(&g_pool.done, &g_pool.mu);
+  g_pool.ctx = NULL;
+  pthread_mutex_unlock(&g_pool.mu);
+  pthread_barrier_destroy(&x.bar);
+
   orc_tick_stats_t st;
   memset(&st, 0, sizeof st);
-  st.n_records = n;
   uint64_t pos = 0;
-  int oom = 0;
   for (int t = 0; t < nthreads; t++) {
-    mt_job_t* j = &jobs[t];
-    oom |= j->oom;
-    for (uint64_t k = 0; k < j->n; k++, pos++) {
-      if (pos < cap) {
-        if (due_idx) due_idx[pos] = j->idx[k];
-        if (due_action) due_action[pos] = j->act[k];
-      }
-    }
-    const uint64_t* a = (const uint64_t*)&j->st;
+    pos += x.slot[t].n;
+    const uint64_t* a = (const uint64_t*)&x.slot[t].st;
     uint64_t* d = (uint64_t*)&st;
     for (size_t q = 1; q < sizeof st / sizeof(uint64_t); q++) {
       if (q == 14) d[q] ^= a[q]; /* idx_xor */
       else d[q] += a[q];
     }
-    free(j->idx);
-    free(j->act);
   }
-  free(jobs);
-  free(th);
+  st.n_records = n;
+  free(x.act8);
+  free(x.slot);
+  pthread_mutex_unlock(&g_pool.call);
   if (n_out) *n_out = pos;
   if (stats) *stats = st;
-  if (oom) return -5;
   return pos > cap ? E_NOSPACE : 0;
 }
 

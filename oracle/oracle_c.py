@@ -101,21 +101,31 @@ def cols_struct(cols: dict) -> OrcCols:
     return s
 
 
-def sweep(cols: dict, T: int, mode: int = 0, seed: int = 0, shard_base: int = 0, threads: int = 1):
+def sweep(cols: dict, T: int, mode: int = 0, seed: int = 0, shard_base: int = 0, threads: int = 1,
+          buffers=None):
     """Run the oracle over numpy SoA columns IN PLACE.
-    Returns (global idx u64[n], action u32[n], stats dict)."""
+    Returns (global idx u64[n], action u32[n], stats dict).  With `buffers=(idx u64[cap],
+    act u32[cap])` the lists are written there and VIEWS are returned (no allocation, no copy:
+    the form the timed CPU baseline uses)."""
     n = len(cols["flags"])
-    idx = np.empty(n, dtype=np.uint64)
-    act = np.empty(n, dtype=np.uint32)
+    if buffers is None:
+        idx = np.empty(n, dtype=np.uint64)
+        act = np.empty(n, dtype=np.uint32)
+    else:
+        idx, act = buffers
+        assert idx.dtype == np.uint64 and act.dtype == np.uint32 and len(idx) == len(act)
+    cap = len(idx)
     cnt = u64(0)
     st = OrcStats()
     cs = cols_struct(cols)
     lib = load()
     if threads <= 1:
         rc = lib.orc_sweep(C.byref(cs), n, shard_base, T, mode, seed, idx.ctypes.data,
-                           act.ctypes.data, n, C.byref(cnt), C.byref(st))
+                           act.ctypes.data, cap, C.byref(cnt), C.byref(st))
     else:
         rc = lib.orc_sweep_mt(C.byref(cs), n, shard_base, T, mode, seed, idx.ctypes.data,
-                              act.ctypes.data, n, C.byref(cnt), C.byref(st), threads)
+                              act.ctypes.data, cap, C.byref(cnt), C.byref(st), threads)
     assert rc == 0, rc
+    if buffers is not None:
+        return idx[:cnt.value], act[:cnt.value], st.as_dict()
     return idx[:cnt.value].copy(), act[:cnt.value].copy(), st.as_dict()

@@ -412,6 +412,59 @@ def test_sweep_mt_equals_single_thread(orc, gen):
         np.testing.assert_array_equal(a[k], b[k])
 
 
+@pytest.mark.parametrize("threads", [2, 3, 16, 200])
+@pytest.mark.parametrize("n", [1, 5, 4097])
+def test_sweep_mt_thread_counts_and_tiny_inputs(orc, gen, n, threads):
+    """More threads than records, thread counts that grow and shrink between calls (the
+    workers are parked and reused), closed loop, a short output buffer."""
+    a = gen.fill(55, 5, 0, n, T0, orc.load().orc_classify)
+    b = {k: v.copy() for k, v in a.items()}
+    for k in range(3):
+        ia, aa, sa = orc.sweep(a, T0 + k, mode=1, seed=5, threads=1)
+        ib, ab, sb = orc.sweep(b, T0 + k, mode=1, seed=5, threads=threads)
+        assert sa == sb
+        np.testing.assert_array_equal(ia, ib)
+        np.testing.assert_array_equal(aa, ab)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k])
+    # short caller buffers: E_NOSPACE, the first `cap` entries valid, the count is the need
+    import ctypes as C
+    c = gen.fill(1, 1, 0, 4097, T0, orc.load().orc_classify)
+    want_idx, _, want_st = orc.sweep({k: v.copy() for k, v in c.items()}, T0, threads=1)
+    cap = 10
+    idx = np.zeros(cap, np.uint64)
+    act = np.zeros(cap, np.uint32)
+    cnt, st = C.c_uint64(0), orc.OrcStats()
+    cs = orc.cols_struct(c)
+    rc = orc.load().orc_sweep_mt(C.byref(cs), 4097, 0, T0, 0, 0, idx.ctypes.data, act.ctypes.data, cap,
+                                 C.byref(cnt), C.byref(st), threads)
+    assert rc == -3 and cnt.value == len(want_idx) > cap
+    np.testing.assert_array_equal(idx, want_idx[:cap])
+    assert st.as_dict() == want_st
+
+
+def test_sweep_mt_concurrent_callers_are_serialised(orc, gen):
+    import threading
+    n = 20_000
+    base = gen.fill(2, 2, 0, n, T0, orc.load().orc_classify)
+    want = orc.sweep({k: v.copy() for k, v in base.items()}, T0, threads=1)
+    out = [None] * 4
+
+    def run(j):
+        out[j] = orc.sweep({k: v.copy() for k, v in base.items()}, T0, threads=3 + j)
+
+    th = [threading.Thread(target=run, args=(j,)) for j in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+        assert not t.is_alive()
+    for o in out:
+        np.testing.assert_array_equal(o[0], want[0])
+        np.testing.assert_array_equal(o[1], want[1])
+        assert o[2] == want[2]
+
+
 def test_closed_loop_oracles_agree(orc, opy, gen):
     n, seed = 1500, 5
     cols = gen.fill(55, seed, 0, n, T0, orc.load().orc_classify)
