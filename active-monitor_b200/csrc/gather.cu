@@ -187,8 +187,9 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const PushParams p) {
 // count per group; every receiver scans the counts and expands
 //   global index = base[rank] + 8192 * group + offset
 // locally into its final index list (the action bytes already sit in their final
-// place; the prefix sum over the group counts is folded into the expansion kernel).  The expansion costs 6 B of local HBM traffic per entry, the exchange
-// saves 2 B of NVLink traffic per entry per peer — NVLink is the scarce resource.
+// place; the prefix sum over the group counts is folded into the expansion kernel).
+// The expansion costs 6 B of local HBM traffic per entry, the exchange saves 2 B of
+// NVLink traffic per entry per peer — NVLink is the scarce resource.
 // ---------------------------------------------------------------------------
 constexpr uint32_t kGroupRecords = 8192;
 
@@ -256,7 +257,8 @@ __global__ void __launch_bounds__(256) gather_push_c3_kernel(const PushC3Params 
     for (uint32_t sb = first_sb; sb < n_search; sb += (split ? n_search : gridDim.x)) {
       const uint32_t g0 = sb * 255u;
       const uint32_t gb = g0 + (uint32_t)tid;  // boundary index
-      s_bound[tid] = gb <= p.ngroups_mine ? lower_bound_idx(p.idx_local, n, gb * kGroupRecords) : n;
+      // the boundary after the last group is n by definition (and gb * 8192 could wrap there)
+      s_bound[tid] = gb < p.ngroups_mine ? lower_bound_idx(p.idx_local, n, gb * kGroupRecords) : n;
       __syncthreads();
       if (tid < 255 && g0 + (uint32_t)tid < p.ngroups_mine) {
         const uint32_t cnt = s_bound[tid + 1] - s_bound[tid];
