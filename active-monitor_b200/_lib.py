@@ -36,6 +36,7 @@ ACT_REMEDY_SKIP, ACT_RESET_ON_PASS, ACT_RESET_ON_INTERVAL, ACT_ANOMALY = 0x10, 0
 SWEEP_CLOSED_LOOP, SWEEP_FULL_SCAN = 0x1, 0x2
 PHASE_NONE, PHASE_SUCCEEDED, PHASE_FAILED = 0, 1, 2
 IPC_HANDLE_BYTES = 64
+WIRE_PLAIN, WIRE_C3, WIRE_BITMAP = 0, 1, 2
 
 
 class AmCron(C.Structure):
@@ -145,6 +146,7 @@ SYMBOLS = {
     "am_gather_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "am_gather_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "am_gather_set_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "am_gather_set_wire": (C.c_int, [C.c_void_p, C.c_int]),
     "am_gather_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, u64, C.c_void_p]),
     "am_gather_out_idx": (C.c_void_p, [C.c_void_p]),
     "am_gather_out_act": (C.c_void_p, [C.c_void_p]),

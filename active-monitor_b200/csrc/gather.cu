@@ -386,6 +386,227 @@ __global__ void __launch_bounds__(256) gather_decode_kernel(const DecodeParams p
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Bitmap wire format ("bm") — EXPERIMENTAL: written after the round-1 GPU budget was
+// spent, compiled but not yet executed on hardware; nothing selects it by default.
+//
+// The NVLink volume, not the sweep, bounds the step from 4 GPUs up (profiles/
+// r01_scaling.md), and the payload is far more compressible than c3's 3 B/entry:
+//   * the emitted SET of a shard is one bit per record (1 KB per 8192-record group):
+//     at 33 % density 3 bits per entry instead of 16;
+//   * almost every action byte is the bare AM_ACT_SUBMIT_HC: every receiver pre-fills
+//     its action list with that default (stream-ordered before its own push, hence
+//     before any peer can write this epoch) and senders skip destination quads that
+//     hold nothing else.  A workload of non-default actions degrades to 1 B/entry.
+// Receivers rebuild the global index list from the eight bitmaps with a popcount
+// prefix per group (gather_expand_bitmap_kernel), starting each group at the sum of
+// the sender's earlier group counts, as in c3.
+// ---------------------------------------------------------------------------
+constexpr uint32_t kGroupWords = kGroupRecords / 32;  // 256 bitmap words per group
+constexpr uint32_t kDefaultAction4 = 0x01010101u * AM_ACT_SUBMIT_HC;
+
+struct PushBmParams {
+  unsigned char* peer[kMaxWorld];
+  const uint32_t* idx_local;
+  const uint8_t* act_local;
+  const uint32_t* count_local;
+  uint32_t* out_counts;
+  uint64_t cap_total;
+  size_t off_act[2], off_gc[2], off_bm[2];
+  uint64_t bm_word0;      // first bitmap word of this rank's row (sum of earlier ranks' groups * 256)
+  uint32_t epoch;
+  uint32_t ngroups_mine;
+  uint32_t ngroups_max;
+  int rank, world;
+};
+
+__global__ void __launch_bounds__(256) gather_push_bm_kernel(const PushBmParams p) {
+  __shared__ uint32_t s_count[kMaxWorld];
+  __shared__ uint32_t s_bound[256];
+  __shared__ uint32_t s_bm[kGroupWords];
+  const int tid = threadIdx.x;
+  ExchangeHeader* mine = reinterpret_cast<ExchangeHeader*>(p.peer[p.rank]);
+  const uint32_t my_count = *p.count_local;
+  const int buf = p.epoch & 1;
+
+  if (blockIdx.x == 0 && tid < p.world) {  // 1. publish my count
+    ExchangeHeader* peer = reinterpret_cast<ExchangeHeader*>(p.peer[tid]);
+    st_release_sys(&peer->count_slot[p.rank], ((unsigned long long)p.epoch << 32) | my_count);
+  }
+  if (tid < p.world) {  // 2. everyone's counts
+    unsigned long long v;
+    do { v = ld_acquire_sys(&mine->count_slot[tid]); } while ((uint32_t)(v >> 32) != p.epoch);
+    s_count[tid] = (uint32_t)v;
+  }
+  __syncthreads();
+  uint64_t offset = 0, total = 0;
+  for (int r = 0; r < p.world; ++r) {
+    if (r < p.rank) offset += s_count[r];
+    total += s_count[r];
+  }
+  const uint64_t room = offset < p.cap_total ? p.cap_total - offset : 0;
+  const uint32_t n = (uint32_t)(my_count < room ? my_count : room);
+
+  // 3a. bitmaps + group counts.  Every CTA owns a contiguous run of this shard's groups,
+  //     taken in batches of up to 255: 256 threads find the batch's boundaries in the
+  //     ascending list (one binary search each, in parallel), then the CTA builds one
+  //     group's 256-word bitmap at a time in shared memory and stores it to every rank.
+  const uint32_t per_cta = (p.ngroups_mine + gridDim.x - 1) / gridDim.x;
+  const uint32_t g_first = blockIdx.x * per_cta;
+  const uint32_t g_last = g_first + per_cta < p.ngroups_mine ? g_first + per_cta : p.ngroups_mine;
+  for (uint32_t b0 = g_first; b0 < g_last; b0 += 255u) {
+    const uint32_t nb = g_last - b0 < 255u ? g_last - b0 : 255u;  // groups in this batch
+    if ((uint32_t)tid <= nb) {
+      const uint32_t gb = b0 + (uint32_t)tid;
+      s_bound[tid] = gb < p.ngroups_mine ? lower_bound_idx(p.idx_local, n, gb * kGroupRecords) : n;
+    }
+    __syncthreads();
+    if ((uint32_t)tid < nb) {
+      const uint32_t cnt = s_bound[tid + 1] - s_bound[tid];
+      for (int r = 0; r < p.world; ++r)
+        reinterpret_cast<uint32_t*>(p.peer[r] + p.off_gc[buf])[(size_t)p.rank * p.ngroups_max + b0 + tid] = cnt;
+    }
+    for (uint32_t k = 0; k < nb; ++k) {
+      s_bm[tid] = 0u;  // blockDim.x == kGroupWords
+      __syncthreads();
+      const uint32_t lo = s_bound[k], hi = s_bound[k + 1];
+      for (uint32_t e = lo + (uint32_t)tid; e < hi; e += blockDim.x) {
+        const uint32_t o = __ldcs(p.idx_local + e) & (kGroupRecords - 1u);
+        atomicOr(&s_bm[o >> 5], 1u << (o & 31u));
+      }
+      __syncthreads();
+      const uint32_t w = s_bm[tid];
+      const uint64_t word = p.bm_word0 + (uint64_t)(b0 + k) * kGroupWords + (uint64_t)tid;
+      for (int r = 0; r < p.world; ++r)
+        reinterpret_cast<uint32_t*>(p.peer[r] + p.off_bm[buf])[word] = w;
+      __syncthreads();  // s_bm is re-zeroed by the next group
+    }
+  }
+
+  // 3b. actions, destination-aligned quads as in the other formats, except that a quad (or a
+  //     ragged byte) holding only the default action is not sent: the receiver pre-filled it.
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  const uint64_t q_lo = offset / 4, q_hi = (offset + n + 3) / 4;
+  for (uint64_t q0 = q_lo + blockIdx.x * (uint64_t)blockDim.x + tid; q0 < q_hi; q0 += 4 * stride) {
+    uint32_t ga[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t q = q0 + (uint64_t)u * stride;
+      ga[u] = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t pos = 4 * q + k;
+        const bool ok = q < q_hi && pos >= offset && pos < offset + n;
+        ga[u] |= (ok ? (uint32_t)__ldcs(p.act_local + (pos - offset)) : 0u) << (8 * k);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t q = q0 + (uint64_t)u * stride;
+      if (q >= q_hi) continue;
+      const bool full = 4 * q >= offset && 4 * q + 4 <= offset + n;
+      if (full) {
+        if (ga[u] == kDefaultAction4) continue;
+        for (int r = 0; r < p.world; ++r)
+          reinterpret_cast<uint32_t*>(p.peer[r] + p.off_act[buf])[q] = ga[u];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint64_t pos = 4 * q + k;
+          if (pos < offset || pos >= offset + n) continue;
+          const uint8_t a = (uint8_t)(ga[u] >> (8 * k));
+          if (a == (uint8_t)AM_ACT_SUBMIT_HC) continue;
+          for (int r = 0; r < p.world; ++r) (p.peer[r] + p.off_act[buf])[pos] = a;
+        }
+      }
+    }
+  }
+  // 4. completion, as in the plain format
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) {
+    const unsigned int ticket = atomicAdd(&mine->cta_done, 1u);
+    if (ticket == gridDim.x - 1) {
+      __threadfence_system();
+      for (int r = 0; r < p.world; ++r) {
+        ExchangeHeader* peer = reinterpret_cast<ExchangeHeader*>(p.peer[r]);
+        st_release_sys(&peer->done_slot[p.rank], (unsigned long long)p.epoch);
+      }
+      for (int r = 0; r < p.world; ++r) {
+        while (ld_acquire_sys(&mine->done_slot[r]) != (unsigned long long)p.epoch) {}
+      }
+      for (int r = 0; r < p.world; ++r) p.out_counts[r] = s_count[r];
+      p.out_counts[p.world] = (uint32_t)(total < p.cap_total ? total : p.cap_total);
+      mine->cta_done = 0;
+      __threadfence();
+    }
+  }
+}
+
+// Receiver: one CTA per (rank, group) turns the group's 256 bitmap words back into
+// ascending global indices.  Start position as in gather_decode_kernel; in-group rank of
+// a word = exclusive prefix of the popcounts (warp shuffles + 8 warp totals); the indices
+// are staged in shared memory so that the stores to the final list are coalesced.
+struct ExpandBmParams {
+  const uint32_t* bm;        // bitmap area of my exchange block (all ranks' rows)
+  const uint32_t* gc;        // [world][ngroups_max]
+  const uint32_t* counts;    // out_counts
+  void* final_idx;
+  uint64_t bases[kMaxWorld];
+  uint64_t bm_word0[kMaxWorld];
+  uint32_t ngroups[kMaxWorld];
+  uint64_t cap_total;
+  uint32_t ngroups_max;
+  int world, idx_bytes;
+};
+__global__ void __launch_bounds__(256) gather_expand_bitmap_kernel(const ExpandBmParams p) {
+  __shared__ uint32_t s_part[8];
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_off[kGroupRecords];  // in-group offsets of the set bits, ascending
+  const int r = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t g = blockIdx.x;
+  if (g >= p.ngroups[r]) return;  // uniform per CTA
+  const uint32_t* row = p.gc + (size_t)r * p.ngroups_max;
+  uint32_t part = 0;
+  for (uint32_t j = tid; j < g; j += blockDim.x) part += row[j];
+  part = __reduce_add_sync(0xFFFFFFFFu, part);
+  uint32_t w = __ldcs(p.bm + p.bm_word0[r] + (uint64_t)g * kGroupWords + (uint64_t)tid);
+  const uint32_t c = (uint32_t)__popc(w);
+  uint32_t inc = c;  // inclusive scan of the popcounts within the warp
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+    if (lane >= d) inc += v;
+  }
+  if (lane == 0) s_part[warp] = part;
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  uint64_t start = 0;
+  uint32_t before = 0, cnt = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    start += s_part[k];
+    before += k < warp ? s_warp[k] : 0u;
+    cnt += s_warp[k];
+  }
+  for (int q = 0; q < r; ++q) start += p.counts[q];
+  uint32_t pos = before + inc - c;  // exclusive prefix of this thread's word
+  while (w) {
+    const uint32_t b = (uint32_t)__ffs((int)w) - 1u;
+    w &= w - 1u;
+    s_off[pos++] = (uint32_t)tid * 32u + b;
+  }
+  __syncthreads();
+  const uint64_t gbase = p.bases[r] + (uint64_t)g * kGroupRecords;
+  for (uint32_t e = tid; e < cnt; e += blockDim.x) {
+    if (start + e >= p.cap_total) break;
+    const uint64_t v = gbase + s_off[e];
+    if (p.idx_bytes == 4) reinterpret_cast<uint32_t*>(p.final_idx)[start + e] = (uint32_t)v;
+    else reinterpret_cast<uint64_t*>(p.final_idx)[start + e] = v;
+  }
+}
+
 }  // namespace
 
 struct am_gather {
@@ -408,6 +629,10 @@ struct am_gather {
   uint64_t bases[kMaxWorld] = {}, sizes[kMaxWorld] = {};
   uint32_t ngroups[kMaxWorld] = {};
   void* final_idx[2] = {nullptr, nullptr};  // expanded global indices, by epoch parity
+  // bitmap wire format (am_gather_set_wire(AM_WIRE_BITMAP) after set_layout; experimental)
+  int wire = AM_WIRE_PLAIN;
+  size_t off_bm[2] = {0, 0};
+  uint64_t bm_word0[kMaxWorld] = {};
   std::string last_error;
 };
 
@@ -441,6 +666,12 @@ int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_
   g->ngroups_max = (uint32_t)((cap_total + kGroupRecords - 1) / kGroupRecords);
   for (int b = 0; b < 2; ++b) { g->off_gc[b] = off; off = align(off + (size_t)world * g->ngroups_max * 4); }
   for (int b = 0; b < 2; ++b) { g->off_o16[b] = off; off = align(off + cap_total * 2); }
+  // bitmap wire format: one 1 KB bitmap per 8192-record group of every shard (at most
+  // ngroups_max + world groups in total, whatever the split)
+  for (int b = 0; b < 2; ++b) {
+    g->off_bm[b] = off;
+    off = align(off + ((size_t)g->ngroups_max + (size_t)world) * kGroupWords * 4);
+  }
   g->block_bytes = off;
   int rc = [&]() -> int {
     AMG_CUDA(g, cudaSetDevice(device));
@@ -498,9 +729,24 @@ int am_gather_set_layout(am_gather_t* g, const uint64_t* bases, const uint64_t* 
     g->sizes[r] = sizes[r];
     g->ngroups[r] = (uint32_t)ng;
   }
+  uint64_t groups_before = 0;
+  for (int r = 0; r < g->world; ++r) {
+    g->bm_word0[r] = groups_before * kGroupWords;
+    groups_before += g->ngroups[r];
+  }
+  if (groups_before > (uint64_t)g->ngroups_max + (uint64_t)g->world) return AM_E_RANGE;
   for (int b = 0; b < 2; ++b)
     if (!g->final_idx[b]) AMG_CUDA(g, cudaMalloc(&g->final_idx[b], g->cap_total * (size_t)g->idx_bytes));
   g->compressed = true;
+  g->wire = AM_WIRE_C3;
+  return AM_OK;
+}
+
+int am_gather_set_wire(am_gather_t* g, int wire) {
+  if (!g) return AM_E_INVAL;
+  if (wire != AM_WIRE_C3 && wire != AM_WIRE_BITMAP) return AM_E_INVAL;  // plain = never call set_layout
+  if (!g->compressed) return AM_E_INVAL;                              // needs the shard layout
+  g->wire = wire;
   return AM_OK;
 }
 
@@ -524,6 +770,47 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
   for (int b = 0; b < 2; ++b) { p.off_idx[b] = g->off_idx[b]; p.off_act[b] = g->off_act[b]; }
   g->epoch += 1;
   if (g->epoch == 0) g->epoch = 2;  // keep parity continuity irrelevant: 0 is the "never written" value
+  if (g->compressed && g->wire == AM_WIRE_BITMAP) {
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int buf = g->epoch & 1;
+    // default actions: stream-ordered before this rank publishes its count, hence before any
+    // peer stores a non-default action of this epoch into the buffer
+    AMG_CUDA(g, cudaMemsetAsync(g->block + g->off_act[buf], (int)AM_ACT_SUBMIT_HC, g->cap_total, st));
+    PushBmParams b{};
+    for (int r = 0; r < g->world; ++r) b.peer[r] = g->peer[r];
+    b.idx_local = (const uint32_t*)d_idx_local;
+    b.act_local = (const uint8_t*)d_act_local;
+    b.count_local = (const uint32_t*)d_count_local;
+    b.out_counts = g->out_counts;
+    b.cap_total = g->cap_total;
+    for (int k = 0; k < 2; ++k) { b.off_act[k] = g->off_act[k]; b.off_gc[k] = g->off_gc[k]; b.off_bm[k] = g->off_bm[k]; }
+    b.bm_word0 = g->bm_word0[g->rank];
+    b.epoch = g->epoch;
+    b.ngroups_mine = g->ngroups[g->rank];
+    b.ngroups_max = g->ngroups_max;
+    b.rank = g->rank;
+    b.world = g->world;
+    gather_push_bm_kernel<<<g->n_ctas, 256, 0, st>>>(b);
+    ExpandBmParams x{};
+    x.bm = reinterpret_cast<const uint32_t*>(g->block + g->off_bm[buf]);
+    x.gc = reinterpret_cast<const uint32_t*>(g->block + g->off_gc[buf]);
+    x.counts = g->out_counts;
+    x.final_idx = g->final_idx[buf];
+    x.cap_total = g->cap_total;
+    x.ngroups_max = g->ngroups_max;
+    x.world = g->world;
+    x.idx_bytes = g->idx_bytes;
+    uint32_t ng_used = 1;
+    for (int r = 0; r < g->world; ++r) {
+      x.ngroups[r] = g->ngroups[r];
+      x.bases[r] = g->bases[r];
+      x.bm_word0[r] = g->bm_word0[r];
+      if (g->ngroups[r] > ng_used) ng_used = g->ngroups[r];
+    }
+    gather_expand_bitmap_kernel<<<dim3(ng_used, g->world), 256, 0, st>>>(x);
+    AMG_CUDA(g, cudaGetLastError());
+    return AM_OK;
+  }
   if (g->compressed) {
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int buf = g->epoch & 1;

@@ -64,10 +64,14 @@ class PeerGather:
     CUDA-IPC handles."""
 
     def __init__(self, device_index: int, cap_total: int, group=None, idx_bytes: int = 8,
-                 shard=None):
+                 shard=None, wire: str = "c3"):
         """shard=(first global index, number of records) of this rank switches on the
         compressed wire format (3 B per entry over NVLink: u16 offsets within
-        8192-record groups + per-group counts, expanded on every receiver)."""
+        8192-record groups + per-group counts, expanded on every receiver).
+        wire="bm" (with `shard`) selects the EXPERIMENTAL bitmap format instead (one bit
+        per record + non-default actions only; not yet run on hardware)."""
+        if wire not in ("c3", "bm"):
+            raise ValueError("wire must be 'c3' or 'bm'")
         import ctypes as C
 
         from . import _lib as L
@@ -117,6 +121,9 @@ class PeerGather:
             sizes = np.ascontiguousarray(lay[:, 1])
             rc = self._lib.am_gather_set_layout(self._h, bases.ctypes.data, sizes.ctypes.data)
             agree(rc == 0, "am_gather_set_layout")
+            if wire == "bm":
+                rc = self._lib.am_gather_set_wire(self._h, L.WIRE_BITMAP)
+                agree(rc == 0, "am_gather_set_wire")
 
     def _check(self, rc, where):
         if rc != 0:

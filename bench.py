@@ -172,11 +172,12 @@ def main():
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="records per GPU")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--wire", default="auto", choices=["auto", "plain", "c3"],
+    ap.add_argument("--wire", default="auto", choices=["auto", "plain", "c3", "bm"],
                     help="peer gather wire format: plain = u32 index + u8 action (5 B/entry), "
                          "c3 = u16 group offset + u8 action + per-group counts (3 B/entry), expanded on the "
                          "receiver; auto = c3 from 4 GPUs up (NVLink-volume-bound), plain below "
-                         "(profiles/r01_scaling.md)")
+                         "(profiles/r01_scaling.md); bm = EXPERIMENTAL bitmap format (1 bit per record + "
+                         "non-default actions), never chosen by auto")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="N>1: NVLink peer-write kernel (csrc/gather.cu) or the padded NCCL all-gather")
     args = ap.parse_args()
@@ -228,7 +229,8 @@ def main():
         try:
             peer = gather.PeerGather(local_rank, cap_total=n * world,
                                      idx_bytes=4 if n * world < (1 << 32) else 8,
-                                     shard=(base, n) if args.wire == "c3" else None)
+                                     shard=(base, n) if args.wire in ("c3", "bm") else None,
+                                     wire="bm" if args.wire == "bm" else "c3")
         except Exception as e:  # noqa: BLE001
             print(f"[bench] rank {rank}: peer-write gather unavailable ({e}); using NCCL", file=sys.stderr)
             ok = 0

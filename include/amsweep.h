@@ -310,6 +310,15 @@ int am_gather_connect(am_gather_t*, const void* handles /* world x AM_IPC_HANDLE
  * expanded by each receiver into the same output as the plain format).  bases[r] /
  * sizes[r] = first global index / number of records of rank r's shard. */
 int am_gather_set_layout(am_gather_t*, const uint64_t* bases, const uint64_t* sizes);
+/* Wire formats.  PLAIN is what a handle uses until set_layout is called; set_layout
+ * selects C3.  BITMAP (after set_layout) is EXPERIMENTAL — one bit per record for the
+ * emitted set plus only the non-default action bytes, ~0.4 B per entry at the bench
+ * density; implemented after the round-1 GPU budget was spent and not yet run on
+ * hardware, so nothing selects it by default. */
+#define AM_WIRE_PLAIN 0
+#define AM_WIRE_C3 1
+#define AM_WIRE_BITMAP 2
+int am_gather_set_wire(am_gather_t*, int wire);
 int am_gather_push(am_gather_t*, const void* d_idx_local /* u32 */, const void* d_act_local /* u8 */,
                    const void* d_count_local /* u32 */, uint64_t shard_base, void* cuda_stream);
 void* am_gather_out_idx(am_gather_t*);    /* u64|u32[cap_total], valid after the last push retires */

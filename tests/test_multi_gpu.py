@@ -44,7 +44,8 @@ def _worker(rank, world, port, n_total, ticks, wire, q):
             s.load_range(0, cols)
             # u32 global indices on worlds divisible by 4, u64 otherwise; wire = plain | c3 (compressed)
             pg = gather.PeerGather(rank, cap_total=n_total, idx_bytes=4 if world % 4 == 0 else 8,
-                                   shard=(first, cnt) if wire == "c3" else None)
+                                   shard=(first, cnt) if wire in ("c3", "bm") else None,
+                                   wire="bm" if wire == "bm" else "c3")
             d_idx = torch.empty(cnt, dtype=torch.int32, device=dev)
             d_act = torch.empty(cnt, dtype=torch.uint8, device=dev)
             d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -67,7 +68,11 @@ def _worker(rank, world, port, n_total, ticks, wire, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("wire", ["plain", "c3"])
+# "bm" (experimental bitmap wire format, not yet run on hardware) only on request
+WIRES = ["plain", "c3"] + (["bm"] if os.environ.get("AMSWEEP_TEST_EXPERIMENTAL_WIRES") else [])
+
+
+@pytest.mark.parametrize("wire", WIRES)
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_sweep_and_both_gathers_equal_unsharded_oracle(world, wire):
     if _ngpu() < world:
@@ -79,7 +84,7 @@ def test_sharded_sweep_and_both_gathers_equal_unsharded_oracle(world, wire):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29700 + os.getpid() % 1000
-    port += 7 if wire == "c3" else 0
+    port += {"plain": 0, "c3": 7, "bm": 14}[wire]
     procs = [ctx.Process(target=_worker, args=(r, world, port, n_total, ticks, wire, q)) for r in range(world)]
     for p in procs:
         p.start()
