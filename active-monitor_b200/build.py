@@ -47,7 +47,7 @@ def _nvcc() -> str:
 
 def build_product(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, f) for f in ("sweep.cu", "gather.cu", "cron_parse.cpp", "handoff.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("sweep_kernels.cuh", "civil.h")] + [
+    deps = srcs + [os.path.join(CSRC, f) for f in ("sweep_kernels.cuh", "gather_kernels.cuh", "civil.h")] + [
         os.path.join(ROOT, "include", "amsweep.h")]
     if force or _newer(LIB, deps):
         os.makedirs(LIBDIR, exist_ok=True)

@@ -1,0 +1,181 @@
+// cuda_emu.h — just enough of the CUDA execution model to run csrc/gather_kernels.cuh on a
+// CPU: test infrastructure, never part of the product.
+//
+//   * one OS thread per rank ("GPU"); the CTAs of a launch run one after the other on it;
+//   * the 256 threads of a CTA are ucontext fibers, scheduled round-robin; __syncthreads and
+//     the warp collectives (__shfl_up_sync, __reduce_add_sync) are rendezvous points;
+//   * __shared__ is static thread_local (one copy per rank thread, reused by successive
+//     CTAs, as on an SM); system-scope acquire/release and atomics are seq_cst std atomics;
+//     a spinning fiber yields to its siblings.
+//
+// What it checks: index arithmetic, buffer offsets, the epoch / ticket / done-flag protocol
+// and its double buffering under real concurrency between ranks.  What it cannot check:
+// the GPU memory model beyond x86-TSO, coalescing, occupancy, performance.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <atomic>
+#include <cstdlib>
+#include <thread>
+#include <vector>
+
+#define AMSWEEP_EMULATE 1
+#define __global__
+#define __device__
+#define __forceinline__ inline
+#define __shared__ static thread_local
+#define __launch_bounds__(...)
+
+struct uint2 { uint32_t x, y; } __attribute__((aligned(8)));
+struct uint4 { uint32_t x, y, z, w; } __attribute__((aligned(16)));
+struct ulonglong2 { unsigned long long x, y; } __attribute__((aligned(16)));
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
+struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+
+namespace emu {
+enum State { READY, WAIT_BLOCK, WAIT_WARP, DONE };
+struct Fiber {
+  ucontext_t ctx;
+  State state = DONE;
+  dim3 tidx;
+  unsigned long long slot = 0;  // value deposited for a warp collective
+  char* stack = nullptr;
+};
+struct Block {
+  std::vector<Fiber> fibers;
+  ucontext_t sched;
+  Fiber* cur = nullptr;
+  dim3 bidx, bdim, gdim;
+  void (*entry)(const void*) = nullptr;
+  const void* params = nullptr;
+};
+inline thread_local Block* blk = nullptr;
+constexpr size_t kStack = 256 * 1024;
+
+inline void to_sched() { swapcontext(&blk->cur->ctx, &blk->sched); }
+inline void yield_spin() { to_sched(); }  // stays READY
+inline void trampoline() {
+  blk->entry(blk->params);
+  blk->cur->state = DONE;
+  to_sched();
+}
+inline void warp_rendezvous() { blk->cur->state = WAIT_WARP; to_sched(); }
+
+// run one CTA to completion on the calling OS thread
+inline void run_block(Block& b) {
+  blk = &b;
+  const unsigned n = b.bdim.x;
+  for (unsigned t = 0; t < n; ++t) {
+    Fiber& f = b.fibers[t];
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = f.stack;
+    f.ctx.uc_stack.ss_size = kStack;
+    f.ctx.uc_link = &b.sched;
+    f.tidx = dim3(t, 0, 0);
+    f.state = READY;
+    makecontext(&f.ctx, (void (*)())trampoline, 0);
+  }
+  unsigned done = 0;
+  while (done < n) {
+    done = 0;
+    for (unsigned t = 0; t < n; ++t) {
+      Fiber& f = b.fibers[t];
+      if (f.state == READY) {
+        b.cur = &f;
+        swapcontext(&b.sched, &f.ctx);
+      }
+      done += f.state == DONE;
+    }
+    // __syncthreads: released when every live thread of the CTA has arrived
+    unsigned waiting = 0, live = 0;
+    for (unsigned t = 0; t < n; ++t) {
+      live += b.fibers[t].state != DONE;
+      waiting += b.fibers[t].state == WAIT_BLOCK;
+    }
+    if (live && waiting == live)
+      for (unsigned t = 0; t < n; ++t)
+        if (b.fibers[t].state == WAIT_BLOCK) b.fibers[t].state = READY;
+    // warp collectives: released per warp
+    for (unsigned w0 = 0; w0 < n; w0 += 32) {
+      unsigned wl = 0, ww = 0;
+      for (unsigned t = w0; t < w0 + 32 && t < n; ++t) {
+        wl += b.fibers[t].state != DONE;
+        ww += b.fibers[t].state == WAIT_WARP;
+      }
+      if (wl && ww == wl)
+        for (unsigned t = w0; t < w0 + 32 && t < n; ++t)
+          if (b.fibers[t].state == WAIT_WARP) b.fibers[t].state = READY;
+    }
+  }
+  blk = nullptr;
+}
+
+// kernel<<<grid, block>>>(params) on the calling rank thread
+template <class P>
+void launch(void (*kernel)(const P), dim3 grid, dim3 block, const P& params) {
+  static thread_local Block b;
+  if (b.fibers.size() < block.x) {
+    const size_t old = b.fibers.size();
+    b.fibers.resize(block.x);
+    for (size_t t = old; t < block.x; ++t) b.fibers[t].stack = (char*)std::malloc(kStack);
+  }
+  struct Call { void (*k)(const P); const P* p; } call{kernel, &params};
+  b.entry = [](const void* c) { const Call* cc = (const Call*)c; cc->k(*cc->p); };
+  b.params = &call;
+  b.bdim = block;
+  b.gdim = grid;
+  for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned bx = 0; bx < grid.x; ++bx) {
+      b.bidx = dim3(bx, by, 0);
+      run_block(b);
+    }
+}
+}  // namespace emu
+
+#define threadIdx (emu::blk->cur->tidx)
+#define blockIdx (emu::blk->bidx)
+#define blockDim (emu::blk->bdim)
+#define gridDim (emu::blk->gdim)
+
+static inline void __syncthreads() { emu::blk->cur->state = emu::WAIT_BLOCK; emu::to_sched(); }
+static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+template <class T> static inline T __ldcs(const T* p) { return *p; }
+static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline uint32_t atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+
+static inline void st_release_sys(unsigned long long* p, unsigned long long v) {
+  __atomic_store_n(p, v, __ATOMIC_SEQ_CST);
+}
+static inline unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  const unsigned long long v = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  emu::yield_spin();  // callers poll in a loop: let the sibling fibers run, other ranks are OS threads
+  return v;
+}
+
+// full-mask warp collectives (every lane of the warp takes part, as in the kernels under test)
+static inline uint32_t __shfl_up_sync(unsigned, uint32_t v, unsigned delta) {
+  emu::Block& b = *emu::blk;
+  const unsigned t = b.cur->tidx.x, lane = t & 31;
+  b.cur->slot = v;
+  emu::warp_rendezvous();
+  const uint32_t r = lane >= delta ? (uint32_t)b.fibers[t - delta].slot : v;
+  emu::warp_rendezvous();  // nobody overwrites a slot before every lane has read
+  return r;
+}
+static inline uint32_t __reduce_add_sync(unsigned, uint32_t v) {
+  emu::Block& b = *emu::blk;
+  const unsigned t = b.cur->tidx.x, w0 = t & ~31u;
+  b.cur->slot = v;
+  emu::warp_rendezvous();
+  uint32_t s = 0;
+  for (unsigned k = w0; k < w0 + 32 && k < b.bdim.x; ++k) s += (uint32_t)b.fibers[k].slot;
+  emu::warp_rendezvous();
+  return s;
+}
