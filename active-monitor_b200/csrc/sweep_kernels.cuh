@@ -41,7 +41,9 @@
 //     compact_kernel is the only global synchronisation, so the sweep kernel
 //     has one __syncthreads, no fences and no completion tickets.
 #pragma once
+#ifndef AMSWEEP_EMULATE  // tests/emu compiles this file for the CPU (cuda_emu.h supplies the model)
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "../../include/amsweep.h"
@@ -109,6 +111,7 @@ __device__ __forceinline__ void st_stream(T* p, T v) { __stcs(p, v); }
 // Segment entries are written once by the sweep and read once, a few tens of
 // microseconds later, by compact_kernel: keep them L2-resident (evict_last)
 // while 560 MB of evict_first column data streams past them.
+#ifndef AMSWEEP_EMULATE
 __device__ __forceinline__ uint64_t l2_evict_last_policy() {
   uint64_t pol;
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -120,6 +123,11 @@ __device__ __forceinline__ void st_keep_u32(uint32_t* p, uint32_t v, uint64_t po
 __device__ __forceinline__ void st_keep_u8(uint8_t* p, uint32_t v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
+#else  // CPU emulation: plain stores, the cache policy has no meaning
+inline uint64_t l2_evict_last_policy() { return 0; }
+inline void st_keep_u32(uint32_t* p, uint32_t v, uint64_t) { *p = v; }
+inline void st_keep_u8(uint8_t* p, uint32_t v, uint64_t) { *p = (uint8_t)v; }
+#endif
 
 __device__ __forceinline__ uint64_t sm64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;

@@ -34,6 +34,10 @@ struct ulonglong2 { unsigned long long x, y; } __attribute__((aligned(16)));
 static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
+struct int2 { int32_t x, y; } __attribute__((aligned(8)));
+struct longlong2 { long long x, y; } __attribute__((aligned(16)));
+static inline int2 make_int2(int32_t x, int32_t y) { return int2{x, y}; }
+static inline longlong2 make_longlong2(long long x, long long y) { return longlong2{x, y}; }
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 
 namespace emu {
@@ -114,17 +118,17 @@ inline void run_block(Block& b) {
   blk = nullptr;
 }
 
-// kernel<<<grid, block>>>(params) on the calling rank thread
-template <class P>
-void launch(void (*kernel)(const P), dim3 grid, dim3 block, const P& params) {
+// kernel<<<grid, block>>>(args...) on the calling rank thread
+template <class K, class... A>
+void launch(K kernel, dim3 grid, dim3 block, const A&... args) {
   static thread_local Block b;
   if (b.fibers.size() < block.x) {
     const size_t old = b.fibers.size();
     b.fibers.resize(block.x);
     for (size_t t = old; t < block.x; ++t) b.fibers[t].stack = (char*)std::malloc(kStack);
   }
-  struct Call { void (*k)(const P); const P* p; } call{kernel, &params};
-  b.entry = [](const void* c) { const Call* cc = (const Call*)c; cc->k(*cc->p); };
+  auto call = [&]() { kernel(args...); };
+  b.entry = [](const void* c) { (*(const decltype(call)*)c)(); };
   b.params = &call;
   b.bdim = block;
   b.gdim = grid;
@@ -159,6 +163,19 @@ static inline unsigned long long ld_acquire_sys(const unsigned long long* p) {
   return v;
 }
 
+template <class T> static inline void __stcs(T* p, T v) { *p = v; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+  return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
+}
+static inline unsigned long long atomicXor(unsigned long long* p, unsigned long long v) {
+  return __atomic_fetch_xor(p, v, __ATOMIC_SEQ_CST);
+}
+static inline uint32_t atomicMax(uint32_t* p, uint32_t v) {
+  uint32_t old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+
 // full-mask warp collectives (every lane of the warp takes part, as in the kernels under test)
 static inline uint32_t __shfl_up_sync(unsigned, uint32_t v, unsigned delta) {
   emu::Block& b = *emu::blk;
@@ -178,4 +195,46 @@ static inline uint32_t __reduce_add_sync(unsigned, uint32_t v) {
   for (unsigned k = w0; k < w0 + 32 && k < b.bdim.x; ++k) s += (uint32_t)b.fibers[k].slot;
   emu::warp_rendezvous();
   return s;
+}
+
+// generic full-warp exchange: every live lane deposits `v`, then `f(slots of the warp, lane)`
+namespace emu {
+template <class F>
+static inline auto warp_collect(unsigned long long v, F f) {
+  Block& b = *blk;
+  const unsigned t = b.cur->tidx.x, w0 = t & ~31u;
+  b.cur->slot = v;
+  warp_rendezvous();
+  unsigned long long vals[32];
+  bool live[32];
+  for (unsigned k = 0; k < 32; ++k) {
+    const bool in = w0 + k < b.bdim.x;
+    live[k] = in && b.fibers[w0 + k].state != DONE;
+    vals[k] = in ? b.fibers[w0 + k].slot : 0;
+  }
+  auto r = f(vals, live, t & 31u);
+  warp_rendezvous();
+  return r;
+}
+}  // namespace emu
+static inline void __syncwarp(unsigned = 0xFFFFFFFFu) { emu::warp_rendezvous(); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+  return emu::warp_collect(pred ? 1ull : 0ull, [](const unsigned long long* v, const bool* live, unsigned) {
+    unsigned m = 0;
+    for (unsigned k = 0; k < 32; ++k) m |= (live[k] && v[k]) ? (1u << k) : 0u;
+    return m;
+  });
+}
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline uint32_t __reduce_xor_sync(unsigned, uint32_t x) {
+  return emu::warp_collect(x, [](const unsigned long long* v, const bool* live, unsigned) {
+    uint32_t s = 0;
+    for (unsigned k = 0; k < 32; ++k) s ^= live[k] ? (uint32_t)v[k] : 0u;
+    return s;
+  });
+}
+static inline unsigned long long __shfl_xor_sync(unsigned, unsigned long long x, int lane_mask) {
+  return emu::warp_collect(x, [lane_mask](const unsigned long long* v, const bool*, unsigned lane) {
+    return v[(lane ^ (unsigned)lane_mask) & 31u];
+  });
 }

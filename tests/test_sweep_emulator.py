@@ -1,0 +1,198 @@
+"""The per-tick kernels (csrc/sweep_kernels.cuh) on the CPU emulation of the CUDA execution
+model (tests/emu): the SAME kernel source the GPU runs — sweep_tick_kernel in its four
+variants, compact_kernel, publish_kernel, the staged-event kernels, next_fire_kernel —
+against the oracle, bit-exact: emitted lists, action bytes, statistics, every mutated column.
+
+This is the CPU-side twin of tests/test_sweep_gpu.py at oracle-friendly sizes.  It checks the
+kernels' logic (decisions, ordered compaction, statistics, the parity hand-off between
+ticks); it says nothing about the GPU memory model or performance, and the launch sequence
+is restated in tests/emu/emu_sweep.cpp (csrc/sweep.cu's host code is exercised on the GPU)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import emu_sweep  # noqa: E402
+
+T0 = 1789982100      # 2026-09-21 09:15:00 UTC Monday
+T_OCT1 = 1790812800  # 2026-10-01 00:00:00 UTC Thursday
+
+
+def _gen_pair(gen, am, orc, config, seed, n, T, first=0):
+    prod = gen.fill(config, seed, first, n, T, am.load().am_healthcheck_classify)
+    orac = gen.fill(config, seed, first, n, T, orc.load().orc_classify)
+    return prod, orac
+
+
+def _assert_tick_equal(am, got, want, sweep, ocols, n, what=""):
+    gi, ga, gs = got
+    wi, wa, ws = want
+    assert gs == ws, f"{what}: stats differ\n emu={gs}\n cpu={ws}"
+    np.testing.assert_array_equal(gi, wi, err_msg=f"{what}: due indices")
+    np.testing.assert_array_equal(ga, wa, err_msg=f"{what}: action bytes")
+    dev = sweep.read_range(0, n)
+    for name in am.COLUMN_NAMES:
+        np.testing.assert_array_equal(dev[name], ocols[name], err_msg=f"{what}: column {name}")
+
+
+@pytest.mark.parametrize("config", [1, 11])
+def test_config1(am, orc, gen, config):
+    n = 1000
+    prod, orac = _gen_pair(gen, am, orc, config, 1, n, T0)
+    with emu_sweep.EmuSweep(n) as s:
+        s.load_range(0, prod)
+        _assert_tick_equal(am, s.tick(T0), orc.sweep(orac, T0), s, orac, n, f"config {config}")
+
+
+@pytest.mark.parametrize("T", [T0, T_OCT1, T0 + 1, T0 + 45, 1709164800])
+@pytest.mark.parametrize("n", [1, 63, 1025, 20_003])
+def test_config2_mixed(am, orc, gen, T, n):
+    prod, orac = _gen_pair(gen, am, orc, 2, 2, n, T0)
+    with emu_sweep.EmuSweep(n) as s:
+        s.load_range(0, prod)
+        _assert_tick_equal(am, s.tick(T), orc.sweep(orac, T), s, orac, n, f"config2 n={n} T={T}")
+        # one second later: "Stopped" is reported once only; other parity of the group counters
+        _assert_tick_equal(am, s.tick(T + 1), orc.sweep(orac, T + 1), s, orac, n, "second tick")
+
+
+@pytest.mark.parametrize("T", [T0, T_OCT1])
+def test_config3_remedy_state_machine_dense_and_sparse(am, orc, gen, T):
+    n = 20_000
+    prod, orac = _gen_pair(gen, am, orc, 3, 3, n, T0)
+    with emu_sweep.EmuSweep(n) as s:
+        s.load_range(0, prod)
+        got = s.tick(T)
+        _assert_tick_equal(am, got, orc.sweep(orac, T), s, orac, n, "config3")
+        if T == T0:
+            for k in ("n_run_remedy", "n_remedy_skip", "n_reset_on_pass", "n_reset_on_interval",
+                      "n_result_ok", "n_result_fail", "n_remedy_ok", "n_remedy_fail"):
+                assert got[2][k] > 0, f"population does not exercise {k}"
+        # nothing pending any more: the sparse path (few or no needy lanes per warp)
+        _assert_tick_equal(am, s.tick(T + 60), orc.sweep(orac, T + 60), s, orac, n, "config3 next minute")
+
+
+def test_full_scan_mode_and_shard_base(am, orc, gen):
+    n, base = 9000, 12_500_000
+    prod, orac = _gen_pair(gen, am, orc, 2, 7, n, T0, first=base)
+    with emu_sweep.EmuSweep(n, shard_base=base) as s:
+        s.load_range(0, prod)
+        for T in (T0 + 7, T0 + 60):
+            got = s.tick(T, mode=am.SWEEP_FULL_SCAN)
+            want = orc.sweep(orac, T, shard_base=base)
+            _assert_tick_equal(am, got, want, s, orac, n, f"full-scan T={T}")
+            assert got[0].min() >= base
+
+
+@pytest.mark.parametrize("config", [5, 55])
+def test_closed_loop_many_ticks(am, orc, gen, config):
+    n, seed = 6000, 5
+    prod, orac = _gen_pair(gen, am, orc, config, seed, n, T0)
+    with emu_sweep.EmuSweep(n) as s:
+        s.load_range(0, prod)
+        s.set_seed(seed)
+        for k in range(75):
+            T = T0 - 10 + k  # crosses a minute boundary: both MASKS variants of the closed-loop kernel
+            got = s.tick(T, mode=am.SWEEP_CLOSED_LOOP)
+            want = orc.sweep(orac, T, mode=1, seed=seed)
+            assert got[2] == want[2], f"config {config} tick {k}"
+            np.testing.assert_array_equal(got[0], want[0])
+            np.testing.assert_array_equal(got[1], want[1])
+        dev = s.read_range(0, n)
+        for name in am.COLUMN_NAMES:
+            np.testing.assert_array_equal(dev[name], orac[name], err_msg=f"config {config} {name}")
+
+
+def test_short_output_buffer(am, gen):
+    n = 4096
+    prod = gen.fill(1, 1, 0, n, T0, am.load().am_healthcheck_classify)
+    with emu_sweep.EmuSweep(n) as s:
+        s.load_range(0, prod)
+        part = s.tick(T0, cap=10)
+        full = s.tick(T0)
+        assert part[2]["n_emitted"] == full[2]["n_emitted"] == len(full[0]) > 10
+        np.testing.assert_array_equal(part[0], full[0][:10])
+
+
+def test_staged_events_take_effect_in_call_order(am):
+    T = T0
+
+    def rec(ras, fin):
+        rc, r = am.classify(repeat_after_sec=ras, finished_at=fin)
+        assert rc == 0
+        return r
+
+    A, B = rec(60, T - 1000), rec(7, T - 1)  # A is due at T, B is not
+    with emu_sweep.EmuSweep(64) as s:
+        s.upsert([0], A); s.remove([0])
+        s.remove([1]); s.upsert([1], A)
+        s.upsert([2], A); s.upsert([2], B)
+        s.upsert([3], B); s.upsert([3], A)
+        s.upsert([4], A)
+        s.post_result([4], [am.PHASE_FAILED]); s.upsert([4], B)
+        s.upsert([5], B); s.post_result([5], [am.PHASE_SUCCEEDED])
+        s.upsert([6], B)
+        s.post_result([6], [am.PHASE_SUCCEEDED]); s.post_result([6], [am.PHASE_FAILED])
+        s.upsert(np.array([7, 7, 7]), np.concatenate([A, B, A]))
+        idx, act, st = s.tick(T)
+        got = dict(zip(idx.tolist(), act.tolist()))
+        assert got == {1: am.ACT_SUBMIT_HC, 3: am.ACT_SUBMIT_HC, 7: am.ACT_SUBMIT_HC}, got
+        cols = s.read_range(0, 8)
+        assert cols["flags"][0] == am.F_TOMBSTONE
+        assert cols["ras"].tolist()[1:8] == [60, 7, 60, 7, 7, 7, 60]
+        assert cols["failed"][4] == 0 and cols["finished_at"][4] == T - 1
+        assert cols["success"][5] == 1 and cols["finished_at"][5] == T
+        assert cols["failed"][6] == 1 and cols["success"][6] == 0
+        assert st["n_result_ok"] == 1 and st["n_result_fail"] == 1 and s.size == 8
+        s.post_result([5], [am.PHASE_FAILED])
+        _, _, st2 = s.tick(T + 1)
+        assert st2["n_result_fail"] == 1 and s.read([5])["failed"][0] == 1
+
+
+def test_upsert_remove_and_deferred_remedy_result(am, orc, gen):
+    n = 3000
+    prod, orac = _gen_pair(gen, am, orc, 3, 11, n, T0)
+    recs = am.columns_to_records(prod)
+    with emu_sweep.EmuSweep(n + 100) as s:
+        perm = np.random.default_rng(0).permutation(n)
+        s.upsert(perm[: n // 2], recs[perm[: n // 2]])
+        s.upsert(perm[n // 2:], recs[perm[n // 2:]])
+        gone = np.array([3, 77, 1024, n - 1], dtype=np.uint64)
+        s.remove(gone)
+        orac["flags"][gone.astype(np.int64)] = am.F_TOMBSTONE
+        got = s.tick(T0)
+        assert s.size == n
+        want = orc.sweep(orac, T0)
+        assert got[2] == want[2]
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+        live = np.flatnonzero((orac["flags"] & 7 == am.KIND_INTERVAL) & (orac["flags"] & am.F_TOMBSTONE == 0))[:50]
+        s.post_result(live, np.zeros(len(live), np.uint8), np.full(len(live), am.PHASE_FAILED, np.uint8))
+        orac["flags"][live] |= am.F_REMEDY_PENDING
+        got = s.tick(T0 + 3)
+        want = orc.sweep(orac, T0 + 3)
+        assert got[2] == want[2] and got[2]["n_remedy_fail"] == len(live)
+        dev = s.read(live)
+        np.testing.assert_array_equal(dev["remedy_failed"], orac["remedy_failed"][live])
+        np.testing.assert_array_equal(dev["remedy_finished_at"], np.full(len(live), T0 + 3))
+
+
+def test_repeat_after_sec_kernel_equals_oracle(am, orc, gen):
+    n = 4000
+    prod, _ = _gen_pair(gen, am, orc, 2, 2, n, T0)
+    lib = orc.load()
+    with emu_sweep.EmuSweep(n) as s:
+        s.load_range(0, prod)
+        for T in (T0, T_OCT1 - 1, 1709164799):
+            got = s.repeat_after_sec(T, 0, n)
+            kind = prod["flags"] & 7
+            want = np.zeros(n, dtype=np.int64)
+            iv = (kind == am.KIND_INTERVAL) | (kind == am.KIND_CRON_EVERY)
+            want[iv] = prod["ras"][iv]
+            for i in np.flatnonzero(kind == am.KIND_CRON_SPEC):
+                c = orc.OrcCron(int(prod["minute"][i]), int(prod["hour"][i]), int(prod["dom"][i]),
+                                int(prod["month"][i]), int(prod["dow"][i]), 0, 1, 0)
+                want[i] = lib.orc_cron_repeat_after_sec(C.byref(c), T)
+            np.testing.assert_array_equal(got, want, err_msg=f"T={T}")
