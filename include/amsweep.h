@@ -201,7 +201,10 @@ int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t
 void am_sweep_destroy(am_sweep_t*);
 
 /* Bulk load of a contiguous index range [first, first+n) — informer re-list
- * after (re)start (SURVEY §5 "failure detection / recovery"). */
+ * after (re)start (SURVEY §5 "failure detection / recovery").  The columns are
+ * taken as they are: they must be values this library produced
+ * (am_healthcheck_classify / am_sweep_read).  In particular
+ * AM_F_REMEDY_OUTCOME_OK only has a meaning together with AM_F_REMEDY_PENDING. */
 int am_sweep_load_range(am_sweep_t*, uint64_t first, uint64_t n, const am_record_cols_t* cols);
 
 /* Reconcile of created/updated CRs (hcc.go:170-188): scatter n records to
