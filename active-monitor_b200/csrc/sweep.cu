@@ -178,17 +178,17 @@ int drain_staged(am_sweep* h) {
   const StagedOp* d_ops = (const StagedOp*)dp;
   const am_record_t* d_recs = (const am_record_t*)(dp + o_rec);
   const unsigned B = 256, G = (unsigned)((n + B - 1) / B);
-  mark_ops_kernel<<<G, B, 0, h->stream>>>(h->marks, d_ops, (uint32_t)n);
+  AM_LAUNCH(mark_ops_kernel, G, B, h->stream, h->marks, d_ops, (uint32_t)n);
   h->launches++;
   if (n_state) {
-    apply_state_ops_kernel<<<G, B, 0, h->stream>>>(h->cols, h->marks, d_ops, d_recs, (uint32_t)n);
+    AM_LAUNCH(apply_state_ops_kernel, G, B, h->stream, h->cols, h->marks, d_ops, d_recs, (uint32_t)n);
     h->launches++;
   }
   if (n_result) {
-    apply_result_ops_kernel<<<G, B, 0, h->stream>>>(h->cols.flags, h->marks, d_ops, (uint32_t)n);
+    AM_LAUNCH(apply_result_ops_kernel, G, B, h->stream, h->cols.flags, h->marks, d_ops, (uint32_t)n);
     h->launches++;
   }
-  clear_marks_kernel<<<G, B, 0, h->stream>>>(h->marks, d_ops, (uint32_t)n);
+  AM_LAUNCH(clear_marks_kernel, G, B, h->stream, h->marks, d_ops, (uint32_t)n);
   h->launches++;
   AM_CUDA(h, cudaGetLastError());
   // the pinned arrays are refilled by the next calls: wait until the copies were consumed
@@ -226,10 +226,10 @@ int launch_sweep(am_sweep* h, int64_t T, uint32_t mode, uint32_t* d_idx, uint8_t
   if (sec_of_min < 0) sec_of_min += 60;
   const bool masks = sec_of_min == 0 || (mode & AM_SWEEP_FULL_SCAN);
   const bool closed = (mode & AM_SWEEP_CLOSED_LOOP) != 0;
-  if (closed && masks) sweep_tick_kernel<true, true><<<p.n_tiles, kBlock, 0, s>>>(p);
-  else if (closed) sweep_tick_kernel<true, false><<<p.n_tiles, kBlock, 0, s>>>(p);
-  else if (masks) sweep_tick_kernel<false, true><<<p.n_tiles, kBlock, 0, s>>>(p);
-  else sweep_tick_kernel<false, false><<<p.n_tiles, kBlock, 0, s>>>(p);
+  if (closed && masks) AM_LAUNCH(AM_SWEEP_KERNEL(true, true), p.n_tiles, kBlock, s, p);
+  else if (closed) AM_LAUNCH(AM_SWEEP_KERNEL(true, false), p.n_tiles, kBlock, s, p);
+  else if (masks) AM_LAUNCH(AM_SWEEP_KERNEL(false, true), p.n_tiles, kBlock, s, p);
+  else AM_LAUNCH(AM_SWEEP_KERNEL(false, false), p.n_tiles, kBlock, s, p);
   if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[1], s));
   CompactParams c{};
   c.seg_idx = h->seg_idx;
@@ -244,8 +244,8 @@ int launch_sweep(am_sweep* h, int64_t T, uint32_t mode, uint32_t* d_idx, uint8_t
   c.n_tiles = p.n_tiles;
   c.n_groups = (p.n_tiles + kGroupTiles - 1) / kGroupTiles;
   c.cap = (uint32_t)(cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : cap);
-  compact_kernel<<<c.n_groups, 256, 0, s>>>(c);
-  publish_kernel<<<1, 32, 0, s>>>(h->acc, out_stats, out_count, h->n_records);
+  AM_LAUNCH(compact_kernel, c.n_groups, 256, s, c);
+  AM_LAUNCH(publish_kernel, 1, 32, s, h->acc, out_stats, out_count, h->n_records);
   if (h->profiling) { AM_CUDA(h, cudaEventRecord(h->evp[2], s)); h->profiled = true; }
   h->parity ^= 1;
   h->launches += 3;
@@ -295,7 +295,7 @@ int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t
       h->col_ptr[k] = p;
       h->col_elem[k] = kColElem[k];
     }
-    fill_u32_kernel<<<1184, 256, 0, h->stream>>>(h->cols.flags, AM_F_TOMBSTONE, h->cap_padded);
+    AM_LAUNCH(fill_u32_kernel, 1184, 256, h->stream, h->cols.flags, AM_F_TOMBSTONE, h->cap_padded);
     h->launches++;
     const size_t ntiles = h->cap_padded / kTile;
     const size_t ngroups = (ntiles + kGroupTiles - 1) / kGroupTiles;
@@ -578,8 +578,8 @@ int am_sweep_repeat_after_sec(am_sweep_t* h, int64_t unix_sec, uint64_t first, u
   if (rc != AM_OK) return rc;
   AM_CUDA(h, h->dev_in.reserve(n * 8));
   AM_CUDA(h, h->pin_out.reserve(n * 8));
-  next_fire_kernel<<<(unsigned)((n + 127) / 128), 128, 0, h->stream>>>(h->cols, (uint32_t)first, (uint32_t)n,
-                                                                     unix_sec, (int64_t*)h->dev_in.p);
+  AM_LAUNCH(next_fire_kernel, (unsigned)((n + 127) / 128), 128, h->stream, h->cols, (uint32_t)first, (uint32_t)n,
+            unix_sec, (int64_t*)h->dev_in.p);
   h->launches++;
   AM_CUDA(h, cudaGetLastError());
   AM_CUDA(h, cudaMemcpyAsync(h->pin_out.p, h->dev_in.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
@@ -620,8 +620,8 @@ int am_sweep_read(am_sweep_t* h, uint64_t first, uint64_t n, const uint64_t* idx
   for (uint64_t k = 0; k < n; ++k) hidx[k] = (uint32_t)idx[k];
   char* dp = (char*)h->dev_in.p;
   AM_CUDA(h, cudaMemcpyAsync(dp + o_idx, hidx, n * 4, cudaMemcpyHostToDevice, h->stream));
-  gather_records_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(
-      h->cols, (const uint32_t*)(dp + o_idx), (am_record_t*)dp, (uint32_t)n);
+  AM_LAUNCH(gather_records_kernel, (unsigned)((n + 255) / 256), 256, h->stream, h->cols,
+            (const uint32_t*)(dp + o_idx), (am_record_t*)dp, (uint32_t)n);
   h->launches++;
   AM_CUDA(h, cudaGetLastError());
   AM_CUDA(h, cudaMemcpyAsync(h->pin_in.p, dp, n * sizeof(am_record_t), cudaMemcpyDeviceToHost, h->stream));

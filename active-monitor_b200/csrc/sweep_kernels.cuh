@@ -49,6 +49,15 @@
 #include "../../include/amsweep.h"
 #include "civil.h"
 
+// Kernel launches are spelled through one macro so that tests/emu can compile the host
+// runtime (sweep.cu) for the CPU emulator as well; under nvcc it is the plain <<<>>> launch.
+#ifndef AMSWEEP_EMULATE
+#define AM_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#else
+#define AM_LAUNCH(kernel, grid, block, stream, ...) emu::launch(kernel, dim3(grid), dim3(block), __VA_ARGS__)
+#endif
+#define AM_SWEEP_KERNEL(closed, masks) sweep_tick_kernel<closed, masks>  // one macro argument
+
 namespace amsweep {
 
 #ifndef AM_BLOCK

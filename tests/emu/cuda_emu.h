@@ -2,7 +2,7 @@
 // CPU: test infrastructure, never part of the product.
 //
 //   * one OS thread per rank ("GPU"); the CTAs of a launch run one after the other on it;
-//   * the 256 threads of a CTA are ucontext fibers, scheduled round-robin; __syncthreads and
+//   * the 256 threads of a CTA are fibers (own stacks, a minimal register switch), scheduled round-robin; __syncthreads and
 //     the warp collectives (__shfl_up_sync, __reduce_add_sync) are rendezvous points;
 //   * __shared__ is static thread_local (one copy per rank thread, reused by successive
 //     CTAs, as on an SM); system-scope acquire/release and atomics are seq_cst std atomics;
@@ -14,7 +14,9 @@
 #pragma once
 #include <stdint.h>
 #include <string.h>
+#if !defined(__x86_64__)
 #include <ucontext.h>
+#endif
 
 #include <atomic>
 #include <cstdlib>
@@ -42,8 +44,39 @@ struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1,
 
 namespace emu {
 enum State { READY, WAIT_BLOCK, WAIT_WARP, DONE };
+#if defined(__x86_64__)
+// Minimal stack switch (callee-saved registers + rsp): glibc's swapcontext makes a sigprocmask
+// system call per switch, and a CTA's 256 fibers switch at every rendezvous.
+extern "C" void emu_switch(void** save_sp, void* load_sp);
+asm(R"(
+.text
+.weak emu_switch
+.hidden emu_switch
+.type emu_switch,@function
+emu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size emu_switch,.-emu_switch
+)");
+struct Context { void* sp = nullptr; };
+#else
+struct Context { ucontext_t uc; };
+#endif
 struct Fiber {
-  ucontext_t ctx;
+  Context ctx;
   State state = DONE;
   dim3 tidx;
   unsigned long long slot = 0;  // value deposited for a warp collective
@@ -51,7 +84,7 @@ struct Fiber {
 };
 struct Block {
   std::vector<Fiber> fibers;
-  ucontext_t sched;
+  Context sched;
   Fiber* cur = nullptr;
   dim3 bidx, bdim, gdim;
   void (*entry)(const void*) = nullptr;
@@ -60,7 +93,12 @@ struct Block {
 inline thread_local Block* blk = nullptr;
 constexpr size_t kStack = 256 * 1024;
 
-inline void to_sched() { swapcontext(&blk->cur->ctx, &blk->sched); }
+#if defined(__x86_64__)
+inline void switch_to(Context& from, Context& to) { emu_switch(&from.sp, to.sp); }
+#else
+inline void switch_to(Context& from, Context& to) { swapcontext(&from.uc, &to.uc); }
+#endif
+inline void to_sched() { switch_to(blk->cur->ctx, blk->sched); }
 inline void yield_spin() { to_sched(); }  // stays READY
 inline void trampoline() {
   blk->entry(blk->params);
@@ -75,13 +113,23 @@ inline void run_block(Block& b) {
   const unsigned n = b.bdim.x;
   for (unsigned t = 0; t < n; ++t) {
     Fiber& f = b.fibers[t];
-    getcontext(&f.ctx);
-    f.ctx.uc_stack.ss_sp = f.stack;
-    f.ctx.uc_stack.ss_size = kStack;
-    f.ctx.uc_link = &b.sched;
     f.tidx = dim3(t, 0, 0);
     f.state = READY;
-    makecontext(&f.ctx, (void (*)())trampoline, 0);
+#if defined(__x86_64__)
+    // first switch "returns" into trampoline with the stack aligned as after a call
+    uintptr_t top = ((uintptr_t)f.stack + kStack) & ~(uintptr_t)15;
+    void** sp = (void**)top;
+    *--sp = nullptr;                 // return address of trampoline (never used)
+    *--sp = (void*)&trampoline;      // popped by emu_switch's ret
+    for (int r = 0; r < 6; ++r) *--sp = nullptr;  // rbp rbx r12 r13 r14 r15
+    f.ctx.sp = sp;
+#else
+    getcontext(&f.ctx.uc);
+    f.ctx.uc.uc_stack.ss_sp = f.stack;
+    f.ctx.uc.uc_stack.ss_size = kStack;
+    f.ctx.uc.uc_link = &b.sched.uc;
+    makecontext(&f.ctx.uc, (void (*)())trampoline, 0);
+#endif
   }
   unsigned done = 0;
   while (done < n) {
@@ -90,7 +138,7 @@ inline void run_block(Block& b) {
       Fiber& f = b.fibers[t];
       if (f.state == READY) {
         b.cur = &f;
-        swapcontext(&b.sched, &f.ctx);
+        switch_to(b.sched, f.ctx);
       }
       done += f.state == DONE;
     }
