@@ -24,7 +24,9 @@
 //
 // The reference has no counterpart (single Go process, no collectives); the
 // consumer of the list is createSubmitWorkflow, hcc.go:502.
+#ifndef AMSWEEP_EMULATE
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include <cstdio>
@@ -216,7 +218,7 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
     b.ngroups_max = g->ngroups_max;
     b.rank = g->rank;
     b.world = g->world;
-    gather_push_bm_kernel<<<g->n_ctas, 256, 0, st>>>(b);
+    AM_LAUNCH(gather_push_bm_kernel, g->n_ctas, 256, st, b);
     ExpandBmParams x{};
     x.bm = reinterpret_cast<const uint32_t*>(g->block + g->off_bm[buf]);
     x.gc = reinterpret_cast<const uint32_t*>(g->block + g->off_gc[buf]);
@@ -233,7 +235,7 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
       x.bm_word0[r] = g->bm_word0[r];
       if (g->ngroups[r] > ng_used) ng_used = g->ngroups[r];
     }
-    gather_expand_bitmap_kernel<<<dim3(ng_used, g->world), 256, 0, st>>>(x);
+    AM_LAUNCH(gather_expand_bitmap_kernel, dim3(ng_used, g->world), 256, st, x);
     AMG_CUDA(g, cudaGetLastError());
     return AM_OK;
   }
@@ -253,7 +255,7 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
     c.ngroups_max = g->ngroups_max;
     c.rank = g->rank;
     c.world = g->world;
-    gather_push_c3_kernel<<<g->n_ctas, 256, 0, st>>>(c);
+    AM_LAUNCH(gather_push_c3_kernel, g->n_ctas, 256, st, c);
     DecodeParams dp{};
     dp.o16 = reinterpret_cast<const uint16_t*>(g->block + g->off_o16[buf]);
     dp.gc = reinterpret_cast<const uint32_t*>(g->block + g->off_gc[buf]);
@@ -269,7 +271,7 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
       dp.bases[r] = g->bases[r];
       if (g->ngroups[r] > ng_used) ng_used = g->ngroups[r];
     }
-    gather_decode_kernel<<<dim3(ng_used, g->world), 256, 0, st>>>(dp);
+    AM_LAUNCH(gather_decode_kernel, dim3(ng_used, g->world), 256, st, dp);
     AMG_CUDA(g, cudaGetLastError());
     return AM_OK;
   }
@@ -277,7 +279,7 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
   p.rank = g->rank;
   p.world = g->world;
   p.idx_bytes = g->idx_bytes;
-  gather_push_kernel<<<g->n_ctas, 256, 0, (cudaStream_t)cuda_stream>>>(p);
+  AM_LAUNCH(gather_push_kernel, g->n_ctas, 256, (cudaStream_t)cuda_stream, p);
   AMG_CUDA(g, cudaGetLastError());
   return AM_OK;
 }

@@ -10,6 +10,15 @@
 
 #include "../../include/amsweep.h"
 
+// one spelling for kernel launches (see sweep_kernels.cuh): <<<>>> under nvcc, emu::launch on the emulator
+#ifndef AM_LAUNCH
+#ifndef AMSWEEP_EMULATE
+#define AM_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#else
+#define AM_LAUNCH(kernel, grid, block, stream, ...) ((void)(stream), emu::launch(kernel, dim3(grid), dim3(block), __VA_ARGS__))
+#endif
+#endif
+
 namespace {
 
 constexpr int kMaxWorld = 16;

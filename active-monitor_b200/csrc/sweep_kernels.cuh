@@ -51,10 +51,12 @@
 
 // Kernel launches are spelled through one macro so that tests/emu can compile the host
 // runtime (sweep.cu) for the CPU emulator as well; under nvcc it is the plain <<<>>> launch.
+#ifndef AM_LAUNCH
 #ifndef AMSWEEP_EMULATE
 #define AM_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
 #else
-#define AM_LAUNCH(kernel, grid, block, stream, ...) emu::launch(kernel, dim3(grid), dim3(block), __VA_ARGS__)
+#define AM_LAUNCH(kernel, grid, block, stream, ...) ((void)(stream), emu::launch(kernel, dim3(grid), dim3(block), __VA_ARGS__))
+#endif
 #endif
 #define AM_SWEEP_KERNEL(closed, masks) sweep_tick_kernel<closed, masks>  // one macro argument
 

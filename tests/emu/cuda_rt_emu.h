@@ -1,4 +1,4 @@
-// cuda_rt_emu.h — the handful of CUDA runtime calls csrc/sweep.cu makes, on host memory, so that
+// cuda_rt_emu.h — the handful of CUDA runtime calls csrc/sweep.cu and csrc/gather.cu make, on host memory, so that
 // the whole host runtime (staging, drain, tick, read, run_ticks, ...) can be compiled with
 // cuda_emu.h into tests/emu/libamsweep_emu.so and driven through the real C-ABI without a GPU.
 // One "device"; every stream operation completes before the call returns (a legal, maximally
@@ -21,8 +21,25 @@ static inline const char* cudaGetErrorString(cudaError_t e) {
   return e == cudaSuccess ? "no error" : (e == cudaErrorMemoryAllocation ? "out of memory" : "emulated CUDA error");
 }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+// sixteen "devices": the exchange tests run one rank per device id, as OS threads of one process
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 16; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int d) { return d >= 0 && d < 16 ? cudaSuccess : cudaErrorInvalidValue; }
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 4; return cudaSuccess; }  // 4 "SMs"
+
+// CUDA IPC between "processes" that are threads here: the handle carries the pointer itself
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  std::memset(h, 0, sizeof *h);
+  std::memcpy(h->reserved, &p, sizeof p);
+  return cudaSuccess;
+}
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+  std::memcpy(p, h.reserved, sizeof *p);
+  return *p ? cudaSuccess : cudaErrorInvalidValue;
+}
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 
 static inline cudaError_t cudaMalloc(void** p, size_t bytes) {

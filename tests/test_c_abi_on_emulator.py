@@ -1,5 +1,5 @@
 """The whole product library — csrc/sweep.cu (handle, staging, drain, tick, read, run_ticks, ...)
-with csrc/sweep_kernels.cuh — compiled for the CPU emulator (tests/emu/cuda_emu.h for the kernels,
+with csrc/sweep_kernels.cuh, and csrc/gather.cu with gather_kernels.cuh — compiled for the CPU emulator (tests/emu/cuda_emu.h for the kernels,
 tests/emu/cuda_rt_emu.h for the dozen CUDA runtime calls) into tests/emu/libamsweep_emu.so, and the
 GPU parity tests run against it THROUGH THE REAL C-ABI in a child process (AMSWEEP_LIB points the
 ctypes layer at it).  Same sources as the shipped library: only the kernel-launch macro and three
@@ -25,9 +25,9 @@ LIB = os.path.join(EMU, "libamsweep_emu.so")
 
 @pytest.fixture(scope="module")
 def emu_lib():
-    srcs = [os.path.join(CSRC, f) for f in ("sweep.cu", "cron_parse.cpp", "handoff.cpp")] + [
-        os.path.join(EMU, "gather_stub.cpp")]
-    deps = srcs + [os.path.join(CSRC, "sweep_kernels.cuh"), os.path.join(CSRC, "civil.h"),
+    srcs = [os.path.join(CSRC, f) for f in ("sweep.cu", "gather.cu", "cron_parse.cpp", "handoff.cpp")]
+    deps = srcs + [os.path.join(CSRC, "sweep_kernels.cuh"), os.path.join(CSRC, "gather_kernels.cuh"),
+                   os.path.join(CSRC, "civil.h"),
                    os.path.join(EMU, "cuda_emu.h"), os.path.join(EMU, "cuda_rt_emu.h"),
                    os.path.join(ROOT, "include", "amsweep.h")]
     if not os.path.exists(LIB) or any(os.path.getmtime(d) > os.path.getmtime(LIB) for d in deps):
@@ -68,3 +68,15 @@ def test_reconciler_cpp_mirror_on_the_emulated_library(emu_lib):
                     f"-Wl,-rpath,{EMU}", "-pthread", "-o", exe], check=True)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("wire", ["plain", "c3", "bm"])
+@pytest.mark.parametrize("world,idx_bytes,records,ticks", [(2, 4, 20000, 6), (3, 8, 30011, 4), (8, 4, 9000, 4)])
+def test_exchange_through_the_c_abi_with_ranks_as_threads(emu_lib, wire, world, idx_bytes, records, ticks):
+    """am_gather_create / export / connect / set_layout / set_wire / push / out_* of csrc/gather.cu on the
+    emulated library: `world` threads, CUDA-IPC handles carrying plain pointers, no barrier between
+    ticks.  Every rank's output of every tick must be the rank-ordered concatenation."""
+    env = dict(os.environ, AMSWEEP_LIB=emu_lib)
+    out = subprocess.run([sys.executable, os.path.join(EMU, "run_gather_ranks.py"), wire, str(world), str(idx_bytes),
+                          str(records), str(ticks)], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().startswith("ok"), out.stdout[-2000:] + out.stderr[-2000:]
