@@ -19,7 +19,10 @@
 #endif
 
 #include <atomic>
+#include <chrono>
 #include <cstdlib>
+#include <functional>
+#include <random>
 #include <thread>
 #include <vector>
 
@@ -166,6 +169,16 @@ inline void run_block(Block& b) {
   blk = nullptr;
 }
 
+// EMU_JITTER=1: random pauses at launches and at system-scope stores, different per rank thread, so
+// that ranks drift apart by whole kernels — the skew the epoch / double-buffer protocol must survive.
+inline void jitter() {
+  static const bool on = std::getenv("EMU_JITTER") != nullptr;
+  if (!on) return;
+  static thread_local std::mt19937 rng((unsigned)std::hash<std::thread::id>()(std::this_thread::get_id()));
+  const unsigned r = rng();
+  if (r % 4 == 0) std::this_thread::sleep_for(std::chrono::microseconds(r % 1500));
+}
+
 // kernel<<<grid, block>>>(args...) on the calling rank thread
 template <class K, class... A>
 void launch(K kernel, dim3 grid, dim3 block, const A&... args) {
@@ -175,6 +188,7 @@ void launch(K kernel, dim3 grid, dim3 block, const A&... args) {
     b.fibers.resize(block.x);
     for (size_t t = old; t < block.x; ++t) b.fibers[t].stack = (char*)std::malloc(kStack);
   }
+  jitter();
   auto call = [&]() { kernel(args...); };
   b.entry = [](const void* c) { (*(const decltype(call)*)c)(); };
   b.params = &call;
@@ -203,6 +217,7 @@ static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetc
 static inline uint32_t atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 
 static inline void st_release_sys(unsigned long long* p, unsigned long long v) {
+  emu::jitter();
   __atomic_store_n(p, v, __ATOMIC_SEQ_CST);
 }
 static inline unsigned long long ld_acquire_sys(const unsigned long long* p) {

@@ -58,3 +58,14 @@ def test_batches_of_more_than_255_groups_per_cta(emu_bin):
         out = subprocess.run([emu_bin, wire, "2", "4", "2200000", "2", "1", "33"], capture_output=True, text=True,
                              timeout=900)
         assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("wire", ["plain", "c3", "bm"])
+def test_protocol_survives_skew_between_ranks(emu_bin, wire):
+    """EMU_JITTER: random pauses at launches and system-scope stores let ranks drift apart by whole
+    kernels over 25 back-to-back ticks; the epoch / done-flag / double-buffer protocol must still
+    deliver the concatenation on every rank.  (Deleting the done-flag wait from the kernels makes
+    this test fail within two ticks.)"""
+    out = subprocess.run([emu_bin, wire, "4", "4", "12000", "25", "3"], capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, EMU_JITTER="1"))
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
