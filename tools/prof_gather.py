@@ -32,8 +32,10 @@ st = torch.cuda.Stream(device=dev)
 torch.cuda.set_stream(st)
 s.tick_device(T0, 0, d_idx.data_ptr(), d_act.data_ptr(), n, d_cnt.data_ptr(), 0, st.cuda_stream)
 st.synchronize()
-for ib, wire in ((4, "plain"), (4, "c3"), (8, "plain"), (4, "c3")):
-    pg = gather.PeerGather(lr, cap_total=n * world, idx_bytes=ib, shard=(rank * n, n) if wire == "c3" else None)
+CASES = [(4, "plain"), (4, "c3"), (8, "plain")] + ([(4, "bm")] if os.environ.get("AMSWEEP_TEST_EXPERIMENTAL_WIRES") else [])
+for ib, wire in CASES:
+    pg = gather.PeerGather(lr, cap_total=n * world, idx_bytes=ib, shard=(rank * n, n) if wire in ("c3", "bm") else None,
+                           wire="bm" if wire == "bm" else "c3")
     for _ in range(5):
         pg.push(d_idx.data_ptr(), d_act.data_ptr(), d_cnt.data_ptr(), rank * n, st.cuda_stream)
     st.synchronize(); dist.barrier()
@@ -45,7 +47,7 @@ for ib, wire in ((4, "plain"), (4, "c3"), (8, "plain"), (4, "c3")):
     st.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / K
     cnt = int(d_cnt.item())
-    wire_b = 3 if wire == "c3" else ib + 1
+    wire_b = {"c3": 3, "bm": 0.4}.get(wire, ib + 1)  # bytes per entry on the wire (bm: bitmap + non-default actions)
     print(f"rank {rank} idx_bytes {ib} wire {wire}: {us:.1f} us/exchange, {cnt} entries, "
           f"{cnt * wire_b * (world - 1) / us / 1e3:.1f} GB/s out over NVLink", flush=True)
     dist.barrier()
