@@ -80,3 +80,14 @@ def test_exchange_through_the_c_abi_with_ranks_as_threads(emu_lib, wire, world, 
     out = subprocess.run([sys.executable, os.path.join(EMU, "run_gather_ranks.py"), wire, str(world), str(idx_bytes),
                           str(records), str(ticks)], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.strip().startswith("ok"), out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_random_call_sequences_against_a_sequential_model(emu_lib):
+    """tests/emu/fuzz_c_abi.py: random upsert / remove / post_result / read / tick sequences (duplicate
+    slots, results before and after upserts, removes of absent slots, short output buffers, open and
+    closed loop, a shard base) through am.Sweep on the emulated library; every tick and every read must
+    equal the sequential model (calls take effect in call order; a tick is the oracle's sweep)."""
+    env = dict(os.environ, AMSWEEP_LIB=emu_lib)
+    out = subprocess.run([sys.executable, os.path.join(EMU, "fuzz_c_abi.py"), "60", "30", "3000"], cwd=ROOT, env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and out.stdout.strip().startswith("ok"), out.stdout[-2000:] + out.stderr[-3000:]
