@@ -211,7 +211,10 @@ int am_sweep_load_range(am_sweep_t*, uint64_t first, uint64_t n, const am_record
  * local slots idx[i].  Thread-safe; staged and applied by the next tick. */
 int am_sweep_upsert(am_sweep_t*, uint64_t n, const uint64_t* idx, const am_record_t* recs);
 
-/* CR deleted (hcc.go:175-186: Stop() its timer): tombstone the slots. */
+/* CR deleted (hcc.go:175-186: Stop() its timer): tombstone the slots.  A removed
+ * slot reads back as flags == AM_F_TOMBSTONE; its other columns are unspecified
+ * until the next upsert.  Staged calls (upsert / remove / post_result) take effect
+ * per slot in call order at the next tick or read. */
 int am_sweep_remove(am_sweep_t*, uint64_t n, const uint64_t* idx);
 
 /* Terminal workflow phases observed by the watch loops (hcc.go:635, :662,
