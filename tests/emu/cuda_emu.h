@@ -45,6 +45,19 @@ static inline int2 make_int2(int32_t x, int32_t y) { return int2{x, y}; }
 static inline longlong2 make_longlong2(long long x, long long y) { return longlong2{x, y}; }
 struct dim3 { unsigned x = 1, y = 1, z = 1; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 
+#if defined(__SANITIZE_THREAD__)
+// ThreadSanitizer must be told about the hand-made stack switches.  Every switch synchronises (the
+// default), so the fibers of one rank thread are totally ordered and only accesses of DIFFERENT
+// ranks can race: exactly what the flag protocol of the exchange has to order.
+extern "C" {
+void* __tsan_get_current_fiber(void);
+void* __tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void* fiber);
+void __tsan_switch_to_fiber(void* fiber, unsigned flags);
+}
+#define EMU_TSAN 1
+#endif
+
 namespace emu {
 enum State { READY, WAIT_BLOCK, WAIT_WARP, DONE };
 #if defined(__x86_64__)
@@ -80,6 +93,7 @@ struct Context { ucontext_t uc; };
 #endif
 struct Fiber {
   Context ctx;
+  void* tsan = nullptr;
   State state = DONE;
   dim3 tidx;
   unsigned long long slot = 0;  // value deposited for a warp collective
@@ -88,6 +102,7 @@ struct Fiber {
 struct Block {
   std::vector<Fiber> fibers;
   Context sched;
+  void* sched_tsan = nullptr;
   Fiber* cur = nullptr;
   dim3 bidx, bdim, gdim;
   void (*entry)(const void*) = nullptr;
@@ -101,7 +116,12 @@ inline void switch_to(Context& from, Context& to) { emu_switch(&from.sp, to.sp);
 #else
 inline void switch_to(Context& from, Context& to) { swapcontext(&from.uc, &to.uc); }
 #endif
-inline void to_sched() { switch_to(blk->cur->ctx, blk->sched); }
+inline void to_sched() {
+#ifdef EMU_TSAN
+  __tsan_switch_to_fiber(blk->sched_tsan, 0);
+#endif
+  switch_to(blk->cur->ctx, blk->sched);
+}
 inline void yield_spin() { to_sched(); }  // stays READY
 inline void trampoline() {
   blk->entry(blk->params);
@@ -118,6 +138,11 @@ inline void run_block(Block& b) {
     Fiber& f = b.fibers[t];
     f.tidx = dim3(t, 0, 0);
     f.state = READY;
+#ifdef EMU_TSAN
+    if (f.tsan) __tsan_destroy_fiber(f.tsan);
+    f.tsan = __tsan_create_fiber(0);
+    b.sched_tsan = __tsan_get_current_fiber();
+#endif
 #if defined(__x86_64__)
     // first switch "returns" into trampoline with the stack aligned as after a call
     uintptr_t top = ((uintptr_t)f.stack + kStack) & ~(uintptr_t)15;
@@ -141,6 +166,9 @@ inline void run_block(Block& b) {
       Fiber& f = b.fibers[t];
       if (f.state == READY) {
         b.cur = &f;
+#ifdef EMU_TSAN
+        __tsan_switch_to_fiber(f.tsan, 0);
+#endif
         switch_to(b.sched, f.ctx);
       }
       done += f.state == DONE;

@@ -69,3 +69,22 @@ def test_protocol_survives_skew_between_ranks(emu_bin, wire):
     out = subprocess.run([emu_bin, wire, "4", "4", "12000", "25", "3"], capture_output=True, text=True, timeout=600,
                          env=dict(os.environ, EMU_JITTER="1"))
     assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+
+
+def test_flag_protocol_orders_every_cross_rank_access_under_threadsanitizer(tmp_path):
+    """The same harness built with -fsanitize=thread (the emulator tells TSan about its fibers; every
+    fiber switch synchronises, so only accesses of DIFFERENT ranks can race).  System-scope
+    release/acquire are atomics there, everything else — peer payload stores, group counts, bitmaps,
+    output reads — plain memory accesses: a report would mean some cross-rank data is not ordered by
+    the count / done-flag protocol.  (Without the done-flag wait TSan reports a data race at once.)"""
+    exe = str(tmp_path / "emu_gather_tsan.bin")
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-Wno-unknown-pragmas", "-Wno-tsan",
+                        "-pthread", "-I", os.path.join(ROOT, "include"), os.path.join(EMU, "emu_gather.cpp"), "-o", exe],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("ThreadSanitizer runtime not available: " + r.stderr[-300:])
+    for wire in ("plain", "c3", "bm"):
+        out = subprocess.run([exe, wire, "3", "4", "12000", "4", "3"], capture_output=True, text=True, timeout=900,
+                             env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66"))
+        assert "ThreadSanitizer" not in out.stderr, out.stderr[-3000:]
+        assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr[-2000:]
