@@ -91,3 +91,22 @@ def test_random_call_sequences_against_a_sequential_model(emu_lib):
     out = subprocess.run([sys.executable, os.path.join(EMU, "fuzz_c_abi.py"), "60", "30", "3000"], cwd=ROOT, env=env,
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and out.stdout.strip().startswith("ok"), out.stdout[-2000:] + out.stderr[-3000:]
+
+
+def test_threading_contract_under_threadsanitizer(tmp_path):
+    """tests/emu/tsan_c_abi.cpp: four threads stage upserts / removes / results while one thread ticks
+    and reads (the contract of SURVEY 8b), built with -fsanitize=thread from the library's own sources
+    on the emulator.  No ThreadSanitizer report = the host runtime's locking covers every shared access."""
+    exe = str(tmp_path / "tsan_c_abi.bin")
+    srcs = [os.path.join(CSRC, f) for f in ("sweep.cu", "gather.cu", "cron_parse.cpp", "handoff.cpp")] + [
+        os.path.join(EMU, "tsan_c_abi.cpp")]
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-Wno-unknown-pragmas", "-Wno-tsan",
+                        "-pthread", "-DAMSWEEP_EMULATE", "-include", os.path.join(EMU, "cuda_emu.h"),
+                        "-include", os.path.join(EMU, "cuda_rt_emu.h"), "-x", "c++"] + srcs + ["-o", exe],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("ThreadSanitizer runtime not available: " + r.stderr[-300:])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0"))
+    assert "ThreadSanitizer" not in out.stderr, out.stderr[-3000:]
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr[-2000:]
