@@ -59,6 +59,7 @@ struct am_gather {
   void* final_idx[2] = {nullptr, nullptr};  // expanded global indices, by epoch parity
   // bitmap wire format (am_gather_set_wire(AM_WIRE_BITMAP) after set_layout; experimental)
   int wire = AM_WIRE_PLAIN;
+  unsigned long long push_timeout_ms = 5000;  // bitmap format only (AMSWEEP_PUSH_TIMEOUT_MS, 0 = none)
   size_t off_bm[2] = {0, 0};
   uint64_t bm_word0[kMaxWorld] = {};
   std::string last_error;
@@ -107,6 +108,7 @@ int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_
     AMG_CUDA(g, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     g->n_ctas = sms;  // one CTA per SM: the exchange shares the GPU with the next sweep
     if (const char* e = getenv("AMSWEEP_PUSH_CTAS")) { int v = atoi(e); if (v > 0 && v <= 4096) g->n_ctas = v; }
+    if (const char* e = getenv("AMSWEEP_PUSH_TIMEOUT_MS")) { long v = atol(e); if (v >= 0) g->push_timeout_ms = (unsigned long long)v; }
     AMG_CUDA(g, cudaMalloc((void**)&g->block, g->block_bytes));
     AMG_CUDA(g, cudaMemset(g->block, 0, g->block_bytes));
     AMG_CUDA(g, cudaMalloc((void**)&g->out_counts, (kMaxWorld + 1) * 4));
@@ -213,6 +215,7 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
     b.cap_total = g->cap_total;
     for (int k = 0; k < 2; ++k) { b.off_act[k] = g->off_act[k]; b.off_gc[k] = g->off_gc[k]; b.off_bm[k] = g->off_bm[k]; }
     b.bm_word0 = g->bm_word0[g->rank];
+    b.timeout_ns = g->push_timeout_ms * 1000000ull;
     b.epoch = g->epoch;
     b.ngroups_mine = g->ngroups[g->rank];
     b.ngroups_max = g->ngroups_max;

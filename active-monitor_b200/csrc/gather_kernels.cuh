@@ -53,7 +53,27 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-#endif  // the emulator supplies both (tests/emu/cuda_emu.h)
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif  // the emulator supplies all three (tests/emu/cuda_emu.h)
+
+constexpr uint32_t kPeerTimeout = 0xFFFFFFFFu;  // out_counts[world] when a peer did not arrive in time
+
+// Bounded wait for a flag word whose upper (count slots) or whole (done slots) value carries the
+// epoch.  timeout_ns == 0: wait for ever (the validated formats); otherwise give up after that long,
+// so that a peer that died or diverged costs seconds, not a hung GPU.
+__device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned long long want, bool upper_half,
+                                          unsigned long long timeout_ns, unsigned long long* value) {
+  const unsigned long long t0 = timeout_ns ? global_timer_ns() : 0ull;
+  for (;;) {
+    const unsigned long long v = ld_acquire_sys(p);
+    if ((upper_half ? (v >> 32) : v) == want) { *value = v; return true; }
+    if (timeout_ns && global_timer_ns() - t0 > timeout_ns) { *value = v; return false; }
+  }
+}
 
 __global__ void __launch_bounds__(256) gather_push_kernel(const PushParams p) {
   __shared__ uint32_t s_count[kMaxWorld];
@@ -401,6 +421,7 @@ struct PushBmParams {
   uint64_t cap_total;
   size_t off_act[2], off_gc[2], off_bm[2];
   uint64_t bm_word0;      // first bitmap word of this rank's row (sum of earlier ranks' groups * 256)
+  unsigned long long timeout_ns;  // 0 = wait for ever; else give up on a peer after this long
   uint32_t epoch;
   uint32_t ngroups_mine;
   uint32_t ngroups_max;
@@ -420,19 +441,23 @@ __global__ void __launch_bounds__(256) gather_push_bm_kernel(const PushBmParams 
     ExchangeHeader* peer = reinterpret_cast<ExchangeHeader*>(p.peer[tid]);
     st_release_sys(&peer->count_slot[p.rank], ((unsigned long long)p.epoch << 32) | my_count);
   }
+  __shared__ uint32_t s_late;  // a peer's count did not arrive in time: nothing is sent
+  if (tid == 0) s_late = 0;
+  __syncthreads();
   if (tid < p.world) {  // 2. everyone's counts
     unsigned long long v;
-    do { v = ld_acquire_sys(&mine->count_slot[tid]); } while ((uint32_t)(v >> 32) != p.epoch);
+    if (!wait_flag(&mine->count_slot[tid], p.epoch, true, p.timeout_ns, &v)) { v = 0; s_late = 1; }
     s_count[tid] = (uint32_t)v;
   }
   __syncthreads();
+  const bool late = s_late != 0;
   uint64_t offset = 0, total = 0;
   for (int r = 0; r < p.world; ++r) {
     if (r < p.rank) offset += s_count[r];
     total += s_count[r];
   }
   const uint64_t room = offset < p.cap_total ? p.cap_total - offset : 0;
-  const uint32_t n = (uint32_t)(my_count < room ? my_count : room);
+  const uint32_t n = late ? 0u : (uint32_t)(my_count < room ? my_count : room);
 
   // 3a. bitmaps + group counts.  Every CTA owns a contiguous run of this shard's groups,
   //     taken in batches of up to 255: 256 threads find the batch's boundaries in the
@@ -519,11 +544,13 @@ __global__ void __launch_bounds__(256) gather_push_bm_kernel(const PushBmParams 
         ExchangeHeader* peer = reinterpret_cast<ExchangeHeader*>(p.peer[r]);
         st_release_sys(&peer->done_slot[p.rank], (unsigned long long)p.epoch);
       }
+      bool all_done = !late;
       for (int r = 0; r < p.world; ++r) {
-        while (ld_acquire_sys(&mine->done_slot[r]) != (unsigned long long)p.epoch) {}
+        unsigned long long v;
+        if (!wait_flag(&mine->done_slot[r], (unsigned long long)p.epoch, false, p.timeout_ns, &v)) all_done = false;
       }
       for (int r = 0; r < p.world; ++r) p.out_counts[r] = s_count[r];
-      p.out_counts[p.world] = (uint32_t)(total < p.cap_total ? total : p.cap_total);
+      p.out_counts[p.world] = all_done ? (uint32_t)(total < p.cap_total ? total : p.cap_total) : kPeerTimeout;
       mine->cta_done = 0;
       __threadfence();
     }
@@ -553,6 +580,7 @@ __global__ void __launch_bounds__(256) gather_expand_bitmap_kernel(const ExpandB
   const int r = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t g = blockIdx.x;
   if (g >= p.ngroups[r]) return;  // uniform per CTA
+  if (p.counts[p.world] == kPeerTimeout) return;  // the push gave up on a peer: nothing to expand
   const uint32_t* row = p.gc + (size_t)r * p.ngroups_max;
   uint32_t part = 0;
   for (uint32_t j = tid; j < g; j += blockDim.x) part += row[j];

@@ -150,6 +150,9 @@ class PeerGather:
         counts_t = self._wrap(self._lib.am_gather_out_counts(self._h), self.world + 1, torch.int32)
         counts = counts_t.tolist()
         total = counts[self.world]
+        if total & 0xFFFFFFFF == 0xFFFFFFFF:  # bitmap format: the push kernel gave up on a peer
+            raise RuntimeError("PeerGather: a peer did not arrive within AMSWEEP_PUSH_TIMEOUT_MS; the handle is "
+                               "out of step with its peers and must be recreated")
         idt = torch.int64 if self.idx_bytes == 8 else torch.int32
         idx = self._wrap(self._lib.am_gather_out_idx(self._h), max(total, 1), idt)[:total]
         act = self._wrap(self._lib.am_gather_out_act(self._h), max(total, 1), torch.uint8)[:total]

@@ -320,7 +320,9 @@ int am_gather_set_layout(am_gather_t*, const uint64_t* bases, const uint64_t* si
  * selects C3.  BITMAP (after set_layout) is EXPERIMENTAL — one bit per record for the
  * emitted set plus only the non-default action bytes, ~0.4 B per entry at the bench
  * density; implemented after the round-1 GPU budget was spent and not yet run on
- * hardware, so nothing selects it by default. */
+ * hardware, so nothing selects it by default.  Its device-side waits are bounded
+ * (AMSWEEP_PUSH_TIMEOUT_MS, default 5000, 0 = unbounded): a peer that never arrives
+ * leaves out_counts[world] == 0xFFFFFFFF and the handle out of step (recreate it). */
 #define AM_WIRE_PLAIN 0
 #define AM_WIRE_C3 1
 #define AM_WIRE_BITMAP 2

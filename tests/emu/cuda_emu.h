@@ -267,6 +267,11 @@ static inline uint32_t atomicMax(uint32_t* p, uint32_t v) {
   return old;
 }
 
+static inline unsigned long long global_timer_ns() {
+  return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
+             std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 // full-mask warp collectives (every lane of the warp takes part, as in the kernels under test)
 static inline uint32_t __shfl_up_sync(unsigned, uint32_t v, unsigned delta) {
   emu::Block& b = *emu::blk;

@@ -5,6 +5,8 @@
 // output is the rank-ordered concatenation of all ranks' lists.
 //
 //   emu_gather <wire: plain|c3|bm> <world> <idx_bytes: 4|8> <records per rank> <epochs> <ctas> [density% [cap]]
+//   EMU_ABSENT_RANK=r (bm only): rank r never pushes; the others must give up after the watchdog
+//   time-out (200 ms here) and report kPeerTimeout instead of spinning for ever.
 // `cap` (optional) shrinks the output capacity below the total, to exercise the truncation
 // paths: only the first `cap` entries of the concatenation exist then.
 #include "cuda_emu.h"
@@ -101,8 +103,10 @@ int main(int argc, char** argv) {
   }
 
   std::atomic<int> failures{0};
+  const int absent = std::getenv("EMU_ABSENT_RANK") ? std::atoi(std::getenv("EMU_ABSENT_RANK")) : -1;
   auto rank_main = [&](int rank) {
     Rank& me = ranks[rank];
+    if (rank == absent) return;
     for (int e = 1; e <= epochs && !failures.load(); ++e) {
       const Lists mine = make_list(rank, e, (uint32_t)sizes[rank], density);
       const uint32_t count = (uint32_t)mine.idx.size();
@@ -138,6 +142,7 @@ int main(int argc, char** argv) {
         b.out_counts = me.out_counts; b.cap_total = cap_total;
         for (int k = 0; k < 2; ++k) { b.off_act[k] = off_act[k]; b.off_gc[k] = off_gc[k]; b.off_bm[k] = off_bm[k]; }
         b.bm_word0 = bm_word0[rank]; b.epoch = (uint32_t)e; b.ngroups_mine = ngroups[rank];
+        b.timeout_ns = absent >= 0 ? 200000000ull : 0ull;
         b.ngroups_max = ngroups_max; b.rank = rank; b.world = world;
         emu::launch(gather_push_bm_kernel, dim3(ctas), dim3(256), b);
         ExpandBmParams x{};
@@ -150,6 +155,10 @@ int main(int argc, char** argv) {
           if (ngroups[r] > ng_used) ng_used = ngroups[r];
         }
         emu::launch(gather_expand_bitmap_kernel, dim3(ng_used, world), dim3(256), x);
+        if (absent >= 0) {  // a peer is missing: the watchdog must have fired, nothing else is defined
+          if (me.out_counts[world] != kPeerTimeout) failures += fail("expected time-out marker", rank, e, 0);
+          return;
+        }
       }
       // check: my output == concatenation of every rank's list of this epoch
       const void* out_idx = wire == "plain" ? (const void*)(me.block + off_idx[buf]) : me.final_idx[buf];
@@ -173,6 +182,7 @@ int main(int argc, char** argv) {
   for (int r = 0; r < world; ++r) th.emplace_back(rank_main, r);
   for (auto& t : th) t.join();
   if (failures.load()) return 1;
+  if (absent >= 0) { std::printf("ok watchdog: rank %d absent, the others gave up\n", absent); return 0; }
   std::printf("ok %s world=%d idx_bytes=%d records=%u epochs=%d ctas=%d\n", wire.c_str(), world, idx_bytes, n_rec, epochs, ctas);
   return 0;
 }

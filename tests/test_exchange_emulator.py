@@ -88,3 +88,12 @@ def test_flag_protocol_orders_every_cross_rank_access_under_threadsanitizer(tmp_
                              env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66"))
         assert "ThreadSanitizer" not in out.stderr, out.stderr[-3000:]
         assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr[-2000:]
+
+
+def test_bitmap_format_watchdog_gives_up_on_an_absent_peer(emu_bin):
+    """Experimental bitmap kernels only: their spin loops are bounded (AMSWEEP_PUSH_TIMEOUT_MS, 200 ms in
+    the harness).  A rank that never pushes makes the others report kPeerTimeout in out_counts[world]
+    instead of hanging the device."""
+    out = subprocess.run([emu_bin, "bm", "3", "4", "20000", "3", "3"], capture_output=True, text=True, timeout=120,
+                         env=dict(os.environ, EMU_ABSENT_RANK="1"))
+    assert out.returncode == 0 and out.stdout.startswith("ok watchdog"), out.stdout + out.stderr
