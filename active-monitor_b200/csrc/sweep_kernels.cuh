@@ -98,7 +98,12 @@ struct SweepParams {
   unsigned long long* acc;   // [kNumAcc] statistics accumulators (zero on entry)
 };
 
-constexpr int kGroupTiles = 8;  // tiles per compaction group
+#ifndef AM_GROUP_TILES
+#define AM_GROUP_TILES 8  // build-time knob for experiments (<= 32: one warp scans a group's tile counts)
+#endif
+constexpr int kGroupTiles = AM_GROUP_TILES;  // tiles per compaction group
+static_assert(kGroupTiles >= 1 && kGroupTiles <= 32 && (kGroupTiles & (kGroupTiles - 1)) == 0,
+              "the in-group scan is a power-of-two shuffle ladder inside one warp");
 
 struct CompactParams {
   const uint32_t* seg_idx;
