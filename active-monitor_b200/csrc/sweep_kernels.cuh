@@ -520,6 +520,11 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
 }
 
 // ---------------------------------------------------------------------------
+#ifndef AM_COMPACT_UNROLL
+#define AM_COMPACT_UNROLL 4  // independent (index, action) loads in flight per thread; build-time knob
+#endif
+constexpr int kCompactUnroll = AM_COMPACT_UNROLL;
+
 // Segments -> contiguous ascending list.  One CTA per group of kGroupTiles
 // tiles: its global base is the sum of the earlier groups' counts (a few KB of
 // L2-resident reads), the in-group offsets a kGroupTiles-wide scan; entries just written
@@ -559,14 +564,14 @@ __global__ void __launch_bounds__(256) compact_kernel(const CompactParams p) {
   const uint32_t group_total = s_off[kGroupTiles];
 
   // per-thread statistics of the entries it moves: 8 action-bit counts (two words of
-  // four bytes; a thread moves < 64 entries) and the checksums of the global indices
+  // four bytes; a thread moves kGroupTiles*kTile/256 <= 128 entries) and the checksums of the global indices
   uint32_t c0 = 0, c1 = 0;
   unsigned long long cx = 0, cs = 0;
-  // four independent (index, action) loads in flight per thread
-  for (uint32_t e0 = tid; e0 < group_total; e0 += 4u * blockDim.x) {
-    uint32_t src[4], vi[4], va[4];
+  // kCompactUnroll independent (index, action) loads in flight per thread
+  for (uint32_t e0 = tid; e0 < group_total; e0 += (uint32_t)kCompactUnroll * blockDim.x) {
+    uint32_t src[kCompactUnroll], vi[kCompactUnroll], va[kCompactUnroll];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kCompactUnroll; ++u) {
       const uint32_t e = e0 + (uint32_t)u * blockDim.x;
       int tt = 0;  // which tile of the group holds entry e
 #pragma unroll
@@ -574,13 +579,13 @@ __global__ void __launch_bounds__(256) compact_kernel(const CompactParams p) {
       src[u] = (g * kGroupTiles + (uint32_t)tt) * (uint32_t)kTile + (e - s_off[tt]);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kCompactUnroll; ++u) {
       const bool ok = e0 + (uint32_t)u * blockDim.x < group_total;
       vi[u] = ok ? __ldcs(p.seg_idx + src[u]) : 0u;
       va[u] = ok ? (uint32_t)__ldcs(p.seg_act + src[u]) : 0u;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < kCompactUnroll; ++u) {
       const uint32_t e = e0 + (uint32_t)u * blockDim.x;
       const uint32_t pos = base + e;
       if (e < group_total) {
