@@ -58,7 +58,7 @@ def test_config2_mixed(am, orc, gen, T, n):
         _assert_tick_equal(am, s.tick(T + 1), orc.sweep(orac, T + 1), s, orac, n, "second tick")
 
 
-@pytest.mark.parametrize("T", [T0, T_OCT1])
+@pytest.mark.parametrize("T", [T0, T_OCT1, T0 + 1])
 def test_config3_remedy_state_machine_dense_and_sparse(am, orc, gen, T):
     n = 20_000
     prod, orac = _gen_pair(gen, am, orc, 3, 3, n, T0)

@@ -71,10 +71,11 @@ def test_config2_mixed(am, orc, gen, T, n):
         _assert_tick_equal(am, got2, want2, s, orac, n, "config2 second tick")
 
 
-@pytest.mark.parametrize("T", [T0, T_OCT1])
+@pytest.mark.parametrize("T", [T0, T_OCT1, T0 + 1])
 @pytest.mark.parametrize("n", [1000, 300_007])
 def test_config3_remedy_state_machine(am, orc, gen, T, n):
-    """BASELINE configs[2]: 50 % pending Failed, 25 % Succeeded; remedy gate and counters."""
+    """BASELINE configs[2]: 50 % pending Failed, 25 % Succeeded; remedy gate and counters.
+    T0 + 1 is off the minute: the no-masks kernel variant takes the dense result path too."""
     prod, orac = _gen_pair(gen, am, orc, 3, 3, n, T0)
     with am.Sweep(capacity=n) as s:
         s.load_range(0, prod)
