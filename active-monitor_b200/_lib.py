@@ -27,7 +27,7 @@ KIND_NO_RESOURCE, KIND_STOPPED, KIND_INTERVAL, KIND_CRON_SPEC = 0, 1, 2, 3
 KIND_CRON_EVERY, KIND_PARSE_ERROR, KIND_HOST_FALLBACK = 4, 5, 6
 F_HAS_REMEDY, F_PENDING_OK, F_PENDING_FAIL = 1 << 3, 1 << 4, 1 << 5
 F_REMEDY_PENDING, F_REMEDY_OUTCOME_OK = 1 << 6, 1 << 7
-F_TOMBSTONE, F_STOPPED_REPORTED = 1 << 8, 1 << 9
+F_TOMBSTONE, F_STOPPED_REPORTED, F_TIMER_ARMED = 1 << 8, 1 << 9, 1 << 10
 F_FAILP_SHIFT = 16
 
 ACT_SUBMIT_HC, ACT_RUN_REMEDY, ACT_STOPPED, ACT_PARSE_ERROR = 0x01, 0x02, 0x04, 0x08
@@ -36,7 +36,6 @@ ACT_REMEDY_SKIP, ACT_RESET_ON_PASS, ACT_RESET_ON_INTERVAL, ACT_ANOMALY = 0x10, 0
 SWEEP_CLOSED_LOOP, SWEEP_FULL_SCAN = 0x1, 0x2
 PHASE_NONE, PHASE_SUCCEEDED, PHASE_FAILED = 0, 1, 2
 IPC_HANDLE_BYTES = 64
-WIRE_PLAIN, WIRE_C3, WIRE_BITMAP = 0, 1, 2
 
 
 class AmCron(C.Structure):
@@ -52,7 +51,7 @@ class AmHealthCheck(C.Structure):
                 ("finished_at_set", i32), ("remedy_finished_at_set", i32),
                 ("success_count", i64), ("failed_count", i64),
                 ("remedy_success_count", i64), ("remedy_failed_count", i64),
-                ("remedy_total_runs", i64), ("fail_p8", u32), ("reserved", u32)]
+                ("remedy_total_runs", i64), ("fail_p8", u32), ("timer_armed", u32)]
 
 
 class AmRecord(C.Structure):
@@ -99,6 +98,10 @@ WORK_ITEM_DTYPE = np.dtype([("idx", "<u8"), ("unix_sec", "<i8"), ("action", "<u4
 assert WORK_ITEM_DTYPE.itemsize == C.sizeof(AmWorkItem) == 24
 
 
+class AmTickView(C.Structure):
+    _fields_ = [("idx_local", C.c_void_p), ("action", C.c_void_p), ("n", u64), ("shard_base", u64)]
+
+
 class AmTickStats(C.Structure):
     _fields_ = [(n, u64) for n in STAT_FIELDS]
 
@@ -127,6 +130,9 @@ SYMBOLS = {
     "am_sweep_post_result": (C.c_int, [C.c_void_p, u64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "am_sweep_tick": (C.c_int, [C.c_void_p, i64, u32, C.c_void_p, C.c_void_p, u64, P(u64),
                                 P(AmTickStats)]),
+    "am_sweep_tick_view": (C.c_int, [C.c_void_p, i64, u32, P(AmTickView), P(AmTickStats)]),
+    "am_sweep_last_list": (C.c_int, [C.c_void_p, u64, C.c_void_p, C.c_void_p, u64, P(u64)]),
+    "am_sweep_tick_shard": (C.c_int, [C.c_void_p, i64, u32, C.c_void_p]),
     "am_sweep_tick_device": (C.c_int, [C.c_void_p, i64, u32, C.c_void_p, C.c_void_p, u64,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "am_sweep_run_ticks": (C.c_int, [C.c_void_p, i64, u64, u32, u64, C.c_void_p]),
@@ -146,7 +152,7 @@ SYMBOLS = {
     "am_gather_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "am_gather_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "am_gather_set_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "am_gather_set_wire": (C.c_int, [C.c_void_p, C.c_int]),
+    "am_gather_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "am_gather_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, u64, C.c_void_p]),
     "am_gather_out_idx": (C.c_void_p, [C.c_void_p]),
     "am_gather_out_act": (C.c_void_p, [C.c_void_p]),

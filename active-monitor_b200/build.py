@@ -21,6 +21,9 @@ LIB = os.path.join(LIBDIR, "libamsweep.so")
 AMGEN = os.path.join(ROOT, "tools", "amgen", "libamgen.so")
 ORACLE = os.path.join(ROOT, "oracle", "_build", "libamsweep_oracle.so")
 
+SOURCES = ("sweep.cu", "gather.cu", "cron_parse.cpp", "handoff.cpp", "host_loops.cpp")
+HEADERS = ("sweep_kernels.cuh", "sweep_types.h", "sweep_internal.h", "gather_kernels.cuh", "civil.h")
+
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -46,8 +49,8 @@ def _nvcc() -> str:
 
 
 def build_product(force: bool = False, verbose: bool = False) -> str:
-    srcs = [os.path.join(CSRC, f) for f in ("sweep.cu", "gather.cu", "cron_parse.cpp", "handoff.cpp")]
-    deps = srcs + [os.path.join(CSRC, f) for f in ("sweep_kernels.cuh", "gather_kernels.cuh", "civil.h")] + [
+    srcs = [os.path.join(CSRC, f) for f in SOURCES]
+    deps = srcs + [os.path.join(CSRC, f) for f in HEADERS] + [
         os.path.join(ROOT, "include", "amsweep.h")]
     if force or _newer(LIB, deps):
         os.makedirs(LIBDIR, exist_ok=True)

@@ -537,7 +537,8 @@ int am_healthcheck_classify(const am_healthcheck_t* hc, am_record_t* out) {
       out->dow = c.dow;
     }
   }
-  out->flags = kind | (hc->has_remedy ? AM_F_HAS_REMEDY : 0u) | (hc->fail_p8 << AM_F_FAILP_SHIFT);
+  out->flags = kind | (hc->has_remedy ? AM_F_HAS_REMEDY : 0u) | (hc->fail_p8 << AM_F_FAILP_SHIFT) |
+               (hc->timer_armed ? AM_F_TIMER_ARMED : 0u);  // r.GetTimerByName(name) != nil, hcc.go:264
   out->ras = ras;
   out->finished_at = hc->finished_at_set ? hc->finished_at : 0;
   out->remedy_finished_at = hc->remedy_finished_at_set ? hc->remedy_finished_at : 0;

@@ -1,29 +1,29 @@
-// gather.cu — concatenation of the per-GPU due lists over NVLink peer memory.
+// gather.cu — the global ascending due list on every GPU, over NVLink peer memory.
 //
-// The record array shards by contiguous global index range, so
-// the global ascending due list is the rank-ordered concatenation of the local
-// lists.  NCCL has no allgatherv; the portable path (gather.py) pads to the
-// largest count and needs a host round-trip to size the exchange.  Here ONE
-// kernel per tick does the whole exchange through CUDA-IPC-mapped peer memory:
+// The record array shards by contiguous global index range, so the global
+// list is the rank-ordered concatenation of the shards' lists.  NCCL has no allgatherv; the
+// portable path (gather.py) pads to the largest count and needs a host round-trip to size
+// the exchange.  Here the exchange goes through CUDA-IPC-mapped peer memory, with no NCCL
+// call and no host round-trip on the data path, in two forms:
 //
-//   1. every rank stores {epoch, my count} into slot[rank] of every peer's
-//      exchange block (system-scope release);
-//   2. every CTA waits until all `world` counts of this epoch have arrived in
-//      its own block, giving offset = sum(count[r], r < rank) and the total;
-//   3. the CTAs stream the local (u32 local index, u8 action) list and write
-//      (u32|u64 global index, u8 action) at `offset` into EVERY peer's output
-//      buffer, as destination-aligned 16 B + 4 B vector stores — NVSwitch gives
-//      each peer full bandwidth;
-//   4. the last CTA fences (system scope), raises done[rank] on every peer and
-//      waits for all peers' done flags: when the kernel retires, this rank's
-//      output buffer holds the complete global list.
+//   am_gather_exchange (round 2, what bench.py uses)
+//     ships the sweep's own per-tick output — 1 bit per record for the emitted set, the
+//     group offsets, the non-default actions — into a per-rank slot of every peer's exchange
+//     block (gather_push_tick_kernel: 16-B peer stores, system-scope done flags), then every
+//     GPU rebuilds the GLOBAL (index, action) list from the world's bitmaps with the same
+//     expand_kernel that rebuilds a single GPU's list.  ~1.3 MB per 10 M-record shard per
+//     peer instead of 16.7 MB of finished entries.
 //
-// Output buffers are double-buffered by epoch parity: a rank can be at most one
-// epoch ahead of a peer (step 4), and each rank's consumers are stream-ordered
-// before its next push, so epoch e+2 never overwrites data still being read.
+//   am_gather_push (round 1 "plain" format, kept as the measured baseline)
+//     every rank writes its finished (u32|u64 global index, u8 action) list straight into
+//     every peer's output buffer at its global offset (counts exchanged in the same kernel).
 //
-// The reference has no counterpart (single Go process, no collectives); the
-// consumer of the list is createSubmitWorkflow, hcc.go:502.
+// Slot and output buffers are double-buffered by epoch parity: a rank can be at most one
+// epoch ahead of a peer, and each rank's consumers are stream-ordered before its next push,
+// so epoch e+2 never overwrites data still being read.
+//
+// The reference has no counterpart (single Go process, no collectives); the consumer of
+// the list is createSubmitWorkflow, hcc.go:502.
 #ifndef AMSWEEP_EMULATE
 #include <cuda_runtime.h>
 #endif
@@ -36,32 +36,32 @@
 #include <string>
 
 #include "gather_kernels.cuh"
+#include "sweep_internal.h"
+
+using namespace amsweep;
 
 struct am_gather {
   int device = 0, rank = 0, world = 1;
   uint64_t cap_total = 0;
   int idx_bytes = 8;
-  int n_ctas = 296;
+  int n_ctas = 148;
   size_t block_bytes = 0;
   size_t off_idx[2] = {0, 0}, off_act[2] = {0, 0};
   unsigned char* block = nullptr;                 // my exchange block (cudaMalloc, IPC-exported)
   unsigned char* peer[kMaxWorld] = {};            // mapped peers (own = block)
   bool opened[kMaxWorld] = {};
   uint32_t* out_counts = nullptr;
+  uint32_t* status = nullptr;                     // device word: 1 after a peer timed out
   uint32_t epoch = 0;
   bool connected = false;
-  // compressed wire format (enabled by am_gather_set_layout)
-  bool compressed = false;
-  size_t off_gc[2] = {0, 0}, off_o16[2] = {0, 0};
-  uint32_t ngroups_max = 0;
+  // tick exchange (am_gather_set_layout): per-rank slots for bitmap / prefix / tile_exc / exc_seg
+  bool layout = false;
+  size_t slots_off = 0, slots_bytes = 0;          // the slot area of the block (both parities)
   uint64_t bases[kMaxWorld] = {}, sizes[kMaxWorld] = {};
-  uint32_t ngroups[kMaxWorld] = {};
-  void* final_idx[2] = {nullptr, nullptr};  // expanded global indices, by epoch parity
-  // bitmap wire format (am_gather_set_wire(AM_WIRE_BITMAP) after set_layout; experimental)
-  int wire = AM_WIRE_PLAIN;
-  unsigned long long push_timeout_ms = 5000;  // bitmap format only (AMSWEEP_PUSH_TIMEOUT_MS, 0 = none)
-  size_t off_bm[2] = {0, 0};
-  uint64_t bm_word0[kMaxWorld] = {};
+  uint32_t ngroups[kMaxWorld] = {}, ntiles[kMaxWorld] = {};
+  size_t off_bitmap[2][kMaxWorld] = {}, off_prefix[2][kMaxWorld] = {}, off_tile_exc[2][kMaxWorld] = {},
+         off_exc[2][kMaxWorld] = {};
+  unsigned long long push_timeout_ms = 5000;      // AMSWEEP_PUSH_TIMEOUT_MS, 0 = none
   std::string last_error;
 };
 
@@ -76,6 +76,10 @@ struct am_gather {
     }                                                                                           \
   } while (0)
 
+namespace {
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+}  // namespace
+
 extern "C" {
 
 int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_t cap_total,
@@ -87,19 +91,20 @@ int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_
   if (!g) return AM_E_NOMEM;
   g->device = device; g->rank = rank; g->world = world; g->cap_total = cap_total;
   g->idx_bytes = idx_bytes;
-  auto align = [](size_t v) { return (v + 255) / 256 * 256; };
-  size_t off = align(sizeof(ExchangeHeader));
-  for (int b = 0; b < 2; ++b) { g->off_idx[b] = off; off = align(off + cap_total * 8); }
-  for (int b = 0; b < 2; ++b) { g->off_act[b] = off; off = align(off + cap_total); }
-  // compressed wire format: per-group counts [world][ngroups_max] and u16 offsets [cap_total]
-  g->ngroups_max = (uint32_t)((cap_total + kGroupRecords - 1) / kGroupRecords);
-  for (int b = 0; b < 2; ++b) { g->off_gc[b] = off; off = align(off + (size_t)world * g->ngroups_max * 4); }
-  for (int b = 0; b < 2; ++b) { g->off_o16[b] = off; off = align(off + cap_total * 2); }
-  // bitmap wire format: one 1 KB bitmap per 8192-record group of every shard (at most
-  // ngroups_max + world groups in total, whatever the split)
-  for (int b = 0; b < 2; ++b) {
-    g->off_bm[b] = off;
-    off = align(off + ((size_t)g->ngroups_max + (size_t)world) * kGroupWords * 4);
+  size_t off = align256(sizeof(ExchangeHeader));
+  for (int b = 0; b < 2; ++b) { g->off_idx[b] = off; off = align256(off + cap_total * 8); }
+  for (int b = 0; b < 2; ++b) { g->off_act[b] = off; off = align256(off + cap_total); }
+  // Slot area for the tick exchange, sized for ANY split of cap_total records over `world` shards
+  // (the split is only known at am_gather_set_layout, after the block has been exported):
+  // per parity, the groups / tiles of all shards plus one ragged group per shard and padding.
+  {
+    const size_t g_tot = (size_t)((cap_total + kGroupRecords - 1) / kGroupRecords) + (size_t)world;
+    const size_t t_tot = g_tot * kGroupTiles;
+    const size_t per_parity = g_tot * kGroupWords * 4 + (g_tot + (size_t)world) * 4 + t_tot * 4 + t_tot * kTile * 4 +
+                              (size_t)world * 4 * 256;
+    g->slots_off = off;
+    g->slots_bytes = 2 * align256(per_parity);
+    off = align256(off + g->slots_bytes);
   }
   g->block_bytes = off;
   int rc = [&]() -> int {
@@ -113,6 +118,8 @@ int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_
     AMG_CUDA(g, cudaMemset(g->block, 0, g->block_bytes));
     AMG_CUDA(g, cudaMalloc((void**)&g->out_counts, (kMaxWorld + 1) * 4));
     AMG_CUDA(g, cudaMemset(g->out_counts, 0, (kMaxWorld + 1) * 4));
+    AMG_CUDA(g, cudaMalloc((void**)&g->status, 4));
+    AMG_CUDA(g, cudaMemset(g->status, 0, 4));
     AMG_CUDA(g, cudaDeviceSynchronize());
     return AM_OK;
   }();
@@ -150,44 +157,118 @@ int am_gather_connect(am_gather_t* g, const void* handles) {
 
 int am_gather_set_layout(am_gather_t* g, const uint64_t* bases, const uint64_t* sizes) {
   if (!g || !bases || !sizes) return AM_E_INVAL;
-  AMG_CUDA(g, cudaSetDevice(g->device));
+  uint64_t total = 0;
   for (int r = 0; r < g->world; ++r) {
-    const uint64_t ng = (sizes[r] + kGroupRecords - 1) / kGroupRecords;
-    if (ng > g->ngroups_max) return AM_E_RANGE;
+    if (sizes[r] == 0) return AM_E_INVAL;
     if (g->idx_bytes == 4 && bases[r] + sizes[r] > (1ull << 32)) return AM_E_RANGE;
+    total += sizes[r];
+  }
+  if (total > g->cap_total) return AM_E_RANGE;
+  // the same arithmetic on every rank (bases / sizes are all-gathered): identical offsets everywhere
+  size_t off = g->slots_off;
+  for (int b = 0; b < 2; ++b)
+    for (int r = 0; r < g->world; ++r) {
+      const uint32_t ng = groups_of(sizes[r]), nt = tiles_of(sizes[r]);
+      g->off_bitmap[b][r] = off;   off = align256(off + (size_t)ng * kGroupWords * 4);
+      g->off_prefix[b][r] = off;   off = align256(off + ((size_t)ng + 1) * 4);
+      g->off_tile_exc[b][r] = off; off = align256(off + (size_t)nt * 4);
+      g->off_exc[b][r] = off;      off = align256(off + (size_t)nt * kTile * 4);
+    }
+  if (off > g->slots_off + g->slots_bytes) return AM_E_RANGE;
+  for (int r = 0; r < g->world; ++r) {
     g->bases[r] = bases[r];
     g->sizes[r] = sizes[r];
-    g->ngroups[r] = (uint32_t)ng;
+    g->ngroups[r] = groups_of(sizes[r]);
+    g->ntiles[r] = tiles_of(sizes[r]);
   }
-  uint64_t groups_before = 0;
-  for (int r = 0; r < g->world; ++r) {
-    g->bm_word0[r] = groups_before * kGroupWords;
-    groups_before += g->ngroups[r];
-  }
-  if (groups_before > (uint64_t)g->ngroups_max + (uint64_t)g->world) return AM_E_RANGE;
-  for (int b = 0; b < 2; ++b)
-    if (!g->final_idx[b]) AMG_CUDA(g, cudaMalloc(&g->final_idx[b], g->cap_total * (size_t)g->idx_bytes));
-  g->compressed = true;
-  g->wire = AM_WIRE_C3;
+  g->layout = true;
   return AM_OK;
 }
 
-int am_gather_set_wire(am_gather_t* g, int wire) {
-  if (!g) return AM_E_INVAL;
-  if (wire != AM_WIRE_C3 && wire != AM_WIRE_BITMAP) return AM_E_INVAL;  // plain = never call set_layout
-  if (!g->compressed) return AM_E_INVAL;                              // needs the shard layout
-  g->wire = wire;
-  return AM_OK;
+int am_gather_exchange(am_gather_t* g, am_sweep_t* sweep, void* d_stats, void* cuda_stream) {
+  if (!g || !sweep) return AM_E_INVAL;
+  if (!g->layout || (!g->connected && g->world > 1)) return AM_E_INVAL;
+  ShardTick t{};
+  // validate BEFORE the epoch advances: a rank that bumps its epoch without launching would
+  // leave its peers waiting for a done flag that never arrives
+  if (!shard_last_tick(sweep, &t)) { g->last_error = "am_gather_exchange: no am_sweep_tick_shard on this handle yet"; return AM_E_INVAL; }
+  if (t.device != g->device || t.shard_base != g->bases[g->rank] || t.n_records != g->sizes[g->rank]) {
+    g->last_error = "am_gather_exchange: the sweep handle is not this rank's shard (device / base / size differ from set_layout)";
+    return AM_E_INVAL;
+  }
+  AMG_CUDA(g, cudaSetDevice(g->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  if (shard_order_consumer(sweep, st) != AM_OK) { g->last_error = am_last_error_detail(sweep); return AM_E_DEVICE; }
+  g->epoch += 1;
+  if (g->epoch == 0) g->epoch = 2;  // 0 is the "never written" value of the flag words
+  const int buf = g->epoch & 1;
+  PushTickParams p{};
+  for (int r = 0; r < g->world; ++r) p.peer[r] = g->peer[r];
+  p.bitmap = t.out.bitmap;
+  p.group_prefix = t.out.group_prefix;
+  p.tile_exc = t.out.tile_exc;
+  p.exc_seg = t.out.exc_seg;
+  p.off_bitmap = g->off_bitmap[buf][g->rank];
+  p.off_prefix = g->off_prefix[buf][g->rank];
+  p.off_tile_exc = g->off_tile_exc[buf][g->rank];
+  p.off_exc = g->off_exc[buf][g->rank];
+  p.n_groups = t.n_groups;
+  p.n_tiles = t.n_tiles;
+  p.epoch = g->epoch;
+  p.rank = g->rank;
+  p.world = g->world;
+  p.timeout_ns = g->push_timeout_ms * 1000000ull;
+  p.status = g->status;
+  AM_LAUNCH(gather_push_tick_kernel, g->n_ctas, 256, st, p);
+  // every rank's slot in MY block is complete when the push retires: rebuild the global list
+  ExpandParams e{};
+  CountsParams c{};
+  uint32_t ng_max = 1;
+  for (int r = 0; r < g->world; ++r) {
+    ExpandSrc& s = e.src[r];
+    if (r == g->rank) {
+      s.bitmap = t.out.bitmap; s.group_prefix = t.out.group_prefix; s.tile_exc = t.out.tile_exc; s.exc_seg = t.out.exc_seg;
+    } else {
+      s.bitmap = reinterpret_cast<const uint32_t*>(g->block + g->off_bitmap[buf][r]);
+      s.group_prefix = reinterpret_cast<const uint32_t*>(g->block + g->off_prefix[buf][r]);
+      s.tile_exc = reinterpret_cast<const uint32_t*>(g->block + g->off_tile_exc[buf][r]);
+      s.exc_seg = reinterpret_cast<const uint32_t*>(g->block + g->off_exc[buf][r]);
+    }
+    s.base = g->bases[r];
+    s.n_groups = g->ngroups[r];
+    s.n_tiles = g->ntiles[r];
+    c.group_prefix[r] = s.group_prefix;
+    c.n_groups[r] = s.n_groups;
+    if (s.n_groups > ng_max) ng_max = s.n_groups;
+  }
+  e.out_idx = g->block + g->off_idx[buf];
+  e.out_act = g->block + g->off_act[buf];
+  e.acc = t.acc;
+  e.stats_base = g->bases[g->rank];
+  e.cap = g->cap_total;
+  e.world = g->world;
+  e.stats_rank = g->rank;
+  e.idx_bytes = g->idx_bytes;
+  c.out_counts = g->out_counts;
+  c.status = g->status;
+  c.cap_total = g->cap_total;
+  c.world = g->world;
+  AM_LAUNCH(gather_counts_kernel, 1, 32, st, c);
+  AMG_CUDA(g, cudaGetLastError());
+  int rc = shard_launch_expand(sweep, e, ng_max, (uint32_t)g->world, st);
+  if (rc == AM_OK) rc = shard_launch_publish(sweep, t.acc, (am_tick_stats_t*)d_stats, t.n_records, st);
+  if (rc == AM_OK) rc = shard_mark_consumed(sweep, t.parity, st);
+  if (rc != AM_OK) g->last_error = am_last_error_detail(sweep);
+  return rc;
 }
 
 int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_local,
                    const void* d_count_local, uint64_t shard_base, void* cuda_stream) {
   if (!g || !d_idx_local || !d_act_local || !d_count_local) return AM_E_INVAL;
   if (!g->connected && g->world > 1) return AM_E_INVAL;
-  // validate BEFORE the epoch advances: a rank that bumps its epoch without launching
-  // would leave its peers spinning on counts that never arrive
-  if (g->compressed && shard_base != g->bases[g->rank]) return AM_E_INVAL;
-  if (!g->compressed && g->idx_bytes == 4 && shard_base > 0xFFFFFFFFull) return AM_E_RANGE;
+  // validate BEFORE the epoch advances (see am_gather_exchange)
+  if (g->idx_bytes == 4 && shard_base > 0xFFFFFFFFull) return AM_E_RANGE;
+  if (g->layout && g->idx_bytes == 4 && shard_base + g->sizes[g->rank] > (1ull << 32)) return AM_E_RANGE;
   AMG_CUDA(g, cudaSetDevice(g->device));
   PushParams p{};
   for (int r = 0; r < g->world; ++r) p.peer[r] = g->peer[r];
@@ -199,85 +280,7 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
   p.cap_total = g->cap_total;
   for (int b = 0; b < 2; ++b) { p.off_idx[b] = g->off_idx[b]; p.off_act[b] = g->off_act[b]; }
   g->epoch += 1;
-  if (g->epoch == 0) g->epoch = 2;  // keep parity continuity irrelevant: 0 is the "never written" value
-  if (g->compressed && g->wire == AM_WIRE_BITMAP) {
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    const int buf = g->epoch & 1;
-    // default actions: stream-ordered before this rank publishes its count, hence before any
-    // peer stores a non-default action of this epoch into the buffer
-    AMG_CUDA(g, cudaMemsetAsync(g->block + g->off_act[buf], (int)AM_ACT_SUBMIT_HC, g->cap_total, st));
-    PushBmParams b{};
-    for (int r = 0; r < g->world; ++r) b.peer[r] = g->peer[r];
-    b.idx_local = (const uint32_t*)d_idx_local;
-    b.act_local = (const uint8_t*)d_act_local;
-    b.count_local = (const uint32_t*)d_count_local;
-    b.out_counts = g->out_counts;
-    b.cap_total = g->cap_total;
-    for (int k = 0; k < 2; ++k) { b.off_act[k] = g->off_act[k]; b.off_gc[k] = g->off_gc[k]; b.off_bm[k] = g->off_bm[k]; }
-    b.bm_word0 = g->bm_word0[g->rank];
-    b.timeout_ns = g->push_timeout_ms * 1000000ull;
-    b.epoch = g->epoch;
-    b.ngroups_mine = g->ngroups[g->rank];
-    b.ngroups_max = g->ngroups_max;
-    b.rank = g->rank;
-    b.world = g->world;
-    AM_LAUNCH(gather_push_bm_kernel, g->n_ctas, 256, st, b);
-    ExpandBmParams x{};
-    x.bm = reinterpret_cast<const uint32_t*>(g->block + g->off_bm[buf]);
-    x.gc = reinterpret_cast<const uint32_t*>(g->block + g->off_gc[buf]);
-    x.counts = g->out_counts;
-    x.final_idx = g->final_idx[buf];
-    x.cap_total = g->cap_total;
-    x.ngroups_max = g->ngroups_max;
-    x.world = g->world;
-    x.idx_bytes = g->idx_bytes;
-    uint32_t ng_used = 1;
-    for (int r = 0; r < g->world; ++r) {
-      x.ngroups[r] = g->ngroups[r];
-      x.bases[r] = g->bases[r];
-      x.bm_word0[r] = g->bm_word0[r];
-      if (g->ngroups[r] > ng_used) ng_used = g->ngroups[r];
-    }
-    AM_LAUNCH(gather_expand_bitmap_kernel, dim3(ng_used, g->world), 256, st, x);
-    AMG_CUDA(g, cudaGetLastError());
-    return AM_OK;
-  }
-  if (g->compressed) {
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    const int buf = g->epoch & 1;
-    PushC3Params c{};
-    for (int r = 0; r < g->world; ++r) c.peer[r] = g->peer[r];
-    c.idx_local = (const uint32_t*)d_idx_local;
-    c.act_local = (const uint8_t*)d_act_local;
-    c.count_local = (const uint32_t*)d_count_local;
-    c.out_counts = g->out_counts;
-    c.cap_total = g->cap_total;
-    for (int b = 0; b < 2; ++b) { c.off_act[b] = g->off_act[b]; c.off_gc[b] = g->off_gc[b]; c.off_o16[b] = g->off_o16[b]; }
-    c.epoch = g->epoch;
-    c.ngroups_mine = g->ngroups[g->rank];
-    c.ngroups_max = g->ngroups_max;
-    c.rank = g->rank;
-    c.world = g->world;
-    AM_LAUNCH(gather_push_c3_kernel, g->n_ctas, 256, st, c);
-    DecodeParams dp{};
-    dp.o16 = reinterpret_cast<const uint16_t*>(g->block + g->off_o16[buf]);
-    dp.gc = reinterpret_cast<const uint32_t*>(g->block + g->off_gc[buf]);
-    dp.counts = g->out_counts;
-    dp.final_idx = g->final_idx[buf];
-    dp.cap_total = g->cap_total;
-    dp.ngroups_max = g->ngroups_max;
-    dp.world = g->world;
-    dp.idx_bytes = g->idx_bytes;
-    uint32_t ng_used = 1;
-    for (int r = 0; r < g->world; ++r) {
-      dp.ngroups[r] = g->ngroups[r];
-      dp.bases[r] = g->bases[r];
-      if (g->ngroups[r] > ng_used) ng_used = g->ngroups[r];
-    }
-    AM_LAUNCH(gather_decode_kernel, dim3(ng_used, g->world), 256, st, dp);
-    AMG_CUDA(g, cudaGetLastError());
-    return AM_OK;
-  }
+  if (g->epoch == 0) g->epoch = 2;
   p.epoch = g->epoch;
   p.rank = g->rank;
   p.world = g->world;
@@ -287,10 +290,7 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
   return AM_OK;
 }
 
-void* am_gather_out_idx(am_gather_t* g) {
-  if (!g) return nullptr;
-  return g->compressed ? g->final_idx[g->epoch & 1] : (void*)(g->block + g->off_idx[g->epoch & 1]);
-}
+void* am_gather_out_idx(am_gather_t* g) { return g ? (void*)(g->block + g->off_idx[g->epoch & 1]) : nullptr; }
 void* am_gather_out_act(am_gather_t* g) { return g ? g->block + g->off_act[g->epoch & 1] : nullptr; }
 void* am_gather_out_counts(am_gather_t* g) { return g ? g->out_counts : nullptr; }
 const char* am_gather_last_error(const am_gather_t* g) { return g ? g->last_error.c_str() : ""; }
@@ -303,7 +303,7 @@ void am_gather_destroy(am_gather_t* g) {
     if (g->opened[r] && g->peer[r]) cudaIpcCloseMemHandle(g->peer[r]);
   if (g->block) cudaFree(g->block);
   if (g->out_counts) cudaFree(g->out_counts);
-  for (int b = 0; b < 2; ++b) if (g->final_idx[b]) cudaFree(g->final_idx[b]);
+  if (g->status) cudaFree(g->status);
   delete g;
 }
 

@@ -4,8 +4,21 @@
 // SURVEY.md Appendix B.1) on one CUDA device, the staging area for
 // upsert / remove / post_result calls coming from the controller's goroutines
 // (hcc.go:170-188 Reconcile workers, hcc.go:635/:662/:821/:836 watch loops),
-// and the launch of the sweep kernel (sweep_kernels.cuh) that replaces the
+// and the launch of the tick's kernels (sweep_kernels.cuh) that replace the
 // per-CR schedule ladder and remedy state machine for every record at once.
+//
+// Shape of the host side (round 2; profiles/r02_e2e_breakdown.md has the timings):
+//   * staged events are two parallel u32 arrays (+ 96-B records for upserts) in pinned
+//     memory, double-buffered: a tick swaps the buffers under the staging lock and
+//     releases it at once — callers never wait for a copy or a kernel;
+//   * posted events are copied to the device in chunks WHILE they are being posted (copy
+//     stream), so at tick time only the tail is left;
+//   * the list rebuild writes (u32 local index, u8 action) straight into mapped pinned
+//     host memory and the statistics into a mapped struct: ONE stream synchronisation per
+//     tick, no device-to-host copy call, and am_sweep_tick_view hands that memory to the
+//     caller without another pass;
+//   * every device operation of a handle is ordered after the previous one even when they
+//     are issued on different streams (am_sweep_tick_device takes the caller's stream).
 //
 // There is deliberately no CPU path in this file: without a CUDA device
 // am_sweep_create fails with AM_E_DEVICE.
@@ -17,9 +30,17 @@
 #include <string>
 #include <vector>
 
+#include "sweep_internal.h"
 #include "sweep_kernels.cuh"
 
 using namespace amsweep;
+
+namespace amsweep_host {
+unsigned stage_results(uint64_t n, const uint64_t* idx, const uint8_t* phase, const uint8_t* remedy, uint64_t capacity,
+                       uint32_t op_result_kind, uint32_t* op_idx, uint32_t* op_arg);
+void widen_list(uint64_t n, uint64_t base, const uint32_t* idx32, const uint8_t* act8, uint64_t* idx64, uint32_t* act32);
+unsigned stage_slots(uint64_t n, const uint64_t* idx, uint64_t capacity, uint32_t* op_idx);
+}  // namespace amsweep_host
 
 namespace {
 // Reason of the last failed am_sweep_create, process-wide: a cgo caller may be moved to
@@ -34,13 +55,13 @@ void set_create_error(const std::string& s) {
 struct PinnedBuf {
   void* p = nullptr;
   size_t cap = 0;
-  cudaError_t reserve(size_t bytes) {
+  cudaError_t reserve(size_t bytes, unsigned flags = cudaHostAllocDefault) {
     if (bytes <= cap) return cudaSuccess;
     if (p) cudaFreeHost(p);
     p = nullptr;
     cap = 0;
     size_t want = bytes + bytes / 2 + 4096;
-    cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(&p, want, flags);
     if (e == cudaSuccess) cap = want;
     return e;
   }
@@ -61,6 +82,33 @@ struct DevBuf {
   }
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+
+// One of the two staging areas for controller events.  The pinned arrays are appended to
+// under am_sweep::mu; the device twins receive them in chunks on the copy stream.
+struct Staging {
+  PinnedBuf idx, arg, recs;
+  DevBuf d_idx, d_arg, d_recs;
+  size_t n_ops = 0, n_recs = 0;
+  size_t flushed_ops = 0, flushed_recs = 0;  // already enqueued for copy to the device twins
+  uint32_t n_state = 0, n_result = 0;
+  uint64_t hwm = 0;                          // highest upserted slot + 1
+  cudaEvent_t copied = nullptr;              // the last copy out of the pinned arrays
+  bool copy_pending = false;
+  cudaEvent_t drained = nullptr;             // the last kernel that read the device twins
+  bool drain_pending = false;
+};
+
+// One of the two buffer sets a tick writes (by tick parity): a consumer of tick k — the
+// list rebuild, or the NVLink exchange on another stream — overlaps the sweep of tick k+1.
+struct TickSet {
+  TickOut out{};
+  unsigned long long* acc = nullptr;
+  cudaEvent_t consumed = nullptr;
+  bool consumed_pending = false;
+};
+
+constexpr size_t kFlushOps = 32768;   // staged ops per early host-to-device chunk
+constexpr size_t kFlushRecs = 8192;   // staged upsert records per early chunk
 }  // namespace
 
 struct am_sweep {
@@ -70,29 +118,31 @@ struct am_sweep {
   DevCols cols{};
   void* col_ptr[16] = {};
   size_t col_elem[16] = {};
-  uint32_t* seg_idx = nullptr;       // per-tile segments written by the sweep kernel
-  uint8_t* seg_act = nullptr;
-  uint32_t* tile_count = nullptr;    // [tiles]
-  uint32_t* group_count[2] = {nullptr, nullptr};  // [groups], parity = tick number & 1
-  unsigned long long* acc = nullptr;
+  TickSet set[2];
   uint32_t parity = 0;
-  uint32_t* due_idx[2] = {nullptr, nullptr};
+  int last_shard_parity = -1;
+  uint32_t* due_idx[2] = {nullptr, nullptr};   // HBM list ring (streaming mode)
   uint8_t* due_action[2] = {nullptr, nullptr};
+  // host-visible list of the last host tick: mapped pinned memory written by expand_kernel
+  PinnedBuf host_out;
+  uint64_t host_out_entries = 0;  // capacity in entries
+  uint64_t host_n = 0;            // entries of the last host tick
   am_tick_stats_t* h_stats = nullptr;  // pinned + mapped
   am_tick_stats_t* d_stats_mapped = nullptr;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // the handle's own stream
+  cudaStream_t cstream = nullptr;  // staging copies
+  cudaStream_t last_stream = nullptr;  // where the handle's last device operation was issued
+  bool has_last = false;
+  cudaEvent_t ev_last = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaEvent_t evp[3] = {nullptr, nullptr, nullptr};  // profiling: before sweep, between, after compact
+  cudaEvent_t evp[3] = {nullptr, nullptr, nullptr};  // profiling: before sweep, after sweep, after publish
   bool profiling = false, profiled = false;
-  std::mutex mu;  // guards the staged vectors
+  std::mutex mu;  // guards the staging areas
   std::atomic_flag ticking = ATOMIC_FLAG_INIT;
-  // staged controller events in arrival order, written straight into pinned host
-  // memory (the H2D copy at the next tick reads them in place)
-  PinnedBuf st_ops, st_recs;
-  size_t n_ops = 0, n_recs = 0;
-  uint32_t n_state_ops = 0, n_result_ops = 0;
-  uint32_t* marks = nullptr;  // [2 * cap_padded] per-slot {latest state op, latest result} of this tick
-  PinnedBuf pin_in, pin_out;
+  Staging stage[2];
+  int cur = 0;                // the staging area callers append to
+  uint32_t* marks = nullptr;  // [3 * cap_padded] per-slot {latest state op, latest phase, latest remedy phase}
+  PinnedBuf pin_in;
   DevBuf dev_in;
   std::string last_error;
   uint64_t launches = 0;
@@ -143,68 +193,148 @@ struct TickGuard {
   ~TickGuard() { if (ok) h->ticking.clear(std::memory_order_release); }
 };
 
-// Grow a pinned staging array (called under h->mu); keeps the contents.
-cudaError_t grow_pinned(PinnedBuf& b, size_t used_bytes, size_t want_bytes) {
+// Every device operation of a handle is ordered after the previous one.  They normally
+// share a stream; when the stream changes (am_sweep_tick_device on a caller stream, then a
+// read on the handle's own, ...) the new stream waits for an event recorded on the old one.
+int order_on(am_sweep* h, cudaStream_t s) {
+  if (h->has_last && h->last_stream != s) {
+    AM_CUDA(h, cudaEventRecord(h->ev_last, h->last_stream));
+    AM_CUDA(h, cudaStreamWaitEvent(s, h->ev_last, 0));
+  }
+  h->last_stream = s;
+  h->has_last = true;
+  return AM_OK;
+}
+
+// Grow a pinned staging array (called under h->mu); keeps the contents.  Copies out of the
+// old array may still be in flight on the copy stream: wait for them before it is freed.
+cudaError_t grow_pinned(am_sweep* h, PinnedBuf& b, size_t used_bytes, size_t want_bytes, bool copies_in_flight) {
   if (want_bytes <= b.cap) return cudaSuccess;
   void* np = nullptr;
   size_t ncap = want_bytes * 2 + 65536;
   cudaError_t e = cudaHostAlloc(&np, ncap, cudaHostAllocDefault);
   if (e != cudaSuccess) return e;
   if (used_bytes) memcpy(np, b.p, used_bytes);
-  if (b.p) cudaFreeHost(b.p);
+  if (b.p) {
+    if (copies_in_flight) cudaStreamSynchronize(h->cstream);
+    cudaFreeHost(b.p);
+  }
   b.p = np;
   b.cap = ncap;
   return cudaSuccess;
 }
 
-// Apply staged upserts / removes / results (called with the tick guard held).
-int drain_staged(am_sweep* h) {
-  // Hold the staging lock for the H2D enqueue only: the copies read the pinned arrays in
-  // place, and callers may not append until the copy has been consumed.
-  std::unique_lock<std::mutex> lk(h->mu);
-  const size_t n = h->n_ops, nrec = h->n_recs;
-  if (n == 0) return AM_OK;
-  const uint32_t n_state = h->n_state_ops, n_result = h->n_result_ops;
-  const StagedOp* ops = (const StagedOp*)h->st_ops.p;
-  if (n_state)
-    for (size_t k = 0; k < n; ++k)  // every upserted slot extends the swept range (high-water mark)
-      if ((ops[k].arg & kOpKindMask) == kOpUpsert && (uint64_t)ops[k].idx + 1 > h->n_records)
-        h->n_records = (uint64_t)ops[k].idx + 1;
-  const size_t o_rec = (n * sizeof(StagedOp) + 255) / 256 * 256, total = o_rec + nrec * sizeof(am_record_t);
-  AM_CUDA(h, h->dev_in.reserve(total));
-  char* dp = (char*)h->dev_in.p;
-  AM_CUDA(h, cudaMemcpyAsync(dp, h->st_ops.p, n * sizeof(StagedOp), cudaMemcpyHostToDevice, h->stream));
-  if (nrec) AM_CUDA(h, cudaMemcpyAsync(dp + o_rec, h->st_recs.p, nrec * sizeof(am_record_t), cudaMemcpyHostToDevice, h->stream));
-  const StagedOp* d_ops = (const StagedOp*)dp;
-  const am_record_t* d_recs = (const am_record_t*)(dp + o_rec);
+// Enqueue the not-yet-copied part of a staging area on the copy stream, if the device
+// twins are large enough (they are grown at drain time only).  Called under h->mu by the
+// posting threads (chunk threshold) and by the drain (everything).
+cudaError_t flush_staging(am_sweep* h, Staging& st, bool all) {
+  const size_t pend = st.n_ops - st.flushed_ops;
+  if (pend && (all || pend >= kFlushOps) && st.d_idx.cap >= st.n_ops * 4 && st.d_arg.cap >= st.n_ops * 4) {
+    cudaError_t e = cudaMemcpyAsync((uint32_t*)st.d_idx.p + st.flushed_ops, (const uint32_t*)st.idx.p + st.flushed_ops,
+                                    pend * 4, cudaMemcpyHostToDevice, h->cstream);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync((uint32_t*)st.d_arg.p + st.flushed_ops, (const uint32_t*)st.arg.p + st.flushed_ops, pend * 4,
+                        cudaMemcpyHostToDevice, h->cstream);
+    if (e != cudaSuccess) return e;
+    st.flushed_ops = st.n_ops;
+    st.copy_pending = true;
+  }
+  const size_t pr = st.n_recs - st.flushed_recs;
+  if (pr && (all || pr >= kFlushRecs) && st.d_recs.cap >= st.n_recs * sizeof(am_record_t)) {
+    cudaError_t e = cudaMemcpyAsync((am_record_t*)st.d_recs.p + st.flushed_recs,
+                                    (const am_record_t*)st.recs.p + st.flushed_recs, pr * sizeof(am_record_t),
+                                    cudaMemcpyHostToDevice, h->cstream);
+    if (e != cudaSuccess) return e;
+    st.flushed_recs = st.n_recs;
+    st.copy_pending = true;
+  }
+  return cudaSuccess;
+}
+
+// Apply staged upserts / removes / results on stream `s` (called with the tick guard held).
+// The staging lock is held only for the buffer swap.
+int drain_staged(am_sweep* h, cudaStream_t s) {
+  Staging* st;
+  {
+    std::lock_guard<std::mutex> lk(h->mu);
+    st = &h->stage[h->cur];
+    if (st->n_ops == 0) return AM_OK;
+    // callers are about to append to the other area: its previous copies must have left it
+    Staging& nx = h->stage[h->cur ^ 1];
+    if (nx.copy_pending) {
+      AM_CUDA(h, cudaEventSynchronize(nx.copied));
+      nx.copy_pending = false;
+    }
+    // ... and the kernels of its previous drain must be done with its device twins before
+    // the chunked copies of the coming events overwrite them (asynchronous ticks only)
+    if (nx.drain_pending) {
+      AM_CUDA(h, cudaStreamWaitEvent(h->cstream, nx.drained, 0));
+      nx.drain_pending = false;
+    }
+    h->cur ^= 1;
+  }
+  // from here on `st` is private to this (single) ticking thread
+  const size_t n = st->n_ops, nrec = st->n_recs;
+  if (st->hwm > h->n_records) h->n_records = st->hwm;  // every upserted slot extends the swept range
+  if (st->d_idx.cap < n * 4 || st->d_arg.cap < n * 4 || st->d_recs.cap < nrec * sizeof(am_record_t)) {
+    // grow the device twins (frees synchronise) and copy everything again
+    AM_CUDA(h, cudaStreamSynchronize(h->cstream));
+    AM_CUDA(h, st->d_idx.reserve(n * 4));
+    AM_CUDA(h, st->d_arg.reserve(n * 4));
+    AM_CUDA(h, st->d_recs.reserve(nrec * sizeof(am_record_t)));
+    st->flushed_ops = st->flushed_recs = 0;
+  }
+  AM_CUDA(h, flush_staging(h, *st, true));
+  AM_CUDA(h, cudaEventRecord(st->copied, h->cstream));
+  st->copy_pending = true;
+  AM_CUDA(h, cudaStreamWaitEvent(s, st->copied, 0));
+  const uint32_t* d_idx = (const uint32_t*)st->d_idx.p;
+  const uint32_t* d_arg = (const uint32_t*)st->d_arg.p;
+  const am_record_t* d_recs = (const am_record_t*)st->d_recs.p;
   const unsigned B = 256, G = (unsigned)((n + B - 1) / B);
-  AM_LAUNCH(mark_ops_kernel, G, B, h->stream, h->marks, d_ops, (uint32_t)n);
+  AM_LAUNCH(mark_ops_kernel, G, B, s, h->marks, d_idx, d_arg, (uint32_t)n);
   h->launches++;
-  if (n_state) {
-    AM_LAUNCH(apply_state_ops_kernel, G, B, h->stream, h->cols, h->marks, d_ops, d_recs, (uint32_t)n);
+  if (st->n_state) {
+    AM_LAUNCH(apply_state_ops_kernel, G, B, s, h->cols, h->marks, d_idx, d_arg, d_recs, (uint32_t)n);
     h->launches++;
   }
-  if (n_result) {
-    AM_LAUNCH(apply_result_ops_kernel, G, B, h->stream, h->cols.flags, h->marks, d_ops, (uint32_t)n);
+  if (st->n_result) {
+    AM_LAUNCH(apply_result_ops_kernel, G, B, s, h->cols.flags, h->marks, d_idx, d_arg, (uint32_t)n);
     h->launches++;
   }
-  AM_LAUNCH(clear_marks_kernel, G, B, h->stream, h->marks, d_ops, (uint32_t)n);
+  AM_LAUNCH(clear_marks_kernel, G, B, s, h->marks, d_idx, (uint32_t)n);
   h->launches++;
   AM_CUDA(h, cudaGetLastError());
-  // the pinned arrays are refilled by the next calls: wait until the copies were consumed
-  AM_CUDA(h, cudaStreamSynchronize(h->stream));
-  h->n_ops = h->n_recs = 0;
-  h->n_state_ops = h->n_result_ops = 0;
+  AM_CUDA(h, cudaEventRecord(st->drained, s));
+  st->drain_pending = true;
+  st->n_ops = st->n_recs = st->flushed_ops = st->flushed_recs = 0;
+  st->n_state = st->n_result = 0;
+  st->hwm = 0;
   return AM_OK;
 }
 
-int launch_sweep(am_sweep* h, int64_t T, uint32_t mode, uint32_t* d_idx, uint8_t* d_act, uint64_t cap,
-                 am_tick_stats_t* out_stats, uint32_t* out_count, cudaStream_t s) {
+// Where the rebuilt list goes: HBM (device-resident pipelines), mapped host memory (host
+// ticks) or nowhere (am_sweep_tick_shard: the exchange rebuilds the global list).
+struct ListOut {
+  void* idx = nullptr;      // u32 local indices
+  uint8_t* act = nullptr;
+  uint64_t cap = 0;
+  uint32_t* count = nullptr;          // min(n_emitted, cap), device memory, may be NULL
+  am_tick_stats_t* stats = nullptr;   // device or mapped host memory, may be NULL
+  bool expand = true;
+};
+
+int launch_tick(am_sweep* h, int64_t T, uint32_t mode, const ListOut& o, cudaStream_t s) {
   if (h->n_records == 0) {
     // nothing to sweep: publish zeros without a launch
-    if (out_stats) AM_CUDA(h, cudaMemsetAsync(out_stats, 0, sizeof(am_tick_stats_t), s));
-    if (out_count) AM_CUDA(h, cudaMemsetAsync(out_count, 0, 4, s));
+    if (o.stats) AM_CUDA(h, cudaMemsetAsync(o.stats, 0, sizeof(am_tick_stats_t), s));
+    if (o.count) AM_CUDA(h, cudaMemsetAsync(o.count, 0, 4, s));
     return AM_OK;
+  }
+  TickSet& ts = h->set[h->parity];
+  if (ts.consumed_pending) {  // an exchange on another stream may still be reading this buffer set
+    AM_CUDA(h, cudaStreamWaitEvent(s, ts.consumed, 0));
+    ts.consumed_pending = false;
   }
   SweepParams p{};
   p.c = h->cols;
@@ -213,13 +343,10 @@ int launch_sweep(am_sweep* h, int64_t T, uint32_t mode, uint32_t* d_idx, uint8_t
   p.seed = h->seed;
   p.T = T;
   p.words = tick_words_from_unix(T);
-  p.n_tiles = (uint32_t)((h->n_records + kTile - 1) / kTile);
+  p.n_tiles = tiles_of(h->n_records);
   p.mode = mode;
-  p.seg_idx = h->seg_idx;
-  p.seg_act = h->seg_act;
-  p.tile_count = h->tile_count;
-  p.group_count = h->group_count[h->parity];
-  p.acc = h->acc;
+  p.out = ts.out;
+  p.acc = ts.acc;
   if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[0], s));
   // off the minute no 5-field schedule can fire: the mask columns are not read
   int64_t sec_of_min = T % 60;
@@ -231,29 +358,128 @@ int launch_sweep(am_sweep* h, int64_t T, uint32_t mode, uint32_t* d_idx, uint8_t
   else if (masks) AM_LAUNCH(AM_SWEEP_KERNEL(false, true), p.n_tiles, kBlock, s, p);
   else AM_LAUNCH(AM_SWEEP_KERNEL(false, false), p.n_tiles, kBlock, s, p);
   if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[1], s));
-  CompactParams c{};
-  c.seg_idx = h->seg_idx;
-  c.seg_act = h->seg_act;
-  c.tile_count = h->tile_count;
-  c.group_count = h->group_count[h->parity];
-  c.group_count_next = h->group_count[h->parity ^ 1];
-  c.acc = h->acc;
-  c.out_idx = d_idx;
-  c.out_act = d_act;
-  c.shard_base = h->shard_base;
-  c.n_tiles = p.n_tiles;
-  c.n_groups = (p.n_tiles + kGroupTiles - 1) / kGroupTiles;
-  c.cap = (uint32_t)(cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : cap);
-  AM_LAUNCH(compact_kernel, c.n_groups, 256, s, c);
-  AM_LAUNCH(publish_kernel, 1, 32, s, h->acc, out_stats, out_count, h->n_records);
+  ScanParams sc{};
+  sc.group_count = ts.out.group_count;
+  sc.group_prefix = ts.out.group_prefix;
+  sc.acc = ts.acc;
+  sc.out_count = o.count;
+  sc.n_groups = groups_of(h->n_records);
+  sc.cap = (uint32_t)(o.cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : o.cap);
+  AM_LAUNCH_PDL(scan_groups_kernel, 1, 1024, s, sc);
+  h->launches += 2;
+  if (o.expand) {
+    ExpandParams e{};
+    e.src[0].bitmap = ts.out.bitmap;
+    e.src[0].group_prefix = ts.out.group_prefix;
+    e.src[0].tile_exc = ts.out.tile_exc;
+    e.src[0].exc_seg = ts.out.exc_seg;
+    e.src[0].base = 0;  // local indices
+    e.src[0].n_groups = sc.n_groups;
+    e.src[0].n_tiles = p.n_tiles;
+    e.out_idx = o.idx;
+    e.out_act = o.act;
+    e.acc = ts.acc;
+    e.stats_base = h->shard_base;
+    e.cap = o.idx ? o.cap : 0;
+    e.world = 1;
+    e.stats_rank = 0;
+    e.idx_bytes = 4;
+    AM_LAUNCH_PDL(expand_kernel, dim3(sc.n_groups, 1), 256, s, e);
+    AM_LAUNCH_PDL(publish_kernel, 1, 32, s, ts.acc, o.stats, h->n_records);
+    h->launches += 2;
+  }
   if (h->profiling) { AM_CUDA(h, cudaEventRecord(h->evp[2], s)); h->profiled = true; }
   h->parity ^= 1;
-  h->launches += 3;
   AM_CUDA(h, cudaGetLastError());
   return AM_OK;
 }
 
+// mapped pinned memory for the list of a host tick: u32 indices, then u8 actions
+int reserve_host_out(am_sweep* h, uint64_t entries) {
+  if (entries <= h->host_out_entries) return AM_OK;
+  const uint64_t want = (entries + entries / 4 + 4095) / 4096 * 4096;
+  AM_CUDA(h, cudaStreamSynchronize(h->stream));
+  AM_CUDA(h, h->host_out.reserve(want * 5, cudaHostAllocMapped));
+  h->host_out_entries = want;
+  return AM_OK;
+}
+
+// One host tick: drain, four kernels, one synchronisation; the list lands in h->host_out.
+int host_tick(am_sweep* h, int64_t unix_sec, uint32_t mode, am_tick_stats_t* stats) {
+  AM_CUDA(h, cudaSetDevice(h->device));
+  int rc = order_on(h, h->stream);
+  if (rc != AM_OK) return rc;
+  rc = drain_staged(h, h->stream);
+  if (rc != AM_OK) return rc;
+  rc = reserve_host_out(h, h->n_records);
+  if (rc != AM_OK) return rc;
+  ListOut o;
+  if (h->host_out_entries) {
+    void* d = nullptr;
+    AM_CUDA(h, cudaHostGetDevicePointer(&d, h->host_out.p, 0));
+    o.idx = d;
+    o.act = (uint8_t*)d + h->host_out_entries * 4;
+    o.cap = h->host_out_entries;
+  }
+  o.stats = h->d_stats_mapped;
+  AM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
+  rc = launch_tick(h, unix_sec, mode, o, h->stream);
+  if (rc != AM_OK) return rc;
+  AM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
+  AM_CUDA(h, cudaStreamSynchronize(h->stream));
+  float ms = 0;
+  AM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_ms = ms;
+  am_tick_stats_t st = *h->h_stats;
+  st.n_records = h->n_records;
+  h->host_n = st.n_emitted;
+  if (stats) *stats = st;
+  return AM_OK;
+}
+
 }  // namespace
+
+namespace amsweep {
+bool shard_last_tick(am_sweep* h, ShardTick* out) {
+  if (!h || h->last_shard_parity < 0) return false;
+  const TickSet& ts = h->set[h->last_shard_parity];
+  out->out = ts.out;
+  out->acc = ts.acc;
+  out->shard_base = h->shard_base;
+  out->n_records = h->n_records;
+  out->n_groups = groups_of(h->n_records);
+  out->n_tiles = tiles_of(h->n_records);
+  out->parity = h->last_shard_parity;
+  out->device = h->device;
+  return true;
+}
+int shard_order_consumer(am_sweep* h, cudaStream_t s) {
+  if (h->has_last && h->last_stream != s) {
+    AM_CUDA(h, cudaEventRecord(h->ev_last, h->last_stream));
+    AM_CUDA(h, cudaStreamWaitEvent(s, h->ev_last, 0));
+  }
+  return AM_OK;
+}
+int shard_launch_expand(am_sweep* h, const ExpandParams& e, uint32_t groups_x, uint32_t world_y, cudaStream_t s) {
+  AM_LAUNCH(expand_kernel, dim3(groups_x, world_y), 256, s, e);
+  h->launches++;
+  AM_CUDA(h, cudaGetLastError());
+  return AM_OK;
+}
+int shard_launch_publish(am_sweep* h, unsigned long long* acc, am_tick_stats_t* out_stats, uint64_t n_records,
+                         cudaStream_t s) {
+  AM_LAUNCH(publish_kernel, 1, 32, s, acc, out_stats, n_records);
+  h->launches++;
+  AM_CUDA(h, cudaGetLastError());
+  return AM_OK;
+}
+int shard_mark_consumed(am_sweep* h, int parity, cudaStream_t s) {
+  TickSet& ts = h->set[parity & 1];
+  AM_CUDA(h, cudaEventRecord(ts.consumed, s));
+  ts.consumed_pending = true;
+  return AM_OK;
+}
+}  // namespace amsweep
 
 extern "C" {
 
@@ -284,9 +510,16 @@ int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t
   h->shard_base = shard_base;
   int rc = [&]() -> int {
     AM_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    AM_CUDA(h, cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
+    AM_CUDA(h, cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming));
     AM_CUDA(h, cudaEventCreate(&h->ev0));
     AM_CUDA(h, cudaEventCreate(&h->ev1));
     for (int k = 0; k < 3; ++k) AM_CUDA(h, cudaEventCreate(&h->evp[k]));
+    for (int b = 0; b < 2; ++b) {
+      AM_CUDA(h, cudaEventCreateWithFlags(&h->stage[b].copied, cudaEventDisableTiming));
+      AM_CUDA(h, cudaEventCreateWithFlags(&h->stage[b].drained, cudaEventDisableTiming));
+      AM_CUDA(h, cudaEventCreateWithFlags(&h->set[b].consumed, cudaEventDisableTiming));
+    }
     for (int k = 0; k < 16; ++k) {
       void* p = nullptr;
       AM_CUDA(h, cudaMalloc(&p, h->cap_padded * kColElem[k]));
@@ -299,18 +532,23 @@ int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t
     h->launches++;
     const size_t ntiles = h->cap_padded / kTile;
     const size_t ngroups = (ntiles + kGroupTiles - 1) / kGroupTiles;
-    AM_CUDA(h, cudaMalloc((void**)&h->seg_idx, h->cap_padded * 4));
-    AM_CUDA(h, cudaMalloc((void**)&h->seg_act, h->cap_padded));
-    AM_CUDA(h, cudaMalloc((void**)&h->tile_count, ntiles * 4));
-    AM_CUDA(h, cudaMemsetAsync(h->tile_count, 0, ntiles * 4, h->stream));
     for (int b = 0; b < 2; ++b) {
-      AM_CUDA(h, cudaMalloc((void**)&h->group_count[b], ngroups * 4));
-      AM_CUDA(h, cudaMemsetAsync(h->group_count[b], 0, ngroups * 4, h->stream));
+      TickOut& t = h->set[b].out;
+      // bitmap words past the last tile of the last group are never written: they stay zero
+      AM_CUDA(h, cudaMalloc((void**)&t.bitmap, ngroups * kGroupWords * 4));
+      AM_CUDA(h, cudaMemsetAsync(t.bitmap, 0, ngroups * kGroupWords * 4, h->stream));
+      AM_CUDA(h, cudaMalloc((void**)&t.group_count, ngroups * 4));
+      AM_CUDA(h, cudaMemsetAsync(t.group_count, 0, ngroups * 4, h->stream));
+      AM_CUDA(h, cudaMalloc((void**)&t.group_prefix, (ngroups + 1) * 4));
+      AM_CUDA(h, cudaMemsetAsync(t.group_prefix, 0, (ngroups + 1) * 4, h->stream));
+      AM_CUDA(h, cudaMalloc((void**)&t.tile_exc, ntiles * 4));
+      AM_CUDA(h, cudaMemsetAsync(t.tile_exc, 0, ntiles * 4, h->stream));
+      AM_CUDA(h, cudaMalloc((void**)&t.exc_seg, h->cap_padded * 4));
+      AM_CUDA(h, cudaMalloc((void**)&h->set[b].acc, kNumAcc * 8));
+      AM_CUDA(h, cudaMemsetAsync(h->set[b].acc, 0, kNumAcc * 8, h->stream));
     }
-    AM_CUDA(h, cudaMalloc((void**)&h->acc, kNumAcc * 8));
-    AM_CUDA(h, cudaMemsetAsync(h->acc, 0, kNumAcc * 8, h->stream));
-    AM_CUDA(h, cudaMalloc((void**)&h->marks, h->cap_padded * 8));
-    AM_CUDA(h, cudaMemsetAsync(h->marks, 0, h->cap_padded * 8, h->stream));
+    AM_CUDA(h, cudaMalloc((void**)&h->marks, h->cap_padded * 12));
+    AM_CUDA(h, cudaMemsetAsync(h->marks, 0, h->cap_padded * 12, h->stream));
     for (int b = 0; b < 2; ++b) {
       AM_CUDA(h, cudaMalloc((void**)&h->due_idx[b], h->cap_padded * 4));
       AM_CUDA(h, cudaMalloc((void**)&h->due_action[b], h->cap_padded));
@@ -334,25 +572,35 @@ int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t
 void am_sweep_destroy(am_sweep_t* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  if (h->stream) cudaStreamSynchronize(h->stream);
+  cudaDeviceSynchronize();  // ticks may have been issued on caller streams
   for (int k = 0; k < 16; ++k) if (h->col_ptr[k]) cudaFree(h->col_ptr[k]);
-  if (h->seg_idx) cudaFree(h->seg_idx);
-  if (h->seg_act) cudaFree(h->seg_act);
-  if (h->tile_count) cudaFree(h->tile_count);
-  for (int b = 0; b < 2; ++b) if (h->group_count[b]) cudaFree(h->group_count[b]);
-  if (h->acc) cudaFree(h->acc);
-  if (h->marks) cudaFree(h->marks);
   for (int b = 0; b < 2; ++b) {
+    TickOut& t = h->set[b].out;
+    if (t.bitmap) cudaFree(t.bitmap);
+    if (t.group_count) cudaFree(t.group_count);
+    if (t.group_prefix) cudaFree(t.group_prefix);
+    if (t.tile_exc) cudaFree(t.tile_exc);
+    if (t.exc_seg) cudaFree(t.exc_seg);
+    if (h->set[b].acc) cudaFree(h->set[b].acc);
+    if (h->set[b].consumed) cudaEventDestroy(h->set[b].consumed);
     if (h->due_idx[b]) cudaFree(h->due_idx[b]);
     if (h->due_action[b]) cudaFree(h->due_action[b]);
+    Staging& st = h->stage[b];
+    st.idx.release(); st.arg.release(); st.recs.release();
+    st.d_idx.release(); st.d_arg.release(); st.d_recs.release();
+    if (st.copied) cudaEventDestroy(st.copied);
+    if (st.drained) cudaEventDestroy(st.drained);
   }
+  if (h->marks) cudaFree(h->marks);
   if (h->h_stats) cudaFreeHost(h->h_stats);
-  h->pin_in.release(); h->pin_out.release(); h->dev_in.release();
-  h->st_ops.release(); h->st_recs.release();
+  h->host_out.release();
+  h->pin_in.release(); h->dev_in.release();
+  if (h->ev_last) cudaEventDestroy(h->ev_last);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int k = 0; k < 3; ++k) if (h->evp[k]) cudaEventDestroy(h->evp[k]);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->cstream) cudaStreamDestroy(h->cstream);
   delete h;
 }
 
@@ -370,7 +618,7 @@ int am_sweep_set_profiling(am_sweep_t* h, int on) {
   h->profiled = false;
   return AM_OK;
 }
-int am_sweep_last_profile(am_sweep_t* h, double* sweep_ms, double* compact_ms) {
+int am_sweep_last_profile(am_sweep_t* h, double* sweep_ms, double* rest_ms) {
   if (!h || !h->profiled) return AM_E_INVAL;
   AM_CUDA(h, cudaSetDevice(h->device));
   AM_CUDA(h, cudaEventSynchronize(h->evp[2]));
@@ -378,7 +626,7 @@ int am_sweep_last_profile(am_sweep_t* h, double* sweep_ms, double* compact_ms) {
   AM_CUDA(h, cudaEventElapsedTime(&a, h->evp[0], h->evp[1]));
   AM_CUDA(h, cudaEventElapsedTime(&b, h->evp[1], h->evp[2]));
   if (sweep_ms) *sweep_ms = a;
-  if (compact_ms) *compact_ms = b;
+  if (rest_ms) *rest_ms = b;
   return AM_OK;
 }
 void* am_sweep_stream(am_sweep_t* h) { return h ? (void*)h->stream : nullptr; }
@@ -394,6 +642,8 @@ int am_sweep_load_range(am_sweep_t* h, uint64_t first, uint64_t n, const am_reco
   TickGuard g(h);
   if (!g.ok) return AM_E_BUSY;
   AM_CUDA(h, cudaSetDevice(h->device));
+  int rc = order_on(h, h->stream);
+  if (rc != AM_OK) return rc;
   for (int k = 0; k < 16; ++k) {
     char* dst = (char*)h->col_ptr[k] + first * kColElem[k];
     const void* src = *cols_member(cols, k);
@@ -407,72 +657,75 @@ int am_sweep_load_range(am_sweep_t* h, uint64_t first, uint64_t n, const am_reco
 
 int am_sweep_upsert(am_sweep_t* h, uint64_t n, const uint64_t* idx, const am_record_t* recs) {
   if (!h || (n && (!idx || !recs))) return AM_E_INVAL;
-  for (uint64_t k = 0; k < n; ++k)
-    if (idx[k] >= h->capacity) return AM_E_RANGE;
+  if (n == 0) return AM_OK;
   std::lock_guard<std::mutex> lk(h->mu);
-  if (h->n_ops + n > 0x3FFFFFF0ull || h->n_recs + n > 0x3FFFFFF0ull) return AM_E_NOSPACE;
+  Staging& st = h->stage[h->cur];
+  if (st.n_ops + n > 0x3FFFFFF0ull || st.n_recs + n > 0x3FFFFFF0ull) return AM_E_NOSPACE;
   AM_CUDA(h, cudaSetDevice(h->device));
-  AM_CUDA(h, grow_pinned(h->st_ops, h->n_ops * sizeof(StagedOp), (h->n_ops + n) * sizeof(StagedOp)));
-  AM_CUDA(h, grow_pinned(h->st_recs, h->n_recs * sizeof(am_record_t), (h->n_recs + n) * sizeof(am_record_t)));
-  StagedOp* ops = (StagedOp*)h->st_ops.p + h->n_ops;
-  am_record_t* dst = (am_record_t*)h->st_recs.p + h->n_recs;
+  const bool inflight = st.flushed_ops || st.flushed_recs;
+  AM_CUDA(h, grow_pinned(h, st.idx, st.n_ops * 4, (st.n_ops + n) * 4, inflight));
+  AM_CUDA(h, grow_pinned(h, st.arg, st.n_ops * 4, (st.n_ops + n) * 4, inflight));
+  AM_CUDA(h, grow_pinned(h, st.recs, st.n_recs * sizeof(am_record_t), (st.n_recs + n) * sizeof(am_record_t), inflight));
+  uint32_t* oi = (uint32_t*)st.idx.p + st.n_ops;
+  uint32_t* oa = (uint32_t*)st.arg.p + st.n_ops;
+  // nothing is committed (counters unchanged) when a slot is out of range
+  if (amsweep_host::stage_slots(n, idx, h->capacity, oi)) return AM_E_RANGE;
+  am_record_t* dst = (am_record_t*)st.recs.p + st.n_recs;
+  uint64_t hwm = st.hwm;
   for (uint64_t k = 0; k < n; ++k) {
-    ops[k] = StagedOp{(uint32_t)idx[k], kOpUpsert | (uint32_t)(h->n_recs + k)};
+    oa[k] = kOpUpsert | (uint32_t)(st.n_recs + k);
     dst[k] = recs[k];
     dst[k].flags &= ~AM_F_TOMBSTONE;
     dst[k].reserved = 0;
+    if (idx[k] + 1 > hwm) hwm = idx[k] + 1;
   }
-  h->n_ops += n; h->n_recs += n;
-  h->n_state_ops += (uint32_t)n;
+  st.hwm = hwm;
+  st.n_ops += n; st.n_recs += n;
+  st.n_state += (uint32_t)n;
+  AM_CUDA(h, flush_staging(h, st, false));
   return AM_OK;
 }
 
 int am_sweep_remove(am_sweep_t* h, uint64_t n, const uint64_t* idx) {
   if (!h || (n && !idx)) return AM_E_INVAL;
-  for (uint64_t k = 0; k < n; ++k)
-    if (idx[k] >= h->capacity) return AM_E_RANGE;
+  if (n == 0) return AM_OK;
   std::lock_guard<std::mutex> lk(h->mu);
-  if (h->n_ops + n > 0x3FFFFFF0ull) return AM_E_NOSPACE;
+  Staging& st = h->stage[h->cur];
+  if (st.n_ops + n > 0x3FFFFFF0ull) return AM_E_NOSPACE;
   AM_CUDA(h, cudaSetDevice(h->device));
-  AM_CUDA(h, grow_pinned(h->st_ops, h->n_ops * sizeof(StagedOp), (h->n_ops + n) * sizeof(StagedOp)));
-  StagedOp* ops = (StagedOp*)h->st_ops.p + h->n_ops;
-  for (uint64_t k = 0; k < n; ++k) ops[k] = StagedOp{(uint32_t)idx[k], kOpRemove};
-  h->n_ops += n;
-  h->n_state_ops += (uint32_t)n;
+  const bool inflight = st.flushed_ops || st.flushed_recs;
+  AM_CUDA(h, grow_pinned(h, st.idx, st.n_ops * 4, (st.n_ops + n) * 4, inflight));
+  AM_CUDA(h, grow_pinned(h, st.arg, st.n_ops * 4, (st.n_ops + n) * 4, inflight));
+  uint32_t* oi = (uint32_t*)st.idx.p + st.n_ops;
+  uint32_t* oa = (uint32_t*)st.arg.p + st.n_ops;
+  if (amsweep_host::stage_slots(n, idx, h->capacity, oi)) return AM_E_RANGE;
+  for (uint64_t k = 0; k < n; ++k) oa[k] = kOpRemove;
+  st.n_ops += n;
+  st.n_state += (uint32_t)n;
+  AM_CUDA(h, flush_staging(h, st, false));
   return AM_OK;
 }
 
 int am_sweep_post_result(am_sweep_t* h, uint64_t n, const uint64_t* idx, const uint8_t* phase,
                          const uint8_t* remedy_phase) {
   if (!h || (n && (!idx || !phase))) return AM_E_INVAL;
+  if (n == 0) return AM_OK;
   std::lock_guard<std::mutex> lk(h->mu);
-  if (h->n_ops + n > 0x3FFFFFF0ull) return AM_E_NOSPACE;
+  Staging& st = h->stage[h->cur];
+  if (st.n_ops + n > 0x3FFFFFF0ull) return AM_E_NOSPACE;
   AM_CUDA(h, cudaSetDevice(h->device));
-  AM_CUDA(h, grow_pinned(h->st_ops, h->n_ops * sizeof(StagedOp), (h->n_ops + n) * sizeof(StagedOp)));
-  StagedOp* ops = (StagedOp*)h->st_ops.p + h->n_ops;
-  // one pass: validate and stage; nothing is committed (n_ops unchanged) on a bad entry.
+  const bool inflight = st.flushed_ops || st.flushed_recs;
+  AM_CUDA(h, grow_pinned(h, st.idx, st.n_ops * 4, (st.n_ops + n) * 4, inflight));
+  AM_CUDA(h, grow_pinned(h, st.arg, st.n_ops * 4, (st.n_ops + n) * 4, inflight));
+  // one vectorised pass: validate and stage; nothing is committed (n_ops unchanged) on a bad entry.
   // phase -> flag bits: {none, Succeeded, Failed} -> {0, PENDING_OK, PENDING_FAIL}
-  static const uint32_t kPhaseBits[4] = {0u, AM_F_PENDING_OK, AM_F_PENDING_FAIL, 0u};
-  static const uint32_t kRemedyBits[4] = {0u, AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK, AM_F_REMEDY_PENDING, 0u};
-  const uint64_t cap = h->capacity;
-  uint64_t bad_range = 0, bad_phase = 0;
-  if (remedy_phase) {
-    for (uint64_t k = 0; k < n; ++k) {
-      bad_range |= (uint64_t)(idx[k] >= cap);
-      bad_phase |= (uint64_t)(phase[k] > AM_PHASE_FAILED) | (uint64_t)(remedy_phase[k] > AM_PHASE_FAILED);
-      ops[k] = StagedOp{(uint32_t)idx[k], kOpResult | kPhaseBits[phase[k] & 3] | kRemedyBits[remedy_phase[k] & 3]};
-    }
-  } else {
-    for (uint64_t k = 0; k < n; ++k) {
-      bad_range |= (uint64_t)(idx[k] >= cap);
-      bad_phase |= (uint64_t)(phase[k] > AM_PHASE_FAILED);
-      ops[k] = StagedOp{(uint32_t)idx[k], kOpResult | kPhaseBits[phase[k] & 3]};
-    }
-  }
-  if (bad_range) return AM_E_RANGE;
-  if (bad_phase) return AM_E_INVAL;
-  h->n_ops += n;
-  h->n_result_ops += (uint32_t)n;
+  const unsigned bad = amsweep_host::stage_results(n, idx, phase, remedy_phase, h->capacity, kOpResult,
+                                                   (uint32_t*)st.idx.p + st.n_ops, (uint32_t*)st.arg.p + st.n_ops);
+  if (bad & 1u) return AM_E_RANGE;
+  if (bad & 2u) return AM_E_INVAL;
+  st.n_ops += n;
+  st.n_result += (uint32_t)n;
+  AM_CUDA(h, flush_staging(h, st, false));
   return AM_OK;
 }
 
@@ -482,38 +735,45 @@ int am_sweep_tick(am_sweep_t* h, int64_t unix_sec, uint32_t mode, uint64_t* due_
   if (unix_sec >= (1ll << 55) || unix_sec <= -(1ll << 55)) return AM_E_RANGE;
   TickGuard g(h);
   if (!g.ok) return AM_E_BUSY;
-  AM_CUDA(h, cudaSetDevice(h->device));
-  int rc = drain_staged(h);
+  int rc = host_tick(h, unix_sec, mode, stats);
   if (rc != AM_OK) return rc;
-  AM_CUDA(h, cudaEventRecord(h->ev0, h->stream));
-  rc = launch_sweep(h, unix_sec, mode, h->due_idx[0], h->due_action[0], h->cap_padded,
-                    h->d_stats_mapped, nullptr, h->stream);
-  if (rc != AM_OK) return rc;
-  AM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-  AM_CUDA(h, cudaStreamSynchronize(h->stream));
-  float ms = 0;
-  AM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-  h->last_ms = ms;
-  am_tick_stats_t st = *h->h_stats;
-  st.n_records = h->n_records;
-  if (stats) *stats = st;
-  const uint64_t n = st.n_emitted;
+  const uint64_t n = h->host_n;
   if (n_out) *n_out = n;
   const uint64_t ncopy = n < cap ? n : cap;
-  if (ncopy) {
-    AM_CUDA(h, h->pin_out.reserve(ncopy * 5));
-    uint32_t* hi = (uint32_t*)h->pin_out.p;
-    uint8_t* ha = (uint8_t*)h->pin_out.p + ncopy * 4;
-    AM_CUDA(h, cudaMemcpyAsync(hi, h->due_idx[0], ncopy * 4, cudaMemcpyDeviceToHost, h->stream));
-    AM_CUDA(h, cudaMemcpyAsync(ha, h->due_action[0], ncopy, cudaMemcpyDeviceToHost, h->stream));
-    AM_CUDA(h, cudaStreamSynchronize(h->stream));
-    const uint64_t base = h->shard_base;
-    for (uint64_t k = 0; k < ncopy; ++k) {  // widen into the caller's (Go) memory
-      due_idx[k] = base + hi[k];
-      due_action[k] = ha[k];
-    }
-  }
+  if (ncopy)  // widen into the caller's (Go) memory
+    amsweep_host::widen_list(ncopy, h->shard_base, (const uint32_t*)h->host_out.p,
+                             (const uint8_t*)h->host_out.p + h->host_out_entries * 4, due_idx, due_action);
   return n > cap ? AM_E_NOSPACE : AM_OK;
+}
+
+int am_sweep_tick_view(am_sweep_t* h, int64_t unix_sec, uint32_t mode, am_tick_view_t* view,
+                       am_tick_stats_t* stats) {
+  if (!h || !view) return AM_E_INVAL;
+  if (unix_sec >= (1ll << 55) || unix_sec <= -(1ll << 55)) return AM_E_RANGE;
+  TickGuard g(h);
+  if (!g.ok) return AM_E_BUSY;
+  int rc = host_tick(h, unix_sec, mode, stats);
+  if (rc != AM_OK) return rc;
+  view->idx_local = (const uint32_t*)h->host_out.p;
+  view->action = h->host_out.p ? (const uint8_t*)h->host_out.p + h->host_out_entries * 4 : nullptr;
+  view->n = h->host_n;
+  view->shard_base = h->shard_base;
+  return AM_OK;
+}
+
+int am_sweep_last_list(am_sweep_t* h, uint64_t offset, uint64_t* due_idx, uint32_t* due_action,
+                       uint64_t cap, uint64_t* n_out) {
+  if (!h || (cap && (!due_idx || !due_action))) return AM_E_INVAL;
+  TickGuard g(h);
+  if (!g.ok) return AM_E_BUSY;
+  const uint64_t n = h->host_n;
+  if (offset > n) return AM_E_RANGE;
+  const uint64_t left = n - offset, ncopy = left < cap ? left : cap;
+  if (n_out) *n_out = left;
+  if (ncopy)
+    amsweep_host::widen_list(ncopy, h->shard_base, (const uint32_t*)h->host_out.p + offset,
+                             (const uint8_t*)h->host_out.p + h->host_out_entries * 4 + offset, due_idx, due_action);
+  return left > cap ? AM_E_NOSPACE : AM_OK;
 }
 
 int am_sweep_tick_device(am_sweep_t* h, int64_t unix_sec, uint32_t mode, void* d_due_idx,
@@ -524,11 +784,38 @@ int am_sweep_tick_device(am_sweep_t* h, int64_t unix_sec, uint32_t mode, void* d
   TickGuard g(h);
   if (!g.ok) return AM_E_BUSY;
   AM_CUDA(h, cudaSetDevice(h->device));
-  int rc = drain_staged(h);
-  if (rc != AM_OK) return rc;
   cudaStream_t s = (cudaStream_t)cuda_stream;  // NULL == CUDA default stream
-  return launch_sweep(h, unix_sec, mode, (uint32_t*)d_due_idx, (uint8_t*)d_due_action, cap,
-                      (am_tick_stats_t*)d_stats, (uint32_t*)d_count, s);
+  int rc = order_on(h, s);
+  if (rc != AM_OK) return rc;
+  rc = drain_staged(h, s);
+  if (rc != AM_OK) return rc;
+  ListOut o;
+  o.idx = d_due_idx;
+  o.act = (uint8_t*)d_due_action;
+  o.cap = cap;
+  o.count = (uint32_t*)d_count;
+  o.stats = (am_tick_stats_t*)d_stats;
+  return launch_tick(h, unix_sec, mode, o, s);
+}
+
+int am_sweep_tick_shard(am_sweep_t* h, int64_t unix_sec, uint32_t mode, void* cuda_stream) {
+  if (!h) return AM_E_INVAL;
+  if (unix_sec >= (1ll << 55) || unix_sec <= -(1ll << 55)) return AM_E_RANGE;
+  TickGuard g(h);
+  if (!g.ok) return AM_E_BUSY;
+  AM_CUDA(h, cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)cuda_stream;
+  int rc = order_on(h, s);
+  if (rc != AM_OK) return rc;
+  rc = drain_staged(h, s);
+  if (rc != AM_OK) return rc;
+  if (h->n_records == 0) return AM_E_INVAL;  // an empty shard has nothing to exchange
+  ListOut o;
+  o.expand = false;
+  const int parity = (int)h->parity;
+  rc = launch_tick(h, unix_sec, mode, o, s);
+  if (rc == AM_OK) h->last_shard_parity = parity;
+  return rc;
 }
 
 int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint32_t mode,
@@ -540,7 +827,9 @@ int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint3
   TickGuard g(h);
   if (!g.ok) return AM_E_BUSY;
   AM_CUDA(h, cudaSetDevice(h->device));
-  int rc = drain_staged(h);
+  int rc = order_on(h, h->stream);
+  if (rc != AM_OK) return rc;
+  rc = drain_staged(h, h->stream);
   if (rc != AM_OK) return rc;
   h->seed = seed;
   am_tick_stats_t* d_stats = nullptr;
@@ -550,8 +839,12 @@ int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint3
     rc = AM_E_DEVICE;
   }
   for (uint64_t k = 0; k < n_ticks && rc == AM_OK; ++k) {
-    rc = launch_sweep(h, unix_sec0 + (int64_t)k, mode, h->due_idx[k & 1], h->due_action[k & 1],
-                      h->cap_padded, d_stats + k, nullptr, h->stream);
+    ListOut o;
+    o.idx = h->due_idx[k & 1];
+    o.act = h->due_action[k & 1];
+    o.cap = h->cap_padded;
+    o.stats = d_stats + k;
+    rc = launch_tick(h, unix_sec0 + (int64_t)k, mode, o, h->stream);
   }
   if (rc == AM_OK) {
     cudaError_t e = cudaEventRecord(h->ev1, h->stream);
@@ -574,17 +867,19 @@ int am_sweep_repeat_after_sec(am_sweep_t* h, int64_t unix_sec, uint64_t first, u
   TickGuard g(h);
   if (!g.ok) return AM_E_BUSY;
   AM_CUDA(h, cudaSetDevice(h->device));
-  int rc = drain_staged(h);
+  int rc = order_on(h, h->stream);
+  if (rc != AM_OK) return rc;
+  rc = drain_staged(h, h->stream);
   if (rc != AM_OK) return rc;
   AM_CUDA(h, h->dev_in.reserve(n * 8));
-  AM_CUDA(h, h->pin_out.reserve(n * 8));
+  AM_CUDA(h, h->pin_in.reserve(n * 8));
   AM_LAUNCH(next_fire_kernel, (unsigned)((n + 127) / 128), 128, h->stream, h->cols, (uint32_t)first, (uint32_t)n,
             unix_sec, (int64_t*)h->dev_in.p);
   h->launches++;
   AM_CUDA(h, cudaGetLastError());
-  AM_CUDA(h, cudaMemcpyAsync(h->pin_out.p, h->dev_in.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
+  AM_CUDA(h, cudaMemcpyAsync(h->pin_in.p, h->dev_in.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
   AM_CUDA(h, cudaStreamSynchronize(h->stream));
-  memcpy(out, h->pin_out.p, n * 8);
+  memcpy(out, h->pin_in.p, n * 8);
   return AM_OK;
 }
 
@@ -596,7 +891,9 @@ int am_sweep_read(am_sweep_t* h, uint64_t first, uint64_t n, const uint64_t* idx
   if (!g.ok) return AM_E_BUSY;
   AM_CUDA(h, cudaSetDevice(h->device));
   {  // a read observes every upsert / remove / result staged before it
-    int rc = drain_staged(h);
+    int rc = order_on(h, h->stream);
+    if (rc != AM_OK) return rc;
+    rc = drain_staged(h, h->stream);
     if (rc != AM_OK) return rc;
   }
   if (!idx) {

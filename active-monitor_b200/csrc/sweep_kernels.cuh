@@ -29,17 +29,22 @@
 //     (five ANDs, no loop);
 //   * remedy/counter columns are touched only by lanes whose record has a
 //     posted result (or is due, in closed-loop mode): 56 B/record otherwise;
-//   * emitted (index, action) pairs are compacted IN ORDER without any
-//     dependency between CTAs: warp ballots + popc give the in-warp rank, a CTA
-//     scan the in-tile rank, and the tile writes its entries to its own
-//     segment (offset = first record of the tile) plus one count; a second,
-//     tiny kernel (compact_kernel) turns segments into the contiguous ascending
-//     list.  A single-pass decoupled look-back was measured first and rejected:
-//     in-order completion left SM slots idle (profiles/r01a_lookback_sweep_ncu.csv);
-//   * per-tick statistics are reduced lane -> warp (redux) -> CTA (shared
-//     atomics) -> global (fire-and-forget RED); the kernel boundary before
-//     compact_kernel is the only global synchronisation, so the sweep kernel
-//     has one __syncthreads, no fences and no completion tickets.
+//   * the emitted set leaves the kernel as a BITMAP (one bit per record: the four
+//     warp ballots the kernel takes anyway, interleaved into four 32-record words
+//     per warp, one 128-B line per tile) plus a per-tile list of EXCEPTIONS — the
+//     few records whose action is anything but the bare AM_ACT_SUBMIT_HC; no
+//     dependency between CTAs.  scan_groups_kernel (one CTA) turns the per-group
+//     popcounts into exclusive offsets and expand_kernel rebuilds the contiguous
+//     ascending (index, action) list from bitmap + exceptions — for the local shard
+//     or, on several GPUs, for every rank's bitmap after the NVLink exchange
+//     (gather_kernels.cuh): 1 bit per record crosses the wire instead of 5 bytes per
+//     entry.  Round 1 wrote (u32, u8) segments and compacted them (16.7 MB written +
+//     33 MB moved per tick at the bench density); a single-pass decoupled look-back was
+//     measured before that and rejected (profiles/r01a_lookback_sweep_ncu.csv);
+//   * per-tick statistics are reduced lane -> warp (redux) -> CTA -> global (fire-and-
+//     forget RED); kernel boundaries (programmatic dependent launches) are the only
+//     global synchronisation, so the sweep kernel has one __syncthreads, no fences and
+//     no completion tickets.
 #pragma once
 #ifndef AMSWEEP_EMULATE  // tests/emu compiles this file for the CPU (cuda_emu.h supplies the model)
 #include <cuda_runtime.h>
@@ -49,74 +54,9 @@
 #include "../../include/amsweep.h"
 #include "civil.h"
 
-// Kernel launches are spelled through one macro so that tests/emu can compile the host
-// runtime (sweep.cu) for the CPU emulator as well; under nvcc it is the plain <<<>>> launch.
-#ifndef AM_LAUNCH
-#ifndef AMSWEEP_EMULATE
-#define AM_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
-#else
-#define AM_LAUNCH(kernel, grid, block, stream, ...) ((void)(stream), emu::launch(kernel, dim3(grid), dim3(block), __VA_ARGS__))
-#endif
-#endif
-#define AM_SWEEP_KERNEL(closed, masks) sweep_tick_kernel<closed, masks>  // one macro argument
+#include "sweep_types.h"
 
 namespace amsweep {
-
-#ifndef AM_BLOCK
-#define AM_BLOCK 256
-#endif
-constexpr int kBlock = AM_BLOCK;
-constexpr int kWarps = kBlock / 32;
-constexpr int kRecPerWarp = 128;             // 2 halves x 32 lanes x 2 records
-constexpr int kTile = kWarps * kRecPerWarp;  // 1024 records per CTA
-constexpr unsigned kFull = 0xFFFFFFFFu;
-constexpr int kNumAcc = 16;  // == number of u64 fields of am_tick_stats_t
-
-struct DevCols {
-  uint64_t *minute, *hour, *dom, *month, *dow;
-  int32_t* ras;
-  uint32_t* flags;
-  int64_t* finished_at;
-  int32_t *runs_limit, *reset_interval;
-  int32_t *success, *failed, *remedy_success, *remedy_failed, *remedy_total;
-  int64_t* remedy_finished_at;
-};
-
-struct SweepParams {
-  DevCols c;
-  uint64_t n_records;
-  uint64_t shard_base;
-  uint64_t seed;
-  int64_t T;
-  TickWords words;  // T's UTC fields as one-hot words, computed once per tick by the launcher
-  uint32_t n_tiles;
-  uint32_t mode;
-  uint32_t* seg_idx;         // [n_tiles * kTile] per-tile segments of local indices
-  uint8_t* seg_act;          // [n_tiles * kTile] ... and action bytes
-  uint32_t* tile_count;      // [n_tiles] entries emitted by each tile
-  uint32_t* group_count;     // [n_groups] sum of tile_count over kGroupTiles tiles (zero on entry)
-  unsigned long long* acc;   // [kNumAcc] statistics accumulators (zero on entry)
-};
-
-#ifndef AM_GROUP_TILES
-#define AM_GROUP_TILES 8  // build-time knob for experiments (<= 32: one warp scans a group's tile counts)
-#endif
-constexpr int kGroupTiles = AM_GROUP_TILES;  // tiles per compaction group
-static_assert(kGroupTiles >= 1 && kGroupTiles <= 32 && (kGroupTiles & (kGroupTiles - 1)) == 0,
-              "the in-group scan is a power-of-two shuffle ladder inside one warp");
-
-struct CompactParams {
-  const uint32_t* seg_idx;
-  const uint8_t* seg_act;
-  const uint32_t* tile_count;
-  const uint32_t* group_count;  // this tick's group sums
-  uint32_t* group_count_next;   // the other parity: zeroed here for the next tick
-  unsigned long long* acc;      // action-bit counts and index checksums are added here
-  uint32_t* out_idx;            // [cap] ascending local indices
-  uint8_t* out_act;             // [cap]
-  uint64_t shard_base;  // for the global-index checksums
-  uint32_t n_tiles, n_groups, cap;
-};
 
 // ---- streaming loads / stores: every byte is touched once per tick --------
 template <typename T>
@@ -139,7 +79,12 @@ __device__ __forceinline__ void st_keep_u32(uint32_t* p, uint32_t v, uint64_t po
 __device__ __forceinline__ void st_keep_u8(uint8_t* p, uint32_t v, uint64_t pol) {
   asm volatile("st.global.L2::cache_hint.u8 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
 }
+// programmatic dependent launch (sm_90+): see AM_LAUNCH_PDL
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 #else  // CPU emulation: plain stores, the cache policy has no meaning
+inline void pdl_wait() {}
+inline void pdl_trigger() {}
 inline uint64_t l2_evict_last_policy() { return 0; }
 inline void st_keep_u32(uint32_t* p, uint32_t v, uint64_t) { *p = v; }
 inline void st_keep_u8(uint8_t* p, uint32_t v, uint64_t) { *p = (uint8_t)v; }
@@ -153,6 +98,16 @@ __device__ __forceinline__ uint64_t sm64(uint64_t z) {
 }
 __device__ __forceinline__ uint64_t outcome_key(uint64_t seed, uint64_t gidx, uint64_t t) {
   return sm64(sm64(seed ^ sm64(gidx)) + t);
+}
+
+// the low 16 bits of x -> the even bit positions of a 32-bit word
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+  x &= 0xFFFFu;
+  x = (x | (x << 8)) & 0x00FF00FFu;
+  x = (x | (x << 4)) & 0x0F0F0F0Fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
 }
 
 // bit i of a 4-bit value -> byte i of a word (0/1 each)
@@ -182,6 +137,8 @@ __device__ __forceinline__ void remedy_result(RecState& r, int64_t T, bool ok, u
 __device__ __forceinline__ uint32_t apply_result(RecState& r, int64_t T, uint32_t& res) {
   uint32_t act = 0;
   const uint32_t f = r.flags;
+  // watchWorkflowReschedule re-arms the repeat timer after either outcome (hcc.go:745-752)
+  const uint32_t armed = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL)) ? AM_F_TIMER_ARMED : 0u;
   if (f & AM_F_PENDING_OK) {  // hcc.go:635-661
     r.s = (int32_t)((uint32_t)r.s + 1u);
     r.fa = T;
@@ -227,7 +184,7 @@ __device__ __forceinline__ uint32_t apply_result(RecState& r, int64_t T, uint32_
   } else if (f & AM_F_REMEDY_PENDING) {  // remedy finished on its own
     remedy_result(r, T, (f & AM_F_REMEDY_OUTCOME_OK) != 0, res);
   }
-  r.flags = f & ~(AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK);
+  r.flags = (f & ~(AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK)) | armed;
   return act;
 }
 
@@ -246,8 +203,9 @@ template <bool CLOSED, bool MASKS>
 __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS + 1) sweep_tick_kernel(const SweepParams p) {
   // one row per warp, written unconditionally: no zero-initialisation, no shared
   // atomics, and therefore a single __syncthreads in the whole kernel
-  __shared__ uint32_t s_warp_tot[kWarps];
-  __shared__ uint32_t s_wres[kWarps][4];  // posted results applied: ok, fail, remedy ok, remedy fail
+  __shared__ uint32_t s_warp_tot[kWarps], s_warp_exc[kWarps];
+  __shared__ uint32_t s_words[kTileWords];  // the tile's 32 bitmap words
+  __shared__ uint32_t s_wres[kWarps][4];    // posted results applied: ok, fail, remedy ok, remedy fail
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -315,7 +273,11 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
       // step 1 sets finishedAt = T before the due decision is taken
       const int64_t fa_eff = has_result ? T : fav;
       const int64_t elapsed = (int64_t)((uint64_t)T - (uint64_t)fa_eff);
-      const bool due_iv = !(elapsed < (int64_t)rasv);  // not(hcc.go:264) == timer :751 fired
+      // not(hcc.go:264): "elapsed < RepeatAfterSec && timer != nil" skips; a posted result re-arms
+      // the timer in this very tick (step 1 runs first), and without a timer (controller restart,
+      // hcc.go:161) the reference submits whatever finishedAt says
+      const bool armed = has_result || (f & AM_F_TIMER_ARMED) != 0;
+      const bool due_iv = !((elapsed < (int64_t)rasv) & armed);
       bool due_cron = false;
       if (MASKS) {
         const uint64_t miv = j ? mi[h].y : mi[h].x, hrv = j ? hr[h].y : hr[h].x;
@@ -460,23 +422,29 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
     }
   }
 
-  // ---- ordered compaction: in-warp ranks from ballots ---------------------
-  const unsigned lt = (1u << lane) - 1u;
-  const unsigned b00 = __ballot_sync(kFull, act[0][0] != 0), b01 = __ballot_sync(kFull, act[0][1] != 0);
-  const unsigned b10 = __ballot_sync(kFull, act[1][0] != 0), b11 = __ballot_sync(kFull, act[1][1] != 0);
-  const uint32_t tot0 = __popc(b00) + __popc(b01);
-  const uint32_t warp_total = tot0 + __popc(b10) + __popc(b11);
-  uint32_t rank[2][2];
-  rank[0][0] = __popc(b00 & lt) + __popc(b01 & lt);
-  rank[0][1] = rank[0][0] + (act[0][0] != 0);
-  rank[1][0] = tot0 + __popc(b10 & lt) + __popc(b11 & lt);
-  rank[1][1] = rank[1][0] + (act[1][0] != 0);
-  if (lane == 0) s_warp_tot[warp] = warp_total;
+  // ---- the emitted set as a bitmap, non-default actions as exceptions -------------
+  // e..: records with any action; x..: records whose action is not the bare SUBMIT_HC
+  const unsigned e00 = __ballot_sync(kFull, act[0][0] != 0), e01 = __ballot_sync(kFull, act[0][1] != 0);
+  const unsigned e10 = __ballot_sync(kFull, act[1][0] != 0), e11 = __ballot_sync(kFull, act[1][1] != 0);
+  const unsigned x00 = __ballot_sync(kFull, act[0][0] > 1u), x01 = __ballot_sync(kFull, act[0][1] > 1u);
+  const unsigned x10 = __ballot_sync(kFull, act[1][0] > 1u), x11 = __ballot_sync(kFull, act[1][1] > 1u);
+  const uint32_t warp_total = __popc(e00) + __popc(e01) + __popc(e10) + __popc(e11);
+  const uint32_t xtot0 = __popc(x00) + __popc(x01);
+  const uint32_t warp_exc = xtot0 + __popc(x10) + __popc(x11);
+  // Word k of the warp (k = lane < 4) covers its records 32k .. 32k+31: half k>>1, lanes
+  // 16(k&1) .. +15, two records per lane — the two ballots of that half, 16 bits each,
+  // interleaved.
+  if (lane < 4) {
+    const unsigned ea = lane < 2 ? e00 : e10, eb = lane < 2 ? e01 : e11;
+    const unsigned sh = (unsigned)(lane & 1) * 16u;
+    s_words[warp * 4 + lane] = spread16(ea >> sh) | (spread16(eb >> sh) << 1);
+  }
+  if (lane == 0) { s_warp_tot[warp] = warp_total; s_warp_exc[warp] = warp_exc; }
 
   // ---- results applied this tick (feeds metrics.MonitorSuccess/Error): lane ->
   //      warp (two redux over 16-bit halves) -> per-warp shared row.  The action
   //      statistics and index checksums are derived from the emitted entries
-  //      by compact_kernel, so records that emit nothing cost nothing here.
+  //      by expand_kernel, so records that emit nothing cost nothing here.
   {
     uint32_t lo = 0, hi = 0;
     if (__any_sync(kFull, res_lane != 0)) {
@@ -487,122 +455,228 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   }
   __syncthreads();
 
-  // ---- in-tile base, segment write-out, per-tile count ----------------------
+  // ---- tile write-out: one 128-B line of bitmap words, the counts, the exceptions ---
+  // Everything written here is read once, a few tens of microseconds later, by
+  // expand_kernel (and by the NVLink push): keep it L2-resident (evict_last) while the
+  // evict_first column data streams past.
   const uint64_t keep = l2_evict_last_policy();
-  uint32_t base = tile_base, tile_total = 0;
-#pragma unroll
-  for (int k = 0; k < kWarps; ++k) {
-    const uint32_t v = s_warp_tot[k];
-    base += (k < warp) ? v : 0u;
-    tile_total += v;
-  }
-#pragma unroll
-  for (int h = 0; h < 2; ++h)
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-      if (act[h][j]) {
-        const uint32_t pos = base + rank[h][j];
-        st_keep_u32(p.seg_idx + pos, r0[h] + (uint32_t)j, keep);
-        st_keep_u8(p.seg_act + pos, act[h][j], keep);
-      }
-  if (warp == 0) {  // per-tile count, group counter, result counters (RED, no return value)
-    if (lane < 4) {
+  if (warp == 0) {
+    st_keep_u32(p.out.bitmap + (size_t)tile * kTileWords + lane, s_words[lane], keep);
+    if (lane < 4) {  // result counters (RED, no return value)
       uint32_t sv = 0;
 #pragma unroll
       for (int k = 0; k < kWarps; ++k) sv += s_wres[k][lane];
       if (sv) atomicAdd(&p.acc[10 + lane], (unsigned long long)sv);
     }
-    if (lane == 4) {
-      p.tile_count[tile] = tile_total;
-      if (tile_total) atomicAdd(&p.group_count[tile / kGroupTiles], tile_total);
+    if (lane == 4 || lane == 5) {
+      uint32_t tot = 0;
+#pragma unroll
+      for (int k = 0; k < kWarps; ++k) tot += lane == 4 ? s_warp_tot[k] : s_warp_exc[k];
+      if (lane == 4) { if (tot) atomicAdd(&p.out.group_count[tile / kGroupTiles], tot); }
+      else st_keep_u32(p.out.tile_exc + tile, tot, keep);
+    }
+  }
+  if (warp_exc) {  // warp-uniform; rare unless results are being applied
+    uint32_t base = tile_base;
+#pragma unroll
+    for (int k = 0; k < kWarps; ++k) base += (k < warp) ? s_warp_exc[k] : 0u;
+    const unsigned lt = (1u << lane) - 1u;
+    uint32_t rank[2];
+    rank[0] = __popc(x00 & lt) + __popc(x01 & lt);
+    rank[1] = xtot0 + __popc(x10 & lt) + __popc(x11 & lt);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t pos = base + rank[h];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (act[h][j] > 1u) {
+          const uint32_t off = (uint32_t)(warp * kRecPerWarp + h * 64 + lane * 2 + j);  // record within the tile
+          st_keep_u32(p.out.exc_seg + pos, (off << 8) | act[h][j], keep);
+          ++pos;
+        }
     }
   }
 }
 
 // ---------------------------------------------------------------------------
-#ifndef AM_COMPACT_UNROLL
-#define AM_COMPACT_UNROLL 4  // independent (index, action) loads in flight per thread; build-time knob
-#endif
-constexpr int kCompactUnroll = AM_COMPACT_UNROLL;
-
-// Segments -> contiguous ascending list.  One CTA per group of kGroupTiles
-// tiles: its global base is the sum of the earlier groups' counts (a few KB of
-// L2-resident reads), the in-group offsets a kGroupTiles-wide scan; entries just written
-// by the sweep are still in L2.  While moving its entries every thread also counts their
-// action bits and checksums their indices (statistics cost is proportional to what
-// was emitted, not to N); every group zeroes its slot of the other-parity group
-// counters for the next tick.
+// Per-group emitted counts -> exclusive offsets.  One CTA: the array is a few KB (one u32
+// per 8192 records; 1221 for 10 M records) and the work is O(groups) whatever the shard size
+// — round 1 had every compaction CTA re-sum all earlier groups, O(groups^2) loads per tick.
+// Also publishes n_emitted early (acc[1], and min(n_emitted, cap) for device-side consumers
+// of the list) and zeroes the group counters again for the next tick.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) compact_kernel(const CompactParams p) {
-  __shared__ uint32_t s_part[8];
-  __shared__ uint32_t s_off[kGroupTiles + 1];
-  __shared__ uint32_t s_cnt[8][8];               // per-warp counts of the 8 action bits
-  __shared__ unsigned long long s_chk[8][2];     // per-warp xor / sum of emitted global indices
+__global__ void __launch_bounds__(1024) scan_groups_kernel(const ScanParams p) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t g = blockIdx.x;
-
-  uint32_t part = 0;
-  for (uint32_t j = tid; j < g; j += blockDim.x) part += p.group_count[j];
-  part = __reduce_add_sync(kFull, part);
-  if (lane == 0) s_part[warp] = part;
-  if (warp == 0) {  // exclusive scan of this group's tile counts (first kGroupTiles lanes)
-    const uint32_t t = g * kGroupTiles + (uint32_t)lane;
-    const uint32_t c = (lane < kGroupTiles && t < p.n_tiles) ? p.tile_count[t] : 0u;
+  if (tid == 0) s_carry = 0;
+  pdl_wait();  // the sweep's REDs into group_count are complete and visible
+  pdl_trigger();
+  __syncthreads();
+  for (uint32_t g0 = 0; g0 < p.n_groups; g0 += blockDim.x) {
+    const uint32_t g = g0 + (uint32_t)tid;
+    const uint32_t c = g < p.n_groups ? p.group_count[g] : 0u;
     uint32_t incl = c;
 #pragma unroll
-    for (int d = 1; d < kGroupTiles; d <<= 1) {
+    for (int d = 1; d < 32; d <<= 1) {
       const uint32_t up = __shfl_up_sync(kFull, incl, d);
       if (lane >= d) incl += up;
     }
-    if (lane < kGroupTiles) s_off[lane] = incl - c;
-    if (lane == kGroupTiles - 1) s_off[kGroupTiles] = incl;
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan of the 32 warp totals
+      const uint32_t t = s_warp[lane];
+      uint32_t wi = t;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t up = __shfl_up_sync(kFull, wi, d);
+        if (lane >= d) wi += up;
+      }
+      s_warp[lane] = wi - t;
+    }
+    __syncthreads();
+    const uint32_t carry = s_carry;
+    const uint32_t excl = carry + s_warp[warp] + incl - c;
+    if (g < p.n_groups) {
+      p.group_prefix[g] = excl;
+      p.group_count[g] = 0;  // re-armed for the next tick that uses this buffer set
+    }
+    __syncthreads();  // every thread has read s_carry / s_warp of this round
+    if (tid == (int)blockDim.x - 1) s_carry = excl + c;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const uint32_t total = s_carry;
+    p.group_prefix[p.n_groups] = total;
+    p.acc[1] = (unsigned long long)total;  // n_emitted
+    if (p.out_count) *p.out_count = total < p.cap ? total : p.cap;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Bitmap + exceptions -> the contiguous ascending (index, action) list.  One CTA per
+// (group, rank): thread t owns bitmap word t of the group (32 records).  The CTA's position
+// in the output is rank offset + group_prefix[g]; the in-group rank of a set bit is the
+// exclusive popcount prefix of its word (warp shuffles + 8 warp totals) plus the bits below
+// it.  Offsets and action bytes are staged in shared memory — defaults first, then the
+// tile's exceptions patched in by rank lookup — and written out as destination-aligned
+// quads (16 B of indices + 4 B of actions per store), so the same kernel can write into
+// HBM, into a peer-visible exchange buffer or straight into mapped host memory.  While
+// writing, every thread counts action bits and checksums global indices for the shard
+// whose statistics this GPU owns.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) expand_kernel(const ExpandParams p) {
+  __shared__ uint16_t s_off[kGroupRecords];  // in-group record offsets of the set bits, ascending (16 KB)
+  __shared__ uint8_t s_act[kGroupRecords];   // their action bytes (8 KB)
+  __shared__ uint32_t s_w[kGroupWords];
+  __shared__ uint16_t s_wpre[kGroupWords];
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_cnt[8][8];            // per-warp counts of the 8 action bits
+  __shared__ unsigned long long s_chk[8][2];  // per-warp xor / sum of emitted global indices
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r = blockIdx.y;
+  const uint32_t g = blockIdx.x;
+  const ExpandSrc& src = p.src[r];
+  if (g >= src.n_groups) return;  // uniform per CTA
+  pdl_wait();
+  pdl_trigger();
+  uint64_t start = src.group_prefix[g];
+  const uint32_t cnt = src.group_prefix[g + 1] - (uint32_t)start;
+  if (cnt == 0) return;  // uniform per CTA: nothing emitted by these 8192 records
+  for (int q = 0; q < r; ++q) start += p.src[q].group_prefix[p.src[q].n_groups];
+
+  // ---- ranks: exclusive popcount prefix over the group's 256 words
+  const uint32_t w = __ldcs(src.bitmap + (size_t)g * kGroupWords + tid);
+  const uint32_t c = (uint32_t)__popc(w);
+  uint32_t incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t up = __shfl_up_sync(kFull, incl, d);
+    if (lane >= d) incl += up;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t before = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) before += k < warp ? s_warp[k] : 0u;
+  const uint32_t excl = before + incl - c;
+  s_w[tid] = w;
+  s_wpre[tid] = (uint16_t)excl;
+  {
+    uint32_t ww = w, pos = excl;
+    while (ww) {
+      const uint32_t b = (uint32_t)__ffs((int)ww) - 1u;
+      ww &= ww - 1u;
+      s_off[pos] = (uint16_t)((uint32_t)tid * 32u + b);
+      s_act[pos] = (uint8_t)AM_ACT_SUBMIT_HC;
+      ++pos;
+    }
   }
   __syncthreads();
-  uint32_t base = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) base += s_part[k];
-  const uint32_t group_total = s_off[kGroupTiles];
+  // ---- exceptions of the group's tiles: action bytes other than the default
+  for (uint32_t tt = 0; tt < (uint32_t)kGroupTiles; ++tt) {
+    const uint32_t tile = g * kGroupTiles + tt;
+    if (tile >= src.n_tiles) break;
+    const uint32_t nx = src.tile_exc[tile];
+    for (uint32_t i = tid; i < nx; i += blockDim.x) {
+      const uint32_t e = __ldcs(src.exc_seg + (size_t)tile * kTile + i);
+      const uint32_t off = tt * (uint32_t)kTile + (e >> 8);
+      const uint32_t wd = off >> 5;
+      const uint32_t rk = (uint32_t)s_wpre[wd] + (uint32_t)__popc(s_w[wd] & ((1u << (off & 31u)) - 1u));
+      s_act[rk] = (uint8_t)e;
+    }
+  }
+  __syncthreads();
 
-  // per-thread statistics of the entries it moves: 8 action-bit counts (two words of
-  // four bytes; a thread moves kGroupTiles*kTile/256 <= 128 entries) and the checksums of the global indices
+  // ---- write-out: destination-aligned quads
+  const bool stats = p.acc != nullptr && r == p.stats_rank;
+  const uint64_t obase = src.base + (uint64_t)g * kGroupRecords;
+  const uint64_t sbase = p.stats_base + (uint64_t)g * kGroupRecords;
+  const uint64_t end = start + cnt;
   uint32_t c0 = 0, c1 = 0;
   unsigned long long cx = 0, cs = 0;
-  // kCompactUnroll independent (index, action) loads in flight per thread
-  for (uint32_t e0 = tid; e0 < group_total; e0 += (uint32_t)kCompactUnroll * blockDim.x) {
-    uint32_t src[kCompactUnroll], vi[kCompactUnroll], va[kCompactUnroll];
+  for (uint64_t q = (start >> 2) + (uint64_t)tid; q < ((end + 3) >> 2); q += blockDim.x) {
+    const uint64_t pos0 = q << 2;
+    uint32_t off[4], a4 = 0;
 #pragma unroll
-    for (int u = 0; u < kCompactUnroll; ++u) {
-      const uint32_t e = e0 + (uint32_t)u * blockDim.x;
-      int tt = 0;  // which tile of the group holds entry e
-#pragma unroll
-      for (int k = 1; k < kGroupTiles; ++k) tt += (e >= s_off[k]) ? 1 : 0;
-      src[u] = (g * kGroupTiles + (uint32_t)tt) * (uint32_t)kTile + (e - s_off[tt]);
-    }
-#pragma unroll
-    for (int u = 0; u < kCompactUnroll; ++u) {
-      const bool ok = e0 + (uint32_t)u * blockDim.x < group_total;
-      vi[u] = ok ? __ldcs(p.seg_idx + src[u]) : 0u;
-      va[u] = ok ? (uint32_t)__ldcs(p.seg_act + src[u]) : 0u;
-    }
-#pragma unroll
-    for (int u = 0; u < kCompactUnroll; ++u) {
-      const uint32_t e = e0 + (uint32_t)u * blockDim.x;
-      const uint32_t pos = base + e;
-      if (e < group_total) {
-        c0 += spread4(va[u]);
-        c1 += spread4(va[u] >> 4);
-        const unsigned long long gi = p.shard_base + vi[u];
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t pos = pos0 + (uint64_t)k;
+      const bool in = pos >= start && pos < end;
+      const uint32_t e = in ? (uint32_t)(pos - start) : 0u;
+      off[k] = in ? (uint32_t)s_off[e] : 0u;
+      const uint32_t a = in ? (uint32_t)s_act[e] : 0u;
+      a4 |= a << (8 * k);
+      if (stats && in) {
+        c0 += spread4(a);
+        c1 += spread4(a >> 4);
+        const unsigned long long gi = sbase + off[k];
         cx ^= gi;
         cs += gi;
-        if (pos < p.cap) {
-          p.out_idx[pos] = vi[u];
-          p.out_act[pos] = (uint8_t)va[u];
-        }
+      }
+    }
+    if (pos0 >= start && pos0 + 4 <= end && pos0 + 4 <= p.cap) {
+      if (p.idx_bytes == 4) {
+        const uint32_t b32 = (uint32_t)obase;
+        reinterpret_cast<uint4*>(p.out_idx)[q] = make_uint4(b32 + off[0], b32 + off[1], b32 + off[2], b32 + off[3]);
+      } else {
+        ulonglong2* d = reinterpret_cast<ulonglong2*>(p.out_idx) + 2 * q;
+        d[0] = make_ulonglong2(obase + off[0], obase + off[1]);
+        d[1] = make_ulonglong2(obase + off[2], obase + off[3]);
+      }
+      reinterpret_cast<uint32_t*>(p.out_act)[q] = a4;
+    } else {  // ragged first / last quad of the group, or the end of a short buffer
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint64_t pos = pos0 + (uint64_t)k;
+        if (pos < start || pos >= end || pos >= p.cap) continue;
+        if (p.idx_bytes == 4) reinterpret_cast<uint32_t*>(p.out_idx)[pos] = (uint32_t)(obase + off[k]);
+        else reinterpret_cast<uint64_t*>(p.out_idx)[pos] = obase + off[k];
+        p.out_act[pos] = (uint8_t)(a4 >> (8 * k));
       }
     }
   }
-  // statistics: thread -> warp (redux; 16-bit fields so 32 lanes x 63 fit) -> CTA -> global RED
-  if (group_total) {
+  // statistics: thread -> warp (redux; 16-bit fields: 32 lanes x 32 entries fit) -> CTA -> global RED
+  if (stats) {
     const uint32_t a0 = __reduce_add_sync(kFull, (c0 & 0xFFu) | ((c0 & 0xFF00u) << 8));
     const uint32_t a1 = __reduce_add_sync(kFull, ((c0 >> 16) & 0xFFu) | ((c0 >> 8) & 0xFF0000u));
     const uint32_t a2 = __reduce_add_sync(kFull, (c1 & 0xFFu) | ((c1 & 0xFF00u) << 8));
@@ -612,8 +686,8 @@ __global__ void __launch_bounds__(256) compact_kernel(const CompactParams p) {
 #pragma unroll
     for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(kFull, sum, d);
     if (lane < 8) {
-      const uint32_t q = lane < 2 ? a0 : (lane < 4 ? a1 : (lane < 6 ? a2 : a3));
-      s_cnt[warp][lane] = (q >> ((lane & 1) * 16)) & 0xFFFFu;
+      const uint32_t qv = lane < 2 ? a0 : (lane < 4 ? a1 : (lane < 6 ? a2 : a3));
+      s_cnt[warp][lane] = (qv >> ((lane & 1) * 16)) & 0xFFFFu;
     }
     if (lane == 0) { s_chk[warp][0] = ((unsigned long long)xh << 32) | xl; s_chk[warp][1] = sum; }
     __syncthreads();
@@ -631,22 +705,18 @@ __global__ void __launch_bounds__(256) compact_kernel(const CompactParams p) {
       atomicAdd(&p.acc[15], t);
     }
   }
-  if (tid == 0) p.group_count_next[g] = 0;
-
-  if (g == p.n_groups - 1 && tid == 0) p.acc[1] = (unsigned long long)base + group_total;  // n_emitted
 }
 
-// One warp, after the kernel boundary that completes every group's REDs: publish the
+// One warp, after the kernel boundary that completes every expand CTA's REDs: publish the
 // tick's am_tick_stats_t (device or mapped-host memory) and re-arm the accumulators.
-__global__ void publish_kernel(unsigned long long* acc, am_tick_stats_t* out_stats, uint32_t* out_count,
-                               uint64_t n_records) {
+__global__ void publish_kernel(unsigned long long* acc, am_tick_stats_t* out_stats, uint64_t n_records) {
   const int k = threadIdx.x;
   if (k >= kNumAcc) return;
+  pdl_wait();
   unsigned long long v = acc[k];
   acc[k] = 0;
   if (k == 0) v = n_records;
   if (out_stats) reinterpret_cast<unsigned long long*>(out_stats)[k] = v;
-  if (k == 1 && out_count) *out_count = (uint32_t)v;
 }
 
 // ---- small maintenance kernels (create / read) -----------------------------
@@ -680,36 +750,41 @@ __global__ void next_fire_kernel(DevCols c, uint32_t first, uint32_t n, int64_t 
 // ---- staged controller events (upsert / remove / post_result) ---------------
 // Events reach the library from many goroutines between two ticks; per slot
 // they must take effect in call order.  An event's tick-local sequence number
-// is its position in the staged array (1-based).  mark: atomicMax of the sequence into the slot's
-// mark pair {latest upsert/remove, latest result}; apply: only the marked
-// winners write — the latest upsert/remove, then the latest result if it was
-// posted after it (an older result belongs to the replaced CR); clear: marks
-// back to zero.  No host-side hashing or sorting.
-struct StagedOp {
-  uint32_t idx;  // local slot
-  uint32_t arg;  // kind in the top 2 bits; low 30 bits: record index (upsert) or flag bits (result)
-};               // the sequence number of an op is its position in the array + 1
+// is its position in the staged arrays (1-based).  mark: atomicMax of the sequence into
+// the slot's mark triple {latest upsert/remove, latest workflow phase, latest remedy
+// phase}; apply: only the marked winners write — the latest upsert/remove, then the latest
+// workflow phase and the latest remedy phase if they were posted after it (an older
+// result belongs to the replaced CR).  The two phases are tracked independently: the
+// reference observes them in separate watch loops (hcc.go:607-756 and :788-852), so a
+// "Failed" and a remedy "Succeeded" posted by two calls before one tick must both
+// survive.  clear: marks back to zero.  No host-side hashing or sorting.
+// Staged ops are two parallel u32 arrays (slot, arg): arg = kind in the top 2 bits; low
+// 30 bits: record index (upsert) or flag bits (result).
 constexpr uint32_t kOpUpsert = 0u << 30, kOpRemove = 1u << 30, kOpResult = 2u << 30, kOpKindMask = 3u << 30;
+constexpr uint32_t kHcBits = AM_F_PENDING_OK | AM_F_PENDING_FAIL;
+constexpr uint32_t kRemedyBits = AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK;
 
-__global__ void mark_ops_kernel(uint32_t* marks, const StagedOp* __restrict__ ops, uint32_t n) {
+__global__ void mark_ops_kernel(uint32_t* marks, const uint32_t* __restrict__ op_idx,
+                                const uint32_t* __restrict__ op_arg, uint32_t n) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const StagedOp op = ops[k];
-  atomicMax(&marks[2u * op.idx + ((op.arg & kOpKindMask) == kOpResult ? 1u : 0u)], k + 1u);
+  const uint32_t i = op_idx[k], arg = op_arg[k];
+  if ((arg & kOpKindMask) != kOpResult) { atomicMax(&marks[3u * i], k + 1u); return; }
+  if (arg & kHcBits) atomicMax(&marks[3u * i + 1u], k + 1u);
+  if (arg & AM_F_REMEDY_PENDING) atomicMax(&marks[3u * i + 2u], k + 1u);
 }
 
 // upserts (hcc.go:170-188 Reconcile) and removes (hcc.go:175-186)
 __global__ void apply_state_ops_kernel(DevCols c, const uint32_t* __restrict__ marks,
-                                       const StagedOp* __restrict__ ops,
+                                       const uint32_t* __restrict__ op_idx, const uint32_t* __restrict__ op_arg,
                                        const am_record_t* __restrict__ recs, uint32_t n) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const StagedOp op = ops[k];
-  const uint32_t kind = op.arg & kOpKindMask;
-  if (kind == kOpResult || marks[2u * op.idx] != k + 1u) return;
-  const uint32_t i = op.idx;
+  const uint32_t i = op_idx[k], arg = op_arg[k];
+  const uint32_t kind = arg & kOpKindMask;
+  if (kind == kOpResult || marks[3u * i] != k + 1u) return;
   if (kind == kOpRemove) { c.flags[i] = AM_F_TOMBSTONE; return; }
-  const am_record_t r = recs[op.arg & ~kOpKindMask];
+  const am_record_t r = recs[arg & ~kOpKindMask];
   c.minute[i] = r.minute; c.hour[i] = r.hour; c.dom[i] = r.dom; c.month[i] = r.month; c.dow[i] = r.dow;
   c.ras[i] = r.ras; c.flags[i] = r.flags; c.finished_at[i] = r.finished_at;
   c.runs_limit[i] = r.runs_limit; c.reset_interval[i] = r.reset_interval;
@@ -718,25 +793,34 @@ __global__ void apply_state_ops_kernel(DevCols c, const uint32_t* __restrict__ m
   c.remedy_finished_at[i] = r.remedy_finished_at;
 }
 
-// terminal phases observed by the watch loops (hcc.go:635/:662/:821/:836)
+// terminal phases observed by the watch loops (hcc.go:635/:662/:821/:836).  The winner of
+// the workflow phase and the winner of the remedy phase may be two different ops of the
+// same slot: each rewrites only its own bit group, atomically.
 __global__ void apply_result_ops_kernel(uint32_t* flags, const uint32_t* __restrict__ marks,
-                                        const StagedOp* __restrict__ ops, uint32_t n) {
+                                        const uint32_t* __restrict__ op_idx, const uint32_t* __restrict__ op_arg,
+                                        uint32_t n) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const StagedOp op = ops[k];
-  if ((op.arg & kOpKindMask) != kOpResult) return;
-  const uint32_t s = marks[2u * op.idx], r = marks[2u * op.idx + 1u];
-  if (r != k + 1u || k + 1u < s) return;
-  const uint32_t m = AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK;
-  flags[op.idx] = (flags[op.idx] & ~m) | (op.arg & m);
+  const uint32_t i = op_idx[k], arg = op_arg[k];
+  if ((arg & kOpKindMask) != kOpResult) return;
+  const uint32_t s = marks[3u * i];
+  if (k + 1u < s) return;  // posted before the slot's latest upsert / remove
+  uint32_t clr = 0, set = 0;
+  if ((arg & kHcBits) && marks[3u * i + 1u] == k + 1u) { clr |= kHcBits; set |= arg & kHcBits; }
+  if ((arg & AM_F_REMEDY_PENDING) && marks[3u * i + 2u] == k + 1u) { clr |= kRemedyBits; set |= arg & kRemedyBits; }
+  if (clr) {
+    atomicAnd(&flags[i], ~clr);
+    atomicOr(&flags[i], set);
+  }
 }
 
-__global__ void clear_marks_kernel(uint32_t* marks, const StagedOp* __restrict__ ops, uint32_t n) {
+__global__ void clear_marks_kernel(uint32_t* marks, const uint32_t* __restrict__ op_idx, uint32_t n) {
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const uint32_t i = ops[k].idx;
-  marks[2u * i] = 0;
-  marks[2u * i + 1u] = 0;
+  const uint32_t i = op_idx[k];
+  marks[3u * i] = 0;
+  marks[3u * i + 1u] = 0;
+  marks[3u * i + 2u] = 0;
 }
 
 __global__ void gather_records_kernel(DevCols c, const uint32_t* __restrict__ idx, am_record_t* out,

@@ -57,21 +57,15 @@ def allgather_due(idx_local: torch.Tensor, act_local: torch.Tensor, count, shard
 
 
 class PeerGather:
-    """B200-native due-list concatenation: one kernel per tick writes every
-    rank's list straight into every peer's output buffer over NVLink
-    (csrc/gather.cu), replacing the counts all-gather + host sync + padded
-    all-gather above.  torch.distributed is used once, at set-up, to swap the
-    CUDA-IPC handles."""
+    """B200-native global due list: per tick every rank ships its sweep's own output (1 bit per
+    record + the non-default actions) into every peer over NVLink and rebuilds the global
+    (index, action) list locally (csrc/gather.cu: am_gather_exchange), replacing the counts
+    all-gather + host sync + padded all-gather above.  torch.distributed is used once, at
+    set-up, to swap the CUDA-IPC handles and the shard layout.  `push` is the round-1 list
+    format (finished entries on the wire), kept as the measured baseline."""
 
-    def __init__(self, device_index: int, cap_total: int, group=None, idx_bytes: int = 8,
-                 shard=None, wire: str = "c3"):
-        """shard=(first global index, number of records) of this rank switches on the
-        compressed wire format (3 B per entry over NVLink: u16 offsets within
-        8192-record groups + per-group counts, expanded on every receiver).
-        wire="bm" (with `shard`) selects the EXPERIMENTAL bitmap format instead (one bit
-        per record + non-default actions only; not yet run on hardware)."""
-        if wire not in ("c3", "bm"):
-            raise ValueError("wire must be 'c3' or 'bm'")
+    def __init__(self, device_index: int, cap_total: int, group=None, idx_bytes: int = 8, shard=None):
+        """shard=(first global index, number of records) of this rank: required for `exchange`."""
         import ctypes as C
 
         from . import _lib as L
@@ -107,7 +101,7 @@ class PeerGather:
             dist.all_gather_object(handles, bytes(mine.raw), group=group)
             rc = self._lib.am_gather_connect(self._h, b"".join(handles))
             agree(rc == 0, "am_gather_connect (CUDA IPC peer mapping)")
-        self.compressed = shard is not None
+        self.has_layout = shard is not None
         if shard is not None:
             import numpy as np
             mine_t = torch.tensor([int(shard[0]), int(shard[1])], dtype=torch.int64, device=self.device)
@@ -117,17 +111,19 @@ class PeerGather:
             else:
                 all_t.copy_(mine_t)
             lay = all_t.cpu().numpy().astype(np.uint64).reshape(self.world, 2)
-            bases = np.ascontiguousarray(lay[:, 0])
-            sizes = np.ascontiguousarray(lay[:, 1])
-            rc = self._lib.am_gather_set_layout(self._h, bases.ctypes.data, sizes.ctypes.data)
+            self.bases = np.ascontiguousarray(lay[:, 0])
+            self.sizes = np.ascontiguousarray(lay[:, 1])
+            rc = self._lib.am_gather_set_layout(self._h, self.bases.ctypes.data, self.sizes.ctypes.data)
             agree(rc == 0, "am_gather_set_layout")
-            if wire == "bm":
-                rc = self._lib.am_gather_set_wire(self._h, L.WIRE_BITMAP)
-                agree(rc == 0, "am_gather_set_wire")
 
     def _check(self, rc, where):
         if rc != 0:
             raise RuntimeError(f"{where}: {rc}: {self._lib.am_gather_last_error(self._h).decode()}")
+
+    def exchange(self, sweep, d_stats_ptr: int = 0, stream: int = 0):
+        """after sweep.tick_shard(): ship this shard's bitmap + exceptions, rebuild the global list"""
+        self._check(self._lib.am_gather_exchange(self._h, sweep._h, d_stats_ptr or None, stream or None),
+                    "am_gather_exchange")
 
     def push(self, d_idx_ptr: int, d_act_ptr: int, d_count_ptr: int, shard_base: int, stream: int):
         self._check(self._lib.am_gather_push(self._h, d_idx_ptr, d_act_ptr, d_count_ptr, shard_base,
@@ -144,19 +140,26 @@ class PeerGather:
                                       "version": 3, "strides": (itemsize,)}
         return torch.as_tensor(a, device=self.device)
 
+    def counts(self):
+        """device view of out_counts: world per-rank counts, then the total"""
+        return self._wrap(self._lib.am_gather_out_counts(self._h), self.world + 1, torch.int32)
+
+    def buffers(self):
+        """device views of the CURRENT output buffers, full capacity (the caller slices by the total)"""
+        idt = torch.int64 if self.idx_bytes == 8 else torch.int32
+        return (self._wrap(self._lib.am_gather_out_idx(self._h), self.cap_total, idt),
+                self._wrap(self._lib.am_gather_out_act(self._h), self.cap_total, torch.uint8))
+
     def result(self):
-        """(global idx int64[total], action uint8[total], counts list) — call after
-        the push has retired on its stream (synchronises to read the counts)."""
-        counts_t = self._wrap(self._lib.am_gather_out_counts(self._h), self.world + 1, torch.int32)
-        counts = counts_t.tolist()
+        """(global idx int64|int32[total], action uint8[total], counts list) — call after
+        the exchange / push has retired on its stream (synchronises to read the counts)."""
+        counts = self.counts().tolist()
         total = counts[self.world]
-        if total & 0xFFFFFFFF == 0xFFFFFFFF:  # bitmap format: the push kernel gave up on a peer
+        if total & 0xFFFFFFFF == 0xFFFFFFFF:  # the push kernel gave up on a peer
             raise RuntimeError("PeerGather: a peer did not arrive within AMSWEEP_PUSH_TIMEOUT_MS; the handle is "
                                "out of step with its peers and must be recreated")
-        idt = torch.int64 if self.idx_bytes == 8 else torch.int32
-        idx = self._wrap(self._lib.am_gather_out_idx(self._h), max(total, 1), idt)[:total]
-        act = self._wrap(self._lib.am_gather_out_act(self._h), max(total, 1), torch.uint8)[:total]
-        return idx, act, counts[: self.world]
+        idx, act = self.buffers()
+        return idx[:total], act[:total], counts[: self.world]
 
     def close(self):
         if getattr(self, "_h", None):

@@ -77,7 +77,7 @@ def classify_batch(items, n_threads: int = 0):
     arr = (L.AmHealthCheck * n)()
     keep = []  # the cron bytes must outlive the call (the library copies nothing before it returns)
     for i, kw in enumerate(kws):
-        unknown = set(kw) - set(_KW) - {"fail_p8"}
+        unknown = set(kw) - set(_KW) - {"fail_p8", "timer_armed"}
         if unknown:
             raise TypeError(f"item {i}: unknown fields {sorted(unknown)}")
         cron = kw.get("cron", "") or ""
@@ -99,6 +99,7 @@ def classify_batch(items, n_threads: int = 0):
         h.remedy_failed_count = int(kw.get("remedy_failed_count", 0) or 0)
         h.remedy_total_runs = int(kw.get("remedy_total_runs", 0) or 0)
         h.fail_p8 = int(kw.get("fail_p8", 0) or 0)
+        h.timer_armed = int(bool(kw.get("timer_armed", True)))  # same default as sweep.classify()
     recs = np.zeros(n, dtype=L.RECORD_DTYPE)
     rcs = np.zeros(n, dtype=np.int32)
     bad = L.u64(0)

@@ -95,7 +95,7 @@ def remedy_is_empty(generate_name: str, resource_is_nil: bool, timeout: int,
 def classify(*, repeat_after_sec=0, cron="", has_resource=True, has_remedy=False,
              remedy_runs_limit=0, remedy_reset_interval=0, finished_at=None,
              remedy_finished_at=None, success_count=0, failed_count=0, remedy_success_count=0,
-             remedy_failed_count=0, remedy_total_runs=0, fail_p8=0):
+             remedy_failed_count=0, remedy_total_runs=0, fail_p8=0, timer_armed=True):
     """am_healthcheck_classify -> (rc, record as a 1-element RECORD_DTYPE array)."""
     raw = bytes(_as_bytes(cron))
     hc = L.AmHealthCheck(repeat_after_sec, raw, len(raw), int(has_resource), int(has_remedy),
@@ -103,7 +103,7 @@ def classify(*, repeat_after_sec=0, cron="", has_resource=True, has_remedy=False
                          finished_at or 0, remedy_finished_at or 0,
                          int(finished_at is not None), int(remedy_finished_at is not None),
                          success_count, failed_count, remedy_success_count, remedy_failed_count,
-                         remedy_total_runs, fail_p8, 0)
+                         remedy_total_runs, fail_p8, int(bool(timer_armed)))
     rec = L.AmRecord()
     rc = L.load().am_healthcheck_classify(C.byref(hc), C.byref(rec))
     arr = np.frombuffer(bytes(rec), dtype=L.RECORD_DTYPE).copy()
@@ -144,8 +144,8 @@ def columns_to_records(cols: dict) -> np.ndarray:
 class Sweep:
     """One shard of the HealthCheck record array on one CUDA device."""
 
-    def __init__(self, capacity: int, device: int = 0, shard_base: int = 0):
-        self._lib = L.load()
+    def __init__(self, capacity: int, device: int = 0, shard_base: int = 0, lib=None):
+        self._lib = lib or L.load()  # `lib`: another build of the same ABI (tests/emu)
         h = C.c_void_p()
         rc = self._lib.am_sweep_create(C.byref(h), device, capacity, shard_base)
         if rc != L.AM_OK:
@@ -228,6 +228,36 @@ class Sweep:
         self._check(rc, "am_sweep_tick")
         return idx[:n.value], act[:n.value], st.as_dict()
 
+    def tick_view(self, unix_sec: int, mode: int = 0):
+        """Host tick without the per-entry pass: (u32 LOCAL idx view, u8 action view, stats).
+        The arrays alias the library's pinned buffer: valid until the next tick on the handle."""
+        v = L.AmTickView()
+        st = L.AmTickStats()
+        self._check(self._lib.am_sweep_tick_view(self._h, unix_sec, mode, C.byref(v), C.byref(st)),
+                    "am_sweep_tick_view")
+        n = int(v.n)
+        if n == 0:
+            return np.empty(0, np.uint32), np.empty(0, np.uint8), st.as_dict()
+        idx = np.ctypeslib.as_array(C.cast(v.idx_local, C.POINTER(C.c_uint32)), shape=(n,))
+        act = np.ctypeslib.as_array(C.cast(v.action, C.POINTER(C.c_uint8)), shape=(n,))
+        return idx, act, st.as_dict()
+
+    def last_list(self, offset: int, cap: int):
+        """Entries [offset, offset+cap) of the last host tick's list, widened; (idx, act, left)."""
+        idx = np.empty(cap, dtype=np.uint64)
+        act = np.empty(cap, dtype=np.uint32)
+        n = L.u64(0)
+        rc = self._lib.am_sweep_last_list(self._h, offset, idx.ctypes.data if cap else None,
+                                          act.ctypes.data if cap else None, cap, C.byref(n))
+        if rc not in (L.AM_OK, L.AM_E_NOSPACE):
+            self._check(rc, "am_sweep_last_list")
+        k = min(int(n.value), cap)
+        return idx[:k], act[:k], int(n.value)
+
+    def tick_shard(self, unix_sec: int, mode: int = 0, stream: int = 0):
+        """Multi-GPU tick, first half (sweep + group scan); PeerGather.exchange does the rest."""
+        self._check(self._lib.am_sweep_tick_shard(self._h, unix_sec, mode, stream or None), "am_sweep_tick_shard")
+
     def tick_device(self, unix_sec: int, mode: int, d_idx: int, d_act: int, cap: int,
                     d_count: int, d_stats: int = 0, stream: int = 0):
         """Device-resident tick on a caller stream (0 = CUDA default stream); raw
@@ -273,7 +303,7 @@ class Sweep:
         self._check(self._lib.am_sweep_set_profiling(self._h, int(on)), "am_sweep_set_profiling")
 
     def last_profile(self):
-        """(sweep_tick_kernel ms, compact_kernel ms) of the last tick; waits for it."""
+        """(sweep_tick_kernel ms, rest of the tick ms) of the last tick; waits for it."""
         a, b = C.c_double(), C.c_double()
         self._check(self._lib.am_sweep_last_profile(self._h, C.byref(a), C.byref(b)), "am_sweep_last_profile")
         return a.value, b.value

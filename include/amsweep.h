@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AMSWEEP_ABI_VERSION 1
+#define AMSWEEP_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------- */
 #define AM_OK 0
@@ -95,6 +95,9 @@ int64_t am_cron_repeat_after_sec(const am_cron_t* c, int64_t unix_sec);
 #define AM_F_REMEDY_OUTCOME_OK (1u << 7) /* ... and it is Succeeded            */
 #define AM_F_TOMBSTONE (1u << 8)         /* removed / never upserted           */
 #define AM_F_STOPPED_REPORTED (1u << 9)  /* "Stopped" status already written   */
+#define AM_F_TIMER_ARMED (1u << 10)      /* RepeatTimersByName holds a timer for the
+                                            check (hcc.go:264 "&& timer != nil";
+                                            armed by hcc.go:745-752 after a result) */
 #define AM_F_FAILP_SHIFT 16              /* closed-loop harness: P(fail)*256   */
 #define AM_F_FAILP_MASK (0xFFu << AM_F_FAILP_SHIFT)
 
@@ -125,7 +128,10 @@ typedef struct am_healthcheck {
   int64_t success_count, failed_count;
   int64_t remedy_success_count, remedy_failed_count, remedy_total_runs;
   uint32_t fail_p8;              /* closed-loop harness only, 0..255           */
-  uint32_t reserved;
+  uint32_t timer_armed;          /* r.GetTimerByName(name) != nil (hcc.go:264):
+                                    0 after a controller restart (hcc.go:161 starts
+                                    with an empty RepeatTimersByName), so the first
+                                    evaluation submits whatever finishedAt says   */
 } am_healthcheck_t;
 
 /* One packed record = one element of each SoA column. */
@@ -235,18 +241,47 @@ int am_sweep_post_result(am_sweep_t*, uint64_t n, const uint64_t* idx, const uin
 int am_sweep_tick(am_sweep_t*, int64_t unix_sec, uint32_t mode, uint64_t* due_idx,
                   uint32_t* due_action, uint64_t cap, uint64_t* n_out, am_tick_stats_t* stats);
 
+/* The same tick without the per-entry pass into caller memory: `view` points at the
+ * library's own pinned host buffer, which the GPU wrote directly — u32 LOCAL indices
+ * (global = shard_base + idx_local[k]) and u8 actions, ascending.  A cgo caller reads
+ * C memory in place (unsafe.Slice).  Valid until the next am_sweep_tick* call on the
+ * handle.  Never returns AM_E_NOSPACE. */
+typedef struct am_tick_view {
+  const uint32_t* idx_local;
+  const uint8_t* action;
+  uint64_t n;
+  uint64_t shard_base;
+} am_tick_view_t;
+int am_sweep_tick_view(am_sweep_t*, int64_t unix_sec, uint32_t mode, am_tick_view_t* view,
+                       am_tick_stats_t* stats);
+
+/* Re-read the list of the last am_sweep_tick / am_sweep_tick_view from entry `offset`
+ * on (an AM_E_NOSPACE tick has consumed its one-shot actions — RUN_REMEDY, STOPPED,
+ * RESET_* — on the device: fetch the rest here instead of losing them).  *n_out = entries
+ * from `offset` to the end; AM_E_NOSPACE again if they exceed cap. */
+int am_sweep_last_list(am_sweep_t*, uint64_t offset, uint64_t* due_idx, uint32_t* due_action,
+                       uint64_t cap, uint64_t* n_out);
+
 /* Same tick, results left in HBM: launches on `cuda_stream` (a cudaStream_t /
  * CUstream as void*; NULL = CUDA's default stream, as in every CUDA API; use
  * am_sweep_stream() for the handle's own stream) and does not synchronise.
  * d_due_idx (u32 LOCAL indices), d_due_action (u8) hold `cap` entries;
- * d_count receives n_emitted (u32); d_stats (may be NULL) receives an
- * am_tick_stats_t.  Used for device-resident pipelines and the multi-GPU
- * gather.  All ticks of one handle must be issued in stream order (they share
- * the handle's segment and counter buffers); the OUTPUT buffers may alternate
- * so that a consumer of tick k overlaps tick k+1. */
+ * d_count receives min(n_emitted, cap) (u32) — the number of valid list entries;
+ * d_stats (may be NULL) receives an am_tick_stats_t whose n_emitted is the full count.
+ * Used for device-resident pipelines.  Stream rule: every device operation of a handle
+ * is ordered after the previous one, whatever streams they were issued on (the library
+ * inserts the event waits); a stream passed here must stay alive until the next call on
+ * the handle has returned. */
 int am_sweep_tick_device(am_sweep_t*, int64_t unix_sec, uint32_t mode, void* d_due_idx,
                          void* d_due_action, uint64_t cap, void* d_count, void* d_stats,
                          void* cuda_stream);
+
+/* Multi-GPU tick, first half: drain + sweep + group scan only.  The emitted set stays
+ * inside the handle as a bitmap (1 bit per record) plus the non-default actions;
+ * am_gather_exchange ships exactly that over NVLink and rebuilds the GLOBAL list on
+ * every GPU.  Two buffer sets alternate, so the exchange of tick k (on another stream)
+ * may overlap am_sweep_tick_shard of tick k+1; tick k+2 waits for exchange k by itself. */
+int am_sweep_tick_shard(am_sweep_t*, int64_t unix_sec, uint32_t mode, void* cuda_stream);
 
 /* Streaming: n_ticks consecutive one-second ticks starting at unix_sec0,
  * back-to-back on the device (BASELINE config 5).  Per-tick stats are written
@@ -275,11 +310,12 @@ int am_sweep_device(const am_sweep_t*);
  * (CUDA events on the launching stream), milliseconds; <0 if none. */
 double am_sweep_last_kernel_ms(const am_sweep_t*);
 /* Per-kernel device timing: when on, every tick records CUDA events on the
- * launching stream around each of its two kernels (sweep_tick_kernel,
- * compact_kernel).  am_sweep_last_profile waits for the last tick and returns
- * their durations in milliseconds.  Off by default. */
+ * launching stream before and after sweep_tick_kernel and after the rest of the
+ * tick (scan + expand + publish).  am_sweep_last_profile waits for the last tick and
+ * returns the two durations in milliseconds.  Off by default (the extra events
+ * break the programmatic launch chain: do not time a step with it on). */
 int am_sweep_set_profiling(am_sweep_t*, int on);
-int am_sweep_last_profile(am_sweep_t*, double* sweep_ms, double* compact_ms);
+int am_sweep_last_profile(am_sweep_t*, double* sweep_ms, double* rest_ms);
 /* Number of kernels this library has launched on the handle so far. */
 uint64_t am_sweep_launch_count(const am_sweep_t*);
 /* Raw device pointer of a column (for zero-copy wrapping by torch / NCCL
@@ -289,47 +325,47 @@ int am_sweep_set_seed(am_sweep_t*, uint64_t seed);
 /* The handle's own non-blocking stream (cudaStream_t as void*). */
 void* am_sweep_stream(am_sweep_t*);
 
-/* ---- multi-GPU: due-list concatenation over NVLink peer memory --
- * One am_gather per rank (one process per GPU).  Every rank creates its
- * exchange block, exports a CUDA-IPC handle, the handles are exchanged by the
- * caller's plumbing (torch.distributed / any side channel) and connected; then
- * each tick every rank calls am_gather_push once, after its sweep on the same
- * stream.  When the push kernel retires, out_idx/out_act on EVERY rank hold the
- * global ascending (u64 index, u8 action) list and out_counts[0..world) the
- * per-rank counts, out_counts[world] the total.  No NCCL, no host round-trip.
- * Like any collective, the push is a rendezvous: every rank must call it the
- * same number of times; the kernel waits on device for its peers' counts and
- * done flags (no timeout: a missing peer blocks the stream, as a missing rank
- * blocks an NCCL collective).  Argument errors are reported before anything
- * that the peers could observe happens.
+/* ---- multi-GPU: the global due list on every GPU, over NVLink peer memory --
+ * One am_gather per rank (one process per GPU).  Every rank creates its exchange block,
+ * exports a CUDA-IPC handle, the handles are exchanged by the caller's plumbing
+ * (torch.distributed / any side channel) and connected, and the shard layout is set.
+ * Then, per tick, every rank calls
+ *     am_sweep_tick_shard(sweep, T, mode, stream_a);      // sweep + group scan
+ *     am_gather_exchange(gather, sweep, d_stats, stream_b);
+ * The exchange ships the sweep's own output — one bit per record for the emitted set,
+ * group offsets, the non-default actions — into every peer's block (one kernel, 16-B peer
+ * stores, no NCCL, no host round-trip) and rebuilds the GLOBAL ascending (index, action)
+ * list locally from the world's bitmaps.  When its last kernel retires, out_idx / out_act
+ * on EVERY rank hold that list, out_counts[0..world) the per-rank counts and
+ * out_counts[world] the total; d_stats (may be NULL) receives this shard's am_tick_stats_t.
+ * stream_b may differ from stream_a (the library orders them): the exchange of tick k then
+ * overlaps the sweep of tick k+1.
+ * Like any collective, the exchange is a rendezvous: every rank must call it the same
+ * number of times.  Its device-side wait for the peers is bounded (AMSWEEP_PUSH_TIMEOUT_MS,
+ * default 5000, 0 = unbounded): a peer that never arrives leaves out_counts[world] ==
+ * 0xFFFFFFFF and the handle out of step (recreate it).  Argument errors are reported before
+ * anything that the peers could observe happens.
  * The reference has no counterpart (single process; consumer is hcc.go:502). */
 #define AM_IPC_HANDLE_BYTES 64
 typedef struct am_gather am_gather_t;
-/* idx_bytes: 8 = u64 global indices; 4 = u32 (halves the NVLink payload; the
- * caller guarantees every global index < 2^32). */
+/* cap_total: records of all shards together (bounds the global list).
+ * idx_bytes: 8 = u64 global indices in the output; 4 = u32 (the caller guarantees every
+ * global index < 2^32). */
 int am_gather_create(am_gather_t** out, int device, int rank, int world, uint64_t cap_total,
                      int idx_bytes);
 int am_gather_export(am_gather_t*, void* handle_out /* AM_IPC_HANDLE_BYTES */);
 int am_gather_connect(am_gather_t*, const void* handles /* world x AM_IPC_HANDLE_BYTES, rank order */);
-/* Optional, after connect: switch to the compressed wire format (3 B per entry on
- * NVLink instead of 5: u16 offsets within 8192-record groups + per-group counts,
- * expanded by each receiver into the same output as the plain format).  bases[r] /
- * sizes[r] = first global index / number of records of rank r's shard. */
+/* bases[r] / sizes[r] = first global index / number of records of rank r's shard (the same
+ * arrays on every rank).  Required before am_gather_exchange. */
 int am_gather_set_layout(am_gather_t*, const uint64_t* bases, const uint64_t* sizes);
-/* Wire formats.  PLAIN is what a handle uses until set_layout is called; set_layout
- * selects C3.  BITMAP (after set_layout) is EXPERIMENTAL — one bit per record for the
- * emitted set plus only the non-default action bytes, ~0.4 B per entry at the bench
- * density; implemented after the round-1 GPU budget was spent and not yet run on
- * hardware, so nothing selects it by default.  Its device-side waits are bounded
- * (AMSWEEP_PUSH_TIMEOUT_MS, default 5000, 0 = unbounded): a peer that never arrives
- * leaves out_counts[world] == 0xFFFFFFFF and the handle out of step (recreate it). */
-#define AM_WIRE_PLAIN 0
-#define AM_WIRE_C3 1
-#define AM_WIRE_BITMAP 2
-int am_gather_set_wire(am_gather_t*, int wire);
+int am_gather_exchange(am_gather_t*, am_sweep_t* shard, void* d_stats, void* cuda_stream);
+/* Round-1 "plain" format, kept as the measured baseline: every rank writes its FINISHED
+ * list (the output of am_sweep_tick_device: u32 local indices, u8 actions, device count)
+ * straight into every peer's output buffer at its global offset, 5 or 9 bytes per entry
+ * on the wire.  Unbounded device-side waits. */
 int am_gather_push(am_gather_t*, const void* d_idx_local /* u32 */, const void* d_act_local /* u8 */,
                    const void* d_count_local /* u32 */, uint64_t shard_base, void* cuda_stream);
-void* am_gather_out_idx(am_gather_t*);    /* u64|u32[cap_total], valid after the last push retires */
+void* am_gather_out_idx(am_gather_t*);    /* u64|u32[cap_total], valid after the last exchange / push retires */
 void* am_gather_out_act(am_gather_t*);    /* u8[cap_total]                                    */
 void* am_gather_out_counts(am_gather_t*); /* u32[world+1]                                     */
 const char* am_gather_last_error(const am_gather_t*);

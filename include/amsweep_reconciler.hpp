@@ -93,7 +93,13 @@ class HealthCheckReconciler {
   std::optional<std::string> ProcessHealthCheck(HealthCheck* hc, int64_t now) {
     am_record_t rec;
     std::string perr;
-    int rc = Classify(*hc, &rec, &perr);
+    // r.GetTimerByName(name) != nil (hcc.go:264): a timer exists once a result of this check was
+    // applied (hcc.go:745-752) and survives re-Reconciles of the same process; a fresh reconciler
+    // (restart, hcc.go:161) has none
+    bool armed = false;
+    am_record_t cur;
+    if (slots_.count(hc->Key()) && ReadRecord(hc->Key(), &cur)) armed = (cur.flags & AM_F_TIMER_ARMED) != 0;
+    int rc = Classify(*hc, armed, &rec, &perr);
     if (rc == AM_E_UNSUPPORTED) return std::string("unsupported on the device path: ") + perr;
     if (rc != AM_OK) return std::string(am_strerror(rc));
     const uint32_t kind = rec.flags & AM_KIND_MASK;
@@ -153,7 +159,8 @@ class HealthCheckReconciler {
     am_record_t r;
     if (!ReadRecord(key, &r)) return std::nullopt;
     const uint32_t kind = r.flags & AM_KIND_MASK;
-    if ((r.flags & AM_F_TOMBSTONE) || (kind != AM_KIND_INTERVAL && kind != AM_KIND_CRON_EVERY)) return std::nullopt;
+    if ((r.flags & AM_F_TOMBSTONE) || !(r.flags & AM_F_TIMER_ARMED) || (kind != AM_KIND_INTERVAL && kind != AM_KIND_CRON_EVERY))
+      return std::nullopt;
     return r.finished_at + r.ras;
   }
 
@@ -180,8 +187,9 @@ class HealthCheckReconciler {
  private:
   HealthCheckReconciler(am_sweep_t* h, uint64_t cap) : h_(h), capacity_(cap) { names_.resize(cap); }
 
-  static int Classify(const HealthCheck& hc, am_record_t* rec, std::string* perr) {
+  static int Classify(const HealthCheck& hc, bool timer_armed, am_record_t* rec, std::string* perr) {
     am_healthcheck_t in{};
+    in.timer_armed = timer_armed ? 1u : 0u;
     in.repeat_after_sec = hc.Spec.RepeatAfterSec;
     in.cron = hc.Spec.Schedule.Cron.data();
     in.cron_len = hc.Spec.Schedule.Cron.size();

@@ -13,6 +13,7 @@
 
 #include <limits.h>
 #include <pthread.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -40,6 +41,7 @@ _Static_assert(sizeof(orc_tick_stats_t) == 128, "layout");
 #define F_REMEDY_OUTCOME_OK (1u << 7)
 #define F_TOMBSTONE (1u << 8)
 #define F_STOPPED_REPORTED (1u << 9)
+#define F_TIMER_ARMED (1u << 10) /* r.GetTimerByName(name) != nil, hcc.go:264 */
 #define F_FAILP_SHIFT 16
 #define ACT_SUBMIT_HC 0x01u
 #define ACT_RUN_REMEDY 0x02u
@@ -777,6 +779,7 @@ int orc_classify(const orc_healthcheck_t* hc, orc_record_t* out) {
   }
   if (hc->has_remedy) flags |= F_HAS_REMEDY;
   flags |= hc->fail_p8 << F_FAILP_SHIFT;
+  if (hc->timer_armed) flags |= F_TIMER_ARMED; /* hcc.go:264: "&& r.GetTimerByName(...) != nil" */
   out->flags = flags;
   out->ras = ras;
   out->finished_at = hc->finished_at_set ? hc->finished_at : 0; /* hcc.go:231-235 */
@@ -871,6 +874,8 @@ static uint32_t apply_result(orc_record_t* r, int64_t T, orc_tick_stats_t* st) {
     apply_remedy_result(r, T, (f & F_REMEDY_OUTCOME_OK) != 0, st);
   }
   r->flags = f & ~(F_PENDING_OK | F_PENDING_FAIL | F_REMEDY_PENDING | F_REMEDY_OUTCOME_OK);
+  /* watchWorkflowReschedule re-arms the repeat timer after either outcome: hcc.go:745-752 */
+  if (f & (F_PENDING_OK | F_PENDING_FAIL)) r->flags |= F_TIMER_ARMED;
   return act;
 }
 
@@ -899,8 +904,10 @@ static uint32_t tick_record_tm(orc_record_t* r, int64_t T, const struct tm* tmT,
       break;
     case KIND_INTERVAL:
     case KIND_CRON_EVERY: { /* not(hcc.go:264)  ==  timer of :751 has fired */
+      /* hcc.go:264: skipped iff "now - finishedAt < RepeatAfterSec && timer != nil"; with no
+       * timer (controller restart: hcc.go:161 starts with an empty map) the check is submitted */
       int64_t elapsed = (int64_t)((uint64_t)T - (uint64_t)r->finished_at);
-      due = !(elapsed < (int64_t)r->ras);
+      due = !(elapsed < (int64_t)r->ras && (r->flags & F_TIMER_ARMED));
       break;
     }
     case KIND_CRON_SPEC: {
@@ -1111,9 +1118,30 @@ static struct {
 
 typedef struct { int k; uint64_t seen; } mt_worker_arg_t;
 
+/* Pin a parked worker to the (k+1)-th CPU of the affinity mask it inherited (the caller's
+ * thread keeps chunk 0 wherever the scheduler puts it): one chunk per core, no migration
+ * between the two passes — the CPU baseline varied 5.8x between two boxes without it. */
+static void mt_pin_worker(int k) {
+  cpu_set_t have, want;
+  if (sched_getaffinity(0, sizeof have, &have) != 0) return;
+  const int ncpu = CPU_COUNT(&have);
+  if (ncpu <= 1) return;
+  int target = (k + 1) % ncpu, seen = 0;
+  for (int c = 0; c < CPU_SETSIZE; c++) {
+    if (!CPU_ISSET(c, &have)) continue;
+    if (seen++ == target) {
+      CPU_ZERO(&want);
+      CPU_SET(c, &want);
+      (void)pthread_setaffinity_np(pthread_self(), sizeof want, &want);
+      return;
+    }
+  }
+}
+
 static void* mt_pool_worker(void* p) {
   mt_worker_arg_t arg = *(mt_worker_arg_t*)p;
   free(p);
+  mt_pin_worker(arg.k);
   uint64_t seen = arg.seen;
   for (;;) {
     pthread_mutex_lock(&g_pool.mu);

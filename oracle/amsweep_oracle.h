@@ -66,7 +66,7 @@ typedef struct orc_healthcheck {
   int64_t success_count, failed_count;
   int64_t remedy_success_count, remedy_failed_count, remedy_total_runs;
   uint32_t fail_p8;
-  uint32_t reserved;
+  uint32_t timer_armed; /* r.GetTimerByName(name) != nil (hcc.go:264) */
 } orc_healthcheck_t;
 
 typedef struct orc_record {

@@ -37,6 +37,7 @@ F_REMEDY_PENDING = 1 << 6
 F_REMEDY_OUTCOME_OK = 1 << 7
 F_TOMBSTONE = 1 << 8
 F_STOPPED_REPORTED = 1 << 9
+F_TIMER_ARMED = 1 << 10  # r.GetTimerByName(name) != nil, hcc.go:264
 F_FAILP_SHIFT = 16
 
 ACT_SUBMIT_HC = 0x01
@@ -426,6 +427,7 @@ class HealthCheck:
     remedy_failed_count: int = 0
     remedy_total_runs: int = 0
     fail_p8: int = 0
+    timer_armed: bool = True  # RepeatTimersByName has a timer for the check (hcc.go:264)
 
 
 @dataclass
@@ -505,7 +507,8 @@ def classify(hc: HealthCheck) -> tuple[int, Record]:
         if not _i32(hc.repeat_after_sec):
             return E_RANGE, Record()
         kind, r.ras = KIND_INTERVAL, hc.repeat_after_sec
-    r.flags = kind | (F_HAS_REMEDY if hc.has_remedy else 0) | (hc.fail_p8 << F_FAILP_SHIFT)
+    r.flags = (kind | (F_HAS_REMEDY if hc.has_remedy else 0) | (hc.fail_p8 << F_FAILP_SHIFT)
+               | (F_TIMER_ARMED if hc.timer_armed else 0))
     r.finished_at = hc.finished_at if hc.finished_at is not None else 0
     r.remedy_finished_at = hc.remedy_finished_at if hc.remedy_finished_at is not None else 0
     r.runs_limit, r.reset_interval = hc.remedy_runs_limit, hc.remedy_reset_interval
@@ -601,6 +604,8 @@ def _apply_result(r: Record, t: int, st: Stats) -> int:
     elif f & F_REMEDY_PENDING:
         _remedy_result(r, t, bool(f & F_REMEDY_OUTCOME_OK), st)
     r.flags = f & ~(F_PENDING_OK | F_PENDING_FAIL | F_REMEDY_PENDING | F_REMEDY_OUTCOME_OK)
+    if f & (F_PENDING_OK | F_PENDING_FAIL):  # hcc.go:745-752: the repeat timer is re-armed after either outcome
+        r.flags |= F_TIMER_ARMED
     return act
 
 
@@ -623,7 +628,8 @@ def tick_record(r: Record, t: int, mode: int = 0, seed: int = 0, gidx: int = 0,
     elif kind == KIND_PARSE_ERROR:
         act |= ACT_PARSE_ERROR
     elif kind in (KIND_INTERVAL, KIND_CRON_EVERY):
-        due = (t - r.finished_at) >= r.ras
+        # hcc.go:264: skipped iff elapsed < RepeatAfterSec AND a timer exists for the check
+        due = not ((t - r.finished_at) < r.ras and bool(r.flags & F_TIMER_ARMED))
     elif kind == KIND_CRON_SPEC:
         due = cron_matches(Cron(CRON_SPEC, r.minute, r.hour, r.dom, r.month, r.dow), t)
     if due:

@@ -109,11 +109,14 @@ static void TestDeleteStopsTimer(HealthCheckReconciler& r) {
   hc.Spec.RepeatAfterSec = 60;
   hc.Status.FinishedAt = T0;
   CHECK(!r.Reconcile(hc.Key(), &hc, T0).has_value());
-  r.Tick(T0 + 100);
-  CHECK(r.GetTimerByName(hc.Key()).has_value());
-  CHECK(!r.Reconcile(hc.Key(), nullptr, T0 + 101).has_value());  // CR not found (hcc.go:175-186)
+  r.Tick(T0 + 100);                                  // submitted (elapsed >= 60, and no timer yet: hcc.go:264)
   CHECK(!r.GetTimerByName(hc.Key()).has_value());
-  for (int64_t t = T0 + 102; t < T0 + 300; t += 60)
+  r.PostResult(hc.Key(), amsweep::Succeeded);
+  r.Tick(T0 + 101);                                  // the result arms the repeat timer (hcc.go:745-752)
+  CHECK(r.GetTimerByName(hc.Key()).has_value());
+  CHECK(!r.Reconcile(hc.Key(), nullptr, T0 + 102).has_value());  // CR not found (hcc.go:175-186)
+  CHECK(!r.GetTimerByName(hc.Key()).has_value());
+  for (int64_t t = T0 + 103; t < T0 + 300; t += 60)
     for (const Due& d : r.Tick(t)) CHECK(d.Key != hc.Key());
 }
 

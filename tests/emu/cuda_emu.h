@@ -243,6 +243,7 @@ static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline uint32_t atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+static inline uint32_t atomicAnd(uint32_t* p, uint32_t v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
 
 static inline void st_release_sys(unsigned long long* p, unsigned long long v) {
   emu::jitter();

@@ -27,6 +27,8 @@ SPECS = [dict(repeat_after_sec=5), dict(repeat_after_sec=60), dict(repeat_after_
          dict(cron="* * * * *"), dict(cron="*/2 * * * *"), dict(cron="16 9 * * mon"), dict(cron="NOT_A_VALID_CRON"),
          dict(), dict(repeat_after_sec=30, has_resource=False), dict(cron="0 0 30 2 *")]
 M = am.F_PENDING_OK | am.F_PENDING_FAIL | am.F_REMEDY_PENDING | am.F_REMEDY_OUTCOME_OK
+HC = am.F_PENDING_OK | am.F_PENDING_FAIL
+RM = am.F_REMEDY_PENDING | am.F_REMEDY_OUTCOME_OK
 PB = {0: 0, 1: am.F_PENDING_OK, 2: am.F_PENDING_FAIL}
 RB = {0: 0, 1: am.F_REMEDY_PENDING | am.F_REMEDY_OUTCOME_OK, 2: am.F_REMEDY_PENDING}
 
@@ -36,6 +38,7 @@ def random_record(rng, T):
     kw.update(has_remedy=bool(rng.integers(0, 2)), remedy_runs_limit=int(rng.choice([0, 1, 2, 5])),
               remedy_reset_interval=int(rng.choice([0, 60, 300])), fail_p8=int(rng.integers(0, 256)),
               finished_at=None if rng.integers(0, 6) == 0 else T - int(rng.integers(0, 200)),
+              timer_armed=bool(rng.integers(0, 4)),
               success_count=int(rng.integers(0, 50)), failed_count=int(rng.integers(0, 50)))
     rs, rf = int(rng.integers(0, 4)), int(rng.integers(0, 4))
     kw.update(remedy_success_count=rs, remedy_failed_count=rf, remedy_total_runs=rs + rf,
@@ -85,9 +88,13 @@ def run_sequence(seed, steps, cap):
                     ph = rng.integers(0, 3, len(idx)).astype(np.uint8)
                     rp = rng.integers(0, 3, len(idx)).astype(np.uint8) if rng.integers(0, 2) else None
                     s.post_result(idx, ph, rp)
+                    # the two phases are observed by separate watch loops: each call replaces only the
+                    # bit group(s) it carries a phase for ("none" leaves a group alone)
                     for j, i in enumerate(idx.tolist()):
-                        bits = PB[int(ph[j])] | (RB[int(rp[j])] if rp is not None else 0)
-                        model["flags"][i] = (model["flags"][i] & ~np.uint32(M)) | np.uint32(bits)
+                        if int(ph[j]):
+                            model["flags"][i] = (model["flags"][i] & ~np.uint32(HC)) | np.uint32(PB[int(ph[j])])
+                        if rp is not None and int(rp[j]):
+                            model["flags"][i] = (model["flags"][i] & ~np.uint32(RM)) | np.uint32(RB[int(rp[j])])
                 else:  # a read between the calls observes everything staged before it
                     q = rng.integers(0, cap, 7)
                     assert_columns_equal(s.read(q), {k: v[q] for k, v in model.items()}, f"seed {seed} step {step} read")

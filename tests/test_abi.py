@@ -25,7 +25,7 @@ def test_header_symbols_all_exported(am, lib):
 
 
 def test_abi_version_and_strerror(am, lib):
-    assert lib.am_abi_version() == 1
+    assert lib.am_abi_version() == 2
     assert lib.am_strerror(0) == b"ok"
     for code in range(-8, 0):
         assert lib.am_strerror(code) not in (b"", b"unknown amsweep error")

@@ -24,7 +24,7 @@ def test_reference_arm_json_line():
     assert d["value"] > 1e5 and abs(d["ms_per_step"] * 1e-3 * d["value"] - 200000) < 1
     assert d["vs_baseline"] is None and d["data"] == "synthetic" and d["dtype"] == "u64"
     assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
     assert d["e2e"] == {"value": d["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 

@@ -173,4 +173,4 @@ def test_classify_domain_checks(am, orc):
     rc, rec = am.classify(repeat_after_sec=-7, cron="")
     assert rc == 0 and rec["flags"][0] & 7 == am.KIND_STOPPED
     rc, rec = am.classify(repeat_after_sec=60, cron="NOT_A_VALID_CRON", has_remedy=True, fail_p8=77)
-    assert rec["flags"][0] == am.KIND_INTERVAL | am.F_HAS_REMEDY | (77 << 16) and rec["ras"][0] == 60
+    assert rec["flags"][0] == am.KIND_INTERVAL | am.F_HAS_REMEDY | am.F_TIMER_ARMED | (77 << 16) and rec["ras"][0] == 60

@@ -1,99 +1,103 @@
-"""The NVLink exchange kernels (csrc/gather_kernels.cuh) on a CPU emulation of the CUDA execution
-model (tests/emu/cuda_emu.h): ranks are OS threads, a CTA's threads are fibers, `__syncthreads`
-and the warp collectives are rendezvous points, system-scope acquire/release are std atomics.
+"""The NVLink tick exchange (csrc/gather.cu + gather_kernels.cuh + the list rebuild of
+sweep_kernels.cuh) on a CPU emulation of the CUDA execution model (tests/emu): ranks are OS
+threads, a CTA's threads are fibers, `__syncthreads` and the warp collectives are rendezvous
+points, system-scope acquire/release are std atomics.
 
-The SAME kernel source the GPU runs is compiled for the host; every rank pushes several ticks
-back to back (no host barrier, as on the stream) and checks that its output is the rank-ordered
-concatenation of all ranks' lists.  This covers the N>1 path's index arithmetic, buffer layout
-and epoch / ticket / done-flag protocol without a GPU — for the two formats validated on
-hardware (plain, c3: which also validates the emulator) and for the experimental bitmap format
-that has not run on hardware yet.  It does not cover the GPU memory model or performance.
+The SAME sources the GPU runs are compiled for the host; every rank sweeps its index-range shard
+of ONE population and exchanges several ticks back to back (no host barrier, as on the stream);
+every rank's global list, counts, shard statistics and final columns must equal the UNSHARDED
+oracle.  This covers the N>1 path's index arithmetic, slot layout and epoch / ticket / done-flag
+protocol without a GPU; it does not cover the GPU memory model or performance — the `-m gpu`
+tests in tests/test_multi_gpu.py do, on 2 / 4 / 8 B200s.
 """
 import os
 import subprocess
+import sys
 
 import pytest
 
 from conftest import ROOT
 
 EMU = os.path.join(ROOT, "tests", "emu")
-EXE = os.path.join(EMU, "emu_gather.bin")
 
 
 @pytest.fixture(scope="module")
-def emu_bin():
-    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", "-Wno-unknown-pragmas", "-pthread",
-                    "-I", os.path.join(ROOT, "include"), os.path.join(EMU, "emu_gather.cpp"), "-o", EXE],
-                   check=True)
-    return EXE
+def emu_lib():
+    sys.path.insert(0, EMU)
+    import emu_sweep
+    return emu_sweep.build()
 
 
-# world, idx_bytes, records per rank, epochs, CTAs, density %, [capacity override]
+def _run(emu_lib, args, env=None, timeout=900):
+    e = dict(os.environ, AMSWEEP_LIB=emu_lib)
+    e.update(env or {})
+    out = subprocess.run([sys.executable, os.path.join(EMU, "run_gather_ranks.py")] + [str(a) for a in args],
+                         cwd=ROOT, env=e, capture_output=True, text=True, timeout=timeout)
+    assert out.returncode == 0 and out.stdout.strip().startswith("ok"), out.stdout[-3000:] + out.stderr[-3000:]
+    return out.stdout
+
+
+# world, idx_bytes, records in total, ticks, population
 CASES = [
-    (2, 4, 20000, 4, 3, 33),
-    (2, 8, 20000, 6, 5, 33),
-    (3, 4, 30011, 5, 4, 33),      # ragged shard sizes, groups straddling nothing: 3 full + 1 partial
-    (4, 4, 9000, 5, 7, 50),
-    (8, 4, 8192, 4, 2, 33),       # exactly one group per rank
-    (8, 8, 5000, 3, 16, 10),      # more CTAs than groups
-    (2, 4, 100, 3, 3, 100),       # every record emitted
-    (3, 8, 8191, 3, 1, 1),        # one CTA, nearly empty lists
-    (2, 4, 16384, 3, 40, 0),      # only the always-dense / always-empty stretches
-    (3, 4, 20000, 4, 3, 50, 21000),   # capacity below the total: truncation paths
-    (2, 4, 600000, 2, 1, 33),     # 74 groups on ONE CTA (c3: no CTAs to split off for the searches)
+    (2, 4, 40_000, 4, 3),      # config 3: dense exceptions (remedy actions)
+    (2, 8, 40_000, 4, 2),      # config 2: sparse exceptions, u64 indices
+    (3, 8, 30_011, 4, 3),      # ragged shard sizes, partial last group and tile
+    (4, 4, 36_000, 4, 2),
+    (8, 4, 65_536, 3, 3),      # exactly one 8192-record group per rank
+    (8, 8, 9_000, 3, 2),       # shards smaller than a group, more CTAs than tiles
+    (5, 4, 5, 2, 2),           # one record per rank
+    (2, 4, 600_000, 2, 2),     # 37 groups per rank
 ]
 
 
-@pytest.mark.parametrize("wire", ["plain", "c3", "bm"])
-@pytest.mark.parametrize("case", CASES, ids=lambda c: "w{}_b{}_n{}_e{}_c{}_d{}{}".format(*c[:6], "_cap" if len(c) > 6 else ""))
-def test_exchange_equals_concatenation_on_the_emulator(emu_bin, wire, case):
-    out = subprocess.run([emu_bin, wire] + [str(v) for v in case], capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "w{}_b{}_n{}_t{}_c{}".format(*c))
+def test_exchanged_ticks_equal_the_unsharded_oracle(emu_lib, case):
+    _run(emu_lib, ["tick"] + list(case))
 
 
-def test_batches_of_more_than_255_groups_per_cta(emu_bin):
-    """2.2 M records per rank on one CTA: 269 groups, i.e. two boundary batches (bm) and the
-    non-split search loop (c3)."""
-    for wire in ("c3", "bm"):
-        out = subprocess.run([emu_bin, wire, "2", "4", "2200000", "2", "1", "33"], capture_output=True, text=True,
-                             timeout=900)
-        assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+@pytest.mark.parametrize("ctas", [1, 3, 40])
+def test_any_push_grid_size(emu_lib, ctas):
+    _run(emu_lib, ["tick", 3, 4, 50_000, 3, 3], env={"AMSWEEP_PUSH_CTAS": str(ctas)})
 
 
-@pytest.mark.parametrize("wire", ["plain", "c3", "bm"])
-def test_protocol_survives_skew_between_ranks(emu_bin, wire):
+def test_protocol_survives_skew_between_ranks(emu_lib):
     """EMU_JITTER: random pauses at launches and system-scope stores let ranks drift apart by whole
-    kernels over 25 back-to-back ticks; the epoch / done-flag / double-buffer protocol must still
-    deliver the concatenation on every rank.  (Deleting the done-flag wait from the kernels makes
-    this test fail within two ticks.)"""
-    out = subprocess.run([emu_bin, wire, "4", "4", "12000", "25", "3"], capture_output=True, text=True, timeout=600,
-                         env=dict(os.environ, EMU_JITTER="1"))
-    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+    kernels over 25 back-to-back ticks; the epoch / done-flag / two-slot-set protocol must still
+    deliver the oracle's list on every rank."""
+    _run(emu_lib, ["tick", 4, 4, 48_000, 25, 2], env={"EMU_JITTER": "1"})
+
+
+def test_watchdog_gives_up_on_an_absent_peer(emu_lib):
+    """The device-side wait for the peers' done flags is bounded (AMSWEEP_PUSH_TIMEOUT_MS): a rank that
+    never exchanges makes the others report 0xFFFFFFFF in out_counts[world] instead of hanging the GPU."""
+    out = _run(emu_lib, ["tick", 3, 4, 30_000, 3], env={"EMU_ABSENT_RANK": "1", "AMSWEEP_PUSH_TIMEOUT_MS": "300"},
+               timeout=120)
+    assert "watchdog" in out
+
+
+@pytest.mark.parametrize("world,idx_bytes,records", [(2, 4, 20_000), (3, 8, 30_011), (8, 4, 9_000)])
+def test_round1_plain_list_format_still_equals_the_concatenation(emu_lib, world, idx_bytes, records):
+    _run(emu_lib, ["plain", world, idx_bytes, records, 5])
 
 
 def test_flag_protocol_orders_every_cross_rank_access_under_threadsanitizer(tmp_path):
-    """The same harness built with -fsanitize=thread (the emulator tells TSan about its fibers; every
-    fiber switch synchronises, so only accesses of DIFFERENT ranks can race).  System-scope
-    release/acquire are atomics there, everything else — peer payload stores, group counts, bitmaps,
-    output reads — plain memory accesses: a report would mean some cross-rank data is not ordered by
-    the count / done-flag protocol.  (Without the done-flag wait TSan reports a data race at once.)"""
-    exe = str(tmp_path / "emu_gather_tsan.bin")
-    r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-Wno-unknown-pragmas", "-Wno-tsan",
-                        "-pthread", "-I", os.path.join(ROOT, "include"), os.path.join(EMU, "emu_gather.cpp"), "-o", exe],
+    """tests/emu/tsan_exchange.cpp: the library's own sources on the emulator, built with
+    -fsanitize=thread (the emulator tells TSan about its fibers; every fiber switch synchronises, so
+    only accesses of DIFFERENT ranks can race).  Three ranks as threads tick and exchange back to back.
+    System-scope release/acquire are atomics there, everything else — peer payload stores, slot reads
+    by the list rebuild — plain memory accesses: a report would mean some cross-rank data is not
+    ordered by the done-flag protocol."""
+    sys.path.insert(0, EMU)
+    import emu_sweep
+    exe = str(tmp_path / "tsan_exchange.bin")
+    srcs = emu_sweep.sources()[0] + [os.path.join(EMU, "tsan_exchange.cpp")]
+    r = subprocess.run(["g++", "-std=c++20", "-O1", "-g", "-fsanitize=thread", "-Wno-unknown-pragmas", "-Wno-tsan",
+                        "-pthread", "-DAMSWEEP_EMULATE", "-include", os.path.join(EMU, "cuda_emu.h"),
+                        "-include", os.path.join(EMU, "cuda_rt_emu.h"), "-x", "c++"] + srcs + ["-o", exe],
                        capture_output=True, text=True)
     if r.returncode != 0:
         pytest.skip("ThreadSanitizer runtime not available: " + r.stderr[-300:])
-    for wire in ("plain", "c3", "bm"):
-        out = subprocess.run([exe, wire, "3", "4", "12000", "4", "3"], capture_output=True, text=True, timeout=900,
-                             env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66"))
-        assert "ThreadSanitizer" not in out.stderr, out.stderr[-3000:]
-        assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr[-2000:]
-
-
-def test_bitmap_format_watchdog_gives_up_on_an_absent_peer(emu_bin):
-    """Experimental bitmap kernels only: their spin loops are bounded (AMSWEEP_PUSH_TIMEOUT_MS, 200 ms in
-    the harness).  A rank that never pushes makes the others report kPeerTimeout in out_counts[world]
-    instead of hanging the device."""
-    out = subprocess.run([emu_bin, "bm", "3", "4", "20000", "3", "3"], capture_output=True, text=True, timeout=120,
-                         env=dict(os.environ, EMU_ABSENT_RANK="1"))
-    assert out.returncode == 0 and out.stdout.startswith("ok watchdog"), out.stdout + out.stderr
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0 exitcode=66"))
+    assert "ThreadSanitizer" not in out.stderr, out.stderr[-3000:]
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr[-2000:]

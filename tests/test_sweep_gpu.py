@@ -279,36 +279,47 @@ def test_tick_device_resident_outputs(am, orc, gen):
         assert got_stats == ws
 
 
-def test_full_size_10m_properties(am, gen):
-    """BASELINE configs[1] at full size (10 M): size-independent properties — the
-    list is strictly ascending, its length/checksums equal the statistics, the
-    sum of per-shard ticks equals the whole, and re-ticking is idempotent."""
+@pytest.mark.parametrize("config,seed", [(2, 2), (3, 3)])
+def test_full_size_10m_equals_the_oracle(am, orc, gen, config, seed):
+    """BASELINE configs[1] and configs[2] at FULL size (10 M HealthChecks): the emitted list,
+    the action bytes, the statistics and all sixteen columns equal the threaded oracle sweep —
+    at T0 (cron + interval arms; config 3: 50 % pending Failed / 25 % Succeeded through the
+    remedy gate) and one minute later (nothing pending: the sparse paths)."""
+    import os
     n = 10_000_000
-    lib = am.load()
-    prod = gen.fill(2, 2, 0, n, T0, lib.am_healthcheck_classify)
+    threads = min(32, len(os.sched_getaffinity(0)))
+    prod = gen.fill(config, seed, 0, n, T0, am.load().am_healthcheck_classify, threads=threads)
+    orac = gen.fill(config, seed, 0, n, T0, orc.load().orc_classify, threads=threads)
+    for name in am.COLUMN_NAMES:
+        assert np.array_equal(prod[name], orac[name]), f"classify column {name}"
+    with am.Sweep(capacity=n) as s:
+        s.load_range(0, prod)
+        for T in (T0, T0 + 60):
+            gi, ga, gs = s.tick(T)
+            wi, wa, ws = orc.sweep(orac, T, threads=threads)
+            assert gs == ws, f"config {config} T={T}: stats differ\n gpu={gs}\n cpu={ws}"
+            assert np.array_equal(gi, wi), f"config {config} T={T}: emitted indices"
+            assert np.array_equal(ga, wa), f"config {config} T={T}: action bytes"
+            # size-independent properties of the list itself
+            assert (np.diff(gi.astype(np.int64)) > 0).all()
+            assert int(np.bitwise_xor.reduce(gi)) == gs["idx_xor"] and int(gi.sum(dtype=np.uint64)) == gs["idx_sum"]
+        dev = s.read_range(0, n)
+        for name in am.COLUMN_NAMES:
+            assert np.array_equal(dev[name], orac[name]), f"config {config}: column {name} after two ticks"
+
+
+def test_shard_additivity_at_10m(am, gen):
+    """4 index-range shards of the 10 M population concatenated == the whole, and
+    re-ticking the same second is idempotent up to the one-shot "Stopped" report."""
+    n = 10_000_000
+    prod = gen.fill(2, 2, 0, n, T0, am.load().am_healthcheck_classify, threads=8)
     with am.Sweep(capacity=n) as s:
         s.load_range(0, prod)
         idx, act, st = s.tick(T0)
-        assert st["n_records"] == n and st["n_emitted"] == len(idx)
-        assert (np.diff(idx.astype(np.int64)) > 0).all()
-        assert int(np.bitwise_xor.reduce(idx)) == st["idx_xor"]
-        assert int(idx.sum(dtype=np.uint64)) == st["idx_sum"]
-        assert int((act & am.ACT_SUBMIT_HC != 0).sum()) == st["n_submit_hc"]
-        assert int((act & am.ACT_PARSE_ERROR != 0).sum()) == st["n_parse_error"]
-        assert int((act & am.ACT_STOPPED != 0).sum()) == st["n_stopped"] > 0
-        # numpy restatement of the interval rule on the same columns (not the oracle)
-        kind = prod["flags"] & 7
-        iv = (kind == am.KIND_INTERVAL) | (kind == am.KIND_CRON_EVERY)
-        due_iv = iv & ((T0 - prod["finished_at"]) >= prod["ras"])
-        got_due = np.zeros(n, bool)
-        got_due[idx[(act & am.ACT_SUBMIT_HC) != 0].astype(np.int64)] = True
-        np.testing.assert_array_equal(got_due[iv], due_iv[iv])
-        # idempotence: open loop, same T -> same due-set (STOPPED already reported)
         idx2, act2, st2 = s.tick(T0)
         keep = (act & ~np.uint32(am.ACT_STOPPED)) != 0
         np.testing.assert_array_equal(idx2, idx[keep])
-        assert st2["n_stopped"] == 0
-    # shard additivity: 4 shards concatenated == the whole
+        assert st2["n_stopped"] == 0 and st["n_stopped"] > 0
     parts = []
     q = n // 4
     for r in range(4):
@@ -317,6 +328,107 @@ def test_full_size_10m_properties(am, gen):
             s.load_range(0, cols)
             parts.append(s.tick(T0)[0])
     np.testing.assert_array_equal(np.concatenate(parts), idx)
+
+
+def test_timer_armed_conjunct_of_the_ladder(am, orc):
+    """hcc.go:264 skips only when "elapsed < RepeatAfterSec && timer != nil".  After a controller
+    restart (empty RepeatTimersByName, hcc.go:161) a check that finished one second ago is
+    submitted anyway; once its result is applied the timer is armed (hcc.go:745-752) and the
+    interval rule holds again."""
+    T = T0
+    recs, orecs = [], []
+    for armed in (True, False):
+        for kw in (dict(repeat_after_sec=3600), dict(cron="@every 1h")):
+            rc, r = am.classify(finished_at=T - 1, timer_armed=armed, **kw)
+            assert rc == 0
+            recs.append(r)
+    recs = np.concatenate(recs)
+    assert [bool(f & am.F_TIMER_ARMED) for f in recs["flags"]] == [True, True, False, False]
+    cols = am.records_to_columns(recs)
+    ocols = {k: v.copy() for k, v in cols.items()}
+    with am.Sweep(capacity=4) as s:
+        s.load_range(0, cols)
+        got = s.tick(T)
+        want = orc.sweep(ocols, T)
+        assert got[2] == want[2]
+        assert got[0].tolist() == want[0].tolist() == [2, 3]            # only the unarmed pair is due
+        assert got[1].tolist() == [am.ACT_SUBMIT_HC] * 2
+        s.post_result([2, 3], [am.PHASE_SUCCEEDED, am.PHASE_FAILED])   # results arm the timers ...
+        ocols["flags"][2] |= am.F_PENDING_OK
+        ocols["flags"][3] |= am.F_PENDING_FAIL
+        got = s.tick(T + 1)
+        want = orc.sweep(ocols, T + 1)
+        assert got[2] == want[2] and len(got[0]) == len(want[0]) == 0   # ... and nothing is due one second later
+        dev = s.read_range(0, 4)
+        for name in am.COLUMN_NAMES:
+            np.testing.assert_array_equal(dev[name], ocols[name], err_msg=name)
+        assert all(f & am.F_TIMER_ARMED for f in dev["flags"])
+
+
+def test_workflow_phase_and_remedy_phase_posted_by_separate_calls(am, orc):
+    """The reference observes the two phases in separate watch loops (hcc.go:607-756, :788-852):
+    a "Failed" and a remedy "Succeeded" posted by two calls before ONE tick must both take
+    effect — and equal the single call carrying both."""
+    T = T0
+    rc, r = am.classify(repeat_after_sec=3600, finished_at=T - 10, has_remedy=True, remedy_runs_limit=2,
+                        remedy_reset_interval=300)
+    assert rc == 0
+    recs = np.concatenate([r, r, r, r])
+    cols = am.records_to_columns(recs)
+    ocols = {k: v.copy() for k, v in cols.items()}
+    with am.Sweep(capacity=4) as s:
+        s.load_range(0, cols)
+        s.post_result([0], [am.PHASE_FAILED])                               # slot 0: two calls
+        s.post_result([0], [am.PHASE_NONE], [am.PHASE_SUCCEEDED])
+        s.post_result([1], [am.PHASE_FAILED], [am.PHASE_SUCCEEDED])         # slot 1: one call
+        s.post_result([2], [am.PHASE_NONE], [am.PHASE_FAILED])              # slot 2: remedy first,
+        s.post_result([2], [am.PHASE_FAILED])                               #         then the failure
+        s.post_result([3], [am.PHASE_SUCCEEDED])                            # slot 3: the later phase wins,
+        s.post_result([3], [am.PHASE_FAILED])                               #         a later "none" does not erase
+        s.post_result([3], [am.PHASE_NONE])
+        for i, bits in ((0, am.F_PENDING_FAIL | am.F_REMEDY_PENDING | am.F_REMEDY_OUTCOME_OK),
+                        (1, am.F_PENDING_FAIL | am.F_REMEDY_PENDING | am.F_REMEDY_OUTCOME_OK),
+                        (2, am.F_PENDING_FAIL | am.F_REMEDY_PENDING), (3, am.F_PENDING_FAIL)):
+            ocols["flags"][i] |= bits
+        got = s.tick(T)
+        want = orc.sweep(ocols, T)
+        assert got[2] == want[2]
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+        assert got[2]["n_result_fail"] == 4 and got[2]["n_remedy_ok"] == 2 and got[2]["n_remedy_fail"] == 1
+        dev = s.read_range(0, 4)
+        for name in am.COLUMN_NAMES:
+            np.testing.assert_array_equal(dev[name], ocols[name], err_msg=name)
+        assert dev["remedy_success"].tolist() == [1, 1, 0, 0] and dev["failed"].tolist() == [1, 1, 1, 1]
+
+
+def test_tick_view_and_last_list(am, orc, gen):
+    """am_sweep_tick_view hands out the library's pinned buffer (u32 local indices, u8 actions);
+    am_sweep_last_list re-reads the same list in pieces after a short-buffer tick (nothing is lost)."""
+    n, base = 50_003, 7_000_000
+    prod, orac = _gen_pair(gen, am, orc, 3, 9, n, T0, first=base)
+    with am.Sweep(capacity=n, shard_base=base) as s:
+        s.load_range(0, prod)
+        vi, va, st = s.tick_view(T0)
+        wi, wa, ws = orc.sweep(orac, T0, shard_base=base)
+        assert st == ws and vi.dtype == np.uint32 and va.dtype == np.uint8
+        np.testing.assert_array_equal(vi.astype(np.uint64) + np.uint64(base), wi)
+        np.testing.assert_array_equal(va.astype(np.uint32), wa)
+        # a short-buffer tick consumes the one-shot actions on the device; the list is still there
+        with pytest.raises(am.AmError) as e:
+            s.tick(T0 + 60, cap=100)
+        assert e.value.code == am.AM_E_NOSPACE
+        wi, wa, ws = orc.sweep(orac, T0 + 60, shard_base=base)
+        assert e.value.needed == len(wi) > 100
+        got_i, got_a, off = [], [], 0
+        while True:
+            i, a, left = s.last_list(off, 7001)
+            got_i.append(i); got_a.append(a)
+            off += len(i)
+            if left <= 7001:
+                break
+        np.testing.assert_array_equal(np.concatenate(got_i), wi)
+        np.testing.assert_array_equal(np.concatenate(got_a), wa)
 
 
 def test_staged_events_take_effect_in_call_order(am):

@@ -38,7 +38,7 @@ uint64_t amgen_key(uint64_t seed, uint64_t i, uint64_t f) { return sm64(sm64(see
 
 /* field ids of the keyed stream */
 enum { K_KIND = 1, K_RAS, K_FIN, K_FINSET, K_FAILP, K_CRON = 16, K_REMEDY = 64, K_LIMIT, K_RESET,
-       K_PEND, K_RT, K_RS, K_RFA, K_ROUT, K_S, K_F, K_VIOL };
+       K_PEND, K_RT, K_RS, K_RFA, K_ROUT, K_S, K_F, K_VIOL, K_ARMED };
 
 typedef struct { uint64_t seed, i, ctr; } rng_t;
 static uint64_t rnd(rng_t* r) { return amgen_key(r->seed, r->i, K_CRON + (r->ctr++)); }
@@ -123,6 +123,7 @@ void amgen_healthcheck(int config, uint64_t seed, uint64_t i, int64_t T0, am_hea
   *post_flags = 0;
   buf[0] = 0;
   hc->has_resource = 1;
+  hc->timer_armed = 1; /* configs 1 / 11: a running controller, every check has its repeat timer */
   hc->cron = buf;
   int64_t period = 60;
   int mix = (config == 3 || config == 55) ? 3 : 2;
@@ -182,6 +183,9 @@ void amgen_healthcheck(int config, uint64_t seed, uint64_t i, int64_t T0, am_hea
     hc->finished_at = T0 - (int64_t)(amgen_key(seed, i, K_FIN) % (uint64_t)(2 * period + 1));
   }
   hc->fail_p8 = (uint32_t)(amgen_key(seed, i, K_FAILP) % 64);
+  /* 2 % of the checks have no repeat timer (left over from a controller restart, hcc.go:161):
+   * the ladder submits them whatever finishedAt says (hcc.go:264) */
+  hc->timer_armed = (amgen_key(seed, i, K_ARMED) % 50) != 0;
   hc->success_count = (int64_t)(amgen_key(seed, i, K_S) % 1001);
   hc->failed_count = (int64_t)(amgen_key(seed, i, K_F) % 1001);
 
@@ -299,6 +303,18 @@ uint64_t amgen_select_submitted(const uint64_t* idx, const uint32_t* act, uint64
   for (uint64_t k = 0; k < n; k++) {
     out_local[m] = idx[k] - base;
     m += (act[k] & AM_ACT_SUBMIT_HC) ? 1u : 0u;
+  }
+  return m;
+}
+
+/* The same walk over an am_tick_view_t (u32 local indices, u8 actions in the library's
+ * pinned buffer): slots of the submitted checks, as the u64 array am_sweep_post_result takes. */
+uint64_t amgen_select_submitted_view(const uint32_t* idx_local, const uint8_t* act, uint64_t n,
+                                     uint64_t* out_local) {
+  uint64_t m = 0;
+  for (uint64_t k = 0; k < n; k++) {
+    out_local[m] = idx_local[k];
+    m += (uint64_t)(act[k] & AM_ACT_SUBMIT_HC);
   }
   return m;
 }

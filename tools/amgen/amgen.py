@@ -34,7 +34,7 @@ class HealthCheckC(C.Structure):  # == am_healthcheck_t
                 ("finished_at_set", C.c_int32), ("remedy_finished_at_set", C.c_int32),
                 ("success_count", C.c_int64), ("failed_count", C.c_int64),
                 ("remedy_success_count", C.c_int64), ("remedy_failed_count", C.c_int64),
-                ("remedy_total_runs", C.c_int64), ("fail_p8", C.c_uint32), ("reserved", C.c_uint32)]
+                ("remedy_total_runs", C.c_int64), ("fail_p8", C.c_uint32), ("timer_armed", C.c_uint32)]
 
 
 _lib = None
@@ -55,6 +55,8 @@ def load() -> C.CDLL:
         lib.amgen_str_stride.restype = C.c_int
         lib.amgen_select_submitted.restype = C.c_uint64
         lib.amgen_select_submitted.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
+        lib.amgen_select_submitted_view.restype = C.c_uint64
+        lib.amgen_select_submitted_view.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.amgen_key.restype = C.c_uint64
         lib.amgen_key.argtypes = [C.c_uint64] * 3
         _lib = lib
@@ -99,4 +101,12 @@ def select_submitted(idx: np.ndarray, act: np.ndarray, base: int, out: np.ndarra
     """local slots of the entries whose action has AM_ACT_SUBMIT_HC (compiled loop: stands
     in for the Go shim walking the tick's result); `out` must hold len(idx) u64."""
     m = load().amgen_select_submitted(idx.ctypes.data, act.ctypes.data, len(idx), base, out.ctypes.data)
+    return out[:m]
+
+
+def select_submitted_view(idx_local: np.ndarray, act: np.ndarray, out: np.ndarray) -> np.ndarray:
+    """local slots (u64) of the entries of an am_tick_view_t whose action carries SUBMIT_HC"""
+    if len(idx_local) == 0:
+        return out[:0]
+    m = load().amgen_select_submitted_view(idx_local.ctypes.data, act.ctypes.data, len(idx_local), out.ctypes.data)
     return out[:m]

@@ -20,12 +20,20 @@ a = ap.parse_args()
 am = importlib.import_module("active-monitor_b200")
 T0 = amgen.T0_MON_0915
 cols = amgen.fill(a.config, a.config, 0, a.n, T0, am.load().am_healthcheck_classify)
+import torch  # noqa: E402
+dev = torch.device("cuda", 0)
+d_idx = torch.empty(a.n, dtype=torch.int32, device=dev)
+d_act = torch.empty(a.n, dtype=torch.uint8, device=dev)
+d_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+d_st = torch.zeros(16, dtype=torch.int64, device=dev)
 with am.Sweep(capacity=a.n) as s:
     s.load_range(0, cols)
     s.set_profiling(True)
     for k in range(a.ticks):
         if a.config == 3 and k:  # re-arm the pending results so every tick does the same work
             s.load_range(0, cols)
-        idx, act, st = s.tick(T0 + k * a.dt, mode=a.mode)
+        # device-resident tick (the list stays in HBM), as in bench.py's timed loop
+        s.tick_device(T0 + k * a.dt, a.mode, d_idx.data_ptr(), d_act.data_ptr(), a.n, d_cnt.data_ptr(), d_st.data_ptr(), 0)
         ka, kb = s.last_profile()
-        print(k, st["n_emitted"], st["n_submit_hc"], f"pair {s.last_kernel_ms * 1e3:.1f} us  sweep {ka * 1e3:.1f} us  compact {kb * 1e3:.1f} us")
+        st = dict(zip(am.abi.STAT_FIELDS, d_st.cpu().tolist()))
+        print(k, st["n_emitted"], st["n_submit_hc"], f"sweep {ka * 1e3:.1f} us  scan+expand+publish {kb * 1e3:.1f} us")
