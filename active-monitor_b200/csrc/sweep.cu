@@ -544,6 +544,7 @@ int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t
       AM_CUDA(h, cudaMalloc((void**)&t.tile_exc, ntiles * 4));
       AM_CUDA(h, cudaMemsetAsync(t.tile_exc, 0, ntiles * 4, h->stream));
       AM_CUDA(h, cudaMalloc((void**)&t.exc_seg, h->cap_padded * 4));
+      AM_CUDA(h, cudaMemsetAsync(t.exc_seg, 0, h->cap_padded * 4, h->stream));  // expand_kernel prefetches past the counts
       AM_CUDA(h, cudaMalloc((void**)&h->set[b].acc, kNumAcc * 8));
       AM_CUDA(h, cudaMemsetAsync(h->set[b].acc, 0, kNumAcc * 8, h->stream));
     }

@@ -580,13 +580,21 @@ __global__ void __launch_bounds__(256) expand_kernel(const ExpandParams p) {
   if (g >= src.n_groups) return;  // uniform per CTA
   pdl_wait();
   pdl_trigger();
+  // ---- every global load of the CTA is issued here, before the first use: the kernel is a chain
+  //      of L2 latencies otherwise (one CTA moves 1 KB in and ~14 KB out)
+  const uint32_t w = __ldcs(src.bitmap + (size_t)g * kGroupWords + tid);
   uint64_t start = src.group_prefix[g];
   const uint32_t cnt = src.group_prefix[g + 1] - (uint32_t)start;
-  if (cnt == 0) return;  // uniform per CTA: nothing emitted by these 8192 records
+  // warp k of the CTA patches the exceptions of tile k of the group; their first 32 entries are
+  // fetched speculatively (the segment is always mapped; entries past the count are never used)
+  const uint32_t tile = g * kGroupTiles + (uint32_t)warp;
+  const bool tile_ok = tile < src.n_tiles;
+  const uint32_t nx = tile_ok ? src.tile_exc[tile] : 0u;
+  const uint32_t e_first = tile_ok ? __ldcs(src.exc_seg + (size_t)tile * kTile + lane) : 0u;
   for (int q = 0; q < r; ++q) start += p.src[q].group_prefix[p.src[q].n_groups];
+  if (cnt == 0) return;  // uniform per CTA: nothing emitted by these 8192 records
 
   // ---- ranks: exclusive popcount prefix over the group's 256 words
-  const uint32_t w = __ldcs(src.bitmap + (size_t)g * kGroupWords + tid);
   const uint32_t c = (uint32_t)__popc(w);
   uint32_t incl = c;
 #pragma unroll
@@ -595,12 +603,12 @@ __global__ void __launch_bounds__(256) expand_kernel(const ExpandParams p) {
     if (lane >= d) incl += up;
   }
   if (lane == 31) s_warp[warp] = incl;
+  s_w[tid] = w;
   __syncthreads();
   uint32_t before = 0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) before += k < warp ? s_warp[k] : 0u;
   const uint32_t excl = before + incl - c;
-  s_w[tid] = w;
   s_wpre[tid] = (uint16_t)excl;
   {
     uint32_t ww = w, pos = excl;
@@ -613,18 +621,13 @@ __global__ void __launch_bounds__(256) expand_kernel(const ExpandParams p) {
     }
   }
   __syncthreads();
-  // ---- exceptions of the group's tiles: action bytes other than the default
-  for (uint32_t tt = 0; tt < (uint32_t)kGroupTiles; ++tt) {
-    const uint32_t tile = g * kGroupTiles + tt;
-    if (tile >= src.n_tiles) break;
-    const uint32_t nx = src.tile_exc[tile];
-    for (uint32_t i = tid; i < nx; i += blockDim.x) {
-      const uint32_t e = __ldcs(src.exc_seg + (size_t)tile * kTile + i);
-      const uint32_t off = tt * (uint32_t)kTile + (e >> 8);
-      const uint32_t wd = off >> 5;
-      const uint32_t rk = (uint32_t)s_wpre[wd] + (uint32_t)__popc(s_w[wd] & ((1u << (off & 31u)) - 1u));
-      s_act[rk] = (uint8_t)e;
-    }
+  // ---- exceptions of this warp's tile: action bytes other than the default
+  for (uint32_t i = (uint32_t)lane; i < nx; i += 32u) {
+    const uint32_t e = i < 32u ? e_first : __ldcs(src.exc_seg + (size_t)tile * kTile + i);
+    const uint32_t off = (uint32_t)warp * (uint32_t)kTile + (e >> 8);
+    const uint32_t wd = off >> 5;
+    const uint32_t rk = (uint32_t)s_wpre[wd] + (uint32_t)__popc(s_w[wd] & ((1u << (off & 31u)) - 1u));
+    s_act[rk] = (uint8_t)e;
   }
   __syncthreads();
 

@@ -55,7 +55,7 @@ WORKLOAD = {
        "seed 2); step = the single tick T0=2026-09-21T09:15:00Z",
     3: "BASELINE configs[2]: {n} HealthChecks, 50 % pending Failed / 25 % pending Succeeded through RemedyRunsLimit / "
        "RemedyResetInterval (tools/amgen config 3, seed 3); step = the tick T0 that applies them; mutable columns "
-       "restored and L2 flushed (256 MB write) between steps, outside the per-step CUDA-event interval",
+       "restored and L2 flushed (256 MB read) between steps, outside the per-step CUDA-event interval",
     5: "BASELINE configs[4]: {n} HealthChecks x consecutive one-second ticks from 2026-09-21T00:00:00Z, closed loop "
        "(a due check completes in its tick), streaming on the device (tools/amgen config 5, seed 5); step = one tick",
 }
@@ -288,7 +288,7 @@ def main():
     gather_launches = [0]
 
     # ---- config 3: the step consumes its inputs (pending results): snapshot / restore ----
-    snap = flush = None
+    snap = flush = flush_sink = None
     if config == 3:
         MUT = ["flags", "finished_at", "success", "failed", "remedy_success", "remedy_failed", "remedy_total",
                "remedy_finished_at"]
@@ -309,12 +309,15 @@ def main():
         live = {m: col_view(m) for m in MUT}
         torch.cuda.synchronize()
         snap = {m: v.clone() for m, v in live.items()}
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        flush = torch.zeros(64 << 20, dtype=torch.int32, device=dev)  # 256 MB
+        flush_sink = torch.zeros((), dtype=torch.int64, device=dev)
 
     def restore():
         for m, v in snap.items():
             live[m].copy_(v)
-        flush.zero_()  # 256 MB > the 126 MB L2: the tick starts with none of its inputs cached
+        # READ 256 MB (> the 126 MB L2): the tick starts with none of its inputs cached and with no
+        # dirty lines of the flush itself left to write back during the timed interval
+        flush_sink.copy_(flush.sum())
 
     def step(_k):
         """one tick of the configured workload, device resident, asynchronous"""
@@ -556,6 +559,7 @@ def main():
         prev = None
         reps = max(10, min(args.steps, 120))
         tick_no = 0
+        h2d = d2h = 0
         h_part = torch.empty(n * 9 + 64, dtype=torch.uint8).pin_memory() if peer is not None and mode_gather == "exchange" else None
         for phase_name in ("warm", "timed"):
             if phase_name == "timed":
@@ -684,7 +688,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": WORKLOAD[config].format(n=n), "records_per_gpu": n, "records_total": n * world,
                        "l2": ("inputs (560 MB/GPU) larger than L2 (126 MB); no flush needed" if config != 3 else
-                              "L2 flushed by a 256 MB write before every step"),
+                              "L2 flushed by a 256 MB read before every step"),
                        "parallelism": par,
                        "due_per_tick": stats["n_submit_hc"], "emitted_per_tick": stats["n_emitted"]},
             "roofline": roof,
