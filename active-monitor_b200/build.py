@@ -62,7 +62,7 @@ def build_product(force: bool = False, verbose: bool = False) -> str:
 def build_amgen(force: bool = False) -> str:
     src = os.path.join(ROOT, "tools", "amgen", "amgen.c")
     if force or _newer(AMGEN, [src, os.path.join(ROOT, "include", "amsweep.h")]):
-        _run(["gcc", "-O2", "-g", "-std=c11", "-Wall", "-fPIC", "-pthread", "-shared", "-o", AMGEN,
+        _run(["gcc", "-O3", "-g", "-std=gnu11", "-Wall", "-fPIC", "-pthread", "-shared", "-o", AMGEN,
               src, "-lpthread"])
     return AMGEN
 

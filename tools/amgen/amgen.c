@@ -309,10 +309,28 @@ uint64_t amgen_select_submitted(const uint64_t* idx, const uint32_t* act, uint64
 
 /* The same walk over an am_tick_view_t (u32 local indices, u8 actions in the library's
  * pinned buffer): slots of the submitted checks, as the u64 array am_sweep_post_result takes. */
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("avx2", "default")))
+#endif
 uint64_t amgen_select_submitted_view(const uint32_t* idx_local, const uint8_t* act, uint64_t n,
                                      uint64_t* out_local) {
-  uint64_t m = 0;
-  for (uint64_t k = 0; k < n; k++) {
+  uint64_t m = 0, k = 0;
+  /* eight entries at a time: when all eight carry the bit (almost always: 98 % of the entries
+   * are bare submits) the copy is a plain widening loop the compiler vectorises */
+  for (; k + 8 <= n; k += 8) {
+    uint64_t a8;
+    memcpy(&a8, act + k, 8);
+    if ((a8 & 0x0101010101010101ull) == 0x0101010101010101ull) {
+      for (int j = 0; j < 8; j++) out_local[m + j] = idx_local[k + j];
+      m += 8;
+    } else {
+      for (int j = 0; j < 8; j++) {
+        out_local[m] = idx_local[k + j];
+        m += (uint64_t)(act[k + j] & AM_ACT_SUBMIT_HC);
+      }
+    }
+  }
+  for (; k < n; k++) {
     out_local[m] = idx_local[k];
     m += (uint64_t)(act[k] & AM_ACT_SUBMIT_HC);
   }
