@@ -565,13 +565,16 @@ __global__ void __launch_bounds__(1024) scan_groups_kernel(const ScanParams p) {
 // writing, every thread counts action bits and checksums global indices for the shard
 // whose statistics this GPU owns.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) expand_kernel(const ExpandParams p) {
-  __shared__ uint16_t s_off[kGroupRecords];  // in-group record offsets of the set bits, ascending (16 KB)
-  __shared__ uint8_t s_act[kGroupRecords];   // their action bytes (8 KB)
+__global__ void __launch_bounds__(256, 6) expand_kernel(const ExpandParams p) {
+  // staged so that shared index j <-> output position (start & ~3) + j: a destination-aligned
+  // quad of the output is one aligned 8-B (offsets) + one 4-B (actions) shared load
+  __shared__ __align__(16) uint16_t s_off[kGroupRecords + 8];
+  __shared__ __align__(16) uint8_t s_act[kGroupRecords + 8];
   __shared__ uint32_t s_w[kGroupWords];
   __shared__ uint16_t s_wpre[kGroupWords];
   __shared__ uint32_t s_warp[8];
-  __shared__ uint32_t s_cnt[8][8];            // per-warp counts of the 8 action bits
+  __shared__ uint32_t s_nx[8];
+  __shared__ uint32_t s_cnt[8][8];            // per-warp counts of the 8 action bits among the exceptions
   __shared__ unsigned long long s_chk[8][2];  // per-warp xor / sum of emitted global indices
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = blockIdx.y;
@@ -593,6 +596,7 @@ __global__ void __launch_bounds__(256) expand_kernel(const ExpandParams p) {
   const uint32_t e_first = tile_ok ? __ldcs(src.exc_seg + (size_t)tile * kTile + lane) : 0u;
   for (int q = 0; q < r; ++q) start += p.src[q].group_prefix[p.src[q].n_groups];
   if (cnt == 0) return;  // uniform per CTA: nothing emitted by these 8192 records
+  const uint32_t sh = (uint32_t)start & 3u;
 
   // ---- ranks: exclusive popcount prefix over the group's 256 words
   const uint32_t c = (uint32_t)__popc(w);
@@ -603,7 +607,11 @@ __global__ void __launch_bounds__(256) expand_kernel(const ExpandParams p) {
     if (lane >= d) incl += up;
   }
   if (lane == 31) s_warp[warp] = incl;
+  if (lane == 0) s_nx[warp] = nx;
   s_w[tid] = w;
+  // default action for every staged entry (and the padding around them), 4 bytes per store
+  for (uint32_t j = (uint32_t)tid * 4u; j < sh + cnt + 4u; j += 1024u)
+    *reinterpret_cast<uint32_t*>(&s_act[j]) = 0x01010101u * AM_ACT_SUBMIT_HC;
   __syncthreads();
   uint32_t before = 0;
 #pragma unroll
@@ -611,93 +619,99 @@ __global__ void __launch_bounds__(256) expand_kernel(const ExpandParams p) {
   const uint32_t excl = before + incl - c;
   s_wpre[tid] = (uint16_t)excl;
   {
-    uint32_t ww = w, pos = excl;
+    uint32_t ww = w, pos = sh + excl;
     while (ww) {
       const uint32_t b = (uint32_t)__ffs((int)ww) - 1u;
       ww &= ww - 1u;
-      s_off[pos] = (uint16_t)((uint32_t)tid * 32u + b);
-      s_act[pos] = (uint8_t)AM_ACT_SUBMIT_HC;
-      ++pos;
+      s_off[pos++] = (uint16_t)((uint32_t)tid * 32u + b);
     }
   }
   __syncthreads();
-  // ---- exceptions of this warp's tile: action bytes other than the default
+  // ---- exceptions of this warp's tile: action bytes other than the default.  Their action bits
+  //      are counted here (the default entries all carry SUBMIT_HC and nothing else).
+  const bool stats = p.acc != nullptr && r == p.stats_rank;
+  uint32_t c0 = 0, c1 = 0;
   for (uint32_t i = (uint32_t)lane; i < nx; i += 32u) {
     const uint32_t e = i < 32u ? e_first : __ldcs(src.exc_seg + (size_t)tile * kTile + i);
     const uint32_t off = (uint32_t)warp * (uint32_t)kTile + (e >> 8);
     const uint32_t wd = off >> 5;
     const uint32_t rk = (uint32_t)s_wpre[wd] + (uint32_t)__popc(s_w[wd] & ((1u << (off & 31u)) - 1u));
-    s_act[rk] = (uint8_t)e;
+    s_act[sh + rk] = (uint8_t)e;
+    c0 += spread4(e);
+    c1 += spread4(e >> 4);
+  }
+  if (stats) {
+    // statistics of this warp's slice of the group: action bits from the exceptions (a lane
+    // holds at most 32 of them: byte counters), index checksums from the bitmap word itself —
+    // sum over the set bits b of word t of (32 t + b) = popc(w) 32 t + sum_j 2^j popc(w & M_j)
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    if (nx) {  // warp-uniform
+      a0 = __reduce_add_sync(kFull, (c0 & 0xFFu) | ((c0 & 0xFF00u) << 8));
+      a1 = __reduce_add_sync(kFull, ((c0 >> 16) & 0xFFu) | ((c0 >> 8) & 0xFF0000u));
+      a2 = __reduce_add_sync(kFull, (c1 & 0xFFu) | ((c1 & 0xFF00u) << 8));
+      a3 = __reduce_add_sync(kFull, ((c1 >> 16) & 0xFFu) | ((c1 >> 8) & 0xFF0000u));
+    }
+    if (lane < 8) {
+      const uint32_t qv = lane < 2 ? a0 : (lane < 4 ? a1 : (lane < 6 ? a2 : a3));
+      s_cnt[warp][lane] = (qv >> ((lane & 1) * 16)) & 0xFFFFu;
+    }
+    const uint32_t bsum = (uint32_t)__popc(w & 0xAAAAAAAAu) + 2u * (uint32_t)__popc(w & 0xCCCCCCCCu) +
+                          4u * (uint32_t)__popc(w & 0xF0F0F0F0u) + 8u * (uint32_t)__popc(w & 0xFF00FF00u) +
+                          16u * (uint32_t)__popc(w & 0xFFFF0000u);
+    const uint32_t wsum = __reduce_add_sync(kFull, c * ((uint32_t)tid * 32u) + bsum);  // < 2^24 per warp
+    if (lane == 0) s_chk[warp][1] = wsum;
   }
   __syncthreads();
 
   // ---- write-out: destination-aligned quads
-  const bool stats = p.acc != nullptr && r == p.stats_rank;
   const uint64_t obase = src.base + (uint64_t)g * kGroupRecords;
   const uint64_t sbase = p.stats_base + (uint64_t)g * kGroupRecords;
-  const uint64_t end = start + cnt;
-  uint32_t c0 = 0, c1 = 0;
-  unsigned long long cx = 0, cs = 0;
-  for (uint64_t q = (start >> 2) + (uint64_t)tid; q < ((end + 3) >> 2); q += blockDim.x) {
-    const uint64_t pos0 = q << 2;
-    uint32_t off[4], a4 = 0;
+  const uint64_t pos_base = start - sh;  // multiple of 4
+  const uint32_t n_stage = sh + cnt;
+  unsigned long long cx = 0;
+  for (uint32_t j = (uint32_t)tid; 4u * j < n_stage; j += blockDim.x) {
+    const uint2 o2 = *reinterpret_cast<const uint2*>(&s_off[4u * j]);
+    const uint32_t a4 = *reinterpret_cast<const uint32_t*>(&s_act[4u * j]);
+    const uint32_t off[4] = {o2.x & 0xFFFFu, o2.x >> 16, o2.y & 0xFFFFu, o2.y >> 16};
+    const uint64_t pos0 = pos_base + 4ull * j;
+    const uint32_t k_lo = j == 0 ? sh : 0u;
+    const uint32_t k_hi = n_stage - 4u * j < 4u ? n_stage - 4u * j : 4u;
+    if (stats) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint64_t pos = pos0 + (uint64_t)k;
-      const bool in = pos >= start && pos < end;
-      const uint32_t e = in ? (uint32_t)(pos - start) : 0u;
-      off[k] = in ? (uint32_t)s_off[e] : 0u;
-      const uint32_t a = in ? (uint32_t)s_act[e] : 0u;
-      a4 |= a << (8 * k);
-      if (stats && in) {
-        c0 += spread4(a);
-        c1 += spread4(a >> 4);
-        const unsigned long long gi = sbase + off[k];
-        cx ^= gi;
-        cs += gi;
-      }
+      for (uint32_t k = 0; k < 4; ++k)
+        if (k >= k_lo && k < k_hi) cx ^= sbase + off[k];
     }
-    if (pos0 >= start && pos0 + 4 <= end && pos0 + 4 <= p.cap) {
+    if (k_lo == 0 && k_hi == 4 && pos0 + 4 <= p.cap) {
       if (p.idx_bytes == 4) {
         const uint32_t b32 = (uint32_t)obase;
-        reinterpret_cast<uint4*>(p.out_idx)[q] = make_uint4(b32 + off[0], b32 + off[1], b32 + off[2], b32 + off[3]);
+        reinterpret_cast<uint4*>(p.out_idx)[pos0 >> 2] = make_uint4(b32 + off[0], b32 + off[1], b32 + off[2], b32 + off[3]);
       } else {
-        ulonglong2* d = reinterpret_cast<ulonglong2*>(p.out_idx) + 2 * q;
+        ulonglong2* d = reinterpret_cast<ulonglong2*>(p.out_idx) + (pos0 >> 1);
         d[0] = make_ulonglong2(obase + off[0], obase + off[1]);
         d[1] = make_ulonglong2(obase + off[2], obase + off[3]);
       }
-      reinterpret_cast<uint32_t*>(p.out_act)[q] = a4;
+      reinterpret_cast<uint32_t*>(p.out_act)[pos0 >> 2] = a4;
     } else {  // ragged first / last quad of the group, or the end of a short buffer
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint64_t pos = pos0 + (uint64_t)k;
-        if (pos < start || pos >= end || pos >= p.cap) continue;
+      for (uint32_t k = 0; k < 4; ++k) {
+        const uint64_t pos = pos0 + k;
+        if (k < k_lo || k >= k_hi || pos >= p.cap) continue;
         if (p.idx_bytes == 4) reinterpret_cast<uint32_t*>(p.out_idx)[pos] = (uint32_t)(obase + off[k]);
         else reinterpret_cast<uint64_t*>(p.out_idx)[pos] = obase + off[k];
         p.out_act[pos] = (uint8_t)(a4 >> (8 * k));
       }
     }
   }
-  // statistics: thread -> warp (redux; 16-bit fields: 32 lanes x 32 entries fit) -> CTA -> global RED
+  // statistics: warp -> CTA -> global RED
   if (stats) {
-    const uint32_t a0 = __reduce_add_sync(kFull, (c0 & 0xFFu) | ((c0 & 0xFF00u) << 8));
-    const uint32_t a1 = __reduce_add_sync(kFull, ((c0 >> 16) & 0xFFu) | ((c0 >> 8) & 0xFF0000u));
-    const uint32_t a2 = __reduce_add_sync(kFull, (c1 & 0xFFu) | ((c1 & 0xFF00u) << 8));
-    const uint32_t a3 = __reduce_add_sync(kFull, ((c1 >> 16) & 0xFFu) | ((c1 >> 8) & 0xFF0000u));
     const uint32_t xl = __reduce_xor_sync(kFull, (uint32_t)cx), xh = __reduce_xor_sync(kFull, (uint32_t)(cx >> 32));
-    unsigned long long sum = cs;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) sum += __shfl_xor_sync(kFull, sum, d);
-    if (lane < 8) {
-      const uint32_t qv = lane < 2 ? a0 : (lane < 4 ? a1 : (lane < 6 ? a2 : a3));
-      s_cnt[warp][lane] = (qv >> ((lane & 1) * 16)) & 0xFFFFu;
-    }
-    if (lane == 0) { s_chk[warp][0] = ((unsigned long long)xh << 32) | xl; s_chk[warp][1] = sum; }
+    if (lane == 0) s_chk[warp][0] = ((unsigned long long)xh << 32) | xl;
     __syncthreads();
     if (tid < 8) {
-      uint32_t v = 0;
+      uint32_t v = 0, n_exc = 0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v += s_cnt[k][tid];
+      for (int k = 0; k < 8; ++k) { v += s_cnt[k][tid]; n_exc += s_nx[k]; }
+      if (tid == 0) v += cnt - n_exc;  // every default entry is a bare SUBMIT_HC
       if (v) atomicAdd(&p.acc[2 + tid], (unsigned long long)v);
     }
     if (tid == 8) {
@@ -705,7 +719,7 @@ __global__ void __launch_bounds__(256) expand_kernel(const ExpandParams p) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) { x ^= s_chk[k][0]; t += s_chk[k][1]; }
       atomicXor(&p.acc[14], x);
-      atomicAdd(&p.acc[15], t);
+      atomicAdd(&p.acc[15], t + (unsigned long long)cnt * sbase);
     }
   }
 }

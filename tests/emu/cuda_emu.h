@@ -32,6 +32,7 @@
 #define __forceinline__ inline
 #define __shared__ static thread_local
 #define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
 
 struct uint2 { uint32_t x, y; } __attribute__((aligned(8)));
 struct uint4 { uint32_t x, y, z, w; } __attribute__((aligned(16)));
