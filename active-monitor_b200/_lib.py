@@ -157,6 +157,8 @@ SYMBOLS = {
     "am_gather_out_idx": (C.c_void_p, [C.c_void_p]),
     "am_gather_out_act": (C.c_void_p, [C.c_void_p]),
     "am_gather_out_counts": (C.c_void_p, [C.c_void_p]),
+    "am_gather_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
+    "am_gather_last_profile": (C.c_int, [C.c_void_p, P(C.c_double), P(C.c_double), P(C.c_double)]),
     "am_gather_last_error": (C.c_char_p, [C.c_void_p]),
     "am_gather_destroy": (None, [C.c_void_p]),
     "am_handoff_create": (C.c_int, [P(C.c_void_p), u64]),

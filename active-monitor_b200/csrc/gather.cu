@@ -62,6 +62,8 @@ struct am_gather {
   size_t off_bitmap[2][kMaxWorld] = {}, off_prefix[2][kMaxWorld] = {}, off_tile_exc[2][kMaxWorld] = {},
          off_exc[2][kMaxWorld] = {};
   unsigned long long push_timeout_ms = 5000;      // AMSWEEP_PUSH_TIMEOUT_MS, 0 = none
+  bool profiling = false, profiled = false;       // am_gather_set_profiling: events around the exchange's kernels
+  cudaEvent_t evp[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string last_error;
 };
 
@@ -219,7 +221,9 @@ int am_gather_exchange(am_gather_t* g, am_sweep_t* sweep, void* d_stats, void* c
   p.world = g->world;
   p.timeout_ns = g->push_timeout_ms * 1000000ull;
   p.status = g->status;
+  if (g->profiling) AMG_CUDA(g, cudaEventRecord(g->evp[0], st));
   AM_LAUNCH(gather_push_tick_kernel, g->n_ctas, 256, st, p);
+  if (g->profiling) AMG_CUDA(g, cudaEventRecord(g->evp[1], st));
   // every rank's slot in MY block is complete when the push retires: rebuild the global list
   ExpandParams e{};
   CountsParams c{};
@@ -256,7 +260,9 @@ int am_gather_exchange(am_gather_t* g, am_sweep_t* sweep, void* d_stats, void* c
   AM_LAUNCH(gather_counts_kernel, 1, 32, st, c);
   AMG_CUDA(g, cudaGetLastError());
   int rc = shard_launch_expand(sweep, e, ng_max, (uint32_t)g->world, st);
+  if (g->profiling) AMG_CUDA(g, cudaEventRecord(g->evp[2], st));
   if (rc == AM_OK) rc = shard_launch_publish(sweep, t.acc, (am_tick_stats_t*)d_stats, t.n_records, st);
+  if (g->profiling) { AMG_CUDA(g, cudaEventRecord(g->evp[3], st)); g->profiled = true; }
   if (rc == AM_OK) rc = shard_mark_consumed(sweep, t.parity, st);
   if (rc != AM_OK) g->last_error = am_last_error_detail(sweep);
   return rc;
@@ -290,6 +296,29 @@ int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_lo
   return AM_OK;
 }
 
+int am_gather_set_profiling(am_gather_t* g, int on) {
+  if (!g) return AM_E_INVAL;
+  AMG_CUDA(g, cudaSetDevice(g->device));
+  if (on && !g->evp[0])
+    for (int k = 0; k < 4; ++k) AMG_CUDA(g, cudaEventCreate(&g->evp[k]));
+  g->profiling = on != 0;
+  g->profiled = false;
+  return AM_OK;
+}
+int am_gather_last_profile(am_gather_t* g, double* push_ms, double* rebuild_ms, double* publish_ms) {
+  if (!g || !g->profiled) return AM_E_INVAL;
+  AMG_CUDA(g, cudaSetDevice(g->device));
+  AMG_CUDA(g, cudaEventSynchronize(g->evp[3]));
+  float a = 0, b = 0, c = 0;
+  AMG_CUDA(g, cudaEventElapsedTime(&a, g->evp[0], g->evp[1]));
+  AMG_CUDA(g, cudaEventElapsedTime(&b, g->evp[1], g->evp[2]));
+  AMG_CUDA(g, cudaEventElapsedTime(&c, g->evp[2], g->evp[3]));
+  if (push_ms) *push_ms = a;
+  if (rebuild_ms) *rebuild_ms = b;
+  if (publish_ms) *publish_ms = c;
+  return AM_OK;
+}
+
 void* am_gather_out_idx(am_gather_t* g) { return g ? (void*)(g->block + g->off_idx[g->epoch & 1]) : nullptr; }
 void* am_gather_out_act(am_gather_t* g) { return g ? g->block + g->off_act[g->epoch & 1] : nullptr; }
 void* am_gather_out_counts(am_gather_t* g) { return g ? g->out_counts : nullptr; }
@@ -304,6 +333,7 @@ void am_gather_destroy(am_gather_t* g) {
   if (g->block) cudaFree(g->block);
   if (g->out_counts) cudaFree(g->out_counts);
   if (g->status) cudaFree(g->status);
+  for (int k = 0; k < 4; ++k) if (g->evp[k]) cudaEventDestroy(g->evp[k]);
   delete g;
 }
 

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   // one row per warp, written unconditionally: no zero-initialisation, no shared
   // atomics, and therefore a single __syncthreads in the whole kernel
   __shared__ uint32_t s_warp_tot[kWarps], s_warp_exc[kWarps];
-  __shared__ uint32_t s_words[kTileWords];  // the tile's 32 bitmap words
+  __shared__ uint32_t s_ballot[kWarps][4];  // each warp's four emitted-record ballots
   __shared__ uint32_t s_wres[kWarps][4];    // posted results applied: ok, fail, remedy ok, remedy fail
 
   const int tid = threadIdx.x;
@@ -423,22 +423,21 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   }
 
   // ---- the emitted set as a bitmap, non-default actions as exceptions -------------
-  // e..: records with any action; x..: records whose action is not the bare SUBMIT_HC
+  // e..: records with any action; x..: records whose action is not the bare SUBMIT_HC (rare
+  // unless results are being applied: their ballots are only taken when the warp has any)
   const unsigned e00 = __ballot_sync(kFull, act[0][0] != 0), e01 = __ballot_sync(kFull, act[0][1] != 0);
   const unsigned e10 = __ballot_sync(kFull, act[1][0] != 0), e11 = __ballot_sync(kFull, act[1][1] != 0);
-  const unsigned x00 = __ballot_sync(kFull, act[0][0] > 1u), x01 = __ballot_sync(kFull, act[0][1] > 1u);
-  const unsigned x10 = __ballot_sync(kFull, act[1][0] > 1u), x11 = __ballot_sync(kFull, act[1][1] > 1u);
   const uint32_t warp_total = __popc(e00) + __popc(e01) + __popc(e10) + __popc(e11);
+  unsigned x00 = 0, x01 = 0, x10 = 0, x11 = 0;
+  if (__any_sync(kFull, (act[0][0] | act[0][1] | act[1][0] | act[1][1]) > 1u)) {
+    x00 = __ballot_sync(kFull, act[0][0] > 1u); x01 = __ballot_sync(kFull, act[0][1] > 1u);
+    x10 = __ballot_sync(kFull, act[1][0] > 1u); x11 = __ballot_sync(kFull, act[1][1] > 1u);
+  }
   const uint32_t xtot0 = __popc(x00) + __popc(x01);
   const uint32_t warp_exc = xtot0 + __popc(x10) + __popc(x11);
-  // Word k of the warp (k = lane < 4) covers its records 32k .. 32k+31: half k>>1, lanes
-  // 16(k&1) .. +15, two records per lane — the two ballots of that half, 16 bits each,
-  // interleaved.
-  if (lane < 4) {
-    const unsigned ea = lane < 2 ? e00 : e10, eb = lane < 2 ? e01 : e11;
-    const unsigned sh = (unsigned)(lane & 1) * 16u;
-    s_words[warp * 4 + lane] = spread16(ea >> sh) | (spread16(eb >> sh) << 1);
-  }
+  // the four ballots go to shared memory as they are; warp 0 interleaves them into the tile's 32
+  // bitmap words after the barrier (once per tile instead of once per warp)
+  if (lane < 4) s_ballot[warp][lane] = lane == 0 ? e00 : (lane == 1 ? e01 : (lane == 2 ? e10 : e11));
   if (lane == 0) { s_warp_tot[warp] = warp_total; s_warp_exc[warp] = warp_exc; }
 
   // ---- results applied this tick (feeds metrics.MonitorSuccess/Error): lane ->
@@ -461,7 +460,13 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   // evict_first column data streams past.
   const uint64_t keep = l2_evict_last_policy();
   if (warp == 0) {
-    st_keep_u32(p.out.bitmap + (size_t)tile * kTileWords + lane, s_words[lane], keep);
+    // Word `lane` of the tile = word k = lane & 3 of warp lane >> 2: its records 32k .. 32k+31 are
+    // half k>>1, lanes 16(k&1) .. +15, two records per lane — the two ballots of that half, 16
+    // bits each, interleaved.
+    const int ww = lane >> 2, hh = (lane >> 1) & 1;
+    const unsigned sh16 = (unsigned)(lane & 1) * 16u;
+    const uint32_t word = spread16(s_ballot[ww][2 * hh] >> sh16) | (spread16(s_ballot[ww][2 * hh + 1] >> sh16) << 1);
+    st_keep_u32(p.out.bitmap + (size_t)tile * kTileWords + lane, word, keep);
     if (lane < 4) {  // result counters (RED, no return value)
       uint32_t sv = 0;
 #pragma unroll

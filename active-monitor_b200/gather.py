@@ -125,6 +125,16 @@ class PeerGather:
         self._check(self._lib.am_gather_exchange(self._h, sweep._h, d_stats_ptr or None, stream or None),
                     "am_gather_exchange")
 
+    def set_profiling(self, on: bool):
+        self._check(self._lib.am_gather_set_profiling(self._h, int(on)), "am_gather_set_profiling")
+
+    def last_profile(self):
+        """(push ms incl. the wait for the peers, list rebuild ms, publish ms) of the last exchange"""
+        a, b, c = self._C.c_double(), self._C.c_double(), self._C.c_double()
+        self._check(self._lib.am_gather_last_profile(self._h, self._C.byref(a), self._C.byref(b), self._C.byref(c)),
+                    "am_gather_last_profile")
+        return a.value, b.value, c.value
+
     def push(self, d_idx_ptr: int, d_act_ptr: int, d_count_ptr: int, shard_base: int, stream: int):
         self._check(self._lib.am_gather_push(self._h, d_idx_ptr, d_act_ptr, d_count_ptr, shard_base,
                                              stream or None), "am_gather_push")

@@ -211,7 +211,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 5])
-    ap.add_argument("--n", type=int, default=N_PER_GPU, help="records per GPU")
+    ap.add_argument("--n", "--records-per-gpu", dest="n", type=int, default=N_PER_GPU, help="records per GPU "
+                    "(spell it --records-per-gpu under torchrun: its parser rejects the abbreviation-like --n)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="N>1: skip the oracle check of the gathered list")

@@ -368,6 +368,10 @@ int am_gather_push(am_gather_t*, const void* d_idx_local /* u32 */, const void* 
 void* am_gather_out_idx(am_gather_t*);    /* u64|u32[cap_total], valid after the last exchange / push retires */
 void* am_gather_out_act(am_gather_t*);    /* u8[cap_total]                                    */
 void* am_gather_out_counts(am_gather_t*); /* u32[world+1]                                     */
+/* Device timing of one exchange (CUDA events on its stream): the NVLink push (including the
+ * wait for the peers), the list rebuild (counts + expand), the statistics publication. */
+int am_gather_set_profiling(am_gather_t*, int on);
+int am_gather_last_profile(am_gather_t*, double* push_ms, double* rebuild_ms, double* publish_ms);
 const char* am_gather_last_error(const am_gather_t*);
 void am_gather_destroy(am_gather_t*);
 

@@ -65,6 +65,14 @@ st.synchronize()
 dist.barrier()
 c1 = nvlink_kib(lr) if rank == 0 else None
 us = e0.elapsed_time(e1) * 1e3 / K
+pg.set_profiling(True)
+prof = []
+for _ in range(10):
+    dist.barrier()
+    pg.exchange(s, d_st.data_ptr(), st.cuda_stream)
+    prof.append(pg.last_profile())
+pg.set_profiling(False)
+prof_us = [round(sum(p[k] for p in prof[2:]) / len(prof[2:]) * 1e3, 1) for k in range(3)]
 stats = dict(zip(am.abi.STAT_FIELDS, d_st.cpu().tolist()))
 idx, act, counts = pg.result()
 n_exc = int((act[sum(counts[:rank]): sum(counts[: rank + 1])] > 1).sum().item())
@@ -75,7 +83,8 @@ if rank == 0:
     out = {"world": world, "records_per_rank": n, "config": config, "exchanges": K,
            "us_per_exchange_max_over_ranks": float(t.item()),
            "what": "push (bitmap + prefixes + exceptions to every peer) + counts + list rebuild of the global list + publish",
-           "emitted_per_rank": int(stats["n_emitted"]), "global_entries": int(sum(counts)), "exceptions_rank0": n_exc,
+           "rank0_us_push_rebuild_publish_after_a_barrier": prof_us,
+           "emitted_per_rank": int(counts[0]), "global_entries": int(sum(counts)), "exceptions_rank0": n_exc,
            "payload_bytes_per_peer": payload, "payload_bytes_out_per_exchange": payload * (world - 1),
            "rebuilt_list_bytes_per_gpu": int(sum(counts)) * (pg.idx_bytes + 1)}
     if c0 and c1:

@@ -13,7 +13,11 @@ AMSWEEP_PUSH_TIMEOUT_MS=20000 timeout 900 python -m pytest tests/test_multi_gpu.
 echo "== standalone exchange, N=$N" >> $O.txt
 N=$NREC K=50 run $N 29801 tools/prof_gather.py > $O.exchange.json 2>> $O.txt; cat $O.exchange.json >> $O.txt
 echo "== bench N=$N exchange" >> $O.txt
-run $N 29802 bench.py --gpus $N --steps 200 --warmup 10 --no-cpu --n $NREC > $O.bench.json 2>> $O.txt; tail -c 2500 $O.bench.json >> $O.txt
+run $N 29802 bench.py --gpus $N --steps 200 --warmup 10 --no-cpu --records-per-gpu $NREC > $O.bench.json 2>> $O.txt; tail -c 2500 $O.bench.json >> $O.txt
 echo "== bench N=$N plain (round-1 format)" >> $O.txt
-run $N 29803 bench.py --gpus $N --steps 200 --warmup 10 --no-cpu --n $NREC --gather plain --no-verify > $O.bench_plain.json 2>> $O.txt; tail -c 600 $O.bench_plain.json >> $O.txt
+run $N 29803 bench.py --gpus $N --steps 200 --warmup 10 --no-cpu --records-per-gpu $NREC --gather plain --no-verify > $O.bench_plain.json 2>> $O.txt; tail -c 600 $O.bench_plain.json >> $O.txt
 tail -40 $O.txt
+echo "== standalone exchange, push grid 16 / 592 CTAs" >> $O.txt
+AMSWEEP_PUSH_CTAS=16 N=$NREC K=20 run $N 29804 tools/prof_gather.py 2>/dev/null | tail -1 | cut -c1-400 >> $O.txt
+AMSWEEP_PUSH_CTAS=592 N=$NREC K=20 run $N 29805 tools/prof_gather.py 2>/dev/null | tail -1 | cut -c1-400 >> $O.txt
+tail -12 $O.txt
