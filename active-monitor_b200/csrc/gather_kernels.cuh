@@ -68,6 +68,16 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned 
   }
 }
 
+// wait until a peer's done flag has reached `epoch` (epochs are compared modulo 2^32)
+__device__ __forceinline__ bool wait_done_at_least(const unsigned long long* p, uint32_t epoch, unsigned long long timeout_ns) {
+  const unsigned long long t0 = timeout_ns ? global_timer_ns() : 0ull;
+  for (;;) {
+    const uint32_t v = (uint32_t)ld_acquire_sys(p);
+    if ((int32_t)(v - epoch) >= 0 && v != 0u) return true;
+    if (timeout_ns && global_timer_ns() - t0 > timeout_ns) return false;
+  }
+}
+
 __global__ void __launch_bounds__(256) gather_push_kernel(const PushParams p) {
   __shared__ uint32_t s_count[kMaxWorld];
   const int tid = threadIdx.x;
@@ -254,10 +264,11 @@ __global__ void __launch_bounds__(256) gather_push_tick_kernel(const PushTickPar
         ExchangeHeader* peer = reinterpret_cast<ExchangeHeader*>(p.peer[r]);
         st_release_sys(&peer->done_slot[p.rank], (unsigned long long)p.epoch);
       }
-      for (int r = 0; r < p.world; ++r) {
-        unsigned long long v;
-        if (!wait_flag(&mine->done_slot[r], (unsigned long long)p.epoch, false, p.timeout_ns, &v)) *p.status = 1u;
-      }
+      // ">= epoch", not "== epoch": there is no count exchange at the start of this kernel, so a fast
+      // peer may already have finished its NEXT push (other parity) and raised done(epoch + 1) while
+      // this rank is still waiting here
+      for (int r = 0; r < p.world; ++r)
+        if (!wait_done_at_least(&mine->done_slot[r], p.epoch, p.timeout_ns)) *p.status = 1u;
       mine->cta_done = 0;
       __threadfence();
     }

@@ -384,7 +384,7 @@ int launch_tick(am_sweep* h, int64_t T, uint32_t mode, const ListOut& o, cudaStr
     e.world = 1;
     e.stats_rank = 0;
     e.idx_bytes = 4;
-    AM_LAUNCH_PDL(expand_kernel, dim3(sc.n_groups, 1), 256, s, e);
+    AM_LAUNCH_PDL(expand_kernel, dim3(sc.n_groups, 1), kExpandThreads, s, e);
     AM_LAUNCH_PDL(publish_kernel, 1, 32, s, ts.acc, o.stats, h->n_records);
     h->launches += 2;
   }
@@ -461,7 +461,7 @@ int shard_order_consumer(am_sweep* h, cudaStream_t s) {
   return AM_OK;
 }
 int shard_launch_expand(am_sweep* h, const ExpandParams& e, uint32_t groups_x, uint32_t world_y, cudaStream_t s) {
-  AM_LAUNCH(expand_kernel, dim3(groups_x, world_y), 256, s, e);
+  AM_LAUNCH(expand_kernel, dim3(groups_x, world_y), kExpandThreads, s, e);
   h->launches++;
   AM_CUDA(h, cudaGetLastError());
   return AM_OK;

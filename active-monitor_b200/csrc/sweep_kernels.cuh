@@ -244,6 +244,43 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   // the second half's loads were delayed behind the first half's compute: -30 % bandwidth).
   __syncwarp();
 
+  // ---- phase A': posted results are visible in the flags alone — the first load issued, the
+  // first to return.  When only a few lanes of the warp have one (results trickling in between
+  // two ticks: the sparse shape below), each such lane fetches the remedy / counter state of its
+  // first record with a result NOW, while the other fifteen loads are still in flight, instead
+  // of paying a second, serial memory round trip after the schedule decision (+60 us on a 10 M
+  // tick with 0.18 M posted results, profiles/r02_e2e_breakdown.md).  A second fence keeps
+  // ptxas from sinking these loads down to their use.
+  int pre_b = -1;
+  int32_t pre_lim = 0, pre_rst = 0, pre_sc = 0, pre_fc = 0, pre_rsc = 0, pre_rfc = 0, pre_rtc = 0;
+  int64_t pre_rfa = 0;
+  if (!CLOSED) {  // (the closed-loop harness posts nothing from outside: its results arise inside the tick)
+    constexpr uint32_t kPend = AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING;
+    const bool maybe = ((fl[0].x | fl[0].y | fl[1].x | fl[1].y) & kPend) != 0;
+    const unsigned lanes = __ballot_sync(kFull, maybe);
+    if (lanes != 0 && __popc(lanes) < 16) {  // warp-uniform
+      if (maybe) {
+        uint32_t pend = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint32_t f = (q & 1) ? fl[q >> 1].y : fl[q >> 1].x;
+          const bool live = ((0x3Eu >> (f & AM_KIND_MASK)) & 1u) && !(f & AM_F_TOMBSTONE);
+          if (live && (f & kPend)) pend |= 1u << q;
+        }
+        if (pend) {
+          pre_b = __ffs(pend) - 1;
+          const uint32_t i = r0[0] + (uint32_t)(64 * (pre_b >> 1) + (pre_b & 1));
+          pre_lim = ld_stream(p.c.runs_limit + i); pre_rst = ld_stream(p.c.reset_interval + i);
+          pre_sc = ld_stream(p.c.success + i); pre_fc = ld_stream(p.c.failed + i);
+          pre_rsc = ld_stream(p.c.remedy_success + i); pre_rfc = ld_stream(p.c.remedy_failed + i);
+          pre_rtc = ld_stream(p.c.remedy_total + i);
+          pre_rfa = ld_stream(p.c.remedy_finished_at + i);
+        }
+      }
+    }
+  }
+  __syncwarp();
+
   // The tick's broken-down time: one-hot words computed once per tick (civil.h) and
   // delivered through the kernel parameters, i.e. the constant bank / uniform
   // registers — cheaper than staging them in shared memory, which cost every CTA a
@@ -374,11 +411,17 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
       const int b = __ffs(needy) - 1;
       needy &= needy - 1;
       const uint32_t i = r0[0] + (uint32_t)(64 * (b >> 1) + (b & 1));
-      const int32_t lim = ld_stream(p.c.runs_limit + i), rst = ld_stream(p.c.reset_interval + i);
-      const int32_t sc = ld_stream(p.c.success + i), fc = ld_stream(p.c.failed + i);
-      const int32_t rsc = ld_stream(p.c.remedy_success + i), rfc = ld_stream(p.c.remedy_failed + i);
-      const int32_t rtc = ld_stream(p.c.remedy_total + i);
-      const int64_t rfa = ld_stream(p.c.remedy_finished_at + i);
+      int32_t lim, rst, sc, fc, rsc, rfc, rtc;
+      int64_t rfa;
+      if (b == pre_b) {  // fetched in phase A'
+        lim = pre_lim; rst = pre_rst; sc = pre_sc; fc = pre_fc; rsc = pre_rsc; rfc = pre_rfc; rtc = pre_rtc; rfa = pre_rfa;
+      } else {
+        lim = ld_stream(p.c.runs_limit + i); rst = ld_stream(p.c.reset_interval + i);
+        sc = ld_stream(p.c.success + i); fc = ld_stream(p.c.failed + i);
+        rsc = ld_stream(p.c.remedy_success + i); rfc = ld_stream(p.c.remedy_failed + i);
+        rtc = ld_stream(p.c.remedy_total + i);
+        rfa = ld_stream(p.c.remedy_finished_at + i);
+      }
       const uint32_t f0 = b == 0 ? nfl[0][0] : b == 1 ? nfl[0][1] : b == 2 ? nfl[1][0] : nfl[1][1];
       const int64_t fa0 = b == 0 ? nfa[0][0] : b == 1 ? nfa[0][1] : b == 2 ? nfa[1][0] : nfa[1][1];
       RecState s{f0, fa0, sc, fc, rsc, rfc, rtc, rfa, lim, rst};
@@ -560,9 +603,9 @@ __global__ void __launch_bounds__(1024) scan_groups_kernel(const ScanParams p) {
 
 // ---------------------------------------------------------------------------
 // Bitmap + exceptions -> the contiguous ascending (index, action) list.  One CTA per
-// (group, rank): thread t owns bitmap word t of the group (32 records).  The CTA's position
+// (group, rank): thread t owns bitmap words 2t, 2t+1 of the group (64 records).  The CTA's position
 // in the output is rank offset + group_prefix[g]; the in-group rank of a set bit is the
-// exclusive popcount prefix of its word (warp shuffles + 8 warp totals) plus the bits below
+// exclusive popcount prefix of its word (warp shuffles + 4 warp totals) plus the bits below
 // it.  Offsets and action bytes are staged in shared memory — defaults first, then the
 // tile's exceptions patched in by rank lookup — and written out as destination-aligned
 // quads (16 B of indices + 4 B of actions per store), so the same kernel can write into
@@ -570,17 +613,19 @@ __global__ void __launch_bounds__(1024) scan_groups_kernel(const ScanParams p) {
 // writing, every thread counts action bits and checksums global indices for the shard
 // whose statistics this GPU owns.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 6) expand_kernel(const ExpandParams p) {
+constexpr int kExpandThreads = 128;  // one thread per PAIR of bitmap words (64 records): the kernel is
+                                     // instruction-bound, and the per-thread fixed cost halves per entry
+__global__ void __launch_bounds__(kExpandThreads, 8) expand_kernel(const ExpandParams p) {
   // staged so that shared index j <-> output position (start & ~3) + j: a destination-aligned
   // quad of the output is one aligned 8-B (offsets) + one 4-B (actions) shared load
   __shared__ __align__(16) uint16_t s_off[kGroupRecords + 8];
   __shared__ __align__(16) uint8_t s_act[kGroupRecords + 8];
   __shared__ uint32_t s_w[kGroupWords];
   __shared__ uint16_t s_wpre[kGroupWords];
-  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_warp[4];
   __shared__ uint32_t s_nx[8];
-  __shared__ uint32_t s_cnt[8][8];            // per-warp counts of the 8 action bits among the exceptions
-  __shared__ unsigned long long s_chk[8][2];  // per-warp xor / sum of emitted global indices
+  __shared__ uint32_t s_cnt[4][8];            // per-warp counts of the 8 action bits among the exceptions
+  __shared__ unsigned long long s_chk[4][2];  // per-warp xor / sum of emitted global indices
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r = blockIdx.y;
   const uint32_t g = blockIdx.x;
@@ -590,21 +635,23 @@ __global__ void __launch_bounds__(256, 6) expand_kernel(const ExpandParams p) {
   pdl_trigger();
   // ---- every global load of the CTA is issued here, before the first use: the kernel is a chain
   //      of L2 latencies otherwise (one CTA moves 1 KB in and ~14 KB out)
-  const uint32_t w = __ldcs(src.bitmap + (size_t)g * kGroupWords + tid);
+  const uint2 w2 = __ldcs(reinterpret_cast<const uint2*>(src.bitmap + (size_t)g * kGroupWords) + tid);
   uint64_t start = src.group_prefix[g];
   const uint32_t cnt = src.group_prefix[g + 1] - (uint32_t)start;
-  // warp k of the CTA patches the exceptions of tile k of the group; their first 32 entries are
-  // fetched speculatively (the segment is always mapped; entries past the count are never used)
-  const uint32_t tile = g * kGroupTiles + (uint32_t)warp;
+  // Exceptions: half-warp (tile & 1) of warp (tile >> 1) patches tile `tile` of the group; its first
+  // 16 entries are fetched speculatively (the segment is always mapped; entries past the count are
+  // never used)
+  const uint32_t tsub = (uint32_t)tid >> 4, l16 = (uint32_t)tid & 15u;  // tile within the group, lane within the half-warp
+  const uint32_t tile = g * kGroupTiles + tsub;
   const bool tile_ok = tile < src.n_tiles;
   const uint32_t nx = tile_ok ? src.tile_exc[tile] : 0u;
-  const uint32_t e_first = tile_ok ? __ldcs(src.exc_seg + (size_t)tile * kTile + lane) : 0u;
+  const uint32_t e_first = tile_ok ? __ldcs(src.exc_seg + (size_t)tile * kTile + l16) : 0u;
   for (int q = 0; q < r; ++q) start += p.src[q].group_prefix[p.src[q].n_groups];
   if (cnt == 0) return;  // uniform per CTA: nothing emitted by these 8192 records
   const uint32_t sh = (uint32_t)start & 3u;
 
-  // ---- ranks: exclusive popcount prefix over the group's 256 words
-  const uint32_t c = (uint32_t)__popc(w);
+  // ---- ranks: exclusive popcount prefix over the group's 256 words (two per thread)
+  const uint32_t c_lo = (uint32_t)__popc(w2.x), c = c_lo + (uint32_t)__popc(w2.y);
   uint32_t incl = c;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -612,33 +659,35 @@ __global__ void __launch_bounds__(256, 6) expand_kernel(const ExpandParams p) {
     if (lane >= d) incl += up;
   }
   if (lane == 31) s_warp[warp] = incl;
-  if (lane == 0) s_nx[warp] = nx;
-  s_w[tid] = w;
+  if (l16 == 0) s_nx[tsub] = nx;
+  *reinterpret_cast<uint2*>(&s_w[2 * tid]) = w2;
   // default action for every staged entry (and the padding around them), 4 bytes per store
-  for (uint32_t j = (uint32_t)tid * 4u; j < sh + cnt + 4u; j += 1024u)
+  for (uint32_t j = (uint32_t)tid * 4u; j < sh + cnt + 4u; j += 4u * kExpandThreads)
     *reinterpret_cast<uint32_t*>(&s_act[j]) = 0x01010101u * AM_ACT_SUBMIT_HC;
   __syncthreads();
   uint32_t before = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) before += k < warp ? s_warp[k] : 0u;
+  for (int k = 0; k < 4; ++k) before += k < warp ? s_warp[k] : 0u;
   const uint32_t excl = before + incl - c;
-  s_wpre[tid] = (uint16_t)excl;
+  *reinterpret_cast<uint32_t*>(&s_wpre[2 * tid]) = excl | ((excl + c_lo) << 16);
   {
-    uint32_t ww = w, pos = sh + excl;
+    unsigned long long ww = ((unsigned long long)w2.y << 32) | w2.x;
+    uint32_t pos = sh + excl;
+    const uint32_t rec0 = (uint32_t)tid * 64u;
     while (ww) {
-      const uint32_t b = (uint32_t)__ffs((int)ww) - 1u;
-      ww &= ww - 1u;
-      s_off[pos++] = (uint16_t)((uint32_t)tid * 32u + b);
+      const uint32_t b = (uint32_t)__ffsll((long long)ww) - 1u;
+      ww &= ww - 1ull;
+      s_off[pos++] = (uint16_t)(rec0 + b);
     }
   }
   __syncthreads();
-  // ---- exceptions of this warp's tile: action bytes other than the default.  Their action bits
-  //      are counted here (the default entries all carry SUBMIT_HC and nothing else).
+  // ---- exceptions of this half-warp's tile: action bytes other than the default.  Their action
+  //      bits are counted here (the default entries all carry SUBMIT_HC and nothing else).
   const bool stats = p.acc != nullptr && r == p.stats_rank;
   uint32_t c0 = 0, c1 = 0;
-  for (uint32_t i = (uint32_t)lane; i < nx; i += 32u) {
-    const uint32_t e = i < 32u ? e_first : __ldcs(src.exc_seg + (size_t)tile * kTile + i);
-    const uint32_t off = (uint32_t)warp * (uint32_t)kTile + (e >> 8);
+  for (uint32_t i = l16; i < nx; i += 16u) {
+    const uint32_t e = i < 16u ? e_first : __ldcs(src.exc_seg + (size_t)tile * kTile + i);
+    const uint32_t off = tsub * (uint32_t)kTile + (e >> 8);
     const uint32_t wd = off >> 5;
     const uint32_t rk = (uint32_t)s_wpre[wd] + (uint32_t)__popc(s_w[wd] & ((1u << (off & 31u)) - 1u));
     s_act[sh + rk] = (uint8_t)e;
@@ -646,11 +695,11 @@ __global__ void __launch_bounds__(256, 6) expand_kernel(const ExpandParams p) {
     c1 += spread4(e >> 4);
   }
   if (stats) {
-    // statistics of this warp's slice of the group: action bits from the exceptions (a lane
-    // holds at most 32 of them: byte counters), index checksums from the bitmap word itself —
+    // statistics of this warp's slice of the group: action bits from the exceptions (a lane holds
+    // at most 64 of them: byte counters), index checksums from the bitmap words themselves — the
     // sum over the set bits b of word t of (32 t + b) = popc(w) 32 t + sum_j 2^j popc(w & M_j)
     uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    if (nx) {  // warp-uniform
+    if (__any_sync(kFull, nx != 0)) {
       a0 = __reduce_add_sync(kFull, (c0 & 0xFFu) | ((c0 & 0xFF00u) << 8));
       a1 = __reduce_add_sync(kFull, ((c0 >> 16) & 0xFFu) | ((c0 >> 8) & 0xFF0000u));
       a2 = __reduce_add_sync(kFull, (c1 & 0xFFu) | ((c1 & 0xFF00u) << 8));
@@ -660,10 +709,15 @@ __global__ void __launch_bounds__(256, 6) expand_kernel(const ExpandParams p) {
       const uint32_t qv = lane < 2 ? a0 : (lane < 4 ? a1 : (lane < 6 ? a2 : a3));
       s_cnt[warp][lane] = (qv >> ((lane & 1) * 16)) & 0xFFFFu;
     }
-    const uint32_t bsum = (uint32_t)__popc(w & 0xAAAAAAAAu) + 2u * (uint32_t)__popc(w & 0xCCCCCCCCu) +
-                          4u * (uint32_t)__popc(w & 0xF0F0F0F0u) + 8u * (uint32_t)__popc(w & 0xFF00FF00u) +
-                          16u * (uint32_t)__popc(w & 0xFFFF0000u);
-    const uint32_t wsum = __reduce_add_sync(kFull, c * ((uint32_t)tid * 32u) + bsum);  // < 2^24 per warp
+    uint32_t osum = 0;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      const uint32_t w = hf ? w2.y : w2.x;
+      osum += (uint32_t)__popc(w) * ((uint32_t)(2 * tid + hf) * 32u) + (uint32_t)__popc(w & 0xAAAAAAAAu) +
+              2u * (uint32_t)__popc(w & 0xCCCCCCCCu) + 4u * (uint32_t)__popc(w & 0xF0F0F0F0u) +
+              8u * (uint32_t)__popc(w & 0xFF00FF00u) + 16u * (uint32_t)__popc(w & 0xFFFF0000u);
+    }
+    const uint32_t wsum = __reduce_add_sync(kFull, osum);  // < 2^25 per warp
     if (lane == 0) s_chk[warp][1] = wsum;
   }
   __syncthreads();
@@ -715,14 +769,16 @@ __global__ void __launch_bounds__(256, 6) expand_kernel(const ExpandParams p) {
     if (tid < 8) {
       uint32_t v = 0, n_exc = 0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { v += s_cnt[k][tid]; n_exc += s_nx[k]; }
+      for (int k = 0; k < 4; ++k) v += s_cnt[k][tid];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) n_exc += s_nx[k];
       if (tid == 0) v += cnt - n_exc;  // every default entry is a bare SUBMIT_HC
       if (v) atomicAdd(&p.acc[2 + tid], (unsigned long long)v);
     }
     if (tid == 8) {
       unsigned long long x = 0, t = 0;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { x ^= s_chk[k][0]; t += s_chk[k][1]; }
+      for (int k = 0; k < 4; ++k) { x ^= s_chk[k][0]; t += s_chk[k][1]; }
       atomicXor(&p.acc[14], x);
       atomicAdd(&p.acc[15], t + (unsigned long long)cnt * sbase);
     }

@@ -562,7 +562,13 @@ def main():
         tick_no = 0
         h2d = d2h = 0
         h_part = torch.empty(n * 9 + 64, dtype=torch.uint8).pin_memory() if peer is not None and mode_gather == "exchange" else None
-        for phase_name in ("warm", "timed"):
+        c_loop = None
+        if h_part is None:
+            # N=1: the loop itself is compiled code calling the C-ABI, as the cgo shim is — ctypes and
+            # numpy plumbing per call would otherwise be a tenth of the step
+            c_loop = amgen.e2e_closed_loop(lib, sweep._h, T0, am.SWEEP_FULL_SCAN, 8, reps, n)
+            dt, h2d, d2h = c_loop["seconds"], c_loop["h2d_bytes"], c_loop["d2h_bytes"]
+        for phase_name in (() if c_loop else ("warm", "timed")):
             if phase_name == "timed":
                 barrier()
                 t0 = time.perf_counter()
@@ -605,6 +611,11 @@ def main():
             dt = float(t.item())
         e2e = {"value": n * world * reps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d // reps,
                "d2h_bytes_per_step": d2h // reps, "ms_per_step": dt / reps * 1e3, "steps": reps,
+               "split_ms_per_step": None if not c_loop else {"post_result": c_loop["post_s"] / reps * 1e3,
+                                                              "tick_view": c_loop["tick_s"] / reps * 1e3,
+                                                              "walk_list": c_loop["walk_s"] / reps * 1e3},
+               "driver": "compiled loop calling the C-ABI (tools/amgen/amgen.c amgen_e2e_closed_loop)" if c_loop
+                         else "python loop (ctypes + torch)",
                "api": ("am_sweep_post_result + am_sweep_tick_view (the GPU writes the list into the library's pinned "
                        "host buffer)" if h_part is None else
                        "am_sweep_post_result + am_sweep_tick_shard + am_gather_exchange + read-back of this rank's "

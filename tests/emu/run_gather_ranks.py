@@ -39,11 +39,23 @@ errors = []
 bar = threading.Barrier(world)
 
 
+def view(ptr, n, ctype, dtype):
+    """numpy copy of n elements at a raw address (np.ctypeslib.as_array on a POINTER patches the
+    ctypes type object: not safe from several rank threads at once)"""
+    if n == 0:
+        return np.zeros(0, dtype)
+    return np.frombuffer((ctype * n).from_address(ptr), dtype=dtype).copy()
+
+
 def out_views(h, total):
-    it = C.c_uint32 if idx_bytes == 4 else C.c_uint64
-    gi = np.ctypeslib.as_array(C.cast(lib.am_gather_out_idx(h), C.POINTER(it)), (max(total, 1),))[:total].astype(np.uint64)
-    ga = np.ctypeslib.as_array(C.cast(lib.am_gather_out_act(h), C.POINTER(C.c_uint8)), (max(total, 1),))[:total].copy()
+    it, dt = (C.c_uint32, np.uint32) if idx_bytes == 4 else (C.c_uint64, np.uint64)
+    gi = view(lib.am_gather_out_idx(h), total, it, dt).astype(np.uint64)
+    ga = view(lib.am_gather_out_act(h), total, C.c_uint8, np.uint8)
     return gi, ga
+
+
+def out_counts(h):
+    return view(lib.am_gather_out_counts(h), world + 1, C.c_uint32, np.uint32)
 
 
 def connect(rank, cap_total):
@@ -90,11 +102,12 @@ if mode == "tick":
                 s.tick_shard(T)
                 rc = lib.am_gather_exchange(h, s._h, st.ctypes.data, None)
                 assert rc == 0, (rc, lib.am_gather_last_error(h))
-                counts = np.ctypeslib.as_array(C.cast(lib.am_gather_out_counts(h), C.POINTER(C.c_uint32)), (world + 1,)).copy()
+                counts = out_counts(h)
                 if absent >= 0:
                     assert int(counts[world]) == 0xFFFFFFFF, counts
                     break
                 total = int(counts[world])
+                assert total <= n_total, (rank, k, counts.tolist())
                 gi, ga = out_views(h, total)
                 np.testing.assert_array_equal(gi, wi, err_msg=f"rank {rank} tick {k} idx")
                 np.testing.assert_array_equal(ga.astype(np.uint32), wa, err_msg=f"rank {rank} tick {k} act")
@@ -143,7 +156,7 @@ else:
                 act_buf = np.concatenate([act, np.zeros(4, np.uint8)])
                 rc = lib.am_gather_push(h, idx_buf.ctypes.data, act_buf.ctypes.data, cnt.ctypes.data, int(bases[rank]), None)
                 assert rc == 0, (rc, lib.am_gather_last_error(h))
-                counts = np.ctypeslib.as_array(C.cast(lib.am_gather_out_counts(h), C.POINTER(C.c_uint32)), (world + 1,)).copy()
+                counts = out_counts(h)
                 gi, ga = out_views(h, int(counts[world]))
                 want_i, want_a = [], []
                 for r in range(world):

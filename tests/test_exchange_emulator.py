@@ -67,6 +67,14 @@ def test_protocol_survives_skew_between_ranks(emu_lib):
     _run(emu_lib, ["tick", 4, 4, 48_000, 25, 2], env={"EMU_JITTER": "1"})
 
 
+def test_a_fast_rank_may_finish_its_next_push_before_a_slow_one_has_seen_this_one(emu_lib):
+    """Tiny shards, 8 ranks, 40 ticks, skew: a rank regularly raises done(e+1) while a peer still waits
+    for its done(e) — the wait must accept ">= e" (round-2 bug found here: waiting for "== e" let the
+    slow rank run into the watchdog)."""
+    _run(emu_lib, ["tick", 8, 8, 9_000, 40, 2], env={"EMU_JITTER": "1", "AMSWEEP_PUSH_TIMEOUT_MS": "20000"})
+    _run(emu_lib, ["tick", 8, 4, 9_000, 40, 3])
+
+
 def test_watchdog_gives_up_on_an_absent_peer(emu_lib):
     """The device-side wait for the peers' done flags is bounded (AMSWEEP_PUSH_TIMEOUT_MS): a rank that
     never exchanges makes the others report 0xFFFFFFFF in out_counts[world] instead of hanging the GPU."""

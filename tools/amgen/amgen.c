@@ -23,6 +23,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "../../include/amsweep.h"
 
@@ -335,4 +336,52 @@ uint64_t amgen_select_submitted_view(const uint32_t* idx_local, const uint8_t* a
     m += (uint64_t)(act[k] & AM_ACT_SUBMIT_HC);
   }
   return m;
+}
+
+/* The host-closed loop of bench.py's e2e measurement, as the cgo shim would run it: compiled code
+ * calling the C-ABI through function pointers (the harness does not link libamsweep).  Per step:
+ * post every check the previous tick submitted as Succeeded (am_sweep_post_result, host memory ->
+ * device), tick at the next second (am_sweep_tick_view: the GPU writes the list into the library's
+ * pinned host buffer), walk the list for the next step's slots (hcc.go:269-288 stand-in).
+ * Times `steps` steps after `warm` untimed ones with CLOCK_MONOTONIC; split[0..3) accumulates the
+ * seconds spent in post / tick / walk.  Returns 0 or the first failing return code. */
+typedef int (*am_post_fn)(void*, uint64_t, const uint64_t*, const uint8_t*, const uint8_t*);
+typedef int (*am_tick_view_fn)(void*, int64_t, uint32_t, am_tick_view_t*, am_tick_stats_t*);
+static double mono_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+int amgen_e2e_closed_loop(am_post_fn post, am_tick_view_fn tick, void* handle, int64_t T_first, uint32_t mode,
+                          uint64_t warm, uint64_t steps, uint64_t* slots /* capacity entries */,
+                          const uint8_t* ok_phase /* capacity x AM_PHASE_SUCCEEDED */, double* seconds,
+                          double* split, uint64_t* h2d_bytes, uint64_t* d2h_bytes, uint64_t* last_emitted,
+                          uint64_t* last_submitted) {
+  uint64_t n_prev = 0, h2d = 0, d2h = 0;
+  double t0 = 0, sp[3] = {0, 0, 0};
+  am_tick_view_t v;
+  am_tick_stats_t st;
+  memset(&v, 0, sizeof v);
+  for (uint64_t k = 0; k < warm + steps; k++) {
+    if (k == warm) { t0 = mono_s(); h2d = d2h = 0; sp[0] = sp[1] = sp[2] = 0; }
+    const double a = mono_s();
+    if (n_prev) {
+      const int rc = post(handle, n_prev, slots, ok_phase, NULL);
+      if (rc) return rc;
+      h2d += n_prev * 8;
+    }
+    const double b = mono_s();
+    const int rc = tick(handle, T_first + (int64_t)k, mode, &v, &st);
+    if (rc) return rc;
+    const double c = mono_s();
+    n_prev = amgen_select_submitted_view(v.idx_local, v.action, v.n, slots);
+    d2h += v.n * 5 + sizeof st;
+    const double d = mono_s();
+    sp[0] += b - a; sp[1] += c - b; sp[2] += d - c;
+  }
+  *seconds = mono_s() - t0;
+  if (split) { split[0] = sp[0]; split[1] = sp[1]; split[2] = sp[2]; }
+  *h2d_bytes = h2d; *d2h_bytes = d2h;
+  *last_emitted = v.n; *last_submitted = n_prev;
+  return 0;
 }

@@ -56,6 +56,8 @@ for _ in range(5):
 st.synchronize()
 dist.barrier()
 c0 = nvlink_kib(lr) if rank == 0 else None
+dist.barrier()  # the counter read takes a while on rank 0: do not let the peers run ahead into the timed loop
+torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(st)
 for _ in range(K):
