@@ -884,6 +884,31 @@ int am_sweep_repeat_after_sec(am_sweep_t* h, int64_t unix_sec, uint64_t first, u
   return AM_OK;
 }
 
+int am_sweep_next_due(am_sweep_t* h, int64_t unix_sec, int64_t* next_out) {
+  if (!h || !next_out) return AM_E_INVAL;
+  if (unix_sec >= (1ll << 55) || unix_sec <= -(1ll << 55)) return AM_E_RANGE;
+  TickGuard g(h);
+  if (!g.ok) return AM_E_BUSY;
+  AM_CUDA(h, cudaSetDevice(h->device));
+  int rc = order_on(h, h->stream);
+  if (rc != AM_OK) return rc;
+  rc = drain_staged(h, h->stream);
+  if (rc != AM_OK) return rc;
+  *next_out = INT64_MAX;  // nothing will ever be due (empty shard, only tombstones / exhausted schedules)
+  if (h->n_records == 0) return AM_OK;
+  AM_CUDA(h, h->dev_in.reserve(8));
+  AM_CUDA(h, h->pin_in.reserve(8));
+  AM_CUDA(h, cudaMemsetAsync(h->dev_in.p, 0xFF, 8, h->stream));
+  AM_LAUNCH(next_due_kernel, 148 * 8, 256, h->stream, h->cols, h->n_records, unix_sec, (unsigned long long*)h->dev_in.p);
+  h->launches++;
+  AM_CUDA(h, cudaGetLastError());
+  AM_CUDA(h, cudaMemcpyAsync(h->pin_in.p, h->dev_in.p, 8, cudaMemcpyDeviceToHost, h->stream));
+  AM_CUDA(h, cudaStreamSynchronize(h->stream));
+  const unsigned long long key = *(const unsigned long long*)h->pin_in.p;
+  if (key != ~0ull) *next_out = (int64_t)(key ^ (1ull << 63));
+  return AM_OK;
+}
+
 int am_sweep_read(am_sweep_t* h, uint64_t first, uint64_t n, const uint64_t* idx,
                   am_record_cols_t* out) {
   if (!h || !out) return AM_E_INVAL;

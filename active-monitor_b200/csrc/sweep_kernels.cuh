@@ -670,14 +670,16 @@ __global__ void __launch_bounds__(kExpandThreads, 8) expand_kernel(const ExpandP
   for (int k = 0; k < 4; ++k) before += k < warp ? s_warp[k] : 0u;
   const uint32_t excl = before + incl - c;
   *reinterpret_cast<uint32_t*>(&s_wpre[2 * tid]) = excl | ((excl + c_lo) << 16);
-  {
-    unsigned long long ww = ((unsigned long long)w2.y << 32) | w2.x;
+  {  // two 32-bit loops (a 64-bit find-first-set / clear-lowest pair costs twice the instructions)
     uint32_t pos = sh + excl;
-    const uint32_t rec0 = (uint32_t)tid * 64u;
-    while (ww) {
-      const uint32_t b = (uint32_t)__ffsll((long long)ww) - 1u;
-      ww &= ww - 1ull;
-      s_off[pos++] = (uint16_t)(rec0 + b);
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      uint32_t ww = hf ? w2.y : w2.x;
+      const uint32_t rec0 = (uint32_t)tid * 64u + (uint32_t)hf * 32u - 1u;  // __ffs is 1-based
+      while (ww) {
+        s_off[pos++] = (uint16_t)(rec0 + (uint32_t)__ffs((int)ww));
+        ww &= ww - 1u;
+      }
     }
   }
   __syncthreads();
@@ -823,6 +825,40 @@ __global__ void next_fire_kernel(DevCols c, uint32_t first, uint32_t n, int64_t 
       v = c.ras[i];
   }
   out[k] = v;
+}
+
+// The earliest second after T at which a tick of this shard would emit anything, given the state
+// as it is (no further upserts / results): the wake-up time of the reference's earliest timer
+// (time.AfterFunc, hcc.go:751) or cron activation (hcc.go:262) — the 1 Hz ticker may sleep until
+// then.  Pending results, an unreported "Stopped" and parse errors (requeued after 1 s, hcc.go:204)
+// are due at once.  Grid-stride, one record per thread and step; lane -> warp (shuffles) -> global
+// atomicMin on a biased unsigned key.
+__global__ void next_due_kernel(DevCols c, uint64_t n, int64_t T, unsigned long long* out_biased) {
+  unsigned long long best = ~0ull;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t f = c.flags[i];
+    const uint32_t kind = f & AM_KIND_MASK;
+    if ((f & AM_F_TOMBSTONE) || !((0x3Eu >> kind) & 1u)) continue;
+    int64_t due = INT64_MAX;
+    if ((f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING)) || kind == AM_KIND_PARSE_ERROR ||
+        (kind == AM_KIND_STOPPED && !(f & AM_F_STOPPED_REPORTED))) {
+      due = T + 1;
+    } else if (kind == AM_KIND_INTERVAL || kind == AM_KIND_CRON_EVERY) {
+      const int64_t at = (int64_t)((uint64_t)c.finished_at[i] + (uint64_t)(int64_t)c.ras[i]);
+      due = ((f & AM_F_TIMER_ARMED) && at > T + 1) ? at : T + 1;
+    } else if (kind == AM_KIND_CRON_SPEC) {
+      const int64_t nx = cron_next_utc(c.minute[i], c.hour[i], c.dom[i], c.month[i], c.dow[i], T);
+      if (nx != kNoNextFire) due = nx;
+    }
+    const unsigned long long key = (unsigned long long)due ^ (1ull << 63);  // order-preserving bias
+    best = key < best ? key : best;
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(kFull, best, d);
+    best = o < best ? o : best;
+  }
+  if ((threadIdx.x & 31) == 0 && best != ~0ull) atomicMin(out_biased, best);
 }
 
 // ---- staged controller events (upsert / remove / post_result) ---------------

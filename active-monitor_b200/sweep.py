@@ -279,6 +279,12 @@ class Sweep:
                     "am_sweep_repeat_after_sec")
         return out
 
+    def next_due(self, unix_sec: int):
+        """earliest second after unix_sec at which a tick would emit anything (None: never)"""
+        v = L.i64(0)
+        self._check(self._lib.am_sweep_next_due(self._h, unix_sec, C.byref(v)), "am_sweep_next_due")
+        return None if v.value == (1 << 63) - 1 else v.value
+
     # -- state out
     def read_range(self, first: int, n: int, names=None) -> dict:
         cols = {name: np.zeros(n, dtype=dt) for name, dt in L.COLUMNS

@@ -297,6 +297,14 @@ int am_sweep_run_ticks(am_sweep_t*, int64_t unix_sec0, uint64_t n_ticks, uint32_
  * checks, 0 otherwise.  On-demand query, not part of the per-tick path. */
 int am_sweep_repeat_after_sec(am_sweep_t*, int64_t unix_sec, uint64_t first, uint64_t n, int64_t* out);
 
+/* The earliest second after unix_sec at which a tick of this shard would emit anything, given
+ * the state as it stands (staged events included, no further ones assumed): the wake-up time of
+ * the reference's earliest repeat timer (hcc.go:751) or cron activation (hcc.go:262), evaluated on
+ * the device over every record (robfig SpecSchedule.Next for 5-field schedules).  The 1 Hz ticker
+ * may sleep until then — or until the next upsert / post_result, whichever comes first: ticks in
+ * between return an empty list.  INT64_MAX when nothing will ever be due. */
+int am_sweep_next_due(am_sweep_t*, int64_t unix_sec, int64_t* next_out);
+
 /* Device -> host read-back of record state (status write-back, hcc.go:1445;
  * checkpoint). idx == NULL reads the range [first, first+n). */
 int am_sweep_read(am_sweep_t*, uint64_t first, uint64_t n, const uint64_t* idx,

@@ -264,6 +264,11 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
 static inline unsigned long long atomicXor(unsigned long long* p, unsigned long long v) {
   return __atomic_fetch_xor(p, v, __ATOMIC_SEQ_CST);
 }
+static inline unsigned long long atomicMin(unsigned long long* p, unsigned long long v) {
+  unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
 static inline uint32_t atomicMax(uint32_t* p, uint32_t v) {
   uint32_t old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
   while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}

@@ -402,6 +402,51 @@ def test_workflow_phase_and_remedy_phase_posted_by_separate_calls(am, orc):
         assert dev["remedy_success"].tolist() == [1, 1, 0, 0] and dev["failed"].tolist() == [1, 1, 1, 1]
 
 
+def test_next_due_is_the_first_second_at_which_a_tick_emits(am, orc):
+    """am_sweep_next_due (on-device Next() consumed as a wake-up time): no tick before
+    it emits anything, the tick at it does — checked by brute force against the oracle's ticks."""
+    T = T0 + 17
+    specs = [dict(repeat_after_sec=300), dict(repeat_after_sec=3600), dict(cron="@every 10m"),
+             dict(cron="*/7 * * * *"), dict(cron="30 10 * * *"), dict(cron="0 0 1 1 *"), dict(repeat_after_sec=86400)]
+    for pick, fin_age in (([0, 1, 2, 4], 5), ([1, 5, 6], 100), ([3, 4, 5], 1), ([5], 1), ([1, 6], 3599)):
+        recs = []
+        for k in pick:
+            rc, r = am.classify(finished_at=T - fin_age, **specs[k])
+            assert rc == 0
+            recs.append(r)
+        cols = am.records_to_columns(np.concatenate(recs))
+        with am.Sweep(capacity=len(pick)) as s:
+            s.load_range(0, cols)
+            nd = s.next_due(T)
+            o = {k: v.copy() for k, v in cols.items()}
+            want = None
+            for t in range(T + 1, T + 4 * 3600):
+                if len(orc.sweep({k: v.copy() for k, v in o.items()}, t)[0]):
+                    want = t
+                    break
+            if want is None:  # beyond the brute-force horizon: at least nothing may be due inside it
+                assert nd is None or nd >= T + 4 * 3600, (pick, nd)
+                continue
+            assert nd == want, (pick, fin_age, nd, want)
+            if nd - 1 > T:
+                assert len(s.tick(nd - 1)[0]) == 0
+            assert len(s.tick(nd)[0]) >= 1
+    # results posted but not yet applied, an unreported "Stopped" and parse errors are due at once
+    for kw in (dict(repeat_after_sec=0), dict(cron="NOT_A_VALID_CRON")):
+        rc, r = am.classify(finished_at=T - 1, **kw)
+        with am.Sweep(capacity=1) as s:
+            s.load_range(0, am.records_to_columns(r))
+            assert s.next_due(T) == T + 1
+    rc, r = am.classify(finished_at=T - 1, repeat_after_sec=3600)
+    with am.Sweep(capacity=4) as s:
+        s.load_range(0, am.records_to_columns(r))
+        assert s.next_due(T) == T - 1 + 3600
+        s.post_result([0], [am.PHASE_FAILED])
+        assert s.next_due(T) == T + 1
+    with am.Sweep(capacity=4) as s:
+        assert s.next_due(T) is None
+
+
 def test_tick_view_and_last_list(am, orc, gen):
     """am_sweep_tick_view hands out the library's pinned buffer (u32 local indices, u8 actions);
     am_sweep_last_list re-reads the same list in pieces after a short-buffer tick (nothing is lost)."""
