@@ -29,6 +29,7 @@ F_HAS_REMEDY, F_PENDING_OK, F_PENDING_FAIL = 1 << 3, 1 << 4, 1 << 5
 F_REMEDY_PENDING, F_REMEDY_OUTCOME_OK = 1 << 6, 1 << 7
 F_TOMBSTONE, F_STOPPED_REPORTED, F_TIMER_ARMED = 1 << 8, 1 << 9, 1 << 10
 F_FAILP_SHIFT = 16
+F_TZ_SHIFT = 24
 
 ACT_SUBMIT_HC, ACT_RUN_REMEDY, ACT_STOPPED, ACT_PARSE_ERROR = 0x01, 0x02, 0x04, 0x08
 ACT_REMEDY_SKIP, ACT_RESET_ON_PASS, ACT_RESET_ON_INTERVAL, ACT_ANOMALY = 0x10, 0x20, 0x40, 0x80
@@ -116,6 +117,8 @@ assert STATS_DTYPE.itemsize == C.sizeof(AmTickStats) == 128
 P = C.POINTER
 SYMBOLS = {
     "am_cron_parse": (C.c_int, [C.c_char_p, C.c_size_t, P(AmCron), C.c_char_p, C.c_size_t]),
+    "am_tz_lookup": (C.c_int, [C.c_char_p, C.c_size_t, P(i32)]),
+    "am_tz_offset": (C.c_int, [i32, i64, P(i32)]),
     "am_cron_matches": (C.c_int, [P(AmCron), i64]),
     "am_cron_next": (i64, [P(AmCron), i64]),
     "am_cron_repeat_after_sec": (i64, [P(AmCron), i64]),

@@ -22,6 +22,7 @@
 
 #include "../../include/amsweep.h"
 #include "civil.h"
+#include "tz.h"
 
 // the ABI's struct layouts are part of the contract (tests/test_abi.py)
 static_assert(sizeof(am_cron_t) == 56, "am_cron_t layout");
@@ -402,6 +403,7 @@ int am_cron_parse(const char* spec_p, size_t len, am_cron_t* out, char* err, siz
   memset(out, 0, sizeof *out);
   string_view spec(spec_p ? spec_p : "", len);
   if (spec.empty()) { es.put("empty spec string"); return AM_E_PARSE; }
+  int32_t tz_id = 0;
 
   if (spec.rfind("TZ=", 0) == 0 || spec.rfind("CRON_TZ=", 0) == 0) {
     size_t sp = spec.find(' ');
@@ -414,10 +416,19 @@ int am_cron_parse(const char* spec_p, size_t len, am_cron_t* out, char* err, siz
     }
     string_view zone = spec.substr(eq + 1, sp - eq - 1);
     spec = trim(spec.substr(sp));
-    if (!(zone.empty() || zone == "UTC" || zone == "Local")) {
-      es.put("time zone %.*s is not evaluated on the device path", SV(zone));
+    // time.LoadLocation(zone): registered once, carried by id (tz.h); "", "UTC", "Local" -> 0
+    int32_t id = 0;
+    const int trc = amsweep_tz::lookup(zone.data(), zone.size(), &id);
+    if (trc == -1) {
+      es.put("provided bad location %.*s: unknown time zone %.*s", SV(zone), SV(zone));
+      return AM_E_PARSE;
+    }
+    if (trc != 0) {
+      es.put("time zone %.*s: more than %d distinct zones are not evaluated on the device path", SV(zone),
+             amsweep_tz::kMaxZones);
       return AM_E_UNSUPPORTED;
     }
+    tz_id = id;
   }
 
   if (!spec.empty() && spec[0] == '@') {
@@ -425,6 +436,7 @@ int am_cron_parse(const char* spec_p, size_t len, am_cron_t* out, char* err, siz
       if (spec == n.text) {
         out->kind = AM_CRON_SPEC;
         out->minute = n.mi; out->hour = n.hr; out->dom = n.dm; out->month = n.mo; out->dow = n.dw;
+        out->tz_id = tz_id;  // SpecSchedule.Location
         return AM_OK;
       }
     }
@@ -457,8 +469,20 @@ int am_cron_parse(const char* spec_p, size_t len, am_cron_t* out, char* err, siz
       !field(f[4], kDow, c.dow, es))
     return AM_E_PARSE;
   c.kind = AM_CRON_SPEC;
+  c.tz_id = tz_id;  // SpecSchedule.Location
   *out = c;
   return AM_OK;
+}
+
+int am_tz_lookup(const char* name, size_t len, int32_t* tz_id) {
+  if (!tz_id || (!name && len)) return AM_E_INVAL;
+  const int rc = amsweep_tz::lookup(name, len, tz_id);
+  return rc == 0 ? AM_OK : (rc == -1 ? AM_E_PARSE : AM_E_UNSUPPORTED);
+}
+
+int am_tz_offset(int32_t tz_id, int64_t unix_sec, int32_t* utoff_out) {
+  if (!utoff_out) return AM_E_INVAL;
+  return amsweep_tz::offset_at(tz_id, unix_sec, utoff_out) ? AM_OK : AM_E_INVAL;
 }
 
 void am_civil_from_unix(int64_t unix_sec, int32_t out[6]) {
@@ -468,7 +492,9 @@ void am_civil_from_unix(int64_t unix_sec, int32_t out[6]) {
 
 int am_cron_matches(const am_cron_t* c, int64_t unix_sec) {
   if (!c || c->kind != AM_CRON_SPEC) return 0;
-  amsweep::TickWords w = amsweep::tick_words_from_unix(unix_sec);
+  int32_t off = 0;
+  if (c->tz_id && !amsweep_tz::offset_at(c->tz_id, unix_sec, &off)) return 0;
+  amsweep::TickWords w = amsweep::tick_words_from_unix(unix_sec + off);  // the zone's wall clock
   if (!w.sec0) return 0;
   if (!(c->minute & w.minute) || !(c->hour & w.hour) || !(c->month & w.month)) return 0;
   bool a = (c->dom & w.dom) != 0, b = (c->dow & w.dow) != 0;
@@ -479,7 +505,59 @@ int64_t am_cron_next(const am_cron_t* c, int64_t t) {
   if (!c) return INT64_MIN;
   if (c->kind == AM_CRON_EVERY) return t + c->delay_sec;
   if (c->kind != AM_CRON_SPEC) return INT64_MIN;
-  return amsweep::cron_next_utc(c->minute, c->hour, c->dom, c->month, c->dow, t);
+  if (c->tz_id == 0) return amsweep::cron_next_utc(c->minute, c->hour, c->dom, c->month, c->dow, t);
+  // Zone-bound schedule: the first instant after t whose LOCAL wall clock matches.  Days whose local
+  // date cannot match are skipped whole (to the next local midnight, re-evaluated with the offset
+  // in force there); inside a candidate day, minute by minute — daylight-saving gaps (local times
+  // that never occur) and overlaps (that occur twice) fall out of evaluating real instants, as in
+  // robfig's Next, which also works on absolute time.  Five-year horizon as upstream.
+  const bool star = ((c->dom | c->dow) >> 63) != 0;
+  int32_t off = 0;
+  if (!amsweep_tz::offset_at(c->tz_id, t + 1, &off)) return INT64_MIN;
+  int64_t d0;
+  int32_t sod;
+  amsweep::split_days(t + 1 + off, d0, sod);
+  int64_t y0;
+  int32_t m0, dd0;
+  amsweep::civil_from_days(d0, y0, m0, dd0);
+  int64_t cand = t + 1 + ((60 - (t + 1 + off) % 60) % 60 + 60) % 60;  // next whole local minute (offsets may carry seconds)
+  for (;;) {
+    if (!amsweep_tz::offset_at(c->tz_id, cand, &off)) return INT64_MIN;
+    int64_t days, y;
+    int32_t m, d;
+    amsweep::split_days(cand + off, days, sod);
+    amsweep::civil_from_days(days, y, m, d);
+    if (y > y0 + 5) return INT64_MIN;
+    const bool a = (c->dom >> d) & 1, b = (c->dow >> amsweep::weekday_from_days(days)) & 1;
+    const bool day_ok = ((c->month >> m) & 1) && (star ? (a && b) : (a || b));
+    if (!day_ok) {
+      // To the first instant of the next local day.  Under the offset in force now that is
+      // cand + 86400 - sod; if the offset changes in between (a transition day) the jump may land
+      // past local midnight — walk back to the first minute that still carries the new date — or
+      // short of it (the loop then simply continues from there).
+      int64_t nx = cand + 86400 - sod;
+      int32_t o2 = 0;
+      if (!amsweep_tz::offset_at(c->tz_id, nx, &o2)) return INT64_MIN;
+      int64_t d2;
+      int32_t s2;
+      amsweep::split_days(nx + o2, d2, s2);
+      if (d2 > days && s2 != 0) {
+        for (int k = 0; k < 300; ++k) {
+          int32_t o3 = 0;
+          if (!amsweep_tz::offset_at(c->tz_id, nx - 60, &o3)) return INT64_MIN;
+          int64_t d3;
+          int32_t s3;
+          amsweep::split_days(nx - 60 + o3, d3, s3);
+          if (d3 != d2) break;
+          nx -= 60;
+        }
+      }
+      cand = nx;
+      continue;
+    }
+    if (sod % 60 == 0 && ((c->hour >> (sod / 3600)) & 1) && ((c->minute >> ((sod % 3600) / 60)) & 1)) return cand;
+    cand += 60 - sod % 60;
+  }
 }
 
 int64_t am_cron_repeat_after_sec(const am_cron_t* c, int64_t unix_sec) {
@@ -537,6 +615,7 @@ int am_healthcheck_classify(const am_healthcheck_t* hc, am_record_t* out) {
       out->dow = c.dow;
     }
   }
+  if (kind == AM_KIND_CRON_SPEC) kind |= (uint32_t)c.tz_id << AM_F_TZ_SHIFT;  // SpecSchedule.Location -> table index
   out->flags = kind | (hc->has_remedy ? AM_F_HAS_REMEDY : 0u) | (hc->fail_p8 << AM_F_FAILP_SHIFT) |
                (hc->timer_armed ? AM_F_TIMER_ARMED : 0u);  // r.GetTimerByName(name) != nil, hcc.go:264
   out->ras = ras;

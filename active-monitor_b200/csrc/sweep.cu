@@ -32,6 +32,7 @@
 
 #include "sweep_internal.h"
 #include "sweep_kernels.cuh"
+#include "tz.h"
 
 using namespace amsweep;
 
@@ -144,6 +145,10 @@ struct am_sweep {
   uint32_t* marks = nullptr;  // [3 * cap_padded] per-slot {latest state op, latest phase, latest remedy phase}
   PinnedBuf pin_in;
   DevBuf dev_in;
+  // named time zones: a flattened copy of the process-wide registry (tz.h), refreshed when it grows
+  uint64_t tz_version = 0;
+  uint32_t tz_n = 0;  // zones + 1; 0 or 1 = nothing registered
+  DevBuf tz_descs, tz_trans, tz_off, tz_table;
   std::string last_error;
   uint64_t launches = 0;
   double last_ms = -1.0;
@@ -324,6 +329,28 @@ struct ListOut {
   bool expand = true;
 };
 
+// Bring the device copy of the time-zone registry up to date (rare: only when a new zone appeared).
+int refresh_zones(am_sweep* h, cudaStream_t s) {
+  if (amsweep_tz::snapshot(nullptr, nullptr, nullptr) == h->tz_version) return AM_OK;
+  std::vector<amsweep_tz::ZoneDesc> descs;
+  std::vector<int64_t> trans;
+  std::vector<int32_t> off;
+  const uint64_t v = amsweep_tz::snapshot(&descs, &trans, &off);
+  AM_CUDA(h, cudaStreamSynchronize(s));  // earlier ticks may still read the old arrays
+  AM_CUDA(h, h->tz_descs.reserve(descs.size() * sizeof(amsweep_tz::ZoneDesc)));
+  AM_CUDA(h, h->tz_trans.reserve((trans.size() + 1) * 8));
+  AM_CUDA(h, h->tz_off.reserve((off.size() + 1) * 4));
+  AM_CUDA(h, h->tz_table.reserve((amsweep_tz::kMaxZones + 1) * sizeof(TickWords)));
+  AM_CUDA(h, cudaMemcpy(h->tz_descs.p, descs.data(), descs.size() * sizeof(amsweep_tz::ZoneDesc), cudaMemcpyHostToDevice));
+  if (!trans.empty()) {
+    AM_CUDA(h, cudaMemcpy(h->tz_trans.p, trans.data(), trans.size() * 8, cudaMemcpyHostToDevice));
+    AM_CUDA(h, cudaMemcpy(h->tz_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+  }
+  h->tz_n = (uint32_t)descs.size();
+  h->tz_version = v;
+  return AM_OK;
+}
+
 int launch_tick(am_sweep* h, int64_t T, uint32_t mode, const ListOut& o, cudaStream_t s) {
   if (h->n_records == 0) {
     // nothing to sweep: publish zeros without a launch
@@ -347,11 +374,29 @@ int launch_tick(am_sweep* h, int64_t T, uint32_t mode, const ListOut& o, cudaStr
   p.mode = mode;
   p.out = ts.out;
   p.acc = ts.acc;
+  {  // named time zones: T's wall clock per zone, computed on the device
+    const int rc = refresh_zones(h, s);
+    if (rc != AM_OK) return rc;
+    if (h->tz_n > 1) {
+      TzTableParams z{};
+      z.descs = (const amsweep_tz::ZoneDesc*)h->tz_descs.p;
+      z.trans = (const int64_t*)h->tz_trans.p;
+      z.off = (const int32_t*)h->tz_off.p;
+      z.table = (TickWords*)h->tz_table.p;
+      z.T = T;
+      z.n = h->tz_n;
+      AM_LAUNCH(tz_table_kernel, (h->tz_n + 63) / 64, 64, s, z);
+      h->launches++;
+      p.tz_table = (const TickWords*)h->tz_table.p;
+    }
+  }
   if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[0], s));
-  // off the minute no 5-field schedule can fire: the mask columns are not read
+  // off the minute no 5-field schedule can fire: the mask columns are not read.  (A zone whose UTC
+  // offset is not a whole number of minutes — historical local mean times — moves the local minute
+  // boundary: every tick then reads the masks.)
   int64_t sec_of_min = T % 60;
   if (sec_of_min < 0) sec_of_min += 60;
-  const bool masks = sec_of_min == 0 || (mode & AM_SWEEP_FULL_SCAN);
+  const bool masks = sec_of_min == 0 || (mode & AM_SWEEP_FULL_SCAN) || (h->tz_n > 1 && !amsweep_tz::all_minute_aligned(T));
   const bool closed = (mode & AM_SWEEP_CLOSED_LOOP) != 0;
   if (closed && masks) AM_LAUNCH(AM_SWEEP_KERNEL(true, true), p.n_tiles, kBlock, s, p);
   else if (closed) AM_LAUNCH(AM_SWEEP_KERNEL(true, false), p.n_tiles, kBlock, s, p);
@@ -596,6 +641,7 @@ void am_sweep_destroy(am_sweep_t* h) {
   if (h->h_stats) cudaFreeHost(h->h_stats);
   h->host_out.release();
   h->pin_in.release(); h->dev_in.release();
+  h->tz_descs.release(); h->tz_trans.release(); h->tz_off.release(); h->tz_table.release();
   if (h->ev_last) cudaEventDestroy(h->ev_last);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -860,6 +906,8 @@ int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint3
   return rc;
 }
 
+static int read_impl(am_sweep_t* h, uint64_t first, uint64_t n, const uint64_t* idx, am_record_cols_t* out);
+
 int am_sweep_repeat_after_sec(am_sweep_t* h, int64_t unix_sec, uint64_t first, uint64_t n, int64_t* out) {
   if (!h || (n && !out)) return AM_E_INVAL;
   if (first + n > h->capacity || first + n < first || n > 0xFFFFFFFFull) return AM_E_INVAL;
@@ -881,6 +929,22 @@ int am_sweep_repeat_after_sec(am_sweep_t* h, int64_t unix_sec, uint64_t first, u
   AM_CUDA(h, cudaMemcpyAsync(h->pin_in.p, h->dev_in.p, n * 8, cudaMemcpyDeviceToHost, h->stream));
   AM_CUDA(h, cudaStreamSynchronize(h->stream));
   memcpy(out, h->pin_in.p, n * 8);
+  {  // schedules bound to a named time zone (marked -1, never a real value): Next() on the host
+    std::vector<uint64_t> zi;
+    for (uint64_t k = 0; k < n; ++k) if (out[k] == -1) zi.push_back(first + k);
+    if (!zi.empty()) {
+      std::vector<uint64_t> mi(zi.size()), hr(zi.size()), dm(zi.size()), mo(zi.size()), dw(zi.size());
+      std::vector<uint32_t> fl(zi.size());
+      am_record_cols_t c{};
+      c.minute = mi.data(); c.hour = hr.data(); c.dom = dm.data(); c.month = mo.data(); c.dow = dw.data(); c.flags = fl.data();
+      const int rrc = read_impl(h, 0, zi.size(), zi.data(), &c);
+      if (rrc != AM_OK) return rrc;
+      for (size_t k = 0; k < zi.size(); ++k) {
+        am_cron_t cr{mi[k], hr[k], dm[k], mo[k], dw[k], 0, AM_CRON_SPEC, (int32_t)(fl[k] >> AM_F_TZ_SHIFT)};
+        out[zi[k] - first] = am_cron_repeat_after_sec(&cr, unix_sec);
+      }
+    }
+  }
   return AM_OK;
 }
 
@@ -909,6 +973,8 @@ int am_sweep_next_due(am_sweep_t* h, int64_t unix_sec, int64_t* next_out) {
   return AM_OK;
 }
 
+static int read_impl(am_sweep_t* h, uint64_t first, uint64_t n, const uint64_t* idx, am_record_cols_t* out);
+
 int am_sweep_read(am_sweep_t* h, uint64_t first, uint64_t n, const uint64_t* idx,
                   am_record_cols_t* out) {
   if (!h || !out) return AM_E_INVAL;
@@ -922,6 +988,11 @@ int am_sweep_read(am_sweep_t* h, uint64_t first, uint64_t n, const uint64_t* idx
     rc = drain_staged(h, h->stream);
     if (rc != AM_OK) return rc;
   }
+  return read_impl(h, first, n, idx, out);
+}
+
+// (tick guard held, staged events drained, h->stream ordered)
+static int read_impl(am_sweep_t* h, uint64_t first, uint64_t n, const uint64_t* idx, am_record_cols_t* out) {
   if (!idx) {
     if (first + n > h->capacity || first + n < first) return AM_E_INVAL;
     for (int k = 0; k < 16; ++k) {

@@ -188,6 +188,18 @@ __device__ __forceinline__ uint32_t apply_result(RecState& r, int64_t T, uint32_
   return act;
 }
 
+// The tick's wall clock in every registered time zone ("CRON_TZ=Zone ..." schedules, robfig
+// parser.go / hcc.go:253): one thread per zone evaluates the zone's UTC offset at T (transition
+// table, then the POSIX rule of the TZif footer: tz_eval.h) and writes T's LOCAL fields as the
+// one-hot words the sweep ANDs against the cron masks.  A few dozen threads, once per tick, only
+// when zones are registered.
+__global__ void tz_table_kernel(const TzTableParams p) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= p.n) return;
+  const int32_t off = k ? amsweep_tz::tz_zone_offset(p.descs[k], p.trans, p.off, p.T) : 0;
+  p.table[k] = tick_words_from_unix(p.T + off);
+}
+
 // ---------------------------------------------------------------------------
 // The sweep.  CLOSED = closed-loop harness: a due record
 // completes in the same tick with its preset outcome.
@@ -286,6 +298,9 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   // registers — cheaper than staging them in shared memory, which cost every CTA a
   // serial thread-0 section and a barrier (profiles/r01_summary.md).
   const TickWords w = p.words;
+  // named time zones are rare: one vote per warp decides whether the per-record zone lookup exists at all
+  const bool warp_tz = MASKS && p.tz_table != nullptr &&
+                       __any_sync(kFull, ((fl[0].x | fl[0].y | fl[1].x | fl[1].y) >> AM_F_TZ_SHIFT) != 0);
 
   uint32_t act[2][2];
   uint32_t res_lane = 0;  // 4 x 8-bit counts of results applied by this lane
@@ -320,11 +335,20 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
         const uint64_t miv = j ? mi[h].y : mi[h].x, hrv = j ? hr[h].y : hr[h].x;
         const uint64_t dmv = j ? dm[h].y : dm[h].x, mov = j ? mo[h].y : mo[h].x;
         const uint64_t dwv = j ? dw[h].y : dw[h].x;
+        uint64_t t_mi = w.minute, t_hr = w.hour, t_dm = w.dom, t_mo = w.month, t_dw = w.dow;
+        uint32_t t_s0 = w.sec0;
+        if (warp_tz) {  // warp-uniform: some record of this warp is bound to a named time zone
+          const uint32_t tz = f >> AM_F_TZ_SHIFT;
+          if (tz) {  // the zone's wall clock instead of UTC's (SpecSchedule.Location)
+            const TickWords* z = p.tz_table + tz;
+            t_mi = z->minute; t_hr = z->hour; t_dm = z->dom; t_mo = z->month; t_dw = z->dow; t_s0 = z->sec0;
+          }
+        }
         // branch-free: every term is evaluated (no short-circuit control flow)
-        const bool fld = ((miv & w.minute) != 0) & ((hrv & w.hour) != 0) & ((mov & w.month) != 0);
-        const bool dmm = (dmv & w.dom) != 0, dwm = (dwv & w.dow) != 0;
+        const bool fld = ((miv & t_mi) != 0) & ((hrv & t_hr) != 0) & ((mov & t_mo) != 0);
+        const bool dmm = (dmv & t_dm) != 0, dwm = (dwv & t_dw) != 0;
         const bool star = ((dmv | dwv) >> 63) != 0;  // robfig dayMatches
-        due_cron = (w.sec0 != 0) & fld & (star ? (dmm & dwm) : (dmm | dwm));
+        due_cron = (t_s0 != 0) & fld & (star ? (dmm & dwm) : (dmm | dwm));
       }
       const bool is_iv = ((0x14u >> kind) & 1u) != 0;  // INTERVAL or CRON_EVERY
       const bool due = live && (is_iv ? due_iv : (kind == AM_KIND_CRON_SPEC && due_cron));
@@ -819,7 +843,9 @@ __global__ void next_fire_kernel(DevCols c, uint32_t first, uint32_t n, int64_t 
   const uint32_t kind = f & AM_KIND_MASK;
   int64_t v = 0;
   if (!(f & AM_F_TOMBSTONE)) {
-    if (kind == AM_KIND_CRON_SPEC)
+    if (kind == AM_KIND_CRON_SPEC && (f >> AM_F_TZ_SHIFT) != 0)
+      v = -1;  // bound to a named time zone: the host evaluates Next() (am_cron_next), marked here
+    else if (kind == AM_KIND_CRON_SPEC)
       v = repeat_after_from_next(cron_next_utc(c.minute[i], c.hour[i], c.dom[i], c.month[i], c.dow[i], T), T);
     else if (kind == AM_KIND_INTERVAL || kind == AM_KIND_CRON_EVERY)
       v = c.ras[i];
@@ -846,6 +872,8 @@ __global__ void next_due_kernel(DevCols c, uint64_t n, int64_t T, unsigned long 
     } else if (kind == AM_KIND_INTERVAL || kind == AM_KIND_CRON_EVERY) {
       const int64_t at = (int64_t)((uint64_t)c.finished_at[i] + (uint64_t)(int64_t)c.ras[i]);
       due = ((f & AM_F_TIMER_ARMED) && at > T + 1) ? at : T + 1;
+    } else if (kind == AM_KIND_CRON_SPEC && (f >> AM_F_TZ_SHIFT) != 0) {
+      due = T + 60 - ((T % 60) + 60) % 60;  // zone-bound: not before the next whole minute (a safe lower bound)
     } else if (kind == AM_KIND_CRON_SPEC) {
       const int64_t nx = cron_next_utc(c.minute[i], c.hour[i], c.dom[i], c.month[i], c.dow[i], T);
       if (nx != kNoNextFire) due = nx;

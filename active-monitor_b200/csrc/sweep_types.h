@@ -9,6 +9,7 @@
 
 #include "../../include/amsweep.h"
 #include "civil.h"
+#include "tz_eval.h"
 
 // Kernel launches are spelled through two macros so that tests/emu can compile the host
 // runtime (sweep.cu) for the CPU emulator as well.  AM_LAUNCH is the plain <<<>>> launch;
@@ -92,6 +93,17 @@ struct SweepParams {
   uint32_t mode;
   TickOut out;
   unsigned long long* acc;   // [kNumAcc] statistics accumulators (zero on entry)
+  const TickWords* tz_table; // [zones + 1] T's LOCAL fields per registered time zone (entry 0 = UTC);
+                             // NULL when no zone is registered
+};
+
+struct TzTableParams {       // tz_table_kernel: one thread per zone
+  const amsweep_tz::ZoneDesc* descs;
+  const int64_t* trans;
+  const int32_t* off;
+  TickWords* table;
+  int64_t T;
+  uint32_t n;                // zones + 1
 };
 
 struct ScanParams {

@@ -17,12 +17,6 @@ using amsweep::days_from_civil;
 using amsweep::split_days;
 using amsweep::weekday_from_days;
 
-struct Rule {      // one side of a POSIX TZ daylight rule
-  int kind = -1;   // 0: Jn (1..365, Feb 29 never counted)  1: n (0..365)  2: Mm.w.d
-  int a = 0, b = 0, c = 0;
-  int32_t time = 7200;  // seconds after local midnight (default 02:00:00; may be negative or > 24 h)
-};
-
 struct Zone {
   std::string name;
   std::vector<int64_t> trans;  // transition instants, ascending
@@ -30,8 +24,22 @@ struct Zone {
   int32_t off_first = 0;       // before the first transition
   bool has_footer = false, has_dst = false;
   int32_t std_off = 0, dst_off = 0;  // seconds EAST of UTC
-  Rule start, end;
+  Rule start{-1, 0, 0, 0, 7200}, end{-1, 0, 0, 0, 7200};
 };
+
+ZoneDesc desc_of(const Zone& z, uint32_t begin) {
+  ZoneDesc d{};
+  d.trans_begin = begin;
+  d.trans_count = (uint32_t)z.trans.size();
+  d.off_first = z.off_first;
+  d.has_footer = z.has_footer;
+  d.has_dst = z.has_dst;
+  d.std_off = z.std_off;
+  d.dst_off = z.dst_off;
+  d.start = z.start;
+  d.end = z.end;
+  return d;
+}
 
 int64_t be64(const unsigned char* p) {
   uint64_t v = 0;
@@ -115,42 +123,6 @@ bool parse_footer(const std::string& f, Zone& z) {
   return true;
 }
 
-bool is_leap(int64_t y) { return (y % 4 == 0 && y % 100 != 0) || y % 400 == 0; }
-
-// seconds since the epoch of LOCAL midnight-based rule instant in year y (in the rule's own local clock)
-int64_t rule_local_seconds(const Rule& r, int64_t y) {
-  int64_t day;  // days since the epoch of the rule's date
-  if (r.kind == 0) {
-    int d = r.a;  // 1..365, Feb 29 never counted
-    if (is_leap(y) && d >= 60) d += 1;
-    day = days_from_civil(y, 1, 1) + d - 1;
-  } else if (r.kind == 1) {
-    day = days_from_civil(y, 1, 1) + r.a;
-  } else {
-    const int64_t first = days_from_civil(y, r.a, 1);
-    const int wd = weekday_from_days(first);
-    int d = 1 + (r.c - wd + 7) % 7 + 7 * (r.b - 1);
-    static const int mdays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
-    int len = mdays[r.a - 1] + ((r.a == 2 && is_leap(y)) ? 1 : 0);
-    while (d > len) d -= 7;  // week 5 = the last one
-    day = first + d - 1;
-  }
-  return day * 86400 + r.time;
-}
-
-int32_t footer_offset(const Zone& z, int64_t utc) {
-  if (!z.has_dst) return z.std_off;
-  int64_t days, y;
-  int32_t sod, m, d;
-  split_days(utc + z.std_off, days, sod);
-  civil_from_days(days, y, m, d);
-  // the rule instants of year y, as UTC: the start is given in standard time, the end in daylight time
-  const int64_t s = rule_local_seconds(z.start, y) - z.std_off;
-  const int64_t e = rule_local_seconds(z.end, y) - z.dst_off;
-  const bool dst = s < e ? (utc >= s && utc < e) : !(utc >= e && utc < s);
-  return dst ? z.dst_off : z.std_off;
-}
-
 bool load_file(const std::string& path, Zone& z) {
   FILE* f = fopen(path.c_str(), "rb");
   if (!f) return false;
@@ -213,18 +185,12 @@ bool load_file(const std::string& path, Zone& z) {
 }
 
 int32_t zone_offset(const Zone& z, int64_t utc) {
-  if (z.trans.empty() || utc < z.trans.front()) return z.trans.empty() && z.has_footer ? footer_offset(z, utc) : z.off_first;
-  if (utc >= z.trans.back() && z.has_footer) return footer_offset(z, utc);
-  size_t lo = 0, hi = z.trans.size();  // last transition <= utc
-  while (hi - lo > 1) {
-    const size_t mid = (lo + hi) / 2;
-    if (z.trans[mid] <= utc) lo = mid; else hi = mid;
-  }
-  return z.off[lo];
+  return tz_zone_offset(desc_of(z, 0), z.trans.data(), z.off.data(), utc);
 }
 
 std::mutex g_mu;
 std::vector<std::unique_ptr<Zone>> g_zones;  // id - 1
+uint64_t g_version = 0;                      // bumped on every registration
 
 bool valid_name(const std::string& n) {  // Go: containsDotDot, leading '/' or '\\' are "invalid location name"
   if (n.empty() || n[0] == '/' || n[0] == '\\' || n.size() > 255) return false;
@@ -251,6 +217,7 @@ int lookup(const char* name, size_t len, int32_t* id_out) {
   if (!ok) return -1;
   if ((int)g_zones.size() >= kMaxZones) return -2;
   g_zones.push_back(std::move(z));
+  ++g_version;
   *id_out = (int32_t)g_zones.size();
   return 0;
 }
@@ -260,6 +227,27 @@ bool offset_at(int32_t id, int64_t utc, int32_t* utoff) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (id < 0 || (size_t)id > g_zones.size()) return false;
   *utoff = zone_offset(*g_zones[(size_t)id - 1], utc);
+  return true;
+}
+
+uint64_t snapshot(std::vector<ZoneDesc>* descs, std::vector<int64_t>* trans, std::vector<int32_t>* off) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (descs) {
+    descs->clear(); trans->clear(); off->clear();
+    descs->push_back(ZoneDesc{});  // id 0 = UTC: no transitions, offset 0
+    for (const auto& z : g_zones) {
+      descs->push_back(desc_of(*z, (uint32_t)trans->size()));
+      trans->insert(trans->end(), z->trans.begin(), z->trans.end());
+      off->insert(off->end(), z->off.begin(), z->off.end());
+    }
+  }
+  return g_version;
+}
+
+bool all_minute_aligned(int64_t utc) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (const auto& z : g_zones)
+    if (zone_offset(*z, utc) % 60) return false;
   return true;
 }
 

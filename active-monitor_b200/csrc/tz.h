@@ -16,7 +16,10 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "civil.h"
+#include "tz_eval.h"
 
 namespace amsweep_tz {
 
@@ -28,6 +31,12 @@ int lookup(const char* name, size_t len, int32_t* id_out);
 // UTC offset (seconds east) of zone `id` at a UTC instant.  false: unknown id.
 bool offset_at(int32_t id, int64_t utc, int32_t* utoff);
 int count();
+// Flattened copy of the registry for the device (entry 0 = UTC) and its version (bumped on every
+// registration); descs == nullptr: the version only.
+uint64_t snapshot(std::vector<ZoneDesc>* descs, std::vector<int64_t>* trans, std::vector<int32_t>* off);
+// true iff every registered zone's offset at `utc` is a whole number of minutes: the kernel may then
+// skip the cron masks off the minute (the local second-of-minute equals the UTC one)
+bool all_minute_aligned(int64_t utc);
 // The tick's local broken-down time per zone (entry 0 = UTC).  Returns true iff every registered
 // zone's offset at `utc` is a whole number of minutes (the kernel may then skip the cron masks off
 // the minute: the local second-of-minute equals the UTC one).

@@ -45,10 +45,11 @@ class Cron:
     month: int = 0
     dow: int = 0
     delay_sec: int = 0
+    tz_id: int = 0  # SpecSchedule.Location: 0 = UTC, else an am_tz_lookup id
 
     def _c(self) -> L.AmCron:
         return L.AmCron(self.minute, self.hour, self.dom, self.month, self.dow, self.delay_sec,
-                        self.kind, 0)
+                        self.kind, self.tz_id)
 
     def matches(self, unix_sec: int) -> bool:
         return bool(L.load().am_cron_matches(C.byref(self._c()), unix_sec))
@@ -77,7 +78,27 @@ def cron_parse(spec) -> Cron:
         raise CronUnsupported(err.value.decode("utf-8", "replace"))
     if rc != L.AM_OK:
         raise AmError(rc, "am_cron_parse")
-    return Cron(out.kind, out.minute, out.hour, out.dom, out.month, out.dow, out.delay_sec)
+    return Cron(out.kind, out.minute, out.hour, out.dom, out.month, out.dow, out.delay_sec, out.tz_id)
+
+
+def tz_lookup(name: str) -> int:
+    """time.LoadLocation: the id of a named time zone (0 = UTC); raises CronParseError when unknown"""
+    raw = name.encode()
+    i = L.i32(0)
+    rc = L.load().am_tz_lookup(raw, len(raw), C.byref(i))
+    if rc == L.AM_E_PARSE:
+        raise CronParseError(f"provided bad location {name}")
+    if rc != L.AM_OK:
+        raise AmError(rc, "am_tz_lookup")
+    return i.value
+
+
+def tz_offset(tz_id: int, unix_sec: int) -> int:
+    off = L.i32(0)
+    rc = L.load().am_tz_offset(tz_id, unix_sec, C.byref(off))
+    if rc != L.AM_OK:
+        raise AmError(rc, "am_tz_offset")
+    return off.value
 
 
 def civil_from_unix(unix_sec: int):

@@ -39,7 +39,8 @@ extern "C" {
 #define AM_E_NOMEM (-5)       /* host or device allocation failed             */
 #define AM_E_PARSE (-6)       /* cron spec rejected (robfig error text in err) */
 #define AM_E_UNSUPPORTED (-7) /* valid spec the device path does not evaluate
-                                 (non-UTC CRON_TZ); keep it on the Go path    */
+                                 (a 256th distinct CRON_TZ zone): keep it on
+                                 the Go path                                  */
 #define AM_E_BUSY (-8)        /* second concurrent am_sweep_tick on a handle  */
 
 /* ---- cron (replaces cron.ParseStandard, hcc.go:253; robfig/cron v3.0.1) - */
@@ -53,14 +54,27 @@ typedef struct am_cron {
   uint64_t minute, hour, dom, month, dow; /* robfig SpecSchedule fields      */
   int64_t delay_sec;                      /* ConstantDelaySchedule.Delay / s  */
   int32_t kind;                           /* AM_CRON_*                        */
-  int32_t tz_id;                          /* 0 = time.Local == UTC (distroless
-                                             image, Dockerfile:25)            */
+  int32_t tz_id;                          /* SpecSchedule.Location: 0 = time.Local ==
+                                             UTC (distroless image, Dockerfile:25),
+                                             else an am_tz_lookup id           */
 } am_cron_t;
 
 /* Parse `spec[0..len)` exactly as cron.ParseStandard does.  On a rejected
  * spec returns AM_E_PARSE, sets out->kind = AM_CRON_ERROR and writes the
  * robfig-style message (NUL-terminated, truncated to errcap) into err. */
 int am_cron_parse(const char* spec, size_t len, am_cron_t* out, char* err, size_t errcap);
+
+/* Named time zones.  robfig resolves a "TZ=" / "CRON_TZ=" prefix with time.LoadLocation and
+ * evaluates the schedule in that zone (parser.go; call site hcc.go:253).  Here a zone is registered
+ * once per process under a small id (1..255; "", "UTC" and "Local" are 0: the shipped image runs in
+ * UTC) read from the system's TZif files ($ZONEINFO, /usr/share/zoneinfo, ...: Go's search path);
+ * am_cron_parse does this by itself and returns the id in am_cron_t.tz_id; classify carries it in
+ * the record's flags (AM_F_TZ_SHIFT); each tick evaluates such records against their zone's wall
+ * clock on the device.  AM_E_PARSE: unknown zone (robfig: "provided bad location");
+ * AM_E_UNSUPPORTED: more than 255 distinct zones in one process. */
+int am_tz_lookup(const char* name, size_t len, int32_t* tz_id);
+/* UTC offset, seconds east, of a registered zone at a UTC instant (0 for id 0). */
+int am_tz_offset(int32_t tz_id, int64_t unix_sec, int32_t* utoff_out);
 
 /* matches(T) of SURVEY Appendix A.7 for one schedule and one UTC second:
  * 1 if a SpecSchedule fires exactly at unix_sec, else 0 (host helper; the
@@ -87,7 +101,8 @@ int64_t am_cron_repeat_after_sec(const am_cron_t* c, int64_t unix_sec);
 #define AM_KIND_CRON_SPEC 3u     /* ras<=0 && 5-field/descriptor, hcc.go:251   */
 #define AM_KIND_CRON_EVERY 4u    /* ras<=0 && "@every d", hcc.go:251           */
 #define AM_KIND_PARSE_ERROR 5u   /* ParseStandard error, hcc.go:254-257        */
-#define AM_KIND_HOST_FALLBACK 6u /* AM_E_UNSUPPORTED specs: never evaluated    */
+#define AM_KIND_HOST_FALLBACK 6u /* AM_E_UNSUPPORTED specs (a 256th distinct time
+                                    zone): not evaluated on the device          */
 #define AM_F_HAS_REMEDY (1u << 3)        /* !RemedyWorkflow.IsEmpty()          */
 #define AM_F_PENDING_OK (1u << 4)        /* workflow phase Succeeded posted    */
 #define AM_F_PENDING_FAIL (1u << 5)      /* workflow phase Failed posted       */
@@ -98,6 +113,9 @@ int64_t am_cron_repeat_after_sec(const am_cron_t* c, int64_t unix_sec);
 #define AM_F_TIMER_ARMED (1u << 10)      /* RepeatTimersByName holds a timer for the
                                             check (hcc.go:264 "&& timer != nil";
                                             armed by hcc.go:745-752 after a result) */
+#define AM_F_TZ_SHIFT 24                 /* bits 24..31: time zone of a 5-field schedule
+                                            ("CRON_TZ=Zone ..."), 0 = UTC; am_tz_lookup   */
+#define AM_F_TZ_MASK (0xFFu << AM_F_TZ_SHIFT)
 #define AM_F_FAILP_SHIFT 16              /* closed-loop harness: P(fail)*256   */
 #define AM_F_FAILP_MASK (0xFFu << AM_F_FAILP_SHIFT)
 

@@ -43,6 +43,7 @@ _Static_assert(sizeof(orc_tick_stats_t) == 128, "layout");
 #define F_STOPPED_REPORTED (1u << 9)
 #define F_TIMER_ARMED (1u << 10) /* r.GetTimerByName(name) != nil, hcc.go:264 */
 #define F_FAILP_SHIFT 16
+#define F_TZ_SHIFT 24 /* bits 24..31: time zone id of a 5-field schedule, 0 = UTC */
 #define ACT_SUBMIT_HC 0x01u
 #define ACT_RUN_REMEDY 0x02u
 #define ACT_STOPPED 0x04u
@@ -56,6 +57,7 @@ _Static_assert(sizeof(orc_tick_stats_t) == 128, "layout");
 #define CRON_SPEC 1
 #define CRON_EVERY 2
 #define STAR_BIT (1ull << 63)
+#define E_INVAL (-1)
 #define E_RANGE (-2)
 #define E_NOSPACE (-3)
 #define E_PARSE (-6)
@@ -533,6 +535,90 @@ static int parse_descriptor(str_t d, orc_cron_t* out, errbuf_t* e) {
   return -1;
 }
 
+/* ---- named time zones (time.LoadLocation, robfig parser.go) ----------------
+ * Ids are handed out in order of first appearance (1..255), like the product's,
+ * but nothing else is shared with it: the product reads TZif files itself
+ * (csrc/tz.cpp); the oracle asks libc — setenv("TZ") + tzset() + localtime_r
+ * under a lock, the process-global way. */
+#define ORC_MAX_ZONES 255
+static pthread_mutex_t g_tz_mu = PTHREAD_MUTEX_INITIALIZER;
+static char g_tz_names[ORC_MAX_ZONES + 1][256];
+static int g_tz_count = 0;
+
+static int tz_file_exists(const char* name) {
+  const char* dirs[] = {getenv("ZONEINFO"), "/usr/share/zoneinfo", "/usr/share/lib/zoneinfo", "/usr/lib/locale/TZ",
+                        "/etc/zoneinfo"};
+  for (size_t k = 0; k < sizeof dirs / sizeof dirs[0]; k++) {
+    if (!dirs[k]) continue;
+    char path[768];
+    snprintf(path, sizeof path, "%s/%s", dirs[k], name);
+    FILE* f = fopen(path, "rb");
+    if (!f) continue;
+    char magic[4] = {0, 0, 0, 0};
+    size_t n = fread(magic, 1, 4, f);
+    fclose(f);
+    if (n == 4 && memcmp(magic, "TZif", 4) == 0) return 1;
+  }
+  return 0;
+}
+
+/* 0 ok (*id set; "", "UTC", "Local" -> 0), -6 unknown zone, -7 table full */
+int orc_tz_lookup(const char* name, size_t len, int32_t* id) {
+  if (len == 0 || (len == 3 && memcmp(name, "UTC", 3) == 0) || (len == 5 && memcmp(name, "Local", 5) == 0)) {
+    *id = 0;
+    return 0;
+  }
+  if (len > 255 || name[0] == '/' || name[0] == '\\') return E_PARSE;
+  char buf[256];
+  memcpy(buf, name, len);
+  buf[len] = 0;
+  if (strstr(buf, "..")) return E_PARSE;
+  pthread_mutex_lock(&g_tz_mu);
+  int rc = 0;
+  int found = 0;
+  for (int k = 1; k <= g_tz_count; k++)
+    if (strcmp(g_tz_names[k], buf) == 0) { *id = k; found = 1; break; }
+  if (!found) {
+    if (!tz_file_exists(buf)) rc = E_PARSE;
+    else if (g_tz_count >= ORC_MAX_ZONES) rc = E_UNSUPPORTED;
+    else { strcpy(g_tz_names[++g_tz_count], buf); *id = g_tz_count; }
+  }
+  pthread_mutex_unlock(&g_tz_mu);
+  return rc;
+}
+
+/* T's broken-down LOCAL time in every registered zone (entry 0 = UTC), through libc */
+static int zone_tms(int64_t T, struct tm* out /* [ORC_MAX_ZONES + 1] */) {
+  time_t tt = (time_t)T;
+  gmtime_r(&tt, &out[0]);
+  pthread_mutex_lock(&g_tz_mu);
+  const int n = g_tz_count;
+  if (n > 0) {
+    char* old = getenv("TZ");
+    char saved[300];
+    if (old) snprintf(saved, sizeof saved, "%s", old);
+    for (int k = 1; k <= n; k++) {
+      char v[300];
+      snprintf(v, sizeof v, ":%s", g_tz_names[k]);
+      setenv("TZ", v, 1);
+      tzset();
+      localtime_r(&tt, &out[k]);
+    }
+    if (old) setenv("TZ", saved, 1); else unsetenv("TZ");
+    tzset();
+  }
+  pthread_mutex_unlock(&g_tz_mu);
+  return n;
+}
+
+int orc_tz_offset(int32_t id, int64_t T, int32_t* utoff) {
+  struct tm tms[ORC_MAX_ZONES + 1];
+  const int n = zone_tms(T, tms);
+  if (id < 0 || id > n) return E_INVAL;
+  *utoff = id ? (int32_t)tms[id].tm_gmtoff : 0;
+  return 0;
+}
+
 /* Parser.Parse with options Minute|Hour|Dom|Month|Dow|Descriptor
  * (= ParseStandard, hcc.go:253) */
 int orc_cron_parse(const char* spec_p, size_t len, orc_cron_t* out, char* err, size_t errcap) {
@@ -541,6 +627,7 @@ int orc_cron_parse(const char* spec_p, size_t len, orc_cron_t* out, char* err, s
   memset(out, 0, sizeof *out);
   if (err && errcap) err[0] = 0;
   if (spec.n == 0) { set_err(&e, "empty spec string"); return E_PARSE; }
+  int32_t tz_id = 0;
 
   /* Extract timezone if present */
   if (str_has_prefix(spec, "TZ=") || str_has_prefix(spec, "CRON_TZ=")) {
@@ -553,13 +640,16 @@ int orc_cron_parse(const char* spec_p, size_t len, orc_cron_t* out, char* err, s
       return E_PARSE;
     }
     str_t loc = {spec.p + eq + 1, (size_t)(i - eq - 1)};
-    int utc = (loc.n == 0) || str_eq(loc, "UTC") || str_eq(loc, "Local");
     str_t rest = {spec.p + i, spec.n - (size_t)i};
     spec = go_trim_space(rest);
-    if (!utc) {
-      /* a named zone needs the tz database: neither oracle nor device
-       * evaluates it — reported as "unsupported", never as parsed */
-      set_err(&e, "time zone %.*s not evaluated on the device path", (int)loc.n, loc.p);
+    /* loc, err = time.LoadLocation(...): "provided bad location %s: %v" */
+    int trc = orc_tz_lookup(loc.p, loc.n, &tz_id);
+    if (trc == E_PARSE) {
+      set_err(&e, "provided bad location %.*s: unknown time zone %.*s", (int)loc.n, loc.p, (int)loc.n, loc.p);
+      return E_PARSE;
+    }
+    if (trc != 0) {
+      set_err(&e, "time zone %.*s: more than %d distinct zones", (int)loc.n, loc.p, ORC_MAX_ZONES);
       return E_UNSUPPORTED;
     }
   }
@@ -567,6 +657,7 @@ int orc_cron_parse(const char* spec_p, size_t len, orc_cron_t* out, char* err, s
   /* Handle named schedules (descriptors) */
   if (str_has_prefix(spec, "@")) {
     if (parse_descriptor(spec, out, &e)) { memset(out, 0, sizeof *out); return E_PARSE; }
+    if (out->kind == CRON_SPEC) out->tz_id = tz_id; /* SpecSchedule.Location; a ConstantDelaySchedule has none */
     return 0;
   }
 
@@ -588,6 +679,7 @@ int orc_cron_parse(const char* spec_p, size_t len, orc_cron_t* out, char* err, s
   (void)second; /* always 1<<0: the reason matches() requires sec == 0 */
   out->kind = CRON_SPEC;
   out->minute = minute; out->hour = hour; out->dom = dom; out->month = month; out->dow = dow;
+  out->tz_id = tz_id; /* SpecSchedule.Location */
   return 0;
 }
 
@@ -595,9 +687,15 @@ int orc_cron_parse(const char* spec_p, size_t len, orc_cron_t* out, char* err, s
 /* robfig/cron v3.0.1 spec.go, in UTC                                        */
 /* ======================================================================== */
 
+/* Set (under g_tz_mu, with TZ pointing at the zone) while Next() walks a zone-bound schedule:
+ * the two calendar helpers then work on the zone's wall clock, as Go's time package does for a
+ * time.Time carrying that Location. */
+static __thread int tl_in_zone = 0;
+
 static void utc_tm(int64_t t, struct tm* tm) {
   time_t tt = (time_t)t;
-  gmtime_r(&tt, tm);
+  if (tl_in_zone) localtime_r(&tt, tm);
+  else gmtime_r(&tt, tm);
 }
 
 void orc_civil_from_unix(int64_t unix_sec, int32_t out[6]) {
@@ -625,6 +723,11 @@ static int matches_tm(const orc_cron_t* c, const struct tm* t) {
   return day_matches(c, t);
 }
 int orc_cron_matches(const orc_cron_t* c, int64_t T) {
+  if (c->tz_id) { /* the schedule's Location: T's wall clock there */
+    struct tm tms[ORC_MAX_ZONES + 1];
+    const int n = zone_tms(T, tms);
+    return c->tz_id <= n ? matches_tm(c, &tms[c->tz_id]) : 0;
+  }
   struct tm t;
   utc_tm(T, &t);
   return matches_tm(c, &t);
@@ -635,15 +738,43 @@ static int64_t tm_date(int year, int mon1, int mday, int hh, int mm, int ss) {
   memset(&tm, 0, sizeof tm);
   tm.tm_year = year - 1900; tm.tm_mon = mon1 - 1; tm.tm_mday = mday;
   tm.tm_hour = hh; tm.tm_min = mm; tm.tm_sec = ss;
+  if (tl_in_zone) {
+    tm.tm_isdst = -1;
+    return (int64_t)mktime(&tm); /* time.Date(..., loc) */
+  }
   return (int64_t)timegm(&tm); /* normalises like time.Date / AddDate */
 }
 
 /* SpecSchedule.Next (spec.go) for a whole-second t in UTC; the zero time
  * (nothing within five years) is reported as INT64_MIN.
  * ConstantDelaySchedule.Next (constantdelay.go) = t + Delay. */
+static int64_t cron_next_in_current_zone(const orc_cron_t* s, int64_t t0);
+
 int64_t orc_cron_next(const orc_cron_t* s, int64_t t0) {
   if (s->kind == CRON_EVERY) return t0 + s->delay_sec;
   if (s->kind != CRON_SPEC) return INT64_MIN;
+  if (s->tz_id == 0) return cron_next_in_current_zone(s, t0);
+  /* t = t.In(s.Location): the same walk on the zone's wall clock, libc's tz database behind it */
+  pthread_mutex_lock(&g_tz_mu);
+  int64_t r = INT64_MIN;
+  if (s->tz_id <= g_tz_count) {
+    char* old = getenv("TZ");
+    char saved[300], v[300];
+    if (old) snprintf(saved, sizeof saved, "%s", old);
+    snprintf(v, sizeof v, ":%s", g_tz_names[s->tz_id]);
+    setenv("TZ", v, 1);
+    tzset();
+    tl_in_zone = 1;
+    r = cron_next_in_current_zone(s, t0);
+    tl_in_zone = 0;
+    if (old) setenv("TZ", saved, 1); else unsetenv("TZ");
+    tzset();
+  }
+  pthread_mutex_unlock(&g_tz_mu);
+  return r;
+}
+
+static int64_t cron_next_in_current_zone(const orc_cron_t* s, int64_t t0) {
   /* Start at the earliest possible time (the upcoming second). */
   int64_t t = t0 + 1;
   int added = 0;
@@ -668,7 +799,7 @@ WRAP:
     if (tm.tm_mon == 0) goto WRAP; /* wrapped around to January */
   }
 
-  /* Now get a day in that month (UTC: the DST hour fix-up never triggers). */
+  /* Now get a day in that month. */
   while (!day_matches(s, &tm)) {
     if (!added) {
       added = 1;
@@ -677,6 +808,13 @@ WRAP:
     }
     t = tm_date(tm.tm_year + 1900, tm.tm_mon + 1, tm.tm_mday + 1, tm.tm_hour, tm.tm_min, tm.tm_sec);
     utc_tm(t, &tm);
+    /* "Notice if the hour is no longer midnight due to DST.  Add an hour if it's 23, subtract an
+     * hour if it's 1." (spec.go) — never in UTC */
+    if (tm.tm_hour != 0) {
+      if (tm.tm_hour > 12) t += (int64_t)(24 - tm.tm_hour) * 3600;
+      else t -= (int64_t)tm.tm_hour * 3600;
+      utc_tm(t, &tm);
+    }
     if (tm.tm_mday == 1) goto WRAP;
   }
 
@@ -768,7 +906,7 @@ int orc_classify(const orc_healthcheck_t* hc, orc_record_t* out) {
       flags = KIND_CRON_EVERY;
       ras = (int32_t)c.delay_sec; /* hcc.go:262 with N2 */
     } else {
-      flags = KIND_CRON_SPEC;
+      flags = KIND_CRON_SPEC | ((uint32_t)c.tz_id << F_TZ_SHIFT); /* SpecSchedule.Location */
       out->minute = c.minute; out->hour = c.hour; out->dom = c.dom;
       out->month = c.month; out->dow = c.dow;
     }
@@ -879,7 +1017,7 @@ static uint32_t apply_result(orc_record_t* r, int64_t T, orc_tick_stats_t* st) {
   return act;
 }
 
-/* `tmT` = gmtime(T), computed once per tick by the sweeps (glibc's gmtime_r
+/* `tmT[z]` = T's broken-down time in zone z (0 = UTC), computed once per tick by the sweeps (glibc's gmtime_r
  * takes a process-wide lock, which would serialise the threaded baseline) */
 static uint32_t tick_record_tm(orc_record_t* r, int64_t T, const struct tm* tmT, uint32_t mode,
                                uint64_t seed, uint64_t gidx, orc_tick_stats_t* st) {
@@ -912,7 +1050,7 @@ static uint32_t tick_record_tm(orc_record_t* r, int64_t T, const struct tm* tmT,
     }
     case KIND_CRON_SPEC: {
       orc_cron_t c = {r->minute, r->hour, r->dom, r->month, r->dow, 0, CRON_SPEC, 0};
-      due = matches_tm(&c, tmT);
+      due = matches_tm(&c, &tmT[r->flags >> F_TZ_SHIFT]); /* T's wall clock in the schedule's Location */
       break;
     }
   }
@@ -934,9 +1072,9 @@ static uint32_t tick_record_tm(orc_record_t* r, int64_t T, const struct tm* tmT,
 
 uint32_t orc_tick_record(orc_record_t* r, int64_t T, uint32_t mode, uint64_t seed,
                          uint64_t gidx, orc_tick_stats_t* st) {
-  struct tm tmT;
-  utc_tm(T, &tmT);
-  return tick_record_tm(r, T, &tmT, mode, seed, gidx, st);
+  struct tm tmT[ORC_MAX_ZONES + 1];
+  zone_tms(T, tmT);
+  return tick_record_tm(r, T, tmT, mode, seed, gidx, st);
 }
 
 /* ---- whole-array sweeps -------------------------------------------------- */
@@ -1016,10 +1154,10 @@ int orc_sweep(orc_record_cols_t* cols, uint64_t n, uint64_t shard_base, int64_t 
   orc_tick_stats_t st;
   memset(&st, 0, sizeof st);
   st.n_records = n;
-  struct tm tmT;
-  utc_tm(T, &tmT);
+  struct tm tmT[ORC_MAX_ZONES + 1];
+  zone_tms(T, tmT);
   for (uint64_t i = 0; i < n; i++) {
-    uint32_t act = sweep_one(cols, i, T, &tmT, mode, seed, shard_base + i, &st);
+    uint32_t act = sweep_one(cols, i, T, tmT, mode, seed, shard_base + i, &st);
     if (act) {
       if (st.n_emitted < cap) {
         if (due_idx) due_idx[st.n_emitted] = shard_base + i;
@@ -1058,6 +1196,7 @@ typedef struct {
   uint8_t* act8; /* scratch: the action byte of every record of this tick */
   mt_slot_t* slot;
   int nthreads;
+  const struct tm* tms; /* T in every registered zone */
   pthread_barrier_t bar;
 } mt_ctx_t;
 
@@ -1073,11 +1212,10 @@ static void mt_run_chunk(mt_ctx_t* x, int t) {
   const int64_t T = x->T;
   const uint32_t mode = x->mode;
   uint8_t* act8 = x->act8;
-  struct tm tmT;
-  utc_tm(T, &tmT);
+  const struct tm* tmT = x->tms; /* computed once per tick by the caller: setenv/tzset are process-global */
   uint64_t n = 0;
   for (uint64_t i = lo; i < hi; i++) {
-    uint32_t a = sweep_one(&cols, i, T, &tmT, mode, seed, base + i, &st);
+    uint32_t a = sweep_one(&cols, i, T, tmT, mode, seed, base + i, &st);
     act8[i] = (uint8_t)a; /* every action bit is below 0x100 */
     if (a) {
       n++;
@@ -1189,6 +1327,9 @@ int orc_sweep_mt(orc_record_cols_t* cols, uint64_t n, uint64_t shard_base, int64
   memset(&x, 0, sizeof x);
   x.cols = cols; x.n = n; x.shard_base = shard_base; x.T = T; x.mode = mode; x.seed = seed;
   x.due_idx = due_idx; x.due_action = due_action; x.cap = cap; x.nthreads = nthreads;
+  struct tm tms[ORC_MAX_ZONES + 1];
+  zone_tms(T, tms);
+  x.tms = tms;
   x.act8 = (uint8_t*)malloc(n ? n : 1);
   x.slot = (mt_slot_t*)calloc((size_t)nthreads, sizeof *x.slot);
   if (!x.act8 || !x.slot || pthread_barrier_init(&x.bar, NULL, (unsigned)nthreads) != 0) {

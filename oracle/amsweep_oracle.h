@@ -100,6 +100,9 @@ typedef struct orc_tick_stats {
 
 /* robfig/cron v3.0.1 ParseStandard.  0 ok, -6 rejected (message in err). */
 int orc_cron_parse(const char* spec, size_t len, orc_cron_t* out, char* err, size_t errcap);
+/* time.LoadLocation for "TZ=" / "CRON_TZ=" prefixes: ids in order of first appearance */
+int orc_tz_lookup(const char* name, size_t len, int32_t* id);
+int orc_tz_offset(int32_t id, int64_t unix_sec, int32_t* utoff); /* through libc's tz database */
 int orc_cron_matches(const orc_cron_t* c, int64_t unix_sec);
 int64_t orc_cron_next(const orc_cron_t* c, int64_t unix_sec);
 int64_t orc_cron_repeat_after_sec(const orc_cron_t* c, int64_t unix_sec);

@@ -54,6 +54,10 @@ def load() -> C.CDLL:
         if not os.path.exists(LIB_PATH):
             raise ImportError(f"{LIB_PATH} missing: run `make -C oracle`")
         lib = C.CDLL(LIB_PATH)
+        lib.orc_tz_lookup.restype = C.c_int
+        lib.orc_tz_lookup.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(i32)]
+        lib.orc_tz_offset.restype = C.c_int
+        lib.orc_tz_offset.argtypes = [i32, i64, C.POINTER(i32)]
         lib.orc_cron_parse.restype = C.c_int
         lib.orc_cron_parse.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(OrcCron), C.c_char_p, C.c_size_t]
         lib.orc_cron_matches.restype = C.c_int

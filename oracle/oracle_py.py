@@ -292,15 +292,56 @@ class Cron:
     month: int = 0
     dow: int = 0
     delay_sec: int = 0
+    tz_id: int = 0  # SpecSchedule.Location: 0 = UTC, else an id of tz_lookup()
 
     def masks(self):
         return (self.minute, self.hour, self.dom, self.month, self.dow)
+
+
+# ---- named time zones (time.LoadLocation): the standard library's zoneinfo, nothing shared
+#      with the product's TZif reader or the C oracle's libc calls; ids in order of first appearance
+F_TZ_SHIFT = 24
+_TZ_NAMES: list[str] = [""]
+_TZ_INFO: list = [None]
+
+
+def tz_lookup(name: str) -> int:
+    if name in ("", "UTC", "Local"):
+        return 0
+    if name in _TZ_NAMES:
+        return _TZ_NAMES.index(name)
+    import zoneinfo
+    if name.startswith(("/", "\\")) or ".." in name or len(name) > 255:
+        raise CronError(f"provided bad location {name}")
+    try:
+        zi = zoneinfo.ZoneInfo(name)
+    except Exception:
+        raise CronError(f"provided bad location {name}: unknown time zone {name}") from None
+    if len(_TZ_NAMES) > 255:
+        raise CronUnsupported(name)
+    _TZ_NAMES.append(name)
+    _TZ_INFO.append(zi)
+    return len(_TZ_NAMES) - 1
+
+
+def _wall(t: int, tz_id: int) -> _dt.datetime:
+    """t's wall clock in the zone (naive datetime)"""
+    if tz_id == 0:
+        return _utc(t)
+    return _dt.datetime.fromtimestamp(t, _TZ_INFO[tz_id]).replace(tzinfo=None)
+
+
+def tz_offset(tz_id: int, t: int) -> int:
+    if tz_id == 0:
+        return 0
+    return int(_dt.datetime.fromtimestamp(t, _TZ_INFO[tz_id]).utcoffset().total_seconds())
 
 
 def cron_parse(spec: str) -> Cron:
     """cron.ParseStandard (hcc.go:253).  Raises CronError / CronUnsupported."""
     if spec == "":
         raise CronError("empty spec string")
+    tz_id = 0
     if spec.startswith("TZ=") or spec.startswith("CRON_TZ="):
         i = spec.find(" ")
         eq = spec.find("=")
@@ -308,8 +349,7 @@ def cron_parse(spec: str) -> Cron:
             raise CronError("robfig v3.0.1 panics: TZ= without a following space")
         loc = spec[eq + 1:i]
         spec = go_trim_space(spec[i:])
-        if loc not in ("", "UTC", "Local"):
-            raise CronUnsupported(loc)
+        tz_id = tz_lookup(loc)
     if spec.startswith("@"):
         one_min, one_hr = 1 << 0, 1 << 0
         table = {
@@ -323,7 +363,7 @@ def cron_parse(spec: str) -> Cron:
         }
         if spec in table:
             mi, hr, dm, mo, dw = table[spec]
-            return Cron(CRON_SPEC, mi, hr, dm, mo, dw)
+            return Cron(CRON_SPEC, mi, hr, dm, mo, dw, tz_id=tz_id)
         if spec.startswith("@every "):
             try:
                 ns = parse_duration(spec[len("@every "):])
@@ -341,7 +381,7 @@ def cron_parse(spec: str) -> Cron:
     dm = _field_mask(fields[2], "dom")
     mo = _field_mask(fields[3], "month")
     dw = _field_mask(fields[4], "dow")
-    return Cron(CRON_SPEC, mi, hr, dm, mo, dw)
+    return Cron(CRON_SPEC, mi, hr, dm, mo, dw, tz_id=tz_id)
 
 
 _EPOCH = _dt.datetime(1970, 1, 1)
@@ -371,7 +411,7 @@ def civil_from_unix(t: int):
 def cron_matches(c: Cron, t: int) -> bool:
     if c.kind != CRON_SPEC:
         return False
-    d = _utc(t)
+    d = _wall(t, c.tz_id)
     return (d.second == 0 and bool(c.minute >> d.minute & 1) and bool(c.hour >> d.hour & 1)
             and bool(c.month >> d.month & 1) and _day_ok(c, d.date()))
 
@@ -383,6 +423,27 @@ def cron_next(c: Cron, t: int):
         return t + c.delay_sec
     if c.kind != CRON_SPEC:
         return None
+    if c.tz_id:
+        # zone-bound: the first instant after t whose wall clock in the zone matches, by brute force
+        # over whole minutes (days whose local date cannot match are skipped a local day at a time)
+        y0 = _wall(t + 1, c.tz_id).year
+        cand = t + 1
+        cand += (-(cand + tz_offset(c.tz_id, cand))) % 60
+        while True:
+            w = _wall(cand, c.tz_id)
+            if w.year > y0 + 5:
+                return None
+            if not ((c.month >> w.month & 1) and _day_ok(c, w.date())):
+                # the first instant whose wall clock shows the next local date (minute steps; a
+                # transition may sit anywhere in between, so no arithmetic on offsets here)
+                nxt = w.date() + _dt.timedelta(days=1)
+                cand += 86400 - (w.hour * 3600 + w.minute * 60 + w.second) - 4 * 3600
+                while _wall(cand, c.tz_id).date() < nxt:
+                    cand += 60
+                continue
+            if w.second == 0 and (c.hour >> w.hour & 1) and (c.minute >> w.minute & 1):
+                return cand
+            cand += 60 - w.second
     start = _utc(t + 1)
     year_limit = start.year + 5
     mins = [m for m in range(60) if c.minute >> m & 1]
@@ -501,7 +562,7 @@ def classify(hc: HealthCheck) -> tuple[int, Record]:
                     return E_RANGE, Record()
                 kind, r.ras = KIND_CRON_EVERY, c.delay_sec
             else:
-                kind = KIND_CRON_SPEC
+                kind = KIND_CRON_SPEC | (c.tz_id << F_TZ_SHIFT)
                 r.minute, r.hour, r.dom, r.month, r.dow = c.masks()
     else:
         if not _i32(hc.repeat_after_sec):
@@ -631,7 +692,7 @@ def tick_record(r: Record, t: int, mode: int = 0, seed: int = 0, gidx: int = 0,
         # hcc.go:264: skipped iff elapsed < RepeatAfterSec AND a timer exists for the check
         due = not ((t - r.finished_at) < r.ras and bool(r.flags & F_TIMER_ARMED))
     elif kind == KIND_CRON_SPEC:
-        due = cron_matches(Cron(CRON_SPEC, r.minute, r.hour, r.dom, r.month, r.dow), t)
+        due = cron_matches(Cron(CRON_SPEC, r.minute, r.hour, r.dom, r.month, r.dow, tz_id=r.flags >> F_TZ_SHIFT), t)
     if due:
         act |= ACT_SUBMIT_HC
         if mode & MODE_CLOSED_LOOP:

@@ -18,6 +18,18 @@ def pytest_configure(config):
     # build in-tree artefacts once (no-op when up to date)
     build = importlib.import_module("active-monitor_b200.build")
     build.build_all()
+    # Time-zone ids are handed out in order of first appearance, per implementation: introduce the
+    # generator's zones first and in its order everywhere, so that flags columns (and the golden
+    # digests over them) do not depend on which test happened to parse which "CRON_TZ=" first.
+    import ctypes as C
+    import amgen
+    import oracle_c
+    import oracle_py
+    am = importlib.import_module("active-monitor_b200")
+    for z in amgen.ZONES:
+        i = C.c_int32()
+        assert am.tz_lookup(z) == oracle_py.tz_lookup(z)
+        assert oracle_c.load().orc_tz_lookup(z.encode(), len(z), C.byref(i)) == 0 and i.value == oracle_py.tz_lookup(z)
 
 
 @pytest.fixture(scope="session")
@@ -40,7 +52,10 @@ def orc():
 
 @pytest.fixture(scope="session")
 def opy():
+    import amgen
     import oracle_py
+    for z in amgen.ZONES:  # zone ids in the generator's order, as in the other implementations
+        oracle_py.tz_lookup(z)
     return oracle_py
 
 

@@ -20,6 +20,8 @@ import amgen  # noqa: E402
 import oracle_c  # noqa: E402
 import oracle_py  # noqa: E402
 
+for _z in amgen.ZONES:  # zone ids in the generator's order in every implementation
+    oracle_py.tz_lookup(_z)
 T0, T_OCT1 = 1789982100, 1790812800
 CASES = [  # name, config, seed, n, ticks [(T, mode)]
     ("config1_ras60", 1, 1, 1000, [(T0, 0)]),

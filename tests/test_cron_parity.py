@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 from hypothesis import given, settings, strategies as st
 
-from test_oracle_golden import (ACTIVATION, APPENDIX_C, EVERY, NEXT, REJECTED, T0, TOKENS, UNSUPPORTED,
+from test_oracle_golden import (ACTIVATION, APPENDIX_C, EVERY, NEXT, REJECTED, REJECTED_ZONES, T0, TOKENS, UNSUPPORTED,
                                 utc)
 
 
@@ -52,7 +52,7 @@ def test_TestRemedyWorkflow_IsEmpty(am):
     assert not am.remedy_is_empty("", True, 0, False)
 
 
-@pytest.mark.parametrize("spec", [s for s, _ in APPENDIX_C] + REJECTED + UNSUPPORTED + [s for s, _ in EVERY])
+@pytest.mark.parametrize("spec", [s for s, _ in APPENDIX_C] + REJECTED + REJECTED_ZONES + UNSUPPORTED + [s for s, _ in EVERY])
 def test_fixed_vectors_product_equals_oracle(am, orc, spec):
     o_rc, o, p_rc, p, _ = both(am, orc, spec)
     assert o_rc == p_rc, spec
@@ -169,7 +169,10 @@ def test_classify_domain_checks(am, orc):
         rc, _ = am.classify(**kw)
         assert rc == am.AM_E_RANGE, kw
     rc, rec = am.classify(cron="CRON_TZ=Europe/Paris 0 9 * * *")
-    assert rc == am.AM_E_UNSUPPORTED and rec["flags"][0] & 7 == am.KIND_HOST_FALLBACK
+    assert rc == 0 and rec["flags"][0] & 7 == am.KIND_CRON_SPEC
+    assert rec["flags"][0] >> am.F_TZ_SHIFT == am.tz_lookup("Europe/Paris") > 0
+    rc, rec = am.classify(cron="CRON_TZ=Nowhere/Land 0 9 * * *")  # time.LoadLocation fails: a parse error
+    assert rc == 0 and rec["flags"][0] & 7 == am.KIND_PARSE_ERROR
     rc, rec = am.classify(repeat_after_sec=-7, cron="")
     assert rc == 0 and rec["flags"][0] & 7 == am.KIND_STOPPED
     rc, rec = am.classify(repeat_after_sec=60, cron="NOT_A_VALID_CRON", has_remedy=True, fail_p8=77)

@@ -529,7 +529,7 @@ def test_repeat_after_sec_on_device_equals_oracle(am, orc, gen):
             want[iv] = prod["ras"][iv]
             for i in np.flatnonzero(kind == am.KIND_CRON_SPEC):
                 c = orc.OrcCron(int(prod["minute"][i]), int(prod["hour"][i]), int(prod["dom"][i]),
-                                int(prod["month"][i]), int(prod["dow"][i]), 0, 1, 0)
+                                int(prod["month"][i]), int(prod["dow"][i]), 0, 1, int(prod["flags"][i] >> 24))
                 want[i] = lib.orc_cron_repeat_after_sec(C.byref(c), T)
             np.testing.assert_array_equal(got, want, err_msg=f"T={T}")
             assert (got[kind == am.KIND_CRON_SPEC] != 0).all()

@@ -112,6 +112,11 @@ static const char* const BAD[] = {"NOT_A_VALID_CRON", "0 * * * * *", "60 * * * *
 static const char* const DESC[] = {"@hourly", "@daily", "@midnight", "@weekly", "@monthly",
                                    "@yearly", "@annually"};
 static const int RAS_CHOICES[] = {5, 10, 30, 60, 300, 900, 3600};
+static const char* const ZONES[] = {"America/New_York", "Europe/Paris", "Asia/Kolkata", "Asia/Kathmandu",
+                                    "Australia/Lord_Howe", "America/St_Johns"};
+static const char* const TZ_PREFIX[] = {"CRON_TZ=UTC ", "TZ=UTC ", "CRON_TZ=America/New_York ", "TZ=Europe/Paris ",
+                                        "CRON_TZ=Asia/Kolkata ", "CRON_TZ=Asia/Kathmandu ",
+                                        "TZ=Australia/Lord_Howe ", "CRON_TZ=America/St_Johns "};
 
 #define AMGEN_STR 128 /* bytes reserved per cron string */
 
@@ -156,7 +161,9 @@ void amgen_healthcheck(int config, uint64_t seed, uint64_t i, int64_t T0, am_hea
       strcpy(buf, DESC[below(&r, 7)]);
     } else {
       char* p = buf;
-      if (below(&r, 50) == 0) p += sprintf(p, "%s", below(&r, 2) ? "CRON_TZ=UTC " : "TZ=UTC ");
+      /* 2 % of the 5-field specs carry a time-zone prefix: UTC under both spellings and six named
+       * zones, among them half-hour, 45-minute and 30-minute-DST offsets (robfig: time.LoadLocation) */
+      if (below(&r, 50) == 0) p += sprintf(p, "%s", TZ_PREFIX[below(&r, 8)]);
       for (int f = 0; f < 5; f++) {
         if (f) { *p++ = ' '; if (below(&r, 40) == 0) *p++ = (below(&r, 2) ? '\t' : ' '); }
         p = put_field(p, &FD[f], &r);
@@ -267,6 +274,20 @@ int64_t amgen_fill(int config, uint64_t seed, uint64_t first, uint64_t n, int64_
                    amgen_classify_fn fn, const am_record_cols_t* cols, int nthreads) {
   if (nthreads < 1) nthreads = 1;
   if (nthreads > 256) nthreads = 256;
+  /* Zone ids are handed out in order of first appearance by whichever implementation sits behind
+   * `fn` (product or oracle): introduce the zones in a fixed order, single-threaded, before the
+   * threaded fill, so that the flags columns of two implementations are comparable. */
+  for (size_t z = 0; z < sizeof ZONES / sizeof ZONES[0]; z++) {
+    am_healthcheck_t hc;
+    am_record_t r;
+    char spec[AMGEN_STR];
+    memset(&hc, 0, sizeof hc);
+    snprintf(spec, sizeof spec, "CRON_TZ=%s * * * * *", ZONES[z]);
+    hc.has_resource = 1;
+    hc.cron = spec;
+    hc.cron_len = strlen(spec);
+    (void)fn(&hc, &r);
+  }
   job_t jobs[256];
   pthread_t th[256];
   uint64_t chunk = (n + (uint64_t)nthreads - 1) / (uint64_t)nthreads;

@@ -11,6 +11,10 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libamgen.so")
 
+# named time zones of the generated populations, in the order amgen_fill introduces them to the
+# implementation behind the classify function (zone ids are handed out in order of first appearance)
+ZONES = ("America/New_York", "Europe/Paris", "Asia/Kolkata", "Asia/Kathmandu", "Australia/Lord_Howe",
+         "America/St_Johns")
 T0_MON_0915 = 1789982100   # 2026-09-21 09:15:00 UTC, Monday  
 T0_OCT_1 = 1790812800      # 2026-10-01 00:00:00 UTC, Thursday (hour/day/month boundary)
 T0_DAY_START = 1789948800  # 2026-09-21 00:00:00 UTC           (config 5)
