@@ -377,23 +377,39 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   //         its next needy record with scalar accesses — the loop runs once or twice
   //         instead of four predicated copies of the state machine.
   if (__popc(__ballot_sync(kFull, needy != 0)) >= 16) {
+    // both halves' loads first (sixteen more in flight per lane: the mask registers are dead by now),
+    // then the state machines, then the stores — a half's stores would otherwise fence the other
+    // half's loads behind them (the compiler cannot tell the columns apart)
+    int2 lim[2], rst[2], sc[2], fc[2], rsc[2], rfc[2], rtc[2];
+    longlong2 rfa[2];
+    auto load_half = [&](int h) {
+      if ((needy >> (2 * h)) & 3u) {
+        const uint32_t r = r0[h];
+        lim[h] = ld_stream(reinterpret_cast<const int2*>(p.c.runs_limit + r));
+        rst[h] = ld_stream(reinterpret_cast<const int2*>(p.c.reset_interval + r));
+        sc[h] = ld_stream(reinterpret_cast<const int2*>(p.c.success + r));
+        fc[h] = ld_stream(reinterpret_cast<const int2*>(p.c.failed + r));
+        rsc[h] = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_success + r));
+        rfc[h] = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_failed + r));
+        rtc[h] = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_total + r));
+        rfa[h] = ld_stream(reinterpret_cast<const longlong2*>(p.c.remedy_finished_at + r));
+      }
+    };
+    if (MASKS) {  // (the variants without the mask columns run at 64 registers: one half at a time there)
+      load_half(0);
+      load_half(1);
+      __syncwarp();
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const uint32_t nb = (needy >> (2 * h)) & 3u;
+      if (!MASKS) load_half(h);
       if (nb) {
         const uint32_t r = r0[h];
-        const int2 lim = ld_stream(reinterpret_cast<const int2*>(p.c.runs_limit + r));
-        const int2 rst = ld_stream(reinterpret_cast<const int2*>(p.c.reset_interval + r));
-        const int2 sc = ld_stream(reinterpret_cast<const int2*>(p.c.success + r));
-        const int2 fc = ld_stream(reinterpret_cast<const int2*>(p.c.failed + r));
-        const int2 rsc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_success + r));
-        const int2 rfc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_failed + r));
-        const int2 rtc = ld_stream(reinterpret_cast<const int2*>(p.c.remedy_total + r));
-        const longlong2 rfa = ld_stream(reinterpret_cast<const longlong2*>(p.c.remedy_finished_at + r));
-        int32_t ns[2] = {sc.x, sc.y}, nf[2] = {fc.x, fc.y};
-        int32_t nrs[2] = {rsc.x, rsc.y}, nrf[2] = {rfc.x, rfc.y}, nrt[2] = {rtc.x, rtc.y};
-        int64_t nrfa[2] = {rfa.x, rfa.y};
-        const int32_t limv[2] = {lim.x, lim.y}, rstv[2] = {rst.x, rst.y};
+        int32_t ns[2] = {sc[h].x, sc[h].y}, nf[2] = {fc[h].x, fc[h].y};
+        int32_t nrs[2] = {rsc[h].x, rsc[h].y}, nrf[2] = {rfc[h].x, rfc[h].y}, nrt[2] = {rtc[h].x, rtc[h].y};
+        int64_t nrfa[2] = {rfa[h].x, rfa[h].y};
+        const int32_t limv[2] = {lim[h].x, lim[h].y}, rstv[2] = {rst[h].x, rst[h].y};
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           if ((nb >> j) & 1u) {
@@ -416,15 +432,15 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
           }
         }
         dirty[h] = true;  // a result always clears its PENDING flags
-        if (ns[0] != sc.x || ns[1] != sc.y) st_stream(reinterpret_cast<int2*>(p.c.success + r), make_int2(ns[0], ns[1]));
-        if (nf[0] != fc.x || nf[1] != fc.y) st_stream(reinterpret_cast<int2*>(p.c.failed + r), make_int2(nf[0], nf[1]));
-        if (nrs[0] != rsc.x || nrs[1] != rsc.y)
+        if (ns[0] != sc[h].x || ns[1] != sc[h].y) st_stream(reinterpret_cast<int2*>(p.c.success + r), make_int2(ns[0], ns[1]));
+        if (nf[0] != fc[h].x || nf[1] != fc[h].y) st_stream(reinterpret_cast<int2*>(p.c.failed + r), make_int2(nf[0], nf[1]));
+        if (nrs[0] != rsc[h].x || nrs[1] != rsc[h].y)
           st_stream(reinterpret_cast<int2*>(p.c.remedy_success + r), make_int2(nrs[0], nrs[1]));
-        if (nrf[0] != rfc.x || nrf[1] != rfc.y)
+        if (nrf[0] != rfc[h].x || nrf[1] != rfc[h].y)
           st_stream(reinterpret_cast<int2*>(p.c.remedy_failed + r), make_int2(nrf[0], nrf[1]));
-        if (nrt[0] != rtc.x || nrt[1] != rtc.y)
+        if (nrt[0] != rtc[h].x || nrt[1] != rtc[h].y)
           st_stream(reinterpret_cast<int2*>(p.c.remedy_total + r), make_int2(nrt[0], nrt[1]));
-        if (nrfa[0] != rfa.x || nrfa[1] != rfa.y)
+        if (nrfa[0] != rfa[h].x || nrfa[1] != rfa[h].y)
           st_stream(reinterpret_cast<longlong2*>(p.c.remedy_finished_at + r), make_longlong2(nrfa[0], nrfa[1]));
       }
     }
