@@ -124,6 +124,7 @@ SYMBOLS = {
     "am_cron_repeat_after_sec": (i64, [P(AmCron), i64]),
     "am_healthcheck_classify": (C.c_int, [P(AmHealthCheck), P(AmRecord)]),
     "am_healthcheck_classify_batch": (C.c_int, [C.c_void_p, u64, C.c_void_p, C.c_void_p, C.c_int, P(u64)]),
+    "am_healthcheck_ingest_json": (C.c_int, [C.c_char_p, C.c_size_t, u32, C.c_void_p, C.c_void_p, u64, P(u64), C.c_int]),
     "am_remedy_is_empty": (C.c_int, [C.c_size_t, C.c_int, i64, C.c_int]),
     "am_sweep_create": (C.c_int, [P(C.c_void_p), C.c_int, u64, u64]),
     "am_sweep_destroy": (None, [C.c_void_p]),

@@ -110,3 +110,23 @@ def classify_batch(items, n_threads: int = 0):
     assert int(bad.value) == int(np.count_nonzero(rcs))
     del keep
     return rcs, recs
+
+
+def ingest_json(text, n_threads: int = 0, timer_armed: bool = True):
+    """`am_healthcheck_ingest_json`: a JSON document (one HealthCheck, an array, or a List with
+    "items") -> (rc array int32[n], records RECORD_DTYPE[n]).  Field extraction and the ladder both
+    run natively, on `n_threads` host threads (0 = all)."""
+    raw = text if isinstance(text, (bytes, bytearray)) else text.encode("utf-8")
+    lib = L.load()
+    n = L.u64(0)
+    rc = lib.am_healthcheck_ingest_json(raw, len(raw), int(bool(timer_armed)), None, None, 0, C.byref(n), n_threads)
+    if rc not in (L.AM_OK, L.AM_E_NOSPACE):
+        raise AmError(rc, "am_healthcheck_ingest_json")
+    recs = np.zeros(n.value, dtype=L.RECORD_DTYPE)
+    rcs = np.zeros(n.value, dtype=np.int32)
+    if n.value:
+        rc = lib.am_healthcheck_ingest_json(raw, len(raw), int(bool(timer_armed)), recs.ctypes.data, rcs.ctypes.data,
+                                            n.value, C.byref(n), n_threads)
+        if rc != L.AM_OK:
+            raise AmError(rc, "am_healthcheck_ingest_json")
+    return rcs, recs

@@ -542,6 +542,8 @@ def main():
         changed = n_res * 16 + (stats["n_remedy_ok"] + stats["n_remedy_fail"]) * 16  # flags+fa+S|F, RS|RF+RT+rfa
         alg_bytes = int(n * B_READ + n_res * B_READ_REMEDY + changed + n * B_BITMAP + n_exc * B_EXC)
         model = "N*56 + results*36 + results*16 + remedy_results*16 + N/8 (bitmap) + exceptions*4"
+        # SURVEY 8(d) literal: every record of config 3 reads 92 B, up to 36 B written per transitioned record
+        survey_bytes = int(n * (B_READ + B_READ_REMEDY) + n_res * B_READ_REMEDY + n * B_BITMAP + n_exc * B_EXC)
     else:
         alg_bytes = int(n * B_READ + n * B_BITMAP + n_exc * B_EXC + stats["n_stopped"] * B_STOP)
         model = f"N*{B_READ} + N/8 (bitmap) + exceptions*{B_EXC} + stopped*{B_STOP}"
@@ -683,6 +685,9 @@ def main():
                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "kernel": "sweep_tick_kernel<false,true>", "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes,
                     "bytes_model": model,
+                    **({"survey_bytes": survey_bytes, "survey_model": "SURVEY 8(d) literal: N*92 + transitioned*36 "
+                        "+ N/8 + exceptions*4", "survey_frac": survey_bytes / (k_ms * 1e-3) / 1e9 / peak}
+                       if config == 3 else {}),
                     "rest_of_tick": {"kernels": "scan_groups_kernel + expand_kernel + publish_kernel", "ms": c_ms,
                                      "bytes": int(n * B_BITMAP + stats["n_emitted"] * 5)},
                     "kernel_share_of_step": k_ms / (ms / args.steps),

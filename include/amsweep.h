@@ -181,6 +181,17 @@ int am_healthcheck_classify(const am_healthcheck_t* hc, am_record_t* out);
 int am_healthcheck_classify_batch(const am_healthcheck_t* hcs, uint64_t n, am_record_t* out,
                                   int32_t* rc_out, int n_threads, uint64_t* n_not_ok);
 
+/* HealthCheck manifests as the API server serves them (JSON: one object, an array of objects, or a
+ * List with "items") -> packed records, natively: one structural pass, then field extraction by the
+ * JSON tags of api/v1alpha1/healthcheck_types.go:32-66 / :88-102 and the ladder, split over n_threads
+ * host threads (<= 0: all).  For the informer's initial list at controller start (hcc.go:170) and for
+ * restores from a dump.  `timer_armed` is applied to every record (0 after a restart, hcc.go:161).
+ * out / rc_out (may be NULL) hold `cap` entries; *n_out = HealthChecks found; AM_E_NOSPACE when
+ * cap is too small (nothing written), AM_E_PARSE when the document is not JSON of that shape.
+ * rc_out[i]: what am_healthcheck_classify returned, or AM_E_PARSE for a malformed object / time. */
+int am_healthcheck_ingest_json(const char* json, size_t len, uint32_t timer_armed, am_record_t* out,
+                               int32_t* rc_out, uint64_t cap, uint64_t* n_out, int n_threads);
+
 /* RemedyWorkflow.IsEmpty (api/v1alpha1/healthcheck_types.go:104-106):
  * reflect.DeepEqual against the zero value — note a non-nil empty rbacRules
  * slice is NOT empty. */
