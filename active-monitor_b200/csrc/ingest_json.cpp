@@ -265,40 +265,55 @@ extern "C" int am_healthcheck_ingest_json(const char* json, size_t len, uint32_t
   if (!json || !n_out || (cap && !out)) return AM_E_INVAL;
   *n_out = 0;
   // 1. spans of the HealthCheck objects: the document itself, the elements of a top-level array, or
-  //    the elements of the "items" array of a List object
+  //    the elements of the "items" array of a List object.  One flat pass over the bytes (depth, in-string
+  //    and escape state only): this is the serial part, everything else runs on all threads.
   std::vector<std::pair<const char*, const char*>> spans;
-  Cur c{json, json + len};
-  auto array_items = [&](Cur& c) {
-    if (!c.eat('[')) { c.ok = false; return; }
-    if (c.eat(']')) return;
-    while (c.ok) {
-      c.ws();
-      const char* s = c.p;
-      skip_value(c);
-      if (*s == '{') spans.emplace_back(s, c.p);
-      if (c.eat(',')) continue;
-      if (c.eat(']')) return;
-      c.ok = false;
+  {
+    const char* p = json;
+    const char* const e = json + len;
+    while (p < e && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p;
+    if (p >= e || (*p != '[' && *p != '{')) return AM_E_PARSE;
+    const bool top_array = *p == '[';
+    int depth = 0;            // counts both {} and []
+    int items_depth = top_array ? 1 : -1;  // depth INSIDE the array that holds the HealthChecks
+    const char* item_start = nullptr;
+    const char* key_start = nullptr;       // last string token seen at depth 1 of a top-level object
+    size_t key_len = 0;
+    bool expect_items_array = false;
+    const char* doc_start = p;
+    for (; p < e; ++p) {
+      const char ch = *p;
+      if (ch == '"') {  // skip the string
+        const char* s = p + 1;
+        ++p;
+        while (p < e && *p != '"') { if (*p == '\\') ++p; ++p; }
+        if (p >= e) return AM_E_PARSE;
+        if (!top_array && depth == 1 && items_depth < 0) { key_start = s; key_len = (size_t)(p - s); }
+        continue;
+      }
+      if (ch == ':' && !top_array && depth == 1 && items_depth < 0) {
+        expect_items_array = key_len == 5 && memcmp(key_start, "items", 5) == 0;
+        continue;
+      }
+      if (ch == '{' || ch == '[') {
+        if (expect_items_array && depth == 1) {
+          if (ch == '[') items_depth = 2;
+          expect_items_array = false;
+        }
+        if (ch == '{' && depth == items_depth) item_start = p;
+        ++depth;
+      } else if (ch == '}' || ch == ']') {
+        --depth;
+        if (depth < 0) return AM_E_PARSE;
+        if (ch == '}' && depth == items_depth && item_start) { spans.emplace_back(item_start, p + 1); item_start = nullptr; }
+        if (depth == 0) { ++p; break; }
+      } else if (ch != ' ' && ch != '\n' && ch != '\t' && ch != '\r' && ch != ',') {
+        expect_items_array = false;  // a scalar value after "items": not a List
+      }
     }
-  };
-  const char first = c.peek();
-  if (first == '[') array_items(c);
-  else if (first == '{') {
-    // a List? look for a top-level "items" array without committing to it
-    Cur probe = c;
-    bool is_list = false;
-    for_members(probe, [&](const std::string& k, Cur& q) {
-      if (k == "items" && q.peek() == '[') { is_list = true; array_items(q); }
-      else skip_value(q);
-    });
-    if (!probe.ok) return AM_E_PARSE;
-    if (!is_list) {
-      const char* s = c.p;
-      skip_value(c);
-      spans.emplace_back(s, c.p);
-    }
-  } else return AM_E_PARSE;
-  if (!c.ok) return AM_E_PARSE;
+    if (depth != 0) return AM_E_PARSE;
+    if (!top_array && items_depth < 0) spans.emplace_back(doc_start, p);  // a single HealthCheck object
+  }
   const uint64_t n = spans.size();
   *n_out = n;
   if (n > cap) return AM_E_NOSPACE;
