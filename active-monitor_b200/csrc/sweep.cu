@@ -25,6 +25,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <new>
 #include <string>
@@ -92,6 +93,10 @@ struct Staging {
   size_t n_ops = 0, n_recs = 0;
   size_t flushed_ops = 0, flushed_recs = 0;  // already enqueued for copy to the device twins
   uint32_t n_state = 0, n_result = 0;
+  // am_sweep_post_result calls that have reserved a range of the op arrays and are filling it
+  // OUTSIDE the lock (the controller's workers post concurrently, hcc.go:170-188): while there are
+  // any, the arrays may not move, nothing past `flushed_ops` is known complete, and the drain waits
+  int writers = 0;
   uint64_t hwm = 0;                          // highest upserted slot + 1
   cudaEvent_t copied = nullptr;              // the last copy out of the pinned arrays
   bool copy_pending = false;
@@ -139,6 +144,7 @@ struct am_sweep {
   cudaEvent_t evp[3] = {nullptr, nullptr, nullptr};  // profiling: before sweep, after sweep, after publish
   bool profiling = false, profiled = false;
   std::mutex mu;  // guards the staging areas
+  std::condition_variable cv;  // a staging area's `writers` dropped to zero
   std::atomic_flag ticking = ATOMIC_FLAG_INIT;
   Staging stage[2];
   int cur = 0;                // the staging area callers append to
@@ -232,16 +238,19 @@ cudaError_t grow_pinned(am_sweep* h, PinnedBuf& b, size_t used_bytes, size_t wan
 // Enqueue the not-yet-copied part of a staging area on the copy stream, if the device
 // twins are large enough (they are grown at drain time only).  Called under h->mu by the
 // posting threads (chunk threshold) and by the drain (everything).
-cudaError_t flush_staging(am_sweep* h, Staging& st, bool all) {
-  const size_t pend = st.n_ops - st.flushed_ops;
-  if (pend && (all || pend >= kFlushOps) && st.d_idx.cap >= st.n_ops * 4 && st.d_arg.cap >= st.n_ops * 4) {
+cudaError_t flush_staging(am_sweep* h, Staging& st, bool all, size_t upto = SIZE_MAX) {
+  // ops: everything below `upto` is complete.  Without an explicit bound that is all of them, unless
+  // posting calls are still filling reserved ranges (the last of them flushes when it is done).
+  if (upto == SIZE_MAX) upto = st.writers ? st.flushed_ops : st.n_ops;
+  const size_t pend = upto > st.flushed_ops ? upto - st.flushed_ops : 0;
+  if (pend && (all || pend >= kFlushOps) && st.d_idx.cap >= upto * 4 && st.d_arg.cap >= upto * 4) {
     cudaError_t e = cudaMemcpyAsync((uint32_t*)st.d_idx.p + st.flushed_ops, (const uint32_t*)st.idx.p + st.flushed_ops,
                                     pend * 4, cudaMemcpyHostToDevice, h->cstream);
     if (e != cudaSuccess) return e;
     e = cudaMemcpyAsync((uint32_t*)st.d_arg.p + st.flushed_ops, (const uint32_t*)st.arg.p + st.flushed_ops, pend * 4,
                         cudaMemcpyHostToDevice, h->cstream);
     if (e != cudaSuccess) return e;
-    st.flushed_ops = st.n_ops;
+    st.flushed_ops = upto;
     st.copy_pending = true;
   }
   const size_t pr = st.n_recs - st.flushed_recs;
@@ -256,13 +265,35 @@ cudaError_t flush_staging(am_sweep* h, Staging& st, bool all) {
   return cudaSuccess;
 }
 
+// Make room for `n` more staged ops (and `nrec` more upsert records) in the current staging area;
+// called with h->mu held through `lk`.  The pinned arrays move when they grow: calls that are
+// still filling a reserved range outside the lock are waited for first.
+int reserve_staging(am_sweep* h, std::unique_lock<std::mutex>& lk, size_t n, size_t nrec, Staging** out) {
+  for (;;) {
+    Staging& st = h->stage[h->cur];
+    if (st.n_ops + n > 0x3FFFFFF0ull || st.n_recs + nrec > 0x3FFFFFF0ull) return AM_E_NOSPACE;
+    const size_t want = (st.n_ops + n) * 4, want_r = (st.n_recs + nrec) * sizeof(am_record_t);
+    if (st.idx.cap < want || st.arg.cap < want || (nrec && st.recs.cap < want_r)) {
+      if (st.writers) { h->cv.wait(lk); continue; }  // (the drain may have swapped the areas meanwhile)
+      AM_CUDA(h, cudaSetDevice(h->device));
+      const bool inflight = st.flushed_ops || st.flushed_recs || st.copy_pending;
+      AM_CUDA(h, grow_pinned(h, st.idx, st.n_ops * 4, want, inflight));
+      AM_CUDA(h, grow_pinned(h, st.arg, st.n_ops * 4, want, inflight));
+      if (nrec) AM_CUDA(h, grow_pinned(h, st.recs, st.n_recs * sizeof(am_record_t), want_r, inflight));
+    }
+    *out = &st;
+    return AM_OK;
+  }
+}
+
 // Apply staged upserts / removes / results on stream `s` (called with the tick guard held).
 // The staging lock is held only for the buffer swap.
 int drain_staged(am_sweep* h, cudaStream_t s) {
   Staging* st;
   {
-    std::lock_guard<std::mutex> lk(h->mu);
+    std::unique_lock<std::mutex> lk(h->mu);
     st = &h->stage[h->cur];
+    h->cv.wait(lk, [&] { return st->writers == 0; });  // posting calls still filling their ranges
     if (st->n_ops == 0) return AM_OK;
     // callers are about to append to the other area: its previous copies must have left it
     Staging& nx = h->stage[h->cur ^ 1];
@@ -705,14 +736,11 @@ int am_sweep_load_range(am_sweep_t* h, uint64_t first, uint64_t n, const am_reco
 int am_sweep_upsert(am_sweep_t* h, uint64_t n, const uint64_t* idx, const am_record_t* recs) {
   if (!h || (n && (!idx || !recs))) return AM_E_INVAL;
   if (n == 0) return AM_OK;
-  std::lock_guard<std::mutex> lk(h->mu);
-  Staging& st = h->stage[h->cur];
-  if (st.n_ops + n > 0x3FFFFFF0ull || st.n_recs + n > 0x3FFFFFF0ull) return AM_E_NOSPACE;
+  std::unique_lock<std::mutex> lk(h->mu);
+  Staging* stp = nullptr;
+  if (int rc = reserve_staging(h, lk, n, n, &stp)) return rc;
+  Staging& st = *stp;
   AM_CUDA(h, cudaSetDevice(h->device));
-  const bool inflight = st.flushed_ops || st.flushed_recs;
-  AM_CUDA(h, grow_pinned(h, st.idx, st.n_ops * 4, (st.n_ops + n) * 4, inflight));
-  AM_CUDA(h, grow_pinned(h, st.arg, st.n_ops * 4, (st.n_ops + n) * 4, inflight));
-  AM_CUDA(h, grow_pinned(h, st.recs, st.n_recs * sizeof(am_record_t), (st.n_recs + n) * sizeof(am_record_t), inflight));
   uint32_t* oi = (uint32_t*)st.idx.p + st.n_ops;
   uint32_t* oa = (uint32_t*)st.arg.p + st.n_ops;
   // nothing is committed (counters unchanged) when a slot is out of range
@@ -736,13 +764,11 @@ int am_sweep_upsert(am_sweep_t* h, uint64_t n, const uint64_t* idx, const am_rec
 int am_sweep_remove(am_sweep_t* h, uint64_t n, const uint64_t* idx) {
   if (!h || (n && !idx)) return AM_E_INVAL;
   if (n == 0) return AM_OK;
-  std::lock_guard<std::mutex> lk(h->mu);
-  Staging& st = h->stage[h->cur];
-  if (st.n_ops + n > 0x3FFFFFF0ull) return AM_E_NOSPACE;
+  std::unique_lock<std::mutex> lk(h->mu);
+  Staging* stp = nullptr;
+  if (int rc = reserve_staging(h, lk, n, 0, &stp)) return rc;
+  Staging& st = *stp;
   AM_CUDA(h, cudaSetDevice(h->device));
-  const bool inflight = st.flushed_ops || st.flushed_recs;
-  AM_CUDA(h, grow_pinned(h, st.idx, st.n_ops * 4, (st.n_ops + n) * 4, inflight));
-  AM_CUDA(h, grow_pinned(h, st.arg, st.n_ops * 4, (st.n_ops + n) * 4, inflight));
   uint32_t* oi = (uint32_t*)st.idx.p + st.n_ops;
   uint32_t* oa = (uint32_t*)st.arg.p + st.n_ops;
   if (amsweep_host::stage_slots(n, idx, h->capacity, oi)) return AM_E_RANGE;
@@ -757,22 +783,47 @@ int am_sweep_post_result(am_sweep_t* h, uint64_t n, const uint64_t* idx, const u
                          const uint8_t* remedy_phase) {
   if (!h || (n && (!idx || !phase))) return AM_E_INVAL;
   if (n == 0) return AM_OK;
-  std::lock_guard<std::mutex> lk(h->mu);
-  Staging& st = h->stage[h->cur];
-  if (st.n_ops + n > 0x3FFFFFF0ull) return AM_E_NOSPACE;
-  AM_CUDA(h, cudaSetDevice(h->device));
-  const bool inflight = st.flushed_ops || st.flushed_recs;
-  AM_CUDA(h, grow_pinned(h, st.idx, st.n_ops * 4, (st.n_ops + n) * 4, inflight));
-  AM_CUDA(h, grow_pinned(h, st.arg, st.n_ops * 4, (st.n_ops + n) * 4, inflight));
-  // one vectorised pass: validate and stage; nothing is committed (n_ops unchanged) on a bad entry.
-  // phase -> flag bits: {none, Succeeded, Failed} -> {0, PENDING_OK, PENDING_FAIL}
-  const unsigned bad = amsweep_host::stage_results(n, idx, phase, remedy_phase, h->capacity, kOpResult,
-                                                   (uint32_t*)st.idx.p + st.n_ops, (uint32_t*)st.arg.p + st.n_ops);
-  if (bad & 1u) return AM_E_RANGE;
-  if (bad & 2u) return AM_E_INVAL;
+  // Reserve a range of the op arrays under the lock, fill it outside: the controller's workers
+  // (hcc.go:170-188) post concurrently and the per-entry pass is the cost of a post.  Per slot the
+  // call order is the reservation order.
+  std::unique_lock<std::mutex> lk(h->mu);
+  Staging* stp = nullptr;
+  if (int rc = reserve_staging(h, lk, n, 0, &stp)) return rc;
+  Staging& st = *stp;
+  const size_t a = st.n_ops;
   st.n_ops += n;
   st.n_result += (uint32_t)n;
-  AM_CUDA(h, flush_staging(h, st, false));
+  ++st.writers;  // the drain and any growth of the arrays now wait for this call
+  uint32_t* const oi = (uint32_t*)st.idx.p + a;
+  uint32_t* const oa = (uint32_t*)st.arg.p + a;
+  lk.unlock();
+  // validate and stage in vectorised passes of one copy chunk each; a single large post hands every
+  // finished chunk to the copy stream before staging the next (when no other call is staging).
+  // phase -> flag bits: {none, Succeeded, Failed} -> {0, PENDING_OK, PENDING_FAIL}
+  unsigned bad = 0;
+  cudaError_t ce = cudaSuccess;
+  for (uint64_t off = 0; off < n && !bad; off += kFlushOps) {
+    const uint64_t m = n - off < kFlushOps ? n - off : kFlushOps;
+    bad = amsweep_host::stage_results(m, idx + off, phase + off, remedy_phase ? remedy_phase + off : nullptr, h->capacity,
+                                      kOpResult, oi + off, oa + off);
+    if (!bad && off + m < n) {
+      lk.lock();
+      if (st.writers == 1 && ce == cudaSuccess && cudaSetDevice(h->device) == cudaSuccess)
+        ce = flush_staging(h, st, false, a + off + m);  // everything below is complete: this call is the only one staging
+      lk.unlock();
+    }
+  }
+  // nothing of a call with a bad entry takes effect: its range is already part of the sequence (later
+  // calls may have reserved behind it), so it becomes ops that mark and set nothing
+  if (bad)
+    for (uint64_t k = 0; k < n; ++k) { oi[k] = 0; oa[k] = kOpResult; }
+  lk.lock();
+  if (--st.writers == 0) {
+    if (ce == cudaSuccess && (ce = cudaSetDevice(h->device)) == cudaSuccess) ce = flush_staging(h, st, false);
+    h->cv.notify_all();
+  }
+  if (bad) return (bad & 1u) ? AM_E_RANGE : AM_E_INVAL;
+  AM_CUDA(h, ce);
   return AM_OK;
 }
 

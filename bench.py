@@ -215,6 +215,8 @@ def main():
                     "(spell it --records-per-gpu under torchrun: its parser rejects the abbreviation-like --n)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-workers", type=int, default=4, help="consumer threads of the e2e loop (walk the tick's "
+                    "list and post results back; the reference's reconcile workers, hcc.go:170-188)")
     ap.add_argument("--no-verify", action="store_true", help="N>1: skip the oracle check of the gathered list")
     ap.add_argument("--gather", default="exchange", choices=["exchange", "plain", "nccl"],
                     help="N>1: NVLink tick exchange (bitmap + exceptions, list rebuilt on every GPU), the round-1 "
@@ -568,7 +570,7 @@ def main():
         if h_part is None:
             # N=1: the loop itself is compiled code calling the C-ABI, as the cgo shim is — ctypes and
             # numpy plumbing per call would otherwise be a tenth of the step
-            c_loop = amgen.e2e_closed_loop(lib, sweep._h, T0, am.SWEEP_FULL_SCAN, 8, reps, n)
+            c_loop = amgen.e2e_closed_loop(lib, sweep._h, T0, am.SWEEP_FULL_SCAN, 8, reps, n, workers=args.e2e_workers)
             dt, h2d, d2h = c_loop["seconds"], c_loop["h2d_bytes"], c_loop["d2h_bytes"]
         for phase_name in (() if c_loop else ("warm", "timed")):
             if phase_name == "timed":
@@ -613,10 +615,15 @@ def main():
             dt = float(t.item())
         e2e = {"value": n * world * reps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d // reps,
                "d2h_bytes_per_step": d2h // reps, "ms_per_step": dt / reps * 1e3, "steps": reps,
-               "split_ms_per_step": None if not c_loop else {"post_result": c_loop["post_s"] / reps * 1e3,
-                                                              "tick_view": c_loop["tick_s"] / reps * 1e3,
-                                                              "walk_list": c_loop["walk_s"] / reps * 1e3},
-               "driver": "compiled loop calling the C-ABI (tools/amgen/amgen.c amgen_e2e_closed_loop)" if c_loop
+               "split_ms_per_step": None if not c_loop else {
+                   "tick_view": c_loop["tick_s"] / reps * 1e3,
+                   "consumer_wall": c_loop["consumer_s"] / reps * 1e3,
+                   "post_result_per_worker": c_loop["post_s"] / reps * 1e3,
+                   "walk_list_per_worker": c_loop["walk_s"] / reps * 1e3},
+               "consumer_workers": c_loop["workers"] if c_loop else 1,
+               "driver": ("compiled loop calling the C-ABI (tools/amgen/amgen.c amgen_e2e_closed_loop): tick on one thread, "
+                          "then the list walked in pieces and posted back by the consumer workers (the controller's "
+                          "reconcile workers, hcc.go:170-188)") if c_loop
                          else "python loop (ctypes + torch)",
                "api": ("am_sweep_post_result + am_sweep_tick_view (the GPU writes the list into the library's pinned "
                        "host buffer)" if h_part is None else

@@ -196,3 +196,53 @@ def test_repeat_after_sec_kernel_equals_oracle(am, orc, gen):
                                 int(prod["month"][i]), int(prod["dow"][i]), 0, 1, int(prod["flags"][i] >> 24))
                 want[i] = lib.orc_cron_repeat_after_sec(C.byref(c), T)
             np.testing.assert_array_equal(got, want, err_msg=f"T={T}")
+
+
+@pytest.mark.parametrize("workers", [1, 3])
+def test_compiled_e2e_loop_equals_the_oracle_loop(am, orc, gen, monkeypatch, workers):
+    """bench.py's e2e driver (tools/amgen amgen_e2e_closed_loop: tick_view, then walk the list in pieces
+    and post every submitted check as Succeeded) on the emulated library = the same loop on the oracle:
+    counts of the last tick and every column afterwards."""
+    n, steps = 60_000, 6
+    monkeypatch.setenv("AMGEN_E2E_PIECE", "300")  # several pieces per tick at this size
+    prod, orac = _gen_pair(gen, am, orc, 2, 5, n, T0)
+    with emu_sweep.EmuSweep(n) as s:
+        s.load_range(0, prod)
+        got = gen.e2e_closed_loop(emu_sweep.load(), s._h, T0, am.SWEEP_FULL_SCAN, 2, steps - 2, n, workers=workers)
+        for k in range(steps):
+            idx, act, st = orc.sweep(orac, T0 + k, am.SWEEP_FULL_SCAN)
+            sub = idx[(act & am.ACT_SUBMIT_HC) != 0]
+            orac["flags"][sub] |= am.F_PENDING_OK
+        assert (got["last_emitted"], got["last_submitted"]) == (len(idx), len(sub))
+        assert len(idx) > 900  # four pieces and more
+        assert got["h2d_bytes"] > 0 and got["d2h_bytes"] > 0 and got["workers"] == workers
+        dev = s.read_range(0, n)  # (drains the last piece's posts, as the oracle's flags hold them)
+        for name in am.COLUMN_NAMES:
+            np.testing.assert_array_equal(dev[name], orac[name], err_msg=f"column {name}")
+
+
+def test_large_post_is_chunked_and_a_bad_entry_commits_nothing(am, orc, gen):
+    """am_sweep_post_result stages a large batch one copy chunk (32768 ops) at a time, handing each to the
+    copy stream; an out-of-range slot or a bad phase in a LATER chunk must leave nothing of the call
+    behind (the chunks already handed over are rolled back), and the next valid post must land."""
+    n = 90_000
+    prod, orac = _gen_pair(gen, am, orc, 2, 9, n, T0)
+    slots = np.arange(0, n, dtype=np.uint64)[:80_000]
+    with emu_sweep.EmuSweep(n) as s:
+        s.load_range(0, prod)
+        bad = slots.copy()
+        bad[70_000] = n + 5
+        with pytest.raises(am.AmError) as e:
+            s.post_result(bad, np.full(len(bad), am.PHASE_FAILED, np.uint8))
+        assert e.value.code == am.AM_E_RANGE
+        ph = np.full(len(slots), am.PHASE_SUCCEEDED, np.uint8)
+        ph[40_000] = 7
+        with pytest.raises(am.AmError) as e:
+            s.post_result(slots, ph)
+        assert e.value.code == am.AM_E_INVAL
+        _assert_tick_equal(am, s.tick(T0), orc.sweep(orac, T0), s, orac, n, "after two rejected posts")
+        ph = np.where(slots % 3 == 0, am.PHASE_FAILED, am.PHASE_SUCCEEDED).astype(np.uint8)
+        s.post_result(slots, ph)
+        live = slots.astype(np.int64)
+        orac["flags"][live] |= np.where(ph == am.PHASE_FAILED, am.F_PENDING_FAIL, am.F_PENDING_OK).astype(np.uint32)
+        _assert_tick_equal(am, s.tick(T0 + 1), orc.sweep(orac, T0 + 1), s, orac, n, "after a chunked post")

@@ -19,6 +19,7 @@
  */
 #define _GNU_SOURCE
 #include <pthread.h>
+#include <stdatomic.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -361,11 +362,14 @@ uint64_t amgen_select_submitted_view(const uint32_t* idx_local, const uint8_t* a
 
 /* The host-closed loop of bench.py's e2e measurement, as the cgo shim would run it: compiled code
  * calling the C-ABI through function pointers (the harness does not link libamsweep).  Per step:
- * post every check the previous tick submitted as Succeeded (am_sweep_post_result, host memory ->
- * device), tick at the next second (am_sweep_tick_view: the GPU writes the list into the library's
- * pinned host buffer), walk the list for the next step's slots (hcc.go:269-288 stand-in).
- * Times `steps` steps after `warm` untimed ones with CLOCK_MONOTONIC; split[0..3) accumulates the
- * seconds spent in post / tick / walk.  Returns 0 or the first failing return code. */
+ * tick at the next second (am_sweep_tick_view: the GPU writes the list into the library's pinned
+ * host buffer); then the consumer side — `workers` threads, the controller's reconcile workers
+ * (hcc.go:170-188, MaxConcurrentReconciles) — walks the list in pieces (hcc.go:269-288 stand-in),
+ * each thread posting every submitted check of its piece as Succeeded (am_sweep_post_result, host
+ * memory -> device) before the next tick.  Workers are persistent and spin between ticks.
+ * Times `steps` steps after `warm` untimed ones with CLOCK_MONOTONIC; split[0..4) accumulates the
+ * seconds in post (mean over workers) / tick / walk (mean over workers) / the whole consumer phase
+ * (wall).  Returns 0 or the first failing return code. */
 typedef int (*am_post_fn)(void*, uint64_t, const uint64_t*, const uint8_t*, const uint8_t*);
 typedef int (*am_tick_view_fn)(void*, int64_t, uint32_t, am_tick_view_t*, am_tick_stats_t*);
 static double mono_s(void) {
@@ -373,36 +377,122 @@ static double mono_s(void) {
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
+#define E2E_PIECE 32768u
+#define E2E_MAX_WORKERS 16
+typedef struct {
+  am_post_fn post;
+  void* handle;
+  const uint8_t* ok_phase;
+  uint64_t* slots; /* workers x piece scratch */
+  uint64_t piece;
+  int workers;
+  /* the tick's job */
+  const uint32_t* idx;
+  const uint8_t* act;
+  uint64_t n;
+  atomic_ullong next_piece, submitted, gen;
+  atomic_int done, rc, quit;
+  double post_s[E2E_MAX_WORKERS], walk_s[E2E_MAX_WORKERS];
+} e2e_pool_t;
+typedef struct { e2e_pool_t* pool; int w; } e2e_arg_t;
+
+static void e2e_consume(e2e_pool_t* P, int w) {
+  uint64_t* scratch = P->slots + (uint64_t)w * P->piece;
+  uint64_t sub = 0;
+  double walk = 0, post_s = 0;
+  for (;;) {
+    const uint64_t off = atomic_fetch_add_explicit(&P->next_piece, 1, memory_order_relaxed) * P->piece;
+    if (off >= P->n) break;
+    const uint64_t len = P->n - off < P->piece ? P->n - off : P->piece;
+    const double w0 = mono_s();
+    const uint64_t m = amgen_select_submitted_view(P->idx + off, P->act + off, len, scratch);
+    const double w1 = mono_s();
+    if (m) {
+      const int rp = P->post(P->handle, m, scratch, P->ok_phase, NULL);
+      if (rp) atomic_store(&P->rc, rp);
+    }
+    const double w2 = mono_s();
+    walk += w1 - w0; post_s += w2 - w1;
+    sub += m;
+  }
+  P->walk_s[w] += walk; P->post_s[w] += post_s;
+  atomic_fetch_add_explicit(&P->submitted, sub, memory_order_relaxed);
+}
+static void* e2e_worker(void* arg) {
+  e2e_pool_t* P = ((e2e_arg_t*)arg)->pool;
+  const int w = ((e2e_arg_t*)arg)->w;
+  unsigned long long seen = 0;
+  for (;;) {
+    unsigned long long g;
+    while ((g = atomic_load_explicit(&P->gen, memory_order_acquire)) == seen) {
+      if (atomic_load_explicit(&P->quit, memory_order_relaxed)) return NULL;
+      __builtin_ia32_pause();
+    }
+    seen = g;
+    e2e_consume(P, w);
+    atomic_fetch_add_explicit(&P->done, 1, memory_order_release);
+  }
+}
+
 int amgen_e2e_closed_loop(am_post_fn post, am_tick_view_fn tick, void* handle, int64_t T_first, uint32_t mode,
-                          uint64_t warm, uint64_t steps, uint64_t* slots /* capacity entries */,
-                          const uint8_t* ok_phase /* capacity x AM_PHASE_SUCCEEDED */, double* seconds,
-                          double* split, uint64_t* h2d_bytes, uint64_t* d2h_bytes, uint64_t* last_emitted,
+                          uint64_t warm, uint64_t steps, uint64_t* slots /* capacity entries */, uint64_t capacity,
+                          const uint8_t* ok_phase /* capacity x AM_PHASE_SUCCEEDED */, int workers, double* seconds,
+                          double* split /* [4] */, uint64_t* h2d_bytes, uint64_t* d2h_bytes, uint64_t* last_emitted,
                           uint64_t* last_submitted) {
   uint64_t n_prev = 0, h2d = 0, d2h = 0;
-  double t0 = 0, sp[3] = {0, 0, 0};
+  double t0 = 0, sp_tick = 0, sp_cons = 0;
   am_tick_view_t v;
   am_tick_stats_t st;
   memset(&v, 0, sizeof v);
-  for (uint64_t k = 0; k < warm + steps; k++) {
-    if (k == warm) { t0 = mono_s(); h2d = d2h = 0; sp[0] = sp[1] = sp[2] = 0; }
-    const double a = mono_s();
-    if (n_prev) {
-      const int rc = post(handle, n_prev, slots, ok_phase, NULL);
-      if (rc) return rc;
-      h2d += n_prev * 8;
+  static e2e_pool_t P; /* (atomics: not copyable) */
+  memset(&P, 0, sizeof P);
+  P.post = post; P.handle = handle; P.ok_phase = ok_phase; P.slots = slots;
+  P.piece = E2E_PIECE;
+  const char* pe = getenv("AMGEN_E2E_PIECE"); /* tests: force several pieces on a small population */
+  if (pe && atoll(pe) > 0) P.piece = (uint64_t)atoll(pe);
+  if (workers < 1) workers = 1;
+  if (workers > E2E_MAX_WORKERS) workers = E2E_MAX_WORKERS;
+  while (workers > 1 && (uint64_t)workers * P.piece > capacity) workers--;
+  if (P.piece > capacity) P.piece = capacity;
+  P.workers = workers;
+  pthread_t th[E2E_MAX_WORKERS];
+  e2e_arg_t args[E2E_MAX_WORKERS];
+  for (int w = 1; w < workers; w++) {
+    args[w].pool = &P; args[w].w = w;
+    if (pthread_create(&th[w], NULL, e2e_worker, &args[w])) return -1;
+  }
+  int rc = 0;
+  for (uint64_t k = 0; k < warm + steps && !rc; k++) {
+    if (k == warm) {
+      t0 = mono_s(); h2d = d2h = 0; sp_tick = sp_cons = 0;
+      for (int w = 0; w < workers; w++) P.post_s[w] = P.walk_s[w] = 0;
     }
     const double b = mono_s();
-    const int rc = tick(handle, T_first + (int64_t)k, mode, &v, &st);
-    if (rc) return rc;
+    rc = tick(handle, T_first + (int64_t)k, mode, &v, &st);
+    if (rc) break;
     const double c = mono_s();
-    n_prev = amgen_select_submitted_view(v.idx_local, v.action, v.n, slots);
-    d2h += v.n * 5 + sizeof st;
+    P.idx = v.idx_local; P.act = v.action; P.n = v.n;
+    atomic_store(&P.next_piece, 0); atomic_store(&P.submitted, 0); atomic_store(&P.done, 0);
+    atomic_fetch_add_explicit(&P.gen, 1, memory_order_release);
+    e2e_consume(&P, 0);
+    while (atomic_load_explicit(&P.done, memory_order_acquire) < workers - 1) __builtin_ia32_pause();
+    rc = atomic_load(&P.rc);
+    n_prev = atomic_load(&P.submitted);
     const double d = mono_s();
-    sp[0] += b - a; sp[1] += c - b; sp[2] += d - c;
+    h2d += n_prev * 8;
+    d2h += v.n * 5 + sizeof st;
+    sp_tick += c - b; sp_cons += d - c;
   }
   *seconds = mono_s() - t0;
-  if (split) { split[0] = sp[0]; split[1] = sp[1]; split[2] = sp[2]; }
+  atomic_store(&P.quit, 1);
+  for (int w = 1; w < workers; w++) pthread_join(th[w], NULL);
+  if (rc) return rc;
+  if (split) {
+    double ps = 0, ws = 0;
+    for (int w = 0; w < workers; w++) { ps += P.post_s[w]; ws += P.walk_s[w]; }
+    split[0] = ps / workers; split[1] = sp_tick; split[2] = ws / workers; split[3] = sp_cons;
+  }
   *h2d_bytes = h2d; *d2h_bytes = d2h;
   *last_emitted = v.n; *last_submitted = n_prev;
-  return 0;
+  return workers;
 }

@@ -61,9 +61,9 @@ def load() -> C.CDLL:
         lib.amgen_select_submitted.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         lib.amgen_e2e_closed_loop.restype = C.c_int
         lib.amgen_e2e_closed_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_uint64,
-                                              C.c_uint64, C.c_void_p, C.c_void_p, C.POINTER(C.c_double),
-                                              C.POINTER(C.c_double * 3), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
-                                              C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+                                              C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int,
+                                              C.POINTER(C.c_double), C.POINTER(C.c_double * 4), C.POINTER(C.c_uint64),
+                                              C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         lib.amgen_select_submitted_view.restype = C.c_uint64
         lib.amgen_select_submitted_view.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.amgen_key.restype = C.c_uint64
@@ -121,18 +121,21 @@ def select_submitted_view(idx_local: np.ndarray, act: np.ndarray, out: np.ndarra
     return out[:m]
 
 
-def e2e_closed_loop(product_lib, sweep_handle, T_first: int, mode: int, warm: int, steps: int, capacity: int) -> dict:
-    """bench.py's e2e loop in compiled code (amgen_e2e_closed_loop): am_sweep_post_result +
-    am_sweep_tick_view of `product_lib` (a ctypes CDLL of the C-ABI) on `sweep_handle`."""
+def e2e_closed_loop(product_lib, sweep_handle, T_first: int, mode: int, warm: int, steps: int, capacity: int,
+                    workers: int = 1) -> dict:
+    """bench.py's e2e loop in compiled code (amgen_e2e_closed_loop): am_sweep_tick_view, then `workers`
+    consumer threads walking the list in pieces and posting through am_sweep_post_result of
+    `product_lib` (a ctypes CDLL of the C-ABI) on `sweep_handle`."""
     slots = np.empty(capacity, dtype=np.uint64)
     ok = np.full(capacity, 1, dtype=np.uint8)  # AM_PHASE_SUCCEEDED
-    sec, split = C.c_double(), (C.c_double * 3)()
+    sec, split = C.c_double(), (C.c_double * 4)()
     h2d, d2h, ne, ns = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
     rc = load().amgen_e2e_closed_loop(C.cast(product_lib.am_sweep_post_result, C.c_void_p),
                                       C.cast(product_lib.am_sweep_tick_view, C.c_void_p), sweep_handle, T_first, mode,
-                                      warm, steps, slots.ctypes.data, ok.ctypes.data, C.byref(sec), C.byref(split),
-                                      C.byref(h2d), C.byref(d2h), C.byref(ne), C.byref(ns))
-    if rc != 0:
+                                      warm, steps, slots.ctypes.data, capacity, ok.ctypes.data, workers, C.byref(sec),
+                                      C.byref(split), C.byref(h2d), C.byref(d2h), C.byref(ne), C.byref(ns))
+    if rc <= 0:
         raise RuntimeError(f"amgen_e2e_closed_loop: C-ABI call failed with {rc}")
-    return {"seconds": sec.value, "post_s": split[0], "tick_s": split[1], "walk_s": split[2],
-            "h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "last_emitted": ne.value, "last_submitted": ns.value}
+    return {"seconds": sec.value, "post_s": split[0], "tick_s": split[1], "walk_s": split[2], "consumer_s": split[3],
+            "workers": rc, "h2d_bytes": h2d.value, "d2h_bytes": d2h.value, "last_emitted": ne.value,
+            "last_submitted": ns.value}
