@@ -28,6 +28,7 @@ KIND_CRON_EVERY, KIND_PARSE_ERROR, KIND_HOST_FALLBACK = 4, 5, 6
 F_HAS_REMEDY, F_PENDING_OK, F_PENDING_FAIL = 1 << 3, 1 << 4, 1 << 5
 F_REMEDY_PENDING, F_REMEDY_OUTCOME_OK = 1 << 6, 1 << 7
 F_TOMBSTONE, F_STOPPED_REPORTED, F_TIMER_ARMED = 1 << 8, 1 << 9, 1 << 10
+F_CARRY_MASK = 0x1F << 11  # library-internal (drain -> same tick's sweep), never visible
 F_FAILP_SHIFT = 16
 F_TZ_SHIFT = 24
 

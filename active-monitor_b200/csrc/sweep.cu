@@ -24,6 +24,7 @@
 // am_sweep_create fails with AM_E_DEVICE.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <condition_variable>
 #include <mutex>
@@ -159,6 +160,7 @@ struct am_sweep {
   uint64_t launches = 0;
   double last_ms = -1.0;
   uint64_t seed = 0;
+  bool early_results = true;  // AMSWEEP_EARLY_RESULTS=0: every posted result is applied inside the sweep
 };
 
 namespace {
@@ -288,7 +290,7 @@ int reserve_staging(am_sweep* h, std::unique_lock<std::mutex>& lk, size_t n, siz
 
 // Apply staged upserts / removes / results on stream `s` (called with the tick guard held).
 // The staging lock is held only for the buffer swap.
-int drain_staged(am_sweep* h, cudaStream_t s) {
+int drain_staged(am_sweep* h, cudaStream_t s, const int64_t* tick_T = nullptr) {
   Staging* st;
   {
     std::unique_lock<std::mutex> lk(h->mu);
@@ -336,6 +338,18 @@ int drain_staged(am_sweep* h, cudaStream_t s) {
   }
   if (st->n_result) {
     AM_LAUNCH(apply_result_ops_kernel, G, B, s, h->cols.flags, h->marks, d_idx, d_arg, (uint32_t)n);
+    h->launches++;
+  }
+  // a tick's drain applies sparse results right away (apply_results_now_kernel: no second memory
+  // round trip in the sweep); a read's drain, or a batch touching more than an eighth of the
+  // records, leaves them pending for the sweep's own streaming path
+  if (tick_T && st->n_result && h->early_results && (uint64_t)st->n_result * 8 <= h->n_records) {
+    TickSet& ts = h->set[h->parity];  // the buffer set of the tick being prepared
+    if (ts.consumed_pending) {        // (its statistics may still be read by an exchange on another stream)
+      AM_CUDA(h, cudaStreamWaitEvent(s, ts.consumed, 0));
+      ts.consumed_pending = false;
+    }
+    AM_LAUNCH(apply_results_now_kernel, G, B, s, h->cols, d_idx, d_arg, (uint32_t)n, *tick_T, ts.acc);
     h->launches++;
   }
   AM_LAUNCH(clear_marks_kernel, G, B, s, h->marks, d_idx, (uint32_t)n);
@@ -485,7 +499,7 @@ int host_tick(am_sweep* h, int64_t unix_sec, uint32_t mode, am_tick_stats_t* sta
   AM_CUDA(h, cudaSetDevice(h->device));
   int rc = order_on(h, h->stream);
   if (rc != AM_OK) return rc;
-  rc = drain_staged(h, h->stream);
+  rc = drain_staged(h, h->stream, &unix_sec);
   if (rc != AM_OK) return rc;
   rc = reserve_host_out(h, h->n_records);
   if (rc != AM_OK) return rc;
@@ -584,6 +598,7 @@ int am_sweep_create(am_sweep_t** out, int device_id, uint64_t capacity, uint64_t
   h->capacity = capacity;
   h->cap_padded = (capacity + kTile - 1) / kTile * kTile;
   h->shard_base = shard_base;
+  if (const char* e = getenv("AMSWEEP_EARLY_RESULTS")) h->early_results = atoi(e) != 0;  // (A/B of the two result paths)
   int rc = [&]() -> int {
     AM_CUDA(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     AM_CUDA(h, cudaStreamCreateWithFlags(&h->cstream, cudaStreamNonBlocking));
@@ -885,7 +900,7 @@ int am_sweep_tick_device(am_sweep_t* h, int64_t unix_sec, uint32_t mode, void* d
   cudaStream_t s = (cudaStream_t)cuda_stream;  // NULL == CUDA default stream
   int rc = order_on(h, s);
   if (rc != AM_OK) return rc;
-  rc = drain_staged(h, s);
+  rc = drain_staged(h, s, &unix_sec);
   if (rc != AM_OK) return rc;
   ListOut o;
   o.idx = d_due_idx;
@@ -905,7 +920,7 @@ int am_sweep_tick_shard(am_sweep_t* h, int64_t unix_sec, uint32_t mode, void* cu
   cudaStream_t s = (cudaStream_t)cuda_stream;
   int rc = order_on(h, s);
   if (rc != AM_OK) return rc;
-  rc = drain_staged(h, s);
+  rc = drain_staged(h, s, &unix_sec);
   if (rc != AM_OK) return rc;
   if (h->n_records == 0) return AM_E_INVAL;  // an empty shard has nothing to exchange
   ListOut o;
@@ -927,7 +942,7 @@ int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint3
   AM_CUDA(h, cudaSetDevice(h->device));
   int rc = order_on(h, h->stream);
   if (rc != AM_OK) return rc;
-  rc = drain_staged(h, h->stream);
+  rc = drain_staged(h, h->stream, &unix_sec0);
   if (rc != AM_OK) return rc;
   h->seed = seed;
   am_tick_stats_t* d_stats = nullptr;

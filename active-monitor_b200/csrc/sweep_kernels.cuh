@@ -188,6 +188,13 @@ __device__ __forceinline__ uint32_t apply_result(RecState& r, int64_t T, uint32_
   return act;
 }
 
+// Action bits of apply_result <-> the carry bits of the flags word (AM_F_CARRY_MASK): RUN_REMEDY (0x02)
+// in bit 11, REMEDY_SKIP .. ANOMALY (0x10 .. 0x80) in bits 12 .. 15.
+__device__ __forceinline__ uint32_t carried_actions(uint32_t f) { return ((f >> 10) & AM_ACT_RUN_REMEDY) | ((f >> 8) & 0xF0u); }
+__device__ __forceinline__ uint32_t carry_of_actions(uint32_t a) { return ((a & AM_ACT_RUN_REMEDY) << 10) | ((a & 0xF0u) << 8); }
+static_assert(AM_F_CARRY_SHIFT == 11 && AM_ACT_RUN_REMEDY == 0x02u && AM_ACT_REMEDY_SKIP == 0x10u && AM_ACT_ANOMALY == 0x80u,
+              "carry bit layout");
+
 // The tick's wall clock in every registered time zone ("CRON_TZ=Zone ..." schedules, robfig
 // parser.go / hcc.go:253): one thread per zone evaluates the zone's UTC offset at T (transition
 // table, then the POSIX rule of the TZif footer: tz_eval.h) and writes T's LOCAL fields as the
@@ -256,43 +263,6 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   // the second half's loads were delayed behind the first half's compute: -30 % bandwidth).
   __syncwarp();
 
-  // ---- phase A': posted results are visible in the flags alone — the first load issued, the
-  // first to return.  When only a few lanes of the warp have one (results trickling in between
-  // two ticks: the sparse shape below), each such lane fetches the remedy / counter state of its
-  // first record with a result NOW, while the other fifteen loads are still in flight, instead
-  // of paying a second, serial memory round trip after the schedule decision (+60 us on a 10 M
-  // tick with 0.18 M posted results, profiles/r02_e2e_breakdown.md).  A second fence keeps
-  // ptxas from sinking these loads down to their use.
-  int pre_b = -1;
-  int32_t pre_lim = 0, pre_rst = 0, pre_sc = 0, pre_fc = 0, pre_rsc = 0, pre_rfc = 0, pre_rtc = 0;
-  int64_t pre_rfa = 0;
-  if (!CLOSED) {  // (the closed-loop harness posts nothing from outside: its results arise inside the tick)
-    constexpr uint32_t kPend = AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING;
-    const bool maybe = ((fl[0].x | fl[0].y | fl[1].x | fl[1].y) & kPend) != 0;
-    const unsigned lanes = __ballot_sync(kFull, maybe);
-    if (lanes != 0 && __popc(lanes) < 16) {  // warp-uniform
-      if (maybe) {
-        uint32_t pend = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint32_t f = (q & 1) ? fl[q >> 1].y : fl[q >> 1].x;
-          const bool live = ((0x3Eu >> (f & AM_KIND_MASK)) & 1u) && !(f & AM_F_TOMBSTONE);
-          if (live && (f & kPend)) pend |= 1u << q;
-        }
-        if (pend) {
-          pre_b = __ffs(pend) - 1;
-          const uint32_t i = r0[0] + (uint32_t)(64 * (pre_b >> 1) + (pre_b & 1));
-          pre_lim = ld_stream(p.c.runs_limit + i); pre_rst = ld_stream(p.c.reset_interval + i);
-          pre_sc = ld_stream(p.c.success + i); pre_fc = ld_stream(p.c.failed + i);
-          pre_rsc = ld_stream(p.c.remedy_success + i); pre_rfc = ld_stream(p.c.remedy_failed + i);
-          pre_rtc = ld_stream(p.c.remedy_total + i);
-          pre_rfa = ld_stream(p.c.remedy_finished_at + i);
-        }
-      }
-    }
-  }
-  __syncwarp();
-
   // The tick's broken-down time: one-hot words computed once per tick (civil.h) and
   // delivered through the kernel parameters, i.e. the constant bank / uniform
   // registers — cheaper than staging them in shared memory, which cost every CTA a
@@ -357,8 +327,13 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
                   ((live && kind == AM_KIND_PARSE_ERROR) ? AM_ACT_PARSE_ERROR : 0u);
       nfl[h][j] = f;
       nfa[h][j] = fav;
+      if (f & AM_F_CARRY_MASK) {  // a result applied at this tick's drain (apply_results_now_kernel): its action bits
+        act[h][j] |= carried_actions(f);
+        nfl[h][j] = f & ~AM_F_CARRY_MASK;
+        dirty[h] = true;
+      }
       if (stopped_now) {  // hcc.go:238-250: Status "Stopped", FinishedAt = now
-        nfl[h][j] = f | AM_F_STOPPED_REPORTED;
+        nfl[h][j] |= AM_F_STOPPED_REPORTED;
         nfa[h][j] = T;
         dirty[h] = true;
       }
@@ -451,17 +426,11 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
       const int b = __ffs(needy) - 1;
       needy &= needy - 1;
       const uint32_t i = r0[0] + (uint32_t)(64 * (b >> 1) + (b & 1));
-      int32_t lim, rst, sc, fc, rsc, rfc, rtc;
-      int64_t rfa;
-      if (b == pre_b) {  // fetched in phase A'
-        lim = pre_lim; rst = pre_rst; sc = pre_sc; fc = pre_fc; rsc = pre_rsc; rfc = pre_rfc; rtc = pre_rtc; rfa = pre_rfa;
-      } else {
-        lim = ld_stream(p.c.runs_limit + i); rst = ld_stream(p.c.reset_interval + i);
-        sc = ld_stream(p.c.success + i); fc = ld_stream(p.c.failed + i);
-        rsc = ld_stream(p.c.remedy_success + i); rfc = ld_stream(p.c.remedy_failed + i);
-        rtc = ld_stream(p.c.remedy_total + i);
-        rfa = ld_stream(p.c.remedy_finished_at + i);
-      }
+      const int32_t lim = ld_stream(p.c.runs_limit + i), rst = ld_stream(p.c.reset_interval + i);
+      const int32_t sc = ld_stream(p.c.success + i), fc = ld_stream(p.c.failed + i);
+      const int32_t rsc = ld_stream(p.c.remedy_success + i), rfc = ld_stream(p.c.remedy_failed + i);
+      const int32_t rtc = ld_stream(p.c.remedy_total + i);
+      const int64_t rfa = ld_stream(p.c.remedy_finished_at + i);
       const uint32_t f0 = b == 0 ? nfl[0][0] : b == 1 ? nfl[0][1] : b == 2 ? nfl[1][0] : nfl[1][1];
       const int64_t fa0 = b == 0 ? nfa[0][0] : b == 1 ? nfa[0][1] : b == 2 ? nfa[1][0] : nfa[1][1];
       RecState s{f0, fa0, sc, fc, rsc, rfc, rtc, rfa, lim, rst};
@@ -969,6 +938,57 @@ __global__ void apply_result_ops_kernel(uint32_t* flags, const uint32_t* __restr
   if (clr) {
     atomicAnd(&flags[i], ~clr);
     atomicOr(&flags[i], set);
+  }
+}
+
+// Results posted between two ticks, applied while the tick drains them instead of inside its sweep.
+// In the sweep a record with a posted result costs its warp a second, dependent memory round trip
+// (the remedy / counter columns) behind the streaming loads; with a result on ~2 % of the records
+// nine warps in ten pay it and the tick's sweep slows from 84 to 143 us at 10 M records
+// (profiles/r02_e2e_breakdown.json).  Here every result is its own thread: one claims the slot's
+// pending bits (atomicAnd: a slot can have two winning ops, workflow phase and remedy phase), gathers
+// the eight state columns, runs the same apply_result and scatters what changed.  The action bits go
+// into the flags' carry bits for the sweep of the SAME tick to emit (it clears them); the finishedAt /
+// timer-armed state it leaves is exactly what the sweep's own step 1 would have decided on.  Only the
+// tick's drain does this (T is the tick's second) and only when results are sparse; a read drains
+// without it, and a dense batch is cheaper as the sweep's streaming path.
+__global__ void apply_results_now_kernel(DevCols c, const uint32_t* __restrict__ op_idx, const uint32_t* __restrict__ op_arg,
+                                         uint32_t n, int64_t T, unsigned long long* acc) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr uint32_t kPend = AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING;
+  uint32_t res = 0;
+  if (k < n && (op_arg[k] & kOpKindMask) == kOpResult) {
+    const uint32_t i = op_idx[k];
+    const uint32_t f0 = c.flags[i];
+    const bool live = ((0x3Eu >> (f0 & AM_KIND_MASK)) & 1u) && !(f0 & AM_F_TOMBSTONE);
+    if (live && (f0 & kPend)) {
+      const uint32_t old = atomicAnd(&c.flags[i], ~(kPend | AM_F_REMEDY_OUTCOME_OK));
+      if (old & kPend) {  // this thread owns the slot's results (another op of the slot finds none)
+        RecState s{old, c.finished_at[i], c.success[i], c.failed[i], c.remedy_success[i], c.remedy_failed[i],
+                   c.remedy_total[i], c.remedy_finished_at[i], c.runs_limit[i], c.reset_interval[i]};
+        const RecState b = s;
+        const uint32_t a = apply_result(s, T, res);
+        if (s.fa != b.fa) c.finished_at[i] = s.fa;
+        if (s.s != b.s) c.success[i] = s.s;
+        if (s.f != b.f) c.failed[i] = s.f;
+        if (s.rs != b.rs) c.remedy_success[i] = s.rs;
+        if (s.rf != b.rf) c.remedy_failed[i] = s.rf;
+        if (s.rt != b.rt) c.remedy_total[i] = s.rt;
+        if (s.rfa != b.rfa) c.remedy_finished_at[i] = s.rfa;
+        const uint32_t set = (s.flags & AM_F_TIMER_ARMED) | carry_of_actions(a);
+        if (set) atomicOr(&c.flags[i], set);
+      }
+    }
+  }
+  // results applied (metrics.MonitorSuccess / Error): warp -> global RED, as the sweep does per tile
+  if (__any_sync(kFull, res != 0)) {
+    const uint32_t lo = __reduce_add_sync(kFull, (res & 0xFFu) | ((res & 0xFF00u) << 8));
+    const uint32_t hi = __reduce_add_sync(kFull, ((res >> 16) & 0xFFu) | ((res >> 8) & 0xFF0000u));
+    const int lane = threadIdx.x & 31;
+    if (lane < 4) {
+      const uint32_t v = ((lane < 2 ? lo : hi) >> ((lane & 1) * 16)) & 0xFFFFu;
+      if (v) atomicAdd(&acc[10 + lane], (unsigned long long)v);
+    }
   }
 }
 

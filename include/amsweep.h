@@ -113,6 +113,11 @@ int64_t am_cron_repeat_after_sec(const am_cron_t* c, int64_t unix_sec);
 #define AM_F_TIMER_ARMED (1u << 10)      /* RepeatTimersByName holds a timer for the
                                             check (hcc.go:264 "&& timer != nil";
                                             armed by hcc.go:745-752 after a result) */
+#define AM_F_CARRY_SHIFT 11              /* bits 11..15: library-internal.  Action bits of a posted result the
+                                          * library applied while draining the staged calls of a tick (before
+                                          * that tick's sweep, which emits and clears them): never set in a
+                                          * record a caller sees or supplies                                */
+#define AM_F_CARRY_MASK (0x1Fu << AM_F_CARRY_SHIFT)
 #define AM_F_TZ_SHIFT 24                 /* bits 24..31: time zone of a 5-field schedule
                                             ("CRON_TZ=Zone ..."), 0 = UTC; am_tz_lookup   */
 #define AM_F_TZ_MASK (0xFFu << AM_F_TZ_SHIFT)
@@ -254,7 +259,12 @@ int am_sweep_remove(am_sweep_t*, uint64_t n, const uint64_t* idx);
 
 /* Terminal workflow phases observed by the watch loops (hcc.go:635, :662,
  * :821, :836).  phase / remedy_phase: 0 none, 1 Succeeded, 2 Failed.
- * Thread-safe; staged and applied at the start of the next tick. */
+ * Thread-safe; staged and applied at the start of the next tick.  Calls from several
+ * threads (the reconcile workers, hcc.go:170-188) stage concurrently: a call holds the
+ * handle's lock only to reserve its range of the staging arrays, so posting scales with
+ * the caller's threads; per slot, calls take effect in the order they entered the library.
+ * A call with an out-of-range slot (AM_E_RANGE) or a phase outside 0..2 (AM_E_INVAL) has
+ * no effect at all. */
 #define AM_PHASE_NONE 0
 #define AM_PHASE_SUCCEEDED 1
 #define AM_PHASE_FAILED 2

@@ -246,3 +246,93 @@ def test_large_post_is_chunked_and_a_bad_entry_commits_nothing(am, orc, gen):
         live = slots.astype(np.int64)
         orac["flags"][live] |= np.where(ph == am.PHASE_FAILED, am.F_PENDING_FAIL, am.F_PENDING_OK).astype(np.uint32)
         _assert_tick_equal(am, s.tick(T0 + 1), orc.sweep(orac, T0 + 1), s, orac, n, "after a chunked post")
+
+
+def test_concurrent_posts_from_many_threads(am, orc, gen):
+    """Six threads post results for disjoint slot sets at once (ctypes releases the GIL: the calls
+    really overlap, each staging its reserved range outside the handle's lock), two of them with a
+    call that must be rejected as a whole, while the main thread ticks now and then.  Every posted
+    result must be applied exactly once: the counters after the last tick equal the oracle's with
+    all results applied."""
+    import threading
+    n, per, rounds = 60_000, 9_000, 5
+    prod, orac = _gen_pair(gen, am, orc, 2, 4, n, T0)
+    rng = np.random.default_rng(7)
+    with emu_sweep.EmuSweep(n) as s:
+        s.load_range(0, prod)
+        errors = []
+
+        def worker(w):
+            try:
+                mine = np.arange(w * per, (w + 1) * per, dtype=np.uint64)
+                for r in range(rounds):
+                    part = mine[r::rounds]
+                    ph = np.where(part % 2 == 0, am.PHASE_SUCCEEDED, am.PHASE_FAILED).astype(np.uint8)
+                    if w in (1, 4) and r == 2:  # a rejected call in the middle of the traffic
+                        bad = part.copy()
+                        bad[len(bad) // 2] = n + 1
+                        try:
+                            s.post_result(bad, ph)
+                            errors.append("bad call accepted")
+                        except am.AmError as e:
+                            assert e.code == am.AM_E_RANGE
+                    s.post_result(part, ph)
+            except Exception as e:  # noqa: BLE001
+                errors.append(repr(e))
+
+        th = [threading.Thread(target=worker, args=(w,)) for w in range(6)]
+        for t in th:
+            t.start()
+        s.tick(T0)  # a tick in the middle: drains whatever complete calls it finds
+        for t in th:
+            t.join()
+        assert not errors, errors
+        s.tick(T0 + 1)
+        dev = s.read_range(0, n)
+        # results are posted once per slot: whichever of the two ticks applied one, the counters add up
+        slots = np.arange(0, 6 * per)
+        live = ((0x3E >> (prod["flags"][slots] & am.KIND_MASK)) & 1).astype(bool) & ((prod["flags"][slots] & am.F_TOMBSTONE) == 0)
+        ok = slots % 2 == 0
+        np.testing.assert_array_equal(dev["success"][slots] - prod["success"][slots], (live & ok).astype(np.int32))
+        np.testing.assert_array_equal(dev["failed"][slots] - prod["failed"][slots], (live & ~ok).astype(np.int32))
+        assert not np.any(dev["flags"][slots][live] & (am.F_PENDING_OK | am.F_PENDING_FAIL))
+        rest = np.arange(6 * per, n)
+        np.testing.assert_array_equal(dev["success"][rest], prod["success"][rest])
+
+
+@pytest.mark.parametrize("every", [23, 3])
+def test_posted_results_sparse_and_dense_paths(am, orc, gen, every):
+    """Results posted between ticks are applied at the tick's drain by apply_results_now_kernel when they
+    are sparse (ops <= 1/8 of the records: `every` = 23) — their action bits travel to the same tick's sweep in
+    the flags' carry bits — and inside the sweep when they are dense (`every` = 3).  Both must equal the
+    oracle: list, action bytes (RUN_REMEDY, REMEDY_SKIP, RESET_ON_PASS, RESET_ON_INTERVAL, ANOMALY all
+    occur in the config-3 mix), statistics, every column; over three ticks, with workflow and remedy phases
+    posted by separate calls."""
+    n = 40_000
+    prod, orac = _gen_pair(gen, am, orc, 3, 12, n, T0)
+    pend = am.F_PENDING_OK | am.F_PENDING_FAIL | am.F_REMEDY_PENDING | am.F_REMEDY_OUTCOME_OK
+    for c in (prod, orac):  # the posted results come through the C-ABI here, not with the population
+        c["flags"] &= ~np.uint32(pend)
+    seen = 0
+    with emu_sweep.EmuSweep(n) as s:
+        s.load_range(0, prod)
+        for k in range(3):
+            T = T0 + 1800 * k
+            slots = np.arange(k, n, every, dtype=np.uint64)
+            ph = (1 + (slots * 7 + k) % 2).astype(np.uint8)        # Succeeded / Failed
+            rp = ((slots // every + k) % 3).astype(np.uint8)         # none / Succeeded / Failed
+            s.post_result(slots, ph)                                 # workflow phase ...
+            with_r = rp != 0
+            s.post_result(slots[with_r], np.zeros(int(with_r.sum()), np.uint8), rp[with_r])  # ... remedy phase, separately
+            i = slots.astype(np.int64)
+            orac["flags"][i] |= np.where(ph == 1, am.F_PENDING_OK, am.F_PENDING_FAIL).astype(np.uint32)
+            orac["flags"][i[with_r]] |= np.where(rp[with_r] == 1, am.F_REMEDY_PENDING | am.F_REMEDY_OUTCOME_OK,
+                                                 am.F_REMEDY_PENDING).astype(np.uint32)
+            l0 = s.launch_count
+            got, want = s.tick(T), orc.sweep(orac, T)
+            # mark, apply_result_ops, [apply_results_now], clear_marks + tz_table, sweep, scan, expand, publish
+            assert s.launch_count - l0 == (9 if every == 23 else 8), s.launch_count - l0
+            _assert_tick_equal(am, got, want, s, orac, n, f"every={every} tick {k}")
+            seen |= int(np.bitwise_or.reduce(want[1]))
+        assert not np.any(s.read_range(0, n)["flags"] & am.F_CARRY_MASK)
+    assert seen & 0xF2 == 0xF2, hex(seen)  # every result-driven action bit occurred
