@@ -333,11 +333,11 @@ int drain_staged(am_sweep* h, cudaStream_t s, const int64_t* tick_T = nullptr) {
   AM_LAUNCH(mark_ops_kernel, G, B, s, h->marks, d_idx, d_arg, (uint32_t)n);
   h->launches++;
   if (st->n_state) {
-    AM_LAUNCH(apply_state_ops_kernel, G, B, s, h->cols, h->marks, d_idx, d_arg, d_recs, (uint32_t)n);
+    AM_LAUNCH_PDL(apply_state_ops_kernel, G, B, s, h->cols, h->marks, d_idx, d_arg, d_recs, (uint32_t)n);
     h->launches++;
   }
   if (st->n_result) {
-    AM_LAUNCH(apply_result_ops_kernel, G, B, s, h->cols.flags, h->marks, d_idx, d_arg, (uint32_t)n);
+    AM_LAUNCH_PDL(apply_result_ops_kernel, G, B, s, h->cols.flags, h->marks, d_idx, d_arg, (uint32_t)n);
     h->launches++;
   }
   // a tick's drain applies sparse results right away (apply_results_now_kernel: no second memory
@@ -349,10 +349,10 @@ int drain_staged(am_sweep* h, cudaStream_t s, const int64_t* tick_T = nullptr) {
       AM_CUDA(h, cudaStreamWaitEvent(s, ts.consumed, 0));
       ts.consumed_pending = false;
     }
-    AM_LAUNCH(apply_results_now_kernel, G, B, s, h->cols, d_idx, d_arg, (uint32_t)n, *tick_T, ts.acc);
+    AM_LAUNCH_PDL(apply_results_now_kernel, G, B, s, h->cols, d_idx, d_arg, (uint32_t)n, *tick_T, ts.acc);
     h->launches++;
   }
-  AM_LAUNCH(clear_marks_kernel, G, B, s, h->marks, d_idx, (uint32_t)n);
+  AM_LAUNCH_PDL(clear_marks_kernel, G, B, s, h->marks, d_idx, (uint32_t)n);
   h->launches++;
   AM_CUDA(h, cudaGetLastError());
   AM_CUDA(h, cudaEventRecord(st->drained, s));
@@ -430,7 +430,7 @@ int launch_tick(am_sweep* h, int64_t T, uint32_t mode, const ListOut& o, cudaStr
       z.table = (TickWords*)h->tz_table.p;
       z.T = T;
       z.n = h->tz_n;
-      AM_LAUNCH(tz_table_kernel, (h->tz_n + 63) / 64, 64, s, z);
+      AM_LAUNCH_PDL(tz_table_kernel, (h->tz_n + 63) / 64, 64, s, z);
       h->launches++;
       p.tz_table = (const TickWords*)h->tz_table.p;
     }
@@ -443,10 +443,10 @@ int launch_tick(am_sweep* h, int64_t T, uint32_t mode, const ListOut& o, cudaStr
   if (sec_of_min < 0) sec_of_min += 60;
   const bool masks = sec_of_min == 0 || (mode & AM_SWEEP_FULL_SCAN) || (h->tz_n > 1 && !amsweep_tz::all_minute_aligned(T));
   const bool closed = (mode & AM_SWEEP_CLOSED_LOOP) != 0;
-  if (closed && masks) AM_LAUNCH(AM_SWEEP_KERNEL(true, true), p.n_tiles, kBlock, s, p);
-  else if (closed) AM_LAUNCH(AM_SWEEP_KERNEL(true, false), p.n_tiles, kBlock, s, p);
-  else if (masks) AM_LAUNCH(AM_SWEEP_KERNEL(false, true), p.n_tiles, kBlock, s, p);
-  else AM_LAUNCH(AM_SWEEP_KERNEL(false, false), p.n_tiles, kBlock, s, p);
+  if (closed && masks) AM_LAUNCH_PDL(AM_SWEEP_KERNEL(true, true), p.n_tiles, kBlock, s, p);
+  else if (closed) AM_LAUNCH_PDL(AM_SWEEP_KERNEL(true, false), p.n_tiles, kBlock, s, p);
+  else if (masks) AM_LAUNCH_PDL(AM_SWEEP_KERNEL(false, true), p.n_tiles, kBlock, s, p);
+  else AM_LAUNCH_PDL(AM_SWEEP_KERNEL(false, false), p.n_tiles, kBlock, s, p);
   if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[1], s));
   ScanParams sc{};
   sc.group_count = ts.out.group_count;

@@ -195,12 +195,27 @@ __device__ __forceinline__ uint32_t carry_of_actions(uint32_t a) { return ((a & 
 static_assert(AM_F_CARRY_SHIFT == 11 && AM_ACT_RUN_REMEDY == 0x02u && AM_ACT_REMEDY_SKIP == 0x10u && AM_ACT_ANOMALY == 0x80u,
               "carry bit layout");
 
+// robfig SpecSchedule matching against the tick's one-hot wall-clock words (Appendix A: five ANDs and
+// the dom/dow star rule).  Branch-free: every term is evaluated (no short-circuit control flow).
+__device__ __forceinline__ bool cron_matches(const TickWords& t, uint64_t mi, uint64_t hr, uint64_t dm, uint64_t mo, uint64_t dw) {
+  const bool fld = ((mi & t.minute) != 0) & ((hr & t.hour) != 0) & ((mo & t.month) != 0);
+  const bool dmm = (dm & t.dom) != 0, dwm = (dw & t.dow) != 0;
+  const bool star = ((dm | dw) >> 63) != 0;  // robfig dayMatches
+  return (t.sec0 != 0) & fld & (star ? (dmm & dwm) : (dmm | dwm));
+}
+__device__ __noinline__ bool cron_matches_in_zone(const TickWords* z, uint64_t mi, uint64_t hr, uint64_t dm, uint64_t mo,
+                                                  uint64_t dw) {
+  const TickWords t = *z;
+  return cron_matches(t, mi, hr, dm, mo, dw);
+}
+
 // The tick's wall clock in every registered time zone ("CRON_TZ=Zone ..." schedules, robfig
 // parser.go / hcc.go:253): one thread per zone evaluates the zone's UTC offset at T (transition
 // table, then the POSIX rule of the TZif footer: tz_eval.h) and writes T's LOCAL fields as the
 // one-hot words the sweep ANDs against the cron masks.  A few dozen threads, once per tick, only
 // when zones are registered.
 __global__ void tz_table_kernel(const TzTableParams p) {
+  pdl_wait();  // (launched with programmatic stream serialisation: nothing of the predecessor is touched before this)
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= p.n) return;
   const int32_t off = k ? amsweep_tz::tz_zone_offset(p.descs[k], p.trans, p.off, p.T) : 0;
@@ -232,6 +247,7 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   const uint32_t tile = blockIdx.x;
   const uint32_t tile_base = tile * (uint32_t)kTile;
   const int64_t T = p.T;
+  pdl_wait();  // the sweep is launched while its predecessor (the previous tick's publish, or the drain) still runs
 
   // ---- phase A: issue every schedule-column load of this lane up front ----
   // half h covers records r0(h) .. r0(h)+1, r0 = tile_base + warp*128 + h*64 + lane*2
@@ -269,8 +285,8 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   // serial thread-0 section and a barrier (profiles/r01_summary.md).
   const TickWords w = p.words;
   // named time zones are rare: one vote per warp decides whether the per-record zone lookup exists at all
-  const bool warp_tz = MASKS && p.tz_table != nullptr &&
-                       __any_sync(kFull, ((fl[0].x | fl[0].y | fl[1].x | fl[1].y) >> AM_F_TZ_SHIFT) != 0);
+  const uint32_t fl_or = fl[0].x | fl[0].y | fl[1].x | fl[1].y;
+  const bool warp_tz = MASKS && p.tz_table != nullptr && __any_sync(kFull, (fl_or >> AM_F_TZ_SHIFT) != 0);
 
   uint32_t act[2][2];
   uint32_t res_lane = 0;  // 4 x 8-bit counts of results applied by this lane
@@ -305,20 +321,14 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
         const uint64_t miv = j ? mi[h].y : mi[h].x, hrv = j ? hr[h].y : hr[h].x;
         const uint64_t dmv = j ? dm[h].y : dm[h].x, mov = j ? mo[h].y : mo[h].x;
         const uint64_t dwv = j ? dw[h].y : dw[h].x;
-        uint64_t t_mi = w.minute, t_hr = w.hour, t_dm = w.dom, t_mo = w.month, t_dw = w.dow;
-        uint32_t t_s0 = w.sec0;
+        due_cron = cron_matches(w, miv, hrv, dmv, mov, dwv);
         if (warp_tz) {  // warp-uniform: some record of this warp is bound to a named time zone
           const uint32_t tz = f >> AM_F_TZ_SHIFT;
-          if (tz) {  // the zone's wall clock instead of UTC's (SpecSchedule.Location)
-            const TickWords* z = p.tz_table + tz;
-            t_mi = z->minute; t_hr = z->hour; t_dm = z->dom; t_mo = z->month; t_dw = z->dow; t_s0 = z->sec0;
-          }
+          // the zone's wall clock instead of UTC's (SpecSchedule.Location) — behind a real call: inlined,
+          // ptxas turns the six table loads per record into predicated instructions that EVERY warp
+          // issues (+24 LDG, +40 address IMADs per warp: 84 -> 96 us per 10 M-record tick, r02_run5)
+          if (tz) due_cron = cron_matches_in_zone(p.tz_table + tz, miv, hrv, dmv, mov, dwv);
         }
-        // branch-free: every term is evaluated (no short-circuit control flow)
-        const bool fld = ((miv & t_mi) != 0) & ((hrv & t_hr) != 0) & ((mov & t_mo) != 0);
-        const bool dmm = (dmv & t_dm) != 0, dwm = (dwv & t_dw) != 0;
-        const bool star = ((dmv | dwv) >> 63) != 0;  // robfig dayMatches
-        due_cron = (t_s0 != 0) & fld & (star ? (dmm & dwm) : (dmm | dwm));
       }
       const bool is_iv = ((0x14u >> kind) & 1u) != 0;  // INTERVAL or CRON_EVERY
       const bool due = live && (is_iv ? due_iv : (kind == AM_KIND_CRON_SPEC && due_cron));
@@ -327,18 +337,31 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
                   ((live && kind == AM_KIND_PARSE_ERROR) ? AM_ACT_PARSE_ERROR : 0u);
       nfl[h][j] = f;
       nfa[h][j] = fav;
-      if (f & AM_F_CARRY_MASK) {  // a result applied at this tick's drain (apply_results_now_kernel): its action bits
-        act[h][j] |= carried_actions(f);
-        nfl[h][j] = f & ~AM_F_CARRY_MASK;
-        dirty[h] = true;
-      }
       if (stopped_now) {  // hcc.go:238-250: Status "Stopped", FinishedAt = now
-        nfl[h][j] |= AM_F_STOPPED_REPORTED;
+        nfl[h][j] = f | AM_F_STOPPED_REPORTED;
         nfa[h][j] = T;
         dirty[h] = true;
       }
       if (live && (pending || (CLOSED && due))) needy |= 1u << (2 * h + j);
       if (due) due_bits |= 1u << (2 * h + j);
+    }
+  }
+
+  // ---- results applied at this tick's drain (apply_results_now_kernel) left their action bits in the
+  //      flags' carry bits: emit and clear them.  Rare (a posted "Succeeded" carries nothing): one vote
+  //      per warp keeps the per-record form out of the common path.
+  if (__any_sync(kFull, (fl_or & AM_F_CARRY_MASK) != 0)) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const uint32_t f = j ? fl[h].y : fl[h].x;
+        if (f & AM_F_CARRY_MASK) {
+          act[h][j] |= carried_actions(f);
+          nfl[h][j] &= ~AM_F_CARRY_MASK;
+          dirty[h] = true;
+        }
+      }
     }
   }
 
@@ -893,6 +916,7 @@ constexpr uint32_t kRemedyBits = AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK;
 
 __global__ void mark_ops_kernel(uint32_t* marks, const uint32_t* __restrict__ op_idx,
                                 const uint32_t* __restrict__ op_arg, uint32_t n) {
+  pdl_wait();  // (launched with programmatic stream serialisation: nothing of the predecessor is touched before this)
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const uint32_t i = op_idx[k], arg = op_arg[k];
@@ -905,6 +929,7 @@ __global__ void mark_ops_kernel(uint32_t* marks, const uint32_t* __restrict__ op
 __global__ void apply_state_ops_kernel(DevCols c, const uint32_t* __restrict__ marks,
                                        const uint32_t* __restrict__ op_idx, const uint32_t* __restrict__ op_arg,
                                        const am_record_t* __restrict__ recs, uint32_t n) {
+  pdl_wait();  // (launched with programmatic stream serialisation: nothing of the predecessor is touched before this)
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const uint32_t i = op_idx[k], arg = op_arg[k];
@@ -926,6 +951,7 @@ __global__ void apply_state_ops_kernel(DevCols c, const uint32_t* __restrict__ m
 __global__ void apply_result_ops_kernel(uint32_t* flags, const uint32_t* __restrict__ marks,
                                         const uint32_t* __restrict__ op_idx, const uint32_t* __restrict__ op_arg,
                                         uint32_t n) {
+  pdl_wait();  // (launched with programmatic stream serialisation: nothing of the predecessor is touched before this)
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const uint32_t i = op_idx[k], arg = op_arg[k];
@@ -954,6 +980,7 @@ __global__ void apply_result_ops_kernel(uint32_t* flags, const uint32_t* __restr
 // without it, and a dense batch is cheaper as the sweep's streaming path.
 __global__ void apply_results_now_kernel(DevCols c, const uint32_t* __restrict__ op_idx, const uint32_t* __restrict__ op_arg,
                                          uint32_t n, int64_t T, unsigned long long* acc) {
+  pdl_wait();  // (launched with programmatic stream serialisation: nothing of the predecessor is touched before this)
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   constexpr uint32_t kPend = AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING;
   uint32_t res = 0;
@@ -993,6 +1020,7 @@ __global__ void apply_results_now_kernel(DevCols c, const uint32_t* __restrict__
 }
 
 __global__ void clear_marks_kernel(uint32_t* marks, const uint32_t* __restrict__ op_idx, uint32_t n) {
+  pdl_wait();  // (launched with programmatic stream serialisation: nothing of the predecessor is touched before this)
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const uint32_t i = op_idx[k];

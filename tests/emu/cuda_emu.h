@@ -30,6 +30,7 @@
 #define __global__
 #define __device__
 #define __forceinline__ inline
+#define __noinline__
 #define __shared__ static thread_local
 #define __launch_bounds__(...)
 #define __align__(n) __attribute__((aligned(n)))
