@@ -35,7 +35,7 @@
   } while (0)
 #else
 #define AM_LAUNCH(kernel, grid, block, stream, ...) ((void)(stream), emu::launch(kernel, dim3(grid), dim3(block), __VA_ARGS__))
-#define AM_LAUNCH_PDL(kernel, grid, block, stream, ...) AM_LAUNCH(kernel, grid, block, stream, __VA_ARGS__)
+#define AM_LAUNCH_PDL(kernel, grid, block, stream, ...) ((void)(stream), emu::launch(kernel, dim3(grid), dim3(block), __VA_ARGS__))
 #endif
 #endif
 #define AM_SWEEP_KERNEL(closed, masks) sweep_tick_kernel<closed, masks>  // one macro argument
