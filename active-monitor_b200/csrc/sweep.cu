@@ -152,10 +152,16 @@ struct am_sweep {
   uint32_t* marks = nullptr;  // [3 * cap_padded] per-slot {latest state op, latest phase, latest remedy phase}
   PinnedBuf pin_in;
   DevBuf dev_in;
-  // named time zones: a flattened copy of the process-wide registry (tz.h), refreshed when it grows
-  uint64_t tz_version = 0;
+  // named time zones: one UTC offset per registered zone (tz.h) on the device, refreshed when the
+  // registry grows or a tick leaves the window [tz_lo, tz_hi) in which no zone changes its offset
+  uint64_t tz_version = ~0ull;
   uint32_t tz_n = 0;  // zones + 1; 0 or 1 = nothing registered
-  DevBuf tz_descs, tz_trans, tz_off, tz_table;
+  int64_t tz_lo = 0, tz_hi = 0;
+  bool tz_aligned = true;  // every offset a whole number of minutes
+  DevBuf tz_off;
+  PinnedBuf tz_pin;
+  cudaEvent_t tz_copied = nullptr;
+  bool tz_copy_pending = false;
   std::string last_error;
   uint64_t launches = 0;
   double last_ms = -1.0;
@@ -374,25 +380,35 @@ struct ListOut {
   bool expand = true;
 };
 
-// Bring the device copy of the time-zone registry up to date (rare: only when a new zone appeared).
-int refresh_zones(am_sweep* h, cudaStream_t s) {
-  if (amsweep_tz::snapshot(nullptr, nullptr, nullptr) == h->tz_version) return AM_OK;
-  std::vector<amsweep_tz::ZoneDesc> descs;
-  std::vector<int64_t> trans;
-  std::vector<int32_t> off;
-  const uint64_t v = amsweep_tz::snapshot(&descs, &trans, &off);
-  AM_CUDA(h, cudaStreamSynchronize(s));  // earlier ticks may still read the old arrays
-  AM_CUDA(h, h->tz_descs.reserve(descs.size() * sizeof(amsweep_tz::ZoneDesc)));
-  AM_CUDA(h, h->tz_trans.reserve((trans.size() + 1) * 8));
-  AM_CUDA(h, h->tz_off.reserve((off.size() + 1) * 4));
-  AM_CUDA(h, h->tz_table.reserve((amsweep_tz::kMaxZones + 1) * sizeof(TickWords)));
-  AM_CUDA(h, cudaMemcpy(h->tz_descs.p, descs.data(), descs.size() * sizeof(amsweep_tz::ZoneDesc), cudaMemcpyHostToDevice));
-  if (!trans.empty()) {
-    AM_CUDA(h, cudaMemcpy(h->tz_trans.p, trans.data(), trans.size() * 8, cudaMemcpyHostToDevice));
-    AM_CUDA(h, cudaMemcpy(h->tz_off.p, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
-  }
-  h->tz_n = (uint32_t)descs.size();
+// The zones' UTC offsets at T on the device.  Per tick: one uncontended lock for the registry version
+// and two compares; the offsets themselves are recomputed (tz_eval.h, host) and copied — a few hundred
+// bytes — only when a zone was registered or T left the window in which no zone changes its offset.
+int refresh_zones(am_sweep* h, int64_t T, cudaStream_t s) {
+  if (amsweep_tz::snapshot(nullptr, nullptr, nullptr) == h->tz_version && T >= h->tz_lo && T < h->tz_hi) return AM_OK;
+  std::vector<int32_t> offs;
+  int64_t until = 0;
+  bool aligned = true;
+  const uint64_t v = amsweep_tz::offsets_at(T, &offs, &until, &aligned);
   h->tz_version = v;
+  h->tz_n = (uint32_t)offs.size();
+  h->tz_lo = T;
+  h->tz_hi = until;
+  h->tz_aligned = aligned;
+  if (h->tz_n <= 1) {  // nothing registered: every T is fine until the registry grows
+    h->tz_lo = INT64_MIN;
+    h->tz_hi = INT64_MAX;
+    return AM_OK;
+  }
+  const size_t bytes = (amsweep_tz::kMaxZones + 1) * sizeof(int32_t);
+  AM_CUDA(h, h->tz_off.reserve(bytes));
+  AM_CUDA(h, h->tz_pin.reserve(bytes));
+  if (!h->tz_copied) AM_CUDA(h, cudaEventCreateWithFlags(&h->tz_copied, cudaEventDisableTiming));
+  if (h->tz_copy_pending) AM_CUDA(h, cudaEventSynchronize(h->tz_copied));  // the previous copy has left the pinned array
+  memcpy(h->tz_pin.p, offs.data(), offs.size() * sizeof(int32_t));
+  // (stream-ordered after every earlier tick of the handle: none of them still reads the old offsets)
+  AM_CUDA(h, cudaMemcpyAsync(h->tz_off.p, h->tz_pin.p, offs.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  AM_CUDA(h, cudaEventRecord(h->tz_copied, s));
+  h->tz_copy_pending = true;
   return AM_OK;
 }
 
@@ -419,21 +435,10 @@ int launch_tick(am_sweep* h, int64_t T, uint32_t mode, const ListOut& o, cudaStr
   p.mode = mode;
   p.out = ts.out;
   p.acc = ts.acc;
-  {  // named time zones: T's wall clock per zone, computed on the device
-    const int rc = refresh_zones(h, s);
+  {  // named time zones: one UTC offset per zone, valid at T
+    const int rc = refresh_zones(h, T, s);
     if (rc != AM_OK) return rc;
-    if (h->tz_n > 1) {
-      TzTableParams z{};
-      z.descs = (const amsweep_tz::ZoneDesc*)h->tz_descs.p;
-      z.trans = (const int64_t*)h->tz_trans.p;
-      z.off = (const int32_t*)h->tz_off.p;
-      z.table = (TickWords*)h->tz_table.p;
-      z.T = T;
-      z.n = h->tz_n;
-      AM_LAUNCH_PDL(tz_table_kernel, (h->tz_n + 63) / 64, 64, s, z);
-      h->launches++;
-      p.tz_table = (const TickWords*)h->tz_table.p;
-    }
+    p.tz_off = h->tz_n > 1 ? (const int32_t*)h->tz_off.p : nullptr;
   }
   if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[0], s));
   // off the minute no 5-field schedule can fire: the mask columns are not read.  (A zone whose UTC
@@ -441,7 +446,7 @@ int launch_tick(am_sweep* h, int64_t T, uint32_t mode, const ListOut& o, cudaStr
   // boundary: every tick then reads the masks.)
   int64_t sec_of_min = T % 60;
   if (sec_of_min < 0) sec_of_min += 60;
-  const bool masks = sec_of_min == 0 || (mode & AM_SWEEP_FULL_SCAN) || (h->tz_n > 1 && !amsweep_tz::all_minute_aligned(T));
+  const bool masks = sec_of_min == 0 || (mode & AM_SWEEP_FULL_SCAN) || (h->tz_n > 1 && !h->tz_aligned);
   const bool closed = (mode & AM_SWEEP_CLOSED_LOOP) != 0;
   if (closed && masks) AM_LAUNCH_PDL(AM_SWEEP_KERNEL(true, true), p.n_tiles, kBlock, s, p);
   else if (closed) AM_LAUNCH_PDL(AM_SWEEP_KERNEL(true, false), p.n_tiles, kBlock, s, p);
@@ -687,7 +692,8 @@ void am_sweep_destroy(am_sweep_t* h) {
   if (h->h_stats) cudaFreeHost(h->h_stats);
   h->host_out.release();
   h->pin_in.release(); h->dev_in.release();
-  h->tz_descs.release(); h->tz_trans.release(); h->tz_off.release(); h->tz_table.release();
+  h->tz_off.release(); h->tz_pin.release();
+  if (h->tz_copied) cudaEventDestroy(h->tz_copied);
   if (h->ev_last) cudaEventDestroy(h->ev_last);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);

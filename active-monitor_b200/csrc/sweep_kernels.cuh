@@ -203,23 +203,15 @@ __device__ __forceinline__ bool cron_matches(const TickWords& t, uint64_t mi, ui
   const bool star = ((dm | dw) >> 63) != 0;  // robfig dayMatches
   return (t.sec0 != 0) & fld & (star ? (dmm & dwm) : (dmm | dwm));
 }
-__device__ __noinline__ bool cron_matches_in_zone(const TickWords* z, uint64_t mi, uint64_t hr, uint64_t dm, uint64_t mo,
-                                                  uint64_t dw) {
-  const TickWords t = *z;
+// A schedule bound to a named time zone ("CRON_TZ=Zone ...", robfig parser.go / hcc.go:253,
+// SpecSchedule.Location): the same match against the zone's wall clock, T + the zone's UTC offset broken
+// down into the one-hot words.  `tz_off` holds one offset per registered zone, valid for this tick (the
+// launcher refreshes it only when a tick leaves the window in which no zone changes its offset).  Rare
+// records, a few dozen instructions: kept out of line.
+__device__ __noinline__ bool cron_matches_in_zone(const int32_t* tz_off, uint32_t tz, int64_t T, uint64_t mi, uint64_t hr,
+                                                  uint64_t dm, uint64_t mo, uint64_t dw) {
+  const TickWords t = tick_words_from_unix(T + (int64_t)tz_off[tz]);
   return cron_matches(t, mi, hr, dm, mo, dw);
-}
-
-// The tick's wall clock in every registered time zone ("CRON_TZ=Zone ..." schedules, robfig
-// parser.go / hcc.go:253): one thread per zone evaluates the zone's UTC offset at T (transition
-// table, then the POSIX rule of the TZif footer: tz_eval.h) and writes T's LOCAL fields as the
-// one-hot words the sweep ANDs against the cron masks.  A few dozen threads, once per tick, only
-// when zones are registered.
-__global__ void tz_table_kernel(const TzTableParams p) {
-  pdl_wait();  // (launched with programmatic stream serialisation: nothing of the predecessor is touched before this)
-  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= p.n) return;
-  const int32_t off = k ? amsweep_tz::tz_zone_offset(p.descs[k], p.trans, p.off, p.T) : 0;
-  p.table[k] = tick_words_from_unix(p.T + off);
 }
 
 // ---------------------------------------------------------------------------
@@ -286,7 +278,7 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   const TickWords w = p.words;
   // named time zones are rare: one vote per warp decides whether the per-record zone lookup exists at all
   const uint32_t fl_or = fl[0].x | fl[0].y | fl[1].x | fl[1].y;
-  const bool warp_tz = MASKS && p.tz_table != nullptr && __any_sync(kFull, (fl_or >> AM_F_TZ_SHIFT) != 0);
+  const bool warp_tz = MASKS && p.tz_off != nullptr && __any_sync(kFull, (fl_or >> AM_F_TZ_SHIFT) != 0);
 
   uint32_t act[2][2];
   uint32_t res_lane = 0;  // 4 x 8-bit counts of results applied by this lane
@@ -324,10 +316,10 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
         due_cron = cron_matches(w, miv, hrv, dmv, mov, dwv);
         if (warp_tz) {  // warp-uniform: some record of this warp is bound to a named time zone
           const uint32_t tz = f >> AM_F_TZ_SHIFT;
-          // the zone's wall clock instead of UTC's (SpecSchedule.Location) — behind a real call: inlined,
-          // ptxas turns the six table loads per record into predicated instructions that EVERY warp
-          // issues (+24 LDG, +40 address IMADs per warp: 84 -> 96 us per 10 M-record tick, r02_run5)
-          if (tz) due_cron = cron_matches_in_zone(p.tz_table + tz, miv, hrv, dmv, mov, dwv);
+          // the zone's wall clock instead of UTC's — behind a real call: inlined, ptxas turned the zone
+          // lookup of all four records into predicated instructions that EVERY warp issues (+24 LDG,
+          // +40 address IMADs per warp: 84 -> 96 us per 10 M-record tick, profiles/r02_summary.md)
+          if (tz) due_cron = cron_matches_in_zone(p.tz_off, tz, T, miv, hrv, dmv, mov, dwv);
         }
       }
       const bool is_iv = ((0x14u >> kind) & 1u) != 0;  // INTERVAL or CRON_EVERY

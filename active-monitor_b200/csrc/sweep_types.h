@@ -93,17 +93,8 @@ struct SweepParams {
   uint32_t mode;
   TickOut out;
   unsigned long long* acc;   // [kNumAcc] statistics accumulators (zero on entry)
-  const TickWords* tz_table; // [zones + 1] T's LOCAL fields per registered time zone (entry 0 = UTC);
-                             // NULL when no zone is registered
-};
-
-struct TzTableParams {       // tz_table_kernel: one thread per zone
-  const amsweep_tz::ZoneDesc* descs;
-  const int64_t* trans;
-  const int32_t* off;
-  TickWords* table;
-  int64_t T;
-  uint32_t n;                // zones + 1
+  const int32_t* tz_off;     // [zones + 1] UTC offset (seconds east) of every registered time zone at T (entry 0 =
+                             // UTC); NULL when no zone is registered
 };
 
 struct ScanParams {

@@ -1,6 +1,7 @@
 // tz.cpp — TZif reader + POSIX TZ footer rules + the zone registry (see tz.h).
 #include "tz.h"
 
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -244,28 +245,56 @@ uint64_t snapshot(std::vector<ZoneDesc>* descs, std::vector<int64_t>* trans, std
   return g_version;
 }
 
-bool all_minute_aligned(int64_t utc) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  for (const auto& z : g_zones)
-    if (zone_offset(*z, utc) % 60) return false;
-  return true;
-}
-
 int count() {
   std::lock_guard<std::mutex> lk(g_mu);
   return (int)g_zones.size();
 }
 
-bool tick_words(int64_t utc, amsweep::TickWords* table) {
+namespace {
+// the next instant after `utc` at which zone_offset(z, .) may change (never later than the true one)
+int64_t next_change(const Zone& z, int64_t utc) {
+  const size_t n = z.trans.size();
+  if (n && utc < z.trans[n - 1]) {  // inside (or before) the transition table: the first transition after utc
+    size_t lo = 0, hi = n;          // first index with trans > utc
+    while (lo < hi) {
+      const size_t mid = (lo + hi) / 2;
+      if (z.trans[mid] > utc) hi = mid; else lo = mid + 1;
+    }
+    return z.trans[lo];
+  }
+  if (!z.has_footer || !z.has_dst) return INT64_MAX;
+  // the footer's rule instants, and the turn of the (standard-time) year at which tz_footer_offset
+  // switches to the next year's instants: years y-1 .. y+1 around utc
+  int64_t days, y;
+  int32_t sod, m, d;
+  split_days(utc + z.std_off, days, sod);
+  civil_from_days(days, y, m, d);
+  int64_t best = INT64_MAX;
+  for (int64_t yy = y - 1; yy <= y + 1; ++yy) {
+    const int64_t c[3] = {tz_rule_local_seconds(z.start, yy) - z.std_off, tz_rule_local_seconds(z.end, yy) - z.dst_off,
+                          days_from_civil(yy, 1, 1) * 86400 - z.std_off};
+    for (int64_t v : c)
+      if (v > utc && v < best) best = v;
+  }
+  return best;
+}
+}  // namespace
+
+uint64_t offsets_at(int64_t utc, std::vector<int32_t>* offs, int64_t* valid_until, bool* minute_aligned) {
   std::lock_guard<std::mutex> lk(g_mu);
+  offs->assign(g_zones.size() + 1, 0);
+  int64_t until = INT64_MAX;
   bool aligned = true;
-  table[0] = amsweep::tick_words_from_unix(utc);
   for (size_t k = 0; k < g_zones.size(); ++k) {
     const int32_t off = zone_offset(*g_zones[k], utc);
+    (*offs)[k + 1] = off;
     if (off % 60) aligned = false;
-    table[k + 1] = amsweep::tick_words_from_unix(utc + off);
+    const int64_t nc = next_change(*g_zones[k], utc);
+    if (nc < until) until = nc;
   }
-  return aligned;
+  *valid_until = until;
+  *minute_aligned = aligned;
+  return g_version;
 }
 
 }  // namespace amsweep_tz

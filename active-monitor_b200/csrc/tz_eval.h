@@ -1,6 +1,6 @@
-// tz_eval.h — UTC offset of a time zone at an instant, from a flattened view of its TZif data:
-// shared by the host registry (tz.cpp) and the device (tz_table_kernel in sweep_kernels.cuh),
-// so the per-tick zone table is computed where it is used — no host copy per tick.
+// tz_eval.h — UTC offset of a time zone at an instant, from a flattened view of its TZif data
+// (transition table, then the POSIX rule of the footer).  Host/device-neutral (AM_HD); used by the
+// registry (tz.cpp), which hands the sweep one offset per zone and the window in which they hold.
 #pragma once
 #include <stdint.h>
 

@@ -151,7 +151,7 @@ T0 = 1789982100
 @pytest.mark.gpu
 def test_zone_bound_checks_fire_on_their_zones_wall_clock(am, orc):
     """One record per KAT row, ticked at the row's instant: the device evaluates matches(T) against the
-    zone table it computed itself (tz_table_kernel), and equals the oracle (libc)."""
+    zone offsets the launcher keeps on the device, and equals the oracle (libc)."""
     recs = []
     for spec, _, _ in KAT:
         rc, r = am.classify(cron=spec, finished_at=T0 - 5)
@@ -202,3 +202,38 @@ def test_population_with_zones_equals_oracle_at_local_midnights(am, orc, gen):
         dev = s.read_range(0, n)
         for name in am.COLUMN_NAMES:
             np.testing.assert_array_equal(dev[name], orac[name], err_msg=name)
+
+
+@pytest.mark.gpu
+def test_consecutive_ticks_across_daylight_transitions(am, orc):
+    """The device keeps one UTC offset per zone and the launcher refreshes them only when a tick leaves the
+    window in which no zone changes its offset: tick second by second (and in jumps) across the 2026/2027
+    transitions of three zones — among them Lord Howe's half-hour shift — with every-minute schedules bound
+    to them; each tick's list must equal the oracle's (libc zones), in particular in the second of the
+    transition itself and the one before it."""
+    zones = ["America/New_York", "Europe/Paris", "Australia/Lord_Howe"]
+    specs = [f"CRON_TZ={z} {m} {h} * * *" for z in zones for h in (1, 2, 3) for m in (0, 30)]
+    specs += ["0 6 * * *", "0 1 * * *"]  # plain UTC neighbours
+    recs = [am.classify(cron=sp, finished_at=T0 - 5)[1] for sp in specs]
+    cols = am.records_to_columns(np.concatenate(recs))
+    ocols = {k: v.copy() for k, v in cols.items()}
+    for k, sp in enumerate(specs):
+        rc, oc, _ = orc.cron_parse(sp)
+        assert rc == 0
+        ocols["flags"][k] = (int(ocols["flags"][k]) & 0x00FFFFFF) | (oc.tz_id << 24)
+    edges = [utc(2026, 11, 1, 6, 0), utc(2027, 3, 14, 7, 0),      # New York: EDT -> EST, EST -> EDT
+             utc(2026, 10, 25, 1, 0), utc(2027, 3, 28, 1, 0),     # Paris: CEST -> CET, CET -> CEST
+             utc(2026, 10, 3, 15, 30), utc(2027, 4, 3, 15, 0)]    # Lord Howe: +10:30 -> +11, +11 -> +10:30
+    fired = 0
+    with am.Sweep(capacity=len(specs)) as s:
+        s.load_range(0, cols)
+        for e in edges:
+            # hours around the edge on the minute (the schedules can fire there), then the edge second by second
+            ticks = [e - 3600, e - 1800, e - 60] + list(range(e - 3, e + 4)) + [e + 60, e + 1800, e + 3600, e - 7200, e]
+            for T in ticks:
+                gi, ga, _ = s.tick(T, mode=am.SWEEP_FULL_SCAN)
+                wi, wa, _ = orc.sweep(ocols, T, am.SWEEP_FULL_SCAN)
+                np.testing.assert_array_equal(gi, wi, err_msg=f"edge {e} tick {T}")
+                np.testing.assert_array_equal(ga, wa)
+                fired += len(gi)
+    assert fired > 20
