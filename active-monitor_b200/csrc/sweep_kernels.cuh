@@ -754,38 +754,60 @@ __global__ void __launch_bounds__(kExpandThreads, 8) expand_kernel(const ExpandP
   const uint64_t pos_base = start - sh;  // multiple of 4
   const uint32_t n_stage = sh + cnt;
   unsigned long long cx = 0;
-  for (uint32_t j = (uint32_t)tid; 4u * j < n_stage; j += blockDim.x) {
+  // any quad, entry by entry: the ragged first / last quad of the group, the end of a short buffer
+  auto write_ragged = [&](uint32_t j) {
     const uint2 o2 = *reinterpret_cast<const uint2*>(&s_off[4u * j]);
     const uint32_t a4 = *reinterpret_cast<const uint32_t*>(&s_act[4u * j]);
     const uint32_t off[4] = {o2.x & 0xFFFFu, o2.x >> 16, o2.y & 0xFFFFu, o2.y >> 16};
     const uint64_t pos0 = pos_base + 4ull * j;
     const uint32_t k_lo = j == 0 ? sh : 0u;
     const uint32_t k_hi = n_stage - 4u * j < 4u ? n_stage - 4u * j : 4u;
-    if (stats) {
 #pragma unroll
-      for (uint32_t k = 0; k < 4; ++k)
-        if (k >= k_lo && k < k_hi) cx ^= sbase + off[k];
+    for (uint32_t k = 0; k < 4; ++k) {
+      if (k < k_lo || k >= k_hi) continue;
+      if (stats) cx ^= sbase + off[k];
+      const uint64_t pos = pos0 + k;
+      if (pos >= p.cap) continue;
+      if (p.idx_bytes == 4) reinterpret_cast<uint32_t*>(p.out_idx)[pos] = (uint32_t)(obase + off[k]);
+      else reinterpret_cast<uint64_t*>(p.out_idx)[pos] = obase + off[k];
+      p.out_act[pos] = (uint8_t)(a4 >> (8 * k));
     }
-    if (k_lo == 0 && k_hi == 4 && pos0 + 4 <= p.cap) {
+  };
+  // Interior quads [q_lo, q_hi): all four slots belong to this group and fit the caller's buffer — no
+  // per-entry predicates (they were two thirds of this loop's 71 instructions per quad).  The index
+  // checksum runs on the low words: a group's indices share their high word unless the group straddles
+  // a multiple of 2^32 (then every quad takes the entry-by-entry form), and four equal high words cancel.
+  const uint32_t q_lo = sh ? 1u : 0u;
+  uint32_t q_hi = n_stage >> 2;
+  {
+    const uint64_t cap_q = p.cap >> 2, base_q = pos_base >> 2;
+    const uint64_t room = cap_q > base_q ? cap_q - base_q : 0;
+    if (room < q_hi) q_hi = (uint32_t)room;
+    if ((uint32_t)sbase > 0xFFFFFFFFu - kGroupRecords) q_hi = q_lo;  // (uniform per CTA)
+    if (q_hi < q_lo) q_hi = q_lo;
+  }
+  const uint32_t n_quads = (n_stage + 3u) >> 2;
+  if (q_lo && (uint32_t)tid == 0u) write_ragged(0);
+  for (uint32_t j = q_hi + (uint32_t)tid; j < n_quads; j += blockDim.x) write_ragged(j);
+  {
+    const uint32_t b32 = (uint32_t)obase, s32 = (uint32_t)sbase;
+    uint32_t cx32 = 0;
+    for (uint32_t j = q_lo + (uint32_t)tid; j < q_hi; j += blockDim.x) {
+      const uint2 o2 = *reinterpret_cast<const uint2*>(&s_off[4u * j]);
+      const uint32_t a4 = *reinterpret_cast<const uint32_t*>(&s_act[4u * j]);
+      const uint32_t o0 = o2.x & 0xFFFFu, o1 = o2.x >> 16, o2_ = o2.y & 0xFFFFu, o3 = o2.y >> 16;
+      const uint64_t q = (pos_base >> 2) + j;
       if (p.idx_bytes == 4) {
-        const uint32_t b32 = (uint32_t)obase;
-        reinterpret_cast<uint4*>(p.out_idx)[pos0 >> 2] = make_uint4(b32 + off[0], b32 + off[1], b32 + off[2], b32 + off[3]);
+        reinterpret_cast<uint4*>(p.out_idx)[q] = make_uint4(b32 + o0, b32 + o1, b32 + o2_, b32 + o3);
       } else {
-        ulonglong2* d = reinterpret_cast<ulonglong2*>(p.out_idx) + (pos0 >> 1);
-        d[0] = make_ulonglong2(obase + off[0], obase + off[1]);
-        d[1] = make_ulonglong2(obase + off[2], obase + off[3]);
+        ulonglong2* d = reinterpret_cast<ulonglong2*>(p.out_idx) + 2 * q;
+        d[0] = make_ulonglong2(obase + o0, obase + o1);
+        d[1] = make_ulonglong2(obase + o2_, obase + o3);
       }
-      reinterpret_cast<uint32_t*>(p.out_act)[pos0 >> 2] = a4;
-    } else {  // ragged first / last quad of the group, or the end of a short buffer
-#pragma unroll
-      for (uint32_t k = 0; k < 4; ++k) {
-        const uint64_t pos = pos0 + k;
-        if (k < k_lo || k >= k_hi || pos >= p.cap) continue;
-        if (p.idx_bytes == 4) reinterpret_cast<uint32_t*>(p.out_idx)[pos] = (uint32_t)(obase + off[k]);
-        else reinterpret_cast<uint64_t*>(p.out_idx)[pos] = obase + off[k];
-        p.out_act[pos] = (uint8_t)(a4 >> (8 * k));
-      }
+      reinterpret_cast<uint32_t*>(p.out_act)[q] = a4;
+      cx32 ^= (s32 + o0) ^ (s32 + o1) ^ (s32 + o2_) ^ (s32 + o3);
     }
+    if (stats) cx ^= (unsigned long long)cx32;
   }
   // statistics: warp -> CTA -> global RED
   if (stats) {

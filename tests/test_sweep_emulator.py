@@ -86,6 +86,27 @@ def test_full_scan_mode_and_shard_base(am, orc, gen):
             assert got[0].min() >= base
 
 
+@pytest.mark.parametrize("base", [(1 << 32) - 5000, (1 << 32) - 8192 - 3, (3 << 32) - 20_001, 8192 * 1000 + 4097])
+def test_index_checksums_where_a_group_straddles_2_to_the_32(am, orc, gen, base):
+    """expand_kernel checksums a group's indices on their low words (the high word is shared) unless the
+    group straddles a multiple of 2^32; statistics (idx_xor, idx_sum), list and short-buffer behaviour
+    must equal the oracle's on both sides of that rule."""
+    n = 20_000
+    prod, orac = _gen_pair(gen, am, orc, 2, 7, n, T0, first=base)
+    with emu_sweep.EmuSweep(n, shard_base=base) as s:
+        s.load_range(0, prod)
+        got = s.tick(T0)
+        want = orc.sweep(orac, T0, shard_base=base)
+        _assert_tick_equal(am, got, want, s, orac, n, f"base={base}")
+        assert len(got[0]) > 5000
+        # a short caller buffer: the statistics still describe the whole tick, the list is its prefix
+        gi, ga, gs = s.tick(T0 + 60, cap=1001)
+        wi, wa, ws = orc.sweep(orac, T0 + 60, shard_base=base)
+        assert gs == ws
+        np.testing.assert_array_equal(gi, wi[:1001])
+        np.testing.assert_array_equal(ga, wa[:1001])
+
+
 @pytest.mark.parametrize("config", [5, 55])
 def test_closed_loop_many_ticks(am, orc, gen, config):
     n, seed = 6000, 5

@@ -85,7 +85,58 @@ def pre_reload():
     s.load_range(0, cols)
 
 
+import threading
+import time
+
+
+def pre_restore_idle(ms):
+    def f():
+        restore(); torch.cuda.synchronize(); time.sleep(ms * 1e-3)
+    return f
+
+
+def clocks_while(fn, seconds=1.0):
+    """SM clock / power / throttle reasons polled through NVML (~1 kHz) while `fn` runs in a loop"""
+    import pynvml
+    pynvml.nvmlInit()
+    hnd = pynvml.nvmlDeviceGetHandleByIndex(0)
+    smp, stop = [], threading.Event()
+
+    def poll():
+        while not stop.is_set():
+            smp.append((pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM), pynvml.nvmlDeviceGetPowerUsage(hnd) / 1000.0,
+                        pynvml.nvmlDeviceGetCurrentClocksEventReasons(hnd)))
+            time.sleep(0.001)
+    th = threading.Thread(target=poll)
+    th.start()
+    t0, times = time.time(), []
+    while time.time() - t0 < seconds:
+        times.append(fn())
+    torch.cuda.synchronize()
+    stop.set(); th.join()
+    mhz = sorted(x[0] for x in smp)
+    reasons = 0
+    for x in smp:
+        reasons |= x[2]
+    return {"samples": len(smp), "sm_mhz_min": mhz[0], "sm_mhz_median": mhz[len(mhz) // 2], "sm_mhz_max": mhz[-1],
+            "power_w_max": round(max(x[1] for x in smp), 1), "reasons_or": hex(reasons),
+            "sweep_us_median": round(statistics.median(times[3:]), 1) if len(times) > 3 else None}
+
+
+def loop_dense():
+    restore()
+    return tick()[0] * 1e3
+
+
+def loop_plain():
+    return tick()[0] * 1e3
+
+
 out = {"what": "sweep_tick_kernel<0,1> on 10 M config-3 records, CUDA events, by what ran before it",
+       "restore_sync_idle_2ms": run(pre_restore_idle(2)),
+       "restore_sync_idle_20ms": run(pre_restore_idle(20)),
+       "restore_sync_idle_200ms": run(pre_restore_idle(200), 8),
+       "clocks_back_to_back_dense": clocks_while(loop_dense),
        "reload_columns_from_host": run(pre_reload, 6),
        "restore_d2d": run(pre_restore),
        "restore_d2d_then_sync": run(pre_restore_sync),
@@ -93,4 +144,5 @@ out = {"what": "sweep_tick_kernel<0,1> on 10 M config-3 records, CUDA events, by
        "restore_then_write_256MB": run(pre_restore_writeflush)}
 # the same tick once the results are applied (nothing pending): the sparse shape
 out["no_pending_results"] = run(lambda: None)
+out["clocks_back_to_back_plain"] = clocks_while(loop_plain)
 print(json.dumps(out))
