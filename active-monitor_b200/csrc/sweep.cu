@@ -953,11 +953,46 @@ int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint3
   h->seed = seed;
   am_tick_stats_t* d_stats = nullptr;
   AM_CUDA(h, cudaMalloc((void**)&d_stats, n_ticks * sizeof(am_tick_stats_t)));
+  const bool blocked = (mode & AM_SWEEP_BLOCKED) != 0 && h->n_records != 0;
+  if (blocked) {  // the block kernel accumulates into the rows
+    if (cudaError_t e = cudaMemsetAsync(d_stats, 0, n_ticks * sizeof(am_tick_stats_t), h->stream); e != cudaSuccess) {
+      h->last_error = cudaGetErrorString(e);
+      cudaFree(d_stats);
+      return AM_E_DEVICE;
+    }
+  }
   if (cudaError_t e = cudaEventRecord(h->ev0, h->stream); e != cudaSuccess) {
     h->last_error = cudaGetErrorString(e);
     rc = AM_E_DEVICE;
   }
-  for (uint64_t k = 0; k < n_ticks && rc == AM_OK; ++k) {
+  // Temporal blocking (sweep_block.cuh): up to kMaxBlockTicks ticks per pass over the columns.  A block
+  // never spans an instant at which a registered zone changes its UTC offset (the kernel holds one
+  // offset per zone for the whole block).
+  uint64_t block_ticks = kMaxBlockTicks;
+  if (const char* e = getenv("AMSWEEP_BLOCK_TICKS")) { long v = atol(e); if (v >= 1 && v <= kMaxBlockTicks) block_ticks = (uint64_t)v; }
+  for (uint64_t k = 0; blocked && k < n_ticks && rc == AM_OK;) {
+    const int64_t T = unix_sec0 + (int64_t)k;
+    rc = refresh_zones(h, T, h->stream);
+    if (rc != AM_OK) break;
+    uint64_t K = n_ticks - k < block_ticks ? n_ticks - k : block_ticks;
+    if (h->tz_n > 1 && h->tz_hi < T + (int64_t)K) K = (uint64_t)(h->tz_hi - T);  // (tz_hi > T after the refresh)
+    BlockParams b{};
+    b.c = h->cols;
+    b.n_records = h->n_records;
+    b.shard_base = h->shard_base;
+    b.seed = h->seed;
+    b.T0 = T;
+    b.K = (uint32_t)K;
+    b.tz_off = h->tz_n > 1 ? (const int32_t*)h->tz_off.p : nullptr;
+    b.stats = reinterpret_cast<unsigned long long*>(d_stats + k);
+    const unsigned grid = (unsigned)((h->n_records + kBlockRecords - 1) / kBlockRecords);
+    if (mode & AM_SWEEP_CLOSED_LOOP) AM_LAUNCH(sweep_block_kernel<true>, grid, kBlockThreads, h->stream, b);
+    else AM_LAUNCH(sweep_block_kernel<false>, grid, kBlockThreads, h->stream, b);
+    h->launches++;
+    if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) { h->last_error = cudaGetErrorString(e); rc = AM_E_DEVICE; }
+    k += K;
+  }
+  for (uint64_t k = 0; !blocked && k < n_ticks && rc == AM_OK; ++k) {
     ListOut o;
     o.idx = h->due_idx[k & 1];
     o.act = h->due_action[k & 1];
@@ -973,6 +1008,8 @@ int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint3
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, h->ev0, h->ev1);
     if (e != cudaSuccess) { h->last_error = cudaGetErrorString(e); rc = AM_E_DEVICE; }
     else h->last_ms = ms;
+    if (blocked && rc == AM_OK)
+      for (uint64_t k = 0; k < n_ticks; ++k) stats_out[k].n_records = h->n_records;
   }
   cudaFree(d_stats);
   return rc;

@@ -1,0 +1,212 @@
+// sweep_block.cuh — K consecutive one-second ticks per pass over the columns ("temporal blocking",
+// SURVEY §7 step 9; the timer-wheel reading of §8f-1 / hcc.go:751).
+//
+// am_sweep_run_ticks streams seconds back to back (BASELINE config 5: one simulated day = 86 400 ticks).
+// With one sweep per tick every tick re-reads 16..56 B per record to find the ~4 % that are due.  But
+// nothing reaches a record from outside between the ticks of such a run, so its whole future inside a
+// block of K ticks follows from its own columns: this kernel loads a record ONCE, then steps it from
+// event to event in registers — the reference's own shape, a timer per HealthCheck (time.AfterFunc,
+// hcc.go:751) instead of a scan per second:
+//
+//   interval / "@every" check   next event = finishedAt + repeatAfterSec (hcc.go:264), every tick while no
+//                               timer is armed (controller restart, hcc.go:161)
+//   5-field cron                next event = the next tick whose LOCAL second is 0 (robfig activates on
+//                               the minute; the zone's offset decides which UTC second that is)
+//   parse error                 every tick (hcc.go:254-257: warning + requeue)
+//   stopped                     once (hcc.go:238-250)
+//   posted result / carry bits  the first tick of the block
+//
+// and at an event tick evaluates EXACTLY what sweep_tick_kernel evaluates for that (record, tick) —
+// same ladder, same apply_result, same closed-loop outcome key — so the per-tick statistics and the
+// columns after the block are bit-identical to K single ticks (tests: run_ticks blocked == unblocked ==
+// oracle).  Work is O(events), not O(records x ticks); the columns are read and written once per K
+// ticks.  What it does NOT produce is the per-tick (index, action) lists: a run of ticks publishes
+// per-tick statistics (counts, action counts, index checksums — am_tick_stats_t), which is all
+// am_sweep_run_ticks ever returned to the host.  Reported separately from the K = 1 roofline number.
+#pragma once
+
+namespace amsweep {
+
+constexpr int kMaxBlockTicks = 64;
+constexpr int kBlockThreads = 256;
+constexpr int kBlockRecords = 2 * kBlockThreads;  // two adjacent records per thread
+
+struct BlockParams {
+  DevCols c;
+  uint64_t n_records, shard_base, seed;
+  int64_t T0;                  // first tick of the block
+  uint32_t K;                  // ticks in the block, <= kMaxBlockTicks
+  const int32_t* tz_off;       // per-zone UTC offsets valid for the whole block (NULL: no zone registered)
+  unsigned long long* stats;   // K rows of 16 accumulators (am_tick_stats_t layout), zero on entry
+};
+
+// first tick index u > t at which the LOCAL second (UTC + off) is 0
+__device__ __forceinline__ int64_t next_local_minute(int64_t T0, int64_t t, int32_t off) {
+  int64_t m = (T0 + t + 1 + (int64_t)off) % 60;
+  if (m < 0) m += 60;
+  return t + 1 + (m ? 60 - m : 0);
+}
+
+template <bool CLOSED>
+__global__ void __launch_bounds__(kBlockThreads) sweep_block_kernel(const BlockParams p) {
+  // per-tick statistics of this CTA's 512 records: [0] emitted, [1..8] action bits, [9..12] results
+  __shared__ uint32_t s_cnt[kMaxBlockTicks][13];
+  __shared__ uint32_t s_sum[kMaxBlockTicks];     // sum of CTA-local offsets of the emitted records
+  __shared__ uint32_t s_xor[kMaxBlockTicks][2];  // xor of the emitted global indices
+  const int tid = threadIdx.x;
+  for (int k = tid; k < kMaxBlockTicks * 13; k += kBlockThreads) (&s_cnt[0][0])[k] = 0;
+  for (int k = tid; k < kMaxBlockTicks; k += kBlockThreads) { s_sum[k] = 0; s_xor[k][0] = 0; s_xor[k][1] = 0; }
+  __syncthreads();
+
+  const uint64_t cta_base = (uint64_t)blockIdx.x * kBlockRecords;
+  const uint32_t loc0 = 2u * (uint32_t)tid;
+  const uint64_t i0 = cta_base + loc0;  // columns are padded to whole tiles; slots past n_records are tombstones
+  const int64_t K = (int64_t)p.K;
+  constexpr uint32_t kPend = AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING;
+
+  const uint2 fl2 = ld_stream(reinterpret_cast<const uint2*>(p.c.flags + i0));
+  const int2 ras2 = ld_stream(reinterpret_cast<const int2*>(p.c.ras + i0));
+  const longlong2 fa2 = ld_stream(reinterpret_cast<const longlong2*>(p.c.finished_at + i0));
+
+#pragma unroll 1
+  for (int j = 0; j < 2; ++j) {
+    const uint64_t i = i0 + (uint64_t)j;
+    uint32_t f = j ? fl2.y : fl2.x;
+    const int32_t rasv = j ? ras2.y : ras2.x;
+    int64_t fa = j ? fa2.y : fa2.x;
+    const uint32_t kind = f & AM_KIND_MASK;
+    const bool live = ((0x3Eu >> kind) & 1u) && !(f & AM_F_TOMBSTONE);
+    if (!live) continue;  // tombstones, NO_RESOURCE (hcc.go:227), host-fallback: never evaluated
+    const bool is_iv = ((0x14u >> kind) & 1u) != 0;  // INTERVAL or CRON_EVERY
+    const bool is_cron = kind == AM_KIND_CRON_SPEC;
+    int32_t zoff = 0;
+    uint64_t mi = 0, hr = 0, dm = 0, mo = 0, dw = 0;
+    if (is_cron) {
+      const uint32_t tz = f >> AM_F_TZ_SHIFT;
+      if (tz && p.tz_off) zoff = p.tz_off[tz];
+      mi = ld_stream(p.c.minute + i); hr = ld_stream(p.c.hour + i); dm = ld_stream(p.c.dom + i);
+      mo = ld_stream(p.c.month + i); dw = ld_stream(p.c.dow + i);
+    }
+    // remedy / counter state: every due record needs it in closed loop, a posted result in open loop
+    RecState s{};
+    const bool with_state = CLOSED || (f & kPend) != 0;
+    if (with_state) {
+      s.limit = ld_stream(p.c.runs_limit + i); s.reset = ld_stream(p.c.reset_interval + i);
+      s.s = ld_stream(p.c.success + i); s.f = ld_stream(p.c.failed + i);
+      s.rs = ld_stream(p.c.remedy_success + i); s.rf = ld_stream(p.c.remedy_failed + i);
+      s.rt = ld_stream(p.c.remedy_total + i); s.rfa = ld_stream(p.c.remedy_finished_at + i);
+    }
+    const RecState s0 = s;
+    const uint32_t f0 = f;
+    const int64_t fa0 = fa;
+
+    auto next_event = [&](int64_t t) -> int64_t {  // the first tick index > t at which this record can act
+      if (kind == AM_KIND_PARSE_ERROR) return t + 1;
+      if (kind == AM_KIND_STOPPED) return (f & AM_F_STOPPED_REPORTED) ? K : t + 1;
+      if (is_iv) {
+        if (!(f & AM_F_TIMER_ARMED)) return t + 1;  // no timer: the reference submits on every pass
+        const int64_t d = fa + (int64_t)rasv - p.T0;  // elapsed >= ras  <=>  tick index >= d
+        return d > t + 1 ? d : t + 1;
+      }
+      return next_local_minute(p.T0, t, zoff);  // 5-field schedule
+    };
+
+    int64_t t = (f & (kPend | AM_F_CARRY_MASK)) ? 0 : next_event(-1);
+    while (t < K) {
+      const int64_t T = p.T0 + t;
+      // ---- exactly sweep_tick_kernel's decision for (record, T) ----
+      const bool has_result = (f & (AM_F_PENDING_OK | AM_F_PENDING_FAIL)) != 0;
+      const bool pending = (f & kPend) != 0;
+      const int64_t fa_eff = has_result ? T : fa;
+      const int64_t elapsed = (int64_t)((uint64_t)T - (uint64_t)fa_eff);
+      const bool armed = has_result || (f & AM_F_TIMER_ARMED) != 0;
+      const bool due_iv = !((elapsed < (int64_t)rasv) & armed);
+      bool due_cron = false;
+      if (is_cron) {
+        const TickWords w = tick_words_from_unix(T + (int64_t)zoff);
+        due_cron = cron_matches(w, mi, hr, dm, mo, dw);
+      }
+      const bool due = is_iv ? due_iv : (is_cron && due_cron);
+      const bool stopped_now = kind == AM_KIND_STOPPED && !(f & AM_F_STOPPED_REPORTED);
+      uint32_t act = (due ? AM_ACT_SUBMIT_HC : 0u) | (stopped_now ? AM_ACT_STOPPED : 0u) |
+                     (kind == AM_KIND_PARSE_ERROR ? AM_ACT_PARSE_ERROR : 0u);
+      if (f & AM_F_CARRY_MASK) {
+        act |= carried_actions(f);
+        f &= ~AM_F_CARRY_MASK;
+      }
+      if (stopped_now) {  // hcc.go:238-250
+        f |= AM_F_STOPPED_REPORTED;
+        fa = T;
+      }
+      uint32_t res = 0;
+      if (pending || (CLOSED && due)) {
+        s.flags = f;
+        s.fa = fa;
+        uint32_t a = apply_result(s, T, res);
+        if (CLOSED && due) {
+          const uint64_t key = outcome_key(p.seed, p.shard_base + i, (uint64_t)T);
+          const uint32_t failp = (s.flags >> AM_F_FAILP_SHIFT) & 0xFFu;
+          const bool fail = (uint32_t)(key & 0xFF) < failp;
+          const bool rem_ok = (uint32_t)((key >> 8) & 0xFF) < 179u;
+          s.flags |= (fail ? AM_F_PENDING_FAIL : AM_F_PENDING_OK) | AM_F_REMEDY_PENDING | (rem_ok ? AM_F_REMEDY_OUTCOME_OK : 0u);
+          a |= apply_result(s, T, res);
+        }
+        act |= a;
+        f = s.flags;
+        fa = s.fa;
+      }
+      // ---- this tick's statistics (what expand_kernel derives from the emitted list) ----
+      if (act) {
+        atomicAdd(&s_cnt[t][0], 1u);
+        uint32_t bits = act;
+        while (bits) {
+          const int b = __ffs((int)bits) - 1;
+          bits &= bits - 1u;
+          atomicAdd(&s_cnt[t][1 + b], 1u);
+        }
+        const uint64_t g = p.shard_base + i;
+        atomicXor(&s_xor[t][0], (uint32_t)g);
+        atomicXor(&s_xor[t][1], (uint32_t)(g >> 32));
+        atomicAdd(&s_sum[t], loc0 + (uint32_t)j);
+      }
+      if (res) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if ((res >> (8 * q)) & 0xFFu) atomicAdd(&s_cnt[t][9 + q], (res >> (8 * q)) & 0xFFu);
+      }
+      t = next_event(t);
+    }
+
+    // ---- write back what changed ----
+    if (f != f0) st_stream(p.c.flags + i, f);
+    if (fa != fa0) st_stream(p.c.finished_at + i, fa);
+    if (with_state) {
+      if (s.s != s0.s) st_stream(p.c.success + i, s.s);
+      if (s.f != s0.f) st_stream(p.c.failed + i, s.f);
+      if (s.rs != s0.rs) st_stream(p.c.remedy_success + i, s.rs);
+      if (s.rf != s0.rf) st_stream(p.c.remedy_failed + i, s.rf);
+      if (s.rt != s0.rt) st_stream(p.c.remedy_total + i, s.rt);
+      if (s.rfa != s0.rfa) st_stream(p.c.remedy_finished_at + i, s.rfa);
+    }
+  }
+
+  // ---- CTA -> global: one RED per non-zero (tick, field) ----
+  __syncthreads();
+  const unsigned long long gbase = (unsigned long long)(p.shard_base + cta_base);
+  for (uint32_t k = (uint32_t)tid; k < p.K * 16u; k += kBlockThreads) {
+    const uint32_t t = k >> 4, fld = k & 15u;
+    unsigned long long* dst = p.stats + (size_t)t * kNumAcc + fld;
+    if (fld >= 1 && fld <= 13) {
+      const uint32_t v = s_cnt[t][fld - 1];
+      if (v) atomicAdd(dst, (unsigned long long)v);
+    } else if (fld == 14) {
+      const unsigned long long x = ((unsigned long long)s_xor[t][1] << 32) | s_xor[t][0];
+      if (x) atomicXor(dst, x);
+    } else if (fld == 15) {
+      const uint32_t cnt = s_cnt[t][0];
+      if (cnt) atomicAdd(dst, (unsigned long long)cnt * gbase + s_sum[t]);
+    }
+  }
+}
+
+}  // namespace amsweep

@@ -1060,3 +1060,5 @@ __global__ void gather_records_kernel(DevCols c, const uint32_t* __restrict__ id
 }
 
 }  // namespace amsweep
+
+#include "sweep_block.cuh"

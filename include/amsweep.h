@@ -233,6 +233,12 @@ typedef struct am_tick_stats {
                                      with its preset outcome     */
 #define AM_SWEEP_FULL_SCAN 0x2u   /* read every schedule column even on ticks
                                      where no 5-field cron can fire (sec!=0)  */
+#define AM_SWEEP_BLOCKED 0x4u     /* am_sweep_run_ticks only: temporal blocking.  Blocks of up to 64
+                                     consecutive ticks are evaluated in one pass over the columns,
+                                     every record stepped from event to event (its next repeat timer,
+                                     hcc.go:751; its next cron minute) — per-tick statistics and the
+                                     columns afterwards are identical to tick-by-tick evaluation, but
+                                     no per-tick lists are produced                                */
 
 /* One shard of the record array on one CUDA device.  `capacity` slots are
  * allocated up front; `shard_base` is added to local indices wherever a
@@ -325,7 +331,8 @@ int am_sweep_tick_shard(am_sweep_t*, int64_t unix_sec, uint32_t mode, void* cuda
 /* Streaming: n_ticks consecutive one-second ticks starting at unix_sec0,
  * back-to-back on the device (BASELINE config 5).  Per-tick stats are written
  * to stats_out[0..n_ticks) (host).  Emitted lists go to an HBM ring and are
- * not copied to the host.  `seed` keys the closed-loop outcome sequence. */
+ * not copied to the host (with AM_SWEEP_BLOCKED there are none: see above).
+ * `seed` keys the closed-loop outcome sequence. */
 int am_sweep_run_ticks(am_sweep_t*, int64_t unix_sec0, uint64_t n_ticks, uint32_t mode,
                        uint64_t seed, am_tick_stats_t* stats_out);
 

@@ -247,6 +247,7 @@ static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline uint32_t atomicOr(uint32_t* p, uint32_t v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
 static inline uint32_t atomicAnd(uint32_t* p, uint32_t v) { return __atomic_fetch_and(p, v, __ATOMIC_SEQ_CST); }
+static inline uint32_t atomicXor(uint32_t* p, uint32_t v) { return __atomic_fetch_xor(p, v, __ATOMIC_SEQ_CST); }
 
 static inline void st_release_sys(unsigned long long* p, unsigned long long v) {
   emu::jitter();

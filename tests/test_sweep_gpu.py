@@ -255,6 +255,43 @@ def test_run_ticks_streaming_matches_single_ticks(am, orc, gen):
             np.testing.assert_array_equal(dev[name], orac[name], err_msg=name)
 
 
+@pytest.mark.parametrize("config,closed,start,nt,block", [
+    (5, True, -30, 200, 0),      # config-2 mix (cron + zones + intervals), closed loop, three minute boundaries
+    (55, True, -75, 160, 7),     # remedy mix, closed loop, short blocks
+    (3, False, -10, 90, 0),      # open loop: posted results and remedy gates at the first tick, then unarmed checks every tick
+    (2, False, 45, 70, 64),      # open loop config 2
+    (5, True, 0, 1, 0),          # a single tick
+])
+def test_run_ticks_blocked_equals_the_oracle_tick_by_tick(am, orc, gen, monkeypatch, config, closed, start, nt, block):
+    """AM_SWEEP_BLOCKED: up to 64 ticks per pass over the columns, every record stepped from event to event
+    in registers (sweep_block.cuh).  Per-tick statistics — counts, action counts, index checksums, result
+    counters — and every column afterwards must equal the oracle's tick-by-tick evaluation, and the
+    library's own unblocked run."""
+    n, seed = 30_000, 9
+    if block:
+        monkeypatch.setenv("AMSWEEP_BLOCK_TICKS", str(block))
+    prod, orac = _gen_pair(gen, am, orc, config, seed, n, T0)
+    mode = am.SWEEP_CLOSED_LOOP if closed else 0
+    with am.Sweep(capacity=n) as s, am.Sweep(capacity=n) as s1:
+        s.load_range(0, prod)
+        s1.load_range(0, prod)
+        l0 = s.launch_count
+        stats = s.run_ticks(T0 + start, nt, mode=mode | am.SWEEP_BLOCKED, seed=seed)
+        assert s.launch_count - l0 <= (nt + (block or 64) - 1) // (block or 64) + 2  # one launch per block (+ a zone-window split)
+        plain = s1.run_ticks(T0 + start, nt, mode=mode, seed=seed)
+        emitted = 0
+        for k in range(nt):
+            _, _, ws = orc.sweep(orac, T0 + start + k, mode=mode, seed=seed)
+            gs = {f: int(stats[f][k]) for f in am.abi.STAT_FIELDS}
+            assert gs == ws, f"tick {k}: blocked {gs} oracle {ws}"
+            assert gs == {f: int(plain[f][k]) for f in am.abi.STAT_FIELDS}, f"tick {k} vs unblocked"
+            emitted += ws["n_emitted"]
+        assert emitted > nt
+        dev = s.read_range(0, n)
+        for name in am.COLUMN_NAMES:
+            np.testing.assert_array_equal(dev[name], orac[name], err_msg=name)
+
+
 def test_tick_device_resident_outputs(am, orc, gen):
     import torch
     n = 100_000

@@ -237,3 +237,33 @@ def test_consecutive_ticks_across_daylight_transitions(am, orc):
                 np.testing.assert_array_equal(ga, wa)
                 fired += len(gi)
     assert fired > 20
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("edge", ["new_york_fall", "lord_howe_spring"])
+def test_blocked_run_of_ticks_across_a_daylight_transition(am, orc, edge):
+    """am_sweep_run_ticks with AM_SWEEP_BLOCKED holds one UTC offset per zone for a whole block of ticks:
+    the launcher must cut the blocks at the instant a zone changes its offset.  Per-tick statistics over
+    200 consecutive seconds around a transition == the oracle (libc zones) tick by tick."""
+    e = {"new_york_fall": utc(2026, 11, 1, 6, 0), "lord_howe_spring": utc(2026, 10, 3, 15, 30)}[edge]
+    zones = ["America/New_York", "Europe/Paris", "Australia/Lord_Howe", "Asia/Kathmandu"]
+    specs = [f"CRON_TZ={z} * * * * *" for z in zones] + [f"CRON_TZ={z} {m} {h} * * *" for z in zones for h in (1, 2) for m in (0, 30)]
+    specs += ["* * * * *", "0 6 * * *"]
+    recs = [am.classify(cron=sp, finished_at=T0 - 5)[1] for sp in specs]
+    cols = am.records_to_columns(np.concatenate(recs))
+    ocols = {k: v.copy() for k, v in cols.items()}
+    for k, sp in enumerate(specs):
+        rc, oc, _ = orc.cron_parse(sp)
+        assert rc == 0
+        ocols["flags"][k] = (int(ocols["flags"][k]) & 0x00FFFFFF) | (oc.tz_id << 24)
+    start, nt = e - 130, 260
+    with am.Sweep(capacity=len(specs)) as s:
+        s.load_range(0, cols)
+        stats = s.run_ticks(start, nt, mode=am.SWEEP_BLOCKED)
+        total = 0
+        for k in range(nt):
+            _, _, ws = orc.sweep(ocols, start + k)
+            gs = {f: int(stats[f][k]) for f in am.abi.STAT_FIELDS}
+            assert gs == ws, f"{edge}: tick {start + k} (edge {e:+d})"
+            total += ws["n_emitted"]
+        assert total > 20
