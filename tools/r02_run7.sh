@@ -31,7 +31,10 @@ print("config3 us/step", d["ms_per_step"]*1e3, "sweep", d["roofline"]["kernel_ms
 d=json.load(open("gpurun_out/r02_run7.bench5.json"))
 print("config5 us/tick", d["ms_per_step"]*1e3, "G/s", d["value"]/1e9)
 PY
+echo "== config 5, one simulated day, temporal blocking vs tick by tick" >> $O.txt
+timeout 900 python tools/run_config5.py --blocked --compare-unblocked > $O.day_blocked.json 2>> $O.txt; cat $O.day_blocked.json >> $O.txt
 echo "== ncu launch list + full capture of the config-2 tick" >> $O.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O.launches.csv python bench.py --steps 5 --warmup 3 --no-cpu --settle-ms 5 > $O.ncu_bench.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"sweep_tick_kernel|expand_kernel|scan_groups" -s 8 -c 3 -o $O.c2 -f python tools/prof_tick.py --config 2 --ticks 5 > $O.ncu_c2.log 2>&1
-tail -30 $O.txt
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"sweep_block_kernel" -s 2 -c 1 -o $O.blk -f python tools/run_config5.py --blocked --ticks 512 --sub 0 --full-ticks 0 > $O.ncu_blk.log 2>&1
+tail -40 $O.txt

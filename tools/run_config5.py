@@ -29,6 +29,9 @@ ap.add_argument("--sub", type=int, default=10_000)
 ap.add_argument("--full-ticks", type=int, default=60)
 ap.add_argument("--config", type=int, default=5)
 ap.add_argument("--full-scan", action="store_true")
+ap.add_argument("--blocked", action="store_true", help="AM_SWEEP_BLOCKED: temporal blocking (csrc/sweep_block.cuh)")
+ap.add_argument("--compare-unblocked", action="store_true", help="with --blocked: also run the whole day tick by tick "
+                "on a second handle and compare every tick's statistics and every column afterwards")
 ap.add_argument("--per-tick", type=int, default=0,
                 help="also time this many ticks one by one (CUDA events around the three kernels of "
                      "each tick) and report p50 / p99 / max per-tick device time")
@@ -37,7 +40,7 @@ a = ap.parse_args()
 am = importlib.import_module("active-monitor_b200")
 lib = am.load()
 T0, seed = amgen.T0_DAY_START, 5
-mode = am.SWEEP_CLOSED_LOOP | (am.SWEEP_FULL_SCAN if a.full_scan else 0)
+mode = am.SWEEP_CLOSED_LOOP | (am.SWEEP_FULL_SCAN if a.full_scan else 0) | (am.SWEEP_BLOCKED if a.blocked else 0)
 fields = am.abi.STAT_FIELDS
 
 cols = amgen.fill(a.config, seed, 0, a.n, T0, lib.am_healthcheck_classify)
@@ -48,6 +51,19 @@ with am.Sweep(capacity=a.n) as s:
     wall = time.perf_counter() - t0
     dev_ms = s.last_kernel_ms
     launches = s.launch_count
+    final = s.read_range(0, a.n) if a.compare_unblocked else None
+
+same_as_unblocked = None
+if a.blocked and a.compare_unblocked:
+    with am.Sweep(capacity=a.n) as s4:
+        s4.load_range(0, cols)
+        plain = s4.run_ticks(T0, a.ticks, mode=mode & ~am.SWEEP_BLOCKED, seed=seed)
+        plain_ms = s4.last_kernel_ms
+        plain_final = s4.read_range(0, a.n)
+    same_as_unblocked = {"per_tick_statistics": bool(all(np.array_equal(stats[f], plain[f]) for f in fields)),
+                         "columns_afterwards": bool(all(np.array_equal(final[c], plain_final[c]) for c in am.COLUMN_NAMES)),
+                         "unblocked_device_ms_total": plain_ms, "speed_up": plain_ms / dev_ms}
+    del plain_final, final
 
 # per-tick latency distribution: the streaming run above only has a total
 per_tick = None
@@ -104,7 +120,9 @@ due = stats["n_submit_hc"].astype(np.float64)
 on_min = np.arange(a.ticks) % 60 == 0
 print(json.dumps({
     "workload": f"config {a.config}: {a.n} records x {a.ticks} one-second ticks from 2026-09-21T00:00:00Z, closed loop, seed 5",
-    "mode": "full-scan" if a.full_scan else "default (masks read only on the minute)",
+    "mode": ("full-scan" if a.full_scan else "default (masks read only on the minute)") +
+            (", AM_SWEEP_BLOCKED (<= 64 ticks per pass over the columns, per-tick statistics only)" if a.blocked else ""),
+    "identical_to_tick_by_tick": same_as_unblocked,
     "device_ms_total": dev_ms, "wall_s": wall, "evals_per_sec": a.n * a.ticks / (dev_ms * 1e-3),
     "us_per_tick_mean": dev_ms * 1e3 / a.ticks, "kernel_launches": int(launches),
     "due_per_tick_mean": float(due.mean()), "due_per_tick_on_minute_mean": float(due[on_min].mean()),
