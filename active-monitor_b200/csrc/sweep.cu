@@ -30,6 +30,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "sweep_internal.h"
@@ -98,6 +99,8 @@ struct Staging {
   // OUTSIDE the lock (the controller's workers post concurrently, hcc.go:170-188): while there are
   // any, the arrays may not move, nothing past `flushed_ops` is known complete, and the drain waits
   int writers = 0;
+  size_t done_ops = 0;  // every op below this index is staged completely (== n_ops when writers == 0)
+  std::vector<std::pair<size_t, size_t>> done_ranges;  // completed ranges above the prefix (other writers still below them)
   uint64_t hwm = 0;                          // highest upserted slot + 1
   cudaEvent_t copied = nullptr;              // the last copy out of the pinned arrays
   bool copy_pending = false;
@@ -158,7 +161,7 @@ struct am_sweep {
   uint32_t tz_n = 0;  // zones + 1; 0 or 1 = nothing registered
   int64_t tz_lo = 0, tz_hi = 0;
   bool tz_aligned = true;  // every offset a whole number of minutes
-  DevBuf tz_off;
+  DevBuf tz_off, tz_table;
   PinnedBuf tz_pin;
   cudaEvent_t tz_copied = nullptr;
   bool tz_copy_pending = false;
@@ -247,9 +250,9 @@ cudaError_t grow_pinned(am_sweep* h, PinnedBuf& b, size_t used_bytes, size_t wan
 // twins are large enough (they are grown at drain time only).  Called under h->mu by the
 // posting threads (chunk threshold) and by the drain (everything).
 cudaError_t flush_staging(am_sweep* h, Staging& st, bool all, size_t upto = SIZE_MAX) {
-  // ops: everything below `upto` is complete.  Without an explicit bound that is all of them, unless
-  // posting calls are still filling reserved ranges (the last of them flushes when it is done).
-  if (upto == SIZE_MAX) upto = st.writers ? st.flushed_ops : st.n_ops;
+  // ops: everything below `upto` is complete.  Without an explicit bound that is all of them, or, while
+  // posting calls are still filling reserved ranges, the completed prefix.
+  if (upto == SIZE_MAX) upto = st.writers ? st.done_ops : st.n_ops;
   const size_t pend = upto > st.flushed_ops ? upto - st.flushed_ops : 0;
   if (pend && (all || pend >= kFlushOps) && st.d_idx.cap >= upto * 4 && st.d_arg.cap >= upto * 4) {
     cudaError_t e = cudaMemcpyAsync((uint32_t*)st.d_idx.p + st.flushed_ops, (const uint32_t*)st.idx.p + st.flushed_ops,
@@ -271,6 +274,24 @@ cudaError_t flush_staging(am_sweep* h, Staging& st, bool all, size_t upto = SIZE
     st.copy_pending = true;
   }
   return cudaSuccess;
+}
+
+// A reserved range [a, b) of the op arrays is completely staged (called under h->mu): extend the
+// completed prefix, absorbing ranges that finished earlier above it.
+void complete_range(Staging& st, size_t a, size_t b) {
+  if (a != st.done_ops) { st.done_ranges.emplace_back(a, b); return; }
+  st.done_ops = b;
+  for (bool again = true; again && !st.done_ranges.empty();) {
+    again = false;
+    for (size_t k = 0; k < st.done_ranges.size(); ++k)
+      if (st.done_ranges[k].first == st.done_ops) {
+        st.done_ops = st.done_ranges[k].second;
+        st.done_ranges[k] = st.done_ranges.back();
+        st.done_ranges.pop_back();
+        again = true;
+        break;
+      }
+  }
 }
 
 // Make room for `n` more staged ops (and `nrec` more upsert records) in the current staging area;
@@ -364,6 +385,8 @@ int drain_staged(am_sweep* h, cudaStream_t s, const int64_t* tick_T = nullptr) {
   AM_CUDA(h, cudaEventRecord(st->drained, s));
   st->drain_pending = true;
   st->n_ops = st->n_recs = st->flushed_ops = st->flushed_recs = 0;
+  st->done_ops = 0;
+  st->done_ranges.clear();
   st->n_state = st->n_result = 0;
   st->hwm = 0;
   return AM_OK;
@@ -401,6 +424,7 @@ int refresh_zones(am_sweep* h, int64_t T, cudaStream_t s) {
   }
   const size_t bytes = (amsweep_tz::kMaxZones + 1) * sizeof(int32_t);
   AM_CUDA(h, h->tz_off.reserve(bytes));
+  AM_CUDA(h, h->tz_table.reserve((amsweep_tz::kMaxZones + 1) * sizeof(TickWords)));
   AM_CUDA(h, h->tz_pin.reserve(bytes));
   if (!h->tz_copied) AM_CUDA(h, cudaEventCreateWithFlags(&h->tz_copied, cudaEventDisableTiming));
   if (h->tz_copy_pending) AM_CUDA(h, cudaEventSynchronize(h->tz_copied));  // the previous copy has left the pinned array
@@ -438,15 +462,20 @@ int launch_tick(am_sweep* h, int64_t T, uint32_t mode, const ListOut& o, cudaStr
   {  // named time zones: one UTC offset per zone, valid at T
     const int rc = refresh_zones(h, T, s);
     if (rc != AM_OK) return rc;
-    p.tz_off = h->tz_n > 1 ? (const int32_t*)h->tz_off.p : nullptr;
   }
-  if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[0], s));
   // off the minute no 5-field schedule can fire: the mask columns are not read.  (A zone whose UTC
   // offset is not a whole number of minutes — historical local mean times — moves the local minute
   // boundary: every tick then reads the masks.)
   int64_t sec_of_min = T % 60;
   if (sec_of_min < 0) sec_of_min += 60;
   const bool masks = sec_of_min == 0 || (mode & AM_SWEEP_FULL_SCAN) || (h->tz_n > 1 && !h->tz_aligned);
+  if (masks && h->tz_n > 1) {  // the tick's wall clock per zone, from the cached offsets
+    AM_LAUNCH_PDL(tz_words_kernel, (h->tz_n + 63) / 64, 64, s, (const int32_t*)h->tz_off.p, (TickWords*)h->tz_table.p, T,
+                  h->tz_n);
+    h->launches++;
+    p.tz_table = (const TickWords*)h->tz_table.p;
+  }
+  if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[0], s));
   const bool closed = (mode & AM_SWEEP_CLOSED_LOOP) != 0;
   if (closed && masks) AM_LAUNCH_PDL(AM_SWEEP_KERNEL(true, true), p.n_tiles, kBlock, s, p);
   else if (closed) AM_LAUNCH_PDL(AM_SWEEP_KERNEL(true, false), p.n_tiles, kBlock, s, p);
@@ -692,7 +721,7 @@ void am_sweep_destroy(am_sweep_t* h) {
   if (h->h_stats) cudaFreeHost(h->h_stats);
   h->host_out.release();
   h->pin_in.release(); h->dev_in.release();
-  h->tz_off.release(); h->tz_pin.release();
+  h->tz_off.release(); h->tz_table.release(); h->tz_pin.release();
   if (h->tz_copied) cudaEventDestroy(h->tz_copied);
   if (h->ev_last) cudaEventDestroy(h->ev_last);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -776,6 +805,7 @@ int am_sweep_upsert(am_sweep_t* h, uint64_t n, const uint64_t* idx, const am_rec
     if (idx[k] + 1 > hwm) hwm = idx[k] + 1;
   }
   st.hwm = hwm;
+  complete_range(st, st.n_ops, st.n_ops + n);
   st.n_ops += n; st.n_recs += n;
   st.n_state += (uint32_t)n;
   AM_CUDA(h, flush_staging(h, st, false));
@@ -794,6 +824,7 @@ int am_sweep_remove(am_sweep_t* h, uint64_t n, const uint64_t* idx) {
   uint32_t* oa = (uint32_t*)st.arg.p + st.n_ops;
   if (amsweep_host::stage_slots(n, idx, h->capacity, oi)) return AM_E_RANGE;
   for (uint64_t k = 0; k < n; ++k) oa[k] = kOpRemove;
+  complete_range(st, st.n_ops, st.n_ops + n);
   st.n_ops += n;
   st.n_state += (uint32_t)n;
   AM_CUDA(h, flush_staging(h, st, false));
@@ -839,10 +870,12 @@ int am_sweep_post_result(am_sweep_t* h, uint64_t n, const uint64_t* idx, const u
   if (bad)
     for (uint64_t k = 0; k < n; ++k) { oi[k] = 0; oa[k] = kOpResult; }
   lk.lock();
-  if (--st.writers == 0) {
-    if (ce == cudaSuccess && (ce = cudaSetDevice(h->device)) == cudaSuccess) ce = flush_staging(h, st, false);
-    h->cv.notify_all();
-  }
+  complete_range(st, a, a + n);
+  --st.writers;
+  // hand the completed prefix to the copy stream (a chunk at a time) even while other calls are staging
+  if (ce == cudaSuccess && st.done_ops - st.flushed_ops >= kFlushOps && (ce = cudaSetDevice(h->device)) == cudaSuccess)
+    ce = flush_staging(h, st, false);
+  if (st.writers == 0) h->cv.notify_all();
   if (bad) return (bad & 1u) ? AM_E_RANGE : AM_E_INVAL;
   AM_CUDA(h, ce);
   return AM_OK;

@@ -204,14 +204,24 @@ __device__ __forceinline__ bool cron_matches(const TickWords& t, uint64_t mi, ui
   return (t.sec0 != 0) & fld & (star ? (dmm & dwm) : (dmm | dwm));
 }
 // A schedule bound to a named time zone ("CRON_TZ=Zone ...", robfig parser.go / hcc.go:253,
-// SpecSchedule.Location): the same match against the zone's wall clock, T + the zone's UTC offset broken
-// down into the one-hot words.  `tz_off` holds one offset per registered zone, valid for this tick (the
-// launcher refreshes it only when a tick leaves the window in which no zone changes its offset).  Rare
-// records, a few dozen instructions: kept out of line.
-__device__ __noinline__ bool cron_matches_in_zone(const int32_t* tz_off, uint32_t tz, int64_t T, uint64_t mi, uint64_t hr,
-                                                  uint64_t dm, uint64_t mo, uint64_t dw) {
-  const TickWords t = tick_words_from_unix(T + (int64_t)tz_off[tz]);
+// SpecSchedule.Location): the same match against the zone's wall clock.  `z` points at the zone's entry
+// of the tick's word table (tz_words_kernel).  Rare records: kept out of line.  (Deriving the words from
+// T + offset inside this call instead of loading them cost the 10 M-record sweep 8 us — half of all warps
+// hold a zone-bound record at 0.6 % of the records and ran ~100 more instructions each.)
+__device__ __noinline__ bool cron_matches_in_zone(const TickWords* z, uint64_t mi, uint64_t hr, uint64_t dm, uint64_t mo,
+                                                  uint64_t dw) {
+  const TickWords t = *z;
   return cron_matches(t, mi, hr, dm, mo, dw);
+}
+
+// The tick's wall clock in every registered zone as one-hot words: T + the zone's UTC offset, broken
+// down.  The offsets are kept by the launcher (valid until a zone changes its offset); this is one
+// thread per zone and no memory traffic to speak of, launched with programmatic serialisation ahead of
+// the sweep — only when zones are registered.
+__global__ void tz_words_kernel(const int32_t* __restrict__ tz_off, TickWords* __restrict__ table, int64_t T, uint32_t n) {
+  pdl_wait();
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) table[k] = tick_words_from_unix(T + (int64_t)tz_off[k]);
 }
 
 // ---------------------------------------------------------------------------
@@ -278,7 +288,7 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   const TickWords w = p.words;
   // named time zones are rare: one vote per warp decides whether the per-record zone lookup exists at all
   const uint32_t fl_or = fl[0].x | fl[0].y | fl[1].x | fl[1].y;
-  const bool warp_tz = MASKS && p.tz_off != nullptr && __any_sync(kFull, (fl_or >> AM_F_TZ_SHIFT) != 0);
+  const bool warp_tz = MASKS && p.tz_table != nullptr && __any_sync(kFull, (fl_or >> AM_F_TZ_SHIFT) != 0);
 
   uint32_t act[2][2];
   uint32_t res_lane = 0;  // 4 x 8-bit counts of results applied by this lane
@@ -319,7 +329,7 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
           // the zone's wall clock instead of UTC's — behind a real call: inlined, ptxas turned the zone
           // lookup of all four records into predicated instructions that EVERY warp issues (+24 LDG,
           // +40 address IMADs per warp: 84 -> 96 us per 10 M-record tick, profiles/r02_summary.md)
-          if (tz) due_cron = cron_matches_in_zone(p.tz_off, tz, T, miv, hrv, dmv, mov, dwv);
+          if (tz) due_cron = cron_matches_in_zone(p.tz_table + tz, miv, hrv, dmv, mov, dwv);
         }
       }
       const bool is_iv = ((0x14u >> kind) & 1u) != 0;  // INTERVAL or CRON_EVERY

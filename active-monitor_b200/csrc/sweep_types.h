@@ -93,8 +93,8 @@ struct SweepParams {
   uint32_t mode;
   TickOut out;
   unsigned long long* acc;   // [kNumAcc] statistics accumulators (zero on entry)
-  const int32_t* tz_off;     // [zones + 1] UTC offset (seconds east) of every registered time zone at T (entry 0 =
-                             // UTC); NULL when no zone is registered
+  const TickWords* tz_table; // [zones + 1] T's LOCAL fields per registered time zone (entry 0 = UTC), written by
+                             // tz_words_kernel ahead of the sweep; NULL when no zone is registered
 };
 
 struct ScanParams {

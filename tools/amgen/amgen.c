@@ -377,7 +377,7 @@ static double mono_s(void) {
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
-#define E2E_PIECE 32768u
+#define E2E_PIECE 8192u
 #define E2E_MAX_WORKERS 16
 typedef struct {
   am_post_fn post;
