@@ -42,6 +42,7 @@ static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }
 struct int2 { int32_t x, y; } __attribute__((aligned(8)));
+struct int4 { int32_t x, y, z, w; } __attribute__((aligned(16)));
 struct longlong2 { long long x, y; } __attribute__((aligned(16)));
 static inline int2 make_int2(int32_t x, int32_t y) { return int2{x, y}; }
 static inline longlong2 make_longlong2(long long x, long long y) { return longlong2{x, y}; }
