@@ -871,11 +871,28 @@ int am_sweep_post_result(am_sweep_t* h, uint64_t n, const uint64_t* idx, const u
     for (uint64_t k = 0; k < n; ++k) { oi[k] = 0; oa[k] = kOpResult; }
   lk.lock();
   complete_range(st, a, a + n);
-  --st.writers;
-  // hand the completed prefix to the copy stream (a chunk at a time) even while other calls are staging
-  if (ce == cudaSuccess && st.done_ops - st.flushed_ops >= kFlushOps && (ce = cudaSetDevice(h->device)) == cudaSuccess)
-    ce = flush_staging(h, st, false);
-  if (st.writers == 0) h->cv.notify_all();
+  // Hand the completed prefix to the copy stream, a chunk at a time, even while other calls are staging.
+  // The range is claimed under the lock; the two copies are issued outside it (a copy call under the lock
+  // serialised every worker behind the CUDA API: 0.38 ms per post with ten workers), while this call still
+  // counts as a writer — the drain, which records the "copied" event, waits for it.
+  size_t c_lo = 0, c_hi = 0;
+  if (ce == cudaSuccess && st.done_ops - st.flushed_ops >= kFlushOps && st.d_idx.cap >= st.done_ops * 4 &&
+      st.d_arg.cap >= st.done_ops * 4) {
+    c_lo = st.flushed_ops;
+    c_hi = st.done_ops;
+    st.flushed_ops = c_hi;
+    st.copy_pending = true;
+  }
+  const uint32_t* src_i = (const uint32_t*)st.idx.p;  // (the arrays cannot move while this call is a writer)
+  const uint32_t* src_a = (const uint32_t*)st.arg.p;
+  lk.unlock();
+  if (c_hi > c_lo && (ce = cudaSetDevice(h->device)) == cudaSuccess) {
+    ce = cudaMemcpyAsync((uint32_t*)st.d_idx.p + c_lo, src_i + c_lo, (c_hi - c_lo) * 4, cudaMemcpyHostToDevice, h->cstream);
+    if (ce == cudaSuccess)
+      ce = cudaMemcpyAsync((uint32_t*)st.d_arg.p + c_lo, src_a + c_lo, (c_hi - c_lo) * 4, cudaMemcpyHostToDevice, h->cstream);
+  }
+  lk.lock();
+  if (--st.writers == 0) h->cv.notify_all();
   if (bad) return (bad & 1u) ? AM_E_RANGE : AM_E_INVAL;
   AM_CUDA(h, ce);
   return AM_OK;
@@ -985,7 +1002,7 @@ int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint3
   if (rc != AM_OK) return rc;
   h->seed = seed;
   am_tick_stats_t* d_stats = nullptr;
-  AM_CUDA(h, cudaMalloc((void**)&d_stats, n_ticks * sizeof(am_tick_stats_t)));
+  AM_CUDA(h, cudaMalloc((void**)&d_stats, (n_ticks + 1) * sizeof(am_tick_stats_t)));  // (+ a row for the block kernels' counter)
   const bool blocked = (mode & AM_SWEEP_BLOCKED) != 0 && h->n_records != 0;
   if (blocked) {  // the block kernel accumulates into the rows
     if (cudaError_t e = cudaMemsetAsync(d_stats, 0, n_ticks * sizeof(am_tick_stats_t), h->stream); e != cudaSuccess) {
@@ -1018,10 +1035,19 @@ int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint3
     b.K = (uint32_t)K;
     b.tz_off = h->tz_n > 1 ? (const int32_t*)h->tz_off.p : nullptr;
     b.stats = reinterpret_cast<unsigned long long*>(d_stats + k);
+    b.heavy_list = h->due_idx[0];  // (the list ring is idle: a blocked run produces no lists)
+    b.heavy_count = reinterpret_cast<uint32_t*>(d_stats + n_ticks);
+    if (cudaError_t e = cudaMemsetAsync(b.heavy_count, 0, 4, h->stream); e != cudaSuccess) { h->last_error = cudaGetErrorString(e); rc = AM_E_DEVICE; break; }
     const unsigned grid = (unsigned)((h->n_records + kBlockRecords - 1) / kBlockRecords);
-    if (mode & AM_SWEEP_CLOSED_LOOP) AM_LAUNCH(sweep_block_kernel<true>, grid, kBlockThreads, h->stream, b);
-    else AM_LAUNCH(sweep_block_kernel<false>, grid, kBlockThreads, h->stream, b);
-    h->launches++;
+    const unsigned heavy_grid = 148u * 8u;  // grid-stride over however many records were set aside
+    if (mode & AM_SWEEP_CLOSED_LOOP) {
+      AM_LAUNCH(sweep_block_kernel<true>, grid, kBlockThreads, h->stream, b);
+      AM_LAUNCH(sweep_block_heavy_kernel<true>, heavy_grid, kHeavyThreads, h->stream, b);
+    } else {
+      AM_LAUNCH(sweep_block_kernel<false>, grid, kBlockThreads, h->stream, b);
+      AM_LAUNCH(sweep_block_heavy_kernel<false>, heavy_grid, kHeavyThreads, h->stream, b);
+    }
+    h->launches += 2;
     if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) { h->last_error = cudaGetErrorString(e); rc = AM_E_DEVICE; }
     k += K;
   }

@@ -27,6 +27,7 @@ CASES = [  # name, config, seed, n, ticks [(T, mode)]
     ("config1_ras60", 1, 1, 1000, [(T0, 0)]),
     ("config1_every1m", 11, 1, 1000, [(T0, 0)]),
     ("config2_mixed", 2, 2, 4000, [(T0, 0), (T0 + 1, 0), (T_OCT1, 0)]),
+    ("config22_zones", 22, 2, 4000, [(T0, 0), (1790013600, 0), (1793512800, 0)]),  # + 2026-09-21T18:00Z, 2026-11-01T06:00Z (New York falls back)
     ("config3_remedy", 3, 3, 4000, [(T0, 0), (T0 + 60, 0)]),
     ("config5_closed_loop", 55, 5, 1500, [(T0 - 2 + k, 1) for k in range(64)]),
 ]

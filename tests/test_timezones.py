@@ -180,11 +180,11 @@ def test_zone_bound_checks_fire_on_their_zones_wall_clock(am, orc):
 
 @pytest.mark.gpu
 def test_population_with_zones_equals_oracle_at_local_midnights(am, orc, gen):
-    """config 2 (0.6 % of the 5-field specs are bound to one of six zones) at instants chosen as local
-    midnights / DST edges of those zones: list, actions, statistics and columns == oracle."""
+    """config 22 (config 2's population with 1.5 % of the 5-field specs bound to one of six zones) at instants
+    chosen as local midnights / DST edges of those zones: list, actions, statistics and columns == oracle."""
     n = 60_000
-    prod = gen.fill(2, 2, 0, n, T0, am.load().am_healthcheck_classify)
-    orac = gen.fill(2, 2, 0, n, T0, orc.load().orc_classify)
+    prod = gen.fill(22, 2, 0, n, T0, am.load().am_healthcheck_classify)
+    orac = gen.fill(22, 2, 0, n, T0, orc.load().orc_classify)
     assert ((prod["flags"] >> 24) != 0).sum() > 100
     for name in am.COLUMN_NAMES:
         np.testing.assert_array_equal(prod[name], orac[name], err_msg=name)
