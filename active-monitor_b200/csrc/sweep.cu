@@ -1002,7 +1002,7 @@ int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint3
   if (rc != AM_OK) return rc;
   h->seed = seed;
   am_tick_stats_t* d_stats = nullptr;
-  AM_CUDA(h, cudaMalloc((void**)&d_stats, (n_ticks + 1) * sizeof(am_tick_stats_t)));  // (+ a row for the block kernels' counter)
+  AM_CUDA(h, cudaMalloc((void**)&d_stats, n_ticks * sizeof(am_tick_stats_t)));
   const bool blocked = (mode & AM_SWEEP_BLOCKED) != 0 && h->n_records != 0;
   if (blocked) {  // the block kernel accumulates into the rows
     if (cudaError_t e = cudaMemsetAsync(d_stats, 0, n_ticks * sizeof(am_tick_stats_t), h->stream); e != cudaSuccess) {
@@ -1035,19 +1035,10 @@ int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint3
     b.K = (uint32_t)K;
     b.tz_off = h->tz_n > 1 ? (const int32_t*)h->tz_off.p : nullptr;
     b.stats = reinterpret_cast<unsigned long long*>(d_stats + k);
-    b.heavy_list = h->due_idx[0];  // (the list ring is idle: a blocked run produces no lists)
-    b.heavy_count = reinterpret_cast<uint32_t*>(d_stats + n_ticks);
-    if (cudaError_t e = cudaMemsetAsync(b.heavy_count, 0, 4, h->stream); e != cudaSuccess) { h->last_error = cudaGetErrorString(e); rc = AM_E_DEVICE; break; }
     const unsigned grid = (unsigned)((h->n_records + kBlockRecords - 1) / kBlockRecords);
-    const unsigned heavy_grid = 148u * 8u;  // grid-stride over however many records were set aside
-    if (mode & AM_SWEEP_CLOSED_LOOP) {
-      AM_LAUNCH(sweep_block_kernel<true>, grid, kBlockThreads, h->stream, b);
-      AM_LAUNCH(sweep_block_heavy_kernel<true>, heavy_grid, kHeavyThreads, h->stream, b);
-    } else {
-      AM_LAUNCH(sweep_block_kernel<false>, grid, kBlockThreads, h->stream, b);
-      AM_LAUNCH(sweep_block_heavy_kernel<false>, heavy_grid, kHeavyThreads, h->stream, b);
-    }
-    h->launches += 2;
+    if (mode & AM_SWEEP_CLOSED_LOOP) AM_LAUNCH(sweep_block_kernel<true>, grid, kBlockThreads, h->stream, b);
+    else AM_LAUNCH(sweep_block_kernel<false>, grid, kBlockThreads, h->stream, b);
+    h->launches++;
     if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) { h->last_error = cudaGetErrorString(e); rc = AM_E_DEVICE; }
     k += K;
   }

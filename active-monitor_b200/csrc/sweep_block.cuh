@@ -28,7 +28,7 @@
 namespace amsweep {
 
 constexpr int kMaxBlockTicks = 64;
-constexpr int kBlockThreads = 256;
+constexpr int kBlockThreads = 128;               // small CTAs: five are resident per SM, so a CTA waiting for its last warp costs little
 constexpr int kBlockRecords = 4 * kBlockThreads;  // four consecutive records per thread in the classification pass
 constexpr int kBlockClasses = 4;                  // by expected number of events in the block: <= 2, <= 8, <= 24, more
 
@@ -39,8 +39,6 @@ struct BlockParams {
   uint32_t K;                  // ticks in the block, <= kMaxBlockTicks
   const int32_t* tz_off;       // per-zone UTC offsets valid for the whole block (NULL: no zone registered)
   unsigned long long* stats;   // K rows of 16 accumulators (am_tick_stats_t layout), zero on entry
-  uint32_t* heavy_list;        // local indices of the records with the most events (class 3), all CTAs together
-  uint32_t* heavy_count;       // zero on entry
 };
 
 // first tick index u > t at which the LOCAL second (UTC + off) is 0
@@ -53,31 +51,84 @@ __device__ __forceinline__ int64_t next_local_minute(int64_t T0, int64_t t, int3
 // Per-CTA statistics of a block of ticks, in shared memory.
 struct BlockStats {
   uint32_t cnt[kMaxBlockTicks][13];   // [0] emitted, [1..8] action bits, [9..12] results applied
-  unsigned long long sum[kMaxBlockTicks];  // sum of the emitted records' offsets (relative to the kernel's base index)
+  uint32_t sum[kMaxBlockTicks];       // sum of CTA-local offsets of the emitted records
   uint32_t x[kMaxBlockTicks][2];      // xor of the emitted global indices
   // records that emit the same bare action on EVERY tick from some tick on (a parse error: hcc.go:254-257
   // warns on every pass; an open-loop check that stays due): registered once, as a delta at their first
   // such tick, and integrated over the ticks when the CTA flushes.  [.][0] = SUBMIT_HC, [.][1] = PARSE_ERROR
-  uint32_t c_cnt[kMaxBlockTicks][2], c_x[kMaxBlockTicks][2][2];
-  unsigned long long c_sum[kMaxBlockTicks][2];
+  uint32_t c_cnt[kMaxBlockTicks][2], c_sum[kMaxBlockTicks][2], c_x[kMaxBlockTicks][2][2];
   uint16_t list[kBlockClasses][kBlockRecords];  // records with events, by class
   uint32_t n_list[kBlockClasses];
 };
 
-__device__ __forceinline__ void block_constant(BlockStats& S, int which, int64_t t_from, int64_t K, uint64_t g, uint64_t loc) {
+__device__ __forceinline__ void block_constant(BlockStats& S, int which, int64_t t_from, int64_t K, uint64_t g, uint32_t loc) {
   if (t_from >= K) return;
   atomicAdd(&S.c_cnt[t_from][which], 1u);
-  atomicAdd(&S.c_sum[t_from][which], (unsigned long long)loc);
+  atomicAdd(&S.c_sum[t_from][which], loc);
   atomicXor(&S.c_x[t_from][which][0], (uint32_t)g);
   atomicXor(&S.c_x[t_from][which][1], (uint32_t)(g >> 32));
 }
 
+// One event's contribution to the tick's row.  Lanes of a warp very often sit on the SAME tick — every
+// 5-field schedule of a block has its event on the minute — and seven shared atomics per lane on the same
+// seven words serialise lane by lane (the dominant stall of the first version).  So the lanes that are in
+// this call together are grouped by tick (match.any), each group reduces its contributions with redux, and
+// one lane per group issues the atomics.
+__device__ __forceinline__ void block_event_stats(BlockStats& S, int64_t t, uint32_t act, uint32_t res, uint64_t g, uint32_t loc) {
+#ifndef AMSWEEP_EMULATE
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, (int)t);
+  // four action bits per word, one byte each (a group has at most 32 lanes); `res` already is four byte counters
+  const uint32_t a_lo = __reduce_add_sync(peers, act ? spread4(act) : 0u);
+  const uint32_t a_hi = __reduce_add_sync(peers, act ? spread4(act >> 4) : 0u);
+  const uint32_t n_em = __reduce_add_sync(peers, act ? 1u : 0u);
+  const uint32_t r_all = __reduce_add_sync(peers, res);
+  const uint32_t x_lo = __reduce_xor_sync(peers, act ? (uint32_t)g : 0u);
+  const uint32_t x_hi = __reduce_xor_sync(peers, act ? (uint32_t)(g >> 32) : 0u);
+  const uint32_t l_sum = __reduce_add_sync(peers, act ? loc : 0u);
+  if ((int)(__ffs((int)peers) - 1) != (int)(threadIdx.x & 31)) return;
+  if (n_em) {
+    atomicAdd(&S.cnt[t][0], n_em);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if ((a_lo >> (8 * b)) & 0xFFu) atomicAdd(&S.cnt[t][1 + b], (a_lo >> (8 * b)) & 0xFFu);
+      if ((a_hi >> (8 * b)) & 0xFFu) atomicAdd(&S.cnt[t][5 + b], (a_hi >> (8 * b)) & 0xFFu);
+    }
+    if (x_lo) atomicXor(&S.x[t][0], x_lo);
+    if (x_hi) atomicXor(&S.x[t][1], x_hi);
+    atomicAdd(&S.sum[t], l_sum);
+  }
+  if (r_all) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if ((r_all >> (8 * q)) & 0xFFu) atomicAdd(&S.cnt[t][9 + q], (r_all >> (8 * q)) & 0xFFu);
+  }
+#else  // (the CPU emulation has no partial-warp collectives: lane by lane)
+  if (act) {
+    atomicAdd(&S.cnt[t][0], 1u);
+    uint32_t bits = act;
+    while (bits) {
+      const int b = __ffs((int)bits) - 1;
+      bits &= bits - 1u;
+      atomicAdd(&S.cnt[t][1 + b], 1u);
+    }
+    atomicXor(&S.x[t][0], (uint32_t)g);
+    atomicXor(&S.x[t][1], (uint32_t)(g >> 32));
+    atomicAdd(&S.sum[t], loc);
+  }
+  if (res) {
+    for (int q = 0; q < 4; ++q)
+      if ((res >> (8 * q)) & 0xFFu) atomicAdd(&S.cnt[t][9 + q], (res >> (8 * q)) & 0xFFu);
+  }
+#endif
+}
+
 // One record through the block, event by event (see the header of this file).
 template <bool CLOSED>
-__device__ __forceinline__ void block_record(const BlockParams& p, BlockStats& S, uint64_t base, uint64_t loc) {
+__device__ __forceinline__ void block_record(const BlockParams& p, BlockStats& S, uint64_t cta_base, uint32_t loc) {
   constexpr uint32_t kPend = AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING;
   const int64_t K = (int64_t)p.K;
-  const uint64_t i = base + loc;  // (statistics sum `loc`; the flush adds count x base)
+  const uint64_t i = cta_base + loc;
   const uint64_t g = p.shard_base + i;
   uint32_t f = ld_stream(p.c.flags + i);
   const int32_t rasv = ld_stream(p.c.ras + i);
@@ -162,23 +213,7 @@ __device__ __forceinline__ void block_record(const BlockParams& p, BlockStats& S
       fa = s.fa;
     }
     // ---- this tick's statistics (what expand_kernel derives from the emitted list) ----
-    if (act) {
-      atomicAdd(&S.cnt[t][0], 1u);
-      uint32_t bits = act;
-      while (bits) {
-        const int b = __ffs((int)bits) - 1;
-        bits &= bits - 1u;
-        atomicAdd(&S.cnt[t][1 + b], 1u);
-      }
-      atomicXor(&S.x[t][0], (uint32_t)g);
-      atomicXor(&S.x[t][1], (uint32_t)(g >> 32));
-      atomicAdd(&S.sum[t], (unsigned long long)loc);
-    }
-    if (res) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if ((res >> (8 * q)) & 0xFFu) atomicAdd(&S.cnt[t][9 + q], (res >> (8 * q)) & 0xFFu);
-    }
+    block_event_stats(S, t, act, res, g, loc);
     // from here on the same bare action on every tick, and nothing changes any more?
     if (kind == AM_KIND_PARSE_ERROR) { block_constant(S, 1, t + 1, K, g, loc); break; }
     if (!CLOSED && is_iv && due) { block_constant(S, 0, t + 1, K, g, loc); break; }  // stays due: nothing completes it in open loop
@@ -198,56 +233,16 @@ __device__ __forceinline__ void block_record(const BlockParams& p, BlockStats& S
   }
 }
 
-__device__ __forceinline__ void block_stats_zero(BlockStats& S, int tid, int nthreads) {
-  uint32_t* z = reinterpret_cast<uint32_t*>(&S);
-  const int n_zero = (int)(offsetof(BlockStats, list) / 4);  // everything before the lists
-  for (int k = tid; k < n_zero; k += nthreads) z[k] = 0;
-  if (tid < kBlockClasses) S.n_list[tid] = 0;
-}
-
-// Integrate the constant emitters over the ticks, then CTA -> global: one RED per non-zero (tick, field).
-// `gbase` = the global index the CTA's statistics offsets are relative to.
-__device__ __forceinline__ void block_stats_flush(const BlockParams& p, BlockStats& S, int tid, int nthreads,
-                                                  unsigned long long gbase) {
-  __syncthreads();
-  for (int t = tid; t < (int)p.K; t += nthreads) {  // tick t: everything registered at ticks <= t
-    uint32_t c0 = 0, c1 = 0, x0 = 0, x1 = 0;
-    unsigned long long s01 = 0;
-    for (int u = 0; u <= t; ++u) {
-      c0 += S.c_cnt[u][0]; c1 += S.c_cnt[u][1];
-      s01 += S.c_sum[u][0] + S.c_sum[u][1];
-      x0 ^= S.c_x[u][0][0] ^ S.c_x[u][1][0];
-      x1 ^= S.c_x[u][0][1] ^ S.c_x[u][1][1];
-    }
-    S.cnt[t][0] += c0 + c1;
-    S.cnt[t][1] += c0;      // AM_ACT_SUBMIT_HC   (bit 0)
-    S.cnt[t][4] += c1;      // AM_ACT_PARSE_ERROR (bit 3)
-    S.sum[t] += s01;
-    S.x[t][0] ^= x0;
-    S.x[t][1] ^= x1;
-  }
-  __syncthreads();
-  for (uint32_t k = (uint32_t)tid; k < p.K * 16u; k += (uint32_t)nthreads) {
-    const uint32_t t = k >> 4, fld = k & 15u;
-    unsigned long long* dst = p.stats + (size_t)t * kNumAcc + fld;
-    if (fld >= 1 && fld <= 13) {
-      const uint32_t v = S.cnt[t][fld - 1];
-      if (v) atomicAdd(dst, (unsigned long long)v);
-    } else if (fld == 14) {
-      const unsigned long long x = ((unsigned long long)S.x[t][1] << 32) | S.x[t][0];
-      if (x) atomicXor(dst, x);
-    } else if (fld == 15) {
-      const uint32_t cnt = S.cnt[t][0];
-      if (cnt) atomicAdd(dst, (unsigned long long)cnt * gbase + S.sum[t]);
-    }
-  }
-}
-
 template <bool CLOSED>
 __global__ void __launch_bounds__(kBlockThreads) sweep_block_kernel(const BlockParams p) {
   __shared__ BlockStats S;
   const int tid = threadIdx.x;
-  block_stats_zero(S, tid, kBlockThreads);
+  {
+    uint32_t* z = reinterpret_cast<uint32_t*>(&S);
+    constexpr int kZero = (int)(offsetof(BlockStats, list) / 4);  // everything before the lists
+    for (int k = tid; k < kZero; k += kBlockThreads) z[k] = 0;
+    if (tid < kBlockClasses) S.n_list[tid] = 0;
+  }
   __syncthreads();
 
   const uint64_t cta_base = (uint64_t)blockIdx.x * kBlockRecords;
@@ -310,43 +305,50 @@ __global__ void __launch_bounds__(kBlockThreads) sweep_block_kernel(const BlockP
   }
   __syncthreads();
 
-  // ---- the records with the longest loops leave the CTA: a handful per CTA would keep one warp — a
-  //      few lanes of it — busy for the CTA's whole life (52 % of all stall samples were the barrier
-  //      below); sweep_block_heavy_kernel runs them in full warps afterwards
-  {
-    __shared__ uint32_t s_heavy_base;
-    const uint32_t n3 = S.n_list[3];
-    if (tid == 0 && n3) s_heavy_base = atomicAdd(p.heavy_count, n3);
-    __syncthreads();
-    for (uint32_t k = (uint32_t)tid; k < n3; k += kBlockThreads)
-      p.heavy_list[s_heavy_base + k] = (uint32_t)cta_base + (uint32_t)S.list[3][k];
-  }
-
   // ---- pass 2: the listed records, longest loops first; the warps start at different places so that the
   //      (short) head of every list does not always land on warp 0
 #pragma unroll 1
-  for (int c = kBlockClasses - 2; c >= 0; --c) {
+  for (int c = kBlockClasses - 1; c >= 0; --c) {
     const uint32_t n = S.n_list[c];
-    for (uint32_t k = ((uint32_t)tid + 64u * (uint32_t)c) & (kBlockThreads - 1); k < n; k += kBlockThreads)
-      block_record<CLOSED>(p, S, cta_base, (uint64_t)S.list[c][k]);
+    for (uint32_t k = ((uint32_t)tid + 32u * (uint32_t)c) & (kBlockThreads - 1); k < n; k += kBlockThreads)
+      block_record<CLOSED>(p, S, cta_base, S.list[c][k]);
   }
-  block_stats_flush(p, S, tid, kBlockThreads, (unsigned long long)(p.shard_base + cta_base));
-}
-
-// The records the block kernel set aside (two dozen events or more in the block: "@every 3s", a 5 s
-// repeat, a check without a timer in closed loop ...), one per thread, in full warps of similar loops.
-constexpr int kHeavyThreads = 128;
-template <bool CLOSED>
-__global__ void __launch_bounds__(kHeavyThreads) sweep_block_heavy_kernel(const BlockParams p) {
-  __shared__ BlockStats S;
-  const int tid = threadIdx.x;
-  const uint32_t n = *p.heavy_count;
-  if ((uint64_t)blockIdx.x * kHeavyThreads >= n) return;  // (uniform per CTA)
-  block_stats_zero(S, tid, kHeavyThreads);
   __syncthreads();
-  for (uint64_t k = (uint64_t)blockIdx.x * kHeavyThreads + tid; k < n; k += (uint64_t)gridDim.x * kHeavyThreads)
-    block_record<CLOSED>(p, S, 0, (uint64_t)p.heavy_list[k]);
-  block_stats_flush(p, S, tid, kHeavyThreads, (unsigned long long)p.shard_base);
+
+  // ---- integrate the constant emitters over the ticks (thread t: everything registered at ticks <= t)
+  if (tid < (int)p.K) {
+    uint32_t c0 = 0, c1 = 0, s0 = 0, s1 = 0, x0 = 0, x1 = 0;
+    for (int u = 0; u <= tid; ++u) {
+      c0 += S.c_cnt[u][0]; c1 += S.c_cnt[u][1];
+      s0 += S.c_sum[u][0]; s1 += S.c_sum[u][1];
+      x0 ^= S.c_x[u][0][0] ^ S.c_x[u][1][0];
+      x1 ^= S.c_x[u][0][1] ^ S.c_x[u][1][1];
+    }
+    S.cnt[tid][0] += c0 + c1;
+    S.cnt[tid][1] += c0;      // AM_ACT_SUBMIT_HC   (bit 0)
+    S.cnt[tid][4] += c1;      // AM_ACT_PARSE_ERROR (bit 3)
+    S.sum[tid] += s0 + s1;
+    S.x[tid][0] ^= x0;
+    S.x[tid][1] ^= x1;
+  }
+  __syncthreads();
+
+  // ---- CTA -> global: one RED per non-zero (tick, field) ----
+  const unsigned long long gbase = (unsigned long long)(p.shard_base + cta_base);
+  for (uint32_t k = (uint32_t)tid; k < p.K * 16u; k += kBlockThreads) {
+    const uint32_t t = k >> 4, fld = k & 15u;
+    unsigned long long* dst = p.stats + (size_t)t * kNumAcc + fld;
+    if (fld >= 1 && fld <= 13) {
+      const uint32_t v = S.cnt[t][fld - 1];
+      if (v) atomicAdd(dst, (unsigned long long)v);
+    } else if (fld == 14) {
+      const unsigned long long x = ((unsigned long long)S.x[t][1] << 32) | S.x[t][0];
+      if (x) atomicXor(dst, x);
+    } else if (fld == 15) {
+      const uint32_t cnt = S.cnt[t][0];
+      if (cnt) atomicAdd(dst, (unsigned long long)cnt * gbase + S.sum[t]);
+    }
+  }
 }
 
 }  // namespace amsweep

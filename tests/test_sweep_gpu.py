@@ -278,7 +278,7 @@ def test_run_ticks_blocked_equals_the_oracle_tick_by_tick(am, orc, gen, monkeypa
         s1.load_range(0, prod)
         l0 = s.launch_count
         stats = s.run_ticks(T0 + start, nt, mode=mode | am.SWEEP_BLOCKED, seed=seed)
-        assert s.launch_count - l0 <= 2 * ((nt + (block or 64) - 1) // (block or 64) + 2)  # two launches per block (+ a zone-window split)
+        assert s.launch_count - l0 <= (nt + (block or 64) - 1) // (block or 64) + 2  # one launch per block (+ a zone-window split)
         plain = s1.run_ticks(T0 + start, nt, mode=mode, seed=seed)
         emitted = 0
         for k in range(nt):

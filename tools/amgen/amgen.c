@@ -19,6 +19,7 @@
  */
 #define _GNU_SOURCE
 #include <pthread.h>
+#include <sched.h>
 #include <stdatomic.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -424,6 +425,39 @@ static void e2e_consume(e2e_pool_t* P, int w) {
   P->walk_s[w] += walk; P->post_s[w] += post_s;
   atomic_fetch_add_explicit(&P->submitted, sub, memory_order_relaxed);
 }
+/* CPUs for the consumer workers: one per physical core, on the calling thread's package (the pinned
+ * buffers and the GPU's PCIe root are local to it), never the calling thread's own core — a worker
+ * spinning on the ticking thread's SMT sibling slowed the tick by a third.  Returns how many were found
+ * (0: topology not readable, the workers stay unpinned). */
+static int e2e_topology(int cpu, const char* what) {
+  char path[128];
+  int v = -1;
+  snprintf(path, sizeof path, "/sys/devices/system/cpu/cpu%d/topology/%s", cpu, what);
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  if (fscanf(f, "%d", &v) != 1) v = -1;
+  fclose(f);
+  return v;
+}
+static int e2e_pick_cpus(int want, int* cpus, const cpu_set_t* allowed, int me) {
+  const cpu_set_t set = *allowed;
+  if (me < 0) return 0;
+  const int my_pkg = e2e_topology(me, "physical_package_id"), my_core = e2e_topology(me, "core_id");
+  if (my_pkg < 0 || my_core < 0) return 0;
+  int seen[1024], n_seen = 0, n = 0;
+  for (int cpu = 0; cpu < CPU_SETSIZE && n < want; cpu++) {
+    if (!CPU_ISSET(cpu, &set)) continue;
+    const int pkg = e2e_topology(cpu, "physical_package_id"), core = e2e_topology(cpu, "core_id");
+    if (pkg != my_pkg || core < 0 || core == my_core) continue;
+    int dup = 0;
+    for (int k = 0; k < n_seen; k++) dup |= seen[k] == core;
+    if (dup || n_seen >= 1024) continue;
+    seen[n_seen++] = core;
+    cpus[n++] = cpu;
+  }
+  return n;
+}
+
 static void* e2e_worker(void* arg) {
   e2e_pool_t* P = ((e2e_arg_t*)arg)->pool;
   const int w = ((e2e_arg_t*)arg)->w;
@@ -463,9 +497,28 @@ int amgen_e2e_closed_loop(am_post_fn post, am_tick_view_fn tick, void* handle, i
   P.workers = workers;
   pthread_t th[E2E_MAX_WORKERS];
   e2e_arg_t args[E2E_MAX_WORKERS];
+  int cpus[E2E_MAX_WORKERS];
+  cpu_set_t old_mask;
+  int n_cpus = 0, repin = 0;
+  if (!getenv("AMGEN_E2E_NO_PIN") && workers > 1 && sched_getaffinity(0, sizeof old_mask, &old_mask) == 0) {
+    const int me = sched_getcpu();
+    n_cpus = e2e_pick_cpus(workers - 1, cpus, &old_mask, me);
+    if (n_cpus > 0) {  /* the ticking thread stays where it is */
+      cpu_set_t mine;
+      CPU_ZERO(&mine);
+      CPU_SET(me, &mine);
+      repin = sched_setaffinity(0, sizeof mine, &mine) == 0;
+    }
+  }
   for (int w = 1; w < workers; w++) {
     args[w].pool = &P; args[w].w = w;
     if (pthread_create(&th[w], NULL, e2e_worker, &args[w])) return -1;
+    if (w - 1 < n_cpus) {
+      cpu_set_t one;
+      CPU_ZERO(&one);
+      CPU_SET(cpus[w - 1], &one);
+      pthread_setaffinity_np(th[w], sizeof one, &one);
+    }
   }
   int rc = 0;
   for (uint64_t k = 0; k < warm + steps && !rc; k++) {
@@ -492,6 +545,7 @@ int amgen_e2e_closed_loop(am_post_fn post, am_tick_view_fn tick, void* handle, i
   *seconds = mono_s() - t0;
   atomic_store(&P.quit, 1);
   for (int w = 1; w < workers; w++) pthread_join(th[w], NULL);
+  if (repin) sched_setaffinity(0, sizeof old_mask, &old_mask);
   if (rc) return rc;
   if (split) {
     double ps = 0, ws = 0;
