@@ -28,7 +28,7 @@
 namespace amsweep {
 
 constexpr int kMaxBlockTicks = 64;
-constexpr int kBlockThreads = 128;               // small CTAs: five are resident per SM, so a CTA waiting for its last warp costs little
+constexpr int kBlockThreads = 256;
 constexpr int kBlockRecords = 4 * kBlockThreads;  // four consecutive records per thread in the classification pass
 constexpr int kBlockClasses = 4;                  // by expected number of events in the block: <= 2, <= 8, <= 24, more
 
@@ -67,60 +67,6 @@ __device__ __forceinline__ void block_constant(BlockStats& S, int which, int64_t
   atomicAdd(&S.c_sum[t_from][which], loc);
   atomicXor(&S.c_x[t_from][which][0], (uint32_t)g);
   atomicXor(&S.c_x[t_from][which][1], (uint32_t)(g >> 32));
-}
-
-// One event's contribution to the tick's row.  Lanes of a warp very often sit on the SAME tick — every
-// 5-field schedule of a block has its event on the minute — and seven shared atomics per lane on the same
-// seven words serialise lane by lane (the dominant stall of the first version).  So the lanes that are in
-// this call together are grouped by tick (match.any), each group reduces its contributions with redux, and
-// one lane per group issues the atomics.
-__device__ __forceinline__ void block_event_stats(BlockStats& S, int64_t t, uint32_t act, uint32_t res, uint64_t g, uint32_t loc) {
-#ifndef AMSWEEP_EMULATE
-  const unsigned active = __activemask();
-  const unsigned peers = __match_any_sync(active, (int)t);
-  // four action bits per word, one byte each (a group has at most 32 lanes); `res` already is four byte counters
-  const uint32_t a_lo = __reduce_add_sync(peers, act ? spread4(act) : 0u);
-  const uint32_t a_hi = __reduce_add_sync(peers, act ? spread4(act >> 4) : 0u);
-  const uint32_t n_em = __reduce_add_sync(peers, act ? 1u : 0u);
-  const uint32_t r_all = __reduce_add_sync(peers, res);
-  const uint32_t x_lo = __reduce_xor_sync(peers, act ? (uint32_t)g : 0u);
-  const uint32_t x_hi = __reduce_xor_sync(peers, act ? (uint32_t)(g >> 32) : 0u);
-  const uint32_t l_sum = __reduce_add_sync(peers, act ? loc : 0u);
-  if ((int)(__ffs((int)peers) - 1) != (int)(threadIdx.x & 31)) return;
-  if (n_em) {
-    atomicAdd(&S.cnt[t][0], n_em);
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      if ((a_lo >> (8 * b)) & 0xFFu) atomicAdd(&S.cnt[t][1 + b], (a_lo >> (8 * b)) & 0xFFu);
-      if ((a_hi >> (8 * b)) & 0xFFu) atomicAdd(&S.cnt[t][5 + b], (a_hi >> (8 * b)) & 0xFFu);
-    }
-    if (x_lo) atomicXor(&S.x[t][0], x_lo);
-    if (x_hi) atomicXor(&S.x[t][1], x_hi);
-    atomicAdd(&S.sum[t], l_sum);
-  }
-  if (r_all) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if ((r_all >> (8 * q)) & 0xFFu) atomicAdd(&S.cnt[t][9 + q], (r_all >> (8 * q)) & 0xFFu);
-  }
-#else  // (the CPU emulation has no partial-warp collectives: lane by lane)
-  if (act) {
-    atomicAdd(&S.cnt[t][0], 1u);
-    uint32_t bits = act;
-    while (bits) {
-      const int b = __ffs((int)bits) - 1;
-      bits &= bits - 1u;
-      atomicAdd(&S.cnt[t][1 + b], 1u);
-    }
-    atomicXor(&S.x[t][0], (uint32_t)g);
-    atomicXor(&S.x[t][1], (uint32_t)(g >> 32));
-    atomicAdd(&S.sum[t], loc);
-  }
-  if (res) {
-    for (int q = 0; q < 4; ++q)
-      if ((res >> (8 * q)) & 0xFFu) atomicAdd(&S.cnt[t][9 + q], (res >> (8 * q)) & 0xFFu);
-  }
-#endif
 }
 
 // One record through the block, event by event (see the header of this file).
@@ -213,7 +159,23 @@ __device__ __forceinline__ void block_record(const BlockParams& p, BlockStats& S
       fa = s.fa;
     }
     // ---- this tick's statistics (what expand_kernel derives from the emitted list) ----
-    block_event_stats(S, t, act, res, g, loc);
+    if (act) {
+      atomicAdd(&S.cnt[t][0], 1u);
+      uint32_t bits = act;
+      while (bits) {
+        const int b = __ffs((int)bits) - 1;
+        bits &= bits - 1u;
+        atomicAdd(&S.cnt[t][1 + b], 1u);
+      }
+      atomicXor(&S.x[t][0], (uint32_t)g);
+      atomicXor(&S.x[t][1], (uint32_t)(g >> 32));
+      atomicAdd(&S.sum[t], loc);
+    }
+    if (res) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if ((res >> (8 * q)) & 0xFFu) atomicAdd(&S.cnt[t][9 + q], (res >> (8 * q)) & 0xFFu);
+    }
     // from here on the same bare action on every tick, and nothing changes any more?
     if (kind == AM_KIND_PARSE_ERROR) { block_constant(S, 1, t + 1, K, g, loc); break; }
     if (!CLOSED && is_iv && due) { block_constant(S, 0, t + 1, K, g, loc); break; }  // stays due: nothing completes it in open loop
@@ -304,13 +266,17 @@ __global__ void __launch_bounds__(kBlockThreads) sweep_block_kernel(const BlockP
     }
   }
   __syncthreads();
+  // (Measured and dropped: a second kernel for the longest loops, run in full warps — slower, its lanes
+  //  all sit on the same tick and collide on every shared atomic; grouping the lanes of a warp by tick
+  //  with match.any + redux before the atomics, and 128-thread CTAs — slower still, 40 vs 27 us per tick:
+  //  the collectives cost more than the conflicts they remove.  profiles/r02_summary.md.)
 
   // ---- pass 2: the listed records, longest loops first; the warps start at different places so that the
   //      (short) head of every list does not always land on warp 0
 #pragma unroll 1
   for (int c = kBlockClasses - 1; c >= 0; --c) {
     const uint32_t n = S.n_list[c];
-    for (uint32_t k = ((uint32_t)tid + 32u * (uint32_t)c) & (kBlockThreads - 1); k < n; k += kBlockThreads)
+    for (uint32_t k = ((uint32_t)tid + 64u * (uint32_t)c) & (kBlockThreads - 1); k < n; k += kBlockThreads)
       block_record<CLOSED>(p, S, cta_base, S.list[c][k]);
   }
   __syncthreads();
