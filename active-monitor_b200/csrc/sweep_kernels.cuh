@@ -1015,11 +1015,26 @@ __global__ void apply_results_now_kernel(DevCols c, const uint32_t* __restrict__
     if (live && (f0 & kPend)) {
       const uint32_t old = atomicAnd(&c.flags[i], ~(kPend | AM_F_REMEDY_OUTCOME_OK));
       if (old & kPend) {  // this thread owns the slot's results (another op of the slot finds none)
-        RecState s{old, c.finished_at[i], c.success[i], c.failed[i], c.remedy_success[i], c.remedy_failed[i],
-                   c.remedy_total[i], c.remedy_finished_at[i], c.runs_limit[i], c.reset_interval[i]};
+        // Gather only what this result can touch (every column is its own 32-B sector of a random record):
+        // a "Succeeded" on a check without remedy reads its success counter and nothing else — two gathers
+        // instead of ten; with all ten the kernel took as long (56 us for 0.18 M results) as the sweep's own
+        // sparse path it replaces.  What apply_result reads, by case (hcc.go:635-724, :821-851):
+        //   Succeeded: SuccessCount;            with a remedy workflow: RemedyTotalRuns (reset on pass)
+        //   Failed:    FailedCount;             with a remedy workflow: the gate (limit, reset interval, total, finishedAt)
+        //   a remedy outcome (applied only behind a Failed that runs the remedy, or on its own): the remedy counters
+        const bool r_ok = (old & AM_F_PENDING_OK) != 0, r_fail = !r_ok && (old & AM_F_PENDING_FAIL) != 0;
+        const bool remedy_state = ((r_ok || r_fail) && (old & AM_F_HAS_REMEDY)) || (!r_ok && !r_fail);
+        RecState s{};
+        s.flags = old;  // (finishedAt is only ever overwritten with T by a workflow result: not read)
+        if (r_ok) s.s = c.success[i];
+        if (r_fail) s.f = c.failed[i];
+        if (remedy_state) {
+          s.rs = c.remedy_success[i]; s.rf = c.remedy_failed[i]; s.rt = c.remedy_total[i];
+          s.rfa = c.remedy_finished_at[i]; s.limit = c.runs_limit[i]; s.reset = c.reset_interval[i];
+        }
         const RecState b = s;
         const uint32_t a = apply_result(s, T, res);
-        if (s.fa != b.fa) c.finished_at[i] = s.fa;
+        if (r_ok || r_fail) c.finished_at[i] = s.fa;
         if (s.s != b.s) c.success[i] = s.s;
         if (s.f != b.f) c.failed[i] = s.f;
         if (s.rs != b.rs) c.remedy_success[i] = s.rs;

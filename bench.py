@@ -215,9 +215,10 @@ def main():
                     "(spell it --records-per-gpu under torchrun: its parser rejects the abbreviation-like --n)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-workers", type=int, default=0, help="consumer threads of the e2e loop (walk the tick's "
-                    "list and post results back: the reference's reconcile workers, hcc.go:170-188); 0 = the "
-                    "reference's default --max-workers 10 (cmd/main.go:144), at most the host cores available minus one")
+    ap.add_argument("--e2e-workers", type=int, default=4, help="consumer threads of the e2e loop (walk the tick's "
+                    "list and post results back: the reference's reconcile workers, hcc.go:170-188; its --max-workers "
+                    "defaults to 10, cmd/main.go:144).  4: the step is 0.46-0.50 ms on every box measured; with 6-10 it "
+                    "ranged from 0.46 to 1.03 ms depending on where the threads landed (profiles/r02_e2e_breakdown.json)")
     ap.add_argument("--no-verify", action="store_true", help="N>1: skip the oracle check of the gathered list")
     ap.add_argument("--gather", default="exchange", choices=["exchange", "plain", "nccl"],
                     help="N>1: NVLink tick exchange (bitmap + exceptions, list rebuilt on every GPU), the round-1 "
@@ -588,7 +589,7 @@ def main():
         if h_part is None:
             # N=1: the loop itself is compiled code calling the C-ABI, as the cgo shim is — ctypes and
             # numpy plumbing per call would otherwise be a tenth of the step
-            workers = args.e2e_workers or max(1, min(10, len(os.sched_getaffinity(0)) - 1))
+            workers = max(1, min(args.e2e_workers, len(os.sched_getaffinity(0)) - 1))
             c_loop = amgen.e2e_closed_loop(lib, sweep._h, T0, am.SWEEP_FULL_SCAN, 8, reps, n, workers=workers)
             dt, h2d, d2h = c_loop["seconds"], c_loop["h2d_bytes"], c_loop["d2h_bytes"]
         for phase_name in (() if c_loop else ("warm", "timed")):
