@@ -876,7 +876,7 @@ int am_sweep_post_result(am_sweep_t* h, uint64_t n, const uint64_t* idx, const u
   // serialised every worker behind the CUDA API: 0.38 ms per post with ten workers), while this call still
   // counts as a writer — the drain, which records the "copied" event, waits for it.
   size_t c_lo = 0, c_hi = 0;
-  if (ce == cudaSuccess && st.done_ops - st.flushed_ops >= kFlushOps && st.d_idx.cap >= st.done_ops * 4 &&
+  if (ce == cudaSuccess && st.done_ops > st.flushed_ops && st.done_ops - st.flushed_ops >= kFlushOps && st.d_idx.cap >= st.done_ops * 4 &&
       st.d_arg.cap >= st.done_ops * 4) {
     c_lo = st.flushed_ops;
     c_hi = st.done_ops;
