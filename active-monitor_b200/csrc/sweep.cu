@@ -477,10 +477,20 @@ int launch_tick(am_sweep* h, int64_t T, uint32_t mode, const ListOut& o, cudaStr
   }
   if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[0], s));
   const bool closed = (mode & AM_SWEEP_CLOSED_LOOP) != 0;
-  if (closed && masks) AM_LAUNCH_PDL(AM_SWEEP_KERNEL(true, true), p.n_tiles, kBlock, s, p);
-  else if (closed) AM_LAUNCH_PDL(AM_SWEEP_KERNEL(true, false), p.n_tiles, kBlock, s, p);
-  else if (masks) AM_LAUNCH_PDL(AM_SWEEP_KERNEL(false, true), p.n_tiles, kBlock, s, p);
-  else AM_LAUNCH_PDL(AM_SWEEP_KERNEL(false, false), p.n_tiles, kBlock, s, p);
+  if (o.expand) {  // single-stream tick: the sweep's launch hides behind its predecessor (the previous tick's publish, the drain)
+    if (closed && masks) AM_LAUNCH_PDL(AM_SWEEP_KERNEL(true, true), p.n_tiles, kBlock, s, p);
+    else if (closed) AM_LAUNCH_PDL(AM_SWEEP_KERNEL(true, false), p.n_tiles, kBlock, s, p);
+    else if (masks) AM_LAUNCH_PDL(AM_SWEEP_KERNEL(false, true), p.n_tiles, kBlock, s, p);
+    else AM_LAUNCH_PDL(AM_SWEEP_KERNEL(false, false), p.n_tiles, kBlock, s, p);
+  } else {
+    // am_sweep_tick_shard: NOT programmatic.  An early-launched sweep parks its 9766 CTAs on every SM while the
+    // previous tick's scan finishes, and the exchange of that tick — on the other stream, eligible at the same
+    // moment — finds no free slot until the sweep drains: 111 -> 126 us per step at two GPUs.
+    if (closed && masks) AM_LAUNCH(AM_SWEEP_KERNEL(true, true), p.n_tiles, kBlock, s, p);
+    else if (closed) AM_LAUNCH(AM_SWEEP_KERNEL(true, false), p.n_tiles, kBlock, s, p);
+    else if (masks) AM_LAUNCH(AM_SWEEP_KERNEL(false, true), p.n_tiles, kBlock, s, p);
+    else AM_LAUNCH(AM_SWEEP_KERNEL(false, false), p.n_tiles, kBlock, s, p);
+  }
   if (h->profiling) AM_CUDA(h, cudaEventRecord(h->evp[1], s));
   ScanParams sc{};
   sc.group_count = ts.out.group_count;
