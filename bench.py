@@ -507,8 +507,17 @@ def main():
             step(-1)
         drain()
         barrier()
-        launches0, gl0 = sweep.launch_count, gather_launches[0]
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # host time to ISSUE a step: a short burst into an empty queue (a long loop blocks on the full launch queue and
+        # shows the device time instead); when this is close to ms_per_step the loop is launch-bound, not GPU-bound
+        torch.cuda.synchronize()
+        h0 = time.perf_counter()
+        for i in range(16):
+            step(-1)
+        host_issue_ms = (time.perf_counter() - h0) * 1e3 / 16
+        drain()
+        barrier()
+        launches0, gl0 = sweep.launch_count, gather_launches[0]
         ev0.record(stream)
         for k in range(args.steps):
             step(k)
@@ -743,6 +752,8 @@ def main():
         }
         if per_step_ms is not None:
             out["per_step_ms"] = {"min": min(per_step_ms), "median": statistics.median(per_step_ms), "max": max(per_step_ms)}
+        if config == 2:
+            out["host_issue_ms_per_step"] = host_issue_ms
         if verify is not None:
             out.update(verify)
         if config == 5 and blocking is not None:
