@@ -483,9 +483,9 @@ int launch_tick(am_sweep* h, int64_t T, uint32_t mode, const ListOut& o, cudaStr
     else if (masks) AM_LAUNCH_PDL(AM_SWEEP_KERNEL(false, true), p.n_tiles, kBlock, s, p);
     else AM_LAUNCH_PDL(AM_SWEEP_KERNEL(false, false), p.n_tiles, kBlock, s, p);
   } else {
-    // am_sweep_tick_shard: NOT programmatic.  An early-launched sweep parks its 9766 CTAs on every SM while the
-    // previous tick's scan finishes, and the exchange of that tick — on the other stream, eligible at the same
-    // moment — finds no free slot until the sweep drains: 111 -> 126 us per step at two GPUs.
+    // am_sweep_tick_shard: a plain launch.  (An early-launched sweep could park its CTAs on every SM ahead of the
+    // previous tick's exchange on the other stream; measured at two GPUs it made no difference — 126 us per step
+    // either way — so the simpler form stays.)
     if (closed && masks) AM_LAUNCH(AM_SWEEP_KERNEL(true, true), p.n_tiles, kBlock, s, p);
     else if (closed) AM_LAUNCH(AM_SWEEP_KERNEL(true, false), p.n_tiles, kBlock, s, p);
     else if (masks) AM_LAUNCH(AM_SWEEP_KERNEL(false, true), p.n_tiles, kBlock, s, p);
