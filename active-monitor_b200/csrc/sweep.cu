@@ -170,6 +170,8 @@ struct am_sweep {
   double last_ms = -1.0;
   uint64_t seed = 0;
   bool early_results = true;  // AMSWEEP_EARLY_RESULTS=0: every posted result is applied inside the sweep
+  Staging* pend_clear = nullptr;  // a host tick's drain leaves clear_marks_kernel for after the tick's kernels
+  size_t pend_clear_n = 0;
 };
 
 namespace {
@@ -317,7 +319,23 @@ int reserve_staging(am_sweep* h, std::unique_lock<std::mutex>& lk, size_t n, siz
 
 // Apply staged upserts / removes / results on stream `s` (called with the tick guard held).
 // The staging lock is held only for the buffer swap.
-int drain_staged(am_sweep* h, cudaStream_t s, const int64_t* tick_T = nullptr) {
+// clear_marks_kernel of a drain that deferred it (host ticks: the sweep does not touch the marks, and the
+// host waits for an event recorded BEFORE this launch — 15 us off the tick's latency)
+int finish_deferred_clear(am_sweep* h, cudaStream_t s) {
+  Staging* st = h->pend_clear;
+  if (!st) return AM_OK;
+  h->pend_clear = nullptr;
+  const size_t n = h->pend_clear_n;
+  const unsigned B = 256, G = (unsigned)((n + B - 1) / B);
+  AM_LAUNCH_PDL(clear_marks_kernel, G, B, s, h->marks, (const uint32_t*)st->d_idx.p, (uint32_t)n);
+  h->launches++;
+  AM_CUDA(h, cudaGetLastError());
+  AM_CUDA(h, cudaEventRecord(st->drained, s));
+  st->drain_pending = true;
+  return AM_OK;
+}
+
+int drain_staged(am_sweep* h, cudaStream_t s, const int64_t* tick_T = nullptr, bool defer_clear = false) {
   Staging* st;
   {
     std::unique_lock<std::mutex> lk(h->mu);
@@ -379,11 +397,17 @@ int drain_staged(am_sweep* h, cudaStream_t s, const int64_t* tick_T = nullptr) {
     AM_LAUNCH_PDL(apply_results_now_kernel, G, B, s, h->cols, d_idx, d_arg, (uint32_t)n, *tick_T, ts.acc);
     h->launches++;
   }
-  AM_LAUNCH_PDL(clear_marks_kernel, G, B, s, h->marks, d_idx, (uint32_t)n);
-  h->launches++;
-  AM_CUDA(h, cudaGetLastError());
-  AM_CUDA(h, cudaEventRecord(st->drained, s));
-  st->drain_pending = true;
+  if (defer_clear) {  // (the caller runs finish_deferred_clear on the same stream before anything else touches the handle)
+    h->pend_clear = st;
+    h->pend_clear_n = n;
+    AM_CUDA(h, cudaGetLastError());
+  } else {
+    AM_LAUNCH_PDL(clear_marks_kernel, G, B, s, h->marks, d_idx, (uint32_t)n);
+    h->launches++;
+    AM_CUDA(h, cudaGetLastError());
+    AM_CUDA(h, cudaEventRecord(st->drained, s));
+    st->drain_pending = true;
+  }
   st->n_ops = st->n_recs = st->flushed_ops = st->flushed_recs = 0;
   st->done_ops = 0;
   st->done_ranges.clear();
@@ -543,7 +567,11 @@ int host_tick(am_sweep* h, int64_t unix_sec, uint32_t mode, am_tick_stats_t* sta
   AM_CUDA(h, cudaSetDevice(h->device));
   int rc = order_on(h, h->stream);
   if (rc != AM_OK) return rc;
-  rc = drain_staged(h, h->stream, &unix_sec);
+  rc = drain_staged(h, h->stream, &unix_sec, /*defer_clear=*/true);
+  struct ClearOnExit {  // whatever happens below, the marks are cleared before the handle is used again
+    am_sweep* h;
+    ~ClearOnExit() { (void)finish_deferred_clear(h, h->stream); }
+  } clear_on_exit{h};
   if (rc != AM_OK) return rc;
   rc = reserve_host_out(h, h->n_records);
   if (rc != AM_OK) return rc;
@@ -560,7 +588,9 @@ int host_tick(am_sweep* h, int64_t unix_sec, uint32_t mode, am_tick_stats_t* sta
   rc = launch_tick(h, unix_sec, mode, o, h->stream);
   if (rc != AM_OK) return rc;
   AM_CUDA(h, cudaEventRecord(h->ev1, h->stream));
-  AM_CUDA(h, cudaStreamSynchronize(h->stream));
+  rc = finish_deferred_clear(h, h->stream);  // behind the event the host waits for
+  if (rc != AM_OK) return rc;
+  AM_CUDA(h, cudaEventSynchronize(h->ev1));
   float ms = 0;
   AM_CUDA(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
   h->last_ms = ms;

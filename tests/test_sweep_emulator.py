@@ -219,13 +219,16 @@ def test_repeat_after_sec_kernel_equals_oracle(am, orc, gen):
             np.testing.assert_array_equal(got, want, err_msg=f"T={T}")
 
 
-@pytest.mark.parametrize("workers", [1, 3])
-def test_compiled_e2e_loop_equals_the_oracle_loop(am, orc, gen, monkeypatch, workers):
+@pytest.mark.parametrize("workers,piece", [(1, "300"), (3, "300"), (4, None)])
+def test_compiled_e2e_loop_equals_the_oracle_loop(am, orc, gen, monkeypatch, workers, piece):
     """bench.py's e2e driver (tools/amgen amgen_e2e_closed_loop: tick_view, then walk the list in pieces
     and post every submitted check as Succeeded) on the emulated library = the same loop on the oracle:
     counts of the last tick and every column afterwards."""
     n, steps = 60_000, 6
-    monkeypatch.setenv("AMGEN_E2E_PIECE", "300")  # several pieces per tick at this size
+    if piece:
+        monkeypatch.setenv("AMGEN_E2E_PIECE", piece)  # several pieces per tick at this size
+    else:
+        monkeypatch.delenv("AMGEN_E2E_PIECE", raising=False)  # the list divided evenly among the workers
     prod, orac = _gen_pair(gen, am, orc, 2, 5, n, T0)
     with emu_sweep.EmuSweep(n) as s:
         s.load_range(0, prod)

@@ -384,14 +384,15 @@ static double mono_s(void) {
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
-#define E2E_PIECE 16384u
+#define E2E_PIECE 8192u
 #define E2E_MAX_WORKERS 16
 typedef struct {
   am_post_fn post;
   void* handle;
   const uint8_t* ok_phase;
   uint64_t* slots; /* workers x piece scratch */
-  uint64_t piece;
+  uint64_t piece;          /* entries per piece of this tick's list */
+  uint64_t scratch_stride; /* entries of scratch per worker */
   int workers;
   /* the tick's job */
   const uint32_t* idx;
@@ -404,7 +405,7 @@ typedef struct {
 typedef struct { e2e_pool_t* pool; int w; } e2e_arg_t;
 
 static void e2e_consume(e2e_pool_t* P, int w) {
-  uint64_t* scratch = P->slots + (uint64_t)w * P->piece;
+  uint64_t* scratch = P->slots + (uint64_t)w * P->scratch_stride;
   uint64_t sub = 0;
   double walk = 0, post_s = 0;
   for (;;) {
@@ -487,14 +488,18 @@ int amgen_e2e_closed_loop(am_post_fn post, am_tick_view_fn tick, void* handle, i
   static e2e_pool_t P; /* (atomics: not copyable) */
   memset(&P, 0, sizeof P);
   P.post = post; P.handle = handle; P.ok_phase = ok_phase; P.slots = slots;
-  P.piece = E2E_PIECE;
+  /* a piece = the list divided evenly among the workers (one post per worker and tick: every post costs
+   * three lock hand-offs and, every 32 K staged results, two copy calls), but at least E2E_PIECE entries */
+  uint64_t fixed_piece = 0;
   const char* pe = getenv("AMGEN_E2E_PIECE"); /* tests: force several pieces on a small population */
-  if (pe && atoll(pe) > 0) P.piece = (uint64_t)atoll(pe);
+  if (pe && atoll(pe) > 0) fixed_piece = (uint64_t)atoll(pe);
+  P.piece = fixed_piece ? fixed_piece : E2E_PIECE;
   if (workers < 1) workers = 1;
   if (workers > E2E_MAX_WORKERS) workers = E2E_MAX_WORKERS;
   while (workers > 1 && (uint64_t)workers * P.piece > capacity) workers--;
   if (P.piece > capacity) P.piece = capacity;
   P.workers = workers;
+  P.scratch_stride = capacity / (uint64_t)workers;  /* >= any piece: a piece never exceeds ceil(n / workers) <= this, or E2E_PIECE */
   pthread_t th[E2E_MAX_WORKERS];
   e2e_arg_t args[E2E_MAX_WORKERS];
   int cpus[E2E_MAX_WORKERS];
@@ -533,6 +538,11 @@ int amgen_e2e_closed_loop(am_post_fn post, am_tick_view_fn tick, void* handle, i
     if (rc) break;
     const double c = mono_s();
     P.idx = v.idx_local; P.act = v.action; P.n = v.n;
+    if (!fixed_piece) {
+      uint64_t even = (v.n + (uint64_t)workers - 1) / (uint64_t)workers;
+      P.piece = even > E2E_PIECE ? even : E2E_PIECE;
+      if (P.piece > P.scratch_stride) P.piece = P.scratch_stride;
+    }
     atomic_store(&P.next_piece, 0); atomic_store(&P.submitted, 0); atomic_store(&P.done, 0);
     atomic_fetch_add_explicit(&P.gen, 1, memory_order_release);
     e2e_consume(&P, 0);
