@@ -239,7 +239,8 @@ def test_compiled_e2e_loop_equals_the_oracle_loop(am, orc, gen, monkeypatch, wor
             orac["flags"][sub] |= am.F_PENDING_OK
         assert (got["last_emitted"], got["last_submitted"]) == (len(idx), len(sub))
         assert len(idx) > 900  # four pieces and more
-        assert got["h2d_bytes"] > 0 and got["d2h_bytes"] > 0 and got["workers"] == workers
+        # (every worker owns one piece of scratch: at the default piece size this population has room for three)
+        assert got["h2d_bytes"] > 0 and got["d2h_bytes"] > 0 and got["workers"] == (workers if piece else min(workers, n // 16384))
         dev = s.read_range(0, n)  # (drains the last piece's posts, as the oracle's flags hold them)
         for name in am.COLUMN_NAMES:
             np.testing.assert_array_equal(dev[name], orac[name], err_msg=f"column {name}")
