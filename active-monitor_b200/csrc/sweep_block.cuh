@@ -28,7 +28,10 @@
 namespace amsweep {
 
 constexpr int kMaxBlockTicks = 64;
-constexpr int kBlockThreads = 256;
+#ifndef AM_BLOCK_THREADS
+#define AM_BLOCK_THREADS 256
+#endif
+constexpr int kBlockThreads = AM_BLOCK_THREADS;  // (build-time knob for the A/B in tools/r02_run15.sh)
 constexpr int kBlockRecords = 4 * kBlockThreads;  // four consecutive records per thread in the classification pass
 constexpr int kBlockClasses = 4;                  // by expected number of events in the block: <= 2, <= 8, <= 24, more
 
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(kBlockThreads) sweep_block_kernel(const BlockP
 #pragma unroll 1
   for (int c = kBlockClasses - 1; c >= 0; --c) {
     const uint32_t n = S.n_list[c];
-    for (uint32_t k = ((uint32_t)tid + 64u * (uint32_t)c) & (kBlockThreads - 1); k < n; k += kBlockThreads)
+    for (uint32_t k = ((uint32_t)tid + (uint32_t)(kBlockThreads / 4) * (uint32_t)c) & (kBlockThreads - 1); k < n; k += kBlockThreads)
       block_record<CLOSED>(p, S, cta_base, S.list[c][k]);
   }
   __syncthreads();
