@@ -27,11 +27,18 @@
 
 namespace amsweep {
 
-constexpr int kMaxBlockTicks = 64;
-#ifndef AM_BLOCK_THREADS
-#define AM_BLOCK_THREADS 256
+#ifndef AM_BLOCK_MAX_TICKS
+#define AM_BLOCK_MAX_TICKS 64
 #endif
-constexpr int kBlockThreads = AM_BLOCK_THREADS;  // (build-time knob for the A/B in tools/r02_run15.sh)
+constexpr int kMaxBlockTicks = AM_BLOCK_MAX_TICKS;
+#ifndef AM_BLOCK_THREADS
+#define AM_BLOCK_THREADS 128
+#endif
+constexpr int kBlockThreads = AM_BLOCK_THREADS;  // 128: 23.2 us per tick; 256: 27.3; 64: 29.2 (tools/r02_run15.sh) — small CTAs
+                                                  // overlap each other's tails (52 % of the 256-thread version's stalls were its final barrier)
+#ifndef AM_BLOCK_MIN_CTAS
+#define AM_BLOCK_MIN_CTAS 1
+#endif
 constexpr int kBlockRecords = 4 * kBlockThreads;  // four consecutive records per thread in the classification pass
 constexpr int kBlockClasses = 4;                  // by expected number of events in the block: <= 2, <= 8, <= 24, more
 
@@ -199,7 +206,7 @@ __device__ __forceinline__ void block_record(const BlockParams& p, BlockStats& S
 }
 
 template <bool CLOSED>
-__global__ void __launch_bounds__(kBlockThreads) sweep_block_kernel(const BlockParams p) {
+__global__ void __launch_bounds__(kBlockThreads, AM_BLOCK_MIN_CTAS) sweep_block_kernel(const BlockParams p) {
   __shared__ BlockStats S;
   const int tid = threadIdx.x;
   {
@@ -285,20 +292,20 @@ __global__ void __launch_bounds__(kBlockThreads) sweep_block_kernel(const BlockP
   __syncthreads();
 
   // ---- integrate the constant emitters over the ticks (thread t: everything registered at ticks <= t)
-  if (tid < (int)p.K) {
+  for (int t = tid; t < (int)p.K; t += kBlockThreads) {
     uint32_t c0 = 0, c1 = 0, s0 = 0, s1 = 0, x0 = 0, x1 = 0;
-    for (int u = 0; u <= tid; ++u) {
+    for (int u = 0; u <= t; ++u) {
       c0 += S.c_cnt[u][0]; c1 += S.c_cnt[u][1];
       s0 += S.c_sum[u][0]; s1 += S.c_sum[u][1];
       x0 ^= S.c_x[u][0][0] ^ S.c_x[u][1][0];
       x1 ^= S.c_x[u][0][1] ^ S.c_x[u][1][1];
     }
-    S.cnt[tid][0] += c0 + c1;
-    S.cnt[tid][1] += c0;      // AM_ACT_SUBMIT_HC   (bit 0)
-    S.cnt[tid][4] += c1;      // AM_ACT_PARSE_ERROR (bit 3)
-    S.sum[tid] += s0 + s1;
-    S.x[tid][0] ^= x0;
-    S.x[tid][1] ^= x1;
+    S.cnt[t][0] += c0 + c1;
+    S.cnt[t][1] += c0;      // AM_ACT_SUBMIT_HC   (bit 0)
+    S.cnt[t][4] += c1;      // AM_ACT_PARSE_ERROR (bit 3)
+    S.sum[t] += s0 + s1;
+    S.x[t][0] ^= x0;
+    S.x[t][1] ^= x1;
   }
   __syncthreads();
 
