@@ -1058,7 +1058,7 @@ int am_sweep_run_ticks(am_sweep_t* h, int64_t unix_sec0, uint64_t n_ticks, uint3
   // Temporal blocking (sweep_block.cuh): up to kMaxBlockTicks ticks per pass over the columns.  A block
   // never spans an instant at which a registered zone changes its UTC offset (the kernel holds one
   // offset per zone for the whole block).
-  uint64_t block_ticks = kMaxBlockTicks;
+  uint64_t block_ticks = kDefaultBlockTicks;
   if (const char* e = getenv("AMSWEEP_BLOCK_TICKS")) { long v = atol(e); if (v >= 1 && v <= kMaxBlockTicks) block_ticks = (uint64_t)v; }
   for (uint64_t k = 0; blocked && k < n_ticks && rc == AM_OK;) {
     const int64_t T = unix_sec0 + (int64_t)k;

@@ -4,7 +4,7 @@
 // am_sweep_run_ticks streams seconds back to back (BASELINE config 5: one simulated day = 86 400 ticks).
 // With one sweep per tick every tick re-reads 16..56 B per record to find the ~4 % that are due.  But
 // nothing reaches a record from outside between the ticks of such a run, so its whole future inside a
-// block of K ticks follows from its own columns: this kernel loads a record ONCE, then steps it from
+// block of K ticks (96 by default) follows from its own columns: this kernel loads a record ONCE, then steps it from
 // event to event in registers — the reference's own shape, a timer per HealthCheck (time.AfterFunc,
 // hcc.go:751) instead of a scan per second:
 //
@@ -28,16 +28,20 @@
 namespace amsweep {
 
 #ifndef AM_BLOCK_MAX_TICKS
-#define AM_BLOCK_MAX_TICKS 64
+#define AM_BLOCK_MAX_TICKS 128
 #endif
 constexpr int kMaxBlockTicks = AM_BLOCK_MAX_TICKS;
+constexpr int kDefaultBlockTicks = 96;  // 16.0 us per tick; 64: 18.1, 128: 17.3 (tools/r02_run17.sh, 10 M records, config 5)
 #ifndef AM_BLOCK_THREADS
 #define AM_BLOCK_THREADS 128
 #endif
-constexpr int kBlockThreads = AM_BLOCK_THREADS;  // 128: 23.2 us per tick; 256: 27.3; 64: 29.2 (tools/r02_run15.sh) — small CTAs
-                                                  // overlap each other's tails (52 % of the 256-thread version's stalls were its final barrier)
+constexpr int kBlockThreads = AM_BLOCK_THREADS;
+// Occupancy is what this kernel wants: its warps wait on each other (per-class lists of different lengths, one
+// barrier before the flush) and on shared atomics.  256 threads at 94 registers = 2 CTAs per SM: 27.3 us per tick,
+// 52 % of the stall samples at the final barrier.  128 threads: 23.2.  128 threads capped at 64 registers (8 CTAs per
+// SM, 4 bytes of spills): 18.0; the same at 256 threads / 4 CTAs: 16.8.  (tools/r02_run15.sh .. r02_run17.sh)
 #ifndef AM_BLOCK_MIN_CTAS
-#define AM_BLOCK_MIN_CTAS 1
+#define AM_BLOCK_MIN_CTAS 8
 #endif
 constexpr int kBlockRecords = 4 * kBlockThreads;  // four consecutive records per thread in the classification pass
 constexpr int kBlockClasses = 4;                  // by expected number of events in the block: <= 2, <= 8, <= 24, more

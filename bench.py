@@ -440,7 +440,7 @@ def main():
                "ms_per_step": wall / args.steps * 1e3, "steps": args.steps,
                "api": "am_sweep_run_ticks (state resident, per-tick statistics copied to host memory)"}
         settle_steps, per_step_ms = settle, None
-        # the same run with temporal blocking (AM_SWEEP_BLOCKED, csrc/sweep_block.cuh: up to 64 ticks per pass over
+        # the same run with temporal blocking (AM_SWEEP_BLOCKED, csrc/sweep_block.cuh: 96 ticks per pass over
         # the columns, records stepped from event to event), on a second handle from the same initial state;
         # reported separately from the K = 1 number, and checked against it tick by tick
         blocking = None
@@ -451,7 +451,7 @@ def main():
                 b_stats = s2.run_ticks(T0, settle + args.steps, am.SWEEP_CLOSED_LOOP | am.SWEEP_BLOCKED, seed)
                 b_ms = s2.last_kernel_ms
                 same = all(np.array_equal(b_stats[f][settle:], stats_k[f]) for f in am.abi.STAT_FIELDS)
-                blocking = {"ticks_per_pass": int(os.environ.get("AMSWEEP_BLOCK_TICKS", 64)),
+                blocking = {"ticks_per_pass": int(os.environ.get("AMSWEEP_BLOCK_TICKS", 96)),
                             "ticks": settle + args.steps, "ms_per_tick": b_ms / (settle + args.steps),
                             "value": n / (b_ms / (settle + args.steps) * 1e-3), "unit": UNIT,
                             "identical_to_tick_by_tick": bool(same),

@@ -233,8 +233,8 @@ typedef struct am_tick_stats {
                                      with its preset outcome     */
 #define AM_SWEEP_FULL_SCAN 0x2u   /* read every schedule column even on ticks
                                      where no 5-field cron can fire (sec!=0)  */
-#define AM_SWEEP_BLOCKED 0x4u     /* am_sweep_run_ticks only: temporal blocking.  Blocks of up to 64
-                                     consecutive ticks are evaluated in one pass over the columns,
+#define AM_SWEEP_BLOCKED 0x4u     /* am_sweep_run_ticks only: temporal blocking.  Blocks of consecutive
+                                     ticks (96; AMSWEEP_BLOCK_TICKS, at most 128) are evaluated in one pass over the columns,
                                      every record stepped from event to event (its next repeat timer,
                                      hcc.go:751; its next cron minute) — per-tick statistics and the
                                      columns afterwards are identical to tick-by-tick evaluation, but

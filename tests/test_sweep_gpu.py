@@ -261,6 +261,7 @@ def test_run_ticks_streaming_matches_single_ticks(am, orc, gen):
     (55, True, -75, 160, 7),     # remedy mix, closed loop, short blocks
     (3, False, -10, 90, 0),      # open loop: posted results and remedy gates at the first tick, then unarmed checks every tick
     (2, False, 45, 70, 64),      # open loop config 2
+    (5, True, -100, 300, 128),   # the longest blocks
     (5, True, 0, 1, 0),          # a single tick
 ])
 def test_run_ticks_blocked_equals_the_oracle_tick_by_tick(am, orc, gen, monkeypatch, config, closed, start, nt, block):
@@ -278,7 +279,7 @@ def test_run_ticks_blocked_equals_the_oracle_tick_by_tick(am, orc, gen, monkeypa
         s1.load_range(0, prod)
         l0 = s.launch_count
         stats = s.run_ticks(T0 + start, nt, mode=mode | am.SWEEP_BLOCKED, seed=seed)
-        assert s.launch_count - l0 <= (nt + (block or 64) - 1) // (block or 64) + 2  # one launch per block (+ a zone-window split)
+        assert s.launch_count - l0 <= (nt + (block or 96) - 1) // (block or 96) + 2  # one launch per block (+ a zone-window split)
         plain = s1.run_ticks(T0 + start, nt, mode=mode, seed=seed)
         emitted = 0
         for k in range(nt):
