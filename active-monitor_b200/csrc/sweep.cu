@@ -542,11 +542,9 @@ int launch_tick(am_sweep* h, int64_t T, uint32_t mode, const ListOut& o, cudaStr
     e.world = 1;
     e.stats_rank = 0;
     e.idx_bytes = 4;
-    e.fold_publish = 1;  // the last CTA publishes the statistics and re-arms the accumulators
-    e.fold_stats = o.stats;
-    e.fold_n_records = h->n_records;
     AM_LAUNCH_PDL(expand_kernel, dim3(sc.n_groups, 1), kExpandThreads, s, e);
-    h->launches += 1;
+    AM_LAUNCH_PDL(publish_kernel, 1, 32, s, ts.acc, o.stats, h->n_records);
+    h->launches += 2;
   }
   if (h->profiling) { AM_CUDA(h, cudaEventRecord(h->evp[2], s)); h->profiled = true; }
   h->parity ^= 1;

@@ -647,27 +647,6 @@ __global__ void __launch_bounds__(1024) scan_groups_kernel(const ScanParams p) {
 // writing, every thread counts action bits and checksums global indices for the shard
 // whose statistics this GPU owns.
 // ---------------------------------------------------------------------------
-// The "last block publishes" pattern for expand_kernel (ExpandParams::fold_publish): every CTA, whatever way it
-// leaves the kernel, takes a ticket after its own REDs are fenced; the last one reads the sixteen accumulators,
-// writes the tick's statistics and zeroes the accumulators (ticket included) for the next tick of this buffer set.
-__device__ __forceinline__ void expand_fold_exit(const ExpandParams& p, int tid) {
-  __shared__ int s_last;
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned long long t = atomicAdd(&p.acc[0], 1ull);
-    s_last = t + 1ull == (unsigned long long)gridDim.x * (unsigned long long)gridDim.y;
-  }
-  __syncthreads();
-  if (s_last && tid < kNumAcc) {
-    __threadfence();
-    unsigned long long v = atomicAdd(&p.acc[tid], 0ull);  // (an atomic read: the other CTAs' REDs were atomics too)
-    p.acc[tid] = 0;
-    if (tid == 0) v = p.fold_n_records;
-    if (p.fold_stats) reinterpret_cast<unsigned long long*>(p.fold_stats)[tid] = v;
-  }
-}
-
 constexpr int kExpandThreads = 128;  // one thread per PAIR of bitmap words (64 records): the kernel is
                                      // instruction-bound, and the per-thread fixed cost halves per entry
 __global__ void __launch_bounds__(kExpandThreads, 8) expand_kernel(const ExpandParams p) {
@@ -685,10 +664,7 @@ __global__ void __launch_bounds__(kExpandThreads, 8) expand_kernel(const ExpandP
   const int r = blockIdx.y;
   const uint32_t g = blockIdx.x;
   const ExpandSrc& src = p.src[r];
-  if (g >= src.n_groups) {  // uniform per CTA
-    if (p.fold_publish) { pdl_wait(); expand_fold_exit(p, tid); }
-    return;
-  }
+  if (g >= src.n_groups) return;  // uniform per CTA
   pdl_wait();
   pdl_trigger();
   // ---- every global load of the CTA is issued here, before the first use: the kernel is a chain
@@ -705,10 +681,7 @@ __global__ void __launch_bounds__(kExpandThreads, 8) expand_kernel(const ExpandP
   const uint32_t nx = tile_ok ? src.tile_exc[tile] : 0u;
   const uint32_t e_first = tile_ok ? __ldcs(src.exc_seg + (size_t)tile * kTile + l16) : 0u;
   for (int q = 0; q < r; ++q) start += p.src[q].group_prefix[p.src[q].n_groups];
-  if (cnt == 0) {  // uniform per CTA: nothing emitted by these 8192 records
-    if (p.fold_publish) expand_fold_exit(p, tid);
-    return;
-  }
+  if (cnt == 0) return;  // uniform per CTA: nothing emitted by these 8192 records
   const uint32_t sh = (uint32_t)start & 3u;
 
   // ---- ranks: exclusive popcount prefix over the group's 256 words (two per thread)
@@ -868,7 +841,6 @@ __global__ void __launch_bounds__(kExpandThreads, 8) expand_kernel(const ExpandP
       atomicAdd(&p.acc[15], t + (unsigned long long)cnt * sbase);
     }
   }
-  if (p.fold_publish) expand_fold_exit(p, tid);
 }
 
 // One warp, after the kernel boundary that completes every expand CTA's REDs: publish the

@@ -121,11 +121,6 @@ struct ExpandParams {
   uint64_t stats_base;       // global index of that rank's record 0 (checksums are over global indices)
   uint64_t cap;
   int world, stats_rank, idx_bytes;
-  // single-GPU ticks: the last CTA to finish publishes the tick's am_tick_stats_t and re-arms the accumulators
-  // (acc[0] is the ticket) — publish_kernel's launch and its 2.6 us leave the tick
-  int fold_publish;
-  am_tick_stats_t* fold_stats;  // device or mapped host memory, may be NULL
-  uint64_t fold_n_records;
 };
 
 }  // namespace amsweep

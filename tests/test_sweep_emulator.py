@@ -355,8 +355,8 @@ def test_posted_results_sparse_and_dense_paths(am, orc, gen, every):
                                                  am.F_REMEDY_PENDING).astype(np.uint32)
             l0 = s.launch_count
             got, want = s.tick(T), orc.sweep(orac, T)
-            # mark, apply_result_ops, [apply_results_now], clear_marks + tz_words (on-minute tick, zones registered), sweep, scan, expand
-            assert s.launch_count - l0 == (8 if every == 23 else 7), s.launch_count - l0
+            # mark, apply_result_ops, [apply_results_now], clear_marks + tz_words (on-minute tick, zones registered), sweep, scan, expand, publish
+            assert s.launch_count - l0 == (9 if every == 23 else 8), s.launch_count - l0
             _assert_tick_equal(am, got, want, s, orac, n, f"every={every} tick {k}")
             seen |= int(np.bitwise_or.reduce(want[1]))
         assert not np.any(s.read_range(0, n)["flags"] & am.F_CARRY_MASK)
