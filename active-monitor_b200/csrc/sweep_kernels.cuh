@@ -250,6 +250,9 @@ __global__ void __launch_bounds__(kBlock, MASKS ? AM_MIN_BLOCKS : AM_MIN_BLOCKS 
   const uint32_t tile_base = tile * (uint32_t)kTile;
   const int64_t T = p.T;
   pdl_wait();  // the sweep is launched while its predecessor (the previous tick's publish, or the drain) still runs
+#ifdef AM_SWEEP_TRIGGER
+  pdl_trigger();  // (A/B) scan_groups_kernel may become resident during the sweep's tail
+#endif
 
   // ---- phase A: issue every schedule-column load of this lane up front ----
   // half h covers records r0(h) .. r0(h)+1, r0 = tile_base + warp*128 + h*64 + lane*2
