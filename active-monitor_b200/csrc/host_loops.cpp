@@ -5,7 +5,7 @@
 // round-1 e2e step (profiles/r02_e2e_breakdown.md).
 //
 //   stage_results  am_sweep_post_result: (u64 slot, u8 phase, u8 remedy phase) -> staged
-//                  op arrays in pinned memory (hcc.go:635/:662/:821/:836 observations)
+//                  ops (one 64-bit word each) in pinned memory (hcc.go:635/:662/:821/:836 observations)
 //   widen_list     am_sweep_tick: (u32 local index, u8 action) -> the caller's
 //                  (u64 global index, u32 action) arrays (SURVEY 8b signature)
 #include <stddef.h>
@@ -21,11 +21,13 @@
 
 namespace amsweep_host {
 
+// A staged op is one 64-bit word: slot in the low half, arg (kind | payload) in the high half — one
+// stream of stores here, one copy to the device, one 8-B load per op in the kernels.
 // returns bit 0: a slot >= capacity, bit 1: a phase outside {0, 1, 2}
 AM_SIMD_CLONES
 unsigned stage_results(uint64_t n, const uint64_t* __restrict__ idx, const uint8_t* __restrict__ phase,
                        const uint8_t* __restrict__ remedy, uint64_t capacity, uint32_t op_result_kind,
-                       uint32_t* __restrict__ op_idx, uint32_t* __restrict__ op_arg) {
+                       uint64_t* __restrict__ ops) {
   uint64_t bad_range = 0;
   uint32_t bad_phase = 0;
   if (remedy) {
@@ -37,8 +39,7 @@ unsigned stage_results(uint64_t n, const uint64_t* __restrict__ idx, const uint8
       const uint32_t bits = (p == AM_PHASE_SUCCEEDED ? AM_F_PENDING_OK : 0u) | (p == AM_PHASE_FAILED ? AM_F_PENDING_FAIL : 0u) |
                             (r != AM_PHASE_NONE ? AM_F_REMEDY_PENDING : 0u) |
                             (r == AM_PHASE_SUCCEEDED ? AM_F_REMEDY_OUTCOME_OK : 0u);
-      op_idx[k] = (uint32_t)i;
-      op_arg[k] = op_result_kind | bits;
+      ops[k] = (uint64_t)(uint32_t)i | ((uint64_t)(op_result_kind | bits) << 32);
     }
   } else {
     for (uint64_t k = 0; k < n; ++k) {
@@ -47,8 +48,7 @@ unsigned stage_results(uint64_t n, const uint64_t* __restrict__ idx, const uint8
       bad_range |= (uint64_t)(i >= capacity);
       bad_phase |= (uint32_t)(p > AM_PHASE_FAILED);
       const uint32_t bits = (p == AM_PHASE_SUCCEEDED ? AM_F_PENDING_OK : 0u) | (p == AM_PHASE_FAILED ? AM_F_PENDING_FAIL : 0u);
-      op_idx[k] = (uint32_t)i;
-      op_arg[k] = op_result_kind | bits;
+      ops[k] = (uint64_t)(uint32_t)i | ((uint64_t)(op_result_kind | bits) << 32);
     }
   }
   return (bad_range ? 1u : 0u) | (bad_phase ? 2u : 0u);
@@ -61,13 +61,14 @@ void widen_list(uint64_t n, uint64_t base, const uint32_t* __restrict__ idx32, c
   for (uint64_t k = 0; k < n; ++k) act32[k] = act8[k];
 }
 
-// slots of an upsert / remove batch: range check + narrowing
+// slots of an upsert / remove batch: range check + narrowing; arg = arg0 + k * arg_step (an upsert's record index)
 AM_SIMD_CLONES
-unsigned stage_slots(uint64_t n, const uint64_t* __restrict__ idx, uint64_t capacity, uint32_t* __restrict__ op_idx) {
+unsigned stage_slots(uint64_t n, const uint64_t* __restrict__ idx, uint64_t capacity, uint32_t arg0, uint32_t arg_step,
+                     uint64_t* __restrict__ ops) {
   uint64_t bad = 0;
   for (uint64_t k = 0; k < n; ++k) {
     bad |= (uint64_t)(idx[k] >= capacity);
-    op_idx[k] = (uint32_t)idx[k];
+    ops[k] = (uint64_t)(uint32_t)idx[k] | ((uint64_t)(arg0 + (uint32_t)k * arg_step) << 32);
   }
   return bad ? 1u : 0u;
 }

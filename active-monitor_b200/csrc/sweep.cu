@@ -8,7 +8,7 @@
 // per-CR schedule ladder and remedy state machine for every record at once.
 //
 // Shape of the host side (round 2; profiles/r02_e2e_breakdown.md has the timings):
-//   * staged events are two parallel u32 arrays (+ 96-B records for upserts) in pinned
+//   * staged events are 64-bit words (slot, arg) (+ 96-B records for upserts) in pinned
 //     memory, double-buffered: a tick swaps the buffers under the staging lock and
 //     releases it at once — callers never wait for a copy or a kernel;
 //   * posted events are copied to the device in chunks WHILE they are being posted (copy
@@ -41,9 +41,9 @@ using namespace amsweep;
 
 namespace amsweep_host {
 unsigned stage_results(uint64_t n, const uint64_t* idx, const uint8_t* phase, const uint8_t* remedy, uint64_t capacity,
-                       uint32_t op_result_kind, uint32_t* op_idx, uint32_t* op_arg);
+                       uint32_t op_result_kind, uint64_t* ops);
 void widen_list(uint64_t n, uint64_t base, const uint32_t* idx32, const uint8_t* act8, uint64_t* idx64, uint32_t* act32);
-unsigned stage_slots(uint64_t n, const uint64_t* idx, uint64_t capacity, uint32_t* op_idx);
+unsigned stage_slots(uint64_t n, const uint64_t* idx, uint64_t capacity, uint32_t arg0, uint32_t arg_step, uint64_t* ops);
 }  // namespace amsweep_host
 
 namespace {
@@ -90,8 +90,8 @@ struct DevBuf {
 // One of the two staging areas for controller events.  The pinned arrays are appended to
 // under am_sweep::mu; the device twins receive them in chunks on the copy stream.
 struct Staging {
-  PinnedBuf idx, arg, recs;
-  DevBuf d_idx, d_arg, d_recs;
+  PinnedBuf ops, recs;   // an op = one 64-bit word: slot | arg << 32
+  DevBuf d_ops, d_recs;
   size_t n_ops = 0, n_recs = 0;
   size_t flushed_ops = 0, flushed_recs = 0;  // already enqueued for copy to the device twins
   uint32_t n_state = 0, n_result = 0;
@@ -256,12 +256,9 @@ cudaError_t flush_staging(am_sweep* h, Staging& st, bool all, size_t upto = SIZE
   // posting calls are still filling reserved ranges, the completed prefix.
   if (upto == SIZE_MAX) upto = st.writers ? st.done_ops : st.n_ops;
   const size_t pend = upto > st.flushed_ops ? upto - st.flushed_ops : 0;
-  if (pend && (all || pend >= kFlushOps) && st.d_idx.cap >= upto * 4 && st.d_arg.cap >= upto * 4) {
-    cudaError_t e = cudaMemcpyAsync((uint32_t*)st.d_idx.p + st.flushed_ops, (const uint32_t*)st.idx.p + st.flushed_ops,
-                                    pend * 4, cudaMemcpyHostToDevice, h->cstream);
-    if (e != cudaSuccess) return e;
-    e = cudaMemcpyAsync((uint32_t*)st.d_arg.p + st.flushed_ops, (const uint32_t*)st.arg.p + st.flushed_ops, pend * 4,
-                        cudaMemcpyHostToDevice, h->cstream);
+  if (pend && (all || pend >= kFlushOps) && st.d_ops.cap >= upto * 8) {
+    cudaError_t e = cudaMemcpyAsync((uint64_t*)st.d_ops.p + st.flushed_ops, (const uint64_t*)st.ops.p + st.flushed_ops,
+                                    pend * 8, cudaMemcpyHostToDevice, h->cstream);
     if (e != cudaSuccess) return e;
     st.flushed_ops = upto;
     st.copy_pending = true;
@@ -303,13 +300,12 @@ int reserve_staging(am_sweep* h, std::unique_lock<std::mutex>& lk, size_t n, siz
   for (;;) {
     Staging& st = h->stage[h->cur];
     if (st.n_ops + n > 0x3FFFFFF0ull || st.n_recs + nrec > 0x3FFFFFF0ull) return AM_E_NOSPACE;
-    const size_t want = (st.n_ops + n) * 4, want_r = (st.n_recs + nrec) * sizeof(am_record_t);
-    if (st.idx.cap < want || st.arg.cap < want || (nrec && st.recs.cap < want_r)) {
+    const size_t want = (st.n_ops + n) * 8, want_r = (st.n_recs + nrec) * sizeof(am_record_t);
+    if (st.ops.cap < want || (nrec && st.recs.cap < want_r)) {
       if (st.writers) { h->cv.wait(lk); continue; }  // (the drain may have swapped the areas meanwhile)
       AM_CUDA(h, cudaSetDevice(h->device));
       const bool inflight = st.flushed_ops || st.flushed_recs || st.copy_pending;
-      AM_CUDA(h, grow_pinned(h, st.idx, st.n_ops * 4, want, inflight));
-      AM_CUDA(h, grow_pinned(h, st.arg, st.n_ops * 4, want, inflight));
+      AM_CUDA(h, grow_pinned(h, st.ops, st.n_ops * 8, want, inflight));
       if (nrec) AM_CUDA(h, grow_pinned(h, st.recs, st.n_recs * sizeof(am_record_t), want_r, inflight));
     }
     *out = &st;
@@ -327,7 +323,7 @@ int finish_deferred_clear(am_sweep* h, cudaStream_t s) {
   h->pend_clear = nullptr;
   const size_t n = h->pend_clear_n;
   const unsigned B = 256, G = (unsigned)((n + B - 1) / B);
-  AM_LAUNCH_PDL(clear_marks_kernel, G, B, s, h->marks, (const uint32_t*)st->d_idx.p, (uint32_t)n);
+  AM_LAUNCH_PDL(clear_marks_kernel, G, B, s, h->marks, (const uint2*)st->d_ops.p, (uint32_t)n);
   h->launches++;
   AM_CUDA(h, cudaGetLastError());
   AM_CUDA(h, cudaEventRecord(st->drained, s));
@@ -359,11 +355,10 @@ int drain_staged(am_sweep* h, cudaStream_t s, const int64_t* tick_T = nullptr, b
   // from here on `st` is private to this (single) ticking thread
   const size_t n = st->n_ops, nrec = st->n_recs;
   if (st->hwm > h->n_records) h->n_records = st->hwm;  // every upserted slot extends the swept range
-  if (st->d_idx.cap < n * 4 || st->d_arg.cap < n * 4 || st->d_recs.cap < nrec * sizeof(am_record_t)) {
+  if (st->d_ops.cap < n * 8 || st->d_recs.cap < nrec * sizeof(am_record_t)) {
     // grow the device twins (frees synchronise) and copy everything again
     AM_CUDA(h, cudaStreamSynchronize(h->cstream));
-    AM_CUDA(h, st->d_idx.reserve(n * 4));
-    AM_CUDA(h, st->d_arg.reserve(n * 4));
+    AM_CUDA(h, st->d_ops.reserve(n * 8));
     AM_CUDA(h, st->d_recs.reserve(nrec * sizeof(am_record_t)));
     st->flushed_ops = st->flushed_recs = 0;
   }
@@ -371,18 +366,17 @@ int drain_staged(am_sweep* h, cudaStream_t s, const int64_t* tick_T = nullptr, b
   AM_CUDA(h, cudaEventRecord(st->copied, h->cstream));
   st->copy_pending = true;
   AM_CUDA(h, cudaStreamWaitEvent(s, st->copied, 0));
-  const uint32_t* d_idx = (const uint32_t*)st->d_idx.p;
-  const uint32_t* d_arg = (const uint32_t*)st->d_arg.p;
+  const uint2* d_ops = (const uint2*)st->d_ops.p;
   const am_record_t* d_recs = (const am_record_t*)st->d_recs.p;
   const unsigned B = 256, G = (unsigned)((n + B - 1) / B);
-  AM_LAUNCH(mark_ops_kernel, G, B, s, h->marks, d_idx, d_arg, (uint32_t)n);
+  AM_LAUNCH(mark_ops_kernel, G, B, s, h->marks, d_ops, (uint32_t)n);
   h->launches++;
   if (st->n_state) {
-    AM_LAUNCH_PDL(apply_state_ops_kernel, G, B, s, h->cols, h->marks, d_idx, d_arg, d_recs, (uint32_t)n);
+    AM_LAUNCH_PDL(apply_state_ops_kernel, G, B, s, h->cols, h->marks, d_ops, d_recs, (uint32_t)n);
     h->launches++;
   }
   if (st->n_result) {
-    AM_LAUNCH_PDL(apply_result_ops_kernel, G, B, s, h->cols.flags, h->marks, d_idx, d_arg, (uint32_t)n);
+    AM_LAUNCH_PDL(apply_result_ops_kernel, G, B, s, h->cols.flags, h->marks, d_ops, (uint32_t)n);
     h->launches++;
   }
   // a tick's drain applies sparse results right away (apply_results_now_kernel: no second memory
@@ -394,7 +388,7 @@ int drain_staged(am_sweep* h, cudaStream_t s, const int64_t* tick_T = nullptr, b
       AM_CUDA(h, cudaStreamWaitEvent(s, ts.consumed, 0));
       ts.consumed_pending = false;
     }
-    AM_LAUNCH_PDL(apply_results_now_kernel, G, B, s, h->cols, d_idx, d_arg, (uint32_t)n, *tick_T, ts.acc);
+    AM_LAUNCH_PDL(apply_results_now_kernel, G, B, s, h->cols, d_ops, (uint32_t)n, *tick_T, ts.acc);
     h->launches++;
   }
   if (defer_clear) {  // (the caller runs finish_deferred_clear on the same stream before anything else touches the handle)
@@ -402,7 +396,7 @@ int drain_staged(am_sweep* h, cudaStream_t s, const int64_t* tick_T = nullptr, b
     h->pend_clear_n = n;
     AM_CUDA(h, cudaGetLastError());
   } else {
-    AM_LAUNCH_PDL(clear_marks_kernel, G, B, s, h->marks, d_idx, (uint32_t)n);
+    AM_LAUNCH_PDL(clear_marks_kernel, G, B, s, h->marks, d_ops, (uint32_t)n);
     h->launches++;
     AM_CUDA(h, cudaGetLastError());
     AM_CUDA(h, cudaEventRecord(st->drained, s));
@@ -752,8 +746,8 @@ void am_sweep_destroy(am_sweep_t* h) {
     if (h->due_idx[b]) cudaFree(h->due_idx[b]);
     if (h->due_action[b]) cudaFree(h->due_action[b]);
     Staging& st = h->stage[b];
-    st.idx.release(); st.arg.release(); st.recs.release();
-    st.d_idx.release(); st.d_arg.release(); st.d_recs.release();
+    st.ops.release(); st.recs.release();
+    st.d_ops.release(); st.d_recs.release();
     if (st.copied) cudaEventDestroy(st.copied);
     if (st.drained) cudaEventDestroy(st.drained);
   }
@@ -831,14 +825,12 @@ int am_sweep_upsert(am_sweep_t* h, uint64_t n, const uint64_t* idx, const am_rec
   if (int rc = reserve_staging(h, lk, n, n, &stp)) return rc;
   Staging& st = *stp;
   AM_CUDA(h, cudaSetDevice(h->device));
-  uint32_t* oi = (uint32_t*)st.idx.p + st.n_ops;
-  uint32_t* oa = (uint32_t*)st.arg.p + st.n_ops;
   // nothing is committed (counters unchanged) when a slot is out of range
-  if (amsweep_host::stage_slots(n, idx, h->capacity, oi)) return AM_E_RANGE;
+  if (amsweep_host::stage_slots(n, idx, h->capacity, kOpUpsert | (uint32_t)st.n_recs, 1u, (uint64_t*)st.ops.p + st.n_ops))
+    return AM_E_RANGE;
   am_record_t* dst = (am_record_t*)st.recs.p + st.n_recs;
   uint64_t hwm = st.hwm;
   for (uint64_t k = 0; k < n; ++k) {
-    oa[k] = kOpUpsert | (uint32_t)(st.n_recs + k);
     dst[k] = recs[k];
     dst[k].flags &= ~AM_F_TOMBSTONE;
     dst[k].reserved = 0;
@@ -860,10 +852,7 @@ int am_sweep_remove(am_sweep_t* h, uint64_t n, const uint64_t* idx) {
   if (int rc = reserve_staging(h, lk, n, 0, &stp)) return rc;
   Staging& st = *stp;
   AM_CUDA(h, cudaSetDevice(h->device));
-  uint32_t* oi = (uint32_t*)st.idx.p + st.n_ops;
-  uint32_t* oa = (uint32_t*)st.arg.p + st.n_ops;
-  if (amsweep_host::stage_slots(n, idx, h->capacity, oi)) return AM_E_RANGE;
-  for (uint64_t k = 0; k < n; ++k) oa[k] = kOpRemove;
+  if (amsweep_host::stage_slots(n, idx, h->capacity, kOpRemove, 0u, (uint64_t*)st.ops.p + st.n_ops)) return AM_E_RANGE;
   complete_range(st, st.n_ops, st.n_ops + n);
   st.n_ops += n;
   st.n_state += (uint32_t)n;
@@ -886,8 +875,7 @@ int am_sweep_post_result(am_sweep_t* h, uint64_t n, const uint64_t* idx, const u
   st.n_ops += n;
   st.n_result += (uint32_t)n;
   ++st.writers;  // the drain and any growth of the arrays now wait for this call
-  uint32_t* const oi = (uint32_t*)st.idx.p + a;
-  uint32_t* const oa = (uint32_t*)st.arg.p + a;
+  uint64_t* const oo = (uint64_t*)st.ops.p + a;
   lk.unlock();
   // validate and stage in vectorised passes of one copy chunk each; a single large post hands every
   // finished chunk to the copy stream before staging the next (when no other call is staging).
@@ -897,7 +885,7 @@ int am_sweep_post_result(am_sweep_t* h, uint64_t n, const uint64_t* idx, const u
   for (uint64_t off = 0; off < n && !bad; off += kFlushOps) {
     const uint64_t m = n - off < kFlushOps ? n - off : kFlushOps;
     bad = amsweep_host::stage_results(m, idx + off, phase + off, remedy_phase ? remedy_phase + off : nullptr, h->capacity,
-                                      kOpResult, oi + off, oa + off);
+                                      kOpResult, oo + off);
     if (!bad && off + m < n) {
       lk.lock();
       if (st.writers == 1 && ce == cudaSuccess && cudaSetDevice(h->device) == cudaSuccess)
@@ -908,29 +896,24 @@ int am_sweep_post_result(am_sweep_t* h, uint64_t n, const uint64_t* idx, const u
   // nothing of a call with a bad entry takes effect: its range is already part of the sequence (later
   // calls may have reserved behind it), so it becomes ops that mark and set nothing
   if (bad)
-    for (uint64_t k = 0; k < n; ++k) { oi[k] = 0; oa[k] = kOpResult; }
+    for (uint64_t k = 0; k < n; ++k) oo[k] = (uint64_t)kOpResult << 32;
   lk.lock();
   complete_range(st, a, a + n);
   // Hand the completed prefix to the copy stream, a chunk at a time, even while other calls are staging.
-  // The range is claimed under the lock; the two copies are issued outside it (a copy call under the lock
+  // The range is claimed under the lock; the copy is issued outside it (a copy call under the lock
   // serialised every worker behind the CUDA API: 0.38 ms per post with ten workers), while this call still
   // counts as a writer — the drain, which records the "copied" event, waits for it.
   size_t c_lo = 0, c_hi = 0;
-  if (ce == cudaSuccess && st.done_ops > st.flushed_ops && st.done_ops - st.flushed_ops >= kFlushOps && st.d_idx.cap >= st.done_ops * 4 &&
-      st.d_arg.cap >= st.done_ops * 4) {
+  if (ce == cudaSuccess && st.done_ops > st.flushed_ops && st.done_ops - st.flushed_ops >= kFlushOps && st.d_ops.cap >= st.done_ops * 8) {
     c_lo = st.flushed_ops;
     c_hi = st.done_ops;
     st.flushed_ops = c_hi;
     st.copy_pending = true;
   }
-  const uint32_t* src_i = (const uint32_t*)st.idx.p;  // (the arrays cannot move while this call is a writer)
-  const uint32_t* src_a = (const uint32_t*)st.arg.p;
+  const uint64_t* src = (const uint64_t*)st.ops.p;  // (the array cannot move while this call is a writer)
   lk.unlock();
-  if (c_hi > c_lo && (ce = cudaSetDevice(h->device)) == cudaSuccess) {
-    ce = cudaMemcpyAsync((uint32_t*)st.d_idx.p + c_lo, src_i + c_lo, (c_hi - c_lo) * 4, cudaMemcpyHostToDevice, h->cstream);
-    if (ce == cudaSuccess)
-      ce = cudaMemcpyAsync((uint32_t*)st.d_arg.p + c_lo, src_a + c_lo, (c_hi - c_lo) * 4, cudaMemcpyHostToDevice, h->cstream);
-  }
+  if (c_hi > c_lo && (ce = cudaSetDevice(h->device)) == cudaSuccess)
+    ce = cudaMemcpyAsync((uint64_t*)st.d_ops.p + c_lo, src + c_lo, (c_hi - c_lo) * 8, cudaMemcpyHostToDevice, h->cstream);
   lk.lock();
   if (--st.writers == 0) h->cv.notify_all();
   if (bad) return (bad & 1u) ? AM_E_RANGE : AM_E_INVAL;

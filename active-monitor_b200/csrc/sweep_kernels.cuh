@@ -935,31 +935,31 @@ __global__ void next_due_kernel(DevCols c, uint64_t n, int64_t T, unsigned long 
 // reference observes them in separate watch loops (hcc.go:607-756 and :788-852), so a
 // "Failed" and a remedy "Succeeded" posted by two calls before one tick must both
 // survive.  clear: marks back to zero.  No host-side hashing or sorting.
-// Staged ops are two parallel u32 arrays (slot, arg): arg = kind in the top 2 bits; low
-// 30 bits: record index (upsert) or flag bits (result).
+// A staged op is a uint2 (slot, arg): arg = kind in the top 2 bits; low 30 bits: record index
+// (upsert) or flag bits (result).
 constexpr uint32_t kOpUpsert = 0u << 30, kOpRemove = 1u << 30, kOpResult = 2u << 30, kOpKindMask = 3u << 30;
 constexpr uint32_t kHcBits = AM_F_PENDING_OK | AM_F_PENDING_FAIL;
 constexpr uint32_t kRemedyBits = AM_F_REMEDY_PENDING | AM_F_REMEDY_OUTCOME_OK;
 
-__global__ void mark_ops_kernel(uint32_t* marks, const uint32_t* __restrict__ op_idx,
-                                const uint32_t* __restrict__ op_arg, uint32_t n) {
+__global__ void mark_ops_kernel(uint32_t* marks, const uint2* __restrict__ ops, uint32_t n) {
   pdl_wait();  // (launched with programmatic stream serialisation: nothing of the predecessor is touched before this)
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const uint32_t i = op_idx[k], arg = op_arg[k];
+  const uint2 op = ops[k];
+  const uint32_t i = op.x, arg = op.y;
   if ((arg & kOpKindMask) != kOpResult) { atomicMax(&marks[3u * i], k + 1u); return; }
   if (arg & kHcBits) atomicMax(&marks[3u * i + 1u], k + 1u);
   if (arg & AM_F_REMEDY_PENDING) atomicMax(&marks[3u * i + 2u], k + 1u);
 }
 
 // upserts (hcc.go:170-188 Reconcile) and removes (hcc.go:175-186)
-__global__ void apply_state_ops_kernel(DevCols c, const uint32_t* __restrict__ marks,
-                                       const uint32_t* __restrict__ op_idx, const uint32_t* __restrict__ op_arg,
+__global__ void apply_state_ops_kernel(DevCols c, const uint32_t* __restrict__ marks, const uint2* __restrict__ ops,
                                        const am_record_t* __restrict__ recs, uint32_t n) {
   pdl_wait();  // (launched with programmatic stream serialisation: nothing of the predecessor is touched before this)
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const uint32_t i = op_idx[k], arg = op_arg[k];
+  const uint2 op = ops[k];
+  const uint32_t i = op.x, arg = op.y;
   const uint32_t kind = arg & kOpKindMask;
   if (kind == kOpResult || marks[3u * i] != k + 1u) return;
   if (kind == kOpRemove) { c.flags[i] = AM_F_TOMBSTONE; return; }
@@ -975,13 +975,13 @@ __global__ void apply_state_ops_kernel(DevCols c, const uint32_t* __restrict__ m
 // terminal phases observed by the watch loops (hcc.go:635/:662/:821/:836).  The winner of
 // the workflow phase and the winner of the remedy phase may be two different ops of the
 // same slot: each rewrites only its own bit group, atomically.
-__global__ void apply_result_ops_kernel(uint32_t* flags, const uint32_t* __restrict__ marks,
-                                        const uint32_t* __restrict__ op_idx, const uint32_t* __restrict__ op_arg,
+__global__ void apply_result_ops_kernel(uint32_t* flags, const uint32_t* __restrict__ marks, const uint2* __restrict__ ops,
                                         uint32_t n) {
   pdl_wait();  // (launched with programmatic stream serialisation: nothing of the predecessor is touched before this)
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const uint32_t i = op_idx[k], arg = op_arg[k];
+  const uint2 op = ops[k];
+  const uint32_t i = op.x, arg = op.y;
   if ((arg & kOpKindMask) != kOpResult) return;
   const uint32_t s = marks[3u * i];
   if (k + 1u < s) return;  // posted before the slot's latest upsert / remove
@@ -1005,14 +1005,16 @@ __global__ void apply_result_ops_kernel(uint32_t* flags, const uint32_t* __restr
 // timer-armed state it leaves is exactly what the sweep's own step 1 would have decided on.  Only the
 // tick's drain does this (T is the tick's second) and only when results are sparse; a read drains
 // without it, and a dense batch is cheaper as the sweep's streaming path.
-__global__ void apply_results_now_kernel(DevCols c, const uint32_t* __restrict__ op_idx, const uint32_t* __restrict__ op_arg,
-                                         uint32_t n, int64_t T, unsigned long long* acc) {
+__global__ void apply_results_now_kernel(DevCols c, const uint2* __restrict__ ops, uint32_t n, int64_t T,
+                                         unsigned long long* acc) {
   pdl_wait();  // (launched with programmatic stream serialisation: nothing of the predecessor is touched before this)
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   constexpr uint32_t kPend = AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING;
   uint32_t res = 0;
-  if (k < n && (op_arg[k] & kOpKindMask) == kOpResult) {
-    const uint32_t i = op_idx[k];
+  uint2 op = make_uint2(0u, 0u);
+  if (k < n) op = ops[k];
+  if (k < n && (op.y & kOpKindMask) == kOpResult) {
+    const uint32_t i = op.x;
     const uint32_t f0 = c.flags[i];
     const bool live = ((0x3Eu >> (f0 & AM_KIND_MASK)) & 1u) && !(f0 & AM_F_TOMBSTONE);
     if (live && (f0 & kPend)) {
@@ -1061,11 +1063,11 @@ __global__ void apply_results_now_kernel(DevCols c, const uint32_t* __restrict__
   }
 }
 
-__global__ void clear_marks_kernel(uint32_t* marks, const uint32_t* __restrict__ op_idx, uint32_t n) {
+__global__ void clear_marks_kernel(uint32_t* marks, const uint2* __restrict__ ops, uint32_t n) {
   pdl_wait();  // (launched with programmatic stream serialisation: nothing of the predecessor is touched before this)
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
-  const uint32_t i = op_idx[k];
+  const uint32_t i = ops[k].x;
   marks[3u * i] = 0;
   marks[3u * i + 1u] = 0;
   marks[3u * i + 2u] = 0;
