@@ -375,20 +375,20 @@ int drain_staged(am_sweep* h, cudaStream_t s, const int64_t* tick_T = nullptr, b
     AM_LAUNCH_PDL(apply_state_ops_kernel, G, B, s, h->cols, h->marks, d_ops, d_recs, (uint32_t)n);
     h->launches++;
   }
-  if (st->n_result) {
-    AM_LAUNCH_PDL(apply_result_ops_kernel, G, B, s, h->cols.flags, h->marks, d_ops, (uint32_t)n);
-    h->launches++;
-  }
-  // a tick's drain applies sparse results right away (apply_results_now_kernel: no second memory
-  // round trip in the sweep); a read's drain, or a batch touching more than an eighth of the
-  // records, leaves them pending for the sweep's own streaming path
+  // A tick's drain applies sparse results right away (apply_results_now_kernel: no second memory round trip
+  // in the sweep, and the posted bits never pass through the flags as a separate step); a read's drain, or a
+  // batch touching more than an eighth of the records, leaves them pending in the flags for the sweep's own
+  // streaming path (apply_result_ops_kernel).
   if (tick_T && st->n_result && h->early_results && (uint64_t)st->n_result * 8 <= h->n_records) {
     TickSet& ts = h->set[h->parity];  // the buffer set of the tick being prepared
     if (ts.consumed_pending) {        // (its statistics may still be read by an exchange on another stream)
       AM_CUDA(h, cudaStreamWaitEvent(s, ts.consumed, 0));
       ts.consumed_pending = false;
     }
-    AM_LAUNCH_PDL(apply_results_now_kernel, G, B, s, h->cols, d_ops, (uint32_t)n, *tick_T, ts.acc);
+    AM_LAUNCH_PDL(apply_results_now_kernel, G, B, s, h->cols, h->marks, d_ops, (uint32_t)n, *tick_T, ts.acc);
+    h->launches++;
+  } else if (st->n_result) {
+    AM_LAUNCH_PDL(apply_result_ops_kernel, G, B, s, h->cols.flags, h->marks, d_ops, (uint32_t)n);
     h->launches++;
   }
   if (defer_clear) {  // (the caller runs finish_deferred_clear on the same stream before anything else touches the handle)

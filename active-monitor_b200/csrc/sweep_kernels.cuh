@@ -998,15 +998,15 @@ __global__ void apply_result_ops_kernel(uint32_t* flags, const uint32_t* __restr
 // In the sweep a record with a posted result costs its warp a second, dependent memory round trip
 // (the remedy / counter columns) behind the streaming loads; with a result on ~2 % of the records
 // nine warps in ten pay it and the tick's sweep slows from 84 to 143 us at 10 M records
-// (profiles/r02_e2e_breakdown.json).  Here every result is its own thread: one claims the slot's
-// pending bits (atomicAnd: a slot can have two winning ops, workflow phase and remedy phase), gathers
-// the eight state columns, runs the same apply_result and scatters what changed.  The action bits go
+// (profiles/r02_e2e_breakdown.json).  Here every result is its own thread: the slot's owner (see below)
+// merges the posted bits into the flags, gathers the state columns its case needs, runs the same
+// apply_result and scatters what changed — this kernel REPLACES apply_result_ops_kernel for such a drain.  The action bits go
 // into the flags' carry bits for the sweep of the SAME tick to emit (it clears them); the finishedAt /
 // timer-armed state it leaves is exactly what the sweep's own step 1 would have decided on.  Only the
 // tick's drain does this (T is the tick's second) and only when results are sparse; a read drains
 // without it, and a dense batch is cheaper as the sweep's streaming path.
-__global__ void apply_results_now_kernel(DevCols c, const uint2* __restrict__ ops, uint32_t n, int64_t T,
-                                         unsigned long long* acc) {
+__global__ void apply_results_now_kernel(DevCols c, const uint32_t* __restrict__ marks, const uint2* __restrict__ ops, uint32_t n,
+                                         int64_t T, unsigned long long* acc) {
   pdl_wait();  // (launched with programmatic stream serialisation: nothing of the predecessor is touched before this)
   const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   constexpr uint32_t kPend = AM_F_PENDING_OK | AM_F_PENDING_FAIL | AM_F_REMEDY_PENDING;
@@ -1014,12 +1014,22 @@ __global__ void apply_results_now_kernel(DevCols c, const uint2* __restrict__ op
   uint2 op = make_uint2(0u, 0u);
   if (k < n) op = ops[k];
   if (k < n && (op.y & kOpKindMask) == kOpResult) {
-    const uint32_t i = op.x;
-    const uint32_t f0 = c.flags[i];
-    const bool live = ((0x3Eu >> (f0 & AM_KIND_MASK)) & 1u) && !(f0 & AM_F_TOMBSTONE);
-    if (live && (f0 & kPend)) {
-      const uint32_t old = atomicAnd(&c.flags[i], ~(kPend | AM_F_REMEDY_OUTCOME_OK));
-      if (old & kPend) {  // this thread owns the slot's results (another op of the slot finds none)
+    const uint32_t i = op.x, arg = op.y;
+    const uint32_t s_state = marks[3u * i], hcw = marks[3u * i + 1u], rmw = marks[3u * i + 2u];
+    // The winners of the slot's two phase groups (apply_result_ops_kernel's rule: the latest op of a group, if
+    // it was posted after the slot's latest upsert / remove) may be two different ops; ONE thread owns the
+    // slot here — the workflow-phase winner, else the remedy-phase winner — and takes the other group's
+    // bits from that op, so the flags are read and written once, without atomics.
+    const bool hc_valid = hcw != 0u && hcw >= s_state, rm_valid = rmw != 0u && rmw >= s_state;
+    const bool mine_hc = hc_valid && hcw == k + 1u, mine_rm = rm_valid && rmw == k + 1u;
+    if (mine_hc || (mine_rm && !hc_valid)) {
+      uint32_t f = c.flags[i];
+      if (mine_hc) f = (f & ~kHcBits) | (arg & kHcBits);
+      if (rm_valid) f = (f & ~kRemedyBits) | ((mine_rm ? arg : ops[rmw - 1u].y) & kRemedyBits);
+      const bool live = ((0x3Eu >> (f & AM_KIND_MASK)) & 1u) && !(f & AM_F_TOMBSTONE);
+      if (!live || !(f & kPend)) {
+        c.flags[i] = f;  // (a record the sweep does not evaluate keeps its posted result)
+      } else {
         // Gather only what this result can touch (every column is its own 32-B sector of a random record):
         // a "Succeeded" on a check without remedy reads its success counter and nothing else — two gathers
         // instead of ten; with all ten the kernel took as long (56 us for 0.18 M results) as the sweep's own
@@ -1027,10 +1037,10 @@ __global__ void apply_results_now_kernel(DevCols c, const uint2* __restrict__ op
         //   Succeeded: SuccessCount;            with a remedy workflow: RemedyTotalRuns (reset on pass)
         //   Failed:    FailedCount;             with a remedy workflow: the gate (limit, reset interval, total, finishedAt)
         //   a remedy outcome (applied only behind a Failed that runs the remedy, or on its own): the remedy counters
-        const bool r_ok = (old & AM_F_PENDING_OK) != 0, r_fail = !r_ok && (old & AM_F_PENDING_FAIL) != 0;
-        const bool remedy_state = ((r_ok || r_fail) && (old & AM_F_HAS_REMEDY)) || (!r_ok && !r_fail);
+        const bool r_ok = (f & AM_F_PENDING_OK) != 0, r_fail = !r_ok && (f & AM_F_PENDING_FAIL) != 0;
+        const bool remedy_state = ((r_ok || r_fail) && (f & AM_F_HAS_REMEDY)) || (!r_ok && !r_fail);
         RecState s{};
-        s.flags = old;  // (finishedAt is only ever overwritten with T by a workflow result: not read)
+        s.flags = f;  // (finishedAt is only ever overwritten with T by a workflow result: not read)
         if (r_ok) s.s = c.success[i];
         if (r_fail) s.f = c.failed[i];
         if (remedy_state) {
@@ -1046,8 +1056,7 @@ __global__ void apply_results_now_kernel(DevCols c, const uint2* __restrict__ op
         if (s.rf != b.rf) c.remedy_failed[i] = s.rf;
         if (s.rt != b.rt) c.remedy_total[i] = s.rt;
         if (s.rfa != b.rfa) c.remedy_finished_at[i] = s.rfa;
-        const uint32_t set = (s.flags & AM_F_TIMER_ARMED) | carry_of_actions(a);
-        if (set) atomicOr(&c.flags[i], set);
+        c.flags[i] = s.flags | carry_of_actions(a);  // pending bits cleared, timer armed, action bits for this tick's sweep
       }
     }
   }

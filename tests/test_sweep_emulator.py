@@ -325,14 +325,16 @@ def test_concurrent_posts_from_many_threads(am, orc, gen):
         np.testing.assert_array_equal(dev["success"][rest], prod["success"][rest])
 
 
-@pytest.mark.parametrize("every", [23, 3])
-def test_posted_results_sparse_and_dense_paths(am, orc, gen, every):
+@pytest.mark.parametrize("every,early", [(23, None), (3, None), (23, "0")])
+def test_posted_results_sparse_and_dense_paths(am, orc, gen, monkeypatch, every, early):
     """Results posted between ticks are applied at the tick's drain by apply_results_now_kernel when they
     are sparse (ops <= 1/8 of the records: `every` = 23) — their action bits travel to the same tick's sweep in
     the flags' carry bits — and inside the sweep when they are dense (`every` = 3).  Both must equal the
     oracle: list, action bytes (RUN_REMEDY, REMEDY_SKIP, RESET_ON_PASS, RESET_ON_INTERVAL, ANOMALY all
     occur in the config-3 mix), statistics, every column; over three ticks, with workflow and remedy phases
     posted by separate calls."""
+    if early is not None:  # "0": the sparse batch too goes through the flags and the sweep's own result path
+        monkeypatch.setenv("AMSWEEP_EARLY_RESULTS", early)
     n = 40_000
     prod, orac = _gen_pair(gen, am, orc, 3, 12, n, T0)
     pend = am.F_PENDING_OK | am.F_PENDING_FAIL | am.F_REMEDY_PENDING | am.F_REMEDY_OUTCOME_OK
@@ -355,8 +357,8 @@ def test_posted_results_sparse_and_dense_paths(am, orc, gen, every):
                                                  am.F_REMEDY_PENDING).astype(np.uint32)
             l0 = s.launch_count
             got, want = s.tick(T), orc.sweep(orac, T)
-            # mark, apply_result_ops, [apply_results_now], clear_marks + tz_words (on-minute tick, zones registered), sweep, scan, expand, publish
-            assert s.launch_count - l0 == (9 if every == 23 else 8), s.launch_count - l0
+            # mark, apply_result_ops OR apply_results_now, clear_marks + tz_words (on-minute tick, zones registered), sweep, scan, expand, publish
+            assert s.launch_count - l0 == 8, s.launch_count - l0
             _assert_tick_equal(am, got, want, s, orac, n, f"every={every} tick {k}")
             seen |= int(np.bitwise_or.reduce(want[1]))
         assert not np.any(s.read_range(0, n)["flags"] & am.F_CARRY_MASK)
