@@ -61,6 +61,27 @@ WORKLOAD = {
 }
 
 
+def gpu_numa_cpus(torch, device_index: int):
+    """CPUs of the NUMA node the GPU hangs off (its PCIe root), within the process's affinity; None when
+    the topology cannot be read.  The timed GPU arm runs on them, as any GPU host process is normally bound
+    (numactl): pinned buffers are then allocated on that node and the threads that fill and read them are
+    next to them — without it a whole e2e run moved by up to 1.8x with where the scheduler put the threads."""
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return (node, cpus) if len(cpus) >= 2 else None
+    except Exception:
+        return None
+
+
 def host_threads() -> int:
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -249,6 +270,10 @@ def main():
         raise SystemExit("--config 3 / 5 are single-GPU lines; the multi-GPU step is config 2 (BASELINE configs[3])")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    numa = gpu_numa_cpus(torch, local_rank)
+    if numa is not None:
+        os.sched_setaffinity(0, numa[1])  # (the CPU baseline below widens it again for its own run)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -657,6 +682,7 @@ def main():
                    "walk_list_per_worker": c_loop["walk_s"] / reps * 1e3},
                "consumer_workers": c_loop["workers"] if c_loop else 1,
                "runs_ms_per_step": c_loop["runs_ms_per_step"] if c_loop else None,
+               "host_cpus": (f"NUMA node {numa[0]} of the GPU ({len(numa[1])} CPUs)" if numa is not None else "unbound"),
                "driver": ("compiled loop calling the C-ABI (tools/amgen/amgen.c amgen_e2e_closed_loop): tick on one thread, "
                           "then the list walked in pieces and posted back by the consumer workers (the controller's "
                           "reconcile workers, hcc.go:170-188)") if c_loop
@@ -690,6 +716,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and config == 2:
         import oracle_c
+        os.sched_setaffinity(0, all_cpus)  # the CPU arm gets every core the process was given
         threads = host_threads()
         host_cols = amgen.fill(config, seed, 0, n, T0, oracle_c.load().orc_classify, threads=min(threads, 64))
         t_mt = cpu_sweep_times(host_cols, T0, 0, threads, oracle_c, seconds=args.cpu_seconds)
