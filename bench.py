@@ -236,10 +236,10 @@ def main():
                     "(spell it --records-per-gpu under torchrun: its parser rejects the abbreviation-like --n)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--e2e-workers", type=int, default=4, help="consumer threads of the e2e loop (walk the tick's "
-                    "list and post results back: the reference's reconcile workers, hcc.go:170-188; its --max-workers "
-                    "defaults to 10, cmd/main.go:144).  4: the step is 0.46-0.50 ms on every box measured; with 6-10 it "
-                    "ranged from 0.46 to 1.03 ms depending on where the threads landed (profiles/r02_e2e_breakdown.json)")
+    ap.add_argument("--e2e-workers", type=int, default=10, help="consumer threads of the e2e loop (walk the tick's "
+                    "list and post results back: the reference's reconcile workers, hcc.go:170-188); default = the "
+                    "reference's default --max-workers (cmd/main.go:144).  Bound to the GPU's NUMA node the step is "
+                    "0.34 / 0.32 / 0.32 / 0.32 ms with 4 / 6 / 10 / 16 workers (profiles/r02_e2e_breakdown.json)")
     ap.add_argument("--no-verify", action="store_true", help="N>1: skip the oracle check of the gathered list")
     ap.add_argument("--gather", default="exchange", choices=["exchange", "plain", "nccl"],
                     help="N>1: NVLink tick exchange (bitmap + exceptions, list rebuilt on every GPU), the round-1 "
