@@ -159,6 +159,8 @@ SYMBOLS = {
     "am_gather_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "am_gather_set_layout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "am_gather_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "am_gather_bind": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "am_gather_tick_view": (C.c_int, [C.c_void_p, i64, u32, P(AmTickView), P(AmTickStats)]),
     "am_gather_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, u64, C.c_void_p]),
     "am_gather_out_idx": (C.c_void_p, [C.c_void_p]),
     "am_gather_out_act": (C.c_void_p, [C.c_void_p]),

@@ -64,6 +64,12 @@ struct am_gather {
   unsigned long long push_timeout_ms = 5000;      // AMSWEEP_PUSH_TIMEOUT_MS, 0 = none
   bool profiling = false, profiled = false;       // am_gather_set_profiling: events around the exchange's kernels
   cudaEvent_t evp[4] = {nullptr, nullptr, nullptr, nullptr};
+  // am_gather_bind / am_gather_tick_view: one e2e step of a multi-GPU shard in one call
+  am_sweep_t* bound = nullptr;
+  cudaStream_t s_sweep = nullptr, s_exchange = nullptr;
+  unsigned char* view_host = nullptr;   // mapped pinned: u32 idx[cap] | u8 act[cap] | u64 n | am_tick_stats_t
+  uint64_t view_cap = 0;
+  cudaEvent_t view_done = nullptr;
   std::string last_error;
 };
 
@@ -268,6 +274,62 @@ int am_gather_exchange(am_gather_t* g, am_sweep_t* sweep, void* d_stats, void* c
   return rc;
 }
 
+int am_gather_bind(am_gather_t* g, am_sweep_t* shard, void* sweep_stream, void* exchange_stream) {
+  if (!g || !shard) return AM_E_INVAL;
+  if (!g->layout) return AM_E_INVAL;
+  AMG_CUDA(g, cudaSetDevice(g->device));
+  const uint64_t cap = g->sizes[g->rank];
+  if (!g->view_host || g->view_cap < cap) {
+    if (g->view_host) cudaFreeHost(g->view_host);
+    g->view_host = nullptr;
+    AMG_CUDA(g, cudaHostAlloc((void**)&g->view_host, cap * 5 + 64 + sizeof(am_tick_stats_t), cudaHostAllocMapped));
+    g->view_cap = cap;
+  }
+  if (!g->view_done) AMG_CUDA(g, cudaEventCreateWithFlags(&g->view_done, cudaEventDisableTiming));
+  g->bound = shard;
+  g->s_sweep = (cudaStream_t)sweep_stream;
+  g->s_exchange = (cudaStream_t)exchange_stream;
+  return AM_OK;
+}
+
+int am_gather_tick_view(am_gather_t* g, int64_t unix_sec, uint32_t mode, am_tick_view_t* view, am_tick_stats_t* stats) {
+  if (!g || !view || !g->bound) return AM_E_INVAL;
+  AMG_CUDA(g, cudaSetDevice(g->device));
+  unsigned char* h = g->view_host;
+  unsigned char* d = nullptr;
+  AMG_CUDA(g, cudaHostGetDevicePointer((void**)&d, h, 0));
+  const size_t off_act = g->view_cap * 4, off_n = (g->view_cap * 5 + 7) / 8 * 8, off_st = off_n + 8;
+  int rc = am_sweep_tick_shard(g->bound, unix_sec, mode, g->s_sweep);
+  if (rc != AM_OK) { g->last_error = am_last_error_detail(g->bound); return rc; }
+  rc = am_gather_exchange(g, g->bound, d + off_st, g->s_exchange);
+  if (rc != AM_OK) return rc;
+  ExtractParams x{};
+  const int buf = g->epoch & 1;
+  x.gidx = g->block + g->off_idx[buf];
+  x.gact = g->block + g->off_act[buf];
+  x.counts = g->out_counts;
+  x.out_idx = (uint32_t*)d;
+  x.out_act = d + off_act;
+  x.out_n = (unsigned long long*)(d + off_n);
+  x.shard_base = g->bases[g->rank];
+  x.cap = g->view_cap;
+  x.rank = g->rank;
+  x.world = g->world;
+  x.idx_bytes = g->idx_bytes;
+  AM_LAUNCH(gather_extract_own_kernel, 148, 256, g->s_exchange, x);
+  AMG_CUDA(g, cudaGetLastError());
+  AMG_CUDA(g, cudaEventRecord(g->view_done, g->s_exchange));
+  AMG_CUDA(g, cudaEventSynchronize(g->view_done));
+  const unsigned long long n = *(const volatile unsigned long long*)(h + off_n);
+  if ((n >> 32) == kPeerTimeout) { g->last_error = "am_gather_tick_view: a peer did not arrive in time"; return AM_E_DEVICE; }
+  view->idx_local = (const uint32_t*)h;
+  view->action = h + off_act;
+  view->n = n;
+  view->shard_base = g->bases[g->rank];
+  if (stats) memcpy(stats, h + off_st, sizeof *stats);
+  return AM_OK;
+}
+
 int am_gather_push(am_gather_t* g, const void* d_idx_local, const void* d_act_local,
                    const void* d_count_local, uint64_t shard_base, void* cuda_stream) {
   if (!g || !d_idx_local || !d_act_local || !d_count_local) return AM_E_INVAL;
@@ -334,6 +396,8 @@ void am_gather_destroy(am_gather_t* g) {
   if (g->out_counts) cudaFree(g->out_counts);
   if (g->status) cudaFree(g->status);
   for (int k = 0; k < 4; ++k) if (g->evp[k]) cudaEventDestroy(g->evp[k]);
+  if (g->view_done) cudaEventDestroy(g->view_done);
+  if (g->view_host) cudaFreeHost(g->view_host);
   delete g;
 }
 

@@ -300,4 +300,34 @@ __global__ void gather_counts_kernel(const CountsParams p) {
   p.out_counts[p.world] = (uint32_t)(total < p.cap_total ? total : p.cap_total);
 }
 
+// This rank's own part of the rebuilt global list — its checks, as LOCAL slots — into (mapped host) memory:
+// the multi-GPU counterpart of am_sweep_tick_view.  The part's offset follows from the counts on the device,
+// so the host needs no count before the copy and synchronises once.
+struct ExtractParams {
+  const void* gidx;          // global list, u32 or u64
+  const uint8_t* gact;
+  const uint32_t* counts;    // [world + 1]
+  uint32_t* out_idx;         // [cap] local slots
+  uint8_t* out_act;          // [cap]
+  unsigned long long* out_n; // entries written (kPeerTimeout << 32 when a peer timed out)
+  uint64_t shard_base, cap;
+  int rank, world, idx_bytes;
+};
+__global__ void gather_extract_own_kernel(const ExtractParams p) {
+  uint64_t off = 0;
+  for (int r = 0; r < p.rank; ++r) off += p.counts[r];
+  const bool timed_out = p.counts[p.world] == kPeerTimeout;
+  uint64_t mine = timed_out ? 0 : p.counts[p.rank];
+  if (mine > p.cap) mine = p.cap;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < mine; k += stride) {
+    const uint64_t g = p.idx_bytes == 4 ? (uint64_t)reinterpret_cast<const uint32_t*>(p.gidx)[off + k]
+                                        : reinterpret_cast<const uint64_t*>(p.gidx)[off + k];
+    // (u32 global indices wrap at 2^32 exactly as the shard base does: the difference is the local slot)
+    p.out_idx[k] = p.idx_bytes == 4 ? (uint32_t)g - (uint32_t)p.shard_base : (uint32_t)(g - p.shard_base);
+    p.out_act[k] = p.gact[off + k];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.out_n = timed_out ? ((unsigned long long)kPeerTimeout << 32) : mine;
+}
+
 }  // namespace

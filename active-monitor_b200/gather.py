@@ -125,6 +125,26 @@ class PeerGather:
         self._check(self._lib.am_gather_exchange(self._h, sweep._h, d_stats_ptr or None, stream or None),
                     "am_gather_exchange")
 
+    def bind(self, sweep, sweep_stream: int = 0, exchange_stream: int = 0):
+        """name the shard and the two streams of tick_view()"""
+        self._check(self._lib.am_gather_bind(self._h, sweep._h, sweep_stream or None, exchange_stream or None),
+                    "am_gather_bind")
+
+    def tick_view(self, unix_sec: int, mode: int = 0):
+        """one whole step of the bound shard (tick_shard + exchange + this rank's own part of the global list as
+        local slots in the library's pinned host memory): (u32 local idx view, u8 action view, stats of the shard)"""
+        import numpy as np
+        from . import _lib as L
+        C = self._C
+        v, st = L.AmTickView(), L.AmTickStats()
+        self._check(self._lib.am_gather_tick_view(self._h, unix_sec, mode, C.byref(v), C.byref(st)), "am_gather_tick_view")
+        n = int(v.n)
+        if n == 0:
+            return np.empty(0, np.uint32), np.empty(0, np.uint8), st.as_dict()
+        idx = np.ctypeslib.as_array(C.cast(v.idx_local, C.POINTER(C.c_uint32)), shape=(n,))
+        act = np.ctypeslib.as_array(C.cast(v.action, C.POINTER(C.c_uint8)), shape=(n,))
+        return idx, act, st.as_dict()
+
     def set_profiling(self, on: bool):
         self._check(self._lib.am_gather_set_profiling(self._h, int(on)), "am_gather_set_profiling")
 

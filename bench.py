@@ -240,6 +240,8 @@ def main():
                     "list and post results back: the reference's reconcile workers, hcc.go:170-188); default = the "
                     "reference's default --max-workers (cmd/main.go:144).  Bound to the GPU's NUMA node the step is "
                     "0.34 / 0.32 / 0.32 / 0.32 ms with 4 / 6 / 10 / 16 workers (profiles/r02_e2e_breakdown.json)")
+    ap.add_argument("--e2e-python-loop", action="store_true", help="N>1: the round-2 python e2e loop (tick_shard, exchange, "
+                    "read-back with torch copies) instead of the compiled loop over am_gather_tick_view")
     ap.add_argument("--no-verify", action="store_true", help="N>1: skip the oracle check of the gathered list")
     ap.add_argument("--gather", default="exchange", choices=["exchange", "plain", "nccl"],
                     help="N>1: NVLink tick exchange (bitmap + exceptions, list rebuilt on every GPU), the round-1 "
@@ -620,7 +622,23 @@ def main():
         h2d = d2h = 0
         h_part = torch.empty(n * 9 + 64, dtype=torch.uint8).pin_memory() if peer is not None and mode_gather == "exchange" else None
         c_loop = None
-        if h_part is None:
+        if h_part is not None and not args.e2e_python_loop:
+            # N>1: the same compiled loop; its tick is am_gather_tick_view — am_sweep_tick_shard + the NVLink exchange +
+            # this rank's own part of the global list into pinned host memory, one synchronisation.  The ranks run their
+            # loops side by side and meet in every exchange.
+            workers = max(1, min(args.e2e_workers, len(os.sched_getaffinity(0)) - 1))
+            peer.bind(sweep, stream.cuda_stream, gstream.cuda_stream)
+            barrier()
+            runs = []
+            for r in range(3):
+                runs.append(amgen.e2e_closed_loop(lib, sweep._h, T0 + r * (reps + 8), am.SWEEP_FULL_SCAN, 8, reps, n,
+                                                  workers=workers, gather_handle=peer._h))
+            c_loop = sorted(runs, key=lambda c: c["seconds"])[1]
+            c_loop["runs_ms_per_step"] = [round(c["seconds"] / reps * 1e3, 4) for c in runs]
+            dt, h2d, d2h = c_loop["seconds"], c_loop["h2d_bytes"], c_loop["d2h_bytes"]
+            torch.cuda.synchronize()
+            barrier()
+        elif h_part is None:
             # N=1: the loop itself is compiled code calling the C-ABI, as the cgo shim is — ctypes and
             # numpy plumbing per call would otherwise be a tenth of the step
             workers = max(1, min(args.e2e_workers, len(os.sched_getaffinity(0)) - 1))
@@ -689,8 +707,10 @@ def main():
                          else "python loop (ctypes + torch)",
                "api": ("am_sweep_post_result + am_sweep_tick_view (the GPU writes the list into the library's pinned "
                        "host buffer)" if h_part is None else
-                       "am_sweep_post_result + am_sweep_tick_shard + am_gather_exchange + read-back of this rank's "
-                       "part of the global list") + ", consecutive 1 s ticks, host-closed loop, AM_SWEEP_FULL_SCAN"}
+                       ("am_sweep_post_result + am_gather_tick_view (am_sweep_tick_shard + the NVLink exchange + this rank's "
+                        "own part of the global list extracted into pinned host memory, one synchronisation)" if c_loop else
+                        "am_sweep_post_result + am_sweep_tick_shard + am_gather_exchange + read-back of this rank's "
+                        "part of the global list")) + ", consecutive 1 s ticks, host-closed loop, AM_SWEEP_FULL_SCAN"}
     elif config == 3:
         # the host path of this step: post the 7.5 M pending results, tick, read the list
         fl = cols["flags"]

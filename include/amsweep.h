@@ -413,6 +413,15 @@ int am_gather_connect(am_gather_t*, const void* handles /* world x AM_IPC_HANDLE
  * arrays on every rank).  Required before am_gather_exchange. */
 int am_gather_set_layout(am_gather_t*, const uint64_t* bases, const uint64_t* sizes);
 int am_gather_exchange(am_gather_t*, am_sweep_t* shard, void* d_stats, void* cuda_stream);
+/* One whole step of a sharded controller in one call — the multi-GPU counterpart of am_sweep_tick_view:
+ * am_sweep_tick_shard of the bound shard on `sweep_stream` (draining what was posted to it), the
+ * exchange on `exchange_stream`, then THIS rank's own part of the global list — its checks, as local
+ * slots — extracted into the library's pinned host buffer; one synchronisation.  am_gather_bind names
+ * the shard and the two streams once; the view is valid until the next call.  AM_E_DEVICE when a peer
+ * did not arrive within AMSWEEP_PUSH_TIMEOUT_MS.  (The global list itself stays on the device:
+ * am_gather_out_idx / _act / _counts.) */
+int am_gather_bind(am_gather_t*, am_sweep_t* shard, void* sweep_stream, void* exchange_stream);
+int am_gather_tick_view(am_gather_t*, int64_t unix_sec, uint32_t mode, am_tick_view_t* view, am_tick_stats_t* stats);
 /* Round-1 "plain" format, kept as the measured baseline: every rank writes its FINISHED
  * list (the output of am_sweep_tick_device: u32 local indices, u8 actions, device count)
  * straight into every peer's output buffer at its global offset, 5 or 9 bytes per entry

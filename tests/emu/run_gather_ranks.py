@@ -11,6 +11,8 @@ tick : every rank owns an index-range shard of ONE amgen population (am.Sweep on
        global list, counts and shard statistics must equal the UNSHARDED oracle sweep, and the
        shard's columns the oracle's columns at the end.
        EMU_ABSENT_RANK=r: rank r never exchanges; the others must report the watchdog value.
+       EMU_TICK_VIEW=1: the step through am_gather_bind + am_gather_tick_view; the view must be the rank's own
+       part of the list as local slots.
 plain: the round-1 list format (am_gather_push) against the concatenation of random lists.
 Prints "ok ..." and exits 0 on success."""
 import ctypes as C
@@ -34,6 +36,7 @@ mode, world, idx_bytes, n_arg, ticks = sys.argv[1], int(sys.argv[2]), int(sys.ar
 config = int(sys.argv[6]) if len(sys.argv) > 6 else 3
 T0 = 1789982100
 absent = int(os.environ.get("EMU_ABSENT_RANK", "-1"))
+use_view = os.environ.get("EMU_TICK_VIEW") == "1"  # am_gather_tick_view instead of tick_shard + exchange
 handles = [None] * world
 errors = []
 bar = threading.Barrier(world)
@@ -95,13 +98,27 @@ if mode == "tick":
             assert lib.am_gather_set_layout(h, bases.ctypes.data, sizes.ctypes.data) == 0
             # argument errors come back before anything a peer could observe happens
             assert lib.am_gather_exchange(h, s._h, None, None) == abi.AM_E_INVAL  # no tick_shard yet
+            if use_view:
+                assert lib.am_gather_tick_view(h, T0, 0, C.byref(abi.AmTickView()), None) == abi.AM_E_INVAL  # not bound yet
+                assert lib.am_gather_bind(h, s._h, None, None) == 0
             st = np.zeros(1, dtype=abi.STATS_DTYPE)
             for k, (T, wi, wa) in enumerate(want):  # no barrier between ticks, as on a stream
                 if rank == absent:
                     continue
-                s.tick_shard(T)
-                rc = lib.am_gather_exchange(h, s._h, st.ctypes.data, None)
-                assert rc == 0, (rc, lib.am_gather_last_error(h))
+                vw = None
+                if use_view:  # the whole step in one call (am_gather_bind + am_gather_tick_view)
+                    v = abi.AmTickView()
+                    rc = lib.am_gather_tick_view(h, T, 0, C.byref(v), C.cast(st.ctypes.data, C.POINTER(abi.AmTickStats)))
+                    if absent >= 0:
+                        assert rc == abi.AM_E_DEVICE, rc  # a peer never arrived: the watchdog, reported as an error
+                    else:
+                        assert rc == 0, (rc, lib.am_gather_last_error(h))
+                        vw = (view(C.cast(v.idx_local, C.c_void_p).value, int(v.n), C.c_uint32, np.uint32),
+                              view(C.cast(v.action, C.c_void_p).value, int(v.n), C.c_uint8, np.uint8), int(v.shard_base))
+                else:
+                    s.tick_shard(T)
+                    rc = lib.am_gather_exchange(h, s._h, st.ctypes.data, None)
+                    assert rc == 0, (rc, lib.am_gather_last_error(h))
                 counts = out_counts(h)
                 if absent >= 0:
                     assert int(counts[world]) == 0xFFFFFFFF, counts
@@ -114,6 +131,10 @@ if mode == "tick":
                 oi, oa, ost = oracle_c.sweep(ocols, T, shard_base=first)  # this shard alone
                 got = {f: int(st[f][0]) for f in abi.STAT_FIELDS}
                 assert got == ost, (rank, k, got, ost)
+                if vw is not None:  # this rank's own part of the global list, as local slots
+                    assert vw[2] == first
+                    np.testing.assert_array_equal(vw[0].astype(np.uint64) + np.uint64(first), oi, err_msg=f"rank {rank} tick {k} view idx")
+                    np.testing.assert_array_equal(vw[1].astype(np.uint32), oa, err_msg=f"rank {rank} tick {k} view act")
                 assert [int(c) for c in counts[:world]] == [int(((wi >= b) & (wi < b + z)).sum()) for b, z in zip(bases, sizes)]
             if absent < 0:
                 dev = s.read_range(0, cnt)

@@ -55,6 +55,21 @@ def test_exchanged_ticks_equal_the_unsharded_oracle(emu_lib, case):
     _run(emu_lib, ["tick"] + list(case))
 
 
+@pytest.mark.parametrize("case", [(2, 4, 40_000, 4, 3), (3, 8, 30_011, 4, 2), (8, 4, 65_536, 3, 3), (5, 4, 5, 2, 2)],
+                         ids=lambda c: "w{}_b{}_n{}_t{}_c{}".format(*c))
+def test_whole_step_in_one_call_returns_the_ranks_own_part_as_local_slots(emu_lib, case):
+    """am_gather_bind + am_gather_tick_view: tick_shard + exchange + extraction of the rank's own part of the
+    global list into pinned host memory, one synchronisation; the global list, the shard statistics and the view
+    must all equal the oracle's."""
+    _run(emu_lib, ["tick"] + list(case), env={"EMU_TICK_VIEW": "1"})
+
+
+def test_whole_step_reports_an_absent_peer_as_an_error(emu_lib):
+    out = _run(emu_lib, ["tick", 3, 4, 30_000, 3], env={"EMU_ABSENT_RANK": "1", "AMSWEEP_PUSH_TIMEOUT_MS": "300",
+                                                         "EMU_TICK_VIEW": "1"}, timeout=120)
+    assert "watchdog" in out
+
+
 @pytest.mark.parametrize("ctas", [1, 3, 40])
 def test_any_push_grid_size(emu_lib, ctas):
     _run(emu_lib, ["tick", 3, 4, 50_000, 3, 3], env={"AMSWEEP_PUSH_CTAS": str(ctas)})

@@ -370,7 +370,8 @@ uint64_t amgen_select_submitted_view(const uint32_t* idx_local, const uint8_t* a
 /* The host-closed loop of bench.py's e2e measurement, as the cgo shim would run it: compiled code
  * calling the C-ABI through function pointers (the harness does not link libamsweep).  Per step:
  * tick at the next second (am_sweep_tick_view: the GPU writes the list into the library's pinned
- * host buffer); then the consumer side — `workers` threads, the controller's reconcile workers
+ * host buffer; on a multi-GPU shard am_gather_tick_view with `tick_handle` = the exchange: sweep,
+ * NVLink exchange, this rank's own part of the global list); then the consumer side — `workers` threads, the controller's reconcile workers
  * (hcc.go:170-188, MaxConcurrentReconciles) — walks the list in pieces (hcc.go:269-288 stand-in),
  * each thread posting every submitted check of its piece as Succeeded (am_sweep_post_result, host
  * memory -> device) before the next tick.  Workers are persistent and spin between ticks.
@@ -477,7 +478,7 @@ static void* e2e_worker(void* arg) {
   }
 }
 
-int amgen_e2e_closed_loop(am_post_fn post, am_tick_view_fn tick, void* handle, int64_t T_first, uint32_t mode,
+int amgen_e2e_closed_loop(am_post_fn post, am_tick_view_fn tick, void* handle, void* tick_handle, int64_t T_first, uint32_t mode,
                           uint64_t warm, uint64_t steps, uint64_t* slots /* capacity entries */, uint64_t capacity,
                           const uint8_t* ok_phase /* capacity x AM_PHASE_SUCCEEDED */, int workers, double* seconds,
                           double* split /* [4] */, uint64_t* h2d_bytes, uint64_t* d2h_bytes, uint64_t* last_emitted,
@@ -536,7 +537,7 @@ int amgen_e2e_closed_loop(am_post_fn post, am_tick_view_fn tick, void* handle, i
       for (int w = 0; w < workers; w++) P.post_s[w] = P.walk_s[w] = 0;
     }
     const double b = mono_s();
-    rc = tick(handle, T_first + (int64_t)k, mode, &v, &st);
+    rc = tick(tick_handle ? tick_handle : handle, T_first + (int64_t)k, mode, &v, &st);
     if (rc) break;
     const double c = mono_s();
     P.idx = v.idx_local; P.act = v.action; P.n = v.n;

@@ -60,7 +60,7 @@ def load() -> C.CDLL:
         lib.amgen_select_submitted.restype = C.c_uint64
         lib.amgen_select_submitted.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
         lib.amgen_e2e_closed_loop.restype = C.c_int
-        lib.amgen_e2e_closed_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_uint64,
+        lib.amgen_e2e_closed_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint32, C.c_uint64,
                                               C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int,
                                               C.POINTER(C.c_double), C.POINTER(C.c_double * 4), C.POINTER(C.c_uint64),
                                               C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -122,7 +122,7 @@ def select_submitted_view(idx_local: np.ndarray, act: np.ndarray, out: np.ndarra
 
 
 def e2e_closed_loop(product_lib, sweep_handle, T_first: int, mode: int, warm: int, steps: int, capacity: int,
-                    workers: int = 1) -> dict:
+                    workers: int = 1, gather_handle=None) -> dict:
     """bench.py's e2e loop in compiled code (amgen_e2e_closed_loop): am_sweep_tick_view, then `workers`
     consumer threads walking the list in pieces and posting through am_sweep_post_result of
     `product_lib` (a ctypes CDLL of the C-ABI) on `sweep_handle`."""
@@ -130,8 +130,10 @@ def e2e_closed_loop(product_lib, sweep_handle, T_first: int, mode: int, warm: in
     ok = np.full(capacity, 1, dtype=np.uint8)  # AM_PHASE_SUCCEEDED
     sec, split = C.c_double(), (C.c_double * 4)()
     h2d, d2h, ne, ns = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    # one GPU: am_sweep_tick_view on the sweep; a multi-GPU shard: am_gather_tick_view on the (bound) exchange
+    tick_fn = product_lib.am_gather_tick_view if gather_handle is not None else product_lib.am_sweep_tick_view
     rc = load().amgen_e2e_closed_loop(C.cast(product_lib.am_sweep_post_result, C.c_void_p),
-                                      C.cast(product_lib.am_sweep_tick_view, C.c_void_p), sweep_handle, T_first, mode,
+                                      C.cast(tick_fn, C.c_void_p), sweep_handle, gather_handle, T_first, mode,
                                       warm, steps, slots.ctypes.data, capacity, ok.ctypes.data, workers, C.byref(sec),
                                       C.byref(split), C.byref(h2d), C.byref(d2h), C.byref(ne), C.byref(ns))
     if rc <= 0:
