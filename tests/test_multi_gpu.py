@@ -62,19 +62,29 @@ def _worker(rank, world, port, n_total, ticks, config, overlap, q):
             torch.cuda.set_stream(sa)
             for k in range(ticks):
                 T = T0 + 60 * k - (k % 2)
-                s.tick_shard(T, 0, sa.cuda_stream)
-                pg.exchange(s, d_st.data_ptr(), sb.cuda_stream)  # the library orders sb after sa
-                sb.synchronize()
+                own = None
+                if overlap and k % 2 == 1:
+                    # the whole step in one call: tick_shard + exchange + this rank's own part of the list as local
+                    # slots in pinned host memory (am_gather_bind / am_gather_tick_view)
+                    if k == 1:
+                        pg.bind(s, sa.cuda_stream, sb.cuda_stream)
+                    vi, va, vst = pg.tick_view(T)
+                    own = (vi.astype(np.uint64) + np.uint64(first), va.astype(np.uint32))
+                    st = [vst[f] for f in am.abi.STAT_FIELDS]
+                else:
+                    s.tick_shard(T, 0, sa.cuda_stream)
+                    pg.exchange(s, d_st.data_ptr(), sb.cuda_stream)  # the library orders sb after sa
+                    sb.synchronize()
+                    st = [int(v) & ((1 << 64) - 1) for v in d_st.cpu().tolist()]
                 xi, xa, xc = pg.result()
                 xi, xa = xi.cpu().numpy().copy(), xa.cpu().numpy().copy()
-                st = [int(v) & ((1 << 64) - 1) for v in d_st.cpu().tolist()]
                 s2.tick_device(T, 0, d_idx.data_ptr(), d_act.data_ptr(), cnt, d_cnt.data_ptr(), 0, sa.cuda_stream)
                 pg2.push(d_idx.data_ptr(), d_act.data_ptr(), d_cnt.data_ptr(), first, sa.cuda_stream)
                 sa.synchronize()
                 pi, pa, pc = pg2.result()
                 ni, na, nc = gather.allgather_due(d_idx, d_act, d_cnt, first)
                 out.append((xi, xa, xc, st, pi.cpu().numpy().copy(), pa.cpu().numpy().copy(), pc,
-                            ni.cpu().numpy().copy(), na.cpu().numpy().copy(), nc))
+                            ni.cpu().numpy().copy(), na.cpu().numpy().copy(), nc, own))
             final = s.read_range(0, cnt)
             dist.barrier()
             pg.close()
@@ -121,8 +131,12 @@ def test_sharded_sweep_and_all_gathers_equal_unsharded_oracle(world, config, ove
         T = T0 + 60 * k - (k % 2)
         wi, wa, _ = oracle_c.sweep(whole, T)
         for rank in range(world):
-            xi, xa, xc, st, pi, pa, pc, ni, na, nc = results[rank][k]
+            xi, xa, xc, st, pi, pa, pc, ni, na, nc, own = results[rank][k]
             first, sc = shard_cols[rank]
+            if own is not None:
+                mine = (wi >= first) & (wi < first + len(sc["flags"]))
+                np.testing.assert_array_equal(own[0], wi[mine], err_msg=f"tick_view rank {rank} tick {k}")
+                np.testing.assert_array_equal(own[1], wa[mine])
             _, _, ws = oracle_c.sweep(sc, T, shard_base=first)
             assert dict(zip(am.abi.STAT_FIELDS, st)) == ws, f"shard stats rank {rank} tick {k}"
             assert sum(xc) == len(wi) and xc == pc == nc
