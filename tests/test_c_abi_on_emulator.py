@@ -8,7 +8,8 @@ and without those guards.
 
 So `-m "not gpu"` now exercises the host runtime and the kernels' logic end to end; the `-m gpu`
 run on a B200 remains the parity test proper (memory model, real launches, real streams).
-Skipped here: only the torch.cuda-based tick_device test (the 10 M-record property test is included).
+Skipped here: the torch.cuda-based tick_device test and the two 10 M-record compares (a minute of emulation for
+no logic the smaller sizes do not reach; they run on the GPU).
 """
 import os
 import subprocess
@@ -43,13 +44,13 @@ def test_gpu_parity_suite_through_the_c_abi_on_the_emulated_library(emu_lib):
     env = dict(os.environ, AMSWEEP_LIB=emu_lib)
     out = subprocess.run([sys.executable, "-m", "pytest", "tests/test_sweep_gpu.py", "tests/test_golden_fixtures.py",
                           "tests/test_timezones.py",
-                          "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", "not tick_device"],
+                          "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", "not tick_device and not 10m"],
                          cwd=ROOT, env=env, capture_output=True, text=True, timeout=1800)
     tail = out.stdout[-3000:] + out.stderr[-2000:]
     assert out.returncode == 0, tail
     last = out.stdout.strip().splitlines()[-1]
     assert " passed" in last and "failed" not in last and "error" not in last, tail
-    assert int(last.split(" passed")[0].split()[-1]) >= 61, tail
+    assert int(last.split(" passed")[0].split()[-1]) >= 68, tail
 
 
 def test_reconciler_cpp_mirror_on_the_emulated_library(emu_lib):
