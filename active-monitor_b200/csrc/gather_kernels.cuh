@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) gather_push_kernel(const PushParams p) {
   //    one 16 B index store + one 4 B action store per peer (NVLink packets of
   //    512 B / 128 B per warp) instead of eight scalar stores; the ragged first and
   //    last quads fall back to scalar stores.  Source reads are local and unaligned
-  //    (scalar, L2-resident: the list was just written by compact_kernel).
+  //    (scalar, L2-resident: the list was just written by expand_kernel).
   //    Four quads are in flight per thread so a small grid saturates the link
   //    while leaving the SMs to the next tick's sweep.
   const int buf = p.epoch & 1;

@@ -65,7 +65,7 @@ template <typename T>
 __device__ __forceinline__ void st_stream(T* p, T v) { __stcs(p, v); }
 
 // Segment entries are written once by the sweep and read once, a few tens of
-// microseconds later, by compact_kernel: keep them L2-resident (evict_last)
+// microseconds later, by expand_kernel: keep them L2-resident (evict_last)
 // while 560 MB of evict_first column data streams past them.
 #ifndef AMSWEEP_EMULATE
 __device__ __forceinline__ uint64_t l2_evict_last_policy() {

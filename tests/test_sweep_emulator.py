@@ -1,12 +1,12 @@
-"""The per-tick kernels (csrc/sweep_kernels.cuh) on the CPU emulation of the CUDA execution
-model (tests/emu): the SAME kernel source the GPU runs — sweep_tick_kernel in its four
-variants, compact_kernel, publish_kernel, the staged-event kernels, next_fire_kernel —
-against the oracle, bit-exact: emitted lists, action bytes, statistics, every mutated column.
+"""The whole product library (csrc/sweep.cu host runtime + csrc/sweep_kernels.cuh + csrc/sweep_block.cuh) on the
+CPU emulation of the CUDA execution model (tests/emu), in-process through `EmuSweep` = `am.Sweep` bound to the
+emulated build: the SAME kernel and host source the GPU runs — sweep_tick_kernel in its four variants,
+scan_groups / expand / publish, the staged-op kernels, sweep_block_kernel, next_fire / next_due — against the
+oracle, bit-exact: emitted lists, action bytes, statistics, every mutated column.
 
-This is the CPU-side twin of tests/test_sweep_gpu.py at oracle-friendly sizes.  It checks the
-kernels' logic (decisions, ordered compaction, statistics, the parity hand-off between
-ticks); it says nothing about the GPU memory model or performance, and the launch sequence
-is restated in tests/emu/emu_sweep.cpp (csrc/sweep.cu's host code is exercised on the GPU)."""
+This is the CPU-side twin of tests/test_sweep_gpu.py at oracle-friendly sizes.  It checks logic (decisions, the
+ordered list rebuild, statistics, staging and drain, the parity hand-off between ticks); it says nothing about
+the GPU memory model or performance."""
 import ctypes as C
 import os
 import sys
